@@ -1,0 +1,199 @@
+/*
+ * bbduk_b200.h -- C ABI of libbbduk_b200.so: BBDuk's per-read k-mer match-and-trim hot path on B200.
+ *
+ * This is the drop-in boundary. Everything here is plain C (pointers, sizes, POD structs); no C++
+ * or torch types cross it. A JNI shim (jni/BBDukCuda.c) or any other FFI binds exactly these
+ * symbols. Each entry point names the reference interface it replaces (paths relative to the
+ * BBTools tree, "jgi/" = current/jgi, "bbduk/" = current/bbduk).
+ *
+ * Thread safety: one handle owns one device table. bbduk_b200_process* may be called from several
+ * host threads on the same handle concurrently (the reference calls its index from THREADS
+ * ProcessThreads, bbduk/BBDukS.java:317-319); each call takes a private stream + staging slot.
+ * create/add_ref/finalize/destroy are single-threaded per handle.
+ *
+ * Errors: every function returns 0 on success, non-zero on failure; bbduk_b200_last_error() gives
+ * the message. Nothing throws, nothing falls back to a CPU path.
+ */
+#ifndef BBDUK_B200_H
+#define BBDUK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BBDUK_B200_ABI_VERSION 1
+
+/* generation: which reference main class' derived-constant quirks to follow */
+#define BBDUK_GEN_JGI 0   /* jgi.BBDuk   (bbdukOld.sh): unset mink -> 6   (jgi/BBDuk.java:804) */
+#define BBDUK_GEN_S 1     /* bbduk.BBDukS (bbduk.sh)   : unset mink stays -1 (bbduk/BBDukParser.java:245) */
+
+/*
+ * User-level parameters with the meaning of the bbduk.sh flags of the same name. The derived
+ * constants (mask, shift2, middleMask, minlen2, forbidNs, useShortKmers, kbig ...) are computed by
+ * the library exactly as jgi/BBDuk.java:583-585, :672-877 does. Fill with bbduk_b200_cfg_default()
+ * first, then override.
+ */
+typedef struct bbduk_cfg {
+    int32_t struct_size;          /* = sizeof(bbduk_cfg); ABI guard */
+    int32_t generation;           /* BBDUK_GEN_* */
+    int32_t k;                    /* k=        ; <=0 means unset -> 27 (jgi/BBDuk.java:708); >31 -> kbig */
+    int32_t mink;                 /* mink=     ; -1 unset */
+    int32_t use_short_kmers;      /* usk=t     ; (jgi/BBDuk.java:255) */
+    int32_t hdist;                /* hdist=    */
+    int32_t hdist2;               /* hdist2=   ; -1 -> hdist  (jgi/BBDuk.java:583) */
+    int32_t edist;                /* edist=    */
+    int32_t edist2;               /* edist2=   ; -1 -> edist */
+    int32_t qhdist;               /* qhdist=   */
+    int32_t qhdist2;              /* qhdist2=  ; -1 -> qhdist */
+    int32_t rcomp;                /* rcomp=    ; default 1 */
+    int32_t mask_middle;          /* mm=t/f    ; default 1 */
+    int32_t mid_mask_len;         /* mm=<n>    ; 0 = automatic 2-(k&1) */
+    int32_t forbid_ns;            /* fn=       */
+    int32_t ktrim_left;           /* ktrim=l   */
+    int32_t ktrim_right;          /* ktrim=r   ; both = ktrim=rl / ktrimtips */
+    int32_t ktrim_n;              /* ktrim=n / kmask= */
+    int32_t ksplit;               /* ksplit=t  */
+    int32_t ktrim_exclusive;      /* ktrimexclusive= */
+    int32_t trim_pad;             /* tp=       */
+    int32_t restrict_left;        /* restrictleft=  */
+    int32_t restrict_right;       /* restrictright= */
+    int32_t skip_r1;              /* skipr1=   */
+    int32_t skip_r2;              /* skipr2=   */
+    int32_t qskip;                /* qskip=    ; default 1 */
+    int32_t speed;                /* speed=    ; 0..16 */
+    int32_t min_skip;             /* minskip=  ; default 1 */
+    int32_t max_skip;             /* maxskip=  ; default 1 */
+    int32_t max_bad_kmers;        /* mbk= (mkh-1) ; default 0 */
+    float   min_kmer_fraction;    /* mkf=      */
+    float   min_covered_fraction; /* mcf=      */
+    int32_t find_best_match;      /* fbm=      */
+    int32_t kmask_fully_covered;  /* mfc=      */
+    int32_t kmask_lowercase;      /* kmask=lc  */
+    int32_t trim_symbol;          /* kmask=<c> ; default 'N' */
+    int32_t min_read_length;      /* minlen=   ; default 10 */
+    float   min_len_fraction;     /* mlf=      ; default 0 */
+    int32_t require_both_bad;     /* rieb=f    ; default 0 */
+    int32_t trim_pairs_evenly;    /* tpe=      */
+    int32_t trim_failures_to_1bp; /* tossbrokenreads-style "trimfailuresto1bp" (jgi/BBDuk.java:3260-3266) */
+    int32_t device;               /* CUDA device ordinal; -1 = current device */
+    int32_t table_load_pct;       /* device table load factor in percent (layout only, no effect on results); 0 -> 50 */
+    int32_t reserved[7];
+} bbduk_cfg;
+
+/* per-read flag bits written to bbduk_out.flags */
+#define BBDUK_F_DISCARDED 0x01 /* read.discarded() after the k-mer block (jgi/BBDuk.java:2740-2777, :2848-2856) */
+#define BBDUK_F_REMOVED   0x02 /* pair-level 'remove' (shouldRemove, jgi/BBDuk.java:2794, :2860, :3286-3289) */
+#define BBDUK_F_KTRIMMED  0x04 /* the read's own ktrim/kmask call returned x>0 */
+#define BBDUK_F_TPE       0x08 /* shortened by trimpairsevenly (jgi/BBDuk.java:2801-2811) */
+#define BBDUK_F_SPLIT     0x10 /* ksplit produced a second segment [count, len-1) */
+
+/*
+ * Per-read outputs, struct of arrays, each n_reads long; any pointer may be NULL (not wanted).
+ * Reads of a pair are adjacent (2i, 2i+1). Host pointers for bbduk_b200_process, device pointers
+ * for bbduk_b200_process_device.
+ *   id0     scaffold id credited for this read (the id whose scaffoldReadCounts is incremented,
+ *           e.g. jgi/BBDuk.java:3984-3992, :3439-3445), -1 if none. ktrim=rl: the right-tip credit.
+ *   id0b    ktrim=rl only: the left-tip credit, else -1.
+ *   lo, hi  the read keeps original bases [lo, hi) after the k-mer block (ktrim + tpe + ksplit).
+ *   flags   BBDUK_F_*.
+ *   count   the scan's return value: ktrim/ktrimTips bases trimmed; kmask BitSet cardinality;
+ *           kfilter hit count as returned by countSetKmers / countCoveredBases / countSetKmersBig,
+ *           or the id returned by findBestMatch; ksplit with BBDUK_F_SPLIT: start s of the new mate,
+ *           which is original bases [s, len-1) -- the reference's subRead(rightmost+1, len-1) is
+ *           end-exclusive and drops the last base (jgi/BBDuk.java:4370, stream/Read.java:3729-3731).
+ *   maskbits  kmask only: bit (i&31) of word mask_off[r]+(i>>5) set <=> base i of read r is masked
+ *           (jgi/BBDuk.java:4187-4196). mask_off has n_reads+1 entries, in words.
+ */
+typedef struct bbduk_out {
+    int32_t  *id0;
+    int32_t  *id0b;
+    int32_t  *lo;
+    int32_t  *hi;
+    uint8_t  *flags;
+    int32_t  *count;
+    uint32_t *maskbits;
+    const int64_t *mask_off;
+} bbduk_out;
+
+/* Aggregate counters of one process call; same meaning as the reference's per-thread sums
+ * (jgi/BBDuk.java:2812-2813, :2863-2868; summed at :2085-2131). */
+typedef struct bbduk_stats {
+    int64_t reads_in, bases_in;
+    int64_t reads_ktrimmed, bases_ktrimmed;
+    int64_t reads_kfiltered, bases_kfiltered;
+    int64_t reads_out, bases_out;          /* pairs not removed: reads and kept bases */
+} bbduk_stats;
+
+/* Device table blobs, for replication to other GPUs (one NCCL broadcast each at build time). */
+typedef struct bbduk_table_desc {
+    int64_t n_slots;        /* key slots (power of two) */
+    int64_t n_filter_words; /* 32-bit words of the on-chip pre-filter image */
+    int64_t stored_kmers;   /* distinct keys == the reference's "Added N kmers" (jgi/BBDuk.java:1973) */
+    int32_t n_scaffolds;    /* ids are 1..n_scaffolds */
+    int32_t reserved;
+    void   *d_keys;         /* uint64[n_slots], device */
+    void   *d_vals;         /* int32[n_slots], device */
+    void   *d_filter;       /* uint32[n_filter_words], device */
+    int64_t scalars[8];     /* hash seeds / geometry the kernels need; opaque, broadcast as-is */
+} bbduk_table_desc;
+
+typedef struct bbduk_handle bbduk_handle;
+
+/* Library/ABI version (BBDUK_B200_ABI_VERSION). */
+int bbduk_b200_version(void);
+
+/* Defaults of jgi.BBDuk's constructor (jgi/BBDuk.java:107-147, :4953-4977). */
+void bbduk_b200_cfg_default(bbduk_cfg *cfg);
+
+/* Replaces: BBDuk constructor's constant derivation + index allocation
+ * (jgi/BBDuk.java:583-877, :1017-1021; bbduk/BBDukLoader.java:35-76). */
+int bbduk_b200_create(const bbduk_cfg *cfg, bbduk_handle **out);
+
+/* Replaces: spawnLoadThreads' scaffold numbering + LoadThread.addToMap scan for a block of
+ * reference sequences (jgi/BBDuk.java:1849-1863, :2210-2288). bases = concatenated ASCII,
+ * offsets[n_seqs+1]. Scaffold ids continue from the previous call (first id 1). Host pointers. */
+int bbduk_b200_add_ref(bbduk_handle *h, const uint8_t *bases, const int64_t *offsets, int32_t n_seqs);
+
+/* Replaces: the join of the LoadThreads ("Added N kmers", jgi/BBDuk.java:1945-1976): expands the
+ * hdist/edist neighbourhoods and short-k-mer tails on the device and fills the hash array
+ * (kmer.AbstractKmerTable.setIfNotPresent semantics: key -> smallest scaffold id). */
+int bbduk_b200_finalize(bbduk_handle *h, int64_t *stored_kmers);
+
+/* Replaces: the k-mer block of ProcessThread's per-pair loop for one batch of reads
+ * (jgi/BBDuk.java:2727-2873 == bbduk/BBDukProcessorS.java:947-1093), including ktrim / ktrimTips /
+ * kmask / ksplit / countSetKmers / countCoveredBases / findBestMatch / countSetKmersBig and
+ * TrimRead.trimToPosition's coordinate rule. HOST buffers; copies to/from the device inside.
+ * paired!=0: reads 2i and 2i+1 are mates (pairnum 0 / 1). stats may be NULL. */
+int bbduk_b200_process(bbduk_handle *h, const uint8_t *bases, const int64_t *offsets, int64_t n_reads,
+                       int32_t paired, const bbduk_out *out, bbduk_stats *stats);
+
+/* Same, on DEVICE buffers (bases, 32-bit offsets[n_reads+1], outputs), asynchronous on `stream`
+ * (a cudaStream_t, NULL = default stream). total bases < 4 GiB per call. d_stats: device
+ * bbduk_stats to accumulate into, may be NULL. */
+int bbduk_b200_process_device(bbduk_handle *h, const uint8_t *d_bases, const uint32_t *d_offsets,
+                              int64_t n_reads, int32_t paired, const bbduk_out *d_out,
+                              bbduk_stats *d_stats, void *stream);
+
+/* Per-scaffold hit accounting accumulated on the device by process calls, index 0..n_scaffolds
+ * (replaces scaffoldReadCounts/scaffoldBaseCounts, jgi/BBDuk.java:1968-1969, :3984-3992). */
+int bbduk_b200_scaffold_counts(bbduk_handle *h, int64_t *read_counts, int64_t *base_counts, int32_t n);
+
+/* Table replication across GPUs: rank 0 describes its table; other ranks allocate the same
+ * geometry with _table_alloc, receive the three blobs (NCCL broadcast done by the caller on the
+ * returned device pointers), then _table_commit. */
+int bbduk_b200_table_describe(bbduk_handle *h, bbduk_table_desc *desc);
+int bbduk_b200_table_alloc(bbduk_handle *h, bbduk_table_desc *desc /* in: geometry+scalars; out: pointers */);
+int bbduk_b200_table_commit(bbduk_handle *h);
+
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+int64_t bbduk_b200_launch_count(bbduk_handle *h);
+
+const char *bbduk_b200_last_error(bbduk_handle *h);
+void bbduk_b200_destroy(bbduk_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BBDUK_B200_H */
