@@ -1,0 +1,54 @@
+"""ctypes loader of libbbduk_b200.so. No fallback: a missing library is an ImportError with build advice."""
+import ctypes as C
+import os
+
+from ._abi import ABI_VERSION, BBDukCfg, BBDukOut, BBDukStats, BBDukTableDesc
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbbduk_b200.so")
+
+# every symbol include/bbduk_b200.h declares: (name, restype, argtypes)
+SYMBOLS = [
+    ("bbduk_b200_version", C.c_int, []),
+    ("bbduk_b200_cfg_default", None, [C.POINTER(BBDukCfg)]),
+    ("bbduk_b200_describe_cfg", C.c_int, [C.POINTER(BBDukCfg), C.c_void_p]),
+    ("bbduk_b200_create", C.c_int, [C.POINTER(BBDukCfg), C.POINTER(C.c_void_p)]),
+    ("bbduk_b200_add_ref", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    ("bbduk_b200_finalize", C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    ("bbduk_b200_process", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                     C.POINTER(BBDukOut), C.POINTER(BBDukStats)]),
+    ("bbduk_b200_process_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                            C.POINTER(BBDukOut), C.c_void_p, C.c_void_p]),
+    ("bbduk_b200_scaffold_counts", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    ("bbduk_b200_table_describe", C.c_int, [C.c_void_p, C.POINTER(BBDukTableDesc)]),
+    ("bbduk_b200_table_alloc", C.c_int, [C.c_void_p, C.POINTER(BBDukTableDesc)]),
+    ("bbduk_b200_table_commit", C.c_int, [C.c_void_p]),
+    ("bbduk_b200_launch_count", C.c_int64, [C.c_void_p]),
+    ("bbduk_b200_last_error", C.c_char_p, [C.c_void_p]),
+    ("bbduk_b200_destroy", None, [C.c_void_p]),
+    ("bbduk_b200_synth_pairs", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_uint64,
+                                         C.c_int32, C.c_int32, C.c_void_p]),
+]
+
+_LIB = None
+
+
+def load():
+    """Load the CUDA library; raises ImportError (never falls back) if it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C bbtools_b200/csrc`). bbtools_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, res, args in SYMBOLS:
+        fn = getattr(lib, name)  # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    v = lib.bbduk_b200_version()
+    if v != ABI_VERSION:
+        raise ImportError(f"libbbduk_b200.so ABI version {v} != binding {ABI_VERSION}")
+    _LIB = lib
+    return lib

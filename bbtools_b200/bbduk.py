@@ -1,0 +1,437 @@
+"""Host-side mirror of the reference's BBDuk surface for the k-mer match-and-trim path.
+
+`parse_args` accepts the bbduk.sh `key=value` flags that reach the path (same names, aliases and
+defaults as jgi/BBDuk.java:186-560 and parse/Parser.java:487-506) and produces the POD config of the
+C ABI. `BBDukIndexGPU` is the fourth index implementation SURVEY.md 8b describes (next to
+bbduk/BBDukIndexMod|Mask|Mask2): it owns a device table and answers whole batches.
+`BBDuk` wires them into the reads-in / reads-out tool for FASTQ files.
+
+Everything numeric happens in libbbduk_b200.so; this file is plumbing (no CPU fallback exists).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._abi import (BBDukOut, BBDukStats, BBDukTableDesc, F_DISCARDED, F_REMOVED, F_SPLIT, GEN_JGI, GEN_S, Outputs,
+                   default_cfg)
+from .fasta import pack, read_fasta, read_fastq
+
+
+def _parse_boolean(s):
+    """parse/Parse.java:187-195"""
+    if s is None or len(s) < 1:
+        return True
+    if len(s) == 1:
+        return s.lower() in ("t", "1")
+    if s.lower() in ("null", "none"):
+        return False
+    return s.lower() == "true"
+
+
+def parse_args(args, generation=GEN_JGI):
+    """bbduk.sh-style argv -> (bbduk_cfg, io dict). Unknown keys raise, like the reference
+    ("Unknown parameter", jgi/BBDuk.java:561)."""
+    cfg = default_cfg()
+    cfg.generation = generation
+    io = {"in1": None, "in2": None, "out1": None, "out2": None, "outm1": None, "outm2": None, "ref": [],
+          "literal": [], "stats": None, "interleaved": None, "ordered": generation == GEN_S, "ottm": False}
+    for arg in args:
+        sp = arg.split("=")
+        a = sp[0].lower()
+        b = sp[1] if len(sp) > 1 else None
+        if a in ("in", "in1"):
+            io["in1"] = b
+        elif a == "in2":
+            io["in2"] = b
+        elif a in ("out", "out1", "outu", "outu1", "outnonmatch", "outnonmatch1"):
+            io["out1"] = b
+        elif a in ("out2", "outu2", "outnonmatch2"):
+            io["out2"] = b
+        elif a in ("outb", "outm", "outb1", "outm1", "outbad", "outbad1", "outmatch", "outmatch1"):
+            io["outm1"] = b
+        elif a in ("outb2", "outm2", "outbad2", "outmatch2"):
+            io["outm2"] = b
+        elif a in ("stats", "scafstats"):
+            io["stats"] = b
+        elif a in ("ref", "adapters"):
+            io["ref"] = [] if b is None else b.split(",")
+        elif a == "literal":
+            io["literal"] = [] if b is None else b.split(",")
+        elif a in ("interleaved", "int"):
+            io["interleaved"] = _parse_boolean(b)
+        elif a in ("ordered", "ord"):
+            io["ordered"] = _parse_boolean(b)
+        elif a in ("ottm", "outputtrimmedtomatch"):
+            io["ottm"] = _parse_boolean(b)
+        elif a in ("t", "threads", "overwrite", "ow", "showspeed", "ss", "prealloc", "preallocate"):
+            pass  # host runtime knobs with no effect on results
+        elif a == "skipr1":
+            cfg.skip_r1 = _parse_boolean(b)
+        elif a == "skipr2":
+            cfg.skip_r2 = _parse_boolean(b)
+        elif a == "k":
+            cfg.k = int(b)
+        elif a in ("mink", "kmin"):
+            cfg.mink = int(b)
+        elif a in ("useshortkmers", "shortkmers", "usk"):
+            cfg.use_short_kmers = _parse_boolean(b)
+        elif a in ("trimextra", "trimpad", "tp"):
+            cfg.trim_pad = int(b)
+        elif a in ("hdist", "hammingdistance"):
+            cfg.hdist = int(b)
+        elif a in ("qhdist", "queryhammingdistance"):
+            cfg.qhdist = int(b)
+        elif a in ("edits", "edist", "editdistance"):
+            cfg.edist = int(b)
+        elif a in ("hdist2", "hammingdistance2"):
+            cfg.hdist2 = int(b)
+        elif a in ("qhdist2", "queryhammingdistance2"):
+            cfg.qhdist2 = int(b)
+        elif a in ("edits2", "edist2", "editdistance2"):
+            cfg.edist2 = int(b)
+        elif a in ("maxskip", "maxrskip", "mxs"):
+            cfg.max_skip = int(b)
+        elif a in ("minskip", "minrskip", "mns"):
+            cfg.min_skip = int(b)
+        elif a in ("skip", "refskip", "rskip"):
+            cfg.min_skip = cfg.max_skip = int(b)
+        elif a == "qskip":
+            cfg.qskip = int(b)
+        elif a == "speed":
+            cfg.speed = int(b)
+        elif a in ("maxbadkmers", "mbk"):
+            cfg.max_bad_kmers = int(b)
+        elif a in ("minhits", "minkmerhits", "mkh"):
+            cfg.max_bad_kmers = int(b) - 1
+        elif a in ("minkmerfraction", "minfraction", "mkf"):
+            cfg.min_kmer_fraction = float(b)
+        elif a in ("mincoveredfraction", "mincovfraction", "mcf"):
+            cfg.min_covered_fraction = float(b)
+        elif a in ("mm", "maskmiddle"):
+            if b is None or b[:1].isalpha():
+                cfg.mask_middle = _parse_boolean(b)
+            else:
+                cfg.mid_mask_len = int(b)
+                cfg.mask_middle = int(b) > 0
+        elif a == "rcomp":
+            cfg.rcomp = _parse_boolean(b)
+        elif a in ("forbidns", "forbidn", "fn"):
+            cfg.forbid_ns = _parse_boolean(b)
+        elif a in ("findbestmatch", "fbm"):
+            cfg.find_best_match = _parse_boolean(b)
+        elif a == "kfilter":
+            if _parse_boolean(b):
+                cfg.ktrim_left = cfg.ktrim_right = cfg.ktrim_n = cfg.ksplit = 0
+        elif a == "ksplit":
+            if _parse_boolean(b):
+                cfg.ksplit = 1
+                cfg.ktrim_left = cfg.ktrim_right = cfg.ktrim_n = 0
+            else:
+                cfg.ksplit = 0
+        elif a == "ktrim":
+            v = (b or "").lower()
+            if v in ("rl", "lr", "tips"):
+                cfg.ktrim_left = cfg.ktrim_right = 1
+                cfg.ktrim_n = cfg.ksplit = 0
+            elif v in ("left", "l"):
+                cfg.ktrim_left, cfg.ktrim_right, cfg.ktrim_n, cfg.ksplit = 1, 0, 0, 0
+            elif v in ("right", "r"):
+                cfg.ktrim_left, cfg.ktrim_right, cfg.ktrim_n, cfg.ksplit = 0, 1, 0, 0
+            elif v == "n":
+                cfg.ktrim_left, cfg.ktrim_right, cfg.ktrim_n, cfg.ksplit = 0, 0, 1, 0
+            elif len(v) == 1 and v not in ("t", "f"):
+                cfg.ktrim_left, cfg.ktrim_right, cfg.ktrim_n, cfg.ksplit = 0, 0, 1, 0
+                cfg.trim_symbol = ord(b[0])
+            else:
+                if v not in ("f", "false"):
+                    raise ValueError("Invalid setting for ktrim - values must be f (false), l (left), r (right), "
+                                     "rl (tips), or n.")
+                cfg.ktrim_left = cfg.ktrim_right = 0
+        elif a in ("trimtips", "ktrimtips"):
+            if b:
+                cfg.ktrim_left = cfg.ktrim_right = 1
+                cfg.ktrim_n = cfg.ksplit = 0
+                cfg.restrict_left = cfg.restrict_right = int(b)
+        elif a in ("kmask", "mask"):
+            if b is not None and b.lower() in ("lc", "lowercase"):
+                cfg.kmask_lowercase = 1
+                cfg.ktrim_left, cfg.ktrim_right, cfg.ktrim_n, cfg.ksplit = 0, 0, 1, 0
+            else:
+                if _parse_boolean(b):
+                    b = "N"
+                if b is not None and len(b) == 1:
+                    cfg.ktrim_left, cfg.ktrim_right, cfg.ktrim_n = 0, 0, 1
+                    cfg.trim_symbol = ord(b)
+                else:
+                    cfg.ktrim_n = _parse_boolean(b)
+        elif a in ("kmaskfullycovered", "maskfullycovered", "mfc"):
+            cfg.kmask_fully_covered = _parse_boolean(b)
+        elif a == "ktrimright":
+            cfg.ktrim_right = _parse_boolean(b)
+            cfg.ktrim_left = cfg.ktrim_n = not cfg.ktrim_right
+        elif a == "ktrimleft":
+            cfg.ktrim_left = _parse_boolean(b)
+            cfg.ktrim_right = cfg.ktrim_n = not cfg.ktrim_left
+        elif a == "ktrimn":
+            cfg.ktrim_n = _parse_boolean(b)
+            cfg.ktrim_left = cfg.ktrim_right = not cfg.ktrim_n
+        elif a == "ktrimexclusive":
+            cfg.ktrim_exclusive = _parse_boolean(b)
+        elif a in ("tpe", "tbe", "trimpairsevenly"):
+            cfg.trim_pairs_evenly = _parse_boolean(b)
+        elif a == "restrictleft":
+            cfg.restrict_left = int(b)
+        elif a == "restrictright":
+            cfg.restrict_right = int(b)
+        elif a in ("ml", "minlen", "minlength"):
+            cfg.min_read_length = int(b)
+        elif a in ("mlf", "minlenfrac", "minlenfraction", "minlengthfraction"):
+            cfg.min_len_fraction = float(b)
+        elif a in ("requirebothbad", "rbb"):
+            cfg.require_both_bad = _parse_boolean(b)
+        elif a in ("removeifeitherbad", "rieb"):
+            cfg.require_both_bad = not _parse_boolean(b)
+        elif a in ("trimfailures", "trimfailuresto1bp"):
+            cfg.trim_failures_to_1bp = _parse_boolean(b)
+        elif a in ("tbo", "trimbyoverlap"):
+            if _parse_boolean(b):
+                raise NotImplementedError("tbo (BBMergeOverlapper) stays on the host in this tier (SURVEY.md 8f row 2)")
+        else:
+            raise ValueError(f"Unknown parameter {arg}")
+    return cfg, io
+
+
+class BBDukIndexGPU:
+    """Device-resident k-mer index + batched per-read k-mer block (the C ABI behind a Python handle)."""
+
+    def __init__(self, cfg):
+        self.lib = _lib.load()
+        self.cfg = cfg
+        h = C.c_void_p()
+        rc = self.lib.bbduk_b200_create(C.byref(cfg), C.byref(h))
+        if rc:
+            raise RuntimeError("bbduk_b200_create: " + self.lib.bbduk_b200_last_error(None).decode())
+        self.h = h
+        self.stored_kmers = None
+        self.n_scaffolds = 0
+
+    def _check(self, rc, what):
+        if rc:
+            raise RuntimeError(f"{what}: " + self.lib.bbduk_b200_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.bbduk_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- table ---------------------------------------------------------------------------------
+    def add_ref(self, bases, offsets):
+        bases = np.ascontiguousarray(bases, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        self._check(self.lib.bbduk_b200_add_ref(self.h, bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1),
+                    "add_ref")
+        self.n_scaffolds += len(offsets) - 1
+
+    def finalize(self):
+        n = C.c_int64(0)
+        self._check(self.lib.bbduk_b200_finalize(self.h, C.byref(n)), "finalize")
+        self.stored_kmers = int(n.value)
+        return self.stored_kmers
+
+    def table_describe(self):
+        d = BBDukTableDesc()
+        self._check(self.lib.bbduk_b200_table_describe(self.h, C.byref(d)), "table_describe")
+        return d
+
+    @staticmethod
+    def _view(ptr, nbytes):
+        """zero-copy uint8 torch view of library-owned device memory (CUDA array interface)"""
+        import torch
+
+        class _Mem:
+            pass
+        m = _Mem()
+        m.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
+                                      "version": 2}
+        return torch.as_tensor(m, device=torch.device("cuda", torch.cuda.current_device()))
+
+    def dump_table(self):
+        """(sorted keys, ids) copied back from the device, for table-parity tests."""
+        d = self.table_describe()
+        k = self._view(d.d_keys, d.n_slots * 8).cpu().numpy().view(np.uint64)
+        v = self._view(d.d_vals, d.n_slots * 4).cpu().numpy().view(np.int32)
+        m = k != np.uint64(0xFFFFFFFFFFFFFFFF)
+        k, v = k[m], v[m]
+        order = np.argsort(k)
+        return k[order], v[order]
+
+    def broadcast_table(self, src=0, group=None):
+        """Replicate rank `src`'s finished table to every rank: one NCCL broadcast per blob (keys, ids,
+        filter image) straight out of / into the library's device arrays over NVLink.
+        Non-source ranks must NOT have called finalize."""
+        import torch
+        import torch.distributed as dist
+        rank = dist.get_rank(group)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        geo = torch.zeros(12, dtype=torch.int64, device=dev)
+        if rank == src:
+            d = self.table_describe()
+            geo[:4] = torch.tensor([d.n_slots, d.n_filter_words, d.stored_kmers, d.n_scaffolds])
+            geo[4:12] = torch.tensor(list(d.scalars))
+        dist.broadcast(geo, src, group=group)
+        g = geo.cpu().tolist()
+        if rank != src:
+            d = BBDukTableDesc()
+            d.n_slots, d.n_filter_words, d.stored_kmers, d.n_scaffolds = g[0], g[1], g[2], int(g[3])
+            for i in range(8):
+                d.scalars[i] = g[4 + i]
+            self._check(self.lib.bbduk_b200_table_alloc(self.h, C.byref(d)), "table_alloc")
+        for ptr, nbytes in ((d.d_keys, g[0] * 8), (d.d_vals, g[0] * 4), (d.d_filter, g[1] * 4)):
+            dist.broadcast(self._view(ptr, nbytes), src, group=group)
+        torch.cuda.synchronize()
+        if rank != src:
+            self._check(self.lib.bbduk_b200_table_commit(self.h), "table_commit")
+            self.stored_kmers = g[2]
+            self.n_scaffolds = int(g[3])
+        return g[2]
+
+    # -- reads ---------------------------------------------------------------------------------
+    def process(self, bases, offsets, paired, want_mask=False, out=None):
+        """HOST buffers in, host struct-of-arrays out (bbduk_b200_process)."""
+        bases = np.ascontiguousarray(bases, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        n = len(offsets) - 1
+        if out is None:
+            out = Outputs(n, np.diff(offsets), want_mask=want_mask)
+        st = BBDukStats()
+        o = out.struct()
+        self._check(self.lib.bbduk_b200_process(self.h, bases.ctypes.data, offsets.ctypes.data, n, int(bool(paired)),
+                                                C.byref(o), C.byref(st)), "process")
+        return out, st
+
+    def process_device(self, d_bases, d_offsets, n_reads, paired, d_out, d_stats=None, stream=None):
+        """DEVICE buffers (torch tensors or raw pointers); d_out: dict name -> tensor/pointer."""
+        def ptr(x):
+            if x is None:
+                return None
+            return x.data_ptr() if hasattr(x, "data_ptr") else int(x)
+        o = BBDukOut()
+        for name in ("id0", "id0b", "lo", "hi", "flags", "count", "maskbits", "mask_off"):
+            setattr(o, name, ptr(d_out.get(name)))
+        self._check(self.lib.bbduk_b200_process_device(self.h, ptr(d_bases), ptr(d_offsets), n_reads,
+                                                       int(bool(paired)), C.byref(o), ptr(d_stats), ptr(stream)),
+                    "process_device")
+
+    def scaffold_counts(self):
+        n = self.n_scaffolds + 1
+        rc_ = np.zeros(n, np.int64)
+        bc = np.zeros(n, np.int64)
+        self._check(self.lib.bbduk_b200_scaffold_counts(self.h, rc_.ctypes.data, bc.ctypes.data, n), "scaffold_counts")
+        return rc_, bc
+
+    @property
+    def launches(self):
+        return int(self.lib.bbduk_b200_launch_count(self.h))
+
+
+class BBDuk:
+    """reads-in / reads-out tool: `BBDuk(["in=r.fq", "ref=adapters.fa", "ktrim=r", "k=23", ...]).process()`.
+
+    FASTQ handling is deliberately simple host code; the k-mer block of every batch runs on the GPU.
+    Output records follow the reference's routing (jgi/BBDuk.java:3190-3254): pairs that are not
+    removed go to out (trimmed), removed pairs go to outm when given."""
+
+    def __init__(self, args, generation=GEN_JGI, resources=None):
+        self.cfg, self.io = parse_args(args, generation)
+        self.resources = resources
+        self.index = BBDukIndexGPU(self.cfg)
+        self.scaffold_names = [""]
+        for ref in self.io["ref"]:
+            path = ref
+            if ref == "adapters" and resources:
+                path = os.path.join(resources, "adapters.fa")
+            names, b, off = read_fasta(path)
+            self.scaffold_names += names
+            self.index.add_ref(b, off)
+        if self.io["literal"]:
+            b, off = pack([s.encode() for s in self.io["literal"]])
+            self.scaffold_names += [str(len(self.scaffold_names) + i) for i in range(len(self.io["literal"]))]
+            self.index.add_ref(b, off)
+        self.stored_kmers = self.index.finalize()
+        self.stats = None
+
+    def process_arrays(self, bases, offsets, paired):
+        want_mask = bool(self.cfg.ktrim_n)
+        return self.index.process(bases, offsets, paired, want_mask=want_mask)
+
+    def process(self):
+        io = self.io
+        n1, s1, q1 = read_fastq(io["in1"])
+        paired = False
+        if io["in2"]:
+            n2, s2, q2 = read_fastq(io["in2"])
+            paired = True
+            names = [x for p in zip(n1, n2) for x in p]
+            seqs = [x for p in zip(s1, s2) for x in p]
+            quals = [x for p in zip(q1, q2) for x in p]
+        else:
+            names, seqs, quals = n1, s1, q1
+            if io["interleaved"]:
+                paired = True
+        bases, offsets = pack(seqs)
+        out, st = self.process_arrays(bases, offsets, paired)
+        self.stats = st
+        sinks = {}
+
+        def sink(path):
+            if path and path not in sinks:
+                sinks[path] = open(path, "wb")
+            return sinks.get(path)
+
+        per = 2 if paired else 1
+        sym = bytes([self.cfg.trim_symbol])
+        for u in range(len(seqs) // per):
+            removed = bool(out.flags[u * per] & F_REMOVED)
+            for q in range(per):
+                i = u * per + q
+                dest = (io["outm2"] if q and io["outm2"] else io["outm1"]) if removed else \
+                       (io["out2"] if q and io["out2"] else io["out1"])
+                f = sink(dest)
+                if f is None:
+                    continue
+                s, ql = bytearray(seqs[i]), bytearray(quals[i])
+                if out.maskbits is not None:
+                    w0 = int(out.mask_off[i])
+                    for j in range(len(s)):
+                        if (int(out.maskbits[w0 + (j >> 5)]) >> (j & 31)) & 1:
+                            if self.cfg.kmask_lowercase:
+                                s[j:j + 1] = bytes(s[j:j + 1]).lower()
+                            else:
+                                s[j:j + 1] = sym
+                                if sym == b"N":
+                                    ql[j] = 33
+                lo, hi = int(out.lo[i]), int(out.hi[i])
+                if removed and not io["ottm"]:
+                    lo, hi = 0, len(s)
+                f.write(b"@" + names[i] + b"\n" + bytes(s[lo:hi]) + b"\n+\n" + bytes(ql[lo:hi]) + b"\n")
+                if out.flags[i] & F_SPLIT:
+                    a = int(out.count[i])
+                    f.write(b"@" + names[i] + b"\n" + bytes(s[a:len(s) - 1]) + b"\n+\n" + bytes(ql[a:len(s) - 1]) + b"\n")
+        for f in sinks.values():
+            f.close()
+        if io["stats"]:
+            rc_, bc = self.index.scaffold_counts()
+            with open(io["stats"], "w") as f:
+                f.write("#Name\tReads\tBases\n")
+                for i in np.argsort(-rc_, kind="stable"):
+                    if i > 0 and rc_[i] > 0:
+                        f.write(f"{self.scaffold_names[i]}\t{rc_[i]}\t{bc[i]}\n")
+        return st

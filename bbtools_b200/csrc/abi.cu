@@ -1,0 +1,541 @@
+// abi.cu -- the extern "C" surface of include/bbduk_b200.h: handle management, table build/replication,
+// host-buffer batching (pinned staging, two streams so copies overlap kernels) and kernel dispatch.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/bbduk_b200.h"
+#include "params.h"
+#include "probe.h"
+#include "table.h"
+
+namespace {
+
+constexpr int N_SLOTS = 3;                    // staging slots (streams) per handle
+constexpr int64_t CHUNK_READS = 4 << 20;      // reads per device batch on the host path
+constexpr int64_t CHUNK_BYTES = 1ll << 30;    // bases per device batch (offsets stay 32-bit)
+
+struct Slot {
+    cudaStream_t st = nullptr;
+    cudaEvent_t done = nullptr;
+    uint8_t *d_bases = nullptr;
+    int64_t *d_off64 = nullptr;
+    uint32_t *d_off32 = nullptr;
+    int32_t *d_id0 = nullptr, *d_id0b = nullptr, *d_lo = nullptr, *d_hi = nullptr, *d_count = nullptr;
+    uint8_t *d_flags = nullptr;
+    uint32_t *d_maskbits = nullptr;
+    int64_t *d_maskoff = nullptr;
+    int32_t *d_handoff = nullptr;
+    unsigned int *d_handoff_n = nullptr;
+    int64_t cap_bases = 0, cap_reads = 0, cap_maskwords = 0;
+    std::mutex mu;
+};
+
+}  // namespace
+
+struct bbduk_handle {
+    bbduk_cfg cfg;
+    BBParams p;
+    int device = 0;
+    int sm_count = 148;
+    bool finalized = false;
+    std::vector<uint8_t> ref;
+    std::vector<int64_t> ref_off{0};
+    DeviceTable table;
+    unsigned long long *d_scaf_reads = nullptr, *d_scaf_bases = nullptr;
+    bbduk_stats *d_stats = nullptr;
+    Slot slots[N_SLOTS];
+    std::atomic<int> next_slot{0};
+    std::atomic<int64_t> launches{0};
+    std::mutex err_mu;
+    std::string err;
+    // per-thread-stream scratch for process_device
+    int32_t *dev_handoff = nullptr;
+    unsigned int *dev_handoff_n = nullptr;
+    int64_t dev_handoff_cap = 0;
+    std::mutex dev_mu;
+};
+
+namespace {
+
+thread_local std::string g_err;  // errors raised before a handle exists
+
+int set_err(bbduk_handle *h, const std::string &m) {
+    if (h) {
+        std::lock_guard<std::mutex> g(h->err_mu);
+        h->err = m;
+    }
+    g_err = m;
+    return 1;
+}
+
+#define CKH(call)                                                                                          \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess) {                                                                           \
+            char b_[512];                                                                                  \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return set_err(h, b_);                                                                         \
+        }                                                                                                  \
+    } while (0)
+
+__global__ void off64_to_32_kernel(const int64_t *__restrict__ off64, int64_t base, uint32_t *__restrict__ off32, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) off32[i] = (uint32_t)(off64[i] - base);
+}
+__global__ void maskoff_rebase_kernel(int64_t *off, int64_t base, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) off[i] -= base;
+}
+__global__ void max_len_kernel(const uint32_t *__restrict__ off, int64_t n_reads, unsigned int *out) {
+    unsigned int m = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_reads; i += (int64_t)gridDim.x * blockDim.x)
+        m = max(m, off[i + 1] - off[i]);
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+void free_slot(Slot &s) {
+    cudaFree(s.d_bases);
+    cudaFree(s.d_off64);
+    cudaFree(s.d_off32);
+    cudaFree(s.d_id0);
+    cudaFree(s.d_id0b);
+    cudaFree(s.d_lo);
+    cudaFree(s.d_hi);
+    cudaFree(s.d_count);
+    cudaFree(s.d_flags);
+    cudaFree(s.d_maskbits);
+    cudaFree(s.d_maskoff);
+    cudaFree(s.d_handoff);
+    cudaFree(s.d_handoff_n);
+    s.d_bases = nullptr;
+    s.d_off64 = nullptr;
+    s.d_off32 = nullptr;
+    s.d_id0 = s.d_id0b = s.d_lo = s.d_hi = s.d_count = nullptr;
+    s.d_flags = nullptr;
+    s.d_maskbits = nullptr;
+    s.d_maskoff = nullptr;
+    s.d_handoff = nullptr;
+    s.d_handoff_n = nullptr;
+    s.cap_bases = s.cap_reads = s.cap_maskwords = 0;
+}
+
+int ensure_slot(bbduk_handle *h, Slot &s, int64_t n_reads, int64_t n_bases, int64_t n_maskwords) {
+    if (!s.st) {
+        CKH(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+        CKH(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    }
+    if (n_bases + 64 > s.cap_bases) {
+        cudaFree(s.d_bases);
+        s.cap_bases = n_bases + n_bases / 8 + 4096;
+        CKH(cudaMalloc(&s.d_bases, (size_t)s.cap_bases));
+    }
+    if (n_reads + 1 > s.cap_reads) {
+        const int64_t c = n_reads + n_reads / 8 + 1024;
+        cudaFree(s.d_off64);
+        cudaFree(s.d_off32);
+        cudaFree(s.d_id0);
+        cudaFree(s.d_id0b);
+        cudaFree(s.d_lo);
+        cudaFree(s.d_hi);
+        cudaFree(s.d_count);
+        cudaFree(s.d_flags);
+        cudaFree(s.d_maskoff);
+        cudaFree(s.d_handoff);
+        cudaFree(s.d_handoff_n);
+        CKH(cudaMalloc(&s.d_off64, sizeof(int64_t) * c));
+        CKH(cudaMalloc(&s.d_off32, sizeof(uint32_t) * c));
+        CKH(cudaMalloc(&s.d_id0, sizeof(int32_t) * c));
+        CKH(cudaMalloc(&s.d_id0b, sizeof(int32_t) * c));
+        CKH(cudaMalloc(&s.d_lo, sizeof(int32_t) * c));
+        CKH(cudaMalloc(&s.d_hi, sizeof(int32_t) * c));
+        CKH(cudaMalloc(&s.d_count, sizeof(int32_t) * c));
+        CKH(cudaMalloc(&s.d_flags, (size_t)c));
+        CKH(cudaMalloc(&s.d_maskoff, sizeof(int64_t) * c));
+        CKH(cudaMalloc(&s.d_handoff, sizeof(int32_t) * c));
+        CKH(cudaMalloc(&s.d_handoff_n, sizeof(unsigned int) * 4));
+        s.cap_reads = c;
+    }
+    if (n_maskwords > s.cap_maskwords) {
+        cudaFree(s.d_maskbits);
+        s.cap_maskwords = n_maskwords + n_maskwords / 8 + 1024;
+        CKH(cudaMalloc(&s.d_maskbits, sizeof(uint32_t) * (size_t)s.cap_maskwords));
+    }
+    return 0;
+}
+
+// dispatch one device-resident batch: fast kernel where it applies, generic kernel for the rest
+int run_batch(bbduk_handle *h, const uint8_t *d_bases, const uint32_t *d_off, int64_t n_reads, int paired,
+              const bbduk_out &dout, bbduk_stats *d_stats, int max_read_len, int32_t *d_handoff,
+              unsigned int *d_handoff_n, cudaStream_t st) {
+    if (n_reads <= 0) return 0;
+    const BBTable t = h->table.view();
+    const int64_t n_units = paired ? n_reads / 2 : n_reads;
+    const FastPlan plan = plan_fast(h->p, t, max_read_len);
+    if (plan.usable && d_handoff) {
+        CKH(cudaMemsetAsync(d_handoff_n, 0, sizeof(unsigned int), st));
+        const int nl = launch_fast(plan, d_bases, d_off, n_reads, paired, h->p, t, dout, d_stats, h->d_scaf_reads,
+                                   h->d_scaf_bases, d_handoff, d_handoff_n, h->sm_count, st);
+        if (nl < 0) return set_err(h, std::string("fast kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+        h->launches += nl;
+        unsigned int n_hand = 0;
+        CKH(cudaMemcpyAsync(&n_hand, d_handoff_n, sizeof n_hand, cudaMemcpyDeviceToHost, st));
+        CKH(cudaStreamSynchronize(st));
+        if (n_hand > 0) {
+            if (launch_generic(d_bases, d_off, n_hand, paired, d_handoff, h->p, t, dout, d_stats, h->d_scaf_reads,
+                               h->d_scaf_bases, st))
+                return set_err(h, std::string("generic kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+            h->launches += 1;
+        }
+        return 0;
+    }
+    if (launch_generic(d_bases, d_off, n_units, paired, nullptr, h->p, t, dout, d_stats, h->d_scaf_reads, h->d_scaf_bases, st))
+        return set_err(h, std::string("generic kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    h->launches += 1;
+    return 0;
+}
+
+int check_mode_inputs(bbduk_handle *h, int paired, const bbduk_out *out) {
+    if (!out) return set_err(h, "out is NULL");
+    if (h->p.mode == MODE_KSPLIT && paired) return set_err(h, "Kmer splitting should only be performed on unpaired reads.");
+    if (h->p.mode == MODE_KMASK && h->table.stored > 0 && (!out->maskbits || !out->mask_off))
+        return set_err(h, "kmask mode needs out->maskbits and out->mask_off");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bbduk_b200_version(void) { return BBDUK_B200_ABI_VERSION; }
+
+void bbduk_b200_cfg_default(bbduk_cfg *c) {
+    if (!c) return;
+    memset(c, 0, sizeof *c);
+    c->struct_size = (int32_t)sizeof *c;
+    c->generation = BBDUK_GEN_JGI;
+    c->mink = -1;
+    c->hdist2 = c->edist2 = c->qhdist2 = -1;
+    c->rcomp = 1;
+    c->mask_middle = 1;
+    c->qskip = 1;
+    c->min_skip = c->max_skip = 1;
+    c->trim_symbol = 'N';
+    c->min_read_length = 10;
+    c->device = -1;
+}
+
+int bbduk_b200_describe_cfg(const bbduk_cfg *cfg, int64_t *v) {
+    BBParams p;
+    char eb[512] = {0};
+    if (!v) return set_err(nullptr, "v is NULL");
+    if (derive_params(cfg, &p, eb, sizeof eb)) return set_err(nullptr, eb);
+    const bool kfilter = p.mode >= MODE_KFILTER;
+    const int64_t out[16] = {p.k, p.kbig, p.mink, p.useShortKmers, p.maskMiddle, p.midMaskLen, p.minlen, p.minlen2,
+                             p.minminlen, p.forbidNs, p.hammingDistance, p.hammingDistance2, (int64_t)p.middleMask,
+                             (int64_t)p.mask, kfilter, p.removePairsIfEitherBad};
+    memcpy(v, out, sizeof out);
+    return 0;
+}
+
+const char *bbduk_b200_last_error(bbduk_handle *h) {
+    if (h) {
+        std::lock_guard<std::mutex> g(h->err_mu);
+        g_err = h->err;
+    }
+    return g_err.c_str();
+}
+
+int bbduk_b200_create(const bbduk_cfg *cfg, bbduk_handle **out) {
+    if (!out) return set_err(nullptr, "out is NULL");
+    *out = nullptr;
+    BBParams p;
+    char eb[512] = {0};
+    if (derive_params(cfg, &p, eb, sizeof eb)) return set_err(nullptr, eb);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev < 1)
+        return set_err(nullptr, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                    " (libbbduk_b200 has no CPU fallback)");
+    int dev = cfg->device;
+    if (dev < 0) {
+        if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    }
+    if (dev >= ndev) return set_err(nullptr, "cfg.device out of range");
+    bbduk_handle *h = new bbduk_handle();
+    h->cfg = *cfg;
+    h->p = p;
+    h->device = dev;
+    if (cudaSetDevice(dev) != cudaSuccess) {
+        delete h;
+        return set_err(nullptr, "cudaSetDevice failed");
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
+    *out = h;
+    return 0;
+}
+
+int bbduk_b200_add_ref(bbduk_handle *h, const uint8_t *bases, const int64_t *offsets, int32_t n_seqs) {
+    if (!h) return set_err(nullptr, "handle is NULL");
+    if (h->finalized) return set_err(h, "add_ref after finalize");
+    if (n_seqs < 0 || (n_seqs > 0 && (!bases || !offsets))) return set_err(h, "bad add_ref arguments");
+    for (int32_t s = 0; s < n_seqs; s++) {
+        const int64_t a = offsets[s], b = offsets[s + 1];
+        if (b < a) return set_err(h, "offsets must be non-decreasing");
+        for (int64_t i = a; i < b; i++)
+            if (bases[i] >= 128) return set_err(h, "reference contains a non-ASCII byte (the reference tool would throw)");
+        h->ref.insert(h->ref.end(), bases + a, bases + b);
+        h->ref_off.push_back((int64_t)h->ref.size());
+    }
+    return 0;
+}
+
+static int alloc_counters(bbduk_handle *h) {
+    const size_t n = (size_t)h->table.n_scaffolds + 1;
+    cudaFree(h->d_scaf_reads);
+    cudaFree(h->d_scaf_bases);
+    cudaFree(h->d_stats);
+    CKH(cudaMalloc(&h->d_scaf_reads, sizeof(unsigned long long) * n));
+    CKH(cudaMalloc(&h->d_scaf_bases, sizeof(unsigned long long) * n));
+    CKH(cudaMalloc(&h->d_stats, sizeof(bbduk_stats)));
+    CKH(cudaMemset(h->d_scaf_reads, 0, sizeof(unsigned long long) * n));
+    CKH(cudaMemset(h->d_scaf_bases, 0, sizeof(unsigned long long) * n));
+    CKH(cudaMemset(h->d_stats, 0, sizeof(bbduk_stats)));
+    return 0;
+}
+
+int bbduk_b200_finalize(bbduk_handle *h, int64_t *stored_kmers) {
+    if (!h) return set_err(nullptr, "handle is NULL");
+    if (h->finalized) {
+        if (stored_kmers) *stored_kmers = h->table.stored;
+        return 0;
+    }
+    CKH(cudaSetDevice(h->device));
+    char eb[512] = {0};
+    int64_t nl = 0;
+    // on-chip filter image: sized for the fast kernel's shared memory budget
+    const uint32_t filter_words = 40960;  // 160 KB
+    if (h->table.build(h->p, h->ref, h->ref_off, h->cfg.table_load_pct, filter_words, nullptr, &nl, eb, sizeof eb))
+        return set_err(h, eb);
+    h->launches += nl;
+    if (alloc_counters(h)) return 1;
+    h->finalized = true;
+    std::vector<uint8_t>().swap(h->ref);
+    if (stored_kmers) *stored_kmers = h->table.stored;
+    return 0;
+}
+
+int bbduk_b200_table_describe(bbduk_handle *h, bbduk_table_desc *d) {
+    if (!h || !d) return set_err(h, "NULL argument");
+    if (!h->finalized) return set_err(h, "table_describe before finalize");
+    memset(d, 0, sizeof *d);
+    d->n_slots = h->table.n_slots;
+    d->n_filter_words = h->table.n_filter_words;
+    d->stored_kmers = h->table.stored;
+    d->n_scaffolds = h->table.n_scaffolds;
+    d->d_keys = h->table.d_keys;
+    d->d_vals = h->table.d_vals;
+    d->d_filter = h->table.d_filter;
+    d->scalars[0] = h->table.ref_kmers;
+    return 0;
+}
+
+int bbduk_b200_table_alloc(bbduk_handle *h, bbduk_table_desc *d) {
+    if (!h || !d) return set_err(h, "NULL argument");
+    if (h->finalized) return set_err(h, "table_alloc on a finalized handle");
+    if (d->n_slots < 4 || (d->n_slots & (d->n_slots - 1))) return set_err(h, "n_slots must be a power of two >= 4");
+    CKH(cudaSetDevice(h->device));
+    char eb[512] = {0};
+    if (h->table.alloc(d->n_slots, (uint32_t)d->n_filter_words, eb, sizeof eb)) return set_err(h, eb);
+    h->table.stored = d->stored_kmers;
+    h->table.n_scaffolds = d->n_scaffolds;
+    h->table.ref_kmers = d->scalars[0];
+    d->d_keys = h->table.d_keys;
+    d->d_vals = h->table.d_vals;
+    d->d_filter = h->table.d_filter;
+    return 0;
+}
+
+int bbduk_b200_table_commit(bbduk_handle *h) {
+    if (!h) return set_err(nullptr, "handle is NULL");
+    if (h->finalized) return 0;
+    if (!h->table.d_keys) return set_err(h, "table_commit without table_alloc");
+    CKH(cudaSetDevice(h->device));
+    if (alloc_counters(h)) return 1;
+    h->finalized = true;
+    return 0;
+}
+
+int bbduk_b200_process_device(bbduk_handle *h, const uint8_t *d_bases, const uint32_t *d_offsets, int64_t n_reads,
+                              int32_t paired, const bbduk_out *d_out, bbduk_stats *d_stats, void *stream) {
+    if (!h) return set_err(nullptr, "handle is NULL");
+    if (!h->finalized) return set_err(h, "process before finalize");
+    if (n_reads < 0 || (paired && (n_reads & 1))) return set_err(h, "bad n_reads");
+    if (check_mode_inputs(h, paired, d_out)) return 1;
+    if (n_reads == 0) return 0;
+    CKH(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    std::lock_guard<std::mutex> g(h->dev_mu);
+    const int64_t n_units = paired ? n_reads / 2 : n_reads;
+    if (n_units + 8 > h->dev_handoff_cap) {
+        cudaFree(h->dev_handoff);
+        cudaFree(h->dev_handoff_n);
+        h->dev_handoff_cap = n_units + n_units / 8 + 1024;
+        CKH(cudaMalloc(&h->dev_handoff, sizeof(int32_t) * h->dev_handoff_cap));
+        CKH(cudaMalloc(&h->dev_handoff_n, sizeof(unsigned int) * 4));
+    }
+    // longest read (sizes the fast kernel's staging)
+    unsigned int mx = 0;
+    CKH(cudaMemsetAsync(h->dev_handoff_n + 1, 0, sizeof(unsigned int), st));
+    max_len_kernel<<<296, 256, 0, st>>>(d_offsets, n_reads, h->dev_handoff_n + 1);
+    h->launches += 1;
+    CKH(cudaMemcpyAsync(&mx, h->dev_handoff_n + 1, sizeof mx, cudaMemcpyDeviceToHost, st));
+    CKH(cudaStreamSynchronize(st));
+    return run_batch(h, d_bases, d_offsets, n_reads, paired, *d_out, d_stats, (int)mx, h->dev_handoff, h->dev_handoff_n, st);
+}
+
+int bbduk_b200_process(bbduk_handle *h, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, int32_t paired,
+                       const bbduk_out *out, bbduk_stats *stats) {
+    if (!h) return set_err(nullptr, "handle is NULL");
+    if (!h->finalized) return set_err(h, "process before finalize");
+    if (n_reads < 0 || (paired && (n_reads & 1))) return set_err(h, "bad n_reads (paired input needs an even count)");
+    if (n_reads > 0 && (!bases || !offsets)) return set_err(h, "NULL input");
+    if (check_mode_inputs(h, paired, out)) return 1;
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (n_reads == 0) return 0;
+    CKH(cudaSetDevice(h->device));
+    const bool want_mask = h->p.mode == MODE_KMASK && out->maskbits && out->mask_off;
+
+    // private device-side stats for this call so concurrent callers do not mix
+    bbduk_stats *d_stats = nullptr;
+    if (stats) {
+        CKH(cudaMalloc(&d_stats, sizeof(bbduk_stats)));
+        CKH(cudaMemset(d_stats, 0, sizeof(bbduk_stats)));
+    }
+    int rc = 0;
+    std::vector<Slot *> used;
+    const int per = paired ? 2 : 1;
+    int64_t r0 = 0;
+    while (r0 < n_reads && !rc) {
+        // chunk [r0, r1): bounded reads and bytes, pairs never split
+        int64_t r1 = std::min(n_reads, r0 + CHUNK_READS);
+        while (r1 > r0 + per && offsets[r1] - offsets[r0] > CHUNK_BYTES) r1 = r0 + std::max<int64_t>(per, ((r1 - r0) / 2 / per) * per);
+        const int64_t nb = offsets[r1] - offsets[r0];
+        if (nb >= (1ll << 32) - 64) {
+            rc = set_err(h, "a single read (pair) exceeds 4 GiB");
+            break;
+        }
+        const int64_t nr = r1 - r0;
+        const int64_t mw0 = want_mask ? out->mask_off[r0] : 0, mw = want_mask ? out->mask_off[r1] - mw0 : 0;
+        Slot &s = h->slots[h->next_slot++ % N_SLOTS];
+        std::lock_guard<std::mutex> g(s.mu);
+        if (s.done) cudaEventSynchronize(s.done);  // previous use of this slot has drained
+        if ((rc = ensure_slot(h, s, nr, nb, mw))) break;
+        // longest read of the chunk (host side, one pass over the offsets that are being copied anyway)
+        int max_len = 0;
+        for (int64_t i = r0; i < r1; i++) {
+            const int64_t l = offsets[i + 1] - offsets[i];
+            if (l < 0 || l > 0x7FFFFFFF) {
+                rc = set_err(h, "bad read length");
+                break;
+            }
+            if (l > max_len) max_len = (int)l;
+        }
+        if (rc) break;
+        cudaStream_t st = s.st;
+#define CKL(call)                                                                                          \
+    if (!rc) {                                                                                             \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess) {                                                                           \
+            char b_[512];                                                                                  \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            rc = set_err(h, b_);                                                                           \
+        }                                                                                                  \
+    }
+        CKL(cudaMemcpyAsync(s.d_bases, bases + offsets[r0], (size_t)nb, cudaMemcpyHostToDevice, st));
+        CKL(cudaMemcpyAsync(s.d_off64, offsets + r0, sizeof(int64_t) * (nr + 1), cudaMemcpyHostToDevice, st));
+        if (!rc) {
+            off64_to_32_kernel<<<(unsigned)((nr + 1 + 255) / 256), 256, 0, st>>>(s.d_off64, offsets[r0], s.d_off32, nr + 1);
+            h->launches += 1;
+        }
+        bbduk_out dout;
+        memset(&dout, 0, sizeof dout);
+        dout.id0 = out->id0 ? s.d_id0 : nullptr;
+        dout.id0b = out->id0b ? s.d_id0b : nullptr;
+        dout.lo = out->lo ? s.d_lo : nullptr;
+        dout.hi = out->hi ? s.d_hi : nullptr;
+        dout.flags = out->flags ? s.d_flags : nullptr;
+        dout.count = out->count ? s.d_count : nullptr;
+        if (want_mask) {
+            CKL(cudaMemcpyAsync(s.d_maskoff, out->mask_off + r0, sizeof(int64_t) * (nr + 1), cudaMemcpyHostToDevice, st));
+            if (!rc) {
+                maskoff_rebase_kernel<<<(unsigned)((nr + 1 + 255) / 256), 256, 0, st>>>(s.d_maskoff, mw0, nr + 1);
+                h->launches += 1;
+            }
+            dout.maskbits = s.d_maskbits;
+            dout.mask_off = s.d_maskoff;
+        }
+        if (!rc) rc = run_batch(h, s.d_bases, s.d_off32, nr, paired, dout, d_stats, max_len, s.d_handoff, s.d_handoff_n, st);
+        if (out->id0) CKL(cudaMemcpyAsync(out->id0 + r0, s.d_id0, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, st));
+        if (out->id0b) CKL(cudaMemcpyAsync(out->id0b + r0, s.d_id0b, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, st));
+        if (out->lo) CKL(cudaMemcpyAsync(out->lo + r0, s.d_lo, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, st));
+        if (out->hi) CKL(cudaMemcpyAsync(out->hi + r0, s.d_hi, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, st));
+        if (out->count) CKL(cudaMemcpyAsync(out->count + r0, s.d_count, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, st));
+        if (out->flags) CKL(cudaMemcpyAsync(out->flags + r0, s.d_flags, (size_t)nr, cudaMemcpyDeviceToHost, st));
+        if (want_mask && mw > 0)
+            CKL(cudaMemcpyAsync(out->maskbits + mw0, s.d_maskbits, sizeof(uint32_t) * mw, cudaMemcpyDeviceToHost, st));
+        CKL(cudaEventRecord(s.done, st));
+#undef CKL
+        used.push_back(&s);
+        r0 = r1;
+    }
+    for (Slot *s : used) cudaStreamSynchronize(s->st);
+    if (!rc && stats) {
+        if (cudaMemcpy(stats, d_stats, sizeof *stats, cudaMemcpyDeviceToHost) != cudaSuccess) rc = set_err(h, "stats copy failed");
+    }
+    cudaFree(d_stats);
+    if (!rc) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = set_err(h, std::string("CUDA error after process: ") + cudaGetErrorString(e));
+    }
+    return rc;
+}
+
+int bbduk_b200_scaffold_counts(bbduk_handle *h, int64_t *read_counts, int64_t *base_counts, int32_t n) {
+    if (!h) return set_err(nullptr, "handle is NULL");
+    if (!h->finalized) return set_err(h, "scaffold_counts before finalize");
+    CKH(cudaSetDevice(h->device));
+    CKH(cudaDeviceSynchronize());
+    const int32_t m = std::min(n, h->table.n_scaffolds + 1);
+    if (m <= 0) return 0;
+    if (read_counts) CKH(cudaMemcpy(read_counts, h->d_scaf_reads, sizeof(int64_t) * m, cudaMemcpyDeviceToHost));
+    if (base_counts) CKH(cudaMemcpy(base_counts, h->d_scaf_bases, sizeof(int64_t) * m, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int64_t bbduk_b200_launch_count(bbduk_handle *h) { return h ? h->launches.load() : 0; }
+
+void bbduk_b200_destroy(bbduk_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (auto &s : h->slots) {
+        if (s.st) cudaStreamSynchronize(s.st);
+        free_slot(s);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.st) cudaStreamDestroy(s.st);
+    }
+    h->table.release();
+    cudaFree(h->d_scaf_reads);
+    cudaFree(h->d_scaf_bases);
+    cudaFree(h->d_stats);
+    cudaFree(h->dev_handoff);
+    cudaFree(h->dev_handoff_n);
+    delete h;
+}
+
+}  // extern "C"

@@ -1,0 +1,101 @@
+// bbduk_dev.cuh -- device-side codec, key formula, hashing and hash-array access shared by all kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "params.h"
+
+// ---- 2-bit codec (replaces dna.AminoAcid tables, dna/AminoAcid.java:269-285, :1289-1320) ----------
+// A/a 0, C/c 1, G/g 2, T/t/U/u 3 from bits 1..2 of the ASCII code; "defined" is an exact membership
+// test, everything else (N, IUPAC, '.', '-', ...) is undefined -> code0 = comp0 = 0.
+__device__ __forceinline__ uint32_t bb_code_raw(uint32_t c) { return ((c >> 1) ^ (c >> 2)) & 3u; }
+__device__ __forceinline__ bool bb_defined(uint32_t c) {
+    // jgi/BBDuk.java:5355-5357 isFullyDefined: symbol>=0 && baseToNumber[symbol]>=0
+    const uint32_t y = c | 0x20u;
+    return (c < 128u) && (y == 'a' || y == 'c' || y == 'g' || y == 't' || y == 'u');
+}
+__device__ __forceinline__ uint32_t bb_code0(uint32_t c) { return bb_defined(c) ? bb_code_raw(c) : 0u; }
+__device__ __forceinline__ uint32_t bb_comp0(uint32_t c) { return bb_defined(c) ? (3u - bb_code_raw(c)) : 0u; }
+// baseToNumber (undefined -> -1), used for extraBase in the loader (jgi/BBDuk.java:2277)
+__device__ __forceinline__ int bb_code_m1(uint32_t c) { return bb_defined(c) ? (int)bb_code_raw(c) : -1; }
+
+// ---- reverse complement of a 2-bit packed k-mer (dna/AminoAcid.java:585-603) -----------------------
+__device__ __forceinline__ uint64_t bb_rcomp(uint64_t kmer, int k) {
+    uint32_t lo = ~(uint32_t)kmer, hi = ~(uint32_t)(kmer >> 32);
+    lo = __brev(lo);
+    hi = __brev(hi);
+    // brev reversed the bits inside each base pair too: swap them back
+    lo = ((lo & 0x55555555u) << 1) | ((lo >> 1) & 0x55555555u);
+    hi = ((hi & 0x55555555u) << 1) | ((hi >> 1) & 0x55555555u);
+    const uint64_t x = ((uint64_t)lo << 32) | hi;  // word swap completes the 64-bit reversal
+    return x >> (2 * (32 - k));
+}
+
+// ---- key formula (jgi/BBDuk.java:4673-4685 toValue / :3373-3375) -----------------------------------
+__device__ __forceinline__ uint64_t bb_to_value(const BBParams &p, uint64_t kmer, uint64_t rkmer, uint64_t lengthMask) {
+    const uint64_t v = p.rcomp ? (kmer > rkmer ? kmer : rkmer) : kmer;
+    return (v & p.middleMask) | lengthMask;
+}
+// (key & Long.MAX_VALUE) % 17 speed filter (jgi/BBDuk.java:4702-4713)
+__device__ __forceinline__ bool bb_passes_speed(const BBParams &p, uint64_t key) {
+    return p.speed < 1 || (int)((key & 0x7FFFFFFFFFFFFFFFull) % 17ull) >= p.speed;
+}
+
+// ---- hashing: layout only, any mixing function gives the same results ------------------------------
+__device__ __forceinline__ uint64_t bb_hash64(uint64_t x) {
+    x ^= x >> 32;
+    x *= 0xD6E8FEB86659FD93ull;
+    x ^= x >> 32;
+    x *= 0xD6E8FEB86659FD93ull;
+    x ^= x >> 32;
+    return x;
+}
+
+#define BB_MAX_PROBE 8192
+// Hash array: buckets of 4 consecutive slots (one 32-byte sector), linear probing across slots.
+// Lookup = kmer.AbstractKmerTable.getValue (kmer/AbstractKmerTable.java:61): id or -1.
+__device__ __forceinline__ int bb_table_get(const BBTable &t, uint64_t key) {
+    uint64_t slot = (bb_hash64(key) & (t.slot_mask >> 2)) << 2;
+    for (int probe = 0; probe < BB_MAX_PROBE; probe++) {  // inserts never go further than BB_MAX_PROBE
+        const uint64_t kk = __ldg(t.keys + slot);
+        if (kk == key) return __ldg(t.vals + slot);
+        if (kk == BB_EMPTY_KEY) return -1;
+        slot = (slot + 1) & t.slot_mask;
+    }
+    return -1;
+}
+
+// Insert = setIfNotPresent with "first writer wins" realised as min id.
+// Returns 1 if this call created the key. The probe length is bounded so that an over-full array
+// raises *overflow instead of spinning forever.
+__device__ __forceinline__ int bb_table_put(uint64_t *keys, int32_t *vals, uint64_t slot_mask, uint64_t key, int32_t id,
+                                            int *overflow) {
+    uint64_t slot = (bb_hash64(key) & (slot_mask >> 2)) << 2;
+    for (int probe = 0; probe < BB_MAX_PROBE; probe++) {
+        uint64_t kk = keys[slot];
+        if (kk == BB_EMPTY_KEY) {
+            kk = atomicCAS((unsigned long long *)(keys + slot), (unsigned long long)BB_EMPTY_KEY, (unsigned long long)key);
+            if (kk == BB_EMPTY_KEY) {
+                atomicMin(vals + slot, id);
+                return 1;
+            }
+        }
+        if (kk == key) {
+            atomicMin(vals + slot, id);
+            return 0;
+        }
+        slot = (slot + 1) & slot_mask;
+    }
+    *overflow = 1;
+    return 0;
+}
+
+// ---- blocked bloom pre-filter over all keys (no false negatives) ----------------------------------
+// word index and a 3-bit pattern from one 64-bit hash; the same function builds and queries.
+__device__ __forceinline__ uint32_t bb_filter_word(uint64_t h, uint32_t n_words) {
+    return __umulhi((uint32_t)(h >> 32), n_words);
+}
+__device__ __forceinline__ uint32_t bb_filter_bits(uint64_t h) {
+    const uint32_t x = (uint32_t)h;
+    return (1u << (x & 31)) | (1u << ((x >> 5) & 31)) | (1u << ((x >> 10) & 31));
+}

@@ -1,0 +1,57 @@
+// params.h -- derived BBDuk constants shared by host code and kernels (POD, passed by value to kernels).
+//
+// Field names follow the reference (jgi/BBDuk.java:5121-5347); derive_params() in derive.cpp computes
+// them exactly as the reference's constructor does (jgi/BBDuk.java:583-585, :672-877).
+#pragma once
+#include <stdint.h>
+
+enum BBMode : int32_t {
+    MODE_KTRIM = 0,    // ktrim=r or ktrim=l          (jgi/BBDuk.java:3866-4013)
+    MODE_KTRIM_TIPS,   // ktrim=rl                    (jgi/BBDuk.java:3686-3858)
+    MODE_KMASK,        // ktrim=n / kmask             (jgi/BBDuk.java:4022-4199)
+    MODE_KSPLIT,       // ksplit                      (jgi/BBDuk.java:4208-4377)
+    MODE_KFILTER,      // countSetKmers               (jgi/BBDuk.java:3395-3457)
+    MODE_KFILTER_BIG,  // countSetKmersBig, k>31      (jgi/BBDuk.java:3596-3677)
+    MODE_KCOVER,       // countCoveredBases, mcf>0    (jgi/BBDuk.java:3466-3519)
+    MODE_KBEST         // findBestMatch               (jgi/BBDuk.java:3527-3589)
+};
+
+struct BBParams {
+    // k-mer geometry
+    int32_t k, k2, kbig, keff, mink;
+    int32_t minlen, minlen2, minminlen, shift2;
+    int32_t midMaskLen, maskMiddle, useShortKmers;
+    uint64_t mask, kmask, middleMask;
+    // distances
+    int32_t hammingDistance, hammingDistance2, editDistance, editDistance2;
+    int32_t qHammingDistance, qHammingDistance2;
+    int32_t minSkip, maxSkip;
+    // query behaviour
+    int32_t forbidNs, rcomp, speed, qSkip;
+    int32_t restrictLeft, restrictRight, skipR1, skipR2;
+    int32_t mode;  // BBMode
+    int32_t ktrimLeft, ktrimRight, ktrimExclusive, trimPad;
+    int32_t kmaskFullyCovered;
+    int32_t maxBadKmers0;
+    float minKmerFraction, minCoveredFraction;
+    // pair logic
+    int32_t minReadLength;
+    float minLenFraction;
+    int32_t removePairsIfEitherBad, trimPairsEvenly, trimFailuresTo1bp;
+};
+
+// Device hash-array geometry (layout only; results do not depend on it -- SURVEY.md section 0.2).
+struct BBTable {
+    const uint64_t *keys;   // [n_slots]; EMPTY = ~0
+    const int32_t *vals;    // [n_slots]; scaffold id (min over writers)
+    uint64_t slot_mask;     // n_slots-1 (n_slots power of two, multiple of 4)
+    const uint32_t *filter; // blocked bloom image of all keys, n_filter_words 32-bit words (may be null)
+    uint32_t n_filter_words;
+    int32_t n_scaffolds;
+    int64_t stored;         // distinct keys
+};
+
+#define BB_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+
+// returns 0 on success, else writes a message (reference's assertion texts) into err
+int derive_params(const struct bbduk_cfg *cfg, BBParams *p, char *err, int errlen);

@@ -1,0 +1,26 @@
+// probe.h -- launchers of the per-read kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/bbduk_b200.h"
+#include "params.h"
+
+// every mode, one thread per unit (pair or single read); d_units = optional list of unit indices
+int launch_generic(const uint8_t *d_bases, const uint32_t *d_offsets, int64_t n_units, int paired, const int32_t *d_units,
+                   const BBParams &p, const BBTable &t, const bbduk_out &out, bbduk_stats *d_stats,
+                   unsigned long long *scaf_reads, unsigned long long *scaf_bases, cudaStream_t st);
+
+// tuned kernel (probe_fast.cu). Returns the number of kernels launched, <0 on error. Units it cannot
+// handle are appended to d_handoff (count in d_handoff_n) for launch_generic.
+struct FastPlan {
+    bool usable;        // configuration covered by the fast kernel
+    int max_read_len;   // longest read the staging is sized for
+    int smem_bytes;     // dynamic shared memory per block
+    int filter_words;   // words of the on-chip filter image actually used
+};
+FastPlan plan_fast(const BBParams &p, const BBTable &t, int max_read_len);
+int launch_fast(const FastPlan &plan, const uint8_t *d_bases, const uint32_t *d_offsets, int64_t n_reads, int paired,
+                const BBParams &p, const BBTable &t, const bbduk_out &out, bbduk_stats *d_stats,
+                unsigned long long *scaf_reads, unsigned long long *scaf_bases, int32_t *d_handoff,
+                unsigned int *d_handoff_n, int sm_count, cudaStream_t st);

@@ -1,0 +1,451 @@
+// table.cu -- one-time reference-table build on the device.
+//
+// Replaces the reference's LoadThread scan + mutate recursion (jgi/BBDuk.java:2210-2452) and the
+// kmer.HashArray1D inserts behind it. The reference walks the (3k)^d mutation tree once per way and
+// throws 6/7 of it away; here every (reference k-mer, mutation prefix) is one thread, mutants are
+// inserted with atomicCAS on the key and atomicMin on the id, which realises "first writer wins with
+// scaffolds in file order" == smallest scaffold id, and duplicate mutants
+// collapse in the insert itself.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <vector>
+
+#include "bbduk_dev.cuh"
+#include "table.h"
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            snprintf(err, errlen, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return 1;                                                                                 \
+        }                                                                                             \
+    } while (0)
+
+struct Seed {
+    uint64_t kmer;
+    int32_t id;
+    int8_t extra;  // next reference base (0..3) or -1; "extraBase" of jgi/BBDuk.java:2277
+    int8_t pad[3];
+};
+
+// ---- pass 1: reference scan (jgi/BBDuk.java:2210-2288 addToMap(Read,skip)) --------------------------
+// One thread per reference base i. run[i] = number of consecutive defined bases ending at i inside the
+// scaffold (the reference's `len`), precomputed for skip>1, else derived from a k-base look-back.
+// Emits the full-length seed at i when len>=k (&& len%skip==0), and -- when useShortKmers -- the
+// prefix seeds at i==k-1 (addToMapRightShift, :2327-2346) and suffix seeds at i==L-1
+// (addToMapLeftShift, :2299-2317).
+__global__ void ref_seed_kernel(const uint8_t *__restrict__ bases, const int64_t *__restrict__ offsets,
+                                const int32_t *__restrict__ scaf_of_block, const int32_t *__restrict__ skips,
+                                int32_t first_id, int64_t total, BBParams p, Seed *full_seeds,
+                                unsigned long long *n_full, Seed *short_seeds /* [32][cap_short] */,
+                                unsigned long long *n_short /* [32] */, int64_t cap_short,
+                                unsigned long long *ref_kmers) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    // locate the scaffold of this base: blocks are annotated with the scaffold of their first base
+    int32_t s = scaf_of_block[blockIdx.x];
+    while (offsets[s + 1] <= g) s++;
+    const int64_t s0 = offsets[s], s1 = offsets[s + 1];
+    const int64_t i = g - s0, L = s1 - s0;
+    const int k = p.k;
+    if (L < k || i < k - 1) return;
+    // rolling state at i, closed form: all of the last k bases must be defined for len>=k
+    uint64_t kmer = 0, rkmer = 0;
+    for (int j = 0; j < k; j++) {
+        const uint32_t c = bases[g - (k - 1) + j];
+        if (!bb_defined(c)) return;
+        const uint32_t x = bb_code_raw(c);
+        kmer = (kmer << 2) | x;
+        rkmer = (rkmer >> 2) | ((uint64_t)(3u - x) << p.shift2);
+    }
+    namespace cg = cooperative_groups;
+    int skip = skips[s];
+    {
+        cg::coalesced_group grp = cg::coalesced_threads();
+        if (grp.thread_rank() == 0) atomicAdd(ref_kmers, (unsigned long long)grp.size());
+    }
+    if (skip > 1) {
+        // exact run length needed: walk back to the last undefined base (rare path, skip>1 only)
+        int64_t len = k;
+        int64_t q = g - k;
+        while (q >= s0 && bb_defined(bases[q])) {
+            len++;
+            q--;
+        }
+        if (len % skip != 0) return;
+    }
+    const int id = first_id + s;
+    const int extra = (i >= L - 1) ? -1 : bb_code_m1(bases[g + 1]);
+    {
+        cg::coalesced_group grp = cg::coalesced_threads();
+        unsigned long long w = 0;
+        if (grp.thread_rank() == 0) w = atomicAdd(n_full, (unsigned long long)grp.size());
+        w = grp.shfl(w, 0) + grp.thread_rank();
+        Seed sd;
+        sd.kmer = kmer;
+        sd.id = id;
+        sd.extra = (int8_t)extra;
+        full_seeds[w] = sd;
+    }
+    if (p.useShortKmers) {
+        if (i == k - 1) {  // prefixes of the first k-mer, lengths k-1..mink
+            uint64_t km = kmer;
+            for (int n = k - 1; n >= p.mink; n--) {
+                const int eb = (int)(km & 3);
+                km >>= 2;
+                const unsigned long long w = atomicAdd(n_short + n, 1ull);
+                Seed sd;
+                sd.kmer = km;
+                sd.id = id;
+                sd.extra = (int8_t)eb;
+                short_seeds[(int64_t)n * cap_short + w] = sd;
+            }
+        }
+        if (i == L - 1) {  // suffixes of the last k-mer
+            for (int n = k - 1; n >= p.mink; n--) {
+                const uint64_t km = kmer & ((1ull << (2 * n)) - 1);
+                const unsigned long long w = atomicAdd(n_short + n, 1ull);
+                Seed sd;
+                sd.kmer = km;
+                sd.id = id;
+                sd.extra = (int8_t)extra;
+                short_seeds[(int64_t)n * cap_short + w] = sd;
+            }
+        }
+    }
+    (void)rkmer;
+}
+
+// ---- pass 2: neighbourhood expansion (jgi/BBDuk.java:2359-2452 addToMap + mutate) ------------------
+// One edit operation of mutate()'s loops, addressed by a flat index:
+//   [0, 4*len)                 Sub   j=op/len, i=op%len                       (:2413-2421)
+//   [.., +len-1)               Del   i=1..len-1, needs extraBase in 0..3      (:2425-2433)
+//   [.., +4*(len-1))           Ins   i=1..len-1, j=0..3                       (:2436-2446)
+// The indel ranges exist only when the global editDistance>0 (:2423).
+__device__ __forceinline__ int n_ops_for(int len, bool edits) { return 4 * len + (edits ? 5 * (len - 1) : 0); }
+
+__device__ __forceinline__ bool apply_op(uint64_t kmer, int len, int extra, int op, uint64_t &out, int &extra_out) {
+    if (op < 4 * len) {
+        const int j = op / len, i = op - j * len;
+        out = (kmer & ~(3ull << (2 * i))) | ((uint64_t)j << (2 * i));
+        extra_out = extra;
+        return out != kmer;
+    }
+    op -= 4 * len;
+    if (op < len - 1) {
+        const int i = op + 1;
+        if (extra < 0 || extra > 3) return false;
+        const uint64_t left = ~0ull << (2 * i), right = ~left;
+        out = (kmer & left) | ((kmer << 2) & right) | (uint64_t)extra;
+        extra_out = -1;
+        return out != kmer;
+    }
+    op -= (len - 1);
+    const int i = (op >> 2) + 1, j = op & 3;
+    const uint64_t left = ~0ull << (2 * i), right = ~left;
+    out = ((kmer & left) | ((kmer & right) >> 2)) | ((uint64_t)j << (2 * (i - 1)));
+    extra_out = (int)(kmer & 3);
+    return out != kmer;
+}
+
+__device__ __forceinline__ int put_kmer(uint64_t *keys, int32_t *vals, uint64_t slot_mask, const BBParams &p,
+                                        uint64_t kmer, int len, int id, int *overflow) {
+    const uint64_t key = bb_to_value(p, kmer, bb_rcomp(kmer, len), 1ull << (2 * len));
+    return bb_table_put(keys, vals, slot_mask, key, id, overflow);
+}
+
+// dist = number of mutate() recursion levels; prefix_levels = dist-1 levels are decoded from the
+// thread index, the last level is a loop. Every intermediate string is inserted too (mutate inserts
+// its own key before recursing, :2395-2407).
+__global__ void expand_kernel(const Seed *__restrict__ seeds, int64_t n_seeds, int len, int dist, int use_extra,
+                              BBParams p, uint64_t *keys, int32_t *vals, uint64_t slot_mask,
+                              unsigned long long *created, int *overflow) {
+    const bool edits = p.editDistance > 0;
+    const int nops = n_ops_for(len, edits);
+    int64_t n_prefix = 1;
+    for (int d = 1; d < dist; d++) n_prefix *= nops;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_seeds * n_prefix) return;
+    const int64_t si = t / n_prefix;
+    int64_t pre = t - si * n_prefix;
+    const Seed sd = seeds[si];
+    uint64_t km = sd.kmer;
+    int extra = use_extra ? (int)sd.extra : -1;
+    int made = 0;
+    if (dist == 0) {
+        // addToMap hdist==0 branch: speed filter applies only here (:2366-2372)
+        const uint64_t key = bb_to_value(p, km, bb_rcomp(km, len), 1ull << (2 * len));
+        if (bb_passes_speed(p, key)) made += bb_table_put(keys, vals, slot_mask, key, sd.id, overflow);
+        if (made) atomicAdd(created, (unsigned long long)made);
+        return;
+    }
+    made += put_kmer(keys, vals, slot_mask, p, km, len, sd.id, overflow);
+    for (int d = 1; d < dist; d++) {
+        const int op = (int)(pre % nops);
+        pre /= nops;
+        uint64_t nk;
+        int ne;
+        if (!apply_op(km, len, extra, op, nk, ne)) return;  // temp==kmer or impossible deletion: no subtree
+        km = nk;
+        extra = ne;
+        made += put_kmer(keys, vals, slot_mask, p, km, len, sd.id, overflow);
+    }
+    for (int op = 0; op < nops; op++) {
+        uint64_t nk;
+        int ne;
+        if (apply_op(km, len, extra, op, nk, ne)) made += put_kmer(keys, vals, slot_mask, p, nk, len, sd.id, overflow);
+    }
+    if (made) atomicAdd(created, (unsigned long long)made);
+}
+
+__global__ void fill_kernel(uint64_t *keys, int32_t *vals, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        keys[i] = BB_EMPTY_KEY;
+        vals[i] = 0x7FFFFFFF;
+    }
+}
+
+__global__ void rehash_kernel(const uint64_t *__restrict__ okeys, const int32_t *__restrict__ ovals, int64_t n_old,
+                              uint64_t *keys, int32_t *vals, uint64_t slot_mask, int *overflow) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_old; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = okeys[i];
+        if (k != BB_EMPTY_KEY) bb_table_put(keys, vals, slot_mask, k, ovals[i], overflow);
+    }
+}
+
+__global__ void filter_build_kernel(const uint64_t *__restrict__ keys, int64_t n, uint32_t *filter, uint32_t n_words) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = keys[i];
+        if (k != BB_EMPTY_KEY) {
+            const uint64_t h = bb_hash64(k);
+            atomicOr(filter + bb_filter_word(h, n_words), bb_filter_bits(h));
+        }
+    }
+}
+
+static int64_t pow2ceil(int64_t x) {
+    int64_t p = 4;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+// number of strings visited by mutate() (upper bound on keys created by one seed)
+static double ball_bound(int len, int dist, bool edits) {
+    const double nops = 4.0 * len + (edits ? 5.0 * (len - 1) : 0.0);
+    double tot = 1, lvl = 1;
+    for (int d = 1; d <= dist; d++) {
+        lvl *= nops;
+        tot += lvl;
+    }
+    if (!edits) {  // exact Hamming-ball size
+        double b = 0, c = 1;
+        for (int d = 0; d <= dist; d++) {
+            b += c;
+            c = c * (len - d) / (d + 1) * 3.0;
+        }
+        return b;
+    }
+    return tot;
+}
+
+void DeviceTable::release() {
+    if (owns) {
+        cudaFree(d_keys);
+        cudaFree(d_vals);
+        cudaFree(d_filter);
+    }
+    d_keys = nullptr;
+    d_vals = nullptr;
+    d_filter = nullptr;
+    n_slots = 0;
+}
+
+int DeviceTable::alloc(int64_t slots, uint32_t filter_words, char *err, int errlen) {
+    release();
+    n_slots = slots;
+    n_filter_words = filter_words;
+    owns = true;
+    CK(cudaMalloc(&d_keys, sizeof(uint64_t) * (size_t)slots));
+    CK(cudaMalloc(&d_vals, sizeof(int32_t) * (size_t)slots));
+    CK(cudaMalloc(&d_filter, sizeof(uint32_t) * (size_t)filter_words));
+    return 0;
+}
+
+BBTable DeviceTable::view() const {
+    BBTable t;
+    t.keys = d_keys;
+    t.vals = d_vals;
+    t.slot_mask = (uint64_t)n_slots - 1;
+    t.filter = d_filter;
+    t.n_filter_words = n_filter_words;
+    t.n_scaffolds = n_scaffolds;
+    t.stored = stored;
+    return t;
+}
+
+int DeviceTable::build(const BBParams &p, const std::vector<uint8_t> &ref, const std::vector<int64_t> &offsets,
+                       int load_pct, uint32_t filter_words, cudaStream_t st, int64_t *launches, char *err, int errlen) {
+    const int32_t n_scaf = (int32_t)offsets.size() - 1;
+    n_scaffolds = n_scaf;
+    stored = 0;
+    ref_kmers = 0;
+    const int64_t total = n_scaf > 0 ? offsets.back() : 0;
+    if (load_pct <= 0 || load_pct > 90) load_pct = 50;
+
+    uint8_t *d_ref = nullptr;
+    int64_t *d_off = nullptr;
+    int32_t *d_blk = nullptr, *d_skip = nullptr;
+    Seed *d_full = nullptr, *d_short = nullptr;
+    unsigned long long *d_cnt = nullptr;  // [0]=n_full [1..32]=n_short[len] [34]=created [35]=ref_kmers
+    const int TPB = 256;
+    const int64_t n_blocks = (total + TPB - 1) / TPB;
+    const int64_t cap_short = 2 * (int64_t)std::max(n_scaf, 1);
+    unsigned long long h_cnt[40] = {0};
+
+    auto cleanup = [&]() {
+        cudaFree(d_ref);
+        cudaFree(d_off);
+        cudaFree(d_blk);
+        cudaFree(d_skip);
+        cudaFree(d_full);
+        cudaFree(d_short);
+        cudaFree(d_cnt);
+    };
+#define CKC(call)                                                                                     \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            snprintf(err, errlen, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            cleanup();                                                                                \
+            return 1;                                                                                 \
+        }                                                                                             \
+    } while (0)
+
+    CKC(cudaMalloc(&d_cnt, sizeof(h_cnt)));
+    CKC(cudaMemsetAsync(d_cnt, 0, sizeof(h_cnt), st));
+    if (total > 0) {
+        // per-scaffold skip (jgi/BBDuk.java:2190, :2211) and per-block scaffold hints
+        std::vector<int32_t> skips(n_scaf), blk(n_blocks);
+        for (int32_t s = 0; s < n_scaf; s++) {
+            const int64_t L = offsets[s + 1] - offsets[s];
+            const int sk = L > 20000000 ? p.k : L > 5000000 ? 11 : L > 500000 ? 2 : 0;
+            skips[s] = std::max(p.minSkip, std::min(p.maxSkip, sk));
+        }
+        {
+            int32_t s = 0;
+            for (int64_t b = 0; b < n_blocks; b++) {
+                const int64_t g = b * TPB;
+                while (s + 1 < n_scaf && offsets[s + 1] <= g) s++;
+                blk[b] = s;
+            }
+        }
+        CKC(cudaMalloc(&d_ref, (size_t)total + 16));
+        CKC(cudaMalloc(&d_off, sizeof(int64_t) * (n_scaf + 1)));
+        CKC(cudaMalloc(&d_blk, sizeof(int32_t) * n_blocks));
+        CKC(cudaMalloc(&d_skip, sizeof(int32_t) * n_scaf));
+        CKC(cudaMalloc(&d_full, sizeof(Seed) * (size_t)total));
+        CKC(cudaMalloc(&d_short, sizeof(Seed) * (size_t)(32 * cap_short)));
+        CKC(cudaMemcpyAsync(d_ref, ref.data(), (size_t)total, cudaMemcpyHostToDevice, st));
+        CKC(cudaMemcpyAsync(d_off, offsets.data(), sizeof(int64_t) * (n_scaf + 1), cudaMemcpyHostToDevice, st));
+        CKC(cudaMemcpyAsync(d_blk, blk.data(), sizeof(int32_t) * n_blocks, cudaMemcpyHostToDevice, st));
+        CKC(cudaMemcpyAsync(d_skip, skips.data(), sizeof(int32_t) * n_scaf, cudaMemcpyHostToDevice, st));
+        ref_seed_kernel<<<(unsigned)n_blocks, TPB, 0, st>>>(d_ref, d_off, d_blk, d_skip, 1, total, p, d_full, d_cnt,
+                                                            d_short, d_cnt + 1, cap_short, d_cnt + 35);
+        (*launches)++;
+        CKC(cudaGetLastError());
+        CKC(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+        CKC(cudaStreamSynchronize(st));
+    }
+    ref_kmers = (int64_t)h_cnt[35];
+    const int64_t n_full = (int64_t)h_cnt[0];
+
+    // distances per class, as addToMap picks them (jgi/BBDuk.java:2366-2378)
+    auto class_dist = [&](int hd, int ed, int *use_extra) {
+        *use_extra = 0;
+        if (hd == 0) return 0;
+        if (ed > 0) {
+            *use_extra = 1;
+            return ed;
+        }
+        return hd;
+    };
+    const bool edits = p.editDistance > 0;
+    int ux_full = 0, ux_short = 0;
+    const int dist_full = class_dist(p.hammingDistance, p.editDistance, &ux_full);
+    const int dist_short = class_dist(p.hammingDistance2, p.editDistance2, &ux_short);
+
+    double bound = (double)n_full * ball_bound(p.k, dist_full, edits && dist_full > 0);
+    for (int n = 1; n < 32; n++) bound += (double)h_cnt[1 + n] * ball_bound(n, dist_short, edits && dist_short > 0);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    int64_t slots = pow2ceil((int64_t)(bound * 100.0 / load_pct) + 4);
+    while ((double)slots * 12.0 > 0.8 * (double)free_b && slots > 1024) slots >>= 1;
+    if (alloc(slots, filter_words, err, errlen)) {
+        cleanup();
+        return 1;
+    }
+    fill_kernel<<<1184, 256, 0, st>>>(d_keys, d_vals, slots);
+    (*launches)++;
+    CKC(cudaMemsetAsync(d_filter, 0, sizeof(uint32_t) * filter_words, st));
+
+    auto launch_expand = [&](const Seed *seeds, int64_t n, int len, int dist, int use_extra) -> int {
+        if (n <= 0) return 0;
+        const double nops = 4.0 * len + (edits ? 5.0 * (len - 1) : 0.0);
+        double n_prefix = 1;
+        for (int d = 1; d < dist; d++) n_prefix *= nops;
+        const double threads = (double)n * n_prefix;
+        // keep each launch below 2^31 blocks' worth of threads by slicing the seed list
+        const int64_t max_seeds = std::max<int64_t>(1, (int64_t)(4.0e9 / n_prefix));
+        for (int64_t s0 = 0; s0 < n; s0 += max_seeds) {
+            const int64_t ns = std::min(max_seeds, n - s0);
+            const int64_t nt = (int64_t)((double)ns * n_prefix);
+            const int64_t nb = (nt + 127) / 128;
+            expand_kernel<<<(unsigned)nb, 128, 0, st>>>(seeds + s0, ns, len, dist, use_extra, p, d_keys, d_vals,
+                                                        (uint64_t)slots - 1, d_cnt + 34, (int *)(d_cnt + 36));
+            (*launches)++;
+        }
+        (void)threads;
+        return 0;
+    };
+    launch_expand(d_full, n_full, p.k, dist_full, ux_full);
+    if (p.useShortKmers)
+        for (int n = p.k - 1; n >= p.mink && n >= 1; n--)
+            launch_expand(d_short + (int64_t)n * cap_short, (int64_t)h_cnt[1 + n], n, dist_short, ux_short);
+    CKC(cudaGetLastError());
+    CKC(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+    CKC(cudaStreamSynchronize(st));
+    stored = (int64_t)h_cnt[34];
+    if (h_cnt[36] != 0 || (double)stored > 0.9 * (double)slots) {
+        snprintf(err, errlen, "device hash array overfull (%lld keys in %lld slots)", (long long)stored, (long long)slots);
+        cleanup();
+        return 1;
+    }
+
+    // duplicates collapse heavily for adapter-like references: shrink to the requested load factor
+    const int64_t want = pow2ceil((int64_t)((double)stored * 100.0 / load_pct) + 4);
+    if (want < slots) {
+        uint64_t *nk = nullptr;
+        int32_t *nv = nullptr;
+        CKC(cudaMalloc(&nk, sizeof(uint64_t) * (size_t)want));
+        CKC(cudaMalloc(&nv, sizeof(int32_t) * (size_t)want));
+        fill_kernel<<<1184, 256, 0, st>>>(nk, nv, want);
+        rehash_kernel<<<1184, 256, 0, st>>>(d_keys, d_vals, slots, nk, nv, (uint64_t)want - 1, (int *)(d_cnt + 36));
+        (*launches) += 2;
+        CKC(cudaStreamSynchronize(st));
+        cudaFree(d_keys);
+        cudaFree(d_vals);
+        d_keys = nk;
+        d_vals = nv;
+        n_slots = want;
+    }
+    filter_build_kernel<<<1184, 256, 0, st>>>(d_keys, n_slots, d_filter, n_filter_words);
+    (*launches)++;
+    CKC(cudaGetLastError());
+    CKC(cudaStreamSynchronize(st));
+    cleanup();
+    return 0;
+#undef CKC
+}

@@ -1,0 +1,27 @@
+// table.h -- host-side owner of the device hash array (see table.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "params.h"
+
+struct DeviceTable {
+    uint64_t *d_keys = nullptr;
+    int32_t *d_vals = nullptr;
+    uint32_t *d_filter = nullptr;
+    int64_t n_slots = 0;
+    uint32_t n_filter_words = 0;
+    int32_t n_scaffolds = 0;
+    int64_t stored = 0;     // distinct keys ("Added N kmers", jgi/BBDuk.java:1973)
+    int64_t ref_kmers = 0;  // refKmers (jgi/BBDuk.java:1956)
+    bool owns = true;
+
+    int alloc(int64_t slots, uint32_t filter_words, char *err, int errlen);
+    void release();
+    BBTable view() const;
+    // ref = concatenated scaffolds (ids 1..n in order)
+    int build(const BBParams &p, const std::vector<uint8_t> &ref, const std::vector<int64_t> &offsets, int load_pct,
+              uint32_t filter_words, cudaStream_t st, int64_t *launches, char *err, int errlen);
+};

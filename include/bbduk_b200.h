@@ -25,6 +25,12 @@ extern "C" {
 
 #define BBDUK_B200_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define BBDUK_API __attribute__((visibility("default")))
+#else
+#define BBDUK_API
+#endif
+
 /* generation: which reference main class' derived-constant quirks to follow */
 #define BBDUK_GEN_JGI 0   /* jgi.BBDuk   (bbdukOld.sh): unset mink -> 6   (jgi/BBDuk.java:804) */
 #define BBDUK_GEN_S 1     /* bbduk.BBDukS (bbduk.sh)   : unset mink stays -1 (bbduk/BBDukParser.java:245) */
@@ -142,56 +148,70 @@ typedef struct bbduk_table_desc {
 typedef struct bbduk_handle bbduk_handle;
 
 /* Library/ABI version (BBDUK_B200_ABI_VERSION). */
-int bbduk_b200_version(void);
+BBDUK_API int bbduk_b200_version(void);
 
 /* Defaults of jgi.BBDuk's constructor (jgi/BBDuk.java:107-147, :4953-4977). */
-void bbduk_b200_cfg_default(bbduk_cfg *cfg);
+BBDUK_API void bbduk_b200_cfg_default(bbduk_cfg *cfg);
+
+/* The derived constants for a configuration, without touching the GPU (host logic; used by tests and by
+ * the Java side to print the reference's "maskMiddle was disabled" style notices). v[16] =
+ * {k, kbig, mink, useShortKmers, maskMiddle, midMaskLen, minlen, minlen2, minminlen, forbidNs,
+ *  hammingDistance, hammingDistance2, middleMask, mask, kfilter, removePairsIfEitherBad}. */
+BBDUK_API int bbduk_b200_describe_cfg(const bbduk_cfg *cfg, int64_t *v);
 
 /* Replaces: BBDuk constructor's constant derivation + index allocation
  * (jgi/BBDuk.java:583-877, :1017-1021; bbduk/BBDukLoader.java:35-76). */
-int bbduk_b200_create(const bbduk_cfg *cfg, bbduk_handle **out);
+BBDUK_API int bbduk_b200_create(const bbduk_cfg *cfg, bbduk_handle **out);
 
 /* Replaces: spawnLoadThreads' scaffold numbering + LoadThread.addToMap scan for a block of
  * reference sequences (jgi/BBDuk.java:1849-1863, :2210-2288). bases = concatenated ASCII,
  * offsets[n_seqs+1]. Scaffold ids continue from the previous call (first id 1). Host pointers. */
-int bbduk_b200_add_ref(bbduk_handle *h, const uint8_t *bases, const int64_t *offsets, int32_t n_seqs);
+BBDUK_API int bbduk_b200_add_ref(bbduk_handle *h, const uint8_t *bases, const int64_t *offsets, int32_t n_seqs);
 
 /* Replaces: the join of the LoadThreads ("Added N kmers", jgi/BBDuk.java:1945-1976): expands the
  * hdist/edist neighbourhoods and short-k-mer tails on the device and fills the hash array
  * (kmer.AbstractKmerTable.setIfNotPresent semantics: key -> smallest scaffold id). */
-int bbduk_b200_finalize(bbduk_handle *h, int64_t *stored_kmers);
+BBDUK_API int bbduk_b200_finalize(bbduk_handle *h, int64_t *stored_kmers);
 
 /* Replaces: the k-mer block of ProcessThread's per-pair loop for one batch of reads
  * (jgi/BBDuk.java:2727-2873 == bbduk/BBDukProcessorS.java:947-1093), including ktrim / ktrimTips /
  * kmask / ksplit / countSetKmers / countCoveredBases / findBestMatch / countSetKmersBig and
  * TrimRead.trimToPosition's coordinate rule. HOST buffers; copies to/from the device inside.
  * paired!=0: reads 2i and 2i+1 are mates (pairnum 0 / 1). stats may be NULL. */
-int bbduk_b200_process(bbduk_handle *h, const uint8_t *bases, const int64_t *offsets, int64_t n_reads,
+BBDUK_API int bbduk_b200_process(bbduk_handle *h, const uint8_t *bases, const int64_t *offsets, int64_t n_reads,
                        int32_t paired, const bbduk_out *out, bbduk_stats *stats);
 
 /* Same, on DEVICE buffers (bases, 32-bit offsets[n_reads+1], outputs), asynchronous on `stream`
  * (a cudaStream_t, NULL = default stream). total bases < 4 GiB per call. d_stats: device
  * bbduk_stats to accumulate into, may be NULL. */
-int bbduk_b200_process_device(bbduk_handle *h, const uint8_t *d_bases, const uint32_t *d_offsets,
+BBDUK_API int bbduk_b200_process_device(bbduk_handle *h, const uint8_t *d_bases, const uint32_t *d_offsets,
                               int64_t n_reads, int32_t paired, const bbduk_out *d_out,
                               bbduk_stats *d_stats, void *stream);
 
 /* Per-scaffold hit accounting accumulated on the device by process calls, index 0..n_scaffolds
  * (replaces scaffoldReadCounts/scaffoldBaseCounts, jgi/BBDuk.java:1968-1969, :3984-3992). */
-int bbduk_b200_scaffold_counts(bbduk_handle *h, int64_t *read_counts, int64_t *base_counts, int32_t n);
+BBDUK_API int bbduk_b200_scaffold_counts(bbduk_handle *h, int64_t *read_counts, int64_t *base_counts, int32_t n);
 
 /* Table replication across GPUs: rank 0 describes its table; other ranks allocate the same
  * geometry with _table_alloc, receive the three blobs (NCCL broadcast done by the caller on the
  * returned device pointers), then _table_commit. */
-int bbduk_b200_table_describe(bbduk_handle *h, bbduk_table_desc *desc);
-int bbduk_b200_table_alloc(bbduk_handle *h, bbduk_table_desc *desc /* in: geometry+scalars; out: pointers */);
-int bbduk_b200_table_commit(bbduk_handle *h);
+BBDUK_API int bbduk_b200_table_describe(bbduk_handle *h, bbduk_table_desc *desc);
+BBDUK_API int bbduk_b200_table_alloc(bbduk_handle *h, bbduk_table_desc *desc /* in: geometry+scalars; out: pointers */);
+BBDUK_API int bbduk_b200_table_commit(bbduk_handle *h);
 
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
-int64_t bbduk_b200_launch_count(bbduk_handle *h);
+BBDUK_API int64_t bbduk_b200_launch_count(bbduk_handle *h);
 
-const char *bbduk_b200_last_error(bbduk_handle *h);
-void bbduk_b200_destroy(bbduk_handle *h);
+/* Bench/test helper (no reference counterpart; the reference's generators need a JVM): fills DEVICE
+ * buffers with n_pairs interleaved synthetic 2 x read_len bp pairs with adapter read-through, the
+ * cfg-2 workload of SURVEY.md 8d. bases: 2*n_pairs*read_len bytes; offsets: 2*n_pairs+1 words.
+ * Byte-identical to bbtools_b200/synth.py:paired_adapter_reads. */
+BBDUK_API int bbduk_b200_synth_pairs(uint8_t *d_bases, uint32_t *d_offsets, int64_t n_pairs, int64_t first_pair,
+                                     int32_t read_len, uint64_t seed, int32_t sub_per_10k, int32_t n_per_10k,
+                                     void *stream);
+
+BBDUK_API const char *bbduk_b200_last_error(bbduk_handle *h);
+BBDUK_API void bbduk_b200_destroy(bbduk_handle *h);
 
 #ifdef __cplusplus
 }

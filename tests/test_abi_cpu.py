@@ -1,0 +1,115 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol the header declares,
+derives the same constants as the oracle, and refuses to run without a GPU (no CPU fallback)."""
+import ctypes as C
+import itertools
+import os
+import re
+
+import numpy as np
+import pytest
+
+from bbtools_b200 import _lib, make_cfg
+from bbtools_b200._abi import BBDukCfg
+from bbtools_b200.bbduk import parse_args
+from oracle.oracle import Oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "bbduk_b200.h")).read()
+    return sorted(set(re.findall(r"BBDUK_API[^;(]*?\b(bbduk_b200_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = header_symbols()
+    assert len(names) >= 16
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/bbduk_b200.h but not exported"
+    assert sorted(s[0] for s in _lib.SYMBOLS) == names  # the binding covers the header exactly
+    assert lib.bbduk_b200_version() == 1
+
+
+def test_cfg_struct_layout_matches_header():
+    lib = _lib.load()
+    c = BBDukCfg()
+    lib.bbduk_b200_cfg_default(C.byref(c))
+    assert c.struct_size == C.sizeof(BBDukCfg)
+    ref = make_cfg()
+    for name, _ in BBDukCfg._fields_:
+        if name != "reserved":
+            assert getattr(c, name) == getattr(ref, name), name
+
+
+def describe(cfg):
+    lib = _lib.load()
+    v = np.zeros(16, np.int64)
+    rc = lib.bbduk_b200_describe_cfg(C.byref(cfg), v.ctypes.data)
+    if rc:
+        raise ValueError(lib.bbduk_b200_last_error(None).decode())
+    names = ["k", "kbig", "mink", "useShortKmers", "maskMiddle", "midMaskLen", "minlen", "minlen2", "minminlen",
+             "forbidNs", "hdist", "hdist2", "middleMask", "mask", "kfilter", "rieb"]
+    return dict(zip(names, (int(x) for x in v)))
+
+
+def test_derived_constants_match_oracle():
+    ks = [1, 5, 11, 12, 23, 27, 31, 32, 40, 0]
+    minks = [-1, 4, 11, 31]
+    modes = [dict(), dict(ktrim_right=1), dict(ktrim_left=1, ktrim_right=1), dict(ktrim_n=1), dict(ksplit=1)]
+    n = 0
+    for k, mink, mode, hd, mm, gen in itertools.product(ks, minks, modes, (0, 1, 2), (0, 1), (0, 1)):
+        for extra in (dict(), dict(mid_mask_len=3), dict(edist=1), dict(hdist2=0, forbid_ns=1, require_both_bad=1)):
+            cfg = make_cfg(k=k, mink=mink, hdist=hd, mask_middle=mm, generation=gen, **mode, **extra)
+            try:
+                want = Oracle(cfg).derived()
+            except ValueError:
+                with pytest.raises(ValueError):
+                    describe(cfg)
+                continue
+            if gen == 1 and mink == -1 and mode and want["useShortKmers"]:
+                continue
+            got = describe(cfg)
+            assert got == want, (k, mink, mode, hd, mm, gen, extra)
+            n += 1
+    assert n > 2000
+
+
+def test_parse_args_mirrors_reference_flags():
+    cfg, io = parse_args("in=a.fq in2=b.fq out=c.fq ref=adapters ktrim=r k=23 mink=11 hdist=1 tpe".split())
+    assert (cfg.ktrim_right, cfg.ktrim_left, cfg.k, cfg.mink, cfg.hdist, cfg.trim_pairs_evenly) == (1, 0, 23, 11, 1, 1)
+    assert io["ref"] == ["adapters"] and io["in2"] == "b.fq"
+    cfg, _ = parse_args(["ktrim=rl", "mm=f", "mkh=3", "rieb=f", "minlen=25", "mlf=0.5"])
+    assert cfg.ktrim_left and cfg.ktrim_right and not cfg.mask_middle and cfg.max_bad_kmers == 2
+    assert cfg.require_both_bad == 1 and cfg.min_read_length == 25 and abs(cfg.min_len_fraction - 0.5) < 1e-7
+    cfg, _ = parse_args(["kmask=lc"])
+    assert cfg.ktrim_n and cfg.kmask_lowercase
+    cfg, _ = parse_args(["ktrim=X"])
+    assert cfg.ktrim_n and cfg.trim_symbol == ord("X")
+    cfg, _ = parse_args(["ktrimtips=40"])
+    assert cfg.ktrim_left and cfg.ktrim_right and cfg.restrict_left == 40 and cfg.restrict_right == 40
+    cfg, _ = parse_args(["mm=3"])
+    assert cfg.mid_mask_len == 3 and cfg.mask_middle
+    with pytest.raises(ValueError):
+        parse_args(["nosuchflag=1"])
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device create() must fail loudly, never compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _lib.load()
+    h = C.c_void_p()
+    cfg = make_cfg(k=23, ktrim_right=1)
+    rc = lib.bbduk_b200_create(C.byref(cfg), C.byref(h))
+    assert rc != 0 and not h.value
+    assert b"no CUDA device" in lib.bbduk_b200_last_error(None)
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "bbtools_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in text.lower() or f in ("synth.py",), f"{f} mentions the oracle"
