@@ -91,11 +91,13 @@ __device__ __forceinline__ int bb_table_put(uint64_t *keys, int32_t *vals, uint6
 }
 
 // ---- blocked bloom pre-filter over all keys (no false negatives) ----------------------------------
-// word index and a 3-bit pattern from one 64-bit hash; the same function builds and queries.
-__device__ __forceinline__ uint32_t bb_filter_word(uint64_t h, uint32_t n_words) {
-    return __umulhi((uint32_t)(h >> 32), n_words);
-}
-__device__ __forceinline__ uint32_t bb_filter_bits(uint64_t h) {
-    const uint32_t x = (uint32_t)h;
-    return (1u << (x & 31)) | (1u << ((x >> 5) & 31)) | (1u << ((x >> 10) & 31));
+// One 32-bit hash t of the key picks the filter word (high bits, multiply-shift range reduction) and
+// a 4-bit pattern: two 2-bit stencils rotated by two independent 5-bit fields of t (funnel shifts use
+// the shift amount mod 32, so no masking is needed). The same functions build and query the filter.
+#define BB_FPAT1 0x00000081u
+#define BB_FPAT2 0x00002001u
+__device__ __forceinline__ uint32_t bb_fhash(uint32_t klo, uint32_t khi) { return klo * 0x9E3779B1u + khi * 0x85EBCA77u; }
+__device__ __forceinline__ uint32_t bb_filter_word(uint32_t t, uint32_t n_words) { return __umulhi(t, n_words); }
+__device__ __forceinline__ uint32_t bb_filter_bits(uint32_t t) {
+    return __funnelshift_l(BB_FPAT1, BB_FPAT1, t) | __funnelshift_l(BB_FPAT2, BB_FPAT2, t >> 5);
 }

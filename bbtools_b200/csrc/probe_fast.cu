@@ -1,10 +1,611 @@
-// probe_fast.cu -- placeholder until the tuned kernel lands: reports "not usable" so every batch takes
-// the generic kernel.
+// probe_fast.cu -- the tuned per-read kernel for the common BBDuk configurations on sm_100a.
+//
+// Covers ktrim=r, ktrim=l and kfilter (countSetKmers) with qhdist=0, speed=0, qskip=1, no
+// restrictleft/right, k<=31, minkmerfraction=0; everything else, and any tile of reads that does not
+// fit the staging, is handed to probe_generic.cu. Results are identical by construction: this kernel
+// only decides WHICH read positions can possibly hit (an on-chip blocked-bloom image of all table
+// keys, no false negatives) and then evaluates those positions with the exact key formula and the
+// exact hash array, in the reference's scan order.
+//
+// Per warp, per tile of 32 consecutive reads (one lane per read; mates are neighbouring lanes):
+//   A. the tile's contiguous ASCII bytes are read once with coalesced 16-byte loads and converted
+//      to a 2-bit big-endian stream F (+ 1 bit/base "defined" stream D) in shared memory;
+//   B. each lane walks its read 16 positions at a time; forward k-mer and reverse-complement k-mer
+//      come from funnel shifts of the packed stream with compile-time shift amounts, then
+//      canonical max -> middle mask -> 32-bit hash -> one shared-memory filter word -> bit test;
+//      survivors are recorded as candidate bits;
+//   C. candidates (and every window that touches an undefined base) are evaluated exactly, in scan
+//      order, against the hash array in L2/HBM; short-k-mer tails run when nothing was found;
+//   D. trim arithmetic (TrimRead rules), minlen, pair logic (rieb, tpe) via lane shuffles, coalesced
+//      result stores, warp-aggregated counters.
+// Rolling-state semantics follow jgi/BBDuk.java:3882-3900 in the closed form of SURVEY.md A.2.
+#include <algorithm>
+
+#include "bbduk_dev.cuh"
 #include "probe.h"
 
-FastPlan plan_fast(const BBParams &, const BBTable &, int) { return FastPlan{false, 0, 0, 0}; }
-int launch_fast(const FastPlan &, const uint8_t *, const uint32_t *, int64_t, int, const BBParams &, const BBTable &,
-                const bbduk_out &, bbduk_stats *, unsigned long long *, unsigned long long *, int32_t *, unsigned int *,
-                int, cudaStream_t) {
-    return -1;
+namespace {
+
+constexpr int PAD = 2;           // zero chunks in front of the staged stream (windows reach back 32 bases)
+constexpr int TAIL = 4;          // zero chunks behind it (the reverse-strand words run two steps ahead)
+constexpr int MAX_FAST_LEN = 1008;
+constexpr int FAST_SMEM_LIMIT = 227 * 1024;
+
+struct FastGeom {
+    int warps;        // warps per block
+    int nch;          // staged 16-base chunks per warp (capacity, without padding)
+    int cwords;       // candidate halfwords per lane (= 16-position steps)
+    int warp_bytes;   // shared memory per warp
+    uint32_t nfw;     // filter words
+};
+
+__device__ __forceinline__ uint32_t pair_reverse_complement(uint32_t x) {
+    // big-endian 16 bases -> little-endian complemented 16 bases
+    uint32_t r = __brev(~x);
+    return ((r & 0x55555555u) << 1) | ((r >> 1) & 0x55555555u);
+}
+
+// 4 ASCII bases (byte 0 first) -> raw 2-bit codes in each byte's low bits, and "bad" (non-zero byte
+// <=> the base is not one of ACGTUacgtu). Exact, see the bit derivation in DESIGN.md.
+__device__ __forceinline__ void classify4(uint32_t w, uint32_t &codes, uint32_t &bad) {
+    codes = ((w >> 1) ^ (w >> 2)) & 0x03030303u;
+    const uint32_t d = (w | 0x20202020u) ^ 0x61616161u;
+    const uint32_t q = (d >> 2) & ~(d >> 1) & 0x01010101u;           // t/u class: bits(2,1) == 10
+    bad = (d & 0xE8E8E8E8u) | (((d >> 4) ^ q) & 0x01010101u) | (d & ~q & 0x01010101u);
+}
+__device__ __forceinline__ uint32_t pack4(uint32_t codes) { return (codes * 0x40100401u) >> 24; }  // big-endian 8 bits
+__device__ __forceinline__ uint32_t valid4(uint32_t bad) {                                           // 4 bits, base 0 in bit 3
+    const uint32_t nz = (((bad & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | bad) & 0x80808080u;
+    return (((nz ^ 0x80808080u) >> 7) * 0x08040201u) >> 24;
+}
+
+struct Stream {
+    const uint32_t *F;  // big-endian 2-bit codes, 16 bases per word, index PAD = first chunk
+    const uint16_t *D;  // defined bits, bit 15-b = base b of the chunk
+    // 16 bases starting at stream base g, big-endian
+    __device__ __forceinline__ uint32_t f16(int g) const {
+        const int w = (g >> 4) + PAD;
+        return __funnelshift_l(F[w + 1], F[w], (g & 15) * 2);
+    }
+    __device__ __forceinline__ uint32_t d16(int g) const {  // bit 15-b = base g+b
+        const int w = (g >> 4) + PAD;
+        const uint32_t x = ((uint32_t)D[w] << 16) | D[w + 1];
+        return (x >> (16 - (g & 15))) & 0xFFFFu;
+    }
+    // defined bits of the 32 bases ending at stream base e: bit t = base e-t
+    __device__ __forceinline__ uint32_t dwin(int e) const {
+        const uint32_t be = (d16(e - 31) << 16) | d16(e - 15);  // bit 31-b = base e-31+b  => bit t = base e-t
+        return be;
+    }
+    // 2-bit codes of the 32 bases ending at stream base e: slot t (bits 2t+1,2t) = base e-t
+    __device__ __forceinline__ uint64_t win(int e) const { return ((uint64_t)f16(e - 31) << 32) | f16(e - 15); }
+};
+
+__device__ __forceinline__ uint64_t spread2(uint32_t m) {  // bit t -> bits (2t+1, 2t)
+    uint64_t x = m;
+    x = (x | (x << 16)) & 0x0000FFFF0000FFFFull;
+    x = (x | (x << 8)) & 0x00FF00FF00FF00FFull;
+    x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    x = (x | (x << 2)) & 0x3333333333333333ull;
+    x = (x | (x << 1)) & 0x5555555555555555ull;
+    return x | (x << 1);
+}
+// reverse the order of the low `n` 2-bit slots (no complement)
+__device__ __forceinline__ uint64_t rev2(uint64_t x, int n) { return bb_rcomp(~x, n); }
+
+// exact id of the full-length probe at read position i (stream base e = s+i), -1 if none / no probe.
+// Handles undefined bases exactly: kmer keeps code 0 for them and is never reset;
+// with forbidNs the reverse k-mer only holds bases after the last undefined one and the probe needs
+// len >= minlen2.
+__device__ __forceinline__ int exact_full(const Stream &st, int e, const BBParams &p, const BBTable &t) {
+    const int k = p.k;
+    uint64_t kmer = st.win(e) & p.mask;
+    const uint32_t dw = st.dwin(e);
+    const uint32_t kbits = (k >= 32) ? 0xFFFFFFFFu : ((1u << k) - 1u);
+    uint64_t rkmer;
+    if ((dw & kbits) == kbits) {
+        rkmer = bb_rcomp(kmer, k);
+    } else {
+        const uint64_t E = spread2(dw & kbits);
+        kmer &= E;
+        if (p.forbidNs) {
+            const int len = __ffs(~dw) - 1;  // bases after the last undefined one (window has one)
+            if (len < p.minlen2) return -1;
+            rkmer = bb_rcomp(kmer, k) & ~((1ull << (2 * (k - len))) - 1ull) & p.mask;
+        } else {
+            rkmer = bb_rcomp(kmer, k) & rev2(E, k);
+        }
+    }
+    return bb_table_get(t, bb_to_value(p, kmer, rkmer, p.kmask));
+}
+
+__device__ __forceinline__ bool filter_pass(const uint32_t *filt, uint32_t nfw, uint64_t key) {
+    const uint32_t tt = bb_fhash((uint32_t)key, (uint32_t)(key >> 32));
+    const uint32_t pat = bb_filter_bits(tt);
+    return (filt[bb_filter_word(tt, nfw)] & pat) == pat;
+}
+
+__device__ __forceinline__ int mid3(int x, int y, int z) { return max(min(x, y), min(max(x, y), z)); }
+
+// shared/TrimRead.java:299-346 on a kept interval
+__device__ __forceinline__ int trim_amounts(int &lo, int &hi, int left, int right, int minLen) {
+    left = max(left, 0);
+    right = max(right, 0);
+    const int len = hi - lo;
+    if (len < 1) return 0;
+    minLen = min(len, max(minLen, 0));
+    if (left + right + minLen > len) {
+        right = max(1, len - minLen);
+        left = 0;
+    }
+    lo += left;
+    hi -= right;
+    return left + right;
+}
+
+enum { FM_KTRIM_R = 0, FM_KTRIM_L = 1, FM_KFILTER = 2 };
+
+template <int FMODE, bool USE_FILTER>
+__global__ void __launch_bounds__(1024, 1)
+bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ offsets, int64_t n_reads, int paired,
+                  BBParams p, BBTable t, bbduk_out out, bbduk_stats *stats, unsigned long long *scaf_reads,
+                  unsigned long long *scaf_bases, int32_t *handoff, unsigned int *handoff_n, FastGeom geo) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t *filt = smem;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *wbase = reinterpret_cast<uint8_t *>(smem + (USE_FILTER ? geo.nfw : 0)) + (size_t)warp * geo.warp_bytes;
+    uint32_t *Fs = reinterpret_cast<uint32_t *>(wbase);
+    uint16_t *Ds = reinterpret_cast<uint16_t *>(Fs + geo.nch + PAD + TAIL);
+    uint16_t *cand = Ds + ((geo.nch + PAD + TAIL + 1) & ~1);  // [cwords][32]
+
+    if (USE_FILTER) {
+        for (uint32_t i = threadIdx.x; i < geo.nfw; i += blockDim.x) filt[i] = __ldg(t.filter + i);
+    }
+    for (int i = lane; i < PAD; i += 32) {
+        Fs[i] = 0;
+        Ds[i] = 0;
+    }
+    __syncthreads();
+
+    const Stream st{Fs, Ds};
+    const int k = p.k;
+    const uint32_t mask_hi = (uint32_t)(p.mask >> 32), mask_lo = (uint32_t)p.mask;
+    const uint32_t mm_hi = (uint32_t)(p.middleMask >> 32), mm_lo = (uint32_t)p.middleMask;
+    const uint32_t km_hi = (uint32_t)(p.kmask >> 32), km_lo = (uint32_t)p.kmask;
+    const uintptr_t base_addr = reinterpret_cast<uintptr_t>(bases);
+    const int64_t n_tiles = (n_reads + 31) >> 5;
+    const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+    long long s_rk = 0, s_bk = 0, s_rf = 0, s_bf = 0, s_ro = 0, s_bo = 0, s_ri = 0, s_bi = 0;
+
+    for (int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; tile < n_tiles; tile += warps_total) {
+        const int64_t r = tile * 32 + lane;
+        const bool live = r < n_reads;
+        const uint32_t o0 = live ? offsets[r] : 0, o1 = live ? offsets[r + 1] : 0;
+        const uint32_t tile_lo = __shfl_sync(0xFFFFFFFFu, o0, 0);
+        const int last_lane = (int)min((long long)31, (long long)(n_reads - 1 - tile * 32));
+        const uint32_t tile_hi = __shfl_sync(0xFFFFFFFFu, o1, last_lane);
+        const uintptr_t a0 = (base_addr + tile_lo) & ~(uintptr_t)15;
+        const int nchunks = (int)((base_addr + tile_hi - a0 + 15) >> 4);
+        const int L = (int)(o1 - o0);
+        const int maxL = __reduce_max_sync(0xFFFFFFFFu, L);
+        if (nchunks > geo.nch || maxL > (geo.cwords - 1) * 16) {
+            // tile does not fit the staging: hand its units to the generic kernel
+            if (live && (!paired || !(lane & 1))) {
+                const unsigned int w = atomicAdd(handoff_n, 1u);
+                handoff[w] = (int32_t)(paired ? (r >> 1) : r);
+            }
+            continue;
+        }
+        // ---- A. stage + convert ---------------------------------------------------------------
+        __syncwarp();
+        for (int c = lane; c < nchunks + TAIL; c += 32) {
+            uint32_t f = 0, dbits = 0;
+            const bool in = c < nchunks;
+            uint32_t cw[4], bw[4];
+            if (in) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(a0) + c);
+                classify4(v.x, cw[0], bw[0]);
+                classify4(v.y, cw[1], bw[1]);
+                classify4(v.z, cw[2], bw[2]);
+                classify4(v.w, cw[3], bw[3]);
+            } else {
+                cw[0] = cw[1] = cw[2] = cw[3] = 0;
+                bw[0] = bw[1] = bw[2] = bw[3] = 0;
+            }
+            const bool anybad = (bw[0] | bw[1] | bw[2] | bw[3]) != 0;
+            f = (pack4(cw[0]) << 24) | (pack4(cw[1]) << 16) | (pack4(cw[2]) << 8) | pack4(cw[3]);
+            dbits = 0xFFFFu;
+            if (__any_sync(__activemask(), anybad)) {
+                if (anybad) dbits = (valid4(bw[0]) << 12) | (valid4(bw[1]) << 8) | (valid4(bw[2]) << 4) | valid4(bw[3]);
+            }
+            if (!in) dbits = 0;
+            Fs[c + PAD] = f;
+            Ds[c + PAD] = (uint16_t)dbits;
+        }
+        __syncwarp();
+
+        // ---- B. per-lane scan ------------------------------------------------------------------
+        const int s = (int)(base_addr + o0 - a0);  // stream base of read position 0
+        const int nsteps = (L + 15) >> 4;
+        bool has_undef = false;
+        {
+            // bases outside [s, s+L) belong to neighbours; only this read's bits count
+            for (int j = 0; j < nsteps; j++) {
+                uint32_t dd = st.d16(s + 16 * j);
+                const int rem = L - 16 * j;
+                if (rem < 16) dd |= (0xFFFFu >> rem);
+                has_undef |= (dd != 0xFFFFu);
+            }
+        }
+        const bool scan = live && L >= k && t.stored > 0 &&
+                          !((p.skipR1 && !(paired && (lane & 1))) || (p.skipR2 && paired && (lane & 1)));
+        const int max_steps = (maxL + 15) >> 4;
+        for (int j = 0; j < max_steps; j++) cand[j * 32 + lane] = 0;
+        if (scan) {
+            // sliding registers: f_m2,f_m1,f_0 = read words j-2,j-1,j (big-endian);
+            // r_0,r_1,r_2 = complemented little-endian words of bases starting at 16j-(k-1)
+            uint32_t f_m2 = 0, f_m1 = 0, f_0;
+            uint32_t r_0 = pair_reverse_complement(st.f16(s - (k - 1))), r_1 = pair_reverse_complement(st.f16(s + 16 - (k - 1))), r_2;
+            for (int j = 0; j < nsteps; j++) {
+                f_0 = st.f16(s + 16 * j);
+                r_2 = pair_reverse_complement(st.f16(s + 16 * (j + 2) - (k - 1)));
+                uint32_t cbits = 0;
+#pragma unroll
+                for (int b = 0; b < 16; b++) {
+                    const int sh = 2 * (15 - b);
+                    uint32_t klo = __funnelshift_r(f_0, f_m1, sh) & mask_lo;
+                    uint32_t khi = __funnelshift_r(f_m1, f_m2, sh) & mask_hi;
+                    if (p.rcomp) {
+                        const uint32_t rlo = __funnelshift_r(r_0, r_1, 2 * b) & mask_lo;
+                        const uint32_t rhi = __funnelshift_r(r_1, r_2, 2 * b) & mask_hi;
+                        const bool gt = (rhi > khi) || (rhi == khi && rlo > klo);
+                        klo = gt ? rlo : klo;
+                        khi = gt ? rhi : khi;
+                    }
+                    klo = (klo & mm_lo) | km_lo;
+                    khi = (khi & mm_hi) | km_hi;
+                    bool pass;
+                    if (USE_FILTER) {
+                        const uint32_t tt = bb_fhash(klo, khi);
+                        const uint32_t pat = bb_filter_bits(tt);
+                        pass = (filt[bb_filter_word(tt, geo.nfw)] & pat) == pat;
+                    } else {
+                        pass = true;
+                    }
+                    cbits |= pass ? (1u << b) : 0u;
+                }
+                // keep positions k-1 <= i < L
+                const int i0 = 16 * j;
+                uint32_t vm = 0xFFFFu;
+                if (i0 < k - 1) vm &= (k - 1 - i0 >= 16) ? 0u : (0xFFFFu << (k - 1 - i0));
+                if (L - i0 < 16) vm &= (1u << (L - i0)) - 1u;
+                cand[j * 32 + lane] = (uint16_t)(cbits & vm);
+                f_m2 = f_m1;
+                f_m1 = f_0;
+                r_0 = r_1;
+                r_1 = r_2;
+            }
+            if (has_undef) {
+                // every window that contains an undefined base is decided by the exact evaluator
+                for (int j = 0; j < nsteps; j++) {
+                    uint32_t dd = st.d16(s + 16 * j);
+                    const int rem = L - 16 * j;
+                    if (rem < 16) dd |= (0xFFFFu >> rem);
+                    uint32_t und = (~dd) & 0xFFFFu;  // bit 15-b = base 16j+b undefined
+                    while (und) {
+                        const int b = 15 - (31 - __clz(und));
+                        und &= ~(1u << (15 - b));
+                        const int pu = 16 * j + b;
+                        const int from = max(pu, k - 1), to = min(pu + k - 1, L - 1);
+                        for (int i = from; i <= to; i++) cand[(i >> 4) * 32 + lane] |= (uint16_t)(1u << (i & 15));
+                    }
+                }
+            }
+        }
+
+        // ---- C. exact evaluation in scan order ---------------------------------------------------
+        int found = 0, id0 = -1, minLoc = 999999999, maxLoc = -1, count = 0;
+        int lo = 0, hi = L;
+        bool discarded = false, ktrimmed = false;
+        if (scan) {
+            if (FMODE == FM_KTRIM_R) {
+                for (int j = 0; j < nsteps && !found; j++) {
+                    uint32_t cb = cand[j * 32 + lane];
+                    while (cb) {
+                        const int b = __ffs(cb) - 1;
+                        cb &= cb - 1;
+                        const int i = 16 * j + b;
+                        const int id = exact_full(st, s + i, p, t);
+                        if (id > 0) {
+                            id0 = id;
+                            minLoc = i - k + 1;
+                            maxLoc = i;
+                            found = 1;
+                            break;
+                        }
+                    }
+                }
+            } else if (FMODE == FM_KTRIM_L) {
+                for (int j = 0; j < nsteps && !found; j++) {  // first hit: id0
+                    uint32_t cb = cand[j * 32 + lane];
+                    while (cb) {
+                        const int b = __ffs(cb) - 1;
+                        cb &= cb - 1;
+                        const int i = 16 * j + b;
+                        const int id = exact_full(st, s + i, p, t);
+                        if (id > 0) {
+                            id0 = id;
+                            minLoc = i - k + 1;
+                            maxLoc = i;
+                            found = 1;
+                            break;
+                        }
+                    }
+                }
+                if (found) {  // last hit: maxLoc
+                    bool done = false;
+                    for (int j = nsteps - 1; j >= 0 && !done; j--) {
+                        uint32_t cb = cand[j * 32 + lane];
+                        while (cb) {
+                            const int b = 31 - __clz(cb);
+                            cb &= ~(1u << b);
+                            const int i = 16 * j + b;
+                            if (i <= maxLoc) {
+                                done = true;
+                                break;
+                            }
+                            if (exact_full(st, s + i, p, t) > 0) {
+                                maxLoc = i;
+                                done = true;
+                                break;
+                            }
+                        }
+                    }
+                }
+            } else {  // FM_KFILTER: countSetKmers, jgi/BBDuk.java:3395-3457
+                const int mb = p.maxBadKmers0;
+                bool stop = false;
+                for (int j = 0; j < nsteps && !stop; j++) {
+                    uint32_t cb = cand[j * 32 + lane];
+                    while (cb) {
+                        const int b = __ffs(cb) - 1;
+                        cb &= cb - 1;
+                        const int id = exact_full(st, s + 16 * j + b, p, t);
+                        if (id > 0) {
+                            if (found == mb) {
+                                id0 = id;
+                                found++;
+                                stop = true;
+                                break;
+                            }
+                            found++;
+                        }
+                    }
+                }
+                count = found;
+                if (count > mb) discarded = true;
+            }
+        }
+        if (FMODE != FM_KFILTER) {
+            // ktrim guard (jgi/BBDuk.java:3868): reads shorter than k still get the short-k-mer tails
+            const bool tscan = live && t.stored > 0 && p.useShortKmers && L >= max(1, min(k, p.mink)) && !found &&
+                               !((p.skipR1 && !(paired && (lane & 1))) || (p.skipR2 && paired && (lane & 1)));
+            int minLocX = 999999999, maxLocX = -1;
+            if (found) {
+                minLocX = minLoc + k;
+                maxLocX = maxLoc - k;
+            }
+            if (tscan) {
+                uint64_t kmer = 0, rkmer = 0;
+                if (FMODE == FM_KTRIM_R) {  // suffixes, growing leftwards (:3945-3975)
+                    const int nmax = min(k - 1, L);
+                    for (int n = 1; n <= nmax; n++) {
+                        const int i = L - n;
+                        const int e = s + i;
+                        const uint32_t w = Fs[(e >> 4) + PAD];
+                        const bool def = (Ds[(e >> 4) + PAD] >> (15 - (e & 15))) & 1;
+                        const uint32_t c = def ? ((w >> (2 * (15 - (e & 15)))) & 3u) : 0u;
+                        kmer |= (uint64_t)c << (2 * (n - 1));
+                        rkmer = ((rkmer << 2) | (def ? (3u - c) : 0u)) & p.mask;
+                        if (n >= p.mink) {
+                            const uint64_t key = bb_to_value(p, kmer, rkmer, 1ull << (2 * n));
+                            if (!USE_FILTER || filter_pass(filt, geo.nfw, key)) {
+                                const int id = bb_table_get(t, key);
+                                if (id > 0) {
+                                    if (id0 < 0) id0 = id;
+                                    minLoc = i;
+                                    minLocX = min(minLocX, L);
+                                    maxLoc = L - 1;
+                                    maxLocX = max(maxLocX, i - 1);
+                                    found++;
+                                }
+                            }
+                        }
+                    }
+                } else {  // prefixes, growing rightwards (:3910-3942)
+                    const int lim = min(k, L);
+                    for (int i = 0; i < lim; i++) {
+                        const int e = s + i;
+                        const uint32_t w = Fs[(e >> 4) + PAD];
+                        const bool def = (Ds[(e >> 4) + PAD] >> (15 - (e & 15))) & 1;
+                        const uint32_t c = def ? ((w >> (2 * (15 - (e & 15)))) & 3u) : 0u;
+                        kmer = ((kmer << 2) | c) & p.mask;
+                        rkmer |= (uint64_t)(def ? (3u - c) : 0u) << (2 * i);
+                        const int n = i + 1;
+                        if (n >= p.mink) {
+                            const uint64_t key = bb_to_value(p, kmer, rkmer, 1ull << (2 * n));
+                            if (!USE_FILTER || filter_pass(filt, geo.nfw, key)) {
+                                const int id = bb_table_get(t, key);
+                                if (id > 0) {
+                                    if (id0 < 0) id0 = id;
+                                    minLoc = 0;
+                                    minLocX = min(minLocX, i + 1);
+                                    maxLoc = max(maxLoc, i);
+                                    maxLocX = max(maxLocX, 0);
+                                    found++;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            if (found) {  // :3981-4012
+                if (p.trimPad != 0) {
+                    maxLoc = mid3(0, maxLoc + p.trimPad, L);
+                    minLoc = mid3(0, minLoc - p.trimPad, L);
+                    maxLocX = mid3(0, maxLocX + p.trimPad, L);
+                    minLocX = mid3(0, minLocX - p.trimPad, L);
+                }
+                if (FMODE == FM_KTRIM_L) {
+                    const int leftLoc = p.ktrimExclusive ? maxLocX + 1 : maxLoc + 1;
+                    count = trim_amounts(lo, hi, leftLoc, L - (L - 1) - 1, 1);
+                } else {
+                    const int rightLoc = p.ktrimExclusive ? minLocX - 1 : minLoc - 1;
+                    count = trim_amounts(lo, hi, 0, L - rightLoc - 1, 1);
+                }
+                ktrimmed = count > 0;
+            }
+        }
+        if (live && id0 > 0 && scaf_reads) {
+            atomicAdd(scaf_reads + id0, 1ull);
+            atomicAdd(scaf_bases + id0, (unsigned long long)L);
+        }
+
+        // ---- D. per-read minlen, pair logic (jgi/BBDuk.java:2750-2813, :2844-2871), outputs ------
+        const bool active = live && t.stored > 0;  // doKmerTrimming / doKmerFiltering need stored k-mers
+        const int minlenR = (int)fmaxf(__fmul_rn((float)L, p.minLenFraction), (float)p.minReadLength);
+        const int len_pre = hi - lo;  // rlen1 / rlen2: captured before setDiscarded
+        if (active && (FMODE == FM_KFILTER ? discarded : (len_pre < minlenR))) {
+            // setDiscarded (jgi/BBDuk.java:3260-3266)
+            if (p.trimFailuresTo1bp) {
+                discarded = false;
+                if (hi - lo > 1) trim_amounts(lo, hi, 0, hi - lo - 1, 1);
+            } else {
+                discarded = true;
+            }
+        }
+        int len_cur = hi - lo;
+        const bool disc_eff = discarded || (p.trimFailuresTo1bp && len_cur == 1);
+        const bool disc_mate = __shfl_xor_sync(0xFFFFFFFFu, (int)disc_eff, 1) != 0;
+        const int len_pre_mate = __shfl_xor_sync(0xFFFFFFFFu, len_pre, 1);
+        const int len_cur_mate = __shfl_xor_sync(0xFFFFFFFFu, len_cur, 1);
+        const int cnt_mate = __shfl_xor_sync(0xFFFFFFFFu, count, 1);
+        const int L_mate = __shfl_xor_sync(0xFFFFFFFFu, L, 1);
+        const bool remove = paired ? (p.removePairsIfEitherBad ? (disc_eff || disc_mate) : (disc_eff && disc_mate)) : disc_eff;
+        bool tpe = false;
+        int x_tpe = 0;
+        if (FMODE == FM_KTRIM_R && paired && active && !remove && p.trimPairsEvenly && (count + cnt_mate) > 0 &&
+            len_cur > len_cur_mate) {
+            // the longer mate is cut to the shorter one's length: trimToPosition(longer, 0, shorterLen-1, 1)
+            x_tpe = trim_amounts(lo, hi, 0, len_cur - len_cur_mate, 1);
+            tpe = true;
+            len_cur = hi - lo;
+        }
+        const int x_tpe_mate = __shfl_xor_sync(0xFFFFFFFFu, x_tpe, 1);
+        const bool tpe_pair = paired && (tpe || (__shfl_xor_sync(0xFFFFFFFFu, (int)tpe, 1) != 0));
+        if (active && (!paired || !(lane & 1))) {  // one lane per unit accounts
+            if (FMODE != FM_KFILTER) {
+                int xsum = count + (paired ? cnt_mate : 0);
+                int rkt = (count > 0) + ((paired && cnt_mate > 0) ? 1 : 0);
+                if (remove) {
+                    xsum += len_pre + (paired ? len_pre_mate : 0);
+                    rkt = paired ? 2 : 1;
+                } else if (tpe_pair) {
+                    if (rkt < 2) rkt++;
+                    xsum += x_tpe + x_tpe_mate;
+                }
+                s_bk += xsum;
+                s_rk += rkt;
+            } else if (remove) {
+                s_rf += paired ? 2 : 1;
+                s_bf += L + (paired ? L_mate : 0);
+            }
+        }
+        if (live) {
+            s_ri += 1;
+            s_bi += L;
+            if (!remove) {
+                s_ro += 1;
+                s_bo += len_cur;
+            }
+        }
+        if (live) {
+            if (out.id0) out.id0[r] = id0;
+            if (out.id0b) out.id0b[r] = -1;
+            if (out.lo) out.lo[r] = lo;
+            if (out.hi) out.hi[r] = hi;
+            if (out.count) out.count[r] = count;
+            if (out.flags)
+                out.flags[r] = (uint8_t)((discarded ? BBDUK_F_DISCARDED : 0) | (remove ? BBDUK_F_REMOVED : 0) |
+                                         (ktrimmed ? BBDUK_F_KTRIMMED : 0) | (tpe ? BBDUK_F_TPE : 0));
+        }
+    }
+    if (stats) {
+        long long v[8] = {s_ri, s_bi, s_rk, s_bk, s_rf, s_bf, s_ro, s_bo};
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            long long x = v[q];
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
+            if (lane == 0 && x) atomicAdd((unsigned long long *)stats + q, (unsigned long long)x);
+        }
+    }
+}
+
+FastGeom make_geom(const BBTable &t, int max_read_len, bool use_filter) {
+    FastGeom g;
+    const int lmax = std::max(max_read_len, 16);
+    g.nch = (32 * lmax + 15 + 15) / 16 + 1;
+    g.cwords = (lmax + 15) / 16 + 1;
+    int wb = (g.nch + PAD + TAIL) * 4 + ((g.nch + PAD + TAIL + 1) & ~1) * 2 + g.cwords * 32 * 2;
+    wb = (wb + 15) & ~15;
+    g.warp_bytes = wb;
+    g.nfw = use_filter ? t.n_filter_words : 0;
+    const int avail = FAST_SMEM_LIMIT - (int)g.nfw * 4 - 64;
+    g.warps = std::min(32, avail / wb);
+    return g;
+}
+
+bool filter_useful(const BBTable &t) {
+    // beyond ~24 keys per filter word the image is saturated and every position would be a candidate
+    return t.filter != nullptr && t.n_filter_words > 0 && t.stored <= (int64_t)t.n_filter_words * 24;
+}
+
+}  // namespace
+
+FastPlan plan_fast(const BBParams &p, const BBTable &t, int max_read_len) {
+    FastPlan pl{false, max_read_len, 0, 0};
+    const bool mode_ok = (p.mode == MODE_KTRIM) || (p.mode == MODE_KFILTER);
+    if (!mode_ok) return pl;
+    if (p.qHammingDistance != 0 || (p.useShortKmers && p.qHammingDistance2 != 0)) return pl;
+    if (p.speed != 0 || p.qSkip != 1 || p.restrictLeft != 0 || p.restrictRight != 0) return pl;
+    if (p.kbig > p.k || p.minKmerFraction != 0.0f) return pl;
+    if (p.k < 2) return pl;
+    if (max_read_len > MAX_FAST_LEN) max_read_len = MAX_FAST_LEN;  // longer reads are handed off per tile
+    if (!filter_useful(t)) return pl;  // HBM-resident tables: handled by the generic kernel for now
+    const FastGeom g = make_geom(t, max_read_len, true);
+    if (g.warps < 8) return pl;
+    pl.usable = true;
+    pl.max_read_len = max_read_len;
+    pl.smem_bytes = (int)g.nfw * 4 + g.warps * g.warp_bytes + 64;
+    pl.filter_words = (int)g.nfw;
+    return pl;
+}
+
+int launch_fast(const FastPlan &plan, const uint8_t *d_bases, const uint32_t *d_offsets, int64_t n_reads, int paired,
+                const BBParams &p, const BBTable &t, const bbduk_out &out, bbduk_stats *d_stats,
+                unsigned long long *scaf_reads, unsigned long long *scaf_bases, int32_t *d_handoff,
+                unsigned int *d_handoff_n, int sm_count, cudaStream_t st) {
+    const FastGeom g = make_geom(t, plan.max_read_len, true);
+    const int threads = g.warps * 32;
+    const int64_t n_tiles = (n_reads + 31) / 32;
+    const int blocks = (int)std::min<int64_t>(sm_count, (n_tiles + g.warps - 1) / g.warps);
+    auto go = [&](auto kern) -> int {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes) != cudaSuccess) return -1;
+        kern<<<blocks, threads, plan.smem_bytes, st>>>(d_bases, d_offsets, n_reads, paired, p, t, out, d_stats, scaf_reads,
+                                                       scaf_bases, d_handoff, d_handoff_n, g);
+        return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    };
+    if (p.mode == MODE_KFILTER) return go(bbduk_fast_kernel<FM_KFILTER, true>);
+    if (p.ktrimLeft) return go(bbduk_fast_kernel<FM_KTRIM_L, true>);
+    return go(bbduk_fast_kernel<FM_KTRIM_R, true>);
 }

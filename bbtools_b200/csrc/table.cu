@@ -188,7 +188,10 @@ __global__ void expand_kernel(const Seed *__restrict__ seeds, int64_t n_seeds, i
         pre /= nops;
         uint64_t nk;
         int ne;
-        if (!apply_op(km, len, extra, op, nk, ne)) return;  // temp==kmer or impossible deletion: no subtree
+        if (!apply_op(km, len, extra, op, nk, ne)) {  // temp==kmer or impossible deletion: no subtree
+            if (made) atomicAdd(created, (unsigned long long)made);
+            return;
+        }
         km = nk;
         extra = ne;
         made += put_kmer(keys, vals, slot_mask, p, km, len, sd.id, overflow);
@@ -220,8 +223,8 @@ __global__ void filter_build_kernel(const uint64_t *__restrict__ keys, int64_t n
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const uint64_t k = keys[i];
         if (k != BB_EMPTY_KEY) {
-            const uint64_t h = bb_hash64(k);
-            atomicOr(filter + bb_filter_word(h, n_words), bb_filter_bits(h));
+            const uint32_t t = bb_fhash((uint32_t)k, (uint32_t)(k >> 32));
+            atomicOr(filter + bb_filter_word(t, n_words), bb_filter_bits(t));
         }
     }
 }
