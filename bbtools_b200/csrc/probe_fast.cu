@@ -502,7 +502,8 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
             len_cur = hi - lo;
         }
         const int x_tpe_mate = __shfl_xor_sync(0xFFFFFFFFu, x_tpe, 1);
-        const bool tpe_pair = paired && (tpe || (__shfl_xor_sync(0xFFFFFFFFu, (int)tpe, 1) != 0));
+        const bool tpe_mate = __shfl_xor_sync(0xFFFFFFFFu, (int)tpe, 1) != 0;  // never inside a short-circuit
+        const bool tpe_pair = paired && (tpe || tpe_mate);
         if (active && (!paired || !(lane & 1))) {  // one lane per unit accounts
             if (FMODE != FM_KFILTER) {
                 int xsum = count + (paired ? cnt_mate : 0);
