@@ -19,6 +19,7 @@ SYMBOLS = [
                                      C.POINTER(BBDukOut), C.POINTER(BBDukStats)]),
     ("bbduk_b200_process_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                             C.POINTER(BBDukOut), C.c_void_p, C.c_void_p]),
+    ("bbduk_b200_set_max_read_len", C.c_int, [C.c_void_p, C.c_int32]),
     ("bbduk_b200_scaffold_counts", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     ("bbduk_b200_table_describe", C.c_int, [C.c_void_p, C.POINTER(BBDukTableDesc)]),
     ("bbduk_b200_table_alloc", C.c_int, [C.c_void_p, C.POINTER(BBDukTableDesc)]),

@@ -330,6 +330,9 @@ class BBDukIndexGPU:
                                                        int(bool(paired)), C.byref(o), ptr(d_stats), ptr(stream)),
                     "process_device")
 
+    def set_max_read_len(self, n):
+        self._check(self.lib.bbduk_b200_set_max_read_len(self.h, int(n)), "set_max_read_len")
+
     def scaffold_counts(self):
         n = self.n_scaffolds + 1
         rc_ = np.zeros(n, np.int64)

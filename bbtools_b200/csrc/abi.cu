@@ -1,5 +1,6 @@
 // abi.cu -- the extern "C" surface of include/bbduk_b200.h: handle management, table build/replication,
 // host-buffer batching (pinned staging, two streams so copies overlap kernels) and kernel dispatch.
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -50,6 +51,7 @@ struct bbduk_handle {
     Slot slots[N_SLOTS];
     std::atomic<int> next_slot{0};
     std::atomic<int64_t> launches{0};
+    std::atomic<int> max_read_len_hint{0};
     std::mutex err_mu;
     std::string err;
     // per-thread-stream scratch for process_device
@@ -182,18 +184,15 @@ int run_batch(bbduk_handle *h, const uint8_t *d_bases, const uint32_t *d_off, in
                                    h->d_scaf_bases, d_handoff, d_handoff_n, h->sm_count, st);
         if (nl < 0) return set_err(h, std::string("fast kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
         h->launches += nl;
-        unsigned int n_hand = 0;
-        CKH(cudaMemcpyAsync(&n_hand, d_handoff_n, sizeof n_hand, cudaMemcpyDeviceToHost, st));
-        CKH(cudaStreamSynchronize(st));
-        if (n_hand > 0) {
-            if (launch_generic(d_bases, d_off, n_hand, paired, d_handoff, h->p, t, dout, d_stats, h->d_scaf_reads,
-                               h->d_scaf_bases, st))
-                return set_err(h, std::string("generic kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
-            h->launches += 1;
-        }
+        // hand-offs (tiles that do not fit the staging): count stays on the device, no host sync
+        if (launch_generic(d_bases, d_off, n_units, paired, d_handoff, d_handoff_n, h->p, t, dout, d_stats, h->d_scaf_reads,
+                           h->d_scaf_bases, h->sm_count, st))
+            return set_err(h, std::string("generic kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+        h->launches += 1;
         return 0;
     }
-    if (launch_generic(d_bases, d_off, n_units, paired, nullptr, h->p, t, dout, d_stats, h->d_scaf_reads, h->d_scaf_bases, st))
+    if (launch_generic(d_bases, d_off, n_units, paired, nullptr, nullptr, h->p, t, dout, d_stats, h->d_scaf_reads,
+                       h->d_scaf_bases, h->sm_count, st))
         return set_err(h, std::string("generic kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
     h->launches += 1;
     return 0;
@@ -389,13 +388,15 @@ int bbduk_b200_process_device(bbduk_handle *h, const uint8_t *d_bases, const uin
         CKH(cudaMalloc(&h->dev_handoff, sizeof(int32_t) * h->dev_handoff_cap));
         CKH(cudaMalloc(&h->dev_handoff_n, sizeof(unsigned int) * 4));
     }
-    // longest read (sizes the fast kernel's staging)
-    unsigned int mx = 0;
-    CKH(cudaMemsetAsync(h->dev_handoff_n + 1, 0, sizeof(unsigned int), st));
-    max_len_kernel<<<296, 256, 0, st>>>(d_offsets, n_reads, h->dev_handoff_n + 1);
-    h->launches += 1;
-    CKH(cudaMemcpyAsync(&mx, h->dev_handoff_n + 1, sizeof mx, cudaMemcpyDeviceToHost, st));
-    CKH(cudaStreamSynchronize(st));
+    // longest read (sizes the fast kernel's staging): caller's hint, else one reduction + sync
+    unsigned int mx = (unsigned int)std::max(0, h->max_read_len_hint.load());
+    if (mx == 0) {
+        CKH(cudaMemsetAsync(h->dev_handoff_n + 1, 0, sizeof(unsigned int), st));
+        max_len_kernel<<<296, 256, 0, st>>>(d_offsets, n_reads, h->dev_handoff_n + 1);
+        h->launches += 1;
+        CKH(cudaMemcpyAsync(&mx, h->dev_handoff_n + 1, sizeof mx, cudaMemcpyDeviceToHost, st));
+        CKH(cudaStreamSynchronize(st));
+    }
     return run_batch(h, d_bases, d_offsets, n_reads, paired, *d_out, d_stats, (int)mx, h->dev_handoff, h->dev_handoff_n, st);
 }
 
@@ -515,6 +516,12 @@ int bbduk_b200_scaffold_counts(bbduk_handle *h, int64_t *read_counts, int64_t *b
     if (m <= 0) return 0;
     if (read_counts) CKH(cudaMemcpy(read_counts, h->d_scaf_reads, sizeof(int64_t) * m, cudaMemcpyDeviceToHost));
     if (base_counts) CKH(cudaMemcpy(base_counts, h->d_scaf_bases, sizeof(int64_t) * m, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int bbduk_b200_set_max_read_len(bbduk_handle *h, int32_t max_read_len) {
+    if (!h) return set_err(nullptr, "handle is NULL");
+    h->max_read_len_hint = max_read_len < 0 ? 0 : max_read_len;
     return 0;
 }
 

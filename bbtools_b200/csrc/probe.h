@@ -7,9 +7,11 @@
 #include "params.h"
 
 // every mode, one thread per unit (pair or single read); d_units = optional list of unit indices
+// d_n_units (optional): device-side count of the entries of d_units; n_units is then only an upper bound
 int launch_generic(const uint8_t *d_bases, const uint32_t *d_offsets, int64_t n_units, int paired, const int32_t *d_units,
-                   const BBParams &p, const BBTable &t, const bbduk_out &out, bbduk_stats *d_stats,
-                   unsigned long long *scaf_reads, unsigned long long *scaf_bases, cudaStream_t st);
+                   const unsigned int *d_n_units, const BBParams &p, const BBTable &t, const bbduk_out &out,
+                   bbduk_stats *d_stats, unsigned long long *scaf_reads, unsigned long long *scaf_bases, int sm_count,
+                   cudaStream_t st);
 
 // tuned kernel (probe_fast.cu). Returns the number of kernels launched, <0 on error. Units it cannot
 // handle are appended to d_handoff (count in d_handoff_n) for launch_generic.

@@ -5,6 +5,8 @@
 // reference's exact scan order; probe_fast.cu is the tuned kernel for the common configurations and
 // hands anything it does not cover to this one. Rolling state per base follows
 // jgi/BBDuk.java:3882-3888 (== bbduk/BBDukProcessorS.java:2009-2016); see each function for its lines.
+#include <algorithm>
+
 #include "bbduk_dev.cuh"
 #include "probe.h"
 
@@ -663,12 +665,14 @@ __device__ __forceinline__ void write_out(const bbduk_out &o, int64_t idx, const
 // One thread per unit (a pair, or a single read). `units` optionally lists the unit indices to
 // process (the fast kernel's hand-offs); null = all units [0, n_units).
 __global__ void __launch_bounds__(128)
-bbduk_generic_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ offsets, int64_t n_units, int paired,
-                     const int32_t *__restrict__ units, BBParams p, BBTable t, bbduk_out out, bbduk_stats *stats,
-                     unsigned long long *scaf_reads, unsigned long long *scaf_bases) {
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+bbduk_generic_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ offsets, int64_t n_units_arg, int paired,
+                     const int32_t *__restrict__ units, const unsigned int *__restrict__ n_units_dev, BBParams p, BBTable t,
+                     bbduk_out out, bbduk_stats *stats, unsigned long long *scaf_reads, unsigned long long *scaf_bases) {
+    // n_units_dev: the number of listed units lives on the device (written by the fast kernel), so the
+    // host never has to synchronise to learn it; the grid then strides over the list.
+    const int64_t n_units = n_units_dev ? (int64_t)*n_units_dev : n_units_arg;
     long long s_rk = 0, s_bk = 0, s_rf = 0, s_bf = 0, s_ro = 0, s_bo = 0, s_ri = 0, s_bi = 0;
-    if (tid < n_units) {
+    for (int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tid < n_units; tid += (int64_t)gridDim.x * blockDim.x) {
         const int64_t u = units ? (int64_t)units[tid] : tid;
         const Ctx c{p, t, scaf_reads, scaf_bases};
         const int per = paired ? 2 : 1;
@@ -795,11 +799,11 @@ bbduk_generic_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restri
         }
         write_out(out, u * per, *r1, remove, kt1, tpe1, split, count1);
         if (r2) write_out(out, u * per + 1, *r2, remove, kt2, tpe2, false, count2);
-        s_ri = per;
-        s_bi = initialLength1 + initialLength2;
+        s_ri += per;
+        s_bi += initialLength1 + initialLength2;
         if (!remove) {
-            s_ro = per;
-            s_bo = rlen(*r1) + (r2 ? rlen(*r2) : 0);
+            s_ro += per;
+            s_bo += rlen(*r1) + (r2 ? rlen(*r2) : 0);
         }
     }
     if (stats) {  // warp-level sums, one atomic per warp and counter
@@ -814,11 +818,13 @@ bbduk_generic_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restri
 }
 
 int launch_generic(const uint8_t *d_bases, const uint32_t *d_offsets, int64_t n_units, int paired, const int32_t *d_units,
-                   const BBParams &p, const BBTable &t, const bbduk_out &out, bbduk_stats *d_stats,
-                   unsigned long long *scaf_reads, unsigned long long *scaf_bases, cudaStream_t st) {
+                   const unsigned int *d_n_units, const BBParams &p, const BBTable &t, const bbduk_out &out,
+                   bbduk_stats *d_stats, unsigned long long *scaf_reads, unsigned long long *scaf_bases, int sm_count,
+                   cudaStream_t st) {
     if (n_units <= 0) return 0;
-    const int64_t nb = (n_units + 127) / 128;
-    bbduk_generic_kernel<<<(unsigned)nb, 128, 0, st>>>(d_bases, d_offsets, n_units, paired, d_units, p, t, out, d_stats,
-                                                       scaf_reads, scaf_bases);
+    // with a device-side count the real number of units is unknown here (usually 0): a small grid strides
+    const int64_t nb = d_n_units ? std::min<int64_t>((n_units + 127) / 128, 8 * (int64_t)sm_count) : (n_units + 127) / 128;
+    bbduk_generic_kernel<<<(unsigned)nb, 128, 0, st>>>(d_bases, d_offsets, n_units, paired, d_units, d_n_units, p, t, out,
+                                                       d_stats, scaf_reads, scaf_bases);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

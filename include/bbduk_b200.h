@@ -188,6 +188,11 @@ BBDUK_API int bbduk_b200_process_device(bbduk_handle *h, const uint8_t *d_bases,
                               int64_t n_reads, int32_t paired, const bbduk_out *d_out,
                               bbduk_stats *d_stats, void *stream);
 
+/* Optional hint for bbduk_b200_process_device: an upper bound on the read length of the batches to come
+ * (reads longer than the hint are still handled, through the generic kernel). 0 = unknown: every call
+ * then measures the batch with one extra reduction kernel and a stream synchronisation. */
+BBDUK_API int bbduk_b200_set_max_read_len(bbduk_handle *h, int32_t max_read_len);
+
 /* Per-scaffold hit accounting accumulated on the device by process calls, index 0..n_scaffolds
  * (replaces scaffoldReadCounts/scaffoldBaseCounts, jgi/BBDuk.java:1968-1969, :3984-3992). */
 BBDUK_API int bbduk_b200_scaffold_counts(bbduk_handle *h, int64_t *read_counts, int64_t *base_counts, int32_t n);
