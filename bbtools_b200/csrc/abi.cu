@@ -347,7 +347,7 @@ int bbduk_b200_table_describe(bbduk_handle *h, bbduk_table_desc *d) {
 int bbduk_b200_table_alloc(bbduk_handle *h, bbduk_table_desc *d) {
     if (!h || !d) return set_err(h, "NULL argument");
     if (h->finalized) return set_err(h, "table_alloc on a finalized handle");
-    if (d->n_slots < 4 || (d->n_slots & (d->n_slots - 1))) return set_err(h, "n_slots must be a power of two >= 4");
+    if (d->n_slots < 1024 || (d->n_slots & (d->n_slots - 1))) return set_err(h, "n_slots must be a power of two >= 1024");
     CKH(cudaSetDevice(h->device));
     char eb[512] = {0};
     if (h->table.alloc(d->n_slots, (uint32_t)d->n_filter_words, eb, sizeof eb)) return set_err(h, eb);

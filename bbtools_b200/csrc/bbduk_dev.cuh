@@ -42,25 +42,32 @@ __device__ __forceinline__ bool bb_passes_speed(const BBParams &p, uint64_t key)
 }
 
 // ---- hashing: layout only, any mixing function gives the same results ------------------------------
-__device__ __forceinline__ uint64_t bb_hash64(uint64_t x) {
-    x ^= x >> 32;
-    x *= 0xD6E8FEB86659FD93ull;
-    x ^= x >> 32;
-    x *= 0xD6E8FEB86659FD93ull;
-    x ^= x >> 32;
-    return x;
-}
+// One 32-bit multiplicative hash of the key serves everything: its HIGH bits pick the hash-array
+// bucket and the filter word, its LOW bits pick the filter bit pattern.
+__device__ __forceinline__ uint32_t bb_fhash(uint32_t klo, uint32_t khi) { return klo * 0x9E3779B1u + khi * 0x85EBCA77u; }
+__device__ __forceinline__ uint32_t bb_fhash64(uint64_t key) { return bb_fhash((uint32_t)key, (uint32_t)(key >> 32)); }
 
+// Hash array: buckets of 4 consecutive slots = one 32-byte sector; linear probing over buckets. Slots
+// of a bucket fill in order and nothing is ever deleted, so an EMPTY slot ends the search.
+// n_slots is a power of two in [1024, 2^34]; bucket = hash >> (34 - log2(n_slots)).
 #define BB_MAX_PROBE 8192
-// Hash array: buckets of 4 consecutive slots (one 32-byte sector), linear probing across slots.
+__device__ __forceinline__ uint32_t bb_bucket(uint32_t h, uint32_t bucket_shift) { return h >> bucket_shift; }
+
 // Lookup = kmer.AbstractKmerTable.getValue (kmer/AbstractKmerTable.java:61): id or -1.
 __device__ __forceinline__ int bb_table_get(const BBTable &t, uint64_t key) {
-    uint64_t slot = (bb_hash64(key) & (t.slot_mask >> 2)) << 2;
-    for (int probe = 0; probe < BB_MAX_PROBE; probe++) {  // inserts never go further than BB_MAX_PROBE
-        const uint64_t kk = __ldg(t.keys + slot);
-        if (kk == key) return __ldg(t.vals + slot);
-        if (kk == BB_EMPTY_KEY) return -1;
-        slot = (slot + 1) & t.slot_mask;
+    uint64_t b = bb_bucket(bb_fhash64(key), t.bucket_shift);
+    const uint64_t bmask = t.slot_mask >> 2;
+    for (int probe = 0; probe < BB_MAX_PROBE / 4; probe++) {
+        const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(t.keys + 4 * b);
+        const ulonglong2 k01 = __ldg(q), k23 = __ldg(q + 1);  // one sector, both halves in flight
+        int j = -1;
+        if (k01.x == key) j = 0;
+        else if (k01.y == key) j = 1;
+        else if (k23.x == key) j = 2;
+        else if (k23.y == key) j = 3;
+        if (j >= 0) return __ldg(t.vals + 4 * b + j);
+        if (k23.y == BB_EMPTY_KEY) return -1;  // slots fill in order: last one empty <=> bucket not full
+        b = (b + 1) & bmask;
     }
     return -1;
 }
@@ -68,9 +75,9 @@ __device__ __forceinline__ int bb_table_get(const BBTable &t, uint64_t key) {
 // Insert = setIfNotPresent with "first writer wins" realised as min id.
 // Returns 1 if this call created the key. The probe length is bounded so that an over-full array
 // raises *overflow instead of spinning forever.
-__device__ __forceinline__ int bb_table_put(uint64_t *keys, int32_t *vals, uint64_t slot_mask, uint64_t key, int32_t id,
-                                            int *overflow) {
-    uint64_t slot = (bb_hash64(key) & (slot_mask >> 2)) << 2;
+__device__ __forceinline__ int bb_table_put(uint64_t *keys, int32_t *vals, uint64_t slot_mask, uint32_t bucket_shift,
+                                            uint64_t key, int32_t id, int *overflow) {
+    uint64_t slot = (uint64_t)bb_bucket(bb_fhash64(key), bucket_shift) << 2;
     for (int probe = 0; probe < BB_MAX_PROBE; probe++) {
         uint64_t kk = keys[slot];
         if (kk == BB_EMPTY_KEY) {
@@ -96,7 +103,6 @@ __device__ __forceinline__ int bb_table_put(uint64_t *keys, int32_t *vals, uint6
 // the shift amount mod 32, so no masking is needed). The same functions build and query the filter.
 #define BB_FPAT1 0x00000081u
 #define BB_FPAT2 0x00002001u
-__device__ __forceinline__ uint32_t bb_fhash(uint32_t klo, uint32_t khi) { return klo * 0x9E3779B1u + khi * 0x85EBCA77u; }
 __device__ __forceinline__ uint32_t bb_filter_word(uint32_t t, uint32_t n_words) { return __umulhi(t, n_words); }
 __device__ __forceinline__ uint32_t bb_filter_bits(uint32_t t) {
     return __funnelshift_l(BB_FPAT1, BB_FPAT1, t) | __funnelshift_l(BB_FPAT2, BB_FPAT2, t >> 5);

@@ -44,7 +44,8 @@ struct BBParams {
 struct BBTable {
     const uint64_t *keys;   // [n_slots]; EMPTY = ~0
     const int32_t *vals;    // [n_slots]; scaffold id (min over writers)
-    uint64_t slot_mask;     // n_slots-1 (n_slots power of two, multiple of 4)
+    uint64_t slot_mask;     // n_slots-1 (n_slots power of two, >= 1024)
+    uint32_t bucket_shift;  // 34 - log2(n_slots): bucket = hash32 >> bucket_shift
     const uint32_t *filter; // blocked bloom image of all keys, n_filter_words 32-bit words (may be null)
     uint32_t n_filter_words;
     int32_t n_scaffolds;

@@ -1,11 +1,11 @@
 // probe_fast.cu -- the tuned per-read kernel for the common BBDuk configurations on sm_100a.
 //
-// Covers ktrim=r, ktrim=l and kfilter (countSetKmers) with qhdist=0, speed=0, qskip=1, no
-// restrictleft/right, k<=31, minkmerfraction=0; everything else, and any tile of reads that does not
-// fit the staging, is handed to probe_generic.cu. Results are identical by construction: this kernel
-// only decides WHICH read positions can possibly hit (an on-chip blocked-bloom image of all table
-// keys, no false negatives) and then evaluates those positions with the exact key formula and the
-// exact hash array, in the reference's scan order.
+// Covers ktrim=r, ktrim=l and kfilter (countSetKmers, maxbadkmers=0) with qhdist=0, speed=0, qskip=1,
+// no restrictleft/right, k<=31, minkmerfraction=0; everything else, and any tile of reads that does
+// not fit the staging, is handed to probe_generic.cu. Results are identical by construction: this
+// kernel only decides WHICH read positions can possibly hit (an on-chip blocked-bloom image of all
+// table keys, no false negatives) and then evaluates those positions with the exact key formula and
+// the exact hash array.
 //
 // Per warp, per tile of 32 consecutive reads (one lane per read; mates are neighbouring lanes):
 //   A. the tile's contiguous ASCII bytes are read once with coalesced 16-byte loads and converted
@@ -13,9 +13,11 @@
 //   B. each lane walks its read 16 positions at a time; forward k-mer and reverse-complement k-mer
 //      come from funnel shifts of the packed stream with compile-time shift amounts, then
 //      canonical max -> middle mask -> 32-bit hash -> one shared-memory filter word -> bit test;
-//      survivors are recorded as candidate bits;
-//   C. candidates (and every window that touches an undefined base) are evaluated exactly, in scan
-//      order, against the hash array in L2/HBM; short-k-mer tails run when nothing was found;
+//      survivors (plus every window that touches an undefined base) become candidates;
+//   C. candidates of ALL lanes are pooled in a warp queue (shuffle prefix sums) and evaluated
+//      32 at a time with every lane busy: exact key, one 32-byte bucket load from the hash array
+//      in L2/HBM; hits fold into per-read (first position,id) / last position with shared atomics;
+//      the short-k-mer tails run for reads without a full-length hit;
 //   D. trim arithmetic (TrimRead rules), minlen, pair logic (rieb, tpe) via lane shuffles, coalesced
 //      result stores, warp-aggregated counters.
 // Rolling-state semantics follow jgi/BBDuk.java:3882-3900 in the closed form of SURVEY.md A.2.
@@ -30,11 +32,11 @@ constexpr int PAD = 2;           // zero chunks in front of the staged stream (w
 constexpr int TAIL = 4;          // zero chunks behind it (the reverse-strand words run two steps ahead)
 constexpr int MAX_FAST_LEN = 1008;
 constexpr int FAST_SMEM_LIMIT = 227 * 1024;
+constexpr int QCAP = 32 + 32 * 16;  // queue entries: a drain threshold of 32 plus one full step of all lanes
 
 struct FastGeom {
     int warps;        // warps per block
     int nch;          // staged 16-base chunks per warp (capacity, without padding)
-    int cwords;       // candidate halfwords per lane (= 16-position steps)
     int warp_bytes;   // shared memory per warp
     uint32_t nfw;     // filter words
 };
@@ -46,11 +48,12 @@ __device__ __forceinline__ uint32_t pair_reverse_complement(uint32_t x) {
 }
 
 // 4 ASCII bases (byte 0 first) -> raw 2-bit codes in each byte's low bits, and "bad" (non-zero byte
-// <=> the base is not one of ACGTUacgtu). Exact, see the bit derivation in DESIGN.md.
+// <=> the base is not one of ACGTUacgtu). With d = (c|0x20)^0x61 a base is valid iff bits 7,6,5,3 of d
+// are 0, bit 4 equals q, and (q or bit 0 is 0), where q = "bits (2,1) are 10" marks the t/u class.
 __device__ __forceinline__ void classify4(uint32_t w, uint32_t &codes, uint32_t &bad) {
     codes = ((w >> 1) ^ (w >> 2)) & 0x03030303u;
     const uint32_t d = (w | 0x20202020u) ^ 0x61616161u;
-    const uint32_t q = (d >> 2) & ~(d >> 1) & 0x01010101u;           // t/u class: bits(2,1) == 10
+    const uint32_t q = (d >> 2) & ~(d >> 1) & 0x01010101u;
     bad = (d & 0xE8E8E8E8u) | (((d >> 4) ^ q) & 0x01010101u) | (d & ~q & 0x01010101u);
 }
 __device__ __forceinline__ uint32_t pack4(uint32_t codes) { return (codes * 0x40100401u) >> 24; }  // big-endian 8 bits
@@ -73,10 +76,7 @@ struct Stream {
         return (x >> (16 - (g & 15))) & 0xFFFFu;
     }
     // defined bits of the 32 bases ending at stream base e: bit t = base e-t
-    __device__ __forceinline__ uint32_t dwin(int e) const {
-        const uint32_t be = (d16(e - 31) << 16) | d16(e - 15);  // bit 31-b = base e-31+b  => bit t = base e-t
-        return be;
-    }
+    __device__ __forceinline__ uint32_t dwin(int e) const { return (d16(e - 31) << 16) | d16(e - 15); }
     // 2-bit codes of the 32 bases ending at stream base e: slot t (bits 2t+1,2t) = base e-t
     __device__ __forceinline__ uint64_t win(int e) const { return ((uint64_t)f16(e - 31) << 32) | f16(e - 15); }
 };
@@ -93,23 +93,28 @@ __device__ __forceinline__ uint64_t spread2(uint32_t m) {  // bit t -> bits (2t+
 // reverse the order of the low `n` 2-bit slots (no complement)
 __device__ __forceinline__ uint64_t rev2(uint64_t x, int n) { return bb_rcomp(~x, n); }
 
-// exact id of the full-length probe at read position i (stream base e = s+i), -1 if none / no probe.
-// Handles undefined bases exactly: kmer keeps code 0 for them and is never reset;
-// with forbidNs the reverse k-mer only holds bases after the last undefined one and the probe needs
-// len >= minlen2.
-__device__ __forceinline__ int exact_full(const Stream &st, int e, const BBParams &p, const BBTable &t) {
+// exact id of the full-length probe whose window ends at stream base e, -1 if none / no probe.
+// clean = the owning read has no undefined base. Otherwise undefined bases are handled exactly
+// (SURVEY.md A.2): kmer keeps code 0 for them and is never reset; with forbidNs the reverse k-mer only
+// holds the bases after the last undefined one and the probe needs len >= minlen2.
+__device__ __forceinline__ int exact_full(const Stream &st, int e, bool clean, const BBParams &p, const BBTable &t) {
     const int k = p.k;
     uint64_t kmer = st.win(e) & p.mask;
-    const uint32_t dw = st.dwin(e);
-    const uint32_t kbits = (k >= 32) ? 0xFFFFFFFFu : ((1u << k) - 1u);
     uint64_t rkmer;
-    if ((dw & kbits) == kbits) {
+    bool plain = clean;
+    uint32_t dw = 0;
+    const uint32_t kbits = (1u << k) - 1u;  // k <= 31
+    if (!clean) {
+        dw = st.dwin(e);
+        plain = (dw & kbits) == kbits;
+    }
+    if (plain) {
         rkmer = bb_rcomp(kmer, k);
     } else {
         const uint64_t E = spread2(dw & kbits);
         kmer &= E;
         if (p.forbidNs) {
-            const int len = __ffs(~dw) - 1;  // bases after the last undefined one (window has one)
+            const int len = __ffs(~dw) - 1;  // bases after the last undefined one (the window has one)
             if (len < p.minlen2) return -1;
             rkmer = bb_rcomp(kmer, k) & ~((1ull << (2 * (k - len))) - 1ull) & p.mask;
         } else {
@@ -120,7 +125,7 @@ __device__ __forceinline__ int exact_full(const Stream &st, int e, const BBParam
 }
 
 __device__ __forceinline__ bool filter_pass(const uint32_t *filt, uint32_t nfw, uint64_t key) {
-    const uint32_t tt = bb_fhash((uint32_t)key, (uint32_t)(key >> 32));
+    const uint32_t tt = bb_fhash64(key);
     const uint32_t pat = bb_filter_bits(tt);
     return (filt[bb_filter_word(tt, nfw)] & pat) == pat;
 }
@@ -143,9 +148,20 @@ __device__ __forceinline__ int trim_amounts(int &lo, int &hi, int left, int righ
     return left + right;
 }
 
+// OR of x >> d for d in [0, n): every set bit also covers the n-1 lower bit positions
+__device__ __forceinline__ uint32_t smear_right(uint64_t x, int n) {
+    int have = 1;
+    while (have < n) {
+        const int s = min(have, n - have);
+        x |= x >> s;
+        have += s;
+    }
+    return (uint32_t)x;
+}
+
 enum { FM_KTRIM_R = 0, FM_KTRIM_L = 1, FM_KFILTER = 2 };
 
-template <int FMODE, bool USE_FILTER>
+template <int FMODE, bool RCOMP, bool K16>
 __global__ void __launch_bounds__(1024, 1)
 bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ offsets, int64_t n_reads, int paired,
                   BBParams p, BBTable t, bbduk_out out, bbduk_stats *stats, unsigned long long *scaf_reads,
@@ -153,14 +169,14 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t *filt = smem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t *wbase = reinterpret_cast<uint8_t *>(smem + (USE_FILTER ? geo.nfw : 0)) + (size_t)warp * geo.warp_bytes;
-    uint32_t *Fs = reinterpret_cast<uint32_t *>(wbase);
+    uint8_t *wbase = reinterpret_cast<uint8_t *>(smem + geo.nfw) + (size_t)warp * geo.warp_bytes;
+    unsigned long long *first64 = reinterpret_cast<unsigned long long *>(wbase);  // [32] (pos<<32 | id) of the first hit
+    int *lastpos = reinterpret_cast<int *>(first64 + 32);                         // [32] last hit position
+    uint32_t *queue = reinterpret_cast<uint32_t *>(lastpos + 32);                 // [QCAP]
+    uint32_t *Fs = queue + QCAP;
     uint16_t *Ds = reinterpret_cast<uint16_t *>(Fs + geo.nch + PAD + TAIL);
-    uint16_t *cand = Ds + ((geo.nch + PAD + TAIL + 1) & ~1);  // [cwords][32]
 
-    if (USE_FILTER) {
-        for (uint32_t i = threadIdx.x; i < geo.nfw; i += blockDim.x) filt[i] = __ldg(t.filter + i);
-    }
+    for (uint32_t i = threadIdx.x; i < geo.nfw; i += blockDim.x) filt[i] = __ldg(t.filter + i);
     for (int i = lane; i < PAD; i += 32) {
         Fs[i] = 0;
         Ds[i] = 0;
@@ -188,7 +204,7 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
         const int nchunks = (int)((base_addr + tile_hi - a0 + 15) >> 4);
         const int L = (int)(o1 - o0);
         const int maxL = __reduce_max_sync(0xFFFFFFFFu, L);
-        if (nchunks > geo.nch || maxL > (geo.cwords - 1) * 16) {
+        if (nchunks > geo.nch || maxL > MAX_FAST_LEN) {
             // tile does not fit the staging: hand its units to the generic kernel
             if (live && (!paired || !(lane & 1))) {
                 const unsigned int w = atomicAdd(handoff_n, 1u);
@@ -200,196 +216,157 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
         __syncwarp();
         for (int c = lane; c < nchunks + TAIL; c += 32) {
             uint32_t f = 0, dbits = 0;
-            const bool in = c < nchunks;
-            uint32_t cw[4], bw[4];
-            if (in) {
+            if (c < nchunks) {
                 const uint4 v = __ldg(reinterpret_cast<const uint4 *>(a0) + c);
+                uint32_t cw[4], bw[4];
                 classify4(v.x, cw[0], bw[0]);
                 classify4(v.y, cw[1], bw[1]);
                 classify4(v.z, cw[2], bw[2]);
                 classify4(v.w, cw[3], bw[3]);
-            } else {
-                cw[0] = cw[1] = cw[2] = cw[3] = 0;
-                bw[0] = bw[1] = bw[2] = bw[3] = 0;
+                f = (pack4(cw[0]) << 24) | (pack4(cw[1]) << 16) | (pack4(cw[2]) << 8) | pack4(cw[3]);
+                dbits = 0xFFFFu;
+                if ((bw[0] | bw[1] | bw[2] | bw[3]) != 0)  // rare: some base of the chunk is not ACGTU
+                    dbits = (valid4(bw[0]) << 12) | (valid4(bw[1]) << 8) | (valid4(bw[2]) << 4) | valid4(bw[3]);
             }
-            const bool anybad = (bw[0] | bw[1] | bw[2] | bw[3]) != 0;
-            f = (pack4(cw[0]) << 24) | (pack4(cw[1]) << 16) | (pack4(cw[2]) << 8) | pack4(cw[3]);
-            dbits = 0xFFFFu;
-            if (__any_sync(__activemask(), anybad)) {
-                if (anybad) dbits = (valid4(bw[0]) << 12) | (valid4(bw[1]) << 8) | (valid4(bw[2]) << 4) | valid4(bw[3]);
-            }
-            if (!in) dbits = 0;
             Fs[c + PAD] = f;
             Ds[c + PAD] = (uint16_t)dbits;
         }
+        first64[lane] = ~0ull;
+        lastpos[lane] = -1;
         __syncwarp();
 
-        // ---- B. per-lane scan ------------------------------------------------------------------
+        // ---- B. per-lane scan, C. pooled exact evaluation ----------------------------------------
         const int s = (int)(base_addr + o0 - a0);  // stream base of read position 0
         const int nsteps = (L + 15) >> 4;
-        bool has_undef = false;
-        {
-            // bases outside [s, s+L) belong to neighbours; only this read's bits count
-            for (int j = 0; j < nsteps; j++) {
-                uint32_t dd = st.d16(s + 16 * j);
-                const int rem = L - 16 * j;
-                if (rem < 16) dd |= (0xFFFFu >> rem);
-                has_undef |= (dd != 0xFFFFu);
-            }
-        }
-        const bool scan = live && L >= k && t.stored > 0 &&
-                          !((p.skipR1 && !(paired && (lane & 1))) || (p.skipR2 && paired && (lane & 1)));
         const int max_steps = (maxL + 15) >> 4;
-        for (int j = 0; j < max_steps; j++) cand[j * 32 + lane] = 0;
-        if (scan) {
-            // sliding registers: f_m2,f_m1,f_0 = read words j-2,j-1,j (big-endian);
-            // r_0,r_1,r_2 = complemented little-endian words of bases starting at 16j-(k-1)
-            uint32_t f_m2 = 0, f_m1 = 0, f_0;
-            uint32_t r_0 = pair_reverse_complement(st.f16(s - (k - 1))), r_1 = pair_reverse_complement(st.f16(s + 16 - (k - 1))), r_2;
-            for (int j = 0; j < nsteps; j++) {
+        const int pairnum = (paired && (lane & 1)) ? 1 : 0;
+        const bool skip = (p.skipR1 && pairnum == 0) || (p.skipR2 && pairnum == 1);
+        const bool scan = live && L >= k && t.stored > 0 && !skip;
+        bool has_undef = false;
+        for (int j = 0; j < nsteps; j++) {
+            uint32_t dd = st.d16(s + 16 * j);
+            const int rem = L - 16 * j;
+            if (rem < 16) dd |= (0xFFFFu >> rem);
+            has_undef |= (dd != 0xFFFFu);
+        }
+        const bool any_undef = __any_sync(0xFFFFFFFFu, has_undef && scan);
+        int qn = 0;  // warp-uniform queue fill
+
+        auto drain = [&](int n_take) {
+            // the last n_take (<= 32) queue entries, one per lane
+            if (lane < n_take) {
+                const uint32_t ent = queue[qn - n_take + lane];
+                const int e = (int)(ent & 0x7FFFu), owner = (int)((ent >> 15) & 31u), pos = (int)((ent >> 20) & 0x7FFu);
+                const int id = exact_full(st, e, (ent >> 31) != 0, p, t);
+                if (id > 0) {
+                    atomicMin(first64 + owner, ((unsigned long long)pos << 32) | (unsigned int)id);
+                    if (FMODE == FM_KTRIM_L) atomicMax(lastpos + owner, pos);
+                }
+            }
+            qn -= n_take;
+            __syncwarp();
+        };
+
+        uint32_t f_m2 = 0, f_m1 = 0, f_0 = 0, r_0 = 0, r_1 = 0, r_2 = 0;
+        uint32_t und_prev = 0;  // undefined bits of the previous 32 positions (bit 31 = oldest)
+        if (scan && RCOMP) {
+            r_0 = pair_reverse_complement(st.f16(s - (k - 1)));
+            r_1 = pair_reverse_complement(st.f16(s + 16 - (k - 1)));
+        }
+        for (int j = 0; j < max_steps; j++) {
+            uint32_t cbits = 0;
+            if (scan && j < nsteps) {
                 f_0 = st.f16(s + 16 * j);
-                r_2 = pair_reverse_complement(st.f16(s + 16 * (j + 2) - (k - 1)));
-                uint32_t cbits = 0;
+                if (RCOMP) r_2 = pair_reverse_complement(st.f16(s + 16 * (j + 2) - (k - 1)));
 #pragma unroll
                 for (int b = 0; b < 16; b++) {
                     const int sh = 2 * (15 - b);
-                    uint32_t klo = __funnelshift_r(f_0, f_m1, sh) & mask_lo;
+                    uint32_t klo = __funnelshift_r(f_0, f_m1, sh);
                     uint32_t khi = __funnelshift_r(f_m1, f_m2, sh) & mask_hi;
-                    if (p.rcomp) {
-                        const uint32_t rlo = __funnelshift_r(r_0, r_1, 2 * b) & mask_lo;
+                    if (!K16) klo &= mask_lo;
+                    if (RCOMP) {
+                        uint32_t rlo = __funnelshift_r(r_0, r_1, 2 * b);
                         const uint32_t rhi = __funnelshift_r(r_1, r_2, 2 * b) & mask_hi;
-                        const bool gt = (rhi > khi) || (rhi == khi && rlo > klo);
+                        if (!K16) rlo &= mask_lo;
+                        const bool gt = (((uint64_t)rhi << 32) | rlo) > (((uint64_t)khi << 32) | klo);
                         klo = gt ? rlo : klo;
                         khi = gt ? rhi : khi;
                     }
                     klo = (klo & mm_lo) | km_lo;
                     khi = (khi & mm_hi) | km_hi;
-                    bool pass;
-                    if (USE_FILTER) {
-                        const uint32_t tt = bb_fhash(klo, khi);
-                        const uint32_t pat = bb_filter_bits(tt);
-                        pass = (filt[bb_filter_word(tt, geo.nfw)] & pat) == pat;
-                    } else {
-                        pass = true;
-                    }
+                    const uint32_t tt = bb_fhash(klo, khi);
+                    const uint32_t pat = bb_filter_bits(tt);
+                    const bool pass = (filt[bb_filter_word(tt, geo.nfw)] & pat) == pat;
                     cbits |= pass ? (1u << b) : 0u;
+                }
+                f_m2 = f_m1;
+                f_m1 = f_0;
+                r_0 = r_1;
+                r_1 = r_2;
+                if (any_undef) {
+                    // every window that contains an undefined base is decided by the exact evaluator
+                    uint32_t dd = st.d16(s + 16 * j);
+                    const int rem = L - 16 * j;
+                    if (rem < 16) dd |= (0xFFFFu >> rem);
+                    const uint32_t und = (~dd) & 0xFFFFu;  // bit 15-b = position 16j+b undefined
+                    // 48 positions [16j-32, 16j+16), oldest in the top bits
+                    const uint64_t hist = ((uint64_t)und_prev << 16) | und;
+                    const uint32_t forced = smear_right(hist, k) & 0xFFFFu;  // bit 15-b: window ending at 16j+b touches one
+                    cbits |= __brev(forced) >> 16;                          // -> bit b
+                    und_prev = (und_prev << 16) | und;
                 }
                 // keep positions k-1 <= i < L
                 const int i0 = 16 * j;
                 uint32_t vm = 0xFFFFu;
                 if (i0 < k - 1) vm &= (k - 1 - i0 >= 16) ? 0u : (0xFFFFu << (k - 1 - i0));
                 if (L - i0 < 16) vm &= (1u << (L - i0)) - 1u;
-                cand[j * 32 + lane] = (uint16_t)(cbits & vm);
-                f_m2 = f_m1;
-                f_m1 = f_0;
-                r_0 = r_1;
-                r_1 = r_2;
+                cbits &= vm;
             }
-            if (has_undef) {
-                // every window that contains an undefined base is decided by the exact evaluator
-                for (int j = 0; j < nsteps; j++) {
-                    uint32_t dd = st.d16(s + 16 * j);
-                    const int rem = L - 16 * j;
-                    if (rem < 16) dd |= (0xFFFFu >> rem);
-                    uint32_t und = (~dd) & 0xFFFFu;  // bit 15-b = base 16j+b undefined
-                    while (und) {
-                        const int b = 15 - (31 - __clz(und));
-                        und &= ~(1u << (15 - b));
-                        const int pu = 16 * j + b;
-                        const int from = max(pu, k - 1), to = min(pu + k - 1, L - 1);
-                        for (int i = from; i <= to; i++) cand[(i >> 4) * 32 + lane] |= (uint16_t)(1u << (i & 15));
-                    }
+            // pool this step's candidates: exclusive prefix sum of the per-lane counts
+            const int cnt = __popc(cbits);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            if (total) {
+                int w = qn + incl - cnt;
+                const uint32_t tag = ((uint32_t)lane << 15) | (has_undef ? 0u : 0x80000000u);
+                uint32_t cb = cbits;
+                while (cb) {
+                    const int b = __ffs(cb) - 1;
+                    cb &= cb - 1;
+                    const int pos = 16 * j + b;
+                    queue[w++] = (uint32_t)(s + pos) | tag | ((uint32_t)pos << 20);
                 }
+                qn += total;
+                __syncwarp();
+                while (qn >= 32) drain(32);
             }
         }
+        if (qn > 0) drain(qn);
 
-        // ---- C. exact evaluation in scan order ---------------------------------------------------
         int found = 0, id0 = -1, minLoc = 999999999, maxLoc = -1, count = 0;
         int lo = 0, hi = L;
         bool discarded = false, ktrimmed = false;
-        if (scan) {
-            if (FMODE == FM_KTRIM_R) {
-                for (int j = 0; j < nsteps && !found; j++) {
-                    uint32_t cb = cand[j * 32 + lane];
-                    while (cb) {
-                        const int b = __ffs(cb) - 1;
-                        cb &= cb - 1;
-                        const int i = 16 * j + b;
-                        const int id = exact_full(st, s + i, p, t);
-                        if (id > 0) {
-                            id0 = id;
-                            minLoc = i - k + 1;
-                            maxLoc = i;
-                            found = 1;
-                            break;
-                        }
-                    }
-                }
-            } else if (FMODE == FM_KTRIM_L) {
-                for (int j = 0; j < nsteps && !found; j++) {  // first hit: id0
-                    uint32_t cb = cand[j * 32 + lane];
-                    while (cb) {
-                        const int b = __ffs(cb) - 1;
-                        cb &= cb - 1;
-                        const int i = 16 * j + b;
-                        const int id = exact_full(st, s + i, p, t);
-                        if (id > 0) {
-                            id0 = id;
-                            minLoc = i - k + 1;
-                            maxLoc = i;
-                            found = 1;
-                            break;
-                        }
-                    }
-                }
-                if (found) {  // last hit: maxLoc
-                    bool done = false;
-                    for (int j = nsteps - 1; j >= 0 && !done; j--) {
-                        uint32_t cb = cand[j * 32 + lane];
-                        while (cb) {
-                            const int b = 31 - __clz(cb);
-                            cb &= ~(1u << b);
-                            const int i = 16 * j + b;
-                            if (i <= maxLoc) {
-                                done = true;
-                                break;
-                            }
-                            if (exact_full(st, s + i, p, t) > 0) {
-                                maxLoc = i;
-                                done = true;
-                                break;
-                            }
-                        }
-                    }
-                }
-            } else {  // FM_KFILTER: countSetKmers, jgi/BBDuk.java:3395-3457
-                const int mb = p.maxBadKmers0;
-                bool stop = false;
-                for (int j = 0; j < nsteps && !stop; j++) {
-                    uint32_t cb = cand[j * 32 + lane];
-                    while (cb) {
-                        const int b = __ffs(cb) - 1;
-                        cb &= cb - 1;
-                        const int id = exact_full(st, s + 16 * j + b, p, t);
-                        if (id > 0) {
-                            if (found == mb) {
-                                id0 = id;
-                                found++;
-                                stop = true;
-                                break;
-                            }
-                            found++;
-                        }
-                    }
-                }
-                count = found;
-                if (count > mb) discarded = true;
+        {
+            const unsigned long long f64 = first64[lane];
+            if (scan && f64 != ~0ull) {
+                const int pos = (int)(f64 >> 32);
+                id0 = (int)(unsigned int)f64;
+                found = 1;
+                minLoc = pos - k + 1;
+                maxLoc = (FMODE == FM_KTRIM_L) ? lastpos[lane] : pos;
             }
         }
-        if (FMODE != FM_KFILTER) {
+        if (FMODE == FM_KFILTER) {  // countSetKmers with maxBadKmers==0 (jgi/BBDuk.java:3395-3457)
+            count = found;
+            discarded = found > 0;
+        } else {
             // ktrim guard (jgi/BBDuk.java:3868): reads shorter than k still get the short-k-mer tails
-            const bool tscan = live && t.stored > 0 && p.useShortKmers && L >= max(1, min(k, p.mink)) && !found &&
-                               !((p.skipR1 && !(paired && (lane & 1))) || (p.skipR2 && paired && (lane & 1)));
+            const bool tscan = live && t.stored > 0 && p.useShortKmers && L >= max(1, min(k, p.mink)) && !found && !skip;
             int minLocX = 999999999, maxLocX = -1;
             if (found) {
                 minLocX = minLoc + k;
@@ -409,7 +386,7 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
                         rkmer = ((rkmer << 2) | (def ? (3u - c) : 0u)) & p.mask;
                         if (n >= p.mink) {
                             const uint64_t key = bb_to_value(p, kmer, rkmer, 1ull << (2 * n));
-                            if (!USE_FILTER || filter_pass(filt, geo.nfw, key)) {
+                            if (filter_pass(filt, geo.nfw, key)) {
                                 const int id = bb_table_get(t, key);
                                 if (id > 0) {
                                     if (id0 < 0) id0 = id;
@@ -434,7 +411,7 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
                         const int n = i + 1;
                         if (n >= p.mink) {
                             const uint64_t key = bb_to_value(p, kmer, rkmer, 1ull << (2 * n));
-                            if (!USE_FILTER || filter_pass(filt, geo.nfw, key)) {
+                            if (filter_pass(filt, geo.nfw, key)) {
                                 const int id = bb_table_get(t, key);
                                 if (id > 0) {
                                     if (id0 < 0) id0 = id;
@@ -458,7 +435,7 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
                 }
                 if (FMODE == FM_KTRIM_L) {
                     const int leftLoc = p.ktrimExclusive ? maxLocX + 1 : maxLoc + 1;
-                    count = trim_amounts(lo, hi, leftLoc, L - (L - 1) - 1, 1);
+                    count = trim_amounts(lo, hi, leftLoc, 0, 1);  // trimToPosition(r, leftLoc, L-1, 1)
                 } else {
                     const int rightLoc = p.ktrimExclusive ? minLocX - 1 : minLoc - 1;
                     count = trim_amounts(lo, hi, 0, L - rightLoc - 1, 1);
@@ -529,8 +506,6 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
                 s_ro += 1;
                 s_bo += len_cur;
             }
-        }
-        if (live) {
             if (out.id0) out.id0[r] = id0;
             if (out.id0b) out.id0b[r] = -1;
             if (out.lo) out.lo[r] = lo;
@@ -552,15 +527,14 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
     }
 }
 
-FastGeom make_geom(const BBTable &t, int max_read_len, bool use_filter) {
+FastGeom make_geom(const BBTable &t, int max_read_len) {
     FastGeom g;
     const int lmax = std::max(max_read_len, 16);
     g.nch = (32 * lmax + 15 + 15) / 16 + 1;
-    g.cwords = (lmax + 15) / 16 + 1;
-    int wb = (g.nch + PAD + TAIL) * 4 + ((g.nch + PAD + TAIL + 1) & ~1) * 2 + g.cwords * 32 * 2;
+    int wb = 32 * 8 + 32 * 4 + QCAP * 4 + (g.nch + PAD + TAIL) * 4 + ((g.nch + PAD + TAIL + 1) & ~1) * 2;
     wb = (wb + 15) & ~15;
     g.warp_bytes = wb;
-    g.nfw = use_filter ? t.n_filter_words : 0;
+    g.nfw = t.n_filter_words;
     const int avail = FAST_SMEM_LIMIT - (int)g.nfw * 4 - 64;
     g.warps = std::min(32, avail / wb);
     return g;
@@ -575,7 +549,7 @@ bool filter_useful(const BBTable &t) {
 
 FastPlan plan_fast(const BBParams &p, const BBTable &t, int max_read_len) {
     FastPlan pl{false, max_read_len, 0, 0};
-    const bool mode_ok = (p.mode == MODE_KTRIM) || (p.mode == MODE_KFILTER);
+    const bool mode_ok = (p.mode == MODE_KTRIM) || (p.mode == MODE_KFILTER && p.maxBadKmers0 == 0);
     if (!mode_ok) return pl;
     if (p.qHammingDistance != 0 || (p.useShortKmers && p.qHammingDistance2 != 0)) return pl;
     if (p.speed != 0 || p.qSkip != 1 || p.restrictLeft != 0 || p.restrictRight != 0) return pl;
@@ -583,7 +557,7 @@ FastPlan plan_fast(const BBParams &p, const BBTable &t, int max_read_len) {
     if (p.k < 2) return pl;
     if (max_read_len > MAX_FAST_LEN) max_read_len = MAX_FAST_LEN;  // longer reads are handed off per tile
     if (!filter_useful(t)) return pl;  // HBM-resident tables: handled by the generic kernel for now
-    const FastGeom g = make_geom(t, max_read_len, true);
+    const FastGeom g = make_geom(t, max_read_len);
     if (g.warps < 8) return pl;
     pl.usable = true;
     pl.max_read_len = max_read_len;
@@ -596,7 +570,7 @@ int launch_fast(const FastPlan &plan, const uint8_t *d_bases, const uint32_t *d_
                 const BBParams &p, const BBTable &t, const bbduk_out &out, bbduk_stats *d_stats,
                 unsigned long long *scaf_reads, unsigned long long *scaf_bases, int32_t *d_handoff,
                 unsigned int *d_handoff_n, int sm_count, cudaStream_t st) {
-    const FastGeom g = make_geom(t, plan.max_read_len, true);
+    const FastGeom g = make_geom(t, plan.max_read_len);
     const int threads = g.warps * 32;
     const int64_t n_tiles = (n_reads + 31) / 32;
     const int blocks = (int)std::min<int64_t>(sm_count, (n_tiles + g.warps - 1) / g.warps);
@@ -606,7 +580,12 @@ int launch_fast(const FastPlan &plan, const uint8_t *d_bases, const uint32_t *d_
                                                        scaf_bases, d_handoff, d_handoff_n, g);
         return cudaGetLastError() == cudaSuccess ? 1 : -1;
     };
-    if (p.mode == MODE_KFILTER) return go(bbduk_fast_kernel<FM_KFILTER, true>);
-    if (p.ktrimLeft) return go(bbduk_fast_kernel<FM_KTRIM_L, true>);
-    return go(bbduk_fast_kernel<FM_KTRIM_R, true>);
+    const bool k16 = p.k >= 16;
+#define BB_DISPATCH(FM)                                                                                  \
+    (p.rcomp ? (k16 ? go(bbduk_fast_kernel<FM, true, true>) : go(bbduk_fast_kernel<FM, true, false>))    \
+             : (k16 ? go(bbduk_fast_kernel<FM, false, true>) : go(bbduk_fast_kernel<FM, false, false>)))
+    if (p.mode == MODE_KFILTER) return BB_DISPATCH(FM_KFILTER);
+    if (p.ktrimLeft) return BB_DISPATCH(FM_KTRIM_L);
+    return BB_DISPATCH(FM_KTRIM_R);
+#undef BB_DISPATCH
 }

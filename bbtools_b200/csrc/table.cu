@@ -24,6 +24,13 @@
         }                                                                                             \
     } while (0)
 
+__host__ __device__ __forceinline__ uint32_t bucket_shift_of(uint64_t slot_mask) {
+    // n_slots = slot_mask+1 = 2^m  ->  34 - m
+    int m = 0;
+    while ((slot_mask >> m) & 1ull) m++;
+    return (uint32_t)(34 - m);
+}
+
 struct Seed {
     uint64_t kmer;
     int32_t id;
@@ -154,7 +161,7 @@ __device__ __forceinline__ bool apply_op(uint64_t kmer, int len, int extra, int 
 __device__ __forceinline__ int put_kmer(uint64_t *keys, int32_t *vals, uint64_t slot_mask, const BBParams &p,
                                         uint64_t kmer, int len, int id, int *overflow) {
     const uint64_t key = bb_to_value(p, kmer, bb_rcomp(kmer, len), 1ull << (2 * len));
-    return bb_table_put(keys, vals, slot_mask, key, id, overflow);
+    return bb_table_put(keys, vals, slot_mask, bucket_shift_of(slot_mask), key, id, overflow);
 }
 
 // dist = number of mutate() recursion levels; prefix_levels = dist-1 levels are decoded from the
@@ -178,7 +185,7 @@ __global__ void expand_kernel(const Seed *__restrict__ seeds, int64_t n_seeds, i
     if (dist == 0) {
         // addToMap hdist==0 branch: speed filter applies only here (:2366-2372)
         const uint64_t key = bb_to_value(p, km, bb_rcomp(km, len), 1ull << (2 * len));
-        if (bb_passes_speed(p, key)) made += bb_table_put(keys, vals, slot_mask, key, sd.id, overflow);
+        if (bb_passes_speed(p, key)) made += bb_table_put(keys, vals, slot_mask, bucket_shift_of(slot_mask), key, sd.id, overflow);
         if (made) atomicAdd(created, (unsigned long long)made);
         return;
     }
@@ -215,7 +222,7 @@ __global__ void rehash_kernel(const uint64_t *__restrict__ okeys, const int32_t 
                               uint64_t *keys, int32_t *vals, uint64_t slot_mask, int *overflow) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_old; i += (int64_t)gridDim.x * blockDim.x) {
         const uint64_t k = okeys[i];
-        if (k != BB_EMPTY_KEY) bb_table_put(keys, vals, slot_mask, k, ovals[i], overflow);
+        if (k != BB_EMPTY_KEY) bb_table_put(keys, vals, slot_mask, bucket_shift_of(slot_mask), k, ovals[i], overflow);
     }
 }
 
@@ -230,7 +237,7 @@ __global__ void filter_build_kernel(const uint64_t *__restrict__ keys, int64_t n
 }
 
 static int64_t pow2ceil(int64_t x) {
-    int64_t p = 4;
+    int64_t p = 1024;
     while (p < x) p <<= 1;
     return p;
 }
@@ -282,6 +289,7 @@ BBTable DeviceTable::view() const {
     t.keys = d_keys;
     t.vals = d_vals;
     t.slot_mask = (uint64_t)n_slots - 1;
+    t.bucket_shift = bucket_shift_of(t.slot_mask);
     t.filter = d_filter;
     t.n_filter_words = n_filter_words;
     t.n_scaffolds = n_scaffolds;
@@ -385,6 +393,7 @@ int DeviceTable::build(const BBParams &p, const std::vector<uint8_t> &ref, const
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     int64_t slots = pow2ceil((int64_t)(bound * 100.0 / load_pct) + 4);
+    if (slots > (1ll << 34)) slots = 1ll << 34;
     while ((double)slots * 12.0 > 0.8 * (double)free_b && slots > 1024) slots >>= 1;
     if (alloc(slots, filter_words, err, errlen)) {
         cleanup();
