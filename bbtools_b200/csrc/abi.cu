@@ -334,13 +334,19 @@ int bbduk_b200_table_describe(bbduk_handle *h, bbduk_table_desc *d) {
     if (!h->finalized) return set_err(h, "table_describe before finalize");
     memset(d, 0, sizeof *d);
     d->n_slots = h->table.n_slots;
-    d->n_filter_words = h->table.n_filter_words;
+    d->n_filter_words = h->table.total_filter_words();
     d->stored_kmers = h->table.stored;
     d->n_scaffolds = h->table.n_scaffolds;
     d->d_keys = h->table.d_keys;
     d->d_vals = h->table.d_vals;
     d->d_filter = h->table.d_filter;
     d->scalars[0] = h->table.ref_kmers;
+    d->scalars[1] = h->table.n_filter_words;
+    d->scalars[2] = h->table.part_words;
+    d->scalars[3] = h->table.short_words;
+    d->scalars[4] = h->table.n_parts | ((int64_t)h->table.part_w << 8);
+    d->scalars[5] = (int64_t)h->table.part_lag[0] | ((int64_t)h->table.part_lag[1] << 8) |
+                    ((int64_t)h->table.part_lag[2] << 16) | ((int64_t)h->table.part_lag[3] << 24);
     return 0;
 }
 
@@ -354,6 +360,13 @@ int bbduk_b200_table_alloc(bbduk_handle *h, bbduk_table_desc *d) {
     h->table.stored = d->stored_kmers;
     h->table.n_scaffolds = d->n_scaffolds;
     h->table.ref_kmers = d->scalars[0];
+    h->table.n_filter_words = (uint32_t)d->scalars[1];
+    h->table.part_words = (uint32_t)d->scalars[2];
+    h->table.short_words = (uint32_t)d->scalars[3];
+    h->table.n_parts = (int32_t)(d->scalars[4] & 0xFF);
+    h->table.part_w = (int32_t)(d->scalars[4] >> 8);
+    for (int j = 0; j < 4; j++) h->table.part_lag[j] = (int32_t)((d->scalars[5] >> (8 * j)) & 0xFF);
+    if ((int64_t)h->table.total_filter_words() != d->n_filter_words) return set_err(h, "inconsistent filter geometry");
     d->d_keys = h->table.d_keys;
     d->d_vals = h->table.d_vals;
     d->d_filter = h->table.d_filter;

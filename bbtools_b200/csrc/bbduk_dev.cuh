@@ -107,3 +107,12 @@ __device__ __forceinline__ uint32_t bb_filter_word(uint32_t t, uint32_t n_words)
 __device__ __forceinline__ uint32_t bb_filter_bits(uint32_t t) {
     return __funnelshift_l(BB_FPAT1, BB_FPAT1, t) | __funnelshift_l(BB_FPAT2, BB_FPAT2, t >> 5);
 }
+
+// ---- pigeonhole part filter -------------------------------------------------------------------------
+// A window can only hit the table if, on one strand, it agrees with an UNMUTATED reference k-mer on at
+// least one of hdist+1 disjoint parts (substitutions only). The filter holds the part values of every
+// reference k-mer and of its reverse complement, so the query needs the forward window only.
+__device__ __forceinline__ uint32_t bb_phash(uint32_t v) { return v * 0x9E3779B1u; }
+__device__ __forceinline__ uint32_t bb_part_bits(uint32_t t) {
+    return __funnelshift_l(1u, 1u, t) | __funnelshift_l(1u, 1u, t >> 5);  // 1<<(t&31) | 1<<((t>>5)&31)
+}

@@ -46,8 +46,14 @@ struct BBTable {
     const int32_t *vals;    // [n_slots]; scaffold id (min over writers)
     uint64_t slot_mask;     // n_slots-1 (n_slots power of two, >= 1024)
     uint32_t bucket_shift;  // 34 - log2(n_slots): bucket = hash32 >> bucket_shift
-    const uint32_t *filter; // blocked bloom image of all keys, n_filter_words 32-bit words (may be null)
-    uint32_t n_filter_words;
+    // on-chip filter images, one device buffer: [canonical bloom of all keys | part filter | short-key bloom]
+    const uint32_t *filter;
+    uint32_t n_filter_words;  // canonical bloom words
+    uint32_t part_words;      // part filter words (0 = not available for this configuration)
+    uint32_t short_words;     // bloom over the short (len<k) keys only
+    int32_t n_parts;          // pigeonhole parts = hdist+1
+    int32_t part_w;           // bases per part (<=16)
+    int32_t part_lag[4];      // part j is the part_w-mer that ends part_lag[j] bases before the window end
     int32_t n_scaffolds;
     int64_t stored;         // distinct keys
 };

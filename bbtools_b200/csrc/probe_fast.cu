@@ -38,7 +38,9 @@ struct FastGeom {
     int warps;        // warps per block
     int nch;          // staged 16-base chunks per warp (capacity, without padding)
     int warp_bytes;   // shared memory per warp
-    uint32_t nfw;     // filter words
+    uint32_t nfw;     // words of the main on-chip filter (canonical bloom, or the part filter)
+    uint32_t nsw;     // words of the short-key bloom that follows it (part-filter kernels only)
+    uint32_t src_off; // word offset of the main filter inside BBTable::filter
 };
 
 __device__ __forceinline__ uint32_t pair_reverse_complement(uint32_t x) {
@@ -161,7 +163,10 @@ __device__ __forceinline__ uint32_t smear_right(uint64_t x, int n) {
 
 enum { FM_KTRIM_R = 0, FM_KTRIM_L = 1, FM_KFILTER = 2 };
 
-template <int FMODE, bool RCOMP, bool K16>
+// PARTS selects the scan: false = canonical k-mer against the bloom image of all keys;
+// true = forward part_w-mer against the pigeonhole part filter (see bbduk_dev.cuh), one lookup per
+// position, the hdist+1 parts of a window being the same lookup at different lags.
+template <int FMODE, bool RCOMP, bool K16, bool PARTS>
 __global__ void __launch_bounds__(1024, 1)
 bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ offsets, int64_t n_reads, int paired,
                   BBParams p, BBTable t, bbduk_out out, bbduk_stats *stats, unsigned long long *scaf_reads,
@@ -169,14 +174,16 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t *filt = smem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t *wbase = reinterpret_cast<uint8_t *>(smem + geo.nfw) + (size_t)warp * geo.warp_bytes;
+    const uint32_t *filt_short = PARTS ? smem + geo.nfw : smem;  // bloom consulted by the short-k-mer tails
+    const uint32_t n_short = PARTS ? geo.nsw : geo.nfw;
+    uint8_t *wbase = reinterpret_cast<uint8_t *>(smem + geo.nfw + geo.nsw) + (size_t)warp * geo.warp_bytes;
     unsigned long long *first64 = reinterpret_cast<unsigned long long *>(wbase);  // [32] (pos<<32 | id) of the first hit
     int *lastpos = reinterpret_cast<int *>(first64 + 32);                         // [32] last hit position
     uint32_t *queue = reinterpret_cast<uint32_t *>(lastpos + 32);                 // [QCAP]
     uint32_t *Fs = queue + QCAP;
     uint16_t *Ds = reinterpret_cast<uint16_t *>(Fs + geo.nch + PAD + TAIL);
 
-    for (uint32_t i = threadIdx.x; i < geo.nfw; i += blockDim.x) filt[i] = __ldg(t.filter + i);
+    for (uint32_t i = threadIdx.x; i < geo.nfw + geo.nsw; i += blockDim.x) filt[i] = __ldg(t.filter + geo.src_off + i);
     for (int i = lane; i < PAD; i += 32) {
         Fs[i] = 0;
         Ds[i] = 0;
@@ -269,40 +276,61 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
 
         uint32_t f_m2 = 0, f_m1 = 0, f_0 = 0, r_0 = 0, r_1 = 0, r_2 = 0;
         uint32_t und_prev = 0;  // undefined bits of the previous 32 positions (bit 31 = oldest)
-        if (scan && RCOMP) {
+        uint64_t mhist = 0;     // PARTS: part-filter results, bit 32+b = position 16j+b, lower bits = older positions
+        const uint32_t part_vm = (t.part_w >= 16) ? 0xFFFFFFFFu : ((1u << (2 * t.part_w)) - 1u);
+        if (!PARTS && scan && RCOMP) {
             r_0 = pair_reverse_complement(st.f16(s - (k - 1)));
             r_1 = pair_reverse_complement(st.f16(s + 16 - (k - 1)));
         }
         for (int j = 0; j < max_steps; j++) {
             uint32_t cbits = 0;
-            if (scan && j < nsteps) {
+            bool stepping = scan && j < nsteps;
+            if (FMODE != FM_KTRIM_L && stepping && first64[lane] != ~0ull) stepping = false;  // first hit known: done
+            if (stepping) {
                 f_0 = st.f16(s + 16 * j);
-                if (RCOMP) r_2 = pair_reverse_complement(st.f16(s + 16 * (j + 2) - (k - 1)));
+                if (PARTS) {
+                    uint32_t mb = 0;
 #pragma unroll
-                for (int b = 0; b < 16; b++) {
-                    const int sh = 2 * (15 - b);
-                    uint32_t klo = __funnelshift_r(f_0, f_m1, sh);
-                    uint32_t khi = __funnelshift_r(f_m1, f_m2, sh) & mask_hi;
-                    if (!K16) klo &= mask_lo;
-                    if (RCOMP) {
-                        uint32_t rlo = __funnelshift_r(r_0, r_1, 2 * b);
-                        const uint32_t rhi = __funnelshift_r(r_1, r_2, 2 * b) & mask_hi;
-                        if (!K16) rlo &= mask_lo;
-                        const bool gt = (((uint64_t)rhi << 32) | rlo) > (((uint64_t)khi << 32) | klo);
-                        klo = gt ? rlo : klo;
-                        khi = gt ? rhi : khi;
+                    for (int b = 0; b < 16; b++) {
+                        const uint32_t v = __funnelshift_r(f_0, f_m1, 2 * (15 - b)) & part_vm;  // part_w bases ending at 16j+b
+                        const uint32_t tt = bb_phash(v);
+                        const uint32_t pat = bb_part_bits(tt);
+                        const bool pass = (filt[bb_filter_word(tt, geo.nfw)] & pat) == pat;
+                        mb |= pass ? (1u << b) : 0u;
                     }
-                    klo = (klo & mm_lo) | km_lo;
-                    khi = (khi & mm_hi) | km_hi;
-                    const uint32_t tt = bb_fhash(klo, khi);
-                    const uint32_t pat = bb_filter_bits(tt);
-                    const bool pass = (filt[bb_filter_word(tt, geo.nfw)] & pat) == pat;
-                    cbits |= pass ? (1u << b) : 0u;
+                    mhist |= (uint64_t)mb << 32;
+                    for (int q = 0; q < t.n_parts; q++) cbits |= (uint32_t)(mhist >> (32 - t.part_lag[q]));
+                    cbits &= 0xFFFFu;
+                    mhist >>= 16;
+                    f_m1 = f_0;
+                } else {
+                    if (RCOMP) r_2 = pair_reverse_complement(st.f16(s + 16 * (j + 2) - (k - 1)));
+#pragma unroll
+                    for (int b = 0; b < 16; b++) {
+                        const int sh = 2 * (15 - b);
+                        uint32_t klo = __funnelshift_r(f_0, f_m1, sh);
+                        uint32_t khi = __funnelshift_r(f_m1, f_m2, sh) & mask_hi;
+                        if (!K16) klo &= mask_lo;
+                        if (RCOMP) {
+                            uint32_t rlo = __funnelshift_r(r_0, r_1, 2 * b);
+                            const uint32_t rhi = __funnelshift_r(r_1, r_2, 2 * b) & mask_hi;
+                            if (!K16) rlo &= mask_lo;
+                            const bool gt = (((uint64_t)rhi << 32) | rlo) > (((uint64_t)khi << 32) | klo);
+                            klo = gt ? rlo : klo;
+                            khi = gt ? rhi : khi;
+                        }
+                        klo = (klo & mm_lo) | km_lo;
+                        khi = (khi & mm_hi) | km_hi;
+                        const uint32_t tt = bb_fhash(klo, khi);
+                        const uint32_t pat = bb_filter_bits(tt);
+                        const bool pass = (filt[bb_filter_word(tt, geo.nfw)] & pat) == pat;
+                        cbits |= pass ? (1u << b) : 0u;
+                    }
+                    f_m2 = f_m1;
+                    f_m1 = f_0;
+                    r_0 = r_1;
+                    r_1 = r_2;
                 }
-                f_m2 = f_m1;
-                f_m1 = f_0;
-                r_0 = r_1;
-                r_1 = r_2;
                 if (any_undef) {
                     // every window that contains an undefined base is decided by the exact evaluator
                     uint32_t dd = st.d16(s + 16 * j);
@@ -386,7 +414,7 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
                         rkmer = ((rkmer << 2) | (def ? (3u - c) : 0u)) & p.mask;
                         if (n >= p.mink) {
                             const uint64_t key = bb_to_value(p, kmer, rkmer, 1ull << (2 * n));
-                            if (filter_pass(filt, geo.nfw, key)) {
+                            if (filter_pass(filt_short, n_short, key)) {
                                 const int id = bb_table_get(t, key);
                                 if (id > 0) {
                                     if (id0 < 0) id0 = id;
@@ -411,7 +439,7 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
                         const int n = i + 1;
                         if (n >= p.mink) {
                             const uint64_t key = bb_to_value(p, kmer, rkmer, 1ull << (2 * n));
-                            if (filter_pass(filt, geo.nfw, key)) {
+                            if (filter_pass(filt_short, n_short, key)) {
                                 const int id = bb_table_get(t, key);
                                 if (id > 0) {
                                     if (id0 < 0) id0 = id;
@@ -527,22 +555,34 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
     }
 }
 
-FastGeom make_geom(const BBTable &t, int max_read_len) {
+bool parts_ok(const BBParams &p, const BBTable &t) {
+    return t.part_words > 0 && t.n_parts > 0 && p.editDistance == 0 && (!p.useShortKmers || t.short_words > 0);
+}
+
+bool canon_ok(const BBTable &t) {
+    // beyond ~24 keys per filter word the image is saturated and every position would be a candidate
+    return t.filter != nullptr && t.n_filter_words > 0 && t.stored <= (int64_t)t.n_filter_words * 24;
+}
+
+FastGeom make_geom(const BBParams &p, const BBTable &t, int max_read_len) {
     FastGeom g;
     const int lmax = std::max(max_read_len, 16);
     g.nch = (32 * lmax + 15 + 15) / 16 + 1;
     int wb = 32 * 8 + 32 * 4 + QCAP * 4 + (g.nch + PAD + TAIL) * 4 + ((g.nch + PAD + TAIL + 1) & ~1) * 2;
     wb = (wb + 15) & ~15;
     g.warp_bytes = wb;
-    g.nfw = t.n_filter_words;
-    const int avail = FAST_SMEM_LIMIT - (int)g.nfw * 4 - 64;
+    if (parts_ok(p, t)) {
+        g.nfw = t.part_words;
+        g.nsw = t.short_words;
+        g.src_off = t.n_filter_words;
+    } else {
+        g.nfw = t.n_filter_words;
+        g.nsw = 0;
+        g.src_off = 0;
+    }
+    const int avail = FAST_SMEM_LIMIT - (int)(g.nfw + g.nsw) * 4 - 64;
     g.warps = std::min(32, avail / wb);
     return g;
-}
-
-bool filter_useful(const BBTable &t) {
-    // beyond ~24 keys per filter word the image is saturated and every position would be a candidate
-    return t.filter != nullptr && t.n_filter_words > 0 && t.stored <= (int64_t)t.n_filter_words * 24;
 }
 
 }  // namespace
@@ -556,13 +596,13 @@ FastPlan plan_fast(const BBParams &p, const BBTable &t, int max_read_len) {
     if (p.kbig > p.k || p.minKmerFraction != 0.0f) return pl;
     if (p.k < 2) return pl;
     if (max_read_len > MAX_FAST_LEN) max_read_len = MAX_FAST_LEN;  // longer reads are handed off per tile
-    if (!filter_useful(t)) return pl;  // HBM-resident tables: handled by the generic kernel for now
-    const FastGeom g = make_geom(t, max_read_len);
+    if (!parts_ok(p, t) && !canon_ok(t)) return pl;  // HBM-resident tables: handled by the generic kernel for now
+    const FastGeom g = make_geom(p, t, max_read_len);
     if (g.warps < 8) return pl;
     pl.usable = true;
     pl.max_read_len = max_read_len;
-    pl.smem_bytes = (int)g.nfw * 4 + g.warps * g.warp_bytes + 64;
-    pl.filter_words = (int)g.nfw;
+    pl.smem_bytes = (int)(g.nfw + g.nsw) * 4 + g.warps * g.warp_bytes + 64;
+    pl.filter_words = (int)(g.nfw + g.nsw);
     return pl;
 }
 
@@ -570,7 +610,7 @@ int launch_fast(const FastPlan &plan, const uint8_t *d_bases, const uint32_t *d_
                 const BBParams &p, const BBTable &t, const bbduk_out &out, bbduk_stats *d_stats,
                 unsigned long long *scaf_reads, unsigned long long *scaf_bases, int32_t *d_handoff,
                 unsigned int *d_handoff_n, int sm_count, cudaStream_t st) {
-    const FastGeom g = make_geom(t, plan.max_read_len);
+    const FastGeom g = make_geom(p, t, plan.max_read_len);
     const int threads = g.warps * 32;
     const int64_t n_tiles = (n_reads + 31) / 32;
     const int blocks = (int)std::min<int64_t>(sm_count, (n_tiles + g.warps - 1) / g.warps);
@@ -581,9 +621,11 @@ int launch_fast(const FastPlan &plan, const uint8_t *d_bases, const uint32_t *d_
         return cudaGetLastError() == cudaSuccess ? 1 : -1;
     };
     const bool k16 = p.k >= 16;
-#define BB_DISPATCH(FM)                                                                                  \
-    (p.rcomp ? (k16 ? go(bbduk_fast_kernel<FM, true, true>) : go(bbduk_fast_kernel<FM, true, false>))    \
-             : (k16 ? go(bbduk_fast_kernel<FM, false, true>) : go(bbduk_fast_kernel<FM, false, false>)))
+    const bool parts = parts_ok(p, t);
+#define BB_DISPATCH(FM)                                                                                               \
+    (parts ? go(bbduk_fast_kernel<FM, true, true, true>)                                                              \
+           : p.rcomp ? (k16 ? go(bbduk_fast_kernel<FM, true, true, false>) : go(bbduk_fast_kernel<FM, true, false, false>))    \
+                     : (k16 ? go(bbduk_fast_kernel<FM, false, true, false>) : go(bbduk_fast_kernel<FM, false, false, false>)))
     if (p.mode == MODE_KFILTER) return BB_DISPATCH(FM_KFILTER);
     if (p.ktrimLeft) return BB_DISPATCH(FM_KTRIM_L);
     return BB_DISPATCH(FM_KTRIM_R);

@@ -236,6 +236,37 @@ __global__ void filter_build_kernel(const uint64_t *__restrict__ keys, int64_t n
     }
 }
 
+// short-key bloom: keys whose length marker sits below bit 2k (the mink..k-1 tails)
+__global__ void short_filter_build_kernel(const uint64_t *__restrict__ keys, int64_t n, uint64_t kmask, uint32_t *filter,
+                                          uint32_t n_words) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = keys[i];
+        if (k != BB_EMPTY_KEY && k < kmask) {
+            const uint32_t t = bb_fhash64(k);
+            atomicOr(filter + bb_filter_word(t, n_words), bb_filter_bits(t));
+        }
+    }
+}
+
+// part filter: the part values of every full-length reference k-mer, both strands (if rcomp)
+__global__ void part_filter_build_kernel(const Seed *__restrict__ seeds, int64_t n, int k, int rcomp, int n_parts, int w,
+                                         int lag0, int lag1, int lag2, int lag3, uint32_t *filter, uint32_t n_words) {
+    const int lags[4] = {lag0, lag1, lag2, lag3};
+    const uint32_t vm = (w >= 16) ? 0xFFFFFFFFu : ((1u << (2 * w)) - 1u);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t f = seeds[i].kmer;
+        const uint64_t r = bb_rcomp(f, k);
+        for (int o = 0; o < (rcomp ? 2 : 1); o++) {
+            const uint64_t x = o ? r : f;
+            for (int j = 0; j < n_parts; j++) {
+                const uint32_t v = (uint32_t)(x >> (2 * lags[j])) & vm;
+                const uint32_t t = bb_phash(v);
+                atomicOr(filter + bb_filter_word(t, n_words), bb_part_bits(t));
+            }
+        }
+    }
+}
+
 static int64_t pow2ceil(int64_t x) {
     int64_t p = 1024;
     while (p < x) p <<= 1;
@@ -273,14 +304,13 @@ void DeviceTable::release() {
     n_slots = 0;
 }
 
-int DeviceTable::alloc(int64_t slots, uint32_t filter_words, char *err, int errlen) {
+int DeviceTable::alloc(int64_t slots, uint32_t total_words, char *err, int errlen) {
     release();
     n_slots = slots;
-    n_filter_words = filter_words;
     owns = true;
     CK(cudaMalloc(&d_keys, sizeof(uint64_t) * (size_t)slots));
     CK(cudaMalloc(&d_vals, sizeof(int32_t) * (size_t)slots));
-    CK(cudaMalloc(&d_filter, sizeof(uint32_t) * (size_t)filter_words));
+    CK(cudaMalloc(&d_filter, sizeof(uint32_t) * (size_t)std::max<uint32_t>(total_words, 1)));
     return 0;
 }
 
@@ -292,6 +322,11 @@ BBTable DeviceTable::view() const {
     t.bucket_shift = bucket_shift_of(t.slot_mask);
     t.filter = d_filter;
     t.n_filter_words = n_filter_words;
+    t.part_words = part_words;
+    t.short_words = short_words;
+    t.n_parts = n_parts;
+    t.part_w = part_w;
+    for (int j = 0; j < 4; j++) t.part_lag[j] = part_lag[j];
     t.n_scaffolds = n_scaffolds;
     t.stored = stored;
     return t;
@@ -395,13 +430,49 @@ int DeviceTable::build(const BBParams &p, const std::vector<uint8_t> &ref, const
     int64_t slots = pow2ceil((int64_t)(bound * 100.0 / load_pct) + 4);
     if (slots > (1ll << 34)) slots = 1ll << 34;
     while ((double)slots * 12.0 > 0.8 * (double)free_b && slots > 1024) slots >>= 1;
-    if (alloc(slots, filter_words, err, errlen)) {
+    // pigeonhole part geometry (substitution neighbourhoods only): hdist+1 disjoint parts of w bases that
+    // avoid the masked middle; part j ends lag[j] bases before the window end
+    n_filter_words = filter_words;
+    part_words = short_words = 0;
+    n_parts = part_w = 0;
+    if (!edits && dist_full <= 3 && n_full > 0) {
+        const int P = dist_full + 1, k = p.k, mml = p.midMaskLen;
+        int offs[4] = {0, 0, 0, 0}, w = 0;
+        if (mml == 0) {
+            const int stride = k / P;
+            w = std::min(16, stride);
+            for (int j = 0; j < P; j++) offs[j] = (j == P - 1) ? k - w : j * stride;
+        } else {
+            const int a = k - 1 - ((k - mml) / 2 + mml - 1);  // first masked window position
+            const int lenL = a, lenR = k - a - mml;
+            const int PL = (P + 1) / 2, PR = P / 2;
+            const int strideL = lenL / PL, strideR = PR ? lenR / PR : 99;
+            w = std::min(16, std::min(strideL, strideR));
+            for (int j = 0; j < PL; j++) offs[j] = j * strideL;
+            for (int j = 0; j < PR; j++) offs[PL + j] = (j == PR - 1) ? k - w : a + mml + j * strideR;
+        }
+        const double entries = (double)n_full * (p.rcomp ? 2 : 1) * P;
+        const uint32_t pw = 16384;  // 64 KB
+        if (w >= 9 && entries <= (double)pw * 6.0) {
+            n_parts = P;
+            part_w = w;
+            for (int j = 0; j < P; j++) part_lag[j] = k - offs[j] - w;
+            part_words = pw;
+            short_words = p.useShortKmers ? 8192 : 0;  // 32 KB
+        }
+    }
+    if (alloc(slots, total_filter_words(), err, errlen)) {
         cleanup();
         return 1;
     }
     fill_kernel<<<1184, 256, 0, st>>>(d_keys, d_vals, slots);
     (*launches)++;
-    CKC(cudaMemsetAsync(d_filter, 0, sizeof(uint32_t) * filter_words, st));
+    CKC(cudaMemsetAsync(d_filter, 0, sizeof(uint32_t) * total_filter_words(), st));
+    if (part_words) {
+        part_filter_build_kernel<<<296, 256, 0, st>>>(d_full, n_full, p.k, p.rcomp, n_parts, part_w, part_lag[0], part_lag[1],
+                                                      part_lag[2], part_lag[3], d_filter + n_filter_words, part_words);
+        (*launches)++;
+    }
 
     auto launch_expand = [&](const Seed *seeds, int64_t n, int len, int dist, int use_extra) -> int {
         if (n <= 0) return 0;
@@ -455,6 +526,11 @@ int DeviceTable::build(const BBParams &p, const std::vector<uint8_t> &ref, const
     }
     filter_build_kernel<<<1184, 256, 0, st>>>(d_keys, n_slots, d_filter, n_filter_words);
     (*launches)++;
+    if (short_words) {
+        short_filter_build_kernel<<<1184, 256, 0, st>>>(d_keys, n_slots, p.kmask, d_filter + n_filter_words + part_words,
+                                                         short_words);
+        (*launches)++;
+    }
     CKC(cudaGetLastError());
     CKC(cudaStreamSynchronize(st));
     cleanup();
