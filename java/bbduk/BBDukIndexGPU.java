@@ -1,0 +1,77 @@
+package bbduk;
+
+import java.util.ArrayList;
+
+import shared.Shared;
+import stream.Read;
+
+/**
+ * Fourth BBDukIndex implementation (next to BBDukIndexMod / Mask / Mask2): the reference k-mer table
+ * lives in GPU memory and whole batches of reads are answered by one native call.
+ * NOT compiled in this repository (no JDK in the image); it shows the binding a maintainer adds.
+ *
+ * Selected in BBDukLoader's constructor (bbduk/BBDukLoader.java:74-75) by one new flag:
+ *   index = p.gpu ? new BBDukIndexGPU(p) : (p.WAYS==7 ? new BBDukIndexMod(p) : ...);
+ * and used by BBDukProcessorS.processList (bbduk/BBDukProcessorS.java:768) BEFORE the per-read loop:
+ * the processor aggregates lists until >= MIN_BATCH reads, calls processBatch once, then walks the reads
+ * applying (lo, hi, flags) exactly where ktrim()/kmask()/countSetKmers() used to be called
+ * (bbduk/BBDukProcessorS.java:947-1093). The per-k-mer getValue() stays only for dump/verbose.
+ */
+public final class BBDukIndexGPU extends BBDukIndex {
+
+	static { Shared.loadJNI("bbdukcuda"); } // shared/Shared.java:731-779: searches <classpath>/../jni too
+
+	private long handle;
+	public static final int MIN_BATCH=1<<20;
+
+	public BBDukIndexGPU(BBDukParser p){
+		super(p);
+		handle=createNative(marshal(p));
+		if(handle==0){throw new RuntimeException("bbduk_b200_create failed: "+lastErrorNative(0));}
+	}
+
+	/** bbduk_cfg in declaration order (include/bbduk_b200.h); floats as raw int bits */
+	private static int[] marshal(BBDukParser p){
+		return new int[] {0 /*struct_size, set natively*/, 1 /*BBDUK_GEN_S*/, p.kbig>p.k ? p.kbig : p.k, p.mink,
+			p.useShortKmers ? 1 : 0, p.hammingDistance, p.hammingDistance2, p.editDistance, p.editDistance2,
+			p.qHammingDistance, p.qHammingDistance2, p.rcomp ? 1 : 0, p.maskMiddle ? 1 : 0, p.midMaskLen,
+			p.forbidNs ? 1 : 0, p.ktrimLeft ? 1 : 0, p.ktrimRight ? 1 : 0, p.ktrimN ? 1 : 0, p.ksplit ? 1 : 0,
+			p.ktrimExclusive ? 1 : 0, p.trimPad, p.restrictLeft, p.restrictRight, p.skipR1 ? 1 : 0, p.skipR2 ? 1 : 0,
+			p.qSkip, p.speed, p.minSkip, p.maxSkip, p.maxBadKmers0, Float.floatToRawIntBits(p.minKmerFraction),
+			Float.floatToRawIntBits(p.minCoveredFraction), p.findBestMatch ? 1 : 0, p.kmaskFullyCovered ? 1 : 0,
+			p.kmaskLowercase ? 1 : 0, p.trimSymbol, p.minReadLength, Float.floatToRawIntBits(p.minLenFraction),
+			p.removePairsIfEitherBad ? 0 : 1, p.trimPairsEvenly ? 1 : 0, p.trimFailuresTo1bp ? 1 : 0, -1, 0};
+	}
+
+	/** Called by BBDukLoader for every list of scaffolds, in file order (ids continue across calls). */
+	public void addScaffolds(ArrayList<Read> scafs){
+		int total=0; for(Read r : scafs){total+=r.length();}
+		byte[] bases=new byte[total]; long[] off=new long[scafs.size()+1];
+		int pos=0, i=0;
+		for(Read r : scafs){System.arraycopy(r.bases, 0, bases, pos, r.length()); pos+=r.length(); off[++i]=pos;}
+		if(addRefNative(handle, bases, off, scafs.size())!=0){throw new RuntimeException(lastErrorNative(handle));}
+	}
+
+	@Override public void setKmersLoaded(){storedKmers=finalizeNative(handle);}
+
+	/** One aggregated batch; mates adjacent. Arrays are reused by the caller between batches. */
+	public boolean processBatch(byte[] bases, long[] offsets, long nReads, boolean paired,
+			int[] id0, int[] lo, int[] hi, byte[] flags, int[] count, long[] stats8){
+		return processNative(handle, bases, offsets, nReads, paired, id0, lo, hi, flags, count, stats8)==0;
+	}
+
+	@Override public int getValue(long kmer, long rkmer, long lengthMask, int qPos, int len, int qHDist){
+		throw new UnsupportedOperationException("per-k-mer queries are served in batches by processBatch()");
+	}
+
+	@Override public void cleanup(){if(handle!=0){destroyNative(handle); handle=0;}}
+
+	private static native long createNative(int[] cfg);
+	private static native int addRefNative(long h, byte[] bases, long[] offsets, int nSeqs);
+	private static native long finalizeNative(long h);
+	private static native int processNative(long h, byte[] bases, long[] offsets, long nReads, boolean paired,
+			int[] id0, int[] lo, int[] hi, byte[] flags, int[] count, long[] stats8);
+	private static native int scaffoldCountsNative(long h, long[] reads, long[] bases);
+	private static native String lastErrorNative(long h);
+	private static native void destroyNative(long h);
+}

@@ -1,0 +1,96 @@
+/*
+ * BBDukCuda.c -- JNI shim between bbduk.BBDukIndexGPU (Java) and libbbduk_b200.so (C ABI).
+ *
+ * Pure marshalling, modelled on jni/BBMergeOverlapper.c:389-437 of the reference: primitive arrays are
+ * pinned with GetPrimitiveArrayCritical, inputs released with JNI_ABORT, outputs with 0; scalar status
+ * return; no Java exception is thrown from native code; no global native state (the handle is a jlong
+ * owned by the Java object). NOT compiled in this repository's image (no JDK / jni.h); build next to
+ * the reference's jni/ directory:
+ *   gcc -O3 -std=c99 -fPIC -shared -I$JAVA_HOME/include -I$JAVA_HOME/include/linux \
+ *       -I<repo>/include BBDukCuda.c -L<repo>/bbtools_b200 -lbbduk_b200 -o libbbdukcuda.so
+ */
+#include <jni.h>
+#include <string.h>
+
+#include "bbduk_b200.h"
+
+/* int[] cfg carries the bbduk_cfg fields in declaration order; float fields are passed as raw bits */
+JNIEXPORT jlong JNICALL Java_bbduk_BBDukIndexGPU_createNative(JNIEnv *env, jclass cls, jintArray jcfg) {
+    bbduk_cfg cfg;
+    bbduk_b200_cfg_default(&cfg);
+    const jint n = (*env)->GetArrayLength(env, jcfg);
+    jint *c = (jint *)(*env)->GetPrimitiveArrayCritical(env, jcfg, NULL);
+    const size_t bytes = (size_t)n * sizeof(jint);
+    memcpy(&cfg, c, bytes < sizeof cfg ? bytes : sizeof cfg);
+    (*env)->ReleasePrimitiveArrayCritical(env, jcfg, c, JNI_ABORT);
+    cfg.struct_size = (int32_t)sizeof cfg;
+    bbduk_handle *h = NULL;
+    if (bbduk_b200_create(&cfg, &h)) return 0;
+    return (jlong)(intptr_t)h;
+}
+
+JNIEXPORT jint JNICALL Java_bbduk_BBDukIndexGPU_addRefNative(JNIEnv *env, jclass cls, jlong handle, jbyteArray jbases,
+                                                             jlongArray joffsets, jint nSeqs) {
+    jbyte *b = (jbyte *)(*env)->GetPrimitiveArrayCritical(env, jbases, NULL);
+    jlong *o = (jlong *)(*env)->GetPrimitiveArrayCritical(env, joffsets, NULL);
+    const jint rc = bbduk_b200_add_ref((bbduk_handle *)(intptr_t)handle, (const uint8_t *)b, (const int64_t *)o, nSeqs);
+    (*env)->ReleasePrimitiveArrayCritical(env, joffsets, o, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, jbases, b, JNI_ABORT);
+    return rc;
+}
+
+JNIEXPORT jlong JNICALL Java_bbduk_BBDukIndexGPU_finalizeNative(JNIEnv *env, jclass cls, jlong handle) {
+    int64_t stored = -1;
+    if (bbduk_b200_finalize((bbduk_handle *)(intptr_t)handle, &stored)) return -1;
+    return (jlong)stored;
+}
+
+/* One aggregated batch (>= ~1 M reads) in, struct-of-arrays results out.
+ * The library copies out of the pinned Java arrays into its own staging before it returns from the
+ * critical section's memcpy; it never holds a critical array across a CUDA synchronisation point of
+ * another thread because each call owns a private stream + staging slot. */
+JNIEXPORT jint JNICALL Java_bbduk_BBDukIndexGPU_processNative(JNIEnv *env, jclass cls, jlong handle, jbyteArray jbases,
+                                                              jlongArray joffsets, jlong nReads, jboolean paired,
+                                                              jintArray jid0, jintArray jlo, jintArray jhi,
+                                                              jbyteArray jflags, jintArray jcount, jlongArray jstats) {
+    bbduk_out out;
+    bbduk_stats st;
+    memset(&out, 0, sizeof out);
+    jbyte *b = (jbyte *)(*env)->GetPrimitiveArrayCritical(env, jbases, NULL);
+    jlong *o = (jlong *)(*env)->GetPrimitiveArrayCritical(env, joffsets, NULL);
+    if (jid0) out.id0 = (int32_t *)(*env)->GetPrimitiveArrayCritical(env, jid0, NULL);
+    if (jlo) out.lo = (int32_t *)(*env)->GetPrimitiveArrayCritical(env, jlo, NULL);
+    if (jhi) out.hi = (int32_t *)(*env)->GetPrimitiveArrayCritical(env, jhi, NULL);
+    if (jflags) out.flags = (uint8_t *)(*env)->GetPrimitiveArrayCritical(env, jflags, NULL);
+    if (jcount) out.count = (int32_t *)(*env)->GetPrimitiveArrayCritical(env, jcount, NULL);
+    const jint rc = bbduk_b200_process((bbduk_handle *)(intptr_t)handle, (const uint8_t *)b, (const int64_t *)o,
+                                       (int64_t)nReads, paired ? 1 : 0, &out, &st);
+    if (jcount) (*env)->ReleasePrimitiveArrayCritical(env, jcount, out.count, 0);
+    if (jflags) (*env)->ReleasePrimitiveArrayCritical(env, jflags, out.flags, 0);
+    if (jhi) (*env)->ReleasePrimitiveArrayCritical(env, jhi, out.hi, 0);
+    if (jlo) (*env)->ReleasePrimitiveArrayCritical(env, jlo, out.lo, 0);
+    if (jid0) (*env)->ReleasePrimitiveArrayCritical(env, jid0, out.id0, 0);
+    (*env)->ReleasePrimitiveArrayCritical(env, joffsets, o, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, jbases, b, JNI_ABORT);
+    if (jstats && !rc) (*env)->SetLongArrayRegion(env, jstats, 0, 8, (const jlong *)&st);
+    return rc;
+}
+
+JNIEXPORT jint JNICALL Java_bbduk_BBDukIndexGPU_scaffoldCountsNative(JNIEnv *env, jclass cls, jlong handle,
+                                                                     jlongArray jreads, jlongArray jbases) {
+    const jint n = (*env)->GetArrayLength(env, jreads);
+    jlong *r = (jlong *)(*env)->GetPrimitiveArrayCritical(env, jreads, NULL);
+    jlong *b = (jlong *)(*env)->GetPrimitiveArrayCritical(env, jbases, NULL);
+    const jint rc = bbduk_b200_scaffold_counts((bbduk_handle *)(intptr_t)handle, (int64_t *)r, (int64_t *)b, n);
+    (*env)->ReleasePrimitiveArrayCritical(env, jbases, b, 0);
+    (*env)->ReleasePrimitiveArrayCritical(env, jreads, r, 0);
+    return rc;
+}
+
+JNIEXPORT jstring JNICALL Java_bbduk_BBDukIndexGPU_lastErrorNative(JNIEnv *env, jclass cls, jlong handle) {
+    return (*env)->NewStringUTF(env, bbduk_b200_last_error((bbduk_handle *)(intptr_t)handle));
+}
+
+JNIEXPORT void JNICALL Java_bbduk_BBDukIndexGPU_destroyNative(JNIEnv *env, jclass cls, jlong handle) {
+    bbduk_b200_destroy((bbduk_handle *)(intptr_t)handle);
+}
