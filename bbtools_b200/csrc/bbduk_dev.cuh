@@ -112,7 +112,21 @@ __device__ __forceinline__ uint32_t bb_filter_bits(uint32_t t) {
 // A window can only hit the table if, on one strand, it agrees with an UNMUTATED reference k-mer on at
 // least one of hdist+1 disjoint parts (substitutions only). The filter holds the part values of every
 // reference k-mer and of its reverse complement, so the query needs the forward window only.
-__device__ __forceinline__ uint32_t bb_phash(uint32_t v) { return v * 0x9E3779B1u; }
-__device__ __forceinline__ uint32_t bb_part_bits(uint32_t t) {
-    return __funnelshift_l(1u, 1u, t) | __funnelshift_l(1u, 1u, t >> 5);  // 1<<(t&31) | 1<<((t>>5)&31)
+// The part value is the low 2w bits of a 32-bit window v; multiplying by mult = C << (32-2w) discards
+// the higher (foreign) bits for free. g = high half of h*K1 is the well-mixed hash: its top bits pick
+// the word, its low 5 bits one filter bit; a second high-half product picks the other bit. All of it
+// runs on the FMA pipe, which the shift/logic-heavy scan leaves idle.
+#define BB_PART_C 0x9E3779B1u
+__host__ __device__ __forceinline__ uint32_t bb_part_mult(int w) { return (w >= 16) ? BB_PART_C : (BB_PART_C << (32 - 2 * w)); }
+struct BBPartProbe {
+    uint32_t word, b1, b2;  // b1/b2: only their low 5 bits matter
+};
+__device__ __forceinline__ BBPartProbe bb_part_probe(uint32_t v, uint32_t mult, uint32_t n_words) {
+    const uint32_t h = v * mult;
+    const uint32_t g = __umulhi(h, 0x85EBCA77u);
+    BBPartProbe r;
+    r.word = __umulhi(g, n_words);
+    r.b1 = g;
+    r.b2 = __umulhi(h, 0xC2B2AE3Du);
+    return r;
 }

@@ -38,6 +38,7 @@ struct FastGeom {
     int warps;        // warps per block
     int nch;          // staged 16-base chunks per warp (capacity, without padding)
     int warp_bytes;   // shared memory per warp
+    int nbadw;        // words of the per-tile "chunk has an undefined base" bit mask
     uint32_t nfw;     // words of the main on-chip filter (canonical bloom, or the part filter)
     uint32_t nsw;     // words of the short-key bloom that follows it (part-filter kernels only)
     uint32_t src_off; // word offset of the main filter inside BBTable::filter
@@ -151,7 +152,7 @@ __device__ __forceinline__ int trim_amounts(int &lo, int &hi, int left, int righ
 }
 
 // OR of x >> d for d in [0, n): every set bit also covers the n-1 lower bit positions
-__device__ __forceinline__ uint32_t smear_right(uint64_t x, int n) {
+__device__ __forceinline__ uint32_t smear_right(uint32_t x, int n) {
     int have = 1;
     while (have < n) {
         const int s = min(have, n - have);
@@ -179,9 +180,10 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
     uint8_t *wbase = reinterpret_cast<uint8_t *>(smem + geo.nfw + geo.nsw) + (size_t)warp * geo.warp_bytes;
     unsigned long long *first64 = reinterpret_cast<unsigned long long *>(wbase);  // [32] (pos<<32 | id) of the first hit
     int *lastpos = reinterpret_cast<int *>(first64 + 32);                         // [32] last hit position
-    uint32_t *queue = reinterpret_cast<uint32_t *>(lastpos + 32);                 // [QCAP]
-    uint32_t *Fs = queue + QCAP;
+    uint32_t *badw = reinterpret_cast<uint32_t *>(lastpos + 32);                  // [nbadw] chunks with a non-ACGTU base
+    uint32_t *Fs = badw + geo.nbadw;
     uint16_t *Ds = reinterpret_cast<uint16_t *>(Fs + geo.nch + PAD + TAIL);
+    uint16_t *queue = Ds + ((geo.nch + PAD + TAIL + 1) & ~1);                     // [QCAP] (owner lane << 11) | position
 
     for (uint32_t i = threadIdx.x; i < geo.nfw + geo.nsw; i += blockDim.x) filt[i] = __ldg(t.filter + geo.src_off + i);
     for (int i = lane; i < PAD; i += 32) {
@@ -220,6 +222,7 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
             continue;
         }
         // ---- A. stage + convert ---------------------------------------------------------------
+        for (int i = lane; i < geo.nbadw; i += 32) badw[i] = 0;
         __syncwarp();
         for (int c = lane; c < nchunks + TAIL; c += 32) {
             uint32_t f = 0, dbits = 0;
@@ -232,8 +235,10 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
                 classify4(v.w, cw[3], bw[3]);
                 f = (pack4(cw[0]) << 24) | (pack4(cw[1]) << 16) | (pack4(cw[2]) << 8) | pack4(cw[3]);
                 dbits = 0xFFFFu;
-                if ((bw[0] | bw[1] | bw[2] | bw[3]) != 0)  // rare: some base of the chunk is not ACGTU
+                if ((bw[0] | bw[1] | bw[2] | bw[3]) != 0) {  // rare: some base of the chunk is not ACGTU
                     dbits = (valid4(bw[0]) << 12) | (valid4(bw[1]) << 8) | (valid4(bw[2]) << 4) | valid4(bw[3]);
+                    atomicOr(badw + (c >> 5), 1u << (c & 31));
+                }
             }
             Fs[c + PAD] = f;
             Ds[c + PAD] = (uint16_t)dbits;
@@ -249,22 +254,27 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
         const int pairnum = (paired && (lane & 1)) ? 1 : 0;
         const bool skip = (p.skipR1 && pairnum == 0) || (p.skipR2 && pairnum == 1);
         const bool scan = live && L >= k && t.stored > 0 && !skip;
-        bool has_undef = false;
-        for (int j = 0; j < nsteps; j++) {
-            uint32_t dd = st.d16(s + 16 * j);
-            const int rem = L - 16 * j;
-            if (rem < 16) dd |= (0xFFFFu >> rem);
-            has_undef |= (dd != 0xFFFFu);
+        bool has_undef = false;  // some chunk overlapping this read holds an undefined base
+        if (L > 0) {
+            const int c0 = s >> 4, c1 = (s + L - 1) >> 4;
+            for (int w = c0 >> 5; w <= (c1 >> 5); w++) {
+                uint32_t m = badw[w];
+                if (w == (c0 >> 5)) m &= 0xFFFFFFFFu << (c0 & 31);
+                if (w == (c1 >> 5)) m &= 0xFFFFFFFFu >> (31 - (c1 & 31));
+                has_undef |= (m != 0);
+            }
         }
+        const uint32_t undef_mask = __ballot_sync(0xFFFFFFFFu, has_undef);
         const bool any_undef = __any_sync(0xFFFFFFFFu, has_undef && scan);
         int qn = 0;  // warp-uniform queue fill
 
         auto drain = [&](int n_take) {
             // the last n_take (<= 32) queue entries, one per lane
+            const uint32_t ent = (lane < n_take) ? queue[qn - n_take + lane] : 0u;
+            const int owner = (int)(ent >> 11), pos = (int)(ent & 0x7FFu);
+            const int s_owner = __shfl_sync(0xFFFFFFFFu, s, owner);
             if (lane < n_take) {
-                const uint32_t ent = queue[qn - n_take + lane];
-                const int e = (int)(ent & 0x7FFFu), owner = (int)((ent >> 15) & 31u), pos = (int)((ent >> 20) & 0x7FFu);
-                const int id = exact_full(st, e, (ent >> 31) != 0, p, t);
+                const int id = exact_full(st, s_owner + pos, !((undef_mask >> owner) & 1u), p, t);
                 if (id > 0) {
                     atomicMin(first64 + owner, ((unsigned long long)pos << 32) | (unsigned int)id);
                     if (FMODE == FM_KTRIM_L) atomicMax(lastpos + owner, pos);
@@ -275,9 +285,9 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
         };
 
         uint32_t f_m2 = 0, f_m1 = 0, f_0 = 0, r_0 = 0, r_1 = 0, r_2 = 0;
-        uint32_t und_prev = 0;  // undefined bits of the previous 32 positions (bit 31 = oldest)
+        int last_und = -(1 << 20);  // position of the most recent undefined base before the current step
         uint64_t mhist = 0;     // PARTS: part-filter results, bit 32+b = position 16j+b, lower bits = older positions
-        const uint32_t part_vm = (t.part_w >= 16) ? 0xFFFFFFFFu : ((1u << (2 * t.part_w)) - 1u);
+        const uint32_t part_mult = bb_part_mult(t.part_w);
         if (!PARTS && scan && RCOMP) {
             r_0 = pair_reverse_complement(st.f16(s - (k - 1)));
             r_1 = pair_reverse_complement(st.f16(s + 16 - (k - 1)));
@@ -289,16 +299,17 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
             if (stepping) {
                 f_0 = st.f16(s + 16 * j);
                 if (PARTS) {
-                    uint32_t mb = 0;
+                    uint32_t mb = 0;  // bit 15-b = position 16j+b passes
 #pragma unroll
                     for (int b = 0; b < 16; b++) {
-                        const uint32_t v = __funnelshift_r(f_0, f_m1, 2 * (15 - b)) & part_vm;  // part_w bases ending at 16j+b
-                        const uint32_t tt = bb_phash(v);
-                        const uint32_t pat = bb_part_bits(tt);
-                        const bool pass = (filt[bb_filter_word(tt, geo.nfw)] & pat) == pat;
-                        mb |= pass ? (1u << b) : 0u;
+                        // the 32-bit window ending at 16j+b; the multiplier drops everything above part_w bases
+                        const uint32_t v = __funnelshift_r(f_0, f_m1, 2 * (15 - b));
+                        const BBPartProbe pr = bb_part_probe(v, part_mult, geo.nfw);
+                        const uint32_t fw = filt[pr.word];
+                        const uint32_t hit = __funnelshift_r(fw, 0u, pr.b1) & __funnelshift_r(fw, 0u, pr.b2) & 1u;
+                        mb = mb * 2u + hit;
                     }
-                    mhist |= (uint64_t)mb << 32;
+                    mhist |= (uint64_t)(__brev(mb) >> 16) << 32;
                     for (int q = 0; q < t.n_parts; q++) cbits |= (uint32_t)(mhist >> (32 - t.part_lag[q]));
                     cbits &= 0xFFFFu;
                     mhist >>= 16;
@@ -337,11 +348,11 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
                     const int rem = L - 16 * j;
                     if (rem < 16) dd |= (0xFFFFu >> rem);
                     const uint32_t und = (~dd) & 0xFFFFu;  // bit 15-b = position 16j+b undefined
-                    // 48 positions [16j-32, 16j+16), oldest in the top bits
-                    const uint64_t hist = ((uint64_t)und_prev << 16) | und;
-                    const uint32_t forced = smear_right(hist, k) & 0xFFFFu;  // bit 15-b: window ending at 16j+b touches one
-                    cbits |= __brev(forced) >> 16;                          // -> bit b
-                    und_prev = (und_prev << 16) | und;
+                    uint32_t forced = smear_right(und, min(k, 16));  // undefined bases inside this step
+                    const int carry = k - (16 * j - last_und);     // positions of this step still covered by an older one
+                    if (carry > 0) forced |= (carry >= 16) ? 0xFFFFu : ((0xFFFFu << (16 - carry)) & 0xFFFFu);
+                    cbits |= __brev(forced) >> 16;  // -> bit b
+                    if (und) last_und = 16 * j + 15 - (__ffs(und) - 1);
                 }
                 // keep positions k-1 <= i < L
                 const int i0 = 16 * j;
@@ -361,13 +372,12 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
             const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
             if (total) {
                 int w = qn + incl - cnt;
-                const uint32_t tag = ((uint32_t)lane << 15) | (has_undef ? 0u : 0x80000000u);
+                const uint32_t tag = ((uint32_t)lane << 11) + 16u * (uint32_t)j;
                 uint32_t cb = cbits;
                 while (cb) {
                     const int b = __ffs(cb) - 1;
                     cb &= cb - 1;
-                    const int pos = 16 * j + b;
-                    queue[w++] = (uint32_t)(s + pos) | tag | ((uint32_t)pos << 20);
+                    queue[w++] = (uint16_t)(tag + b);
                 }
                 qn += total;
                 __syncwarp();
@@ -401,55 +411,53 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
                 maxLocX = maxLoc - k;
             }
             if (tscan) {
-                uint64_t kmer = 0, rkmer = 0;
-                if (FMODE == FM_KTRIM_R) {  // suffixes, growing leftwards (:3945-3975)
-                    const int nmax = min(k - 1, L);
-                    for (int n = 1; n <= nmax; n++) {
-                        const int i = L - n;
-                        const int e = s + i;
-                        const uint32_t w = Fs[(e >> 4) + PAD];
-                        const bool def = (Ds[(e >> 4) + PAD] >> (15 - (e & 15))) & 1;
-                        const uint32_t c = def ? ((w >> (2 * (15 - (e & 15)))) & 3u) : 0u;
-                        kmer |= (uint64_t)c << (2 * (n - 1));
-                        rkmer = ((rkmer << 2) | (def ? (3u - c) : 0u)) & p.mask;
-                        if (n >= p.mink) {
-                            const uint64_t key = bb_to_value(p, kmer, rkmer, 1ull << (2 * n));
-                            if (filter_pass(filt_short, n_short, key)) {
-                                const int id = bb_table_get(t, key);
-                                if (id > 0) {
-                                    if (id0 < 0) id0 = id;
-                                    minLoc = i;
-                                    minLocX = min(minLocX, L);
-                                    maxLoc = L - 1;
-                                    maxLocX = max(maxLocX, i - 1);
-                                    found++;
-                                }
-                            }
-                        }
+                // All tail k-mers of a read are sub-windows of ONE 32-base window: the suffix tails
+                // (ktrim=r, :3945-3975) of the window ending at the last base, the prefix tails
+                // (ktrim=l, :3910-3942) of the window ending at base min(k,L)-1. Its reverse complement is
+                // taken once; per length n the key costs a mask, a shift and a compare. The tails read
+                // undefined bases as code 0 / complement 0 ("no N handling in tails").
+                const int nmax = (FMODE == FM_KTRIM_R) ? min(k - 1, L) : min(k, L);
+                const int e = (FMODE == FM_KTRIM_R) ? (s + L - 1) : (s + nmax - 1);
+                uint64_t W = st.win(e);  // slot t = base e-t
+                uint64_t RC;
+                if (has_undef) {
+                    const uint64_t E = spread2(st.dwin(e));
+                    W &= E;
+                    RC = bb_rcomp(W, 32) & rev2(E, 32);
+                } else {
+                    RC = bb_rcomp(W, 32);
+                }
+                for (int n = max(p.mink, 1); n <= nmax; n++) {
+                    const uint64_t nm = (1ull << (2 * n)) - 1ull;
+                    uint64_t kmer, rkmer;
+                    int i;
+                    if (FMODE == FM_KTRIM_R) {  // last n bases; reference loop index i = L-n
+                        kmer = W & nm;
+                        rkmer = RC >> (2 * (32 - n));
+                        i = L - n;
+                    } else {  // first n bases; reference loop index i = n-1
+                        kmer = (W >> (2 * (nmax - n))) & nm;
+                        rkmer = (RC >> (2 * (32 - nmax))) & nm;
+                        i = n - 1;
                     }
-                } else {  // prefixes, growing rightwards (:3910-3942)
-                    const int lim = min(k, L);
-                    for (int i = 0; i < lim; i++) {
-                        const int e = s + i;
-                        const uint32_t w = Fs[(e >> 4) + PAD];
-                        const bool def = (Ds[(e >> 4) + PAD] >> (15 - (e & 15))) & 1;
-                        const uint32_t c = def ? ((w >> (2 * (15 - (e & 15)))) & 3u) : 0u;
-                        kmer = ((kmer << 2) | c) & p.mask;
-                        rkmer |= (uint64_t)(def ? (3u - c) : 0u) << (2 * i);
-                        const int n = i + 1;
-                        if (n >= p.mink) {
-                            const uint64_t key = bb_to_value(p, kmer, rkmer, 1ull << (2 * n));
-                            if (filter_pass(filt_short, n_short, key)) {
-                                const int id = bb_table_get(t, key);
-                                if (id > 0) {
-                                    if (id0 < 0) id0 = id;
-                                    minLoc = 0;
-                                    minLocX = min(minLocX, i + 1);
-                                    maxLoc = max(maxLoc, i);
-                                    maxLocX = max(maxLocX, 0);
-                                    found++;
-                                }
+                    const uint64_t key = bb_to_value(p, kmer, rkmer, 1ull << (2 * n));
+                    // the short-key bloom only knows keys shorter than k; a prefix of length k goes straight to the table
+                    if (n == k || filter_pass(filt_short, n_short, key)) {
+                        const int id = bb_table_get(t, key);
+                        if (id > 0) {
+                            if (id0 < 0) id0 = id;
+                            if (FMODE == FM_KTRIM_R) {
+                                minLoc = i;
+                                minLocX = min(minLocX, L);
+                                maxLoc = L - 1;
+                                maxLocX = max(maxLocX, i - 1);
+                            } else {
+                                minLoc = 0;
+                                minLocX = min(minLocX, i + 1);
+                                maxLoc = max(maxLoc, i);
+                                maxLocX = max(maxLocX, 0);
                             }
+                            found++;
                         }
                     }
                 }
@@ -568,7 +576,8 @@ FastGeom make_geom(const BBParams &p, const BBTable &t, int max_read_len) {
     FastGeom g;
     const int lmax = std::max(max_read_len, 16);
     g.nch = (32 * lmax + 15 + 15) / 16 + 1;
-    int wb = 32 * 8 + 32 * 4 + QCAP * 4 + (g.nch + PAD + TAIL) * 4 + ((g.nch + PAD + TAIL + 1) & ~1) * 2;
+    g.nbadw = (g.nch + 31) / 32 + 1;
+    int wb = 32 * 8 + 32 * 4 + g.nbadw * 4 + (g.nch + PAD + TAIL) * 4 + ((g.nch + PAD + TAIL + 1) & ~1) * 2 + QCAP * 2;
     wb = (wb + 15) & ~15;
     g.warp_bytes = wb;
     if (parts_ok(p, t)) {

@@ -260,8 +260,8 @@ __global__ void part_filter_build_kernel(const Seed *__restrict__ seeds, int64_t
             const uint64_t x = o ? r : f;
             for (int j = 0; j < n_parts; j++) {
                 const uint32_t v = (uint32_t)(x >> (2 * lags[j])) & vm;
-                const uint32_t t = bb_phash(v);
-                atomicOr(filter + bb_filter_word(t, n_words), bb_part_bits(t));
+                const BBPartProbe pr = bb_part_probe(v, bb_part_mult(w), n_words);
+                atomicOr(filter + pr.word, (1u << (pr.b1 & 31)) | (1u << (pr.b2 & 31)));
             }
         }
     }
