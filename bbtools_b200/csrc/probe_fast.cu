@@ -32,13 +32,15 @@ constexpr int PAD = 2;           // zero chunks in front of the staged stream (w
 constexpr int TAIL = 4;          // zero chunks behind it (the reverse-strand words run two steps ahead)
 constexpr int MAX_FAST_LEN = 1008;
 constexpr int FAST_SMEM_LIMIT = 227 * 1024;
-constexpr int QCAP = 32 + 32 * 16;  // queue entries: a drain threshold of 32 plus one full step of all lanes
+constexpr int CAND_CAP = 20;         // candidates a read without undefined bases may have unresolved at a time
+constexpr int QCAP = 32 + 32 * 16;   // queue entries: the drain threshold plus one full step of all lanes
 
 struct FastGeom {
     int warps;        // warps per block
     int nch;          // staged 16-base chunks per warp (capacity, without padding)
     int warp_bytes;   // shared memory per warp
     int nbadw;        // words of the per-tile "chunk has an undefined base" bit mask
+    int csteps;       // 16-position steps the candidate buffer holds per lane
     uint32_t nfw;     // words of the main on-chip filter (canonical bloom, or the part filter)
     uint32_t nsw;     // words of the short-key bloom that follows it (part-filter kernels only)
     uint32_t src_off; // word offset of the main filter inside BBTable::filter
@@ -184,6 +186,7 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
     uint32_t *Fs = badw + geo.nbadw;
     uint16_t *Ds = reinterpret_cast<uint16_t *>(Fs + geo.nch + PAD + TAIL);
     uint16_t *queue = Ds + ((geo.nch + PAD + TAIL + 1) & ~1);                     // [QCAP] (owner lane << 11) | position
+    uint16_t *cand = queue + QCAP;                                                // [csteps][32] candidate bits per step
 
     for (uint32_t i = threadIdx.x; i < geo.nfw + geo.nsw; i += blockDim.x) filt[i] = __ldg(t.filter + geo.src_off + i);
     for (int i = lane; i < PAD; i += 32) {
@@ -197,6 +200,8 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
     const uint32_t mask_hi = (uint32_t)(p.mask >> 32), mask_lo = (uint32_t)p.mask;
     const uint32_t mm_hi = (uint32_t)(p.middleMask >> 32), mm_lo = (uint32_t)p.middleMask;
     const uint32_t km_hi = (uint32_t)(p.kmask >> 32), km_lo = (uint32_t)p.kmask;
+    const int psh0 = 32 - t.part_lag[0], psh1 = 32 - t.part_lag[1], psh2 = 32 - t.part_lag[2],
+              psh3 = 32 - t.part_lag[t.n_parts > 3 ? 3 : 2];
     const uintptr_t base_addr = reinterpret_cast<uintptr_t>(bases);
     const int64_t n_tiles = (n_reads + 31) >> 5;
     const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -213,7 +218,7 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
         const int nchunks = (int)((base_addr + tile_hi - a0 + 15) >> 4);
         const int L = (int)(o1 - o0);
         const int maxL = __reduce_max_sync(0xFFFFFFFFu, L);
-        if (nchunks > geo.nch || maxL > MAX_FAST_LEN) {
+        if (nchunks > geo.nch || maxL > MAX_FAST_LEN || ((maxL + 15) >> 4) > geo.csteps) {
             // tile does not fit the staging: hand its units to the generic kernel
             if (live && (!paired || !(lane & 1))) {
                 const unsigned int w = atomicAdd(handoff_n, 1u);
@@ -267,6 +272,17 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
         const uint32_t undef_mask = __ballot_sync(0xFFFFFFFFu, has_undef);
         const bool any_undef = __any_sync(0xFFFFFFFFu, has_undef && scan);
         int qn = 0;  // warp-uniform queue fill
+        // Every step's candidate bits are kept in cand[step][lane]. A read releases them to the warp queue
+        // as it goes, but a read without undefined bases releases at most CAND_CAP per step: a window run
+        // entering an adapter is a long streak of true hits of which only the first matters (ktrim=r,
+        // kfilter). The surplus -- and everything after it, to keep position order -- is deferred; it is
+        // only ever evaluated if all released candidates of the read turn out to be misses.
+        bool done = !scan;      // the read's first hit is confirmed (or it is not scanned at all)
+        bool deferred = false;  // candidates from (dj, dbits) onwards are held back
+        int rel = 0;            // candidates released since the last full drain
+        int dj = 0;
+        uint32_t dbits = 0;
+        const uint32_t lt_mask = (1u << lane) - 1u;
 
         auto drain = [&](int n_take) {
             // the last n_take (<= 32) queue entries, one per lane
@@ -282,6 +298,7 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
             }
             qn -= n_take;
             __syncwarp();
+            if (first64[lane] != ~0ull) done = true;
         };
 
         uint32_t f_m2 = 0, f_m1 = 0, f_0 = 0, r_0 = 0, r_1 = 0, r_2 = 0;
@@ -292,99 +309,145 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
             r_0 = pair_reverse_complement(st.f16(s - (k - 1)));
             r_1 = pair_reverse_complement(st.f16(s + 16 - (k - 1)));
         }
-        for (int j = 0; j < max_steps; j++) {
-            uint32_t cbits = 0;
-            bool stepping = scan && j < nsteps;
-            if (FMODE != FM_KTRIM_L && stepping && first64[lane] != ~0ull) stepping = false;  // first hit known: done
-            if (stepping) {
-                f_0 = st.f16(s + 16 * j);
-                if (PARTS) {
-                    uint32_t mb = 0;  // bit 15-b = position 16j+b passes
-#pragma unroll
-                    for (int b = 0; b < 16; b++) {
-                        // the 32-bit window ending at 16j+b; the multiplier drops everything above part_w bases
-                        const uint32_t v = __funnelshift_r(f_0, f_m1, 2 * (15 - b));
-                        const BBPartProbe pr = bb_part_probe(v, part_mult, geo.nfw);
-                        const uint32_t fw = filt[pr.word];
-                        const uint32_t hit = __funnelshift_r(fw, 0u, pr.b1) & __funnelshift_r(fw, 0u, pr.b2) & 1u;
-                        mb = mb * 2u + hit;
-                    }
-                    mhist |= (uint64_t)(__brev(mb) >> 16) << 32;
-                    for (int q = 0; q < t.n_parts; q++) cbits |= (uint32_t)(mhist >> (32 - t.part_lag[q]));
-                    cbits &= 0xFFFFu;
-                    mhist >>= 16;
-                    f_m1 = f_0;
-                } else {
-                    if (RCOMP) r_2 = pair_reverse_complement(st.f16(s + 16 * (j + 2) - (k - 1)));
-#pragma unroll
-                    for (int b = 0; b < 16; b++) {
-                        const int sh = 2 * (15 - b);
-                        uint32_t klo = __funnelshift_r(f_0, f_m1, sh);
-                        uint32_t khi = __funnelshift_r(f_m1, f_m2, sh) & mask_hi;
-                        if (!K16) klo &= mask_lo;
-                        if (RCOMP) {
-                            uint32_t rlo = __funnelshift_r(r_0, r_1, 2 * b);
-                            const uint32_t rhi = __funnelshift_r(r_1, r_2, 2 * b) & mask_hi;
-                            if (!K16) rlo &= mask_lo;
-                            const bool gt = (((uint64_t)rhi << 32) | rlo) > (((uint64_t)khi << 32) | klo);
-                            klo = gt ? rlo : klo;
-                            khi = gt ? rhi : khi;
+        // One loop drives both the scan steps (j < max_steps) and, afterwards, the rare release of deferred
+        // candidates, so that the evaluation code below exists once in the instruction stream.
+        for (int j = 0;; j++) {
+            if (j < max_steps) {
+                uint32_t cbits = 0;
+                bool stepping = scan && j < nsteps;
+                if (FMODE != FM_KTRIM_L && done) stepping = false;  // first hit known: nothing further matters
+                if (stepping) {
+                    f_0 = st.f16(s + 16 * j);
+                    if (PARTS) {
+                        uint32_t mb = 0;  // bit 15-b = position 16j+b passes
+    #pragma unroll
+                        for (int b = 0; b < 16; b++) {
+                            // the 32-bit window ending at 16j+b; the multiplier drops everything above part_w bases
+                            const uint32_t v = __funnelshift_r(f_0, f_m1, 2 * (15 - b));
+                            const BBPartProbe pr = bb_part_probe(v, part_mult, geo.nfw);
+                            const uint32_t fw = filt[pr.word];
+                            const uint32_t hit = __funnelshift_r(fw, 0u, pr.b1) & __funnelshift_r(fw, 0u, pr.b2) & 1u;
+                            mb = mb * 2u + hit;
                         }
-                        klo = (klo & mm_lo) | km_lo;
-                        khi = (khi & mm_hi) | km_hi;
-                        const uint32_t tt = bb_fhash(klo, khi);
-                        const uint32_t pat = bb_filter_bits(tt);
-                        const bool pass = (filt[bb_filter_word(tt, geo.nfw)] & pat) == pat;
-                        cbits |= pass ? (1u << b) : 0u;
+                        mhist |= (uint64_t)(__brev(mb) >> 16) << 32;
+                        cbits = (uint32_t)(mhist >> psh0);
+                    if (t.n_parts > 1) cbits |= (uint32_t)(mhist >> psh1);
+                    if (t.n_parts > 2) cbits |= (uint32_t)(mhist >> psh2) | (uint32_t)(mhist >> psh3);
+                        cbits &= 0xFFFFu;
+                        mhist >>= 16;
+                        f_m1 = f_0;
+                    } else {
+                        if (RCOMP) r_2 = pair_reverse_complement(st.f16(s + 16 * (j + 2) - (k - 1)));
+    #pragma unroll
+                        for (int b = 0; b < 16; b++) {
+                            const int sh = 2 * (15 - b);
+                            uint32_t klo = __funnelshift_r(f_0, f_m1, sh);
+                            uint32_t khi = __funnelshift_r(f_m1, f_m2, sh) & mask_hi;
+                            if (!K16) klo &= mask_lo;
+                            if (RCOMP) {
+                                uint32_t rlo = __funnelshift_r(r_0, r_1, 2 * b);
+                                const uint32_t rhi = __funnelshift_r(r_1, r_2, 2 * b) & mask_hi;
+                                if (!K16) rlo &= mask_lo;
+                                const bool gt = (((uint64_t)rhi << 32) | rlo) > (((uint64_t)khi << 32) | klo);
+                                klo = gt ? rlo : klo;
+                                khi = gt ? rhi : khi;
+                            }
+                            klo = (klo & mm_lo) | km_lo;
+                            khi = (khi & mm_hi) | km_hi;
+                            const uint32_t tt = bb_fhash(klo, khi);
+                            const uint32_t pat = bb_filter_bits(tt);
+                            const bool pass = (filt[bb_filter_word(tt, geo.nfw)] & pat) == pat;
+                            cbits |= pass ? (1u << b) : 0u;
+                        }
+                        f_m2 = f_m1;
+                        f_m1 = f_0;
+                        r_0 = r_1;
+                        r_1 = r_2;
                     }
-                    f_m2 = f_m1;
-                    f_m1 = f_0;
-                    r_0 = r_1;
-                    r_1 = r_2;
+                    if (any_undef) {
+                        // every window that contains an undefined base is decided by the exact evaluator
+                        uint32_t dd = st.d16(s + 16 * j);
+                        const int rem = L - 16 * j;
+                        if (rem < 16) dd |= (0xFFFFu >> rem);
+                        const uint32_t und = (~dd) & 0xFFFFu;  // bit 15-b = position 16j+b undefined
+                        uint32_t forced = smear_right(und, min(k, 16));  // undefined bases inside this step
+                        const int carry = k - (16 * j - last_und);     // positions of this step still covered by an older one
+                        if (carry > 0) forced |= (carry >= 16) ? 0xFFFFu : ((0xFFFFu << (16 - carry)) & 0xFFFFu);
+                        cbits |= __brev(forced) >> 16;  // -> bit b
+                        if (und) last_und = 16 * j + 15 - (__ffs(und) - 1);
+                    }
+                    // keep positions k-1 <= i < L
+                    const int i0 = 16 * j;
+                    uint32_t vm = 0xFFFFu;
+                    if (i0 < k - 1) vm &= (k - 1 - i0 >= 16) ? 0u : (0xFFFFu << (k - 1 - i0));
+                    if (L - i0 < 16) vm &= (1u << (L - i0)) - 1u;
+                    cbits &= vm;
                 }
-                if (any_undef) {
-                    // every window that contains an undefined base is decided by the exact evaluator
-                    uint32_t dd = st.d16(s + 16 * j);
-                    const int rem = L - 16 * j;
-                    if (rem < 16) dd |= (0xFFFFu >> rem);
-                    const uint32_t und = (~dd) & 0xFFFFu;  // bit 15-b = position 16j+b undefined
-                    uint32_t forced = smear_right(und, min(k, 16));  // undefined bases inside this step
-                    const int carry = k - (16 * j - last_und);     // positions of this step still covered by an older one
-                    if (carry > 0) forced |= (carry >= 16) ? 0xFFFFu : ((0xFFFFu << (16 - carry)) & 0xFFFFu);
-                    cbits |= __brev(forced) >> 16;  // -> bit b
-                    if (und) last_und = 16 * j + 15 - (__ffs(und) - 1);
+                if (scan && j < nsteps) cand[j * 32 + lane] = (uint16_t)cbits;
+                uint32_t pb = (done || deferred) ? 0u : cbits;
+                if (!has_undef && rel + __popc(pb) > CAND_CAP) {
+                    // keep the lowest (CAND_CAP - rel) bits, hold everything else back
+                    uint32_t rest = pb;
+    #pragma unroll 1
+                for (int c = rel; c < CAND_CAP; c++) rest &= rest - 1;
+                    pb ^= rest;
+                    deferred = true;
+                    dj = j;
+                    dbits = rest;
                 }
-                // keep positions k-1 <= i < L
-                const int i0 = 16 * j;
-                uint32_t vm = 0xFFFFu;
-                if (i0 < k - 1) vm &= (k - 1 - i0 >= 16) ? 0u : (0xFFFFu << (k - 1 - i0));
-                if (L - i0 < 16) vm &= (1u << (L - i0)) - 1u;
-                cbits &= vm;
-            }
-            // pool this step's candidates: exclusive prefix sum of the per-lane counts
-            const int cnt = __popc(cbits);
-            int incl = cnt;
+                rel += __popc(pb);
+
+                // pool this step's released candidates: exclusive prefix sum of the per-lane counts
+                const int cnt = __popc(pb);
+                int incl = cnt;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            if (total) {
-                int w = qn + incl - cnt;
-                const uint32_t tag = ((uint32_t)lane << 11) + 16u * (uint32_t)j;
-                uint32_t cb = cbits;
-                while (cb) {
-                    const int b = __ffs(cb) - 1;
-                    cb &= cb - 1;
-                    queue[w++] = (uint16_t)(tag + b);
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if (lane >= o) incl += v;
                 }
-                qn += total;
-                __syncwarp();
-                while (qn >= 32) drain(32);
+                const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                if (total) {
+                    int w = qn + incl - cnt;
+                    const uint32_t tag = ((uint32_t)lane << 11) + 16u * (uint32_t)j;
+                    while (pb) {
+                        const int b = __ffs(pb) - 1;
+                        pb &= pb - 1;
+                        queue[w++] = (uint16_t)(tag + b);
+                    }
+                    qn += total;
+                }
+            } else {
+                // rare: a read whose released candidates all missed still holds deferred ones; release them
+                // in position order, 8 at a time, until a hit is confirmed or they are exhausted
+                if (!__any_sync(0xFFFFFFFFu, deferred && !done)) break;
+#pragma unroll 1
+                for (int c = 0; c < 8; c++) {
+                    bool has = false;
+                    if (deferred && !done) {
+                        while (dbits == 0 && dj < nsteps - 1) {
+                            dj++;
+                            dbits = cand[dj * 32 + lane];
+                        }
+                        has = dbits != 0;
+                        if (!has) deferred = false;
+                    }
+                    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, has);
+                    if (!bal) break;
+                    if (has) {
+                        const int b = __ffs(dbits) - 1;
+                        dbits &= dbits - 1;
+                        queue[qn + __popc(bal & lt_mask)] = (uint16_t)((lane << 11) + 16 * dj + b);
+                    }
+                    qn += __popc(bal);
+                }
+            }
+            __syncwarp();
+            if (qn >= 32 || (j >= max_steps - 1 && qn > 0)) {
+                // evaluate everything released so far; afterwards nothing of any lane is unresolved
+                while (qn > 0) drain(min(32, qn));
+                rel = 0;
             }
         }
-        if (qn > 0) drain(qn);
 
         int found = 0, id0 = -1, minLoc = 999999999, maxLoc = -1, count = 0;
         int lo = 0, hi = L;
@@ -396,8 +459,49 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
                 id0 = (int)(unsigned int)f64;
                 found = 1;
                 minLoc = pos - k + 1;
-                maxLoc = (FMODE == FM_KTRIM_L) ? lastpos[lane] : pos;
+                maxLoc = pos;
             }
+        }
+        if (FMODE == FM_KTRIM_L) {
+            // ktrim=l also needs the LAST hit: walk the buffered candidates downwards from the read end
+            // until one beyond the first hit is confirmed (same in-flight cap, highest position first)
+            // hits at or below the forward phase's last confirmed hit are already accounted for
+            const int firstpos = found ? max(maxLoc, lastpos[lane]) : -1;
+            bool bdone = !found;
+            int bj = nsteps;
+            uint32_t bbits = 0;
+            while (true) {
+                for (int c = 0; c < 4; c++) {
+                    bool has = false;
+                    int pos = 0;
+                    if (!bdone) {
+                        while (bbits == 0 && bj > 0) {
+                            bj--;
+                            bbits = cand[bj * 32 + lane];
+                        }
+                        if (bbits != 0) {
+                            const int b = 31 - __clz(bbits);
+                            pos = 16 * bj + b;
+                            bbits &= ~(1u << b);
+                            if (pos > firstpos)
+                                has = true;
+                            else
+                                bdone = true;  // reached the first hit: it is also the last one
+                        } else {
+                            bdone = true;
+                        }
+                    }
+                    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, has);
+                    if (!bal) break;
+                    if (has) queue[qn + __popc(bal & lt_mask)] = (uint16_t)((lane << 11) + pos);
+                    qn += __popc(bal);
+                }
+                __syncwarp();
+                if (qn == 0) break;
+                while (qn > 0) drain(min(32, qn));
+                if (lastpos[lane] > firstpos) bdone = true;
+            }
+            if (found) maxLoc = max(firstpos, lastpos[lane]);
         }
         if (FMODE == FM_KFILTER) {  // countSetKmers with maxBadKmers==0 (jgi/BBDuk.java:3395-3457)
             count = found;
@@ -553,13 +657,17 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
         }
     }
     if (stats) {
-        long long v[8] = {s_ri, s_bi, s_rk, s_bk, s_rf, s_bf, s_ro, s_bo};
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            long long x = v[q];
-            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
-            if (lane == 0 && x) atomicAdd((unsigned long long *)stats + q, (unsigned long long)x);
-        }
+        // block-level sums through shared-memory atomics (small code; this runs once per kernel)
+        __syncthreads();
+        unsigned long long *acc = reinterpret_cast<unsigned long long *>(smem);  // the filter image is dead now
+        if (threadIdx.x < 8) acc[threadIdx.x] = 0ull;
+        __syncthreads();
+        const long long v[8] = {s_ri, s_bi, s_rk, s_bk, s_rf, s_bf, s_ro, s_bo};
+#pragma unroll 1
+        for (int q = 0; q < 8; q++)
+            if (v[q]) atomicAdd(acc + q, (unsigned long long)v[q]);
+        __syncthreads();
+        if (threadIdx.x < 8 && acc[threadIdx.x]) atomicAdd((unsigned long long *)stats + threadIdx.x, acc[threadIdx.x]);
     }
 }
 
@@ -577,7 +685,9 @@ FastGeom make_geom(const BBParams &p, const BBTable &t, int max_read_len) {
     const int lmax = std::max(max_read_len, 16);
     g.nch = (32 * lmax + 15 + 15) / 16 + 1;
     g.nbadw = (g.nch + 31) / 32 + 1;
-    int wb = 32 * 8 + 32 * 4 + g.nbadw * 4 + (g.nch + PAD + TAIL) * 4 + ((g.nch + PAD + TAIL + 1) & ~1) * 2 + QCAP * 2;
+    g.csteps = (lmax + 15) / 16 + 1;
+    int wb = 32 * 8 + 32 * 4 + g.nbadw * 4 + (g.nch + PAD + TAIL) * 4 + ((g.nch + PAD + TAIL + 1) & ~1) * 2 + QCAP * 2 +
+             g.csteps * 32 * 2;
     wb = (wb + 15) & ~15;
     g.warp_bytes = wb;
     if (parts_ok(p, t)) {
