@@ -15,9 +15,10 @@
 
 namespace {
 
-constexpr int N_SLOTS = 3;                    // staging slots (streams) per handle
-constexpr int64_t CHUNK_READS = 4 << 20;      // reads per device batch on the host path
-constexpr int64_t CHUNK_BYTES = 1ll << 30;    // bases per device batch (offsets stay 32-bit)
+constexpr int N_SLOTS = 4;                    // staging slots (streams) per handle
+constexpr int64_t CHUNK_READS = 1 << 20;      // reads per device batch on the host path: small enough that H2D of
+                                              // chunk i+1, the kernels of chunk i and D2H of chunk i-1 overlap
+constexpr int64_t CHUNK_BYTES = 256ll << 20;  // bases per device batch (offsets stay 32-bit)
 
 struct Slot {
     cudaStream_t st = nullptr;

@@ -657,17 +657,14 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
         }
     }
     if (stats) {
-        // block-level sums through shared-memory atomics (small code; this runs once per kernel)
-        __syncthreads();
-        unsigned long long *acc = reinterpret_cast<unsigned long long *>(smem);  // the filter image is dead now
-        if (threadIdx.x < 8) acc[threadIdx.x] = 0ull;
-        __syncthreads();
-        const long long v[8] = {s_ri, s_bi, s_rk, s_bk, s_rf, s_bf, s_ro, s_bo};
-#pragma unroll 1
-        for (int q = 0; q < 8; q++)
-            if (v[q]) atomicAdd(acc + q, (unsigned long long)v[q]);
-        __syncthreads();
-        if (threadIdx.x < 8 && acc[threadIdx.x]) atomicAdd((unsigned long long *)stats + threadIdx.x, acc[threadIdx.x]);
+        // per-warp sums with one REDUX per counter (a launch holds < 2^32 bases, so 32 bits suffice per warp)
+        const unsigned int v[8] = {(unsigned int)s_ri, (unsigned int)s_bi, (unsigned int)s_rk, (unsigned int)s_bk,
+                                   (unsigned int)s_rf, (unsigned int)s_bf, (unsigned int)s_ro, (unsigned int)s_bo};
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const unsigned int x = __reduce_add_sync(0xFFFFFFFFu, v[q]);
+            if (lane == 0 && x) atomicAdd((unsigned long long *)stats + q, (unsigned long long)x);
+        }
     }
 }
 
