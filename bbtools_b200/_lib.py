@@ -29,6 +29,21 @@ SYMBOLS = [
     ("bbduk_b200_destroy", None, [C.c_void_p]),
     ("bbduk_b200_synth_pairs", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_uint64,
                                          C.c_int32, C.c_int32, C.c_void_p]),
+    # include/kcount_b200.h
+    ("kcount_b200_create", C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]),
+    ("kcount_b200_add_reads", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    ("kcount_b200_add_reads_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    ("kcount_b200_stats", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("kcount_b200_khist", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    ("kcount_b200_dump", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
+                                   C.POINTER(C.c_int64)]),
+    ("kcount_b200_export_partitioned", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("kcount_b200_merge_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    ("kcount_b200_table_info", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("kcount_b200_synth_reads", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int64,
+                                          C.c_uint64, C.c_int32, C.c_void_p]),
+    ("kcount_b200_last_error", C.c_char_p, [C.c_void_p]),
+    ("kcount_b200_destroy", None, [C.c_void_p]),
 ]
 
 _LIB = None

@@ -178,3 +178,34 @@ def ragged_reads(n_reads, seed=3, min_len=0, max_len=400, alphabet=b"ACGTNacgtnR
     np.cumsum(lens, out=offsets[1:])
     bases = np.concatenate(seqs) if seqs else np.zeros(0, np.uint8)
     return bases.astype(np.uint8), offsets
+
+
+def genome_bases(genome_len, seed=11, start=0, n=None):
+    """cfg 5 genome: base i = ACGT[rnd(seed, 5, i) & 3] for i in [start, start+n)."""
+    n = genome_len - start if n is None else n
+    out = np.empty(n, np.uint8)
+    step = 1 << 22
+    for s in range(0, n, step):
+        idx = np.arange(start + s, start + min(n, s + step), dtype=np.uint64)
+        out[s:s + len(idx)] = _ACGT[(rnd(seed, 5, idx) & np.uint64(3)).astype(np.int64)]
+    return out
+
+
+def genome_reads(n_reads, genome_len, first_read=0, read_len=150, seed=11, sub_per_10k=10):
+    """cfg 5 reads: SE, sampled uniformly from the synthetic genome (either strand), substitutions only.
+    Same formulas as csrc/kcount.cu:kc_synth_kernel."""
+    L = read_len
+    r = np.arange(first_read, first_read + n_reads, dtype=np.uint64)
+    c = rnd(seed, 0, r)
+    rev = (c & np.uint64(1)) != 0
+    start = ((c >> np.uint64(8)) % np.uint64(genome_len - L + 1)).astype(np.int64)
+    j = np.arange(L, dtype=np.int64)[None, :]
+    gi = start[:, None] + np.where(rev[:, None], L - 1 - j, j)
+    code = (rnd(seed, 5, gi.astype(np.uint64)) & np.uint64(3)).astype(np.int64)
+    code = np.where(rev[:, None], 3 - code, code)
+    e = rnd(seed, 3, r[:, None] * np.uint64(L) + j.astype(np.uint64))
+    sub = (e % np.uint64(10000)) < np.uint64(sub_per_10k)
+    newcode = (code + 1 + ((e >> np.uint64(16)) % np.uint64(3)).astype(np.int64)) & 3
+    code = np.where(sub, newcode, code)
+    offsets = np.arange(0, (n_reads + 1) * L, L, dtype=np.int64)
+    return _ACGT[code].astype(np.uint8).reshape(-1), offsets
