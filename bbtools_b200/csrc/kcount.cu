@@ -5,14 +5,15 @@
 // all three. In closed form: position g of the concatenated base array ends a counted k-mer iff the k bases
 // [g-k+1, g] are all defined and belong to one read. That makes every position independent, so the kernel is
 // position-parallel over the flat base array (balanced for any read-length mix, including Mbp contigs):
-//   * a CTA takes a span of 4096 positions, stages it (+32 bases of look-back) as a big-endian 2-bit stream F,
-//     a "defined" bit stream D and a "read starts here" bit stream S in shared memory (16-byte coalesced loads,
-//     SIMD-in-register classification as in probe_fast.cu);
+//   * a pre-pass scatters one "a read starts here" bit per read into a bit stream S (2 bytes per 16 bases);
+//   * a warp takes a sub-span of 512 positions, stages it (+32 bases of look-back) as a big-endian 2-bit stream
+//     F, a "defined" bit stream D and S in shared memory (16-byte coalesced loads, SIMD-in-register
+//     classification as in probe_fast.cu); warps never wait for each other;
 //   * a thread owns 16 consecutive positions: validity of all 16 is decided bit-parallel (smears of ~D and S),
 //     each window is two funnel shifts, the reverse complement a bit-reverse;
 //   * insert = one 16-byte slot {key, count}: a k-mer costs one 32-byte sector read + one L2 atomic.
-// The table is HBM-resident (config 5: ~1e9 distinct keys = 32 GB at load 0.5); all 16 target sectors of a
-// thread are prefetched into L2 before the dependent probe loops run, so the DRAM latency is paid once.
+// The table is HBM-resident (config 5: ~1e9 distinct keys = 32 GB at load 0.5); a thread keeps the first-probe
+// sectors of 4 windows in flight before the dependent compare/CAS/RED steps run.
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
@@ -82,12 +83,13 @@ __device__ __forceinline__ void kc_add(uint32_t *c, uint32_t seen, uint32_t incr
     }
 }
 
-// returns 1 if the key was created. Lookup/insert = incrementAndReturnNumCreated (kmer/HashArray1D.java:68-89)
-__device__ __forceinline__ int kc_insert(const KTable &t, uint64_t key, uint32_t incr, unsigned long long *overflow) {
-    uint64_t s = kc_slot_of(key, t.shift);
+// returns 1 if the key was created. Lookup/insert = incrementAndReturnNumCreated (kmer/HashArray1D.java:68-89).
+// `v` is the caller's (possibly stale) 16-byte snapshot of slot s -- stale is fine: keys never change once set
+// and the count is only a saturation hint.
+__device__ __forceinline__ int kc_insert_from(const KTable &t, uint64_t s, ulonglong2 v, uint64_t key, uint32_t incr,
+                                              unsigned long long *overflow) {
     for (int probe = 0; probe < KC_MAX_PROBE; probe++) {
         KSlot *p = t.slots + s;
-        const ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2 *>(p));
         uint64_t kk = v.x;
         uint32_t seen = (uint32_t)v.y;
         int created = 0;
@@ -105,9 +107,14 @@ __device__ __forceinline__ int kc_insert(const KTable &t, uint64_t key, uint32_t
             return created;
         }
         s = (s + 1) & t.mask;
+        v = __ldcg(reinterpret_cast<const ulonglong2 *>(t.slots + s));
     }
     *overflow = 1ull;
     return 0;
+}
+__device__ __forceinline__ int kc_insert(const KTable &t, uint64_t key, uint32_t incr, unsigned long long *overflow) {
+    const uint64_t s = kc_slot_of(key, t.shift);
+    return kc_insert_from(t, s, __ldcg(reinterpret_cast<const ulonglong2 *>(t.slots + s)), key, incr, overflow);
 }
 
 __device__ __forceinline__ void kc_classify4(uint32_t w, uint32_t &codes, uint32_t &bad) {
@@ -134,27 +141,38 @@ __device__ __forceinline__ uint64_t kc_smear(uint64_t x, int n) {
     return x;
 }
 
+// read-start bit stream: bit 15-b of the 16-bit word c set <=> some read starts at position 16c+b
+__global__ void kc_starts_kernel(const uint32_t *__restrict__ offsets, int64_t n_reads, uint32_t *sbits) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t o = offsets[r];
+        atomicOr(&sbits[o >> 5], 1u << ((((o >> 4) & 1u) << 4) + 15u - (o & 15u)));
+    }
+}
+
 template <bool RCOMP>
-__global__ void __launch_bounds__(KC_THREADS)
-kcount_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ offsets, int64_t n_reads, int64_t n_bases,
-              int64_t span_lo, int64_t span_hi, int k, KTable t, KCounters *ctr) {
-    __shared__ uint32_t Fs[KC_THREADS + KC_LOOK];
-    __shared__ uint32_t DSs[KC_THREADS + KC_LOOK];  // D in the high half, S in the low half; bit 15-b = base b
-    __shared__ int64_t r_first;
-    const int tid = threadIdx.x;
+__global__ void __launch_bounds__(KC_THREADS, 3)
+kcount_kernel(const uint8_t *__restrict__ bases, const uint16_t *__restrict__ sbits, int64_t n_bases, int64_t span_lo,
+              int64_t span_hi, int k, KTable t, KCounters *ctr) {
+    // every warp works alone on 512-position sub-spans: no CTA-wide barrier ever waits on a DRAM chain
+    __shared__ uint32_t Fs_all[KC_THREADS / 32][32 + KC_LOOK];
+    __shared__ uint32_t DSs_all[KC_THREADS / 32][32 + KC_LOOK];  // D in the high half, S in the low half; bit 15-b = base b
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *Fs = Fs_all[warp], *DSs = DSs_all[warp];
+    const int tid = lane;
     const uint64_t kmask = (k == 32) ? ~0ull : ((1ull << (2 * k)) - 1ull);
     unsigned long long n_valid = 0, n_created = 0;
 
     for (int64_t span = span_lo + blockIdx.x; span < span_hi; span += gridDim.x) {
-        const int64_t g_lo = span * KC_SPAN;          // first position of the span
-        const int64_t c_lo = (g_lo >> 4) - KC_LOOK;   // first staged chunk (may be negative)
-        __syncthreads();
-        // ---- stage: chunk c_lo + i -> Fs[i], D bits --------------------------------------------
-        for (int i = tid; i < KC_THREADS + KC_LOOK; i += KC_THREADS) {
+        const int64_t g_lo = span * KC_SPAN + warp * 512;  // first position of this warp's sub-span
+        const int64_t c_lo = (g_lo >> 4) - KC_LOOK;        // first staged chunk (may be negative)
+        __syncwarp();
+        // ---- stage: chunk c_lo + i -> Fs[i], D and S bits ----------------------------------------
+        for (int i = lane; i < 32 + KC_LOOK; i += 32) {
             const int64_t c = c_lo + i;
-            uint32_t f = 0, dbits = 0;
+            uint32_t f = 0, dbits = 0, sb = 0;
             if (c >= 0 && c * 16 < n_bases) {
                 const uint4 v = __ldg(reinterpret_cast<const uint4 *>(bases) + c);
+                sb = __ldg(sbits + c);
                 uint32_t cw[4], bw[4];
                 kc_classify4(v.x, cw[0], bw[0]);
                 kc_classify4(v.y, cw[1], bw[1]);
@@ -168,30 +186,9 @@ kcount_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ of
                 if (rem < 16) dbits &= 0xFFFFu << (16 - rem);
             }
             Fs[i] = f;
-            DSs[i] = dbits << 16;
+            DSs[i] = (dbits << 16) | sb;
         }
-        // ---- read starts inside the staged range: first read with offsets[r] >= range start -----
-        if (tid == 0) {
-            const int64_t lo_pos = max((int64_t)0, c_lo * 16);
-            int64_t a = 0, b = n_reads;  // offsets[a..b], find the first index with offsets[idx] >= lo_pos
-            while (a < b) {
-                const int64_t m = (a + b) >> 1;
-                if ((int64_t)offsets[m] < lo_pos) a = m + 1;
-                else b = m;
-            }
-            r_first = a;
-        }
-        __syncthreads();
-        {
-            const int64_t hi_pos = min(n_bases, g_lo + KC_SPAN);
-            for (int64_t r = r_first + tid; r < n_reads; r += KC_THREADS) {
-                const int64_t o = offsets[r];
-                if (o >= hi_pos) break;
-                const int64_t rel = o - c_lo * 16;
-                atomicOr(&DSs[rel >> 4], 1u << (15 - (int)(rel & 15)));
-            }
-        }
-        __syncthreads();
+        __syncwarp();
 
         // ---- 16 positions per thread -----------------------------------------------------------
         const int64_t g0 = g_lo + 16 * tid;
@@ -207,27 +204,32 @@ kcount_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ of
             uint32_t ok = (~(uint32_t)inval) & 0xFFFFu;  // bit 15-b = position g0+b ends a counted k-mer
             // the look-back of the very first chunks is "undefined", positions >= n_bases have D = 0
             n_valid += __popc(ok);
-            uint64_t keys[16];
+            // groups of 4 windows: keys, then the 4 first-probe slots are loaded together (4 sectors in
+            // flight per thread; a deeper look-ahead would push the in-flight footprint past the L2), then the
+            // dependent compare / CAS / RED steps run
 #pragma unroll
-            for (int b = 0; b < 16; b++) {
-                const int sh = 2 * (15 - b);
-                const uint32_t klo = __funnelshift_r(f_0, f_m1, sh);
-                const uint32_t khi = __funnelshift_r(f_m1, f_m2, sh);
-                const uint64_t kmer = (((uint64_t)khi << 32) | klo) & kmask;
-                uint64_t key = kmer;
-                if (RCOMP) {
-                    const uint64_t rk = bb_rcomp(kmer, k);
-                    key = rk > kmer ? rk : kmer;
-                }
-                keys[b] = key;
-                if ((ok >> (15 - b)) & 1u) {
-                    const KSlot *p = t.slots + kc_slot_of(key, t.shift);
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-                }
-            }
+            for (int b0 = 0; b0 < 16; b0 += 4) {
+                if (((ok >> (12 - b0)) & 0xFu) == 0) continue;
+                uint64_t keys[4], sl[4];
+                ulonglong2 snap[4];
 #pragma unroll
-            for (int b = 0; b < 16; b++) {
-                if ((ok >> (15 - b)) & 1u) n_created += kc_insert(t, keys[b], 1u, &ctr->overflow);
+                for (int q = 0; q < 4; q++) {
+                    const int sh = 2 * (15 - (b0 + q));
+                    const uint32_t klo = __funnelshift_r(f_0, f_m1, sh);
+                    const uint32_t khi = __funnelshift_r(f_m1, f_m2, sh);
+                    const uint64_t kmer = (((uint64_t)khi << 32) | klo) & kmask;
+                    uint64_t key = kmer;
+                    if (RCOMP) {
+                        const uint64_t rk = bb_rcomp(kmer, k);
+                        key = rk > kmer ? rk : kmer;
+                    }
+                    keys[q] = key;
+                    sl[q] = kc_slot_of(key, t.shift);
+                    if ((ok >> (15 - (b0 + q))) & 1u) snap[q] = __ldcg(reinterpret_cast<const ulonglong2 *>(t.slots + sl[q]));
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if ((ok >> (15 - (b0 + q))) & 1u) n_created += kc_insert_from(t, sl[q], snap[q], keys[q], 1u, &ctr->overflow);
             }
         }
     }
@@ -358,7 +360,8 @@ struct kcount_handle {
     // host path staging
     uint8_t *d_bases = nullptr;
     uint32_t *d_off = nullptr;
-    int64_t cap_bases = 0, cap_reads = 0;
+    uint16_t *d_sbits = nullptr;  // read-start bit stream of the batch being counted
+    int64_t cap_bases = 0, cap_reads = 0, cap_sbits = 0;
     std::vector<uint32_t> h_off;
     cudaStream_t st = nullptr;
 };
@@ -452,6 +455,19 @@ int count_device(kcount_handle *h, const uint8_t *d_bases, const uint32_t *d_off
     if (n_bases <= 0) return 0;
     if (reinterpret_cast<uintptr_t>(d_bases) & 15) return kerr(h, "d_bases must be 16-byte aligned");
     const int64_t n_spans = (n_bases + KC_SPAN - 1) / KC_SPAN;
+    // read-start bit stream for this batch (2 bytes per 16 bases)
+    const int64_t sb_bytes = ((n_bases + 31) / 32 + 2) * 4;
+    if (sb_bytes > h->cap_sbits) {
+        KCK(cudaStreamSynchronize(st));
+        cudaFree(h->d_sbits);
+        h->d_sbits = nullptr;
+        h->cap_sbits = sb_bytes + sb_bytes / 8 + 4096;
+        KCK(cudaMalloc(&h->d_sbits, (size_t)h->cap_sbits));
+    }
+    KCK(cudaMemsetAsync(h->d_sbits, 0, (size_t)sb_bytes, st));
+    kc_starts_kernel<<<(unsigned)std::min<int64_t>((n_reads + 255) / 256, (int64_t)h->sm_count * 16), 256, 0, st>>>(
+        d_off, n_reads, reinterpret_cast<uint32_t *>(h->d_sbits));
+    h->launches += 1;
     int64_t span = 0;
     while (span < n_spans) {
         int64_t allowed = 0;
@@ -461,9 +477,9 @@ int count_device(kcount_handle *h, const uint8_t *d_bases, const uint32_t *d_off
         take = std::min(take, n_spans - span);
         const int blocks = (int)std::min<int64_t>(take, (int64_t)h->sm_count * 8);
         if (h->rcomp)
-            kcount_kernel<true><<<blocks, KC_THREADS, 0, st>>>(d_bases, d_off, n_reads, n_bases, span, span + take, h->k, view(h), h->d_ctr);
+            kcount_kernel<true><<<blocks, KC_THREADS, 0, st>>>(d_bases, h->d_sbits, n_bases, span, span + take, h->k, view(h), h->d_ctr);
         else
-            kcount_kernel<false><<<blocks, KC_THREADS, 0, st>>>(d_bases, d_off, n_reads, n_bases, span, span + take, h->k, view(h), h->d_ctr);
+            kcount_kernel<false><<<blocks, KC_THREADS, 0, st>>>(d_bases, h->d_sbits, n_bases, span, span + take, h->k, view(h), h->d_ctr);
         h->launches += 1;
         KCK(cudaGetLastError());
         h->added_since += take * (int64_t)KC_SPAN;
@@ -503,6 +519,8 @@ int kcount_b200_create(int32_t k, int32_t rcomp, int64_t initial_keys, int32_t d
     if (cudaSetDevice(device) != cudaSuccess) return fail("cudaSetDevice failed");
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
+    // random 16-byte slot accesses: ask the L2 not to fetch more than the touched sector (a hint; may be ignored)
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
     uint64_t n = 1 << 16;
     while (initial_keys > 0 && (int64_t)(n / 2) < initial_keys) n <<= 1;
     if (cudaMalloc(&h->d_ctr, sizeof(KCounters)) != cudaSuccess) return fail("cudaMalloc failed");
@@ -710,6 +728,7 @@ void kcount_b200_destroy(kcount_handle *h) {
     cudaFree(h->d_ctr);
     cudaFree(h->d_bases);
     cudaFree(h->d_off);
+    cudaFree(h->d_sbits);
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
 }
