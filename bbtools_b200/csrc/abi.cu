@@ -32,7 +32,11 @@ struct Slot {
     int64_t *d_maskoff = nullptr;
     int32_t *d_handoff = nullptr;
     unsigned int *d_handoff_n = nullptr;
-    int64_t cap_bases = 0, cap_reads = 0, cap_maskwords = 0;
+    // scratch of the direct (HBM-table) path: per-read first/last hit, read-start bit stream
+    unsigned long long *d_first64 = nullptr;
+    int *d_lastpos = nullptr;
+    uint16_t *d_sbits = nullptr;
+    int64_t cap_bases = 0, cap_reads = 0, cap_maskwords = 0, cap_sbits = 0;
     std::mutex mu;
 };
 
@@ -59,6 +63,10 @@ struct bbduk_handle {
     int32_t *dev_handoff = nullptr;
     unsigned int *dev_handoff_n = nullptr;
     int64_t dev_handoff_cap = 0;
+    unsigned long long *dev_first64 = nullptr;
+    int *dev_lastpos = nullptr;
+    uint16_t *dev_sbits = nullptr;
+    int64_t dev_sbits_cap = 0, dev_first_cap = 0;
     std::mutex dev_mu;
 };
 
@@ -115,6 +123,13 @@ void free_slot(Slot &s) {
     cudaFree(s.d_maskoff);
     cudaFree(s.d_handoff);
     cudaFree(s.d_handoff_n);
+    cudaFree(s.d_first64);
+    cudaFree(s.d_lastpos);
+    cudaFree(s.d_sbits);
+    s.d_first64 = nullptr;
+    s.d_lastpos = nullptr;
+    s.d_sbits = nullptr;
+    s.cap_sbits = 0;
     s.d_bases = nullptr;
     s.d_off64 = nullptr;
     s.d_off32 = nullptr;
@@ -127,7 +142,13 @@ void free_slot(Slot &s) {
     s.cap_bases = s.cap_reads = s.cap_maskwords = 0;
 }
 
-int ensure_slot(bbduk_handle *h, Slot &s, int64_t n_reads, int64_t n_bases, int64_t n_maskwords) {
+int ensure_slot(bbduk_handle *h, Slot &s, int64_t n_reads, int64_t n_bases, int64_t n_maskwords, bool direct) {
+    if (direct && (int64_t)direct_sbits_bytes(n_bases) > s.cap_sbits) {
+        cudaFree(s.d_sbits);
+        s.d_sbits = nullptr;
+        s.cap_sbits = (int64_t)direct_sbits_bytes(n_bases + n_bases / 8 + 4096);
+        CKH(cudaMalloc(&s.d_sbits, (size_t)s.cap_sbits));
+    }
     if (!s.st) {
         CKH(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
         CKH(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
@@ -150,6 +171,10 @@ int ensure_slot(bbduk_handle *h, Slot &s, int64_t n_reads, int64_t n_bases, int6
         cudaFree(s.d_maskoff);
         cudaFree(s.d_handoff);
         cudaFree(s.d_handoff_n);
+        cudaFree(s.d_first64);
+        cudaFree(s.d_lastpos);
+        CKH(cudaMalloc(&s.d_first64, sizeof(unsigned long long) * c));
+        CKH(cudaMalloc(&s.d_lastpos, sizeof(int) * c));
         CKH(cudaMalloc(&s.d_off64, sizeof(int64_t) * c));
         CKH(cudaMalloc(&s.d_off32, sizeof(uint32_t) * c));
         CKH(cudaMalloc(&s.d_id0, sizeof(int32_t) * c));
@@ -172,9 +197,21 @@ int ensure_slot(bbduk_handle *h, Slot &s, int64_t n_reads, int64_t n_bases, int6
 }
 
 // dispatch one device-resident batch: fast kernel where it applies, generic kernel for the rest
-int run_batch(bbduk_handle *h, const uint8_t *d_bases, const uint32_t *d_off, int64_t n_reads, int paired,
+struct DirectScratch {
+    unsigned long long *first64;
+    int *lastpos;
+    uint16_t *sbits;
+};
+
+// which kernel family a batch of this handle goes to
+bool uses_direct(const bbduk_handle *h, int max_read_len) {
+    const BBTable t = h->table.view();
+    return !plan_fast(h->p, t, max_read_len).usable && plan_direct(h->p, t);
+}
+
+int run_batch(bbduk_handle *h, const uint8_t *d_bases, const uint32_t *d_off, int64_t n_reads, int64_t n_bases, int paired,
               const bbduk_out &dout, bbduk_stats *d_stats, int max_read_len, int32_t *d_handoff,
-              unsigned int *d_handoff_n, cudaStream_t st) {
+              unsigned int *d_handoff_n, const DirectScratch &ds, cudaStream_t st) {
     if (n_reads <= 0) return 0;
     const BBTable t = h->table.view();
     const int64_t n_units = paired ? n_reads / 2 : n_reads;
@@ -190,6 +227,17 @@ int run_batch(bbduk_handle *h, const uint8_t *d_bases, const uint32_t *d_off, in
                            h->d_scaf_bases, h->sm_count, st))
             return set_err(h, std::string("generic kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
         h->launches += 1;
+        return 0;
+    }
+    if (!plan.usable && plan_direct(h->p, t) && ds.first64 && ds.sbits && n_bases >= 0) {
+        // HBM-resident table: flat position-parallel probe, then the per-read epilogue
+        const int n1 = launch_direct(d_bases, d_off, n_reads, n_bases, paired, h->p, t, ds.first64, ds.lastpos, ds.sbits,
+                                     h->sm_count, st);
+        if (n1 < 0) return set_err(h, std::string("direct kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+        const int n2 = launch_epilogue(d_bases, d_off, n_reads, paired, h->p, t, dout, d_stats, h->d_scaf_reads,
+                                       h->d_scaf_bases, ds.first64, ds.lastpos, h->sm_count, st);
+        if (n2 < 0) return set_err(h, std::string("epilogue kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+        h->launches += n1 + n2;
         return 0;
     }
     if (launch_generic(d_bases, d_off, n_units, paired, nullptr, nullptr, h->p, t, dout, d_stats, h->d_scaf_reads,
@@ -411,7 +459,31 @@ int bbduk_b200_process_device(bbduk_handle *h, const uint8_t *d_bases, const uin
         CKH(cudaMemcpyAsync(&mx, h->dev_handoff_n + 1, sizeof mx, cudaMemcpyDeviceToHost, st));
         CKH(cudaStreamSynchronize(st));
     }
-    return run_batch(h, d_bases, d_offsets, n_reads, paired, *d_out, d_stats, (int)mx, h->dev_handoff, h->dev_handoff_n, st);
+    DirectScratch ds{nullptr, nullptr, nullptr};
+    int64_t n_bases = -1;
+    if (uses_direct(h, (int)mx)) {
+        // the flat scan needs the batch's total base count: one 4-byte read-back
+        uint32_t last = 0;
+        CKH(cudaMemcpyAsync(&last, d_offsets + n_reads, sizeof last, cudaMemcpyDeviceToHost, st));
+        CKH(cudaStreamSynchronize(st));
+        n_bases = (int64_t)last;
+        if (reinterpret_cast<uintptr_t>(d_bases) & 15) return set_err(h, "d_bases must be 16-byte aligned");
+        if (n_reads + 8 > h->dev_first_cap) {
+            cudaFree(h->dev_first64);
+            cudaFree(h->dev_lastpos);
+            h->dev_first_cap = n_reads + n_reads / 8 + 1024;
+            CKH(cudaMalloc(&h->dev_first64, sizeof(unsigned long long) * h->dev_first_cap));
+            CKH(cudaMalloc(&h->dev_lastpos, sizeof(int) * h->dev_first_cap));
+        }
+        if ((int64_t)direct_sbits_bytes(n_bases) > h->dev_sbits_cap) {
+            cudaFree(h->dev_sbits);
+            h->dev_sbits_cap = (int64_t)direct_sbits_bytes(n_bases + n_bases / 8 + 4096);
+            CKH(cudaMalloc(&h->dev_sbits, (size_t)h->dev_sbits_cap));
+        }
+        ds = DirectScratch{h->dev_first64, h->dev_lastpos, h->dev_sbits};
+    }
+    return run_batch(h, d_bases, d_offsets, n_reads, n_bases, paired, *d_out, d_stats, (int)mx, h->dev_handoff,
+                     h->dev_handoff_n, ds, st);
 }
 
 int bbduk_b200_process(bbduk_handle *h, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, int32_t paired,
@@ -450,7 +522,8 @@ int bbduk_b200_process(bbduk_handle *h, const uint8_t *bases, const int64_t *off
         Slot &s = h->slots[h->next_slot++ % N_SLOTS];
         std::lock_guard<std::mutex> g(s.mu);
         if (s.done) cudaEventSynchronize(s.done);  // previous use of this slot has drained
-        if ((rc = ensure_slot(h, s, nr, nb, mw))) break;
+        const bool direct = uses_direct(h, 1 << 20);  // conservative: decided again per chunk in run_batch
+        if ((rc = ensure_slot(h, s, nr, nb, mw, direct))) break;
         // longest read of the chunk (host side, one pass over the offsets that are being copied anyway)
         int max_len = 0;
         for (int64_t i = r0; i < r1; i++) {
@@ -495,7 +568,9 @@ int bbduk_b200_process(bbduk_handle *h, const uint8_t *bases, const int64_t *off
             dout.maskbits = s.d_maskbits;
             dout.mask_off = s.d_maskoff;
         }
-        if (!rc) rc = run_batch(h, s.d_bases, s.d_off32, nr, paired, dout, d_stats, max_len, s.d_handoff, s.d_handoff_n, st);
+        if (!rc)
+            rc = run_batch(h, s.d_bases, s.d_off32, nr, nb, paired, dout, d_stats, max_len, s.d_handoff, s.d_handoff_n,
+                           DirectScratch{s.d_first64, s.d_lastpos, s.d_sbits}, st);
         if (out->id0) CKL(cudaMemcpyAsync(out->id0 + r0, s.d_id0, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, st));
         if (out->id0b) CKL(cudaMemcpyAsync(out->id0b + r0, s.d_id0b, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, st));
         if (out->lo) CKL(cudaMemcpyAsync(out->lo + r0, s.d_lo, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, st));
@@ -556,6 +631,9 @@ void bbduk_b200_destroy(bbduk_handle *h) {
     cudaFree(h->d_stats);
     cudaFree(h->dev_handoff);
     cudaFree(h->dev_handoff_n);
+    cudaFree(h->dev_first64);
+    cudaFree(h->dev_lastpos);
+    cudaFree(h->dev_sbits);
     delete h;
 }
 

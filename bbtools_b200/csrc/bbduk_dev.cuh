@@ -130,3 +130,57 @@ __device__ __forceinline__ BBPartProbe bb_part_probe(uint32_t v, uint32_t mult, 
     r.b2 = __umulhi(h, 0xC2B2AE3Du);
     return r;
 }
+
+// ---- exact key of a window that may contain undefined bases (SURVEY.md A.2 closed form) -------------
+// win: 2-bit codes of the 32 bases ending at the probe position, slot t = base i-t, undefined bases read as 0;
+// dw: their "defined" bits, bit t = base i-t. kmer keeps code 0 for undefined bases and is never reset; with
+// forbidNs the reverse k-mer only holds the bases after the last undefined one and the probe needs
+// len >= minlen2 (jgi/BBDuk.java:3882-3900). Returns false if the reference would not probe here.
+__device__ __forceinline__ uint64_t bb_spread2(uint32_t m) {  // bit t -> bits (2t+1, 2t)
+    uint64_t x = m;
+    x = (x | (x << 16)) & 0x0000FFFF0000FFFFull;
+    x = (x | (x << 8)) & 0x00FF00FF00FF00FFull;
+    x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    x = (x | (x << 2)) & 0x3333333333333333ull;
+    x = (x | (x << 1)) & 0x5555555555555555ull;
+    return x | (x << 1);
+}
+__device__ __forceinline__ bool bb_window_key(const BBParams &p, uint64_t win, uint32_t dw, uint64_t *key) {
+    const int k = p.k;
+    const uint32_t kbits = (k >= 32) ? 0xFFFFFFFFu : ((1u << k) - 1u);
+    uint64_t kmer = win & p.mask, rkmer;
+    if ((dw & kbits) == kbits) {
+        rkmer = bb_rcomp(kmer, k);
+    } else {
+        const uint64_t E = bb_spread2(dw & kbits);
+        kmer &= E;
+        if (p.forbidNs) {
+            const int len = __ffs(~dw) - 1;  // bases after the last undefined one (the window has one)
+            if (len < p.minlen2) return false;
+            rkmer = bb_rcomp(kmer, k) & ~((1ull << (2 * (k - len))) - 1ull) & p.mask;
+        } else {
+            rkmer = bb_rcomp(kmer, k) & bb_rcomp(~E, k);  // E reversed slot-wise
+        }
+    }
+    *key = bb_to_value(p, kmer, rkmer, p.kmask);
+    return true;
+}
+
+// lookup continuing from a bucket whose 32 bytes the caller has already loaded
+__device__ __forceinline__ int bb_table_get_from(const BBTable &t, uint64_t b, ulonglong2 k01, ulonglong2 k23, uint64_t key) {
+    const uint64_t bmask = t.slot_mask >> 2;
+    for (int probe = 0; probe < BB_MAX_PROBE / 4; probe++) {
+        int j = -1;
+        if (k01.x == key) j = 0;
+        else if (k01.y == key) j = 1;
+        else if (k23.x == key) j = 2;
+        else if (k23.y == key) j = 3;
+        if (j >= 0) return __ldg(t.vals + 4 * b + j);
+        if (k23.y == BB_EMPTY_KEY) return -1;
+        b = (b + 1) & bmask;
+        const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(t.keys + 4 * b);
+        k01 = __ldg(q);
+        k23 = __ldg(q + 1);
+    }
+    return -1;
+}

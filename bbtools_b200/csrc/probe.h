@@ -26,3 +26,15 @@ int launch_fast(const FastPlan &plan, const uint8_t *d_bases, const uint32_t *d_
                 const BBParams &p, const BBTable &t, const bbduk_out &out, bbduk_stats *d_stats,
                 unsigned long long *scaf_reads, unsigned long long *scaf_bases, int32_t *d_handoff,
                 unsigned int *d_handoff_n, int sm_count, cudaStream_t st);
+
+// HBM-resident tables (probe_direct.cu): flat position-parallel scan -> per-read first/last hit, then
+// launch_epilogue (probe_fast.cu stage D). launch_* return the number of kernels launched, <0 on error.
+bool plan_direct(const BBParams &p, const BBTable &t);
+size_t direct_sbits_bytes(int64_t n_bases);
+int launch_direct(const uint8_t *d_bases, const uint32_t *d_offsets, int64_t n_reads, int64_t n_bases, int paired,
+                  const BBParams &p, const BBTable &t, unsigned long long *d_first64, int *d_lastpos, uint16_t *d_sbits,
+                  int sm_count, cudaStream_t st);
+int launch_epilogue(const uint8_t *d_bases, const uint32_t *d_offsets, int64_t n_reads, int paired, const BBParams &p,
+                    const BBTable &t, const bbduk_out &out, bbduk_stats *d_stats, unsigned long long *scaf_reads,
+                    unsigned long long *scaf_bases, const unsigned long long *d_first64, const int *d_lastpos, int sm_count,
+                    cudaStream_t st);

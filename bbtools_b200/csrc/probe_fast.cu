@@ -169,11 +169,14 @@ enum { FM_KTRIM_R = 0, FM_KTRIM_L = 1, FM_KFILTER = 2 };
 // PARTS selects the scan: false = canonical k-mer against the bloom image of all keys;
 // true = forward part_w-mer against the pigeonhole part filter (see bbduk_dev.cuh), one lookup per
 // position, the hdist+1 parts of a window being the same lookup at different lags.
-template <int FMODE, bool RCOMP, bool K16, bool PARTS>
+// PRE = the first/last full-length hits of every read were already found by probe_direct.cu (pre_first /
+// pre_last): stages A-C compile away and only the per-read epilogue (stage D) runs.
+template <int FMODE, bool RCOMP, bool K16, bool PARTS, bool PRE = false>
 __global__ void __launch_bounds__(1024, 1)
 bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ offsets, int64_t n_reads, int paired,
                   BBParams p, BBTable t, bbduk_out out, bbduk_stats *stats, unsigned long long *scaf_reads,
-                  unsigned long long *scaf_bases, int32_t *handoff, unsigned int *handoff_n, FastGeom geo) {
+                  unsigned long long *scaf_bases, int32_t *handoff, unsigned int *handoff_n, FastGeom geo,
+                  const unsigned long long *__restrict__ pre_first = nullptr, const int *__restrict__ pre_last = nullptr) {
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t *filt = smem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -218,7 +221,7 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
         const int nchunks = (int)((base_addr + tile_hi - a0 + 15) >> 4);
         const int L = (int)(o1 - o0);
         const int maxL = __reduce_max_sync(0xFFFFFFFFu, L);
-        if (nchunks > geo.nch || maxL > MAX_FAST_LEN || ((maxL + 15) >> 4) > geo.csteps) {
+        if (!PRE && (nchunks > geo.nch || maxL > MAX_FAST_LEN || ((maxL + 15) >> 4) > geo.csteps)) {
             // tile does not fit the staging: hand its units to the generic kernel
             if (live && (!paired || !(lane & 1))) {
                 const unsigned int w = atomicAdd(handoff_n, 1u);
@@ -229,7 +232,7 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
         // ---- A. stage + convert ---------------------------------------------------------------
         for (int i = lane; i < geo.nbadw; i += 32) badw[i] = 0;
         __syncwarp();
-        for (int c = lane; c < nchunks + TAIL; c += 32) {
+        for (int c = lane; c < (PRE ? 0 : nchunks + TAIL); c += 32) {
             uint32_t f = 0, dbits = 0;
             if (c < nchunks) {
                 const uint4 v = __ldg(reinterpret_cast<const uint4 *>(a0) + c);
@@ -255,12 +258,12 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
         // ---- B. per-lane scan, C. pooled exact evaluation ----------------------------------------
         const int s = (int)(base_addr + o0 - a0);  // stream base of read position 0
         const int nsteps = (L + 15) >> 4;
-        const int max_steps = (maxL + 15) >> 4;
+        const int max_steps = PRE ? 0 : ((maxL + 15) >> 4);
         const int pairnum = (paired && (lane & 1)) ? 1 : 0;
         const bool skip = (p.skipR1 && pairnum == 0) || (p.skipR2 && pairnum == 1);
         const bool scan = live && L >= k && t.stored > 0 && !skip;
         bool has_undef = false;  // some chunk overlapping this read holds an undefined base
-        if (L > 0) {
+        if (!PRE && L > 0) {
             const int c0 = s >> 4, c1 = (s + L - 1) >> 4;
             for (int w = c0 >> 5; w <= (c1 >> 5); w++) {
                 uint32_t m = badw[w];
@@ -449,6 +452,10 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
             }
         }
 
+        if (PRE) {
+            first64[lane] = live ? pre_first[r] : ~0ull;
+            lastpos[lane] = (live && pre_last) ? pre_last[r] : -1;
+        }
         int found = 0, id0 = -1, minLoc = 999999999, maxLoc = -1, count = 0;
         int lo = 0, hi = L;
         bool discarded = false, ktrimmed = false;
@@ -462,7 +469,8 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
                 maxLoc = pos;
             }
         }
-        if (FMODE == FM_KTRIM_L) {
+        if (FMODE == FM_KTRIM_L && PRE && found) maxLoc = max(maxLoc, lastpos[lane]);
+        if (FMODE == FM_KTRIM_L && !PRE) {
             // ktrim=l also needs the LAST hit: walk the buffered candidates downwards from the read end
             // until one beyond the first hit is confirmed (same in-flight cap, highest position first)
             // hits at or below the forward phase's last confirmed hit are already accounted for
@@ -508,7 +516,7 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
             discarded = found > 0;
         } else {
             // ktrim guard (jgi/BBDuk.java:3868): reads shorter than k still get the short-k-mer tails
-            const bool tscan = live && t.stored > 0 && p.useShortKmers && L >= max(1, min(k, p.mink)) && !found && !skip;
+            const bool tscan = !PRE && live && t.stored > 0 && p.useShortKmers && L >= max(1, min(k, p.mink)) && !found && !skip;
             int minLocX = 999999999, maxLocX = -1;
             if (found) {
                 minLocX = minLoc + k;
@@ -677,17 +685,19 @@ bool canon_ok(const BBTable &t) {
     return t.filter != nullptr && t.n_filter_words > 0 && t.stored <= (int64_t)t.n_filter_words * 24;
 }
 
-FastGeom make_geom(const BBParams &p, const BBTable &t, int max_read_len) {
+FastGeom make_geom(const BBParams &p, const BBTable &t, int max_read_len, bool pre = false) {
     FastGeom g;
     const int lmax = std::max(max_read_len, 16);
-    g.nch = (32 * lmax + 15 + 15) / 16 + 1;
+    g.nch = pre ? 0 : (32 * lmax + 15 + 15) / 16 + 1;
     g.nbadw = (g.nch + 31) / 32 + 1;
-    g.csteps = (lmax + 15) / 16 + 1;
+    g.csteps = pre ? 0 : (lmax + 15) / 16 + 1;
     int wb = 32 * 8 + 32 * 4 + g.nbadw * 4 + (g.nch + PAD + TAIL) * 4 + ((g.nch + PAD + TAIL + 1) & ~1) * 2 + QCAP * 2 +
              g.csteps * 32 * 2;
     wb = (wb + 15) & ~15;
     g.warp_bytes = wb;
-    if (parts_ok(p, t)) {
+    if (pre) {
+        g.nfw = g.nsw = g.src_off = 0;
+    } else if (parts_ok(p, t)) {
         g.nfw = t.part_words;
         g.nsw = t.short_words;
         g.src_off = t.n_filter_words;
@@ -733,7 +743,7 @@ int launch_fast(const FastPlan &plan, const uint8_t *d_bases, const uint32_t *d_
     auto go = [&](auto kern) -> int {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes) != cudaSuccess) return -1;
         kern<<<blocks, threads, plan.smem_bytes, st>>>(d_bases, d_offsets, n_reads, paired, p, t, out, d_stats, scaf_reads,
-                                                       scaf_bases, d_handoff, d_handoff_n, g);
+                                                       scaf_bases, d_handoff, d_handoff_n, g, nullptr, nullptr);
         return cudaGetLastError() == cudaSuccess ? 1 : -1;
     };
     const bool k16 = p.k >= 16;
@@ -746,4 +756,25 @@ int launch_fast(const FastPlan &plan, const uint8_t *d_bases, const uint32_t *d_
     if (p.ktrimLeft) return BB_DISPATCH(FM_KTRIM_L);
     return BB_DISPATCH(FM_KTRIM_R);
 #undef BB_DISPATCH
+}
+
+// stage D only: ktrim arithmetic, minlen, pair logic, counters and outputs from precomputed first/last hits
+int launch_epilogue(const uint8_t *d_bases, const uint32_t *d_offsets, int64_t n_reads, int paired, const BBParams &p,
+                    const BBTable &t, const bbduk_out &out, bbduk_stats *d_stats, unsigned long long *scaf_reads,
+                    unsigned long long *scaf_bases, const unsigned long long *d_first64, const int *d_lastpos, int sm_count,
+                    cudaStream_t st) {
+    const FastGeom g = make_geom(p, t, 16, true);
+    const int threads = 1024;
+    const int smem = g.warps * g.warp_bytes + 64;
+    const int64_t n_tiles = (n_reads + 31) / 32;
+    const int blocks = (int)std::min<int64_t>(sm_count, (n_tiles + g.warps - 1) / g.warps);
+    auto go = [&](auto kern) -> int {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
+        kern<<<blocks, threads, smem, st>>>(d_bases, d_offsets, n_reads, paired, p, t, out, d_stats, scaf_reads, scaf_bases,
+                                            nullptr, nullptr, g, d_first64, d_lastpos);
+        return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    };
+    if (p.mode == MODE_KFILTER) return go(bbduk_fast_kernel<FM_KFILTER, true, true, true, true>);
+    if (p.ktrimLeft) return go(bbduk_fast_kernel<FM_KTRIM_L, true, true, true, true>);
+    return go(bbduk_fast_kernel<FM_KTRIM_R, true, true, true, true>);
 }
