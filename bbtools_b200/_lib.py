@@ -29,6 +29,9 @@ SYMBOLS = [
     ("bbduk_b200_destroy", None, [C.c_void_p]),
     ("bbduk_b200_synth_pairs", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_uint64,
                                          C.c_int32, C.c_int32, C.c_void_p]),
+    ("bbduk_b200_synth_reference", C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]),
+    ("bbduk_b200_synth_contam", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64,
+                                          C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     # include/kcount_b200.h
     ("kcount_b200_create", C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]),
     ("kcount_b200_add_reads", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),

@@ -396,6 +396,7 @@ int bbduk_b200_table_describe(bbduk_handle *h, bbduk_table_desc *d) {
     d->scalars[4] = h->table.n_parts | ((int64_t)h->table.part_w << 8);
     d->scalars[5] = (int64_t)h->table.part_lag[0] | ((int64_t)h->table.part_lag[1] << 8) |
                     ((int64_t)h->table.part_lag[2] << 16) | ((int64_t)h->table.part_lag[3] << 24);
+    d->scalars[6] = h->table.big_words;
     return 0;
 }
 
@@ -412,6 +413,7 @@ int bbduk_b200_table_alloc(bbduk_handle *h, bbduk_table_desc *d) {
     h->table.n_filter_words = (uint32_t)d->scalars[1];
     h->table.part_words = (uint32_t)d->scalars[2];
     h->table.short_words = (uint32_t)d->scalars[3];
+    h->table.big_words = (uint32_t)d->scalars[6];
     h->table.n_parts = (int32_t)(d->scalars[4] & 0xFF);
     h->table.part_w = (int32_t)(d->scalars[4] >> 8);
     for (int j = 0; j < 4; j++) h->table.part_lag[j] = (int32_t)((d->scalars[5] >> (8 * j)) & 0xFF);

@@ -108,6 +108,8 @@ __device__ __forceinline__ uint32_t bb_filter_bits(uint32_t t) {
     return __funnelshift_l(BB_FPAT1, BB_FPAT1, t) | __funnelshift_l(BB_FPAT2, BB_FPAT2, t >> 5);
 }
 
+__device__ __forceinline__ uint32_t bb_big_word(uint32_t t, uint32_t n_words) { return __umulhi(t, n_words); }
+
 // ---- pigeonhole part filter -------------------------------------------------------------------------
 // A window can only hit the table if, on one strand, it agrees with an UNMUTATED reference k-mer on at
 // least one of hdist+1 disjoint parts (substitutions only). The filter holds the part values of every

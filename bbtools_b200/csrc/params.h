@@ -51,6 +51,7 @@ struct BBTable {
     uint32_t n_filter_words;  // canonical bloom words
     uint32_t part_words;      // part filter words (0 = not available for this configuration)
     uint32_t short_words;     // bloom over the short (len<k) keys only
+    uint32_t big_words;       // L2-resident one-bit-per-key filter in front of an HBM-resident array (0 = none)
     int32_t n_parts;          // pigeonhole parts = hdist+1
     int32_t part_w;           // bases per part (<=16)
     int32_t part_lag[4];      // part j is the part_w-mer that ends part_lag[j] bases before the window end

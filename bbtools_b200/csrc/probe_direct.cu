@@ -47,6 +47,46 @@ __device__ __forceinline__ uint64_t dp_smear(uint64_t x, int n) {  // OR of x >>
     return x;
 }
 
+// one 32-byte bucket in one instruction; table lines are use-once, so they must not push the filter out of L2
+__device__ __forceinline__ void dp_load_bucket(const uint64_t *p, ulonglong2 &k01, ulonglong2 &k23) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(k01.x), "=l"(k01.y), "=l"(k23.x), "=l"(k23.y)
+                 : "l"(p));
+}
+__device__ __forceinline__ uint64_t dp_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint32_t dp_load_filter(const uint32_t *p, uint64_t pol) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
+// out-of-line slow paths keep the probe loop small enough for the instruction cache
+__device__ __noinline__ bool dp_dirty_key(const BBParams &p, uint64_t win, uint32_t dw, uint64_t *key) {
+    return bb_window_key(p, win, dw, key);
+}
+__device__ __noinline__ int dp_chain(const BBTable &t, uint64_t b, uint64_t key) {
+    // the first bucket was full and did not hold the key: continue along the chain
+    const uint64_t bmask = t.slot_mask >> 2;
+    b = (b + 1) & bmask;
+    const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(t.keys + 4 * b);
+    return bb_table_get_from(t, b, __ldg(q), __ldg(q + 1), key);
+}
+// id of `key` given its first bucket's 32 bytes; -1 if absent
+__device__ __forceinline__ int dp_resolve(const BBTable &t, uint64_t b, const ulonglong2 &k01, const ulonglong2 &k23, uint64_t key) {
+    int j = -1;
+    if (k01.x == key) j = 0;
+    else if (k01.y == key) j = 1;
+    else if (k23.x == key) j = 2;
+    else if (k23.y == key) j = 3;
+    if (j >= 0) return __ldg(t.vals + 4 * b + j);
+    if (k23.y == BB_EMPTY_KEY) return -1;
+    return dp_chain(t, b, key);
+}
+
 __global__ void dp_starts_kernel(const uint32_t *__restrict__ offsets, int64_t n_reads, uint32_t *sbits) {
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t o = offsets[r];
@@ -79,6 +119,22 @@ __device__ __noinline__ void dp_hit(const uint32_t *__restrict__ offsets, int64_
     if (lastpos) atomicMax(lastpos + r, (int)pos);
 }
 
+// a hit at flat position g whose read index was derived from the start bits: verify, else search
+__device__ __noinline__ void dp_credit(const uint32_t *__restrict__ offsets, int64_t n_reads, int64_t g, int64_t r, int id,
+                                       int paired, const BBParams &p, unsigned long long *first64, int *lastpos) {
+    bool ok = r >= 0 && r < n_reads;
+    if (ok) ok = (int64_t)offsets[r] <= g && g < (int64_t)offsets[r + 1];
+    if (!ok) {  // empty reads share a start bit: fall back to the search
+        dp_hit(offsets, n_reads, g, id, paired, p, first64, lastpos);
+        return;
+    }
+    const int pairnum = (paired && (r & 1)) ? 1 : 0;
+    if ((p.skipR1 && pairnum == 0) || (p.skipR2 && pairnum == 1)) return;
+    const unsigned int pos = (unsigned int)(g - (int64_t)offsets[r]);
+    atomicMin(first64 + r, ((unsigned long long)pos << 32) | (unsigned int)id);
+    if (lastpos) atomicMax(lastpos + r, (int)pos);
+}
+
 __global__ void __launch_bounds__(DP_THREADS, 3)
 bbduk_direct_kernel(const uint8_t *__restrict__ bases, const uint16_t *__restrict__ sbits,
                     const uint32_t *__restrict__ offsets, int64_t n_reads, int64_t n_bases, int paired, BBParams p,
@@ -90,6 +146,10 @@ bbduk_direct_kernel(const uint8_t *__restrict__ bases, const uint16_t *__restric
     const int k = p.k;
     const int64_t n_spans = (n_bases + DP_SPAN - 1) / DP_SPAN;
     const uint64_t bmask = t.slot_mask >> 2;
+    // L2-resident one-bit-per-key filter in front of the HBM probes (none for small arrays)
+    const uint32_t *bigf = t.filter + t.n_filter_words + t.part_words + t.short_words;
+    const uint32_t big_words = t.big_words;
+    const uint64_t pol_keep = dp_policy_evict_last();
 
     for (int64_t span = blockIdx.x; span < n_spans; span += gridDim.x) {
         const int64_t g_lo = span * DP_SPAN + warp * 512;
@@ -122,7 +182,6 @@ bbduk_direct_kernel(const uint8_t *__restrict__ bases, const uint16_t *__restric
         __syncwarp();
 
         const int64_t g0 = g_lo + 16 * lane;
-        if (g0 >= n_bases) continue;
         const uint32_t f_m2 = Fs[lane], f_m1 = Fs[lane + 1], f_0 = Fs[lane + 2];
         const uint32_t w0 = DSs[lane], w1 = DSs[lane + 1], w2 = DSs[lane + 2];
         // 48-base strings, base i of the string at bit 47-i; this thread's positions are bases 32..47
@@ -134,15 +193,22 @@ bbduk_direct_kernel(const uint8_t *__restrict__ bases, const uint16_t *__restric
         const uint32_t cross = (uint32_t)(k > 1 ? dp_smear(Sall, k - 1) : 0ull) & 0xFFFFu;
         uint32_t exists = ~cross & 0xFFFFu;
         const int64_t left = n_bases - g0;
-        if (left < 16) exists &= 0xFFFFu << (16 - left);
+        if (left < 16) exists &= (left <= 0) ? 0u : (0xFFFFu << (16 - left));
         const uint32_t dirty = (uint32_t)dp_smear(U, k) & exists;  // window holds an undefined base: exact path
         const uint32_t clean = exists & ~dirty;
+        // the read of a hit: index of the read holding the sub-span's first position (one binary search per warp,
+        // only if the warp has a hit at all) + the read starts seen since then
+        bool have_base = false;
+        int64_t r_base = 0;
+        int starts_before = 0;
+        const uint32_t s16 = w2 & 0xFFFFu;  // bit 15-b = a read starts at position g0+b
 
-#pragma unroll
+#pragma unroll 1
         for (int b0 = 0; b0 < 16; b0 += 4) {
             const uint32_t cm = (clean >> (12 - b0)) & 0xFu, dm = (dirty >> (12 - b0)) & 0xFu;
-            if ((cm | dm) == 0) continue;
+            if (!__any_sync(0xFFFFFFFFu, (cm | dm) != 0)) continue;
             uint64_t keys[4], bk[4];
+            uint32_t hs[4], fw[4];
             ulonglong2 k01[4], k23[4];
             bool probe[4];
 #pragma unroll
@@ -159,21 +225,55 @@ bbduk_direct_kernel(const uint8_t *__restrict__ bases, const uint16_t *__restric
                     key = bb_to_value(p, kmer, bb_rcomp(kmer, k), p.kmask);
                 } else if ((dm >> (3 - q)) & 1u) {
                     const uint32_t dw = (uint32_t)(Dall >> (15 - b));  // bit t = base g-t
-                    probe[q] = bb_window_key(p, win, dw, &key);
+                    probe[q] = dp_dirty_key(p, win, dw, &key);
                 }
                 keys[q] = key;
-                bk[q] = bb_bucket(bb_fhash64(key), t.bucket_shift);
-                if (probe[q]) {
-                    const ulonglong2 *ptr = reinterpret_cast<const ulonglong2 *>(t.keys + 4 * bk[q]);
-                    k01[q] = __ldg(ptr);
-                    k23[q] = __ldg(ptr + 1);
-                }
+                hs[q] = bb_fhash64(key);
+                bk[q] = bb_bucket(hs[q], t.bucket_shift);
+                if (probe[q] && big_words) fw[q] = dp_load_filter(bigf + bb_big_word(hs[q], big_words), pol_keep);
             }
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                if (!probe[q]) continue;
-                const int id = bb_table_get_from(t, bk[q] & bmask, k01[q], k23[q], keys[q]);
-                if (id > 0) dp_hit(offsets, n_reads, g0 + b0 + q, id, paired, p, first64, lastpos);
+                if (big_words) probe[q] = probe[q] && ((fw[q] >> (hs[q] & 31u)) & 1u);
+                if (probe[q]) dp_load_bucket(t.keys + 4 * bk[q], k01[q], k23[q]);
+            }
+            int ids[4];
+            bool any_hit = false;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                ids[q] = probe[q] ? dp_resolve(t, bk[q] & bmask, k01[q], k23[q], keys[q]) : -1;
+                any_hit |= ids[q] > 0;
+            }
+            if (!__any_sync(0xFFFFFFFFu, any_hit)) continue;
+            if (!have_base) {
+                int64_t rb = 0;
+                if (lane == 0) {
+                    int64_t a = 0, b = n_reads + 1;  // first index with offsets[idx] > g_lo
+                    while (a < b) {
+                        const int64_t m = (a + b) >> 1;
+                        if ((int64_t)offsets[m] <= g_lo) a = m + 1;
+                        else b = m;
+                    }
+                    rb = a - 1;
+                }
+                // the start bit of g_lo itself belongs to read r_base
+                r_base = __shfl_sync(0xFFFFFFFFu, rb, 0) - (int64_t)((__shfl_sync(0xFFFFFFFFu, s16, 0) >> 15) & 1u);
+                const int cnt = __popc(s16);
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                starts_before = incl - cnt;
+                have_base = true;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (ids[q] <= 0) continue;
+                const int b = b0 + q;
+                dp_credit(offsets, n_reads, g0 + b, r_base + starts_before + __popc(s16 >> (15 - b)), ids[q], paired, p, first64,
+                          lastpos);
             }
         }
     }

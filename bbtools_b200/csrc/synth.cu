@@ -63,7 +63,51 @@ __global__ void synth_pairs_kernel(uint8_t *bases, uint32_t *offsets, int64_t n_
     bases[(2 * lp + 1) * L + j] = b2;
 }
 
+// cfg 3 / cfg 4 reference: base i = ACGT[rnd(seed, 5, i) & 3]  (synth.py:random_reference)
+__global__ void synth_reference_kernel(uint8_t *out, int64_t n, uint64_t seed) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = kACGT[rnd(seed, 5, (uint64_t)i) & 3ull];
+}
+
+// cfg 3 reads (synth.py:contaminant_reads): contam_pct % copied from the reference (forward strand, uniform
+// start over the concatenated reference), the rest uniform ACGT; then substitutions and N's
+__global__ void synth_contam_kernel(uint8_t *bases, uint32_t *offsets, int64_t n_reads, int64_t first_read, int L,
+                                    const uint8_t *__restrict__ ref, int64_t ref_len, uint64_t seed, int contam_pct,
+                                    int sub_per_10k, int n_per_10k) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t <= n_reads) offsets[t] = (uint32_t)(t * L);
+    if (t >= n_reads * L) return;
+    const int64_t lr = t / L;
+    const int j = (int)(t - lr * L);
+    const uint64_t r = (uint64_t)(first_read + lr);
+    const uint64_t g = r * (uint64_t)L + (uint64_t)j;
+    uint8_t b = kACGT[rnd(seed, 1, g) & 3ull];
+    const uint64_t c = rnd(seed, 0, r);
+    if ((int)(c % 100ull) < contam_pct) {
+        const uint64_t start = (c >> 8) % (uint64_t)(ref_len - L + 1);
+        b = ref[start + (uint64_t)j];
+    }
+    bases[t] = with_errors(b, rnd(seed, 3, g), sub_per_10k, n_per_10k);
+}
+
 }  // namespace
+
+extern "C" BBDUK_API int bbduk_b200_synth_reference(uint8_t *d_out, int64_t n, uint64_t seed, void *stream) {
+    if (n <= 0) return 1;
+    synth_reference_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_out, n, seed);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+extern "C" BBDUK_API int bbduk_b200_synth_contam(uint8_t *d_bases, uint32_t *d_offsets, int64_t n_reads, int64_t first_read,
+                                                 int32_t read_len, const uint8_t *d_ref, int64_t ref_len, uint64_t seed,
+                                                 int32_t contam_pct, int32_t sub_per_10k, int32_t n_per_10k, void *stream) {
+    if (n_reads <= 0 || read_len <= 0 || ref_len < read_len || !d_ref) return 1;
+    if (n_reads * (int64_t)read_len >= (1ll << 32)) return 1;
+    const int64_t threads = std::max<int64_t>(n_reads * read_len, n_reads + 1);
+    synth_contam_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        d_bases, d_offsets, n_reads, first_read, read_len, d_ref, ref_len, seed, contam_pct, sub_per_10k, n_per_10k);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
 
 extern "C" BBDUK_API int bbduk_b200_synth_pairs(uint8_t *d_bases, uint32_t *d_offsets, int64_t n_pairs, int64_t first_pair,
                                                 int32_t read_len, uint64_t seed, int32_t sub_per_10k, int32_t n_per_10k,

@@ -9,6 +9,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstdio>
 #include <vector>
 
@@ -236,6 +237,17 @@ __global__ void filter_build_kernel(const uint64_t *__restrict__ keys, int64_t n
     }
 }
 
+// L2-resident filter: ONE bit per key, word = high-half range reduction of the 32-bit hash, bit = its low 5 bits
+__global__ void big_filter_build_kernel(const uint64_t *__restrict__ keys, int64_t n, uint32_t *filter, uint32_t n_words) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = keys[i];
+        if (k != BB_EMPTY_KEY) {
+            const uint32_t t = bb_fhash64(k);
+            atomicOr(filter + bb_big_word(t, n_words), 1u << (t & 31u));
+        }
+    }
+}
+
 // short-key bloom: keys whose length marker sits below bit 2k (the mink..k-1 tails)
 __global__ void short_filter_build_kernel(const uint64_t *__restrict__ keys, int64_t n, uint64_t kmask, uint32_t *filter,
                                           uint32_t n_words) {
@@ -324,6 +336,7 @@ BBTable DeviceTable::view() const {
     t.n_filter_words = n_filter_words;
     t.part_words = part_words;
     t.short_words = short_words;
+    t.big_words = big_words;
     t.n_parts = n_parts;
     t.part_w = part_w;
     for (int j = 0; j < 4; j++) t.part_lag[j] = part_lag[j];
@@ -530,6 +543,28 @@ int DeviceTable::build(const BBParams &p, const std::vector<uint8_t> &ref, const
         short_filter_build_kernel<<<1184, 256, 0, st>>>(d_keys, n_slots, p.kmask, d_filter + n_filter_words + part_words,
                                                          short_words);
         (*launches)++;
+    }
+    // HBM-resident arrays (too many keys for the on-chip images): an L2-resident one-bit-per-key filter, up to
+    // a cap well inside the 126 MB L2, appended to the filter buffer so that it replicates with it
+    big_words = 0;
+    if (stored > (int64_t)n_filter_words * 24) {
+        // ~2.75 bits per key: measured best on cfg 3 (1e8 keys -> 32 MB); beyond 64 MB the filter starts to fall
+        // out of the L2 next to the streaming reads (cfg 4, 2.9e8 keys: 64 MB best, 80 MB slower)
+        const uint64_t want_words = std::max<uint64_t>(1u << 16, (uint64_t)((double)stored * 2.75 / 32.0));
+        uint64_t cap_mb = 64;
+        if (const char *e = getenv("BBDUK_B200_BIGFILTER_MB")) cap_mb = (uint64_t)std::max(1, atoi(e));
+        const uint32_t bw = (uint32_t)std::min<uint64_t>(want_words, (cap_mb << 20) / 4);
+        uint32_t *nf = nullptr;
+        const size_t old_words = total_filter_words();
+        CKC(cudaMalloc(&nf, sizeof(uint32_t) * (old_words + bw)));
+        CKC(cudaMemcpyAsync(nf, d_filter, sizeof(uint32_t) * old_words, cudaMemcpyDeviceToDevice, st));
+        CKC(cudaMemsetAsync(nf + old_words, 0, sizeof(uint32_t) * (size_t)bw, st));
+        big_filter_build_kernel<<<1184, 256, 0, st>>>(d_keys, n_slots, nf + old_words, bw);
+        (*launches)++;
+        CKC(cudaStreamSynchronize(st));
+        cudaFree(d_filter);
+        d_filter = nf;
+        big_words = bw;
     }
     CKC(cudaGetLastError());
     CKC(cudaStreamSynchronize(st));

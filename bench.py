@@ -153,39 +153,194 @@ def run_reference(args):
     }))
 
 
-def run_ours(args):
+# ---- workloads (BASELINE.json configs) ---------------------------------------------------
+# alg_bytes: ALGORITHMIC bytes per read = L + 12 + 8*P*[table in HBM]
+WORKLOADS = {
+    "cfg2": dict(cfg=CFG, paired=True, read_len=READ_LEN, alg_bytes=READ_LEN + 4 + 8, kernel="bbduk_fast_kernel",
+                 desc=WORKLOAD, stored=217135),
+    "cfg3": dict(cfg=dict(k=31), paired=False, read_len=READ_LEN, alg_bytes=READ_LEN + 12 + 8 * 120, kernel="bbduk_direct_kernel",
+                 desc="bbduk.sh k=31 (kfilter, mm=t) vs 100 x 1 Mbp synthetic reference (seed 7), synthetic 150 bp SE reads, "
+                      "10 % contaminant with 1 % subs (cfg 3)", ref=(100, 1_000_000, 7)),
+    "cfg4": dict(cfg=dict(k=27, hdist=2), paired=True, read_len=READ_LEN, alg_bytes=READ_LEN + 12 + 8 * 124,
+                 kernel="bbduk_direct_kernel",
+                 desc="bbduk.sh k=27 hdist=2 (kfilter) vs 100 x 1 kbp synthetic reference (seed 9), synthetic 2x150 bp PE as cfg 2 (cfg 4)",
+                 ref=(100, 1000, 9)),
+    "cfg5": dict(paired=False, read_len=READ_LEN, alg_bytes=READ_LEN + 4 + 8 * 120, kernel="kcount_kernel",
+                 desc="kmercountexact.sh k=31, synthetic 150 bp SE reads sampled from a 100 Mbp genome (seed 11), 0.1 % subs (cfg 5)",
+                 genome=100_000_000),
+}
+
+
+def build_engine(wl, rank, local_rank, world, lib, torch):
+    """table built on rank 0 and replicated by NCCL broadcast; returns (engine, stored, d_ref or None)"""
+    from bbtools_b200 import make_cfg
+    from bbtools_b200.bbduk import BBDukIndexGPU
+    cfg = make_cfg(device=local_rank, **wl["cfg"])
+    eng = BBDukIndexGPU(cfg)
+    d_ref = None
+    if "ref" in wl:
+        n_scaf, scaf_len, seed = wl["ref"]
+        d_ref = torch.empty(n_scaf * scaf_len, dtype=torch.uint8, device="cuda")
+        assert lib.bbduk_b200_synth_reference(d_ref.data_ptr(), d_ref.numel(), C.c_uint64(seed), None) == 0
+        torch.cuda.synchronize()
+    stored = 0
+    if rank == 0:
+        if d_ref is None:
+            rb, roff = adapters_ref()
+        else:
+            rb = d_ref.cpu().numpy()
+            roff = np.arange(0, rb.size + 1, wl["ref"][1], dtype=np.int64)
+        eng.add_ref(rb, roff)
+        stored = eng.finalize()
+    if world > 1:
+        stored = eng.broadcast_table(src=0)
+    torch.cuda.synchronize()
+    return eng, stored, d_ref
+
+
+def run_kcount(args, wl):
+    """config 5: a step = counting one batch of reads into the rank-private table; at N>1 the ONE exchange
+    (all_to_all by key owner) runs once after the timed steps and is reported separately"""
     import torch
     import torch.distributed as dist
 
-    from bbtools_b200 import _lib, make_cfg
-    from bbtools_b200.bbduk import BBDukIndexGPU
-
+    from bbtools_b200 import _lib
+    from bbtools_b200.kcount import KmerTableSetGPU, exchange_counts, global_summary
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the BBDuk path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+    L, G = wl["read_len"], wl["genome"]
+    n_reads = 2 * args.pairs_per_step
+    tab = KmerTableSetGPU(31, True, initial_keys=1 << 29, device=local_rank)
+    nbuf = 2
+    bufs = []
+    for b in range(nbuf):
+        d_bases = torch.empty(n_reads * L, dtype=torch.uint8, device=dev)
+        d_off = torch.empty(n_reads + 1, dtype=torch.int32, device=dev)
+        first = (rank * nbuf + b) * n_reads
+        assert lib.kcount_b200_synth_reads(d_bases.data_ptr(), d_off.data_ptr(), n_reads, first, L, G, C.c_uint64(11), 10, None) == 0
+        bufs.append((d_bases, d_off))
+    torch.cuda.synchronize()
+    stream = torch.cuda.Stream(device=dev)
+
+    def step(i):
+        d_bases, d_off = bufs[i % nbuf]
+        tab.add_reads_device(d_bases, d_off, n_reads, n_reads * L, stream=stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = tab.table_info()["launches"]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    with torch.cuda.stream(stream):
+        ev[0].record(stream)
+        for i in range(args.steps):
+            step(args.warmup + i)
+            ev[i + 1].record(stream)
+    barrier()
+    launches = tab.table_info()["launches"] - l0
+    clocks = sampler.stop()
+    total_ms = ev[0].elapsed_time(ev[args.steps])
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms_max = float(tmax.item())
+    value = world * n_reads * args.steps / (total_ms_max * 1e-3)
+    # end to end: host buffers through kcount_b200_add_reads
+    e_reads = 2 * args.e2e_pairs
+    hb = bufs[0][0][: e_reads * L].cpu().numpy()
+    ho = np.arange(0, (e_reads + 1) * L, L, dtype=np.int64)
+    tab.add_reads(hb, ho)
+    barrier()
+    t0 = time.perf_counter()
+    e_steps = 3
+    for _ in range(e_steps):
+        tab.add_reads(hb, ho)
+    torch.cuda.synchronize()
+    e_dt = time.perf_counter() - t0
+    te = torch.tensor([e_dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e_value = world * e_reads * e_steps / float(te.item())
+    exch_ms = None
+    st = tab.stats()
+    if world > 1:
+        barrier()
+        t0 = time.perf_counter()
+        owner = exchange_counts(tab)
+        uniq, _ = global_summary(owner, 1000)
+        barrier()
+        exch_ms = 1e3 * (time.perf_counter() - t0)
+    else:
+        uniq = st["unique_kmers"]
+    if rank == 0:
+        peak, peak_kind = load_peak()
+        kern_ms = total_ms_max / args.steps
+        achieved = n_reads * wl["alg_bytes"] / (kern_ms * 1e-3) / 1e9
+        info = tab.table_info()
+        print(json.dumps({
+            "metric": "kmercount_reads_per_s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": kern_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": {"workload": wl["desc"], "reads_per_step_per_gpu": n_reads, "read_len": L, "unique_kmers": uniq,
+                       "kmers_per_s": value * (L - 30), "table_bytes_per_gpu": info["bytes"], "exchange_ms": exch_ms,
+                       "l2": f"table {info['bytes'] / 2**30:.0f} GiB >> 126 MB L2; inputs {n_reads * L / 2**20:.0f} MiB per step"},
+            "e2e": {"value": e_value, "unit": "reads/s", "h2d_bytes_per_step": int(hb.nbytes + (e_reads + 1) * 4),
+                    "d2h_bytes_per_step": 32, "reads_per_step_per_gpu": e_reads, "steps": e_steps},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_kind, "kernel": wl["kernel"],
+                         "algorithmic_bytes_per_read": wl["alg_bytes"], "ms_per_launch": kern_ms,
+                         "sector_granular_bytes_per_read": L + 4 + 64 * 120},
+        }))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from bbtools_b200 import _lib, make_cfg
+
+    wl = WORKLOADS[args.workload]
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the BBDuk path has no CPU fallback")
+    if args.workload == "cfg5":
+        return run_kcount(args, wl)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    paired = wl["paired"]
+    L = wl["read_len"]
 
     # ---- table: built on rank 0, replicated by NCCL broadcast (no per-read collective afterwards) ----
-    cfg = make_cfg(device=local_rank, **CFG)
-    eng = BBDukIndexGPU(cfg)
     t_build = time.perf_counter()
-    if rank == 0:
-        rb, roff = adapters_ref()
-        eng.add_ref(rb, roff)
-        stored = eng.finalize()
-    if world > 1:
-        stored = eng.broadcast_table(src=0)
-    torch.cuda.synchronize()
+    eng, stored, d_ref = build_engine(wl, rank, local_rank, world, lib, torch)
     t_build = time.perf_counter() - t_build
-    assert stored == 217135, stored
-    eng.set_max_read_len(READ_LEN)
+    if "stored" in wl:
+        assert stored == wl["stored"], stored
+    eng.set_max_read_len(L)
 
     # ---- HBM-resident batches from the device generator (distinct per rank and per buffer) ----------
     n_pairs = args.pairs_per_step
@@ -193,10 +348,15 @@ def run_ours(args):
     nbuf = 2
     bufs = []
     for b in range(nbuf):
-        d_bases = torch.empty(n_reads * READ_LEN, dtype=torch.uint8, device=dev)
+        d_bases = torch.empty(n_reads * L, dtype=torch.uint8, device=dev)
         d_off = torch.empty(n_reads + 1, dtype=torch.int32, device=dev)
-        first = (rank * nbuf + b) * n_pairs
-        rc = lib.bbduk_b200_synth_pairs(d_bases.data_ptr(), d_off.data_ptr(), n_pairs, first, READ_LEN, C.c_uint64(1), 50, 5, None)
+        if args.workload == "cfg3":
+            first = (rank * nbuf + b) * n_reads
+            rc = lib.bbduk_b200_synth_contam(d_bases.data_ptr(), d_off.data_ptr(), n_reads, first, L, d_ref.data_ptr(),
+                                             d_ref.numel(), C.c_uint64(1), 10, 100, 5, None)
+        else:
+            first = (rank * nbuf + b) * n_pairs
+            rc = lib.bbduk_b200_synth_pairs(d_bases.data_ptr(), d_off.data_ptr(), n_pairs, first, L, C.c_uint64(1), 50, 5, None)
         assert rc == 0
         bufs.append((d_bases, d_off))
     outs = {"id0": torch.empty(n_reads, dtype=torch.int32, device=dev),
@@ -209,7 +369,7 @@ def run_ours(args):
 
     def step(i):
         d_bases, d_off = bufs[i % nbuf]
-        eng.process_device(d_bases, d_off, n_reads, True, outs, d_stats=d_stats, stream=stream.cuda_stream)
+        eng.process_device(d_bases, d_off, n_reads, paired, outs, d_stats=d_stats, stream=stream.cuda_stream)
 
     def barrier():
         if world > 1:
@@ -242,9 +402,9 @@ def run_ours(args):
     # ---- end to end through the C ABI with pinned host buffers ------------------------------------
     e_pairs = args.e2e_pairs
     e_reads = 2 * e_pairs
-    h_bases = torch.empty(e_reads * READ_LEN, dtype=torch.uint8, pin_memory=True)
-    h_bases.copy_(bufs[0][0][: e_reads * READ_LEN])
-    h_off = torch.arange(0, (e_reads + 1) * READ_LEN, READ_LEN, dtype=torch.int64).pin_memory()
+    h_bases = torch.empty(e_reads * L, dtype=torch.uint8, pin_memory=True)
+    h_bases.copy_(bufs[0][0][: e_reads * L])
+    h_off = torch.arange(0, (e_reads + 1) * L, L, dtype=torch.int64).pin_memory()
     from bbtools_b200._abi import Outputs
     hout = Outputs(0)
     hout.n = e_reads
@@ -258,11 +418,11 @@ def run_ours(args):
     d2h = int(sum(pinned[k].numpy().nbytes for k in pinned))
     e_steps = max(2, min(args.steps, 8))
     for _ in range(2):
-        eng.process(hb, ho, True, out=hout)
+        eng.process(hb, ho, paired, out=hout)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e_steps):
-        _, est = eng.process(hb, ho, True, out=hout)
+        _, est = eng.process(hb, ho, paired, out=hout)
     torch.cuda.synchronize()
     e_dt = time.perf_counter() - t0
     te = torch.tensor([e_dt], dtype=torch.float64, device=dev)
@@ -272,18 +432,23 @@ def run_ours(args):
 
     # ---- sanity: the timed batch agrees with the CPU oracle on a slice (checker only) -----------------
     parity = None
-    if rank == 0:
-        from bbtools_b200 import synth
+    if rank == 0 and (args.workload == "cfg2" or args.verify):
         from oracle.oracle import Oracle
         chk = 20000
-        o = Oracle(make_cfg(**CFG))
-        rb, roff = adapters_ref()
+        o = Oracle(make_cfg(**wl["cfg"]))
+        if d_ref is None:
+            rb, roff = adapters_ref()
+        else:
+            rb = d_ref.cpu().numpy()
+            roff = np.arange(0, rb.size + 1, wl["ref"][1], dtype=np.int64)
         o.add_ref(rb, roff)
         o.finalize()
-        hb2, ho2 = synth.paired_adapter_reads(chk, first_pair=(args.warmup + args.steps - 1) % nbuf * n_pairs, seed=1)
-        want, _ = o.process(hb2, ho2, True, threads=min(8, os.cpu_count() or 1))
         step(args.warmup + args.steps - 1)
         torch.cuda.synchronize()
+        db, _ = bufs[(args.warmup + args.steps - 1) % nbuf]
+        hb2 = db[: 2 * chk * L].cpu().numpy()  # the device generators are tested against synth.py byte for byte
+        ho2 = np.arange(0, (2 * chk + 1) * L, L, dtype=np.int64)
+        want, _ = o.process(hb2, ho2, paired, threads=min(8, os.cpu_count() or 1))
         parity = bool(np.array_equal(outs["hi"][: 2 * chk].cpu().numpy(), want.hi) and
                       np.array_equal(outs["id0"][: 2 * chk].cpu().numpy(), want.id0) and
                       np.array_equal(outs["flags"][: 2 * chk].cpu().numpy(), want.flags))
@@ -291,22 +456,21 @@ def run_ours(args):
     if rank == 0:
         peak, peak_kind = load_peak()
         kern_ms = statistics.mean(step_ms)
-        achieved = n_reads * ALG_BYTES_PER_READ / (kern_ms * 1e-3) / 1e9
+        achieved = n_reads * wl["alg_bytes"] / (kern_ms * 1e-3) / 1e9
         cores = os.cpu_count() or 1
         cpu_pairs = args.cpu_pairs
         cpu_rate = None
-        if world == 1 and cpu_pairs > 0:
+        if world == 1 and cpu_pairs > 0 and args.workload == "cfg2":
             # the sample is the head of the timed workload, copied back from the device generator
-            from bbtools_b200 import make_cfg as _mk
             from oracle.oracle import Oracle as _Or
             cpu_pairs = min(cpu_pairs, n_pairs)
-            cb = bufs[0][0][: 2 * cpu_pairs * READ_LEN].cpu().numpy()
-            co = np.arange(0, (2 * cpu_pairs + 1) * READ_LEN, READ_LEN, dtype=np.int64)
-            oo = _Or(_mk(**CFG))
+            cb = bufs[0][0][: 2 * cpu_pairs * L].cpu().numpy()
+            co = np.arange(0, (2 * cpu_pairs + 1) * L, L, dtype=np.int64)
+            oo = _Or(make_cfg(**wl["cfg"]))
             rb, roff = adapters_ref()
             oo.add_ref(rb, roff)
             oo.finalize()
-            oo.process(cb[: 4000 * READ_LEN], co[:4001], True, threads=cores)
+            oo.process(cb[: 4000 * L], co[:4001], True, threads=cores)
             t0 = time.perf_counter()
             oo.process(cb, co, True, threads=cores)
             cpu_rate = 2 * cpu_pairs / (time.perf_counter() - t0)
@@ -314,8 +478,8 @@ def run_ours(args):
             "metric": "bbduk_reads_per_s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": n_pairs, "read_len": READ_LEN,
-                       "stored_kmers": stored, "l2": f"inputs {n_reads * READ_LEN / 2**20:.0f} MiB per step > 126 MB L2, "
+            "config": {"workload": wl["desc"], "pairs_per_step_per_gpu": n_pairs, "read_len": L,
+                       "stored_kmers": stored, "l2": f"inputs {n_reads * L / 2**20:.0f} MiB per step > 126 MB L2, "
                        f"{nbuf} alternating buffers, no flush", "table_build_s": round(t_build, 3),
                        "parity_vs_oracle_on_timed_batch": parity},
             "e2e": {"value": e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -323,9 +487,14 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_kind, "kernel": "bbduk_fast_kernel",
-                         "algorithmic_bytes_per_read": ALG_BYTES_PER_READ, "ms_per_launch": kern_ms},
+                         "traffic": None, "peak_source": peak_kind, "kernel": wl["kernel"],
+                         "algorithmic_bytes_per_read": wl["alg_bytes"], "ms_per_launch": kern_ms},
         }
+        if args.workload in ("cfg3", "cfg4"):
+            # DRAM cannot fetch less than a 32-byte sector per probe: the sector-granular variant of SURVEY.md 8d
+            sect = L + 12 + 32 * (wl["alg_bytes"] - L - 12) // 8
+            line["roofline"]["sector_granular_bytes_per_read"] = sect
+            line["roofline"]["sector_granular_frac"] = n_reads * sect / (kern_ms * 1e-3) / 1e9 / peak
         if cpu_rate is not None:
             line["cpu_baseline"] = {"value": cpu_rate, "unit": "reads/s", "cores": cores, "kind": "port",
                                     "sample": f"{2 * cpu_pairs} reads of the same synthetic workload (seed 1), oracle C port, "
@@ -346,6 +515,9 @@ def main():
     ap.add_argument("--e2e-pairs", type=int, default=2 << 20, help="pairs per GPU per end-to-end step (host buffers)")
     ap.add_argument("--cpu-pairs", type=int, default=4 << 20, help="pairs of the cpu_baseline sample (0 = skip)")
     ap.add_argument("--ref-pairs", type=int, default=1 << 19, help="pairs per step of --impl reference")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS),
+                    help="cfg2 = the headline line (default); cfg3/cfg4 = HBM-resident tables; cfg5 = kmercountexact")
+    ap.add_argument("--verify", action="store_true", help="cfg3/cfg4: also build the CPU oracle's table and check a slice")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

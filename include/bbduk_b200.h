@@ -215,6 +215,14 @@ BBDUK_API int bbduk_b200_synth_pairs(uint8_t *d_bases, uint32_t *d_offsets, int6
                                      int32_t read_len, uint64_t seed, int32_t sub_per_10k, int32_t n_per_10k,
                                      void *stream);
 
+/* Bench/test helpers for the cfg-3 / cfg-4 workloads: a uniform-ACGT reference (synth.py:random_reference, one
+ * byte per base into a DEVICE buffer) and SE reads of which contam_pct % are copied from that reference
+ * (synth.py:contaminant_reads). */
+BBDUK_API int bbduk_b200_synth_reference(uint8_t *d_out, int64_t n, uint64_t seed, void *stream);
+BBDUK_API int bbduk_b200_synth_contam(uint8_t *d_bases, uint32_t *d_offsets, int64_t n_reads, int64_t first_read,
+                                      int32_t read_len, const uint8_t *d_ref, int64_t ref_len, uint64_t seed,
+                                      int32_t contam_pct, int32_t sub_per_10k, int32_t n_per_10k, void *stream);
+
 BBDUK_API const char *bbduk_b200_last_error(bbduk_handle *h);
 BBDUK_API void bbduk_b200_destroy(bbduk_handle *h);
 
