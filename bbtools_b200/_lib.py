@@ -29,6 +29,7 @@ SYMBOLS = [
     ("bbduk_b200_destroy", None, [C.c_void_p]),
     ("bbduk_b200_synth_pairs", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_uint64,
                                          C.c_int32, C.c_int32, C.c_void_p]),
+    ("bbduk_b200_pack_bases", C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     ("bbduk_b200_synth_reference", C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]),
     ("bbduk_b200_synth_contam", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64,
                                           C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),

@@ -2,13 +2,16 @@
 // host-buffer batching (pinned staging, two streams so copies overlap kernels) and kernel dispatch.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
 #include <vector>
 
 #include "../../include/bbduk_b200.h"
+#include "hostpack.h"
 #include "params.h"
 #include "probe.h"
 #include "table.h"
@@ -36,6 +39,11 @@ struct Slot {
     unsigned long long *d_first64 = nullptr;
     int *d_lastpos = nullptr;
     uint16_t *d_sbits = nullptr;
+    // host-packed transfer (hostpack.h): pinned staging + device copies of the 2-bit stream F and defined bits D
+    uint32_t *h_F = nullptr, *d_F = nullptr;
+    uint16_t *h_D = nullptr, *d_D = nullptr;
+    uint32_t *h_off32 = nullptr;
+    int64_t cap_groups = 0, cap_hoff = 0;
     int64_t cap_bases = 0, cap_reads = 0, cap_maskwords = 0, cap_sbits = 0;
     std::mutex mu;
 };
@@ -57,6 +65,8 @@ struct bbduk_handle {
     std::atomic<int> next_slot{0};
     std::atomic<int64_t> launches{0};
     std::atomic<int> max_read_len_hint{0};
+    bool trace = false;     // BBDUK_B200_TRACE=1: per-chunk host timings on stderr
+    bool pack_host = true;  // BBDUK_B200_PACK_HOST=0 keeps the bases ASCII across PCIe
     std::mutex err_mu;
     std::string err;
     // per-thread-stream scratch for process_device
@@ -67,6 +77,8 @@ struct bbduk_handle {
     int *dev_lastpos = nullptr;
     uint16_t *dev_sbits = nullptr;
     int64_t dev_sbits_cap = 0, dev_first_cap = 0;
+    HostPool *pool = nullptr;  // host packing workers, created on first use
+    std::mutex pool_mu;
     std::mutex dev_mu;
 };
 
@@ -126,6 +138,14 @@ void free_slot(Slot &s) {
     cudaFree(s.d_first64);
     cudaFree(s.d_lastpos);
     cudaFree(s.d_sbits);
+    cudaFree(s.d_F);
+    cudaFree(s.d_D);
+    cudaFreeHost(s.h_F);
+    cudaFreeHost(s.h_D);
+    cudaFreeHost(s.h_off32);
+    s.d_F = s.h_F = s.h_off32 = nullptr;
+    s.d_D = s.h_D = nullptr;
+    s.cap_groups = s.cap_hoff = 0;
     s.d_first64 = nullptr;
     s.d_lastpos = nullptr;
     s.d_sbits = nullptr;
@@ -196,6 +216,30 @@ int ensure_slot(bbduk_handle *h, Slot &s, int64_t n_reads, int64_t n_bases, int6
     return 0;
 }
 
+int ensure_packed(bbduk_handle *h, Slot &s, int64_t n_reads, int64_t n_bases) {
+    const int64_t groups = (n_bases + 15) / 16 + 8;
+    if (groups > s.cap_groups) {
+        cudaFree(s.d_F);
+        cudaFree(s.d_D);
+        cudaFreeHost(s.h_F);
+        cudaFreeHost(s.h_D);
+        s.d_F = s.h_F = nullptr;
+        s.d_D = s.h_D = nullptr;
+        s.cap_groups = groups + groups / 8 + 1024;
+        CKH(cudaMalloc(&s.d_F, sizeof(uint32_t) * s.cap_groups));
+        CKH(cudaMalloc(&s.d_D, sizeof(uint16_t) * s.cap_groups));
+        CKH(cudaHostAlloc(&s.h_F, sizeof(uint32_t) * s.cap_groups, cudaHostAllocDefault));
+        CKH(cudaHostAlloc(&s.h_D, sizeof(uint16_t) * s.cap_groups, cudaHostAllocDefault));
+    }
+    if (n_reads + 1 > s.cap_hoff) {
+        cudaFreeHost(s.h_off32);
+        s.h_off32 = nullptr;
+        s.cap_hoff = n_reads + n_reads / 8 + 1024;
+        CKH(cudaHostAlloc(&s.h_off32, sizeof(uint32_t) * s.cap_hoff, cudaHostAllocDefault));
+    }
+    return 0;
+}
+
 // dispatch one device-resident batch: fast kernel where it applies, generic kernel for the rest
 struct DirectScratch {
     unsigned long long *first64;
@@ -211,7 +255,8 @@ bool uses_direct(const bbduk_handle *h, int max_read_len) {
 
 int run_batch(bbduk_handle *h, const uint8_t *d_bases, const uint32_t *d_off, int64_t n_reads, int64_t n_bases, int paired,
               const bbduk_out &dout, bbduk_stats *d_stats, int max_read_len, int32_t *d_handoff,
-              unsigned int *d_handoff_n, const DirectScratch &ds, cudaStream_t st) {
+              unsigned int *d_handoff_n, const DirectScratch &ds, cudaStream_t st, const uint32_t *pk_F = nullptr,
+              const uint16_t *pk_D = nullptr) {
     if (n_reads <= 0) return 0;
     const BBTable t = h->table.view();
     const int64_t n_units = paired ? n_reads / 2 : n_reads;
@@ -219,9 +264,10 @@ int run_batch(bbduk_handle *h, const uint8_t *d_bases, const uint32_t *d_off, in
     if (plan.usable && d_handoff) {
         CKH(cudaMemsetAsync(d_handoff_n, 0, sizeof(unsigned int), st));
         const int nl = launch_fast(plan, d_bases, d_off, n_reads, paired, h->p, t, dout, d_stats, h->d_scaf_reads,
-                                   h->d_scaf_bases, d_handoff, d_handoff_n, h->sm_count, st);
+                                   h->d_scaf_bases, d_handoff, d_handoff_n, h->sm_count, st, pk_F, pk_D);
         if (nl < 0) return set_err(h, std::string("fast kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
         h->launches += nl;
+        if (pk_F) return 0;  // packed batches are sized so that no tile is handed off
         // hand-offs (tiles that do not fit the staging): count stays on the device, no host sync
         if (launch_generic(d_bases, d_off, n_units, paired, d_handoff, d_handoff_n, h->p, t, dout, d_stats, h->d_scaf_reads,
                            h->d_scaf_bases, h->sm_count, st))
@@ -324,6 +370,8 @@ int bbduk_b200_create(const bbduk_cfg *cfg, bbduk_handle **out) {
     }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
+    if (const char *e = getenv("BBDUK_B200_PACK_HOST")) h->pack_host = atoi(e) != 0;
+    if (const char *e = getenv("BBDUK_B200_TRACE")) h->trace = atoi(e) != 0;
     *out = h;
     return 0;
 }
@@ -497,6 +545,7 @@ int bbduk_b200_process(bbduk_handle *h, const uint8_t *bases, const int64_t *off
     if (check_mode_inputs(h, paired, out)) return 1;
     if (stats) memset(stats, 0, sizeof *stats);
     if (n_reads == 0) return 0;
+    const auto t_call0 = std::chrono::steady_clock::now();
     CKH(cudaSetDevice(h->device));
     const bool want_mask = h->p.mode == MODE_KMASK && out->maskbits && out->mask_off;
 
@@ -523,18 +572,42 @@ int bbduk_b200_process(bbduk_handle *h, const uint8_t *bases, const int64_t *off
         const int64_t mw0 = want_mask ? out->mask_off[r0] : 0, mw = want_mask ? out->mask_off[r1] - mw0 : 0;
         Slot &s = h->slots[h->next_slot++ % N_SLOTS];
         std::lock_guard<std::mutex> g(s.mu);
+        const auto t_wait0 = std::chrono::steady_clock::now();
         if (s.done) cudaEventSynchronize(s.done);  // previous use of this slot has drained
+        if (h->trace)
+            fprintf(stderr, "[bbduk_b200] slot wait %.3f ms\n",
+                    1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_wait0).count());
         const bool direct = uses_direct(h, 1 << 20);  // conservative: decided again per chunk in run_batch
         if ((rc = ensure_slot(h, s, nr, nb, mw, direct))) break;
-        // longest read of the chunk (host side, one pass over the offsets that are being copied anyway)
+        // longest read of the chunk: one pass over the offsets, shared among the host workers
         int max_len = 0;
-        for (int64_t i = r0; i < r1; i++) {
-            const int64_t l = offsets[i + 1] - offsets[i];
-            if (l < 0 || l > 0x7FFFFFFF) {
-                rc = set_err(h, "bad read length");
-                break;
+        {
+            std::lock_guard<std::mutex> pg(h->pool_mu);
+            if (!h->pool) {
+                // one process per GPU: share the host cores among the ranks of this node (torchrun exports the count)
+                int share = 1;
+                if (const char *e = getenv("LOCAL_WORLD_SIZE")) share = std::max(1, atoi(e));
+                if (const char *e = getenv("BBDUK_B200_HOST_THREADS")) share = -atoi(e);
+                const int hc = (int)std::thread::hardware_concurrency();
+                h->pool = new HostPool(share < 0 ? std::max(1, -share) : std::max(1, std::min(32, hc / share)));
             }
-            if (l > max_len) max_len = (int)l;
+            std::atomic<int> mx{0};
+            std::atomic<bool> bad{false};
+            const int64_t *osrc = offsets + r0;
+            h->pool->run([&](int part, int n_parts) {
+                const int64_t i0 = nr * part / n_parts, i1 = nr * (part + 1) / n_parts;
+                int64_t m = 0;
+                for (int64_t i = i0; i < i1; i++) {
+                    const int64_t l = osrc[i + 1] - osrc[i];
+                    if (l < 0 || l > 0x7FFFFFFF) bad = true;
+                    if (l > m) m = l;
+                }
+                int cur = mx.load();
+                while ((int)std::min<int64_t>(m, 0x7FFFFFFF) > cur && !mx.compare_exchange_weak(cur, (int)std::min<int64_t>(m, 0x7FFFFFFF))) {
+                }
+            });
+            if (bad) rc = set_err(h, "bad read length");
+            max_len = mx.load();
         }
         if (rc) break;
         cudaStream_t st = s.st;
@@ -547,11 +620,41 @@ int bbduk_b200_process(bbduk_handle *h, const uint8_t *bases, const int64_t *off
             rc = set_err(h, b_);                                                                           \
         }                                                                                                  \
     }
-        CKL(cudaMemcpyAsync(s.d_bases, bases + offsets[r0], (size_t)nb, cudaMemcpyHostToDevice, st));
-        CKL(cudaMemcpyAsync(s.d_off64, offsets + r0, sizeof(int64_t) * (nr + 1), cudaMemcpyHostToDevice, st));
-        if (!rc) {
-            off64_to_32_kernel<<<(unsigned)((nr + 1 + 255) / 256), 256, 0, st>>>(s.d_off64, offsets[r0], s.d_off32, nr + 1);
-            h->launches += 1;
+        // PCIe leg: when the tuned kernel takes the whole chunk, the bases cross as 2-bit codes + defined bits
+        // (0.375 B/base instead of 1) packed by the host workers, and the offsets as 32-bit words
+        bool packed = false;
+        {
+            const BBTable tv = h->table.view();
+            packed = h->pack_host && !want_mask && max_len <= FAST_MAX_READ_LEN && nb >= (1 << 16) &&
+                     plan_fast(h->p, tv, max_len).usable && packed_ok(h->p, tv);
+        }
+        if (packed && !rc) rc = ensure_packed(h, s, nr, nb);
+        if (packed && !rc) {
+            std::lock_guard<std::mutex> pg(h->pool_mu);
+            const uint8_t *src = bases + offsets[r0];
+            const int64_t *osrc = offsets + r0;
+            const int64_t groups = (nb + 15) / 16;
+            Slot *sp = &s;
+            const auto t_pack0 = std::chrono::steady_clock::now();
+            h->pool->run([=](int part, int n_parts) {
+                const int64_t g0 = groups * part / n_parts, g1 = groups * (part + 1) / n_parts;
+                pack_bases_range(src, nb, g0, g1, sp->h_F, sp->h_D);
+                const int64_t i0 = (nr + 1) * part / n_parts, i1 = (nr + 1) * (part + 1) / n_parts;
+                for (int64_t i = i0; i < i1; i++) sp->h_off32[i] = (uint32_t)(osrc[i] - osrc[0]);
+            });
+            if (h->trace)
+                fprintf(stderr, "[bbduk_b200] packed %lld bases in %.3f ms on %d threads\n", (long long)nb,
+                        1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_pack0).count(), h->pool->size());
+            CKL(cudaMemcpyAsync(s.d_F, s.h_F, sizeof(uint32_t) * groups, cudaMemcpyHostToDevice, st));
+            CKL(cudaMemcpyAsync(s.d_D, s.h_D, sizeof(uint16_t) * groups, cudaMemcpyHostToDevice, st));
+            CKL(cudaMemcpyAsync(s.d_off32, s.h_off32, sizeof(uint32_t) * (nr + 1), cudaMemcpyHostToDevice, st));
+        } else {
+            CKL(cudaMemcpyAsync(s.d_bases, bases + offsets[r0], (size_t)nb, cudaMemcpyHostToDevice, st));
+            CKL(cudaMemcpyAsync(s.d_off64, offsets + r0, sizeof(int64_t) * (nr + 1), cudaMemcpyHostToDevice, st));
+            if (!rc) {
+                off64_to_32_kernel<<<(unsigned)((nr + 1 + 255) / 256), 256, 0, st>>>(s.d_off64, offsets[r0], s.d_off32, nr + 1);
+                h->launches += 1;
+            }
         }
         bbduk_out dout;
         memset(&dout, 0, sizeof dout);
@@ -572,7 +675,8 @@ int bbduk_b200_process(bbduk_handle *h, const uint8_t *bases, const int64_t *off
         }
         if (!rc)
             rc = run_batch(h, s.d_bases, s.d_off32, nr, nb, paired, dout, d_stats, max_len, s.d_handoff, s.d_handoff_n,
-                           DirectScratch{s.d_first64, s.d_lastpos, s.d_sbits}, st);
+                           DirectScratch{s.d_first64, s.d_lastpos, s.d_sbits}, st, packed ? s.d_F : nullptr,
+                           packed ? s.d_D : nullptr);
         if (out->id0) CKL(cudaMemcpyAsync(out->id0 + r0, s.d_id0, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, st));
         if (out->id0b) CKL(cudaMemcpyAsync(out->id0b + r0, s.d_id0b, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, st));
         if (out->lo) CKL(cudaMemcpyAsync(out->lo + r0, s.d_lo, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, st));
@@ -586,7 +690,12 @@ int bbduk_b200_process(bbduk_handle *h, const uint8_t *bases, const int64_t *off
         used.push_back(&s);
         r0 = r1;
     }
+    const auto t_sync0 = std::chrono::steady_clock::now();
     for (Slot *s : used) cudaStreamSynchronize(s->st);
+    if (h->trace)
+        fprintf(stderr, "[bbduk_b200] process: enqueue %.3f ms, final sync %.3f ms\n",
+                1e3 * std::chrono::duration<double>(t_sync0 - t_call0).count(),
+                1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_sync0).count());
     if (!rc && stats) {
         if (cudaMemcpy(stats, d_stats, sizeof *stats, cudaMemcpyDeviceToHost) != cudaSuccess) rc = set_err(h, "stats copy failed");
     }
@@ -616,6 +725,12 @@ int bbduk_b200_set_max_read_len(bbduk_handle *h, int32_t max_read_len) {
     return 0;
 }
 
+int bbduk_b200_pack_bases(const uint8_t *bases, int64_t n, uint32_t *F, uint16_t *D) {
+    if (n < 0 || (n > 0 && (!bases || !F || !D))) return set_err(nullptr, "bad pack_bases arguments");
+    pack_bases(bases, n, F, D);
+    return 0;
+}
+
 int64_t bbduk_b200_launch_count(bbduk_handle *h) { return h ? h->launches.load() : 0; }
 
 void bbduk_b200_destroy(bbduk_handle *h) {
@@ -636,6 +751,7 @@ void bbduk_b200_destroy(bbduk_handle *h) {
     cudaFree(h->dev_first64);
     cudaFree(h->dev_lastpos);
     cudaFree(h->dev_sbits);
+    delete h->pool;
     delete h;
 }
 

@@ -1,0 +1,139 @@
+// hostpack.cpp -- see hostpack.h. AVX2 path selected at run time on x86-64; portable scalar path otherwise.
+#include "hostpack.h"
+
+#include <cstring>
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
+namespace {
+
+struct Tables {
+    uint8_t code[256], valid[256];
+    Tables() {
+        memset(code, 0, sizeof code);
+        memset(valid, 0, sizeof valid);
+        const char *s = "ACGT";
+        for (int i = 0; i < 4; i++) {
+            code[(uint8_t)s[i]] = code[(uint8_t)(s[i] | 0x20)] = (uint8_t)i;
+            valid[(uint8_t)s[i]] = valid[(uint8_t)(s[i] | 0x20)] = 1;
+        }
+        code['U'] = code['u'] = 3;
+        valid['U'] = valid['u'] = 1;
+    }
+};
+const Tables g_tab;
+
+void pack_scalar(const uint8_t *b, int64_t n, int64_t g0, int64_t g1, uint32_t *F, uint16_t *D) {
+    for (int64_t g = g0; g < g1; g++) {
+        uint32_t f = 0, d = 0;
+        const int64_t base = g * 16;
+        const int m = (int)((n - base) < 16 ? (n - base) : 16);
+        for (int j = 0; j < m; j++) {
+            const uint8_t c = b[base + j];
+            f |= (uint32_t)g_tab.code[c] << (30 - 2 * j);
+            d |= (uint32_t)g_tab.valid[c] << (15 - j);
+        }
+        // undefined bases keep code 0 (code[] is 0 for them already)
+        F[g] = f;
+        D[g] = (uint16_t)d;
+    }
+}
+
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) void pack_avx2(const uint8_t *b, int64_t n, int64_t g0, int64_t g1, uint32_t *F, uint16_t *D) {
+    const __m256i three = _mm256_set1_epi8(3);
+    const __m256i lower = _mm256_set1_epi8(0x20);
+    const __m256i lut = _mm256_setr_epi8((char)0xFF, 0x61, (char)0xFF, 0x63, 0x74, 0x75, (char)0xFF, 0x67, (char)0xFF, (char)0xFF, (char)0xFF,
+                                         (char)0xFF, (char)0xFF, (char)0xFF, (char)0xFF, (char)0xFF, (char)0xFF, 0x61, (char)0xFF, 0x63, 0x74,
+                                         0x75, (char)0xFF, 0x67, (char)0xFF, (char)0xFF, (char)0xFF, (char)0xFF, (char)0xFF, (char)0xFF,
+                                         (char)0xFF, (char)0xFF);
+    const __m256i m41 = _mm256_set1_epi16(0x0104);      // bytes (4,1): 4*c0 + c1
+    const __m256i m161 = _mm256_set1_epi32(0x00010010);  // words (16,1): 16*x0 + x1
+    const __m256i gather = _mm256_setr_epi8(12, 8, 4, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 12, 8, 4, 0, -1, -1, -1, -1,
+                                            -1, -1, -1, -1, -1, -1, -1, -1);
+    const __m256i rev = _mm256_setr_epi8(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4,
+                                         3, 2, 1, 0);
+    int64_t g = g0;
+    const int64_t full = n / 16;  // groups whose 16 bytes are all inside the batch
+    for (; g + 1 < g1 && g + 1 < full; g += 2) {
+        const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(b + g * 16));
+        // codes = ((c>>1) ^ (c>>2)) & 3 per byte (bits shifted in from the neighbour byte are masked away)
+        __m256i c = _mm256_and_si256(_mm256_xor_si256(_mm256_srli_epi16(v, 1), _mm256_srli_epi16(v, 2)), three);
+        // defined <=> (c|0x20) is one of a c g t u and c < 128 (pshufb zeroes lanes whose index has bit 7 set)
+        const __m256i y = _mm256_or_si256(v, lower);
+        const __m256i ok = _mm256_cmpeq_epi8(_mm256_shuffle_epi8(lut, y), y);
+        c = _mm256_and_si256(c, ok);  // undefined -> code 0
+        const __m256i p4 = _mm256_madd_epi16(_mm256_maddubs_epi16(c, m41), m161);  // one byte per 4 bases in each dword
+        const __m256i w = _mm256_shuffle_epi8(p4, gather);
+        F[g] = (uint32_t)_mm256_extract_epi32(w, 0);
+        F[g + 1] = (uint32_t)_mm256_extract_epi32(w, 4);
+        const uint32_t mk = (uint32_t)_mm256_movemask_epi8(_mm256_shuffle_epi8(ok, rev));  // bit 15-b = base b, per half
+        D[g] = (uint16_t)mk;
+        D[g + 1] = (uint16_t)(mk >> 16);
+    }
+    if (g < g1) pack_scalar(b, n, g, g1, F, D);
+}
+#endif
+
+}  // namespace
+
+void pack_bases_range(const uint8_t *bases, int64_t n, int64_t g0, int64_t g1, uint32_t *F, uint16_t *D) {
+#if defined(__x86_64__)
+    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    if (have_avx2) {
+        pack_avx2(bases, n, g0, g1, F, D);
+        return;
+    }
+#endif
+    pack_scalar(bases, n, g0, g1, F, D);
+}
+
+void pack_bases(const uint8_t *bases, int64_t n, uint32_t *F, uint16_t *D) { pack_bases_range(bases, n, 0, (n + 15) / 16, F, D); }
+
+HostPool::HostPool(int n_threads) {
+    for (int i = 1; i < n_threads; i++) workers.emplace_back([this, i] { loop(i); });
+}
+
+HostPool::~HostPool() {
+    {
+        std::lock_guard<std::mutex> g(mu);
+        stop = true;
+        epoch++;
+    }
+    cv_go.notify_all();
+    for (auto &t : workers) t.join();
+}
+
+void HostPool::loop(int idx) {
+    uint64_t seen = 0;
+    while (true) {
+        const std::function<void(int, int)> *fn = nullptr;
+        {
+            std::unique_lock<std::mutex> g(mu);
+            cv_go.wait(g, [&] { return epoch != seen; });
+            seen = epoch;
+            if (stop) return;
+            fn = job;
+        }
+        (*fn)(idx, size());
+        {
+            std::lock_guard<std::mutex> g(mu);
+            if (--pending == 0) cv_done.notify_all();
+        }
+    }
+}
+
+void HostPool::run(const std::function<void(int, int)> &fn) {
+    {
+        std::lock_guard<std::mutex> g(mu);
+        job = &fn;
+        pending = (int)workers.size();
+        epoch++;
+    }
+    cv_go.notify_all();
+    fn(0, size());
+    std::unique_lock<std::mutex> g(mu);
+    cv_done.wait(g, [&] { return pending == 0; });
+}

@@ -22,6 +22,7 @@
 //      result stores, warp-aggregated counters.
 // Rolling-state semantics follow jgi/BBDuk.java:3882-3900 in the closed form of SURVEY.md A.2.
 #include <algorithm>
+#include <cstdlib>
 
 #include "bbduk_dev.cuh"
 #include "probe.h"
@@ -44,6 +45,7 @@ struct FastGeom {
     uint32_t nfw;     // words of the main on-chip filter (canonical bloom, or the part filter)
     uint32_t nsw;     // words of the short-key bloom that follows it (part-filter kernels only)
     uint32_t src_off; // word offset of the main filter inside BBTable::filter
+    int cand_cap;     // candidates a read without undefined bases may release between two full drains
 };
 
 __device__ __forceinline__ uint32_t pair_reverse_complement(uint32_t x) {
@@ -171,12 +173,15 @@ enum { FM_KTRIM_R = 0, FM_KTRIM_L = 1, FM_KFILTER = 2 };
 // position, the hdist+1 parts of a window being the same lookup at different lags.
 // PRE = the first/last full-length hits of every read were already found by probe_direct.cu (pre_first /
 // pre_last): stages A-C compile away and only the per-read epilogue (stage D) runs.
-template <int FMODE, bool RCOMP, bool K16, bool PARTS, bool PRE = false>
+// PACKED = the host already converted the batch (hostpack.cpp): stage A copies the F / D words of the tile
+// instead of classifying ASCII (pk_F[i], pk_D[i] = bases 16i..16i+15 of the batch; `bases` is unused).
+template <int FMODE, bool RCOMP, bool K16, bool PARTS, bool PRE = false, bool PACKED = false>
 __global__ void __launch_bounds__(1024, 1)
 bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ offsets, int64_t n_reads, int paired,
                   BBParams p, BBTable t, bbduk_out out, bbduk_stats *stats, unsigned long long *scaf_reads,
                   unsigned long long *scaf_bases, int32_t *handoff, unsigned int *handoff_n, FastGeom geo,
-                  const unsigned long long *__restrict__ pre_first = nullptr, const int *__restrict__ pre_last = nullptr) {
+                  const unsigned long long *__restrict__ pre_first, const int *__restrict__ pre_last,
+                  const uint32_t *__restrict__ pk_F, const uint16_t *__restrict__ pk_D) {
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t *filt = smem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -205,7 +210,7 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
     const uint32_t km_hi = (uint32_t)(p.kmask >> 32), km_lo = (uint32_t)p.kmask;
     const int psh0 = 32 - t.part_lag[0], psh1 = 32 - t.part_lag[1], psh2 = 32 - t.part_lag[2],
               psh3 = 32 - t.part_lag[t.n_parts > 3 ? 3 : 2];
-    const uintptr_t base_addr = reinterpret_cast<uintptr_t>(bases);
+    const uintptr_t base_addr = PACKED ? (uintptr_t)0 : reinterpret_cast<uintptr_t>(bases);
     const int64_t n_tiles = (n_reads + 31) >> 5;
     const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
     long long s_rk = 0, s_bk = 0, s_rf = 0, s_bf = 0, s_ro = 0, s_bo = 0, s_ri = 0, s_bi = 0;
@@ -234,7 +239,13 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
         __syncwarp();
         for (int c = lane; c < (PRE ? 0 : nchunks + TAIL); c += 32) {
             uint32_t f = 0, dbits = 0;
-            if (c < nchunks) {
+            if (PACKED) {
+                if (c < nchunks) {
+                    f = __ldg(pk_F + (a0 >> 4) + c);
+                    dbits = __ldg(pk_D + (a0 >> 4) + c);
+                    if (dbits != 0xFFFFu) atomicOr(badw + (c >> 5), 1u << (c & 31));
+                }
+            } else if (c < nchunks) {
                 const uint4 v = __ldg(reinterpret_cast<const uint4 *>(a0) + c);
                 uint32_t cw[4], bw[4];
                 classify4(v.x, cw[0], bw[0]);
@@ -388,11 +399,11 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
                 }
                 if (scan && j < nsteps) cand[j * 32 + lane] = (uint16_t)cbits;
                 uint32_t pb = (done || deferred) ? 0u : cbits;
-                if (!has_undef && rel + __popc(pb) > CAND_CAP) {
+                if (!has_undef && rel + __popc(pb) > geo.cand_cap) {
                     // keep the lowest (CAND_CAP - rel) bits, hold everything else back
                     uint32_t rest = pb;
     #pragma unroll 1
-                for (int c = rel; c < CAND_CAP; c++) rest &= rest - 1;
+                for (int c = rel; c < geo.cand_cap; c++) rest &= rest - 1;
                     pb ^= rest;
                     deferred = true;
                     dj = j;
@@ -708,10 +719,15 @@ FastGeom make_geom(const BBParams &p, const BBTable &t, int max_read_len, bool p
     }
     const int avail = FAST_SMEM_LIMIT - (int)(g.nfw + g.nsw) * 4 - 64;
     g.warps = std::min(32, avail / wb);
+    g.cand_cap = CAND_CAP;
+    if (const char *e = getenv("BBDUK_B200_CAND_CAP")) g.cand_cap = std::max(1, atoi(e));
     return g;
 }
 
 }  // namespace
+
+// the packed stage A exists for the part-filter kernels and the canonical rcomp/k>=16 kernels
+bool packed_ok(const BBParams &p, const BBTable &t) { return parts_ok(p, t) || (p.rcomp && p.k >= 16); }
 
 FastPlan plan_fast(const BBParams &p, const BBTable &t, int max_read_len) {
     FastPlan pl{false, max_read_len, 0, 0};
@@ -735,7 +751,7 @@ FastPlan plan_fast(const BBParams &p, const BBTable &t, int max_read_len) {
 int launch_fast(const FastPlan &plan, const uint8_t *d_bases, const uint32_t *d_offsets, int64_t n_reads, int paired,
                 const BBParams &p, const BBTable &t, const bbduk_out &out, bbduk_stats *d_stats,
                 unsigned long long *scaf_reads, unsigned long long *scaf_bases, int32_t *d_handoff,
-                unsigned int *d_handoff_n, int sm_count, cudaStream_t st) {
+                unsigned int *d_handoff_n, int sm_count, cudaStream_t st, const uint32_t *pk_F, const uint16_t *pk_D) {
     const FastGeom g = make_geom(p, t, plan.max_read_len);
     const int threads = g.warps * 32;
     const int64_t n_tiles = (n_reads + 31) / 32;
@@ -743,7 +759,7 @@ int launch_fast(const FastPlan &plan, const uint8_t *d_bases, const uint32_t *d_
     auto go = [&](auto kern) -> int {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes) != cudaSuccess) return -1;
         kern<<<blocks, threads, plan.smem_bytes, st>>>(d_bases, d_offsets, n_reads, paired, p, t, out, d_stats, scaf_reads,
-                                                       scaf_bases, d_handoff, d_handoff_n, g, nullptr, nullptr);
+                                                       scaf_bases, d_handoff, d_handoff_n, g, nullptr, nullptr, pk_F, pk_D);
         return cudaGetLastError() == cudaSuccess ? 1 : -1;
     };
     const bool k16 = p.k >= 16;
@@ -752,6 +768,14 @@ int launch_fast(const FastPlan &plan, const uint8_t *d_bases, const uint32_t *d_
     (parts ? go(bbduk_fast_kernel<FM, true, true, true>)                                                              \
            : p.rcomp ? (k16 ? go(bbduk_fast_kernel<FM, true, true, false>) : go(bbduk_fast_kernel<FM, true, false, false>))    \
                      : (k16 ? go(bbduk_fast_kernel<FM, false, true, false>) : go(bbduk_fast_kernel<FM, false, false, false>)))
+    if (pk_F) {  // host-packed batch (only offered when packed_ok())
+        if (!pk_D || !packed_ok(p, t)) return -1;
+#define BB_PK(FM) (parts ? go(bbduk_fast_kernel<FM, true, true, true, false, true>) : go(bbduk_fast_kernel<FM, true, true, false, false, true>))
+        if (p.mode == MODE_KFILTER) return BB_PK(FM_KFILTER);
+        if (p.ktrimLeft) return BB_PK(FM_KTRIM_L);
+        return BB_PK(FM_KTRIM_R);
+#undef BB_PK
+    }
     if (p.mode == MODE_KFILTER) return BB_DISPATCH(FM_KFILTER);
     if (p.ktrimLeft) return BB_DISPATCH(FM_KTRIM_L);
     return BB_DISPATCH(FM_KTRIM_R);
@@ -771,7 +795,7 @@ int launch_epilogue(const uint8_t *d_bases, const uint32_t *d_offsets, int64_t n
     auto go = [&](auto kern) -> int {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
         kern<<<blocks, threads, smem, st>>>(d_bases, d_offsets, n_reads, paired, p, t, out, d_stats, scaf_reads, scaf_bases,
-                                            nullptr, nullptr, g, d_first64, d_lastpos);
+                                            nullptr, nullptr, g, d_first64, d_lastpos, nullptr, nullptr);
         return cudaGetLastError() == cudaSuccess ? 1 : -1;
     };
     if (p.mode == MODE_KFILTER) return go(bbduk_fast_kernel<FM_KFILTER, true, true, true, true>);

@@ -223,6 +223,12 @@ BBDUK_API int bbduk_b200_synth_contam(uint8_t *d_bases, uint32_t *d_offsets, int
                                       int32_t read_len, const uint8_t *d_ref, int64_t ref_len, uint64_t seed,
                                       int32_t contam_pct, int32_t sub_per_10k, int32_t n_per_10k, void *stream);
 
+/* Host helper (no GPU needed): the 2-bit packing bbduk_b200_process applies to a chunk before it crosses PCIe when
+ * the tuned kernel takes the whole chunk (set BBDUK_B200_PACK_HOST=0 to ship ASCII instead). F[i] = big-endian
+ * 2-bit codes of bases 16i..16i+15 (A0 C1 G2 T/U3, anything else 0), D[i] = "defined" bits (bit 15-b = base 16i+b);
+ * both have (n+15)/16 entries. Same tables as dna/AminoAcid.java:269-285, :1289-1320. */
+BBDUK_API int bbduk_b200_pack_bases(const uint8_t *bases, int64_t n, uint32_t *F, uint16_t *D);
+
 BBDUK_API const char *bbduk_b200_last_error(bbduk_handle *h);
 BBDUK_API void bbduk_b200_destroy(bbduk_handle *h);
 

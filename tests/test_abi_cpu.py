@@ -116,3 +116,34 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle" not in text.lower() or f in ("synth.py",), f"{f} mentions the oracle"
+
+
+def test_host_packer_matches_the_codec_tables():
+    """bbduk_b200_pack_bases (AVX2 or scalar) against a table-driven numpy restatement, every byte value included"""
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    code = np.zeros(256, np.uint32)
+    valid = np.zeros(256, np.uint32)
+    for i, ch in enumerate("ACGT"):
+        code[ord(ch)] = code[ord(ch.lower())] = i
+        valid[ord(ch)] = valid[ord(ch.lower())] = 1
+    code[ord("U")] = code[ord("u")] = 3
+    valid[ord("U")] = valid[ord("u")] = 1
+    for n in (0, 1, 15, 16, 17, 31, 32, 33, 1000, 4099, 100003):
+        b = rng.integers(0, 256, n).astype(np.uint8)
+        if n > 50:
+            b[10:n // 2] = np.frombuffer(b"ACGTacgtUuNn", np.uint8)[rng.integers(0, 12, n // 2 - 10)]
+        g = (n + 15) // 16
+        F = np.full(g + 1, 0xDEADBEEF, np.uint32)
+        D = np.full(g + 1, 0xBEEF, np.uint16)
+        assert lib.bbduk_b200_pack_bases(b.ctypes.data, n, F.ctypes.data, D.ctypes.data) == 0
+        pad = np.zeros(g * 16, np.uint8)
+        pad[:n] = b
+        inside = (np.arange(g * 16) < n).astype(np.uint32)
+        c = (code[pad] * inside).reshape(g, 16)
+        v = (valid[pad] * inside).reshape(g, 16)
+        wantF = (c << (30 - 2 * np.arange(16, dtype=np.uint32))[None, :]).sum(axis=1).astype(np.uint32)
+        wantD = (v << (15 - np.arange(16, dtype=np.uint32))[None, :]).sum(axis=1).astype(np.uint16)
+        assert np.array_equal(F[:g], wantF), n
+        assert np.array_equal(D[:g], wantD), n
+        assert F[g] == 0xDEADBEEF and D[g] == 0xBEEF  # nothing written past the end
