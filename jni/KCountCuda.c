@@ -1,0 +1,52 @@
+/*
+ * KCountCuda.c -- JNI shim between a GPU-backed kmer.KmerTableSet (Java) and the counting entry points of
+ * libbbduk_b200.so (include/kcount_b200.h). Pure marshalling, same conventions as jni/BBDukCuda.c and the
+ * reference's jni/BBMergeOverlapper.c:389-437. NOT compiled against a real JDK in this repository's image.
+ *
+ * Java side: KmerTableSet.LoadThread (kmer/KmerTableSet.java:489-592) aggregates reads into one byte[] +
+ * long[] offsets per >= 1 M reads and calls addReadsNative instead of addKmersToTable (:652-716);
+ * AbstractKmerTableSet.fillHistogram (:370) calls khistNative; "Unique Kmers" comes from statsNative[3].
+ */
+#include <jni.h>
+#include <stddef.h>
+
+#include "kcount_b200.h"
+
+JNIEXPORT jlong JNICALL Java_kmer_KmerTableSetGPU_createNative(JNIEnv *env, jclass cls, jint k, jboolean rcomp, jlong initialKeys) {
+    kcount_handle *h = NULL;
+    if (kcount_b200_create(k, rcomp ? 1 : 0, initialKeys, -1, &h)) return 0;
+    return (jlong)(intptr_t)h;
+}
+
+JNIEXPORT jint JNICALL Java_kmer_KmerTableSetGPU_addReadsNative(JNIEnv *env, jclass cls, jlong handle, jbyteArray jbases,
+                                                                jlongArray joffsets, jlong nReads) {
+    jbyte *b = (jbyte *)(*env)->GetPrimitiveArrayCritical(env, jbases, NULL);
+    jlong *o = (jlong *)(*env)->GetPrimitiveArrayCritical(env, joffsets, NULL);
+    const jint rc = kcount_b200_add_reads((kcount_handle *)(intptr_t)handle, (const uint8_t *)b, (const int64_t *)o, nReads);
+    (*env)->ReleasePrimitiveArrayCritical(env, joffsets, o, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, jbases, b, JNI_ABORT);
+    return rc;
+}
+
+/* stats4 = {readsIn, basesIn, kmersIn, unique k-mers} */
+JNIEXPORT jint JNICALL Java_kmer_KmerTableSetGPU_statsNative(JNIEnv *env, jclass cls, jlong handle, jlongArray jstats4) {
+    int64_t v[4];
+    const jint rc = kcount_b200_stats((kcount_handle *)(intptr_t)handle, v);
+    if (!rc) (*env)->SetLongArrayRegion(env, jstats4, 0, 4, (const jlong *)v);
+    return rc;
+}
+
+JNIEXPORT jint JNICALL Java_kmer_KmerTableSetGPU_khistNative(JNIEnv *env, jclass cls, jlong handle, jint histMax, jlongArray jhist) {
+    jlong *hst = (jlong *)(*env)->GetPrimitiveArrayCritical(env, jhist, NULL);
+    const jint rc = kcount_b200_khist((kcount_handle *)(intptr_t)handle, histMax, (int64_t *)hst);
+    (*env)->ReleasePrimitiveArrayCritical(env, jhist, hst, 0);
+    return rc;
+}
+
+JNIEXPORT jstring JNICALL Java_kmer_KmerTableSetGPU_lastErrorNative(JNIEnv *env, jclass cls, jlong handle) {
+    return (*env)->NewStringUTF(env, kcount_b200_last_error((kcount_handle *)(intptr_t)handle));
+}
+
+JNIEXPORT void JNICALL Java_kmer_KmerTableSetGPU_destroyNative(JNIEnv *env, jclass cls, jlong handle) {
+    kcount_b200_destroy((kcount_handle *)(intptr_t)handle);
+}

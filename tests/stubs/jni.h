@@ -1,0 +1,36 @@
+/*
+ * Minimal stand-in for <jni.h>, written for this repository's tests only: the image has no JDK, and the JNI shims
+ * under jni/ must at least compile and link against the C ABI. It declares just the types and the JNIEnv members
+ * those shims use, with the signatures of the JNI specification. NOT a usable JNI header.
+ */
+#ifndef TEST_STUB_JNI_H
+#define TEST_STUB_JNI_H
+#include <stdint.h>
+
+typedef int32_t jint;
+typedef int64_t jlong;
+typedef int8_t jbyte;
+typedef uint8_t jboolean;
+typedef jint jsize;
+typedef struct _jobject *jobject;
+typedef jobject jclass;
+typedef jobject jstring;
+typedef jobject jarray;
+typedef jarray jintArray;
+typedef jarray jlongArray;
+typedef jarray jbyteArray;
+
+#define JNI_ABORT 2
+#define JNIEXPORT __attribute__((visibility("default")))
+#define JNICALL
+
+struct JNINativeInterface_;
+typedef const struct JNINativeInterface_ *JNIEnv;
+struct JNINativeInterface_ {
+    jsize (*GetArrayLength)(JNIEnv *env, jarray array);
+    void *(*GetPrimitiveArrayCritical)(JNIEnv *env, jarray array, jboolean *isCopy);
+    void (*ReleasePrimitiveArrayCritical)(JNIEnv *env, jarray array, void *carray, jint mode);
+    jstring (*NewStringUTF)(JNIEnv *env, const char *utf);
+    void (*SetLongArrayRegion)(JNIEnv *env, jlongArray array, jsize start, jsize len, const jlong *buf);
+};
+#endif

@@ -147,3 +147,19 @@ def test_host_packer_matches_the_codec_tables():
         assert np.array_equal(F[:g], wantF), n
         assert np.array_equal(D[:g], wantD), n
         assert F[g] == 0xDEADBEEF and D[g] == 0xBEEF  # nothing written past the end
+
+
+@pytest.mark.parametrize("shim", ["BBDukCuda.c", "KCountCuda.c"])
+def test_jni_shims_compile_and_link_against_the_c_abi(shim, tmp_path):
+    """No JDK in the image: the shims are compiled with a stub jni.h (tests/stubs) and linked against the library,
+    so that every C-ABI call they make is checked against the real prototypes and resolves."""
+    import subprocess
+    _lib.load()
+    out = tmp_path / (shim + ".so")
+    cmd = ["gcc", "-O2", "-std=c99", "-Wall", "-Werror", "-fPIC", "-shared", "-Wl,--no-undefined",
+           "-I", os.path.join(ROOT, "tests", "stubs"), "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "jni", shim),
+           "-L", os.path.join(ROOT, "bbtools_b200"), "-lbbduk_b200", "-o", str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    syms = subprocess.run(["nm", "-D", "--defined-only", str(out)], capture_output=True, text=True).stdout
+    assert "Java_" in syms
