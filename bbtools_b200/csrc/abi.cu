@@ -19,7 +19,7 @@
 namespace {
 
 constexpr int N_SLOTS = 4;                    // staging slots (streams) per handle
-constexpr int64_t CHUNK_READS = 1 << 20;      // reads per device batch on the host path: small enough that H2D of
+constexpr int64_t CHUNK_READS = 1 << 19;      // reads per device batch on the host path: small enough that H2D of
                                               // chunk i+1, the kernels of chunk i and D2H of chunk i-1 overlap
 constexpr int64_t CHUNK_BYTES = 256ll << 20;  // bases per device batch (offsets stay 32-bit)
 
@@ -66,6 +66,7 @@ struct bbduk_handle {
     std::atomic<int64_t> launches{0};
     std::atomic<int> max_read_len_hint{0};
     bool trace = false;     // BBDUK_B200_TRACE=1: per-chunk host timings on stderr
+    int ascii_every = 3;    // BBDUK_B200_ASCII_EVERY=n: every n-th chunk crosses PCIe as ASCII (0 = never)
     bool pack_host = true;  // BBDUK_B200_PACK_HOST=0 keeps the bases ASCII across PCIe
     std::mutex err_mu;
     std::string err;
@@ -372,6 +373,7 @@ int bbduk_b200_create(const bbduk_cfg *cfg, bbduk_handle **out) {
     if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
     if (const char *e = getenv("BBDUK_B200_PACK_HOST")) h->pack_host = atoi(e) != 0;
     if (const char *e = getenv("BBDUK_B200_TRACE")) h->trace = atoi(e) != 0;
+    if (const char *e = getenv("BBDUK_B200_ASCII_EVERY")) h->ascii_every = std::max(0, atoi(e));
     *out = h;
     return 0;
 }
@@ -556,6 +558,7 @@ int bbduk_b200_process(bbduk_handle *h, const uint8_t *bases, const int64_t *off
         CKH(cudaMemset(d_stats, 0, sizeof(bbduk_stats)));
     }
     int rc = 0;
+    int chunk_no = 0;
     std::vector<Slot *> used;
     const int per = paired ? 2 : 1;
     int64_t r0 = 0;
@@ -627,6 +630,11 @@ int bbduk_b200_process(bbduk_handle *h, const uint8_t *bases, const int64_t *off
             const BBTable tv = h->table.view();
             packed = h->pack_host && !want_mask && max_len <= FAST_MAX_READ_LEN && nb >= (1 << 16) &&
                      plan_fast(h->p, tv, max_len).usable && packed_ok(h->p, tv);
+            // host packing is bound by the host's memory bandwidth, the ASCII path by PCIe: every n-th chunk goes
+            // ASCII (no CPU work, DMA straight from the caller's buffer) so that both resources are used
+            // (never the last chunk of a call: its transfer is the tail nothing overlaps with)
+            if (packed && h->ascii_every > 0 && (chunk_no % h->ascii_every) == h->ascii_every - 1 && r1 < n_reads) packed = false;
+            chunk_no++;
         }
         if (packed && !rc) rc = ensure_packed(h, s, nr, nb);
         if (packed && !rc) {
@@ -637,7 +645,9 @@ int bbduk_b200_process(bbduk_handle *h, const uint8_t *bases, const int64_t *off
             Slot *sp = &s;
             const auto t_pack0 = std::chrono::steady_clock::now();
             h->pool->run([=](int part, int n_parts) {
-                const int64_t g0 = groups * part / n_parts, g1 = groups * (part + 1) / n_parts;
+                // worker ranges start on 512-base boundaries so that the packer can stream whole cache lines
+                const int64_t gb = (groups + 31) / 32;
+                const int64_t g0 = std::min(groups, gb * part / n_parts * 32), g1 = std::min(groups, gb * (part + 1) / n_parts * 32);
                 pack_bases_range(src, nb, g0, g1, sp->h_F, sp->h_D);
                 const int64_t i0 = (nr + 1) * part / n_parts, i1 = (nr + 1) * (part + 1) / n_parts;
                 for (int64_t i = i0; i < i1; i++) sp->h_off32[i] = (uint32_t)(osrc[i] - osrc[0]);

@@ -42,36 +42,68 @@ void pack_scalar(const uint8_t *b, int64_t n, int64_t g0, int64_t g1, uint32_t *
 }
 
 #if defined(__x86_64__)
-__attribute__((target("avx2"))) void pack_avx2(const uint8_t *b, int64_t n, int64_t g0, int64_t g1, uint32_t *F, uint16_t *D) {
+// 32 bases -> two F words and two D halfwords (in one uint32)
+__attribute__((target("avx2"))) static inline void pack32(const uint8_t *src, uint32_t &f0, uint32_t &f1, uint32_t &dd) {
     const __m256i three = _mm256_set1_epi8(3);
     const __m256i lower = _mm256_set1_epi8(0x20);
-    const __m256i lut = _mm256_setr_epi8((char)0xFF, 0x61, (char)0xFF, 0x63, 0x74, 0x75, (char)0xFF, 0x67, (char)0xFF, (char)0xFF, (char)0xFF,
-                                         (char)0xFF, (char)0xFF, (char)0xFF, (char)0xFF, (char)0xFF, (char)0xFF, 0x61, (char)0xFF, 0x63, 0x74,
-                                         0x75, (char)0xFF, 0x67, (char)0xFF, (char)0xFF, (char)0xFF, (char)0xFF, (char)0xFF, (char)0xFF,
-                                         (char)0xFF, (char)0xFF);
+    const char X = (char)0xFF;
+    // expected lower-case byte by low nibble: a(1) c(3) t(4) u(5) g(7)
+    const __m256i lut = _mm256_setr_epi8(X, 0x61, X, 0x63, 0x74, 0x75, X, 0x67, X, X, X, X, X, X, X, X,
+                                         X, 0x61, X, 0x63, 0x74, 0x75, X, 0x67, X, X, X, X, X, X, X, X);
     const __m256i m41 = _mm256_set1_epi16(0x0104);      // bytes (4,1): 4*c0 + c1
     const __m256i m161 = _mm256_set1_epi32(0x00010010);  // words (16,1): 16*x0 + x1
-    const __m256i gather = _mm256_setr_epi8(12, 8, 4, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 12, 8, 4, 0, -1, -1, -1, -1,
-                                            -1, -1, -1, -1, -1, -1, -1, -1);
-    const __m256i rev = _mm256_setr_epi8(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4,
-                                         3, 2, 1, 0);
+    const __m256i gather = _mm256_setr_epi8(12, 8, 4, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
+                                            12, 8, 4, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
+    const __m256i rev = _mm256_setr_epi8(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0,
+                                         15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0);
+    const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src));
+    // codes = ((c>>1) ^ (c>>2)) & 3 per byte (bits shifted in from the neighbour byte are masked away)
+    __m256i c = _mm256_and_si256(_mm256_xor_si256(_mm256_srli_epi16(v, 1), _mm256_srli_epi16(v, 2)), three);
+    // defined <=> (c|0x20) is one of a c g t u and c < 128 (pshufb zeroes lanes whose index has bit 7 set)
+    const __m256i y = _mm256_or_si256(v, lower);
+    const __m256i ok = _mm256_cmpeq_epi8(_mm256_shuffle_epi8(lut, y), y);
+    c = _mm256_and_si256(c, ok);  // undefined -> code 0
+    const __m256i p4 = _mm256_madd_epi16(_mm256_maddubs_epi16(c, m41), m161);  // one byte per 4 bases in each dword
+    const __m256i w = _mm256_shuffle_epi8(p4, gather);
+    f0 = (uint32_t)_mm256_extract_epi32(w, 0);
+    f1 = (uint32_t)_mm256_extract_epi32(w, 4);
+    dd = (uint32_t)_mm256_movemask_epi8(_mm256_shuffle_epi8(ok, rev));  // bit 15-b = base b, per 16-bit half
+}
+
+__attribute__((target("avx2"))) void pack_avx2(const uint8_t *b, int64_t n, int64_t g0, int64_t g1, uint32_t *F, uint16_t *D) {
     int64_t g = g0;
     const int64_t full = n / 16;  // groups whose 16 bytes are all inside the batch
+    // peel to a 64-byte boundary of F (16 groups) so that whole cache lines can be written without reading them
+    while (g + 1 < g1 && g + 1 < full && ((reinterpret_cast<uintptr_t>(F + g) & 63) != 0 || (reinterpret_cast<uintptr_t>(D + g) & 63) != 0)) {
+        uint32_t f0, f1, dd;
+        pack32(b + g * 16, f0, f1, dd);
+        F[g] = f0;
+        F[g + 1] = f1;
+        D[g] = (uint16_t)dd;
+        D[g + 1] = (uint16_t)(dd >> 16);
+        g += 2;
+    }
+    // 32 groups (512 bases) per iteration: two 64-byte lines of F and one of D, streamed past the cache
+    if ((reinterpret_cast<uintptr_t>(F + g) & 63) == 0 && (reinterpret_cast<uintptr_t>(D + g) & 63) == 0) {
+        for (; g + 32 <= g1 && g + 32 <= full; g += 32) {
+            alignas(64) uint32_t fb[32];
+            alignas(64) uint32_t db[16];
+#pragma GCC unroll 4
+            for (int q = 0; q < 16; q++) pack32(b + (g + 2 * q) * 16, fb[2 * q], fb[2 * q + 1], db[q]);
+            for (int q = 0; q < 4; q++)
+                _mm256_stream_si256(reinterpret_cast<__m256i *>(F + g) + q, _mm256_load_si256(reinterpret_cast<const __m256i *>(fb) + q));
+            for (int q = 0; q < 2; q++)
+                _mm256_stream_si256(reinterpret_cast<__m256i *>(D + g) + q, _mm256_load_si256(reinterpret_cast<const __m256i *>(db) + q));
+        }
+        _mm_sfence();
+    }
     for (; g + 1 < g1 && g + 1 < full; g += 2) {
-        const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(b + g * 16));
-        // codes = ((c>>1) ^ (c>>2)) & 3 per byte (bits shifted in from the neighbour byte are masked away)
-        __m256i c = _mm256_and_si256(_mm256_xor_si256(_mm256_srli_epi16(v, 1), _mm256_srli_epi16(v, 2)), three);
-        // defined <=> (c|0x20) is one of a c g t u and c < 128 (pshufb zeroes lanes whose index has bit 7 set)
-        const __m256i y = _mm256_or_si256(v, lower);
-        const __m256i ok = _mm256_cmpeq_epi8(_mm256_shuffle_epi8(lut, y), y);
-        c = _mm256_and_si256(c, ok);  // undefined -> code 0
-        const __m256i p4 = _mm256_madd_epi16(_mm256_maddubs_epi16(c, m41), m161);  // one byte per 4 bases in each dword
-        const __m256i w = _mm256_shuffle_epi8(p4, gather);
-        F[g] = (uint32_t)_mm256_extract_epi32(w, 0);
-        F[g + 1] = (uint32_t)_mm256_extract_epi32(w, 4);
-        const uint32_t mk = (uint32_t)_mm256_movemask_epi8(_mm256_shuffle_epi8(ok, rev));  // bit 15-b = base b, per half
-        D[g] = (uint16_t)mk;
-        D[g + 1] = (uint16_t)(mk >> 16);
+        uint32_t f0, f1, dd;
+        pack32(b + g * 16, f0, f1, dd);
+        F[g] = f0;
+        F[g + 1] = f1;
+        D[g] = (uint16_t)dd;
+        D[g + 1] = (uint16_t)(dd >> 16);
     }
     if (g < g1) pack_scalar(b, n, g, g1, F, D);
 }
