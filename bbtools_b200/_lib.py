@@ -48,6 +48,13 @@ SYMBOLS = [
                                           C.c_uint64, C.c_int32, C.c_void_p]),
     ("kcount_b200_last_error", C.c_char_p, [C.c_void_p]),
     ("kcount_b200_destroy", None, [C.c_void_p]),
+    # include/fastq_b200.h
+    ("fastq_b200_index", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
+                                   C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int32]),
+    ("fastq_b200_gather", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]),
+    ("fastq_b200_format", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
+                                    C.POINTER(C.c_int64), C.c_int32]),
 ]
 
 _LIB = None

@@ -375,8 +375,39 @@ class BBDuk:
         want_mask = bool(self.cfg.ktrim_n)
         return self.index.process(bases, offsets, paired, want_mask=want_mask)
 
-    def process(self):
+    def process_native(self):
+        """FASTQ in / FASTQ out through the native feed (include/fastq_b200.h); ktrim / kfilter modes"""
+        from .fastq import FastqBatch, load_text
         io = self.io
+        fb = FastqBatch(load_text(io["in1"]), load_text(io["in2"]) if io["in2"] else None)
+        paired = bool(io["in2"] or io["interleaved"])
+        per = 2 if paired else 1
+        bases, offsets = fb.arrays()
+        out, st = self.process_arrays(bases, offsets, paired)
+        self.stats = st
+        for removed, p1, p2 in ((False, io["out1"], io["out2"]), (True, io["outm1"], io["outm2"])):
+            if not p1:
+                continue
+            for path, sel in (((p1, 1), (p2, 2)) if p2 else ((p1, 0),)):
+                fb.format(per, out.lo, out.hi, out.flags, removed=removed, mate_sel=sel,
+                          trim_removed=bool(io["ottm"])).tofile(path)
+        self._write_stats()
+        return st
+
+    def _write_stats(self):
+        io = self.io
+        if io["stats"]:
+            rc_, bc = self.index.scaffold_counts()
+            with open(io["stats"], "w") as f:
+                f.write("#Name\tReads\tBases\n")
+                for i in np.argsort(-rc_, kind="stable"):
+                    if i > 0 and rc_[i] > 0:
+                        f.write(f"{self.scaffold_names[i]}\t{rc_[i]}\t{bc[i]}\n")
+
+    def process(self, native=True):
+        io = self.io
+        if native and not self.cfg.ktrim_n and not self.cfg.ksplit:
+            return self.process_native()
         n1, s1, q1 = read_fastq(io["in1"])
         paired = False
         if io["in2"]:
@@ -430,11 +461,5 @@ class BBDuk:
                     f.write(b"@" + names[i] + b"\n" + bytes(s[a:len(s) - 1]) + b"\n+\n" + bytes(ql[a:len(s) - 1]) + b"\n")
         for f in sinks.values():
             f.close()
-        if io["stats"]:
-            rc_, bc = self.index.scaffold_counts()
-            with open(io["stats"], "w") as f:
-                f.write("#Name\tReads\tBases\n")
-                for i in np.argsort(-rc_, kind="stable"):
-                    if i > 0 and rc_[i] > 0:
-                        f.write(f"{self.scaffold_names[i]}\t{rc_[i]}\t{bc[i]}\n")
+        self._write_stats()
         return st

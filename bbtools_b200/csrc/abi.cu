@@ -66,6 +66,7 @@ struct bbduk_handle {
     std::atomic<int64_t> launches{0};
     std::atomic<int> max_read_len_hint{0};
     bool trace = false;     // BBDUK_B200_TRACE=1: per-chunk host timings on stderr
+    bool ascii_every_set = false;
     int ascii_every = 3;    // BBDUK_B200_ASCII_EVERY=n: every n-th chunk crosses PCIe as ASCII (0 = never)
     bool pack_host = true;  // BBDUK_B200_PACK_HOST=0 keeps the bases ASCII across PCIe
     std::mutex err_mu;
@@ -373,7 +374,10 @@ int bbduk_b200_create(const bbduk_cfg *cfg, bbduk_handle **out) {
     if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
     if (const char *e = getenv("BBDUK_B200_PACK_HOST")) h->pack_host = atoi(e) != 0;
     if (const char *e = getenv("BBDUK_B200_TRACE")) h->trace = atoi(e) != 0;
-    if (const char *e = getenv("BBDUK_B200_ASCII_EVERY")) h->ascii_every = std::max(0, atoi(e));
+    if (const char *e = getenv("BBDUK_B200_ASCII_EVERY")) {
+        h->ascii_every = std::max(0, atoi(e));
+        h->ascii_every_set = true;
+    }
     *out = h;
     return 0;
 }
@@ -593,6 +597,8 @@ int bbduk_b200_process(bbduk_handle *h, const uint8_t *bases, const int64_t *off
                 if (const char *e = getenv("BBDUK_B200_HOST_THREADS")) share = -atoi(e);
                 const int hc = (int)std::thread::hardware_concurrency();
                 h->pool = new HostPool(share < 0 ? std::max(1, -share) : std::max(1, std::min(32, hc / share)));
+                // few packing workers per GPU (many ranks on one host): lean on PCIe more
+                if (!h->ascii_every_set) h->ascii_every = h->pool->size() >= 12 ? 3 : h->pool->size() >= 6 ? 2 : 1;
             }
             std::atomic<int> mx{0};
             std::atomic<bool> bad{false};

@@ -1,0 +1,76 @@
+"""The reads-in / reads-out surface (bbtools_b200.bbduk.BBDuk, the bbduk.sh command line) on FASTQ files: native
+feed vs the plain-Python feed, and both against records cut with the ORACLE's coordinates."""
+import os
+
+import numpy as np
+import pytest
+
+from bbtools_b200 import F_REMOVED, make_cfg, synth
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def write_fastq(path, bases, offsets, first, step, tag):
+    with open(path, "wb") as f:
+        for i in range(first, len(offsets) - 1, step):
+            s = bytes(bases[offsets[i]:offsets[i + 1]])
+            f.write(b"@pair%d %s\n" % (i // 2, tag) + s + b"\n+\n" + b"I" * len(s) + b"\n")
+
+
+@pytest.mark.parametrize("extra", [[], ["ottm=t"], ["rieb=f", "minlen=60"]])
+def test_bbduk_tool_paired_fastq(tmp_path, extra):
+    from bbtools_b200.bbduk import BBDuk
+    from bbtools_b200.fasta import read_fasta
+    from oracle.oracle import Oracle
+    bases, offsets = synth.paired_adapter_reads(4000, seed=41)
+    r1, r2 = tmp_path / "r1.fq", tmp_path / "r2.fq"
+    write_fastq(r1, bases, offsets, 0, 2, b"1:N:0")
+    write_fastq(r2, bases, offsets, 1, 2, b"2:N:0")
+    common = [f"in={r1}", f"in2={r2}", f"ref={GOLDEN}/adapters.fa", "ktrim=r", "k=23", "mink=11", "hdist=1", "tpe"] + extra
+    outs = {}
+    for mode in ("native", "python"):
+        o1, o2, m1, m2 = (tmp_path / f"{mode}_{x}.fq" for x in ("o1", "o2", "m1", "m2"))
+        tool = BBDuk(common + [f"out={o1}", f"out2={o2}", f"outm={m1}", f"outm2={m2}", f"stats={tmp_path}/{mode}.stats"])
+        st = tool.process(native=(mode == "native"))
+        outs[mode] = tuple(open(p, "rb").read() for p in (o1, o2, m1, m2)) + (open(f"{tmp_path}/{mode}.stats").read(),)
+        cfg = tool.cfg
+    assert outs["native"] == outs["python"]
+    # the same files from the oracle's coordinates
+    _, rb, roff = read_fasta(os.path.join(GOLDEN, "adapters.fa"))
+    ora = Oracle(cfg)
+    ora.add_ref(rb, roff)
+    ora.finalize()
+    want, wst = ora.process(bases, offsets, True)
+    assert wst.as_dict() == st.as_dict()
+    ottm = "ottm=t" in extra
+    exp = [[], [], [], []]
+    for i in range(len(offsets) - 1):
+        rem = bool(want.flags[i & ~1] & F_REMOVED)
+        s = bytes(bases[offsets[i]:offsets[i + 1]])
+        a, b = (int(want.lo[i]), int(want.hi[i])) if (not rem or ottm) else (0, len(s))
+        recd = b"@pair%d %s\n" % (i // 2, b"1:N:0" if i % 2 == 0 else b"2:N:0") + s[a:b] + b"\n+\n" + b"I" * (b - a) + b"\n"
+        exp[(2 if rem else 0) + (i & 1)].append(recd)
+    for k in range(4):
+        assert outs["native"][k] == b"".join(exp[k]), k
+    assert len(outs["native"][2]) > 0  # some pairs were removed
+
+
+def test_bbduk_tool_single_kfilter(tmp_path):
+    from bbtools_b200.bbduk import BBDuk
+    ref = synth.random_reference(2, 50_000, seed=7)
+    rf = tmp_path / "ref.fa"
+    with open(rf, "wb") as f:
+        for i in range(2):
+            f.write(b">scaf%d\n" % i + bytes(ref[0][ref[1][i]:ref[1][i + 1]]) + b"\n")
+    bases, offsets = synth.contaminant_reads(5000, ref[0], seed=3, contam_pct=25)
+    rq = tmp_path / "r.fq"
+    write_fastq(rq, bases, offsets, 0, 1, b"se")
+    res = {}
+    for mode in ("native", "python"):
+        o, m = tmp_path / f"{mode}_clean.fq", tmp_path / f"{mode}_contam.fq"
+        st = BBDuk([f"in={rq}", f"ref={rf}", "k=31", f"out={o}", f"outm={m}"]).process(native=(mode == "native"))
+        res[mode] = (open(o, "rb").read(), open(m, "rb").read(), st.as_dict())
+    assert res["native"] == res["python"]
+    assert 1000 < res["native"][2]["reads_kfiltered"] < 1500
+    assert res["native"][0].count(b"\n") + res["native"][1].count(b"\n") == 4 * 5000
