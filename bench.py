@@ -31,6 +31,10 @@ CFG = dict(k=23, mink=11, hdist=1, ktrim_right=1, trim_pairs_evenly=1)
 WORKLOAD = "bbduk.sh ktrim=r k=23 mink=11 hdist=1 tpe, ref=adapters.fa, synthetic 2x150 bp PE (cfg 2; tbo stays on the host)"
 ALG_BYTES_PER_READ = READ_LEN + 4 + 8  # bases + 4 B offset in + 8 B result out (hi + id0); table on-chip
 FALLBACK_HBM_GBS = 6650.0
+# dram__bytes_read.sum + dram__bytes_write.sum per read of the dominant kernel, from the committed `ncu --set full`
+# captures (profiles/r01_d_fast_kernel_raw.txt: 653.35 MB + 36.03 MB for a 4,194,304-read launch;
+# profiles/r01_e_kcount_kernel.txt: 28.33 GB + 6.91 GB for 217.6 M k-mers = 162 B per k-mer)
+NCU_TRAFFIC_BYTES_PER_READ = {"cfg2": (653351680 + 36031488) / 4194304, "cfg5": 120 * (28328275000 + 6911184000) / 217637790}
 
 
 def load_peak():
@@ -56,7 +60,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -302,9 +306,11 @@ def run_kcount(args, wl):
                     "d2h_bytes_per_step": 32, "reads_per_step_per_gpu": e_reads, "steps": e_steps},
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_kind, "kernel": wl["kernel"],
+                         "traffic": NCU_TRAFFIC_BYTES_PER_READ["cfg5"] * n_reads,
+                         "traffic_unit": "bytes per launch (ncu dram read+write per k-mer x k-mers per launch)",
+                         "peak_source": peak_kind, "kernel": wl["kernel"],
                          "algorithmic_bytes_per_read": wl["alg_bytes"], "ms_per_launch": kern_ms,
-                         "sector_granular_bytes_per_read": L + 4 + 64 * 120},
+                         "dram_line_bytes_per_read": L + 4 + (128 + 32) * 120},
         }))
     if world > 1:
         dist.barrier()
@@ -487,7 +493,10 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_kind, "kernel": wl["kernel"],
+                         "traffic": (NCU_TRAFFIC_BYTES_PER_READ[args.workload] * n_reads
+                                     if args.workload in NCU_TRAFFIC_BYTES_PER_READ else None),
+                         "traffic_unit": "bytes per launch (ncu dram read+write per read x reads per launch)",
+                         "peak_source": peak_kind, "kernel": wl["kernel"],
                          "algorithmic_bytes_per_read": wl["alg_bytes"], "ms_per_launch": kern_ms},
         }
         if args.workload in ("cfg3", "cfg4"):
