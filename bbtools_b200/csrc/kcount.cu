@@ -357,12 +357,18 @@ struct kcount_handle {
     std::atomic<int64_t> launches{0};
     std::mutex mu;
     std::string err;
-    // host path staging
-    uint8_t *d_bases = nullptr;
-    uint32_t *d_off = nullptr;
-    uint16_t *d_sbits = nullptr;  // read-start bit stream of the batch being counted
-    int64_t cap_bases = 0, cap_reads = 0, cap_sbits = 0;
-    std::vector<uint32_t> h_off;
+    // read-start bit stream of the batch being counted (device entry point)
+    uint16_t *d_sbits = nullptr;
+    int64_t cap_sbits = 0;
+    // host path: two staging sets so that the copy of chunk i+1 overlaps the counting of chunk i
+    struct Stage {
+        uint8_t *d_bases = nullptr;
+        uint32_t *d_off = nullptr, *h_off = nullptr;  // h_off pinned
+        uint16_t *d_sbits = nullptr;
+        int64_t cap_bases = 0, cap_reads = 0, cap_sbits = 0;
+        cudaStream_t st = nullptr;
+        cudaEvent_t done = nullptr;
+    } stage[2];
     cudaStream_t st = nullptr;
 };
 
@@ -416,7 +422,8 @@ int read_counters(kcount_handle *h, KCounters *c, cudaStream_t st) {
 }
 
 int grow(kcount_handle *h, uint64_t new_slots, cudaStream_t st) {
-    KCK(cudaStreamSynchronize(st));
+    (void)st;
+    KCK(cudaDeviceSynchronize());  // every stream that counts into the old table
     KSlot *ns = nullptr;
     if (alloc_table(h, new_slots, &ns)) return 1;
     KSlot *old = h->slots;
@@ -439,6 +446,7 @@ int reserve(kcount_handle *h, int64_t incoming, int64_t *allowed, cudaStream_t s
         return 0;
     }
     KCounters c;
+    KCK(cudaDeviceSynchronize());  // kernels of the other staging stream also create keys
     if (read_counters(h, &c, st)) return 1;
     int64_t room = limit() - h->unique_known;
     // grow while less than 1/8 of the table is free for this launch
@@ -451,22 +459,22 @@ int reserve(kcount_handle *h, int64_t incoming, int64_t *allowed, cudaStream_t s
 }
 
 int count_device(kcount_handle *h, const uint8_t *d_bases, const uint32_t *d_off, int64_t n_reads, int64_t n_bases,
-                 cudaStream_t st) {
+                 cudaStream_t st, uint16_t **sbits, int64_t *cap_sbits) {
     if (n_bases <= 0) return 0;
     if (reinterpret_cast<uintptr_t>(d_bases) & 15) return kerr(h, "d_bases must be 16-byte aligned");
     const int64_t n_spans = (n_bases + KC_SPAN - 1) / KC_SPAN;
     // read-start bit stream for this batch (2 bytes per 16 bases)
     const int64_t sb_bytes = ((n_bases + 31) / 32 + 2) * 4;
-    if (sb_bytes > h->cap_sbits) {
+    if (sb_bytes > *cap_sbits) {
         KCK(cudaStreamSynchronize(st));
-        cudaFree(h->d_sbits);
-        h->d_sbits = nullptr;
-        h->cap_sbits = sb_bytes + sb_bytes / 8 + 4096;
-        KCK(cudaMalloc(&h->d_sbits, (size_t)h->cap_sbits));
+        cudaFree(*sbits);
+        *sbits = nullptr;
+        *cap_sbits = sb_bytes + sb_bytes / 8 + 4096;
+        KCK(cudaMalloc(sbits, (size_t)*cap_sbits));
     }
-    KCK(cudaMemsetAsync(h->d_sbits, 0, (size_t)sb_bytes, st));
+    KCK(cudaMemsetAsync(*sbits, 0, (size_t)sb_bytes, st));
     kc_starts_kernel<<<(unsigned)std::min<int64_t>((n_reads + 255) / 256, (int64_t)h->sm_count * 16), 256, 0, st>>>(
-        d_off, n_reads, reinterpret_cast<uint32_t *>(h->d_sbits));
+        d_off, n_reads, reinterpret_cast<uint32_t *>(*sbits));
     h->launches += 1;
     int64_t span = 0;
     while (span < n_spans) {
@@ -477,9 +485,9 @@ int count_device(kcount_handle *h, const uint8_t *d_bases, const uint32_t *d_off
         take = std::min(take, n_spans - span);
         const int blocks = (int)std::min<int64_t>(take, (int64_t)h->sm_count * 8);
         if (h->rcomp)
-            kcount_kernel<true><<<blocks, KC_THREADS, 0, st>>>(d_bases, h->d_sbits, n_bases, span, span + take, h->k, view(h), h->d_ctr);
+            kcount_kernel<true><<<blocks, KC_THREADS, 0, st>>>(d_bases, *sbits, n_bases, span, span + take, h->k, view(h), h->d_ctr);
         else
-            kcount_kernel<false><<<blocks, KC_THREADS, 0, st>>>(d_bases, h->d_sbits, n_bases, span, span + take, h->k, view(h), h->d_ctr);
+            kcount_kernel<false><<<blocks, KC_THREADS, 0, st>>>(d_bases, *sbits, n_bases, span, span + take, h->k, view(h), h->d_ctr);
         h->launches += 1;
         KCK(cudaGetLastError());
         h->added_since += take * (int64_t)KC_SPAN;
@@ -542,7 +550,7 @@ int kcount_b200_add_reads_device(kcount_handle *h, const uint8_t *d_bases, const
     KCK(cudaSetDevice(h->device));
     h->reads_in += n_reads;
     h->bases_in += n_bases;
-    return count_device(h, d_bases, d_offsets, n_reads, n_bases, (cudaStream_t)stream);
+    return count_device(h, d_bases, d_offsets, n_reads, n_bases, (cudaStream_t)stream, &h->d_sbits, &h->cap_sbits);
 }
 
 int kcount_b200_add_reads(kcount_handle *h, const uint8_t *bases, const int64_t *offsets, int64_t n_reads) {
@@ -551,38 +559,48 @@ int kcount_b200_add_reads(kcount_handle *h, const uint8_t *bases, const int64_t 
     if (n_reads == 0) return 0;
     std::lock_guard<std::mutex> g(h->mu);
     KCK(cudaSetDevice(h->device));
-    const int64_t CH_READS = 1 << 22, CH_BYTES = 1ll << 30;
+    const int64_t CH_READS = 1 << 21, CH_BYTES = 1ll << 29;
     int64_t r0 = 0;
+    int chunk_no = 0;
     while (r0 < n_reads) {
         int64_t r1 = std::min(n_reads, r0 + CH_READS);
         while (r1 > r0 + 1 && offsets[r1] - offsets[r0] > CH_BYTES) r1 = r0 + (r1 - r0) / 2;
         const int64_t nb = offsets[r1] - offsets[r0], nr = r1 - r0;
         if (nb < 0 || nb >= (1ll << 32) - 64) return kerr(h, "a single read exceeds 4 GiB (or offsets decrease)");
-        if (nb + 64 > h->cap_bases) {
-            cudaFree(h->d_bases);
-            h->d_bases = nullptr;
-            h->cap_bases = nb + nb / 8 + 4096;
-            KCK(cudaMalloc(&h->d_bases, (size_t)h->cap_bases));
+        kcount_handle::Stage &sg = h->stage[chunk_no++ & 1];
+        if (!sg.st) {
+            KCK(cudaStreamCreateWithFlags(&sg.st, cudaStreamNonBlocking));
+            KCK(cudaEventCreateWithFlags(&sg.done, cudaEventDisableTiming));
         }
-        if (nr + 1 > h->cap_reads) {
-            cudaFree(h->d_off);
-            h->d_off = nullptr;
-            h->cap_reads = nr + nr / 8 + 1024;
-            KCK(cudaMalloc(&h->d_off, sizeof(uint32_t) * h->cap_reads));
+        KCK(cudaEventSynchronize(sg.done));  // the previous chunk staged here has been counted
+        if (nb + 64 > sg.cap_bases) {
+            cudaFree(sg.d_bases);
+            sg.d_bases = nullptr;
+            sg.cap_bases = nb + nb / 8 + 4096;
+            KCK(cudaMalloc(&sg.d_bases, (size_t)sg.cap_bases));
         }
-        h->h_off.resize(nr + 1);
+        if (nr + 1 > sg.cap_reads) {
+            cudaFree(sg.d_off);
+            cudaFreeHost(sg.h_off);
+            sg.d_off = sg.h_off = nullptr;
+            sg.cap_reads = nr + nr / 8 + 1024;
+            KCK(cudaMalloc(&sg.d_off, sizeof(uint32_t) * sg.cap_reads));
+            KCK(cudaHostAlloc(&sg.h_off, sizeof(uint32_t) * sg.cap_reads, cudaHostAllocDefault));
+        }
         for (int64_t i = 0; i <= nr; i++) {
             if (i > 0 && offsets[r0 + i] < offsets[r0 + i - 1]) return kerr(h, "offsets must be non-decreasing");
-            h->h_off[i] = (uint32_t)(offsets[r0 + i] - offsets[r0]);
+            sg.h_off[i] = (uint32_t)(offsets[r0 + i] - offsets[r0]);
         }
-        KCK(cudaMemcpyAsync(h->d_bases, bases + offsets[r0], (size_t)nb, cudaMemcpyHostToDevice, h->st));
-        KCK(cudaMemcpyAsync(h->d_off, h->h_off.data(), sizeof(uint32_t) * (nr + 1), cudaMemcpyHostToDevice, h->st));
+        KCK(cudaMemcpyAsync(sg.d_bases, bases + offsets[r0], (size_t)nb, cudaMemcpyHostToDevice, sg.st));
+        KCK(cudaMemcpyAsync(sg.d_off, sg.h_off, sizeof(uint32_t) * (nr + 1), cudaMemcpyHostToDevice, sg.st));
         h->reads_in += nr;
         h->bases_in += nb;
-        if (count_device(h, h->d_bases, h->d_off, nr, nb, h->st)) return 1;
-        KCK(cudaStreamSynchronize(h->st));
+        if (count_device(h, sg.d_bases, sg.d_off, nr, nb, sg.st, &sg.d_sbits, &sg.cap_sbits)) return 1;
+        KCK(cudaEventRecord(sg.done, sg.st));
         r0 = r1;
     }
+    for (auto &sg : h->stage)
+        if (sg.st) KCK(cudaStreamSynchronize(sg.st));
     return 0;
 }
 
@@ -726,8 +744,14 @@ void kcount_b200_destroy(kcount_handle *h) {
     cudaDeviceSynchronize();
     cudaFree(h->slots);
     cudaFree(h->d_ctr);
-    cudaFree(h->d_bases);
-    cudaFree(h->d_off);
+    for (auto &sg : h->stage) {
+        cudaFree(sg.d_bases);
+        cudaFree(sg.d_off);
+        cudaFree(sg.d_sbits);
+        cudaFreeHost(sg.h_off);
+        if (sg.done) cudaEventDestroy(sg.done);
+        if (sg.st) cudaStreamDestroy(sg.st);
+    }
     cudaFree(h->d_sbits);
     if (h->st) cudaStreamDestroy(h->st);
     delete h;

@@ -265,7 +265,9 @@ def run_kcount(args, wl):
     value = world * n_reads * args.steps / (total_ms_max * 1e-3)
     # end to end: host buffers through kcount_b200_add_reads
     e_reads = 2 * args.e2e_pairs
-    hb = bufs[0][0][: e_reads * L].cpu().numpy()
+    h_bases = torch.empty(e_reads * L, dtype=torch.uint8, pin_memory=True)
+    h_bases.copy_(bufs[0][0][: e_reads * L])
+    hb = h_bases.numpy()
     ho = np.arange(0, (e_reads + 1) * L, L, dtype=np.int64)
     tab.add_reads(hb, ho)
     barrier()
