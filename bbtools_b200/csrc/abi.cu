@@ -563,6 +563,14 @@ int bbduk_b200_process(bbduk_handle *h, const uint8_t *bases, const int64_t *off
     }
     int rc = 0;
     int chunk_no = 0;
+    // ASCII chunks are DMA'd straight from the caller's buffer: only worth it when that buffer is page-locked (a Java
+    // array reached through GetPrimitiveArrayCritical is not; then every chunk is packed into the pinned staging)
+    bool src_pinned = false;
+    {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, bases) == cudaSuccess) src_pinned = pa.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+    }
     std::vector<Slot *> used;
     const int per = paired ? 2 : 1;
     int64_t r0 = 0;
@@ -639,7 +647,8 @@ int bbduk_b200_process(bbduk_handle *h, const uint8_t *bases, const int64_t *off
             // host packing is bound by the host's memory bandwidth, the ASCII path by PCIe: every n-th chunk goes
             // ASCII (no CPU work, DMA straight from the caller's buffer) so that both resources are used
             // (never the last chunk of a call: its transfer is the tail nothing overlaps with)
-            if (packed && h->ascii_every > 0 && (chunk_no % h->ascii_every) == h->ascii_every - 1 && r1 < n_reads) packed = false;
+            if (packed && src_pinned && h->ascii_every > 0 && (chunk_no % h->ascii_every) == h->ascii_every - 1 && r1 < n_reads)
+                packed = false;
             chunk_no++;
         }
         if (packed && !rc) rc = ensure_packed(h, s, nr, nb);
