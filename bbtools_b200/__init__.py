@@ -5,8 +5,8 @@ include/bbduk_b200.h), the ctypes binding, and the host-side mirror of jgi.BBDuk
 read-in/read-out surface. There is no CPU fallback: importing the binding fails loudly when
 libbbduk_b200.so has not been built.
 """
-from ._abi import (BBDukCfg, BBDukOut, BBDukStats, F_DISCARDED, F_KTRIMMED, F_REMOVED, F_SPLIT, F_TPE, GEN_JGI, GEN_S,
+from ._abi import (BBDukCfg, BBDukOut, BBDukStats, BBDukTboCfg, F_DISCARDED, F_KTRIMMED, F_REMOVED, F_SPLIT, F_TBO, F_TPE, GEN_JGI, GEN_S,
                    Outputs, default_cfg, make_cfg)
 
 __all__ = ["BBDukCfg", "BBDukOut", "BBDukStats", "Outputs", "default_cfg", "make_cfg", "GEN_JGI", "GEN_S",
-           "F_DISCARDED", "F_REMOVED", "F_KTRIMMED", "F_TPE", "F_SPLIT"]
+           "F_DISCARDED", "F_REMOVED", "F_KTRIMMED", "F_TPE", "F_SPLIT", "F_TBO", "BBDukTboCfg"]

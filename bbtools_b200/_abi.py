@@ -12,6 +12,7 @@ F_REMOVED = 0x02
 F_KTRIMMED = 0x04
 F_TPE = 0x08
 F_SPLIT = 0x10
+F_TBO = 0x20
 
 
 class BBDukCfg(C.Structure):
@@ -73,6 +74,20 @@ class BBDukOut(C.Structure):
         ("count", C.c_void_p),
         ("maskbits", C.c_void_p),
         ("mask_off", C.c_void_p),
+    ]
+
+
+class BBDukTboCfg(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32),
+        ("strict_overlap", C.c_int32),
+        ("min_overlap0", C.c_int32),
+        ("min_overlap", C.c_int32),
+        ("min_insert0", C.c_int32),
+        ("min_insert", C.c_int32),
+        ("qual_offset", C.c_int32),
+        ("mee_filter", C.c_float),
+        ("reserved", C.c_int32 * 4),
     ]
 
 

@@ -330,6 +330,40 @@ class BBDukIndexGPU:
                                                        int(bool(paired)), C.byref(o), ptr(d_stats), ptr(stream)),
                     "process_device")
 
+    # -- trim by overlap (tbo=t), the step after the k-mer block (jgi/BBDuk.java:2878-2926) -----------
+    def tbo_cfg(self, **kw):
+        from ._abi import BBDukTboCfg
+        c = BBDukTboCfg()
+        self.lib.bbduk_b200_tbo_cfg_default(C.byref(c))
+        for k, v in kw.items():
+            setattr(c, k, v)
+        return c
+
+    def tbo(self, bases, quals, offsets, out, cfg=None):
+        """HOST buffers; `out` is the Outputs of process(): hi / flags are updated in place.
+        -> (insert per pair, [reads trimmed, bases trimmed])"""
+        cfg = cfg or self.tbo_cfg()
+        bases = np.ascontiguousarray(bases, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        q = None if quals is None else np.ascontiguousarray(quals, np.uint8)
+        n = len(offsets) - 1
+        insert = np.full(n // 2, -9, np.int32)
+        st = np.zeros(2, np.int64)
+        self._check(self.lib.bbduk_b200_tbo(self.h, C.byref(cfg), bases.ctypes.data, None if q is None else q.ctypes.data,
+                                            offsets.ctypes.data, n, out.lo.ctypes.data, out.hi.ctypes.data,
+                                            out.flags.ctypes.data, insert.ctypes.data, st.ctypes.data), "tbo")
+        return insert, st
+
+    def tbo_device(self, d_bases, d_quals, d_offsets, n_reads, max_read_len, d_lo, d_hi, d_flags, d_insert=None, d_stats=None,
+                   stream=None, cfg=None):
+        cfg = cfg or self.tbo_cfg()
+
+        def ptr(x):
+            return None if x is None else (x.data_ptr() if hasattr(x, "data_ptr") else int(x))
+        self._check(self.lib.bbduk_b200_tbo_device(self.h, C.byref(cfg), ptr(d_bases), ptr(d_quals), ptr(d_offsets), n_reads,
+                                                   max_read_len, ptr(d_lo), ptr(d_hi), ptr(d_flags), ptr(d_insert), ptr(d_stats),
+                                                   ptr(stream)), "tbo_device")
+
     def set_max_read_len(self, n):
         self._check(self.lib.bbduk_b200_set_max_read_len(self.h, int(n)), "set_max_read_len")
 

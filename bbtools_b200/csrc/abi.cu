@@ -79,6 +79,13 @@ struct bbduk_handle {
     int *dev_lastpos = nullptr;
     uint16_t *dev_sbits = nullptr;
     int64_t dev_sbits_cap = 0, dev_first_cap = 0;
+    struct TboBuf {  // staging of the synchronous bbduk_b200_tbo entry point
+        uint8_t *d_bases = nullptr, *d_quals = nullptr, *d_flags = nullptr;
+        uint32_t *d_off = nullptr;
+        int32_t *d_lo = nullptr, *d_hi = nullptr, *d_insert = nullptr;
+        int64_t cap_bases = 0, cap_quals = 0, cap_flags = 0, cap_off = 0, cap_lo = 0, cap_hi = 0, cap_insert = 0;
+    } tbo;
+    std::mutex tbo_mu;
     HostPool *pool = nullptr;  // host packing workers, created on first use
     std::mutex pool_mu;
     std::mutex dev_mu;
@@ -750,6 +757,102 @@ int bbduk_b200_set_max_read_len(bbduk_handle *h, int32_t max_read_len) {
     return 0;
 }
 
+void bbduk_b200_tbo_cfg_default(bbduk_tbo_cfg *c) {
+    if (!c) return;
+    memset(c, 0, sizeof *c);
+    c->struct_size = (int32_t)sizeof *c;
+    c->strict_overlap = 1;
+    c->min_overlap0 = c->min_overlap = c->min_insert0 = c->min_insert = -1;
+    c->qual_offset = 33;
+}
+
+int bbduk_b200_tbo_device(bbduk_handle *h, const bbduk_tbo_cfg *cfg, const uint8_t *d_bases, const uint8_t *d_quals,
+                          const uint32_t *d_offsets, int64_t n_reads, int32_t max_read_len, const int32_t *d_lo, int32_t *d_hi,
+                          uint8_t *d_flags, int32_t *d_insert, int64_t *d_stats2, void *stream) {
+    if (!h) return set_err(nullptr, "handle is NULL");
+    if (!cfg || cfg->struct_size != (int32_t)sizeof *cfg) return set_err(h, "bad bbduk_tbo_cfg");
+    if (n_reads < 0 || (n_reads & 1)) return set_err(h, "tbo needs paired reads (an even count)");
+    if (n_reads == 0) return 0;
+    if (!d_bases || !d_offsets || !d_lo || !d_hi || !d_flags) return set_err(h, "NULL input");
+    CKH(cudaSetDevice(h->device));
+    const int rc = launch_tbo(h->device, h->sm_count, cfg, d_bases, d_quals, d_offsets, n_reads, max_read_len, d_lo, d_hi, d_flags,
+                              d_insert, reinterpret_cast<unsigned long long *>(d_stats2), (cudaStream_t)stream);
+    if (rc == 2) return set_err(h, "tbo: a read is longer than 1008 bases (no device path, and no CPU fallback)");
+    if (rc) return set_err(h, std::string("tbo kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    h->launches += 1;
+    return 0;
+}
+
+int bbduk_b200_tbo(bbduk_handle *h, const bbduk_tbo_cfg *cfg, const uint8_t *bases, const uint8_t *quals, const int64_t *offsets,
+                   int64_t n_reads, const int32_t *lo, int32_t *hi, uint8_t *flags, int32_t *insert, int64_t *stats2) {
+    if (!h) return set_err(nullptr, "handle is NULL");
+    if (n_reads < 0 || (n_reads & 1)) return set_err(h, "tbo needs paired reads (an even count)");
+    if (n_reads == 0) return 0;
+    if (!bases || !offsets || !lo || !hi || !flags) return set_err(h, "NULL input");
+    CKH(cudaSetDevice(h->device));
+    std::lock_guard<std::mutex> g(h->tbo_mu);
+    cudaStream_t st = nullptr;  // the legacy default stream: this entry point is synchronous
+    int64_t *d_stats = nullptr;
+    CKH(cudaMalloc(&d_stats, 2 * sizeof(int64_t)));
+    CKH(cudaMemset(d_stats, 0, 2 * sizeof(int64_t)));
+    int rc = 0;
+    int64_t r0 = 0;
+    std::vector<uint32_t> off32;
+    while (r0 < n_reads && !rc) {
+        int64_t r1 = std::min(n_reads, r0 + (CHUNK_READS << 1));
+        while (r1 > r0 + 2 && offsets[r1] - offsets[r0] > CHUNK_BYTES) r1 = r0 + std::max<int64_t>(2, ((r1 - r0) / 4) * 2);
+        const int64_t nr = r1 - r0, nb = offsets[r1] - offsets[r0];
+        if (nb < 0 || nb >= (1ll << 32) - 64) {
+            rc = set_err(h, "a pair exceeds 4 GiB (or offsets decrease)");
+            break;
+        }
+        int max_len = 0;
+        off32.resize(nr + 1);
+        for (int64_t i = 0; i <= nr; i++) off32[i] = (uint32_t)(offsets[r0 + i] - offsets[r0]);
+        for (int64_t i = 0; i < nr; i++) max_len = std::max(max_len, (int)(hi[r0 + i] - lo[r0 + i]));
+        auto need = [&](void **p, int64_t *cap, int64_t bytes) -> int {
+            if (bytes <= *cap) return 0;
+            cudaFree(*p);
+            *p = nullptr;
+            *cap = bytes + bytes / 8 + 4096;
+            return cudaMalloc(p, (size_t)*cap) == cudaSuccess ? 0 : 1;
+        };
+        auto &tb = h->tbo;
+        if (need((void **)&tb.d_bases, &tb.cap_bases, nb + 64) || (quals && need((void **)&tb.d_quals, &tb.cap_quals, nb + 64)) ||
+            need((void **)&tb.d_off, &tb.cap_off, 4 * (nr + 1)) || need((void **)&tb.d_lo, &tb.cap_lo, 4 * nr) ||
+            need((void **)&tb.d_hi, &tb.cap_hi, 4 * nr) || need((void **)&tb.d_flags, &tb.cap_flags, nr) ||
+            need((void **)&tb.d_insert, &tb.cap_insert, 2 * nr + 8)) {
+            rc = set_err(h, "tbo: device allocation failed");
+            break;
+        }
+#define CKT(call)                                                                       \
+    if (!rc && (call) != cudaSuccess) rc = set_err(h, std::string(#call " failed: ") + cudaGetErrorString(cudaGetLastError()))
+        CKT(cudaMemcpyAsync(tb.d_bases, bases + offsets[r0], (size_t)nb, cudaMemcpyHostToDevice, st));
+        if (quals) CKT(cudaMemcpyAsync(tb.d_quals, quals + offsets[r0], (size_t)nb, cudaMemcpyHostToDevice, st));
+        CKT(cudaMemcpyAsync(tb.d_off, off32.data(), 4 * (size_t)(nr + 1), cudaMemcpyHostToDevice, st));
+        CKT(cudaMemcpyAsync(tb.d_lo, lo + r0, 4 * (size_t)nr, cudaMemcpyHostToDevice, st));
+        CKT(cudaMemcpyAsync(tb.d_hi, hi + r0, 4 * (size_t)nr, cudaMemcpyHostToDevice, st));
+        CKT(cudaMemcpyAsync(tb.d_flags, flags + r0, (size_t)nr, cudaMemcpyHostToDevice, st));
+        if (!rc)
+            rc = bbduk_b200_tbo_device(h, cfg, tb.d_bases, quals ? tb.d_quals : nullptr, tb.d_off, nr, max_len, tb.d_lo, tb.d_hi,
+                                       tb.d_flags, tb.d_insert, d_stats, st);
+        CKT(cudaMemcpyAsync(hi + r0, tb.d_hi, 4 * (size_t)nr, cudaMemcpyDeviceToHost, st));
+        CKT(cudaMemcpyAsync(flags + r0, tb.d_flags, (size_t)nr, cudaMemcpyDeviceToHost, st));
+        if (insert) CKT(cudaMemcpyAsync(insert + r0 / 2, tb.d_insert, 4 * (size_t)(nr / 2), cudaMemcpyDeviceToHost, st));
+        CKT(cudaStreamSynchronize(st));
+#undef CKT
+        r0 = r1;
+    }
+    if (!rc && stats2) {
+        int64_t v[2] = {0, 0};
+        if (cudaMemcpy(v, d_stats, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) rc = set_err(h, "tbo: stats copy failed");
+        stats2[0] += v[0];
+        stats2[1] += v[1];
+    }
+    cudaFree(d_stats);
+    return rc;
+}
+
 int bbduk_b200_pack_bases(const uint8_t *bases, int64_t n, uint32_t *F, uint16_t *D) {
     if (n < 0 || (n > 0 && (!bases || !F || !D))) return set_err(nullptr, "bad pack_bases arguments");
     pack_bases(bases, n, F, D);
@@ -776,6 +879,13 @@ void bbduk_b200_destroy(bbduk_handle *h) {
     cudaFree(h->dev_first64);
     cudaFree(h->dev_lastpos);
     cudaFree(h->dev_sbits);
+    cudaFree(h->tbo.d_bases);
+    cudaFree(h->tbo.d_quals);
+    cudaFree(h->tbo.d_flags);
+    cudaFree(h->tbo.d_off);
+    cudaFree(h->tbo.d_lo);
+    cudaFree(h->tbo.d_hi);
+    cudaFree(h->tbo.d_insert);
     delete h->pool;
     delete h;
 }

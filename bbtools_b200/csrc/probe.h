@@ -42,3 +42,8 @@ int launch_epilogue(const uint8_t *d_bases, const uint32_t *d_offsets, int64_t n
                     const BBTable &t, const bbduk_out &out, bbduk_stats *d_stats, unsigned long long *scaf_reads,
                     unsigned long long *scaf_bases, const unsigned long long *d_first64, const int *d_lastpos, int sm_count,
                     cudaStream_t st);
+
+// trim by overlap (tbo.cu); 0 ok, 1 CUDA failure, 2 read too long
+int launch_tbo(int device, int sm_count, const bbduk_tbo_cfg *cfg, const uint8_t *d_bases, const uint8_t *d_quals,
+               const uint32_t *d_offsets, int64_t n_reads, int max_len, const int32_t *d_lo, int32_t *d_hi, uint8_t *d_flags,
+               int32_t *d_insert, unsigned long long *d_stats, cudaStream_t st);

@@ -94,6 +94,7 @@ typedef struct bbduk_cfg {
 #define BBDUK_F_KTRIMMED  0x04 /* the read's own ktrim/kmask call returned x>0 */
 #define BBDUK_F_TPE       0x08 /* shortened by trimpairsevenly (jgi/BBDuk.java:2801-2811) */
 #define BBDUK_F_SPLIT     0x10 /* ksplit produced a second segment [count, len-1) */
+#define BBDUK_F_TBO       0x20 /* shortened by trim-by-overlap (bbduk_b200_tbo; jgi/BBDuk.java:2911-2924) */
 
 /*
  * Per-read outputs, struct of arrays, each n_reads long; any pointer may be NULL (not wanted).
@@ -222,6 +223,42 @@ BBDUK_API int bbduk_b200_synth_reference(uint8_t *d_out, int64_t n, uint64_t see
 BBDUK_API int bbduk_b200_synth_contam(uint8_t *d_bases, uint32_t *d_offsets, int64_t n_reads, int64_t first_read,
                                       int32_t read_len, const uint8_t *d_ref, int64_t ref_len, uint64_t seed,
                                       int32_t contam_pct, int32_t sub_per_10k, int32_t n_per_10k, void *stream);
+
+/*
+ * Trim by overlap (tbo=t), the step that follows the k-mer block in the canonical adapter-trimming command
+ * (`ktrim=r k=23 mink=11 hdist=1 tpe tbo`). Parameters with the meaning of the bbduk.sh flags; -1 / 0 = the reference's
+ * default (jgi/BBDuk.java:5368-5371, :712-728).
+ */
+typedef struct bbduk_tbo_cfg {
+    int32_t struct_size;     /* = sizeof(bbduk_tbo_cfg) */
+    int32_t strict_overlap;  /* strictoverlap= ; default 1 */
+    int32_t min_overlap0;    /* -1 -> 7  */
+    int32_t min_overlap;     /* minoverlap= ; -1 -> 14 */
+    int32_t min_insert0;     /* -1 -> 16 */
+    int32_t min_insert;      /* mininsert= ; -1 -> 40 */
+    int32_t qual_offset;     /* ASCII offset of the quality bytes; 0 -> 33 */
+    float   mee_filter;      /* 0 -> 15 (strict) / off (loose) */
+    int32_t reserved[4];
+} bbduk_tbo_cfg;
+BBDUK_API void bbduk_b200_tbo_cfg_default(bbduk_tbo_cfg *cfg);
+
+/* Replaces: the tbo block of the per-pair loop (jgi/BBDuk.java:2878-2926) for one batch that has been through
+ * bbduk_b200_process: the expectedErrors guard (needs quals; NULL = reads without qualities, guard passes),
+ * r2.reverseComplementFast(), BBMergeOverlapper.mateByOverlapRatio (jgi/BBMergeOverlapper.java:98-136, :411-621,
+ * :785-836; useq=f), the minInsert cut, and TrimRead.trimToPosition(r, 0, bestInsert-1, 1) of both mates.
+ * Reads are paired (2i, 2i+1) and currently keep [lo,hi); pairs whose flags carry BBDUK_F_REMOVED are skipped.
+ * hi[] and flags[] (|= BBDUK_F_TBO) are updated in place; insert[n_reads/2] (may be NULL) receives the insert size
+ * used, -1 for none, -2 for ambiguous; stats2 += {readsTrimmedByOverlap, basesTrimmedByOverlap}.
+ * HOST buffers; quals has the layout of bases. Reads longer than 1008 bases after the k-mer block are an error. */
+BBDUK_API int bbduk_b200_tbo(bbduk_handle *h, const bbduk_tbo_cfg *cfg, const uint8_t *bases, const uint8_t *quals,
+                             const int64_t *offsets, int64_t n_reads, const int32_t *lo, int32_t *hi, uint8_t *flags,
+                             int32_t *insert, int64_t *stats2);
+
+/* Same on DEVICE buffers (32-bit offsets), asynchronous on `stream`; max_read_len = upper bound on the read lengths
+ * (<= 1008); d_stats2 = device int64[2] to accumulate into, may be NULL. */
+BBDUK_API int bbduk_b200_tbo_device(bbduk_handle *h, const bbduk_tbo_cfg *cfg, const uint8_t *d_bases, const uint8_t *d_quals,
+                                    const uint32_t *d_offsets, int64_t n_reads, int32_t max_read_len, const int32_t *d_lo,
+                                    int32_t *d_hi, uint8_t *d_flags, int32_t *d_insert, int64_t *d_stats2, void *stream);
 
 /* Host helper (no GPU needed): the 2-bit packing bbduk_b200_process applies to a chunk before it crosses PCIe when
  * the tuned kernel takes the whole chunk (set BBDUK_B200_PACK_HOST=0 to ship ASCII instead). F[i] = big-endian
