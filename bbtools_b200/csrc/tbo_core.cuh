@@ -1,0 +1,516 @@
+// tbo_core.cuh -- the per-pair arithmetic of BBDuk's trim-by-overlap step, written once for the device (tbo.cu, one lane
+// per pair, per-lane arrays interleaved in shared memory with stride S) and for a host build (S = 1) that the CPU tests
+// compare with the oracle, so that the bit-plane packing and the two insert loops can be checked without a GPU.
+//
+// Follows jgi/BBMergeOverlapper.java:411-621 (mateByOverlapRatioJava) and :785-836 (findBestRatio); single-precision
+// evaluation order kept (no contraction). The reference adds 0.95f per matching / mismatching base and leaves its
+// base loop once bad > badlimit. Those partial sums only grow, so "the loop ran to its end" <=> T[mismatches] <= badlimit
+// with T[c] = 0.95f added c times: the code COUNTS mismatches and looks the float sums up in T.
+//
+// Layout: every mate is held as bit planes, 32 bases per word, base i = bit 31-(i&31) of word i>>5 ("big-endian"):
+// H / L = the two bits of the base code, N = "the byte is 'N'". A mismatch word of 32 aligned bases is
+// (Ha^Hb)|(La^Lb): 2 logic ops + 1 popc per 32 bases. One of the two mates always starts at base 0 of an alignment
+// (insert >= blen: r2' from 0, r1 from insert-blen; insert < blen: r1 from 0, r2' from blen-insert), so only the other
+// one is funnel-shifted. Every alignment is first screened on its first 64 bases with the sliding mate held in
+// registers (prefix64): more mismatches there than the largest count any badlimit of the loop admits => skipped.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define TBO_HD __host__ __device__ __forceinline__
+#else
+#define TBO_HD static inline
+#endif
+
+namespace tbo {
+
+constexpr int MAX_LEN = 1008;
+constexpr int EXTRA_BADLIMIT = 20;  // jgi/BBMergeOverlapper.java:1464
+
+struct Params {
+    int minOverlap0, minOverlap, minInsert0, minInsert;  // BBDuk's values (jgi/BBDuk.java:5368-5371)
+    float maxRatio, minSecondRatio, margin, offset, meeFilter;
+    int qualOffset;
+    int W;  // words per bit plane per lane
+};
+
+// words per plane for reads of up to max_len bases: the sliding reads touch word (len-1)/32 + 2
+TBO_HD int plane_words(int max_len) { return (max_len + 31) / 32 + 3; }
+
+// (hi << s) | (lo >> (32 - s)), s taken mod 32
+TBO_HD uint32_t fsl(uint32_t lo, uint32_t hi, uint32_t s) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, s);
+#else
+    s &= 31u;
+    return s ? ((hi << s) | (lo >> (32u - s))) : hi;
+#endif
+}
+TBO_HD int popc(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+TBO_HD uint32_t brev(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __brev(x);
+#else
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
+    return __builtin_bswap32(x);
+#endif
+}
+TBO_HD uint32_t bperm(uint32_t a, uint32_t b, uint32_t s) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, s);
+#else
+    const uint64_t v = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) r |= (uint32_t)((v >> (8 * ((s >> (4 * i)) & 7u))) & 0xFFu) << (8 * i);
+    return r;
+#endif
+}
+TBO_HD float fmul(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fmul_rn(a, b);
+#else
+    volatile float r = a * b;
+    return r;
+#endif
+}
+TBO_HD float fadd(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fadd_rn(a, b);
+#else
+    volatile float r = a + b;
+    return r;
+#endif
+}
+TBO_HD float fdiv(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fdiv_rn(a, b);
+#else
+    volatile float r = a / b;
+    return r;
+#endif
+}
+TBO_HD int imin(int a, int b) { return a < b ? a : b; }
+TBO_HD int imax(int a, int b) { return a > b ? a : b; }
+// top `n` bits set (n clamped to [0,32]): the first n bases of a plane word
+TBO_HD uint32_t head_mask(int n) { return n >= 32 ? 0xFFFFFFFFu : (n <= 0 ? 0u : ~(0xFFFFFFFFu >> n)); }
+
+// ---- packing ----------------------------------------------------------------------------------------------------------
+// 16 aligned bytes at q as four little-endian words. The device reads them with one vector load (an aligned 16-byte
+// block that holds a valid byte lies inside the allocation); the host build only touches [v_lo, v_hi).
+TBO_HD void load_chunk(const uint8_t *q, uint32_t x[4], const uint8_t *v_lo, const uint8_t *v_hi) {
+#if defined(__CUDA_ARCH__)
+    (void)v_lo;
+    (void)v_hi;
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(q));
+    x[0] = v.x;
+    x[1] = v.y;
+    x[2] = v.z;
+    x[3] = v.w;
+#else
+    for (int k = 0; k < 4; k++) {
+        uint32_t w = 0;
+        for (int j = 0; j < 4; j++) {
+            const uint8_t *b = q + 4 * k + j;
+            if (b >= v_lo && b < v_hi) w |= (uint32_t)*b << (8 * j);
+        }
+        x[k] = w;
+    }
+#endif
+}
+
+// Raw planes of the aligned 16-byte chunks that cover p[0..len): stream position of base i = u0 + i, u0 = p & 15.
+// Bytes of the first / last chunk outside the read are replaced by 'A' (code 0, valid). Writes nw = ceil(chunks/2) words
+// per plane and zeroes the rest of the W words; returns nw. bad != 0 afterwards <=> some byte of the read is not one
+// of A C G T (GENERAL: ... and not N; n_any != 0 <=> some byte is N). tn is only written if GENERAL.
+//   code bits: bit0 = b1^b2, bit1 = b2^b3 of the ASCII byte (dna/AminoAcid.java:1289-1320 for A C G T);
+//   four byte lanes -> four plane bits with one multiply (all partial products land on distinct bits);
+//   validity: (b4,b2,b1) indexes an 8-entry table of the only byte that may sit there; PRMT does four lookups at once.
+template <bool GENERAL, int S>
+TBO_HD int pack_raw(const uint8_t *p, int len, uint32_t *th, uint32_t *tl, uint32_t *tn, int W, uint32_t &u0_out, uint32_t &bad,
+                    uint32_t &n_any) {
+    const uint32_t u0 = len > 0 ? (uint32_t)((uintptr_t)p & 15u) : 0u;
+    const uint8_t *q = p - u0;
+    const int nchunks = len > 0 ? (int)((u0 + (uint32_t)len + 15u) >> 4) : 0;
+    uint32_t ah = 0, al = 0, an = 0;
+    int wi = 0;
+    for (int c = 0; c < nchunks; c++) {
+        uint32_t x[4];
+        load_chunk(q + 16 * c, x, p, p + len);
+        if (c == 0 || c == nchunks - 1) {
+            for (int k = 0; k < 4; k++) {
+                uint32_t keep = 0;
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t pos = 16u * (uint32_t)c + 4u * (uint32_t)k + (uint32_t)j;
+                    if (pos >= u0 && pos < u0 + (uint32_t)len) keep |= 0xFFu << (8 * j);
+                }
+                x[k] = (x[k] & keep) | (0x41414141u & ~keep);
+            }
+        }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < 4; k++) {
+            uint32_t xx = x[k];
+            if (GENERAL) {
+                const uint32_t y = xx ^ 0x4E4E4E4Eu;                                     // zero byte <=> 'N'
+                const uint32_t z = ((y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | y;                // bit 7 of a lane <=> byte != 0
+                const uint32_t nb = (~z >> 7) & 0x01010101u;
+                an = fsl(nb * 0x80402010u, an, 4);
+                n_any |= nb;
+                xx ^= nb * 0x0Fu;  // 'N' -> 'A'
+            }
+            const uint32_t B1 = xx >> 1, B2 = xx >> 2, t = B1 ^ B2;
+            al = fsl((t & 0x01010101u) * 0x80402010u, al, 4);
+            ah = fsl((t & 0x02020202u) * 0x40201008u, ah, 4);
+            const uint32_t idx = (B1 & 0x03030303u) | (B2 & 0x04040404u);
+            const uint32_t sel = (idx | (idx >> 12)) & 0xFFFFu;  // nibbles: lane 0, lane 2, lane 1, lane 3
+            bad |= bperm(0x47004341u, 0x00540000u, sel) ^ bperm(xx, xx, 0x3120u);
+        }
+        if (c & 1) {
+            th[wi * S] = ah;
+            tl[wi * S] = al;
+            if (GENERAL) tn[wi * S] = an;
+            wi++;
+        }
+    }
+    if (nchunks & 1) {
+        th[wi * S] = ah << 16;
+        tl[wi * S] = al << 16;
+        if (GENERAL) tn[wi * S] = an << 16;
+        wi++;
+    }
+    const int nw = wi;
+    for (; wi < W; wi++) {
+        th[wi * S] = 0;
+        tl[wi * S] = 0;
+        if (GENERAL) tn[wi * S] = 0;
+    }
+    u0_out = u0;
+    return nw;
+}
+
+// plane of the read itself: base i -> bit i of the output (stream position u0 + i of the raw plane)
+template <int S>
+TBO_HD void finish_forward(const uint32_t *raw, uint32_t *out, int len, uint32_t u0, int W) {
+    uint32_t cur = raw[0];
+    for (int w = 0; w < W; w++) {
+        const uint32_t nxt = (w + 1 < W) ? raw[(w + 1) * S] : 0u;
+        out[w * S] = fsl(nxt, cur, u0) & head_mask(len - 32 * w);
+        cur = nxt;
+    }
+}
+
+// plane of the reverse(-complemented) read: out base j = raw base len-1-j, inverted if `complement` (3 - code = ~code)
+template <int S>
+TBO_HD void finish_reverse(const uint32_t *raw, uint32_t *out, int len, uint32_t u0, int nw, int W, bool complement) {
+    const int start = 32 * nw - (int)u0 - len;  // position of out base 0 in the reversed stream
+    const int w0 = start >> 5;
+    const uint32_t r = (uint32_t)start & 31u;
+    auto R = [&](int i) -> uint32_t { return (i < nw) ? brev(raw[(nw - 1 - i) * S]) : 0u; };
+    uint32_t cur = R(w0);
+    for (int w = 0; w < W; w++) {
+        const uint32_t nxt = R(w0 + w + 1);
+        uint32_t v = fsl(nxt, cur, r);
+        if (complement) v = ~v;
+        out[w * S] = v & head_mask(len - 32 * w);
+        cur = nxt;
+    }
+}
+
+// ---- counting ---------------------------------------------------------------------------------------------------------
+template <int S>
+struct Ctx {
+    const uint32_t *ah, *al, *an, *bh, *bl, *bn;  // planes of r1 (forward) and r2' (reverse complement); word w at [w * S]
+    // exact path: a mate holds a byte other than A C G T N, the reference compares raw bytes
+    const uint8_t *a_bytes;      // r1 trimmed, forward
+    const uint8_t *b_rev_bytes;  // r2 trimmed, LAST base (b[j] = comp[b_rev_bytes[-j]])
+    const uint8_t *comp;
+    bool exact;
+};
+
+// mismatches / non-N matches of a[istart..istart+ov) against b[jstart..jstart+ov); one of istart, jstart is 0.
+// Exact while T[nbad] <= badlimit; counting stops once it is exceeded (then ngood is not used).
+template <bool GENERAL, int S>
+TBO_HD void count_exact(const Ctx<S> &c, int istart, int jstart, int ov, float badlimit, const float *T, int &nbad, int &ngood) {
+    nbad = 0;
+    ngood = 0;
+    if (GENERAL && c.exact) {
+        for (int t = 0; t < ov; t++) {
+            const uint8_t ca = c.a_bytes[istart + t];
+            const uint8_t cb = c.comp[c.b_rev_bytes[-(jstart + t)] & 127];
+            if (ca == cb) {
+                if (ca != 'N') ngood++;
+            } else {
+                nbad++;
+                if (T[nbad] > badlimit) return;
+            }
+        }
+        return;
+    }
+    const bool slide_a = istart > 0;
+    const uint32_t *fh = slide_a ? c.bh : c.ah, *fl = slide_a ? c.bl : c.al, *fn = slide_a ? c.bn : c.an;
+    const uint32_t *sh = slide_a ? c.ah : c.bh, *sl = slide_a ? c.al : c.bl, *sn = slide_a ? c.an : c.bn;
+    const int s = slide_a ? istart : jstart;
+    int w = (s >> 5) * S;
+    const uint32_t r = (uint32_t)s & 31u;
+    uint32_t h_cur = sh[w], l_cur = sl[w], n_cur = GENERAL ? sn[w] : 0u;
+    for (int t = 0, tw = 0; t < ov; t += 32, tw += S) {
+        w += S;
+        const uint32_t h_nxt = sh[w], l_nxt = sl[w];
+        const uint32_t d = (fsl(h_nxt, h_cur, r) ^ fh[tw]) | (fsl(l_nxt, l_cur, r) ^ fl[tw]);
+        const uint32_t m = head_mask(ov - t);
+        if (GENERAL) {
+            const uint32_t n_nxt = sn[w];
+            const uint32_t na = fsl(n_nxt, n_cur, r), nb = fn[tw];
+            nbad += popc(((d & ~(na | nb)) | (na ^ nb)) & m);
+            ngood += popc(~d & ~(na | nb) & m);
+            n_cur = n_nxt;
+        } else {
+            nbad += popc(d & m);
+        }
+        h_cur = h_nxt;
+        l_cur = l_nxt;
+        if (T[nbad] > badlimit) return;
+    }
+    if (!GENERAL) ngood = ov - nbad;
+}
+
+// registers of the 64-base screen: the fixed mate's words 0,1 and the sliding mate's words w..w+2
+template <bool GENERAL>
+struct Pre {
+    uint32_t fh0, fh1, fl0, fl1, fn0, fn1;
+    uint32_t sh0, sh1, sh2, sl0, sl1, sl2, sn0, sn1, sn2;
+    int w;     // word index held in s*, -1 = none
+    int side;  // 0 = r1 slides, 1 = r2' slides, -1 = none
+};
+
+// mismatches (GENERAL: by the reference's N rules) among the first min(ov, 64) bases of the alignment
+template <bool GENERAL, int S>
+TBO_HD int prefix64(const Ctx<S> &c, Pre<GENERAL> &p, int istart, int jstart, int ov) {
+    const int side = istart > 0 ? 0 : 1;
+    const int s = istart > 0 ? istart : jstart;
+    const int w = s >> 5;
+    if (side != p.side) {
+        const uint32_t *fh = side == 0 ? c.bh : c.ah, *fl = side == 0 ? c.bl : c.al;
+        p.fh0 = fh[0];
+        p.fh1 = fh[S];
+        p.fl0 = fl[0];
+        p.fl1 = fl[S];
+        if (GENERAL) {
+            const uint32_t *fn = side == 0 ? c.bn : c.an;
+            p.fn0 = fn[0];
+            p.fn1 = fn[S];
+        }
+        p.side = side;
+        p.w = -1;
+    }
+    if (w != p.w) {
+        const uint32_t *sh = side == 0 ? c.ah : c.bh, *sl = side == 0 ? c.al : c.bl;
+        p.sh0 = sh[w * S];
+        p.sh1 = sh[(w + 1) * S];
+        p.sh2 = sh[(w + 2) * S];
+        p.sl0 = sl[w * S];
+        p.sl1 = sl[(w + 1) * S];
+        p.sl2 = sl[(w + 2) * S];
+        if (GENERAL) {
+            const uint32_t *sn = side == 0 ? c.an : c.bn;
+            p.sn0 = sn[w * S];
+            p.sn1 = sn[(w + 1) * S];
+            p.sn2 = sn[(w + 2) * S];
+        }
+        p.w = w;
+    }
+    const uint32_t r = (uint32_t)s & 31u;
+    uint32_t d0 = (fsl(p.sh1, p.sh0, r) ^ p.fh0) | (fsl(p.sl1, p.sl0, r) ^ p.fl0);
+    uint32_t d1 = (fsl(p.sh2, p.sh1, r) ^ p.fh1) | (fsl(p.sl2, p.sl1, r) ^ p.fl1);
+    if (GENERAL) {
+        const uint32_t na0 = fsl(p.sn1, p.sn0, r), na1 = fsl(p.sn2, p.sn1, r);
+        d0 = (d0 & ~(na0 | p.fn0)) | (na0 ^ p.fn0);
+        d1 = (d1 & ~(na1 | p.fn1)) | (na1 ^ p.fn1);
+    }
+    if (ov < 64) {
+        d0 &= head_mask(ov);
+        d1 &= head_mask(ov - 32);
+    }
+    return popc(d0) + popc(d1);
+}
+
+// largest count c with T[c] <= limit (T grows strictly; T[0] = 0 <= limit always holds for the limits used here)
+TBO_HD int cap_of(float limit, const float *T, int n_T) {
+    int c = (int)fdiv(limit, 0.95f) + 2;
+    if (c > n_T - 1) c = n_T - 1;
+    if (c < 0) c = 0;
+    while (c > 0 && T[c] > limit) c--;
+    return c;
+}
+
+// jgi/BBMergeOverlapper.java:785-836
+template <bool GENERAL, int S>
+TBO_HD float find_best_ratio(const Ctx<S> &c, int alen, int blen, int minOverlap0, int minOverlap, int minInsert,
+                             float maxRatio, float offset, const float *T, int n_T) {
+    float bestRatio = fadd(maxRatio, 0.0001f);
+    const float halfmax = fmul(maxRatio, 0.5f);
+    // badlimit never exceeds its value for the initial bestRatio and the longest overlap (rounding is monotone), so an
+    // alignment that shows more than cap_max mismatches on its first 64 bases fails every badlimit of this loop
+    const int cap_max = cap_of(fadd(fmul(bestRatio, (float)imin(alen, blen)), (float)EXTRA_BADLIMIT), T, n_T);
+    const bool screen = !(GENERAL && c.exact);
+    Pre<GENERAL> pre;
+    pre.w = -1;
+    pre.side = -1;
+    for (int insert = alen + blen - minOverlap; insert >= minInsert; insert--) {
+        const int istart = (insert <= blen ? 0 : insert - blen);
+        const int jstart = (insert >= blen ? 0 : blen - insert);
+        const int ov = imin(alen - istart, imin(blen - jstart, insert));
+        int nbad, ngood;
+        const float badlimit = fadd(fmul(bestRatio, (float)ov), (float)EXTRA_BADLIMIT);
+        if (screen) {
+            const int n64 = prefix64<GENERAL, S>(c, pre, istart, jstart, ov);
+            if (n64 > cap_max) continue;
+            if (!GENERAL && ov <= 64) {
+                nbad = n64;
+                ngood = ov - n64;
+            } else {
+                count_exact<GENERAL, S>(c, istart, jstart, ov, badlimit, T, nbad, ngood);
+            }
+        } else {
+            count_exact<GENERAL, S>(c, istart, jstart, ov, badlimit, T, nbad, ngood);
+        }
+        const float bad = T[nbad];
+        if (bad <= badlimit) {
+            const float good = T[ngood];
+            if (bad == 0.0f && good > (float)minOverlap0 && good < (float)minOverlap) return 100.0f;
+            const float ratio = fdiv(fadd(bad, offset), (float)ov);
+            if (ratio < bestRatio) {
+                bestRatio = ratio;
+                if (good >= (float)minOverlap && ratio < halfmax) return bestRatio;
+            }
+        }
+    }
+    return bestRatio;
+}
+
+// jgi/BBMergeOverlapper.java:411-621 (TAG_CUSTOM = MAKE_VECTOR = false); returns bestInsert, sets ambig
+// STAGE 0: both loops. STAGE 1: findBestRatio only; returns -3 and *x_io if the second loop has to run.
+// STAGE 2: the second loop, with findBestRatio's result handed in through *x_io.
+template <bool GENERAL, int STAGE, int S>
+TBO_HD int mate_by_overlap_ratio(const Ctx<S> &c, int alen, int blen, const Params &p, const float *T, int n_T, bool &ambig_out,
+                                 float *x_io) {
+    const int minOverlap = imax(4, imax(p.minOverlap0, p.minOverlap));
+    int minOverlap0;
+    {  // Tools.mid(4, minOverlap0, minOverlap): the median
+        const int x = 4, y = p.minOverlap0, z = minOverlap;
+        minOverlap0 = x < y ? (y < z ? y : imax(x, z)) : (x < z ? x : imax(y, z));
+    }
+    const int minLength = imin(alen, blen);
+    float maxRatio = p.maxRatio;
+    ambig_out = false;
+    {
+        float x;
+        if (STAGE == 2) x = *x_io;
+        else x = find_best_ratio<GENERAL, S>(c, alen, blen, minOverlap0, minOverlap, p.minInsert, maxRatio, p.offset, T, n_T);
+        if (x > maxRatio) return -1;  // rvector[4] = 0
+        if (STAGE == 1) {
+            *x_io = x;
+            return -3;
+        }
+        maxRatio = x < maxRatio ? x : maxRatio;
+    }
+    const float margin = p.margin, offset = p.offset;
+    const float margin2 = fdiv(fadd(margin, offset), (float)minLength);
+    int bestInsert = -1;
+    float bestRatio = 1.0f, secondBestRatio = 1.0f;
+    bool ambig = false;
+    // min(bestRatio, maxRatio) <= maxRatio and ov <= minLength: the screen's cap for this loop
+    const int cap_max =
+        cap_of(fadd(fadd(fmul(1.2f, fmul(fmul(maxRatio, margin), (float)minLength)), 1.0f), (float)EXTRA_BADLIMIT), T, n_T);
+    const bool screen = !(GENERAL && c.exact);
+    Pre<GENERAL> pre;
+    pre.w = -1;
+    pre.side = -1;
+    for (int insert = alen + blen - minOverlap0; insert >= p.minInsert0; insert--) {
+        const int istart = (insert <= blen ? 0 : insert - blen);
+        const int jstart = (insert >= blen ? 0 : blen - insert);
+        const int ov = imin(alen - istart, imin(blen - jstart, insert));
+        const float rmin = bestRatio < maxRatio ? bestRatio : maxRatio;
+        const float badlimit = fadd(fadd(fmul(1.2f, fmul(fmul(rmin, margin), (float)ov)), 1.0f), (float)EXTRA_BADLIMIT);
+        int nbad, ngood;
+        if (screen) {
+            const int n64 = prefix64<GENERAL, S>(c, pre, istart, jstart, ov);
+            if (n64 > cap_max) continue;
+            if (!GENERAL && ov <= 64) {
+                nbad = n64;
+                ngood = ov - n64;
+            } else {
+                count_exact<GENERAL, S>(c, istart, jstart, ov, badlimit, T, nbad, ngood);
+            }
+        } else {
+            count_exact<GENERAL, S>(c, istart, jstart, ov, badlimit, T, nbad, ngood);
+        }
+        const float bad = T[nbad];
+        if (bad <= badlimit) {
+            const float good = T[ngood];
+            if (bad == 0.0f && good > (float)minOverlap0 && good < (float)minOverlap) {
+                ambig_out = true;
+                return -1;
+            }
+            const float ratio = fdiv(fadd(bad, offset), (float)ov);
+            if (ratio < fmul(bestRatio, margin)) {
+                ambig = (fmul(ratio, margin) >= bestRatio || good < (float)minOverlap);
+                if (ratio < bestRatio) {
+                    secondBestRatio = bestRatio;
+                    bestInsert = insert;
+                    bestRatio = ratio;
+                } else if (ratio < secondBestRatio) {
+                    secondBestRatio = ratio;
+                }
+                if ((ambig && bestRatio < margin2) || secondBestRatio < p.minSecondRatio) {
+                    ambig_out = true;
+                    return -1;
+                }
+            }
+        }
+    }
+    if (!ambig && bestRatio > maxRatio) bestInsert = -1;
+    ambig_out = ambig;
+    return bestInsert;
+}
+
+// pack both mates of a pair into the lane's planes; arrays: planes[k * W * S], k = 0..5 (AH AL BH BL TH TL) and, if
+// GENERAL, 6..8 (AN BN TN). Returns bit 0 = a byte outside A C G T (GENERAL: outside A C G T N), bit 1 = an 'N' seen.
+template <bool GENERAL, int S>
+TBO_HD uint32_t pack_pair(const uint8_t *a, int alen, const uint8_t *b0, int blen, uint32_t *planes, int W, Ctx<S> &c) {
+    const int P = W * S;
+    uint32_t *ah = planes, *al = planes + P, *bh = planes + 2 * P, *bl = planes + 3 * P, *th = planes + 4 * P,
+             *tl = planes + 5 * P;
+    uint32_t *an = GENERAL ? planes + 6 * P : nullptr, *bn = GENERAL ? planes + 7 * P : nullptr,
+             *tn = GENERAL ? planes + 8 * P : nullptr;
+    uint32_t bad = 0, n_any = 0, u0;
+    int nw = pack_raw<GENERAL, S>(a, alen, th, tl, tn, W, u0, bad, n_any);
+    finish_forward<S>(th, ah, alen, u0, W);
+    finish_forward<S>(tl, al, alen, u0, W);
+    if (GENERAL) finish_forward<S>(tn, an, alen, u0, W);
+    nw = pack_raw<GENERAL, S>(b0, blen, th, tl, tn, W, u0, bad, n_any);
+    finish_reverse<S>(th, bh, blen, u0, nw, W, true);
+    finish_reverse<S>(tl, bl, blen, u0, nw, W, true);
+    if (GENERAL) finish_reverse<S>(tn, bn, blen, u0, nw, W, false);
+    c.ah = ah;
+    c.al = al;
+    c.an = an;
+    c.bh = bh;
+    c.bl = bl;
+    c.bn = bn;
+    c.a_bytes = a;
+    c.b_rev_bytes = b0 + blen - 1;
+    c.exact = GENERAL && bad != 0;
+    return (bad != 0 ? 1u : 0u) | (n_any != 0 ? 2u : 0u);
+}
+
+}  // namespace tbo
