@@ -83,14 +83,15 @@ tbo_kernel(const uint8_t *__restrict__ bases, const uint8_t *__restrict__ quals,
         if (run && (tbo::plane_words(alen) > W || tbo::plane_words(blen) > W)) run = false;  // guarded on the host: cannot happen
         if (run) {
             tbo::Ctx<S> c;
+            tbo::Cands<S> q;
             c.comp = comp;
-            const uint32_t what = tbo::pack_pair<GENERAL, S>(a, alen, b0, blen, planes, W, c);
+            const uint32_t what = tbo::pack_pair<GENERAL, S>(a, alen, b0, blen, planes, W, c, q);
             if (MODE == 0 && (what & 1u)) {  // an N or another byte: left to the general launch
                 list_g[atomicAdd(list_g_n, 1u)] = (int32_t)pair;
                 continue;
             }
             float x = MODE == 1 ? list_m_x[item] : 0.0f;
-            best = tbo::mate_by_overlap_ratio<GENERAL, MODE == 0 ? 1 : MODE == 1 ? 2 : 0, S>(c, alen, blen, p, T, n_T, ambig, &x);
+            best = tbo::mate_by_overlap_ratio<GENERAL, MODE == 0 ? 1 : MODE == 1 ? 2 : 0, S>(c, q, alen, blen, p, T, n_T, ambig, &x);
             if (MODE == 0 && best == -3) {  // the second loop runs in the compacted launch
                 const unsigned int w = atomicAdd(list_m_n, 1u);
                 list_m[w] = (int32_t)pair;
@@ -228,10 +229,10 @@ int launch_tbo(int device, int sm_count, const bbduk_tbo_cfg *cfg, const uint8_t
     p.qualOffset = cfg->qual_offset > 0 ? cfg->qual_offset : 33;
     p.W = tbo::plane_words(std::max(max_len, 16));
     const int n_T = TBO_MAX_LEN + 2;
-    // per lane: 6 planes (AH AL BH BL + 2 raw) in the A C G T launches, 9 (+ AN BN + 1 raw) in the general one
+    // per lane: 8 arrays (AH AL BH BL, 2 raw planes, 2 candidate bitmaps) in the A C G T launches, 11 (+ AN BN + 1 raw) in the general one
     const size_t smem_fixed = sizeof(float) * (n_T + 128) + 128;
-    const size_t smem6 = smem_fixed + sizeof(uint32_t) * 6 * (size_t)p.W * TBO_THREADS;
-    const size_t smem9 = smem_fixed + sizeof(uint32_t) * 9 * (size_t)p.W * TBO_THREADS;
+    const size_t smem6 = smem_fixed + sizeof(uint32_t) * tbo::N_PLANES_ACGT * (size_t)p.W * TBO_THREADS;
+    const size_t smem9 = smem_fixed + sizeof(uint32_t) * tbo::N_PLANES_GENERAL * (size_t)p.W * TBO_THREADS;
     if (cudaFuncSetAttribute(tbo_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6) != cudaSuccess ||
         cudaFuncSetAttribute(tbo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6) != cudaSuccess ||
         cudaFuncSetAttribute(tbo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem9) != cudaSuccess)

@@ -12,7 +12,7 @@
 // (Ha^Hb)|(La^Lb): 2 logic ops + 1 popc per 32 bases. One of the two mates always starts at base 0 of an alignment
 // (insert >= blen: r2' from 0, r1 from insert-blen; insert < blen: r1 from 0, r2' from blen-insert), so only the other
 // one is funnel-shifted. Every alignment is first screened on its first 64 bases with the sliding mate held in
-// registers (prefix64): more mismatches there than the largest count any badlimit of the loop admits => skipped.
+// registers (scan_side): more mismatches there than the largest count any badlimit of the loop admits => skipped.
 #pragma once
 #include <stdint.h>
 
@@ -34,8 +34,8 @@ struct Params {
     int W;  // words per bit plane per lane
 };
 
-// words per plane for reads of up to max_len bases: the sliding reads touch word (len-1)/32 + 2
-TBO_HD int plane_words(int max_len) { return (max_len + 31) / 32 + 3; }
+// words per plane for reads of up to max_len bases: the screen's sliding window touches word (len-1)/32 + 4
+TBO_HD int plane_words(int max_len) { return (max_len + 31) / 32 + 4; }
 
 // (hi << s) | (lo >> (32 - s)), s taken mod 32
 TBO_HD uint32_t fsl(uint32_t lo, uint32_t hi, uint32_t s) {
@@ -99,6 +99,8 @@ TBO_HD float fdiv(float a, float b) {
 }
 TBO_HD int imin(int a, int b) { return a < b ? a : b; }
 TBO_HD int imax(int a, int b) { return a > b ? a : b; }
+// 0xFF in the n lowest byte lanes (n clamped to [0,4])
+TBO_HD uint32_t low_bytes(int n) { return n >= 4 ? 0xFFFFFFFFu : (n <= 0 ? 0u : ((1u << (8 * n)) - 1u)); }
 // top `n` bits set (n clamped to [0,32]): the first n bases of a plane word
 TBO_HD uint32_t head_mask(int n) { return n >= 32 ? 0xFFFFFFFFu : (n <= 0 ? 0u : ~(0xFFFFFFFFu >> n)); }
 
@@ -145,12 +147,10 @@ TBO_HD int pack_raw(const uint8_t *p, int len, uint32_t *th, uint32_t *tl, uint3
         uint32_t x[4];
         load_chunk(q + 16 * c, x, p, p + len);
         if (c == 0 || c == nchunks - 1) {
+            // bytes [v0, v1) of this chunk belong to the read
+            const int v0 = imax((int)u0 - 16 * c, 0), v1 = imin((int)u0 + len - 16 * c, 16);
             for (int k = 0; k < 4; k++) {
-                uint32_t keep = 0;
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t pos = 16u * (uint32_t)c + 4u * (uint32_t)k + (uint32_t)j;
-                    if (pos >= u0 && pos < u0 + (uint32_t)len) keep |= 0xFFu << (8 * j);
-                }
+                const uint32_t keep = low_bytes(v1 - 4 * k) & ~low_bytes(v0 - 4 * k);
                 x[k] = (x[k] & keep) | (0x41414141u & ~keep);
             }
         }
@@ -283,64 +283,183 @@ TBO_HD void count_exact(const Ctx<S> &c, int istart, int jstart, int ov, float b
     if (!GENERAL) ngood = ov - nbad;
 }
 
-// registers of the 64-base screen: the fixed mate's words 0,1 and the sliding mate's words w..w+2
-template <bool GENERAL>
-struct Pre {
-    uint32_t fh0, fh1, fl0, fl1, fn0, fn1;
-    uint32_t sh0, sh1, sh2, sl0, sl1, sl2, sn0, sn1, sn2;
-    int w;     // word index held in s*, -1 = none
-    int side;  // 0 = r1 slides, 1 = r2' slides, -1 = none
+// ---- the screen ---------------------------------------------------------------------------------------------------------
+// Alignments are visited by falling insert size. While insert > blen r1 slides (from base s = insert - blen, s falling)
+// against r2' from base 0 ("side A"); afterwards r2' slides (from s = blen - insert, s rising) against r1 from base 0
+// ("side B"). The screen runs BEFORE the insert loops and out of their order: for every s of a side it counts the
+// mismatches (GENERAL: by the reference's N rules) among the first min(ov, 32*NW) bases and sets bit s of the lane's
+// candidate bitmap if they do not exceed `cap`, the largest count any badlimit of the coming loop admits. All lanes of a
+// warp walk the same (word, shift) sequence, so the warp stays on one code path whatever the lengths of its pairs:
+// per word index the fixed mate's NW words and the sliding mate's NW+1 words sit in registers and one alignment costs
+// 2*NW funnel shifts, 2*NW logic ops and NW popc. The insert loops then visit the set bits only.
+TBO_HD bool any_lane(bool p) {
+#if defined(__CUDA_ARCH__)
+    return __any_sync(__activemask(), p) != 0;  // a hint only: either answer is correct for every lane that votes true
+#else
+    return p;
+#endif
+}
+TBO_HD int clz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __clz((int)x);
+#else
+    return x ? __builtin_clz(x) : 32;
+#endif
+}
+TBO_HD int ffs32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x);
+#else
+    return __builtin_ffs((int)x);
+#endif
+}
+// head_mask without selects on the device: a right shift clamped at 32
+TBO_HD uint32_t head_mask_fast(int n) {
+#if defined(__CUDA_ARCH__)
+    return ~__funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t)imax(n, 0));
+#else
+    return head_mask(n);
+#endif
+}
+// bits r of word w whose position 32w + r lies in [lo, hi]
+TBO_HD uint32_t range_bits(int w, int lo, int hi) {
+    const int r_lo = imax(lo - 32 * w, 0), r_hi = imin(hi - 32 * w, 31);
+    if (r_lo > r_hi) return 0u;
+    return ((2u << r_hi) - 1u) & ~((1u << r_lo) - 1u);
+}
+
+template <bool GENERAL, int NW, bool MASKED>
+TBO_HD uint32_t scan_word(const uint32_t (&fh)[NW], const uint32_t (&fl)[NW], const uint32_t (&fn)[NW], const uint32_t (&vh)[NW + 1],
+                          const uint32_t (&vl)[NW + 1], const uint32_t (&vn)[NW + 1], int X, int Y, int s0, int cap) {
+    uint32_t bits = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 4
+#endif
+    for (uint32_t r = 0; r < 32; r++) {
+        int n = 0;
+        const int ov = MASKED ? imin(X - (s0 + (int)r), Y) : 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < NW; k++) {
+            uint32_t d = (fsl(vh[k + 1], vh[k], r) ^ fh[k]) | (fsl(vl[k + 1], vl[k], r) ^ fl[k]);
+            if (GENERAL) {
+                const uint32_t na = fsl(vn[k + 1], vn[k], r);
+                d = (d & ~(na | fn[k])) | (na ^ fn[k]);
+            }
+            if (MASKED) d &= head_mask_fast(ov - 32 * k);
+            n += popc(d);
+        }
+        bits |= (n <= cap ? 1u : 0u) << r;
+    }
+    return bits;
+}
+
+// candidate bits of one side for s in [s_lo, s_hi] (words s_lo>>5 .. s_hi>>5 of cand are written). X = length of the
+// sliding mate, Y = of the fixed one: ov(s) = min(X - s, Y).
+template <bool GENERAL, int S, int NW>
+TBO_HD void scan_side(const uint32_t *sh, const uint32_t *sl, const uint32_t *sn, const uint32_t *fhp, const uint32_t *flp,
+                      const uint32_t *fnp, int X, int Y, int s_lo, int s_hi, int cap, uint32_t *cand) {
+    if (s_hi < s_lo) return;
+    uint32_t fh[NW], fl[NW], fn[NW];
+    for (int k = 0; k < NW; k++) {
+        fh[k] = fhp[k * S];
+        fl[k] = flp[k * S];
+        fn[k] = GENERAL ? fnp[k * S] : 0u;
+    }
+    for (int w = s_lo >> 5; w <= (s_hi >> 5); w++) {
+        uint32_t vh[NW + 1], vl[NW + 1], vn[NW + 1];
+        for (int k = 0; k <= NW; k++) {
+            vh[k] = sh[(w + k) * S];
+            vl[k] = sl[(w + k) * S];
+            vn[k] = GENERAL ? sn[(w + k) * S] : 0u;
+        }
+        // the shortest overlap of the word is at its last s; unmasked only if no lane of the warp needs the masks
+        const bool masked = any_lane(imin(X - (32 * w + 31), Y) < 32 * NW);
+        const uint32_t bits = masked ? scan_word<GENERAL, NW, true>(fh, fl, fn, vh, vl, vn, X, Y, 32 * w, cap)
+                                     : scan_word<GENERAL, NW, false>(fh, fl, fn, vh, vl, vn, X, Y, 32 * w, cap);
+        cand[w * S] = bits & range_bits(w, s_lo, s_hi);
+    }
+}
+
+// the alignments of one insert loop (inserts i_top down to i_bot) as two runs of s, and their candidate bitmaps
+template <int S>
+struct Cands {
+    uint32_t *A, *B;   // bit s of side A / side B; word w at [w * S]
+    int a_lo, a_hi;    // side A: s = insert - blen in [a_lo, a_hi], visited from a_hi down
+    int b_lo, b_hi;    // side B: s = blen - insert in [b_lo, b_hi], visited from b_lo up
+    int phase, w;      // iterator: 0 = side A, 1 = side B, 2 = done
+    uint32_t bits;
 };
 
-// mismatches (GENERAL: by the reference's N rules) among the first min(ov, 64) bases of the alignment
 template <bool GENERAL, int S>
-TBO_HD int prefix64(const Ctx<S> &c, Pre<GENERAL> &p, int istart, int jstart, int ov) {
-    const int side = istart > 0 ? 0 : 1;
-    const int s = istart > 0 ? istart : jstart;
-    const int w = s >> 5;
-    if (side != p.side) {
-        const uint32_t *fh = side == 0 ? c.bh : c.ah, *fl = side == 0 ? c.bl : c.al;
-        p.fh0 = fh[0];
-        p.fh1 = fh[S];
-        p.fl0 = fl[0];
-        p.fl1 = fl[S];
-        if (GENERAL) {
-            const uint32_t *fn = side == 0 ? c.bn : c.an;
-            p.fn0 = fn[0];
-            p.fn1 = fn[S];
+TBO_HD void build_cands(const Ctx<S> &c, int alen, int blen, int i_top, int i_bot, int cap, Cands<S> &q) {
+    q.a_hi = i_top - blen;
+    q.a_lo = imax(1, i_bot - blen);
+    q.b_lo = imax(0, blen - i_top);
+    q.b_hi = blen - i_bot;
+    if (i_top < i_bot) {
+        q.a_hi = q.a_lo - 1;
+        q.b_hi = q.b_lo - 1;
+    }
+    const int longest = imin(alen, blen);
+    if ((GENERAL && c.exact) || cap >= imin(longest, 90)) {  // no screen: the byte path, or a cap the screen cannot beat
+        for (int w = imax(q.a_lo, 0) >> 5; w <= (q.a_hi >> 5) && q.a_hi >= q.a_lo; w++) q.A[w * S] = range_bits(w, q.a_lo, q.a_hi);
+        for (int w = q.b_lo >> 5; w <= (q.b_hi >> 5) && q.b_hi >= q.b_lo; w++) q.B[w * S] = range_bits(w, q.b_lo, q.b_hi);
+    } else if (cap <= 43) {
+        scan_side<GENERAL, S, 2>(c.ah, c.al, c.an, c.bh, c.bl, c.bn, alen, blen, q.a_lo, q.a_hi, cap, q.A);
+        scan_side<GENERAL, S, 2>(c.bh, c.bl, c.bn, c.ah, c.al, c.an, blen, alen, q.b_lo, q.b_hi, cap, q.B);
+    } else {
+        scan_side<GENERAL, S, 4>(c.ah, c.al, c.an, c.bh, c.bl, c.bn, alen, blen, q.a_lo, q.a_hi, cap, q.A);
+        scan_side<GENERAL, S, 4>(c.bh, c.bl, c.bn, c.ah, c.al, c.an, blen, alen, q.b_lo, q.b_hi, cap, q.B);
+    }
+    if (q.a_hi >= q.a_lo) {
+        q.phase = 0;
+        q.w = q.a_hi >> 5;
+        q.bits = q.A[q.w * S];
+    } else if (q.b_hi >= q.b_lo) {
+        q.phase = 1;
+        q.w = q.b_lo >> 5;
+        q.bits = q.B[q.w * S];
+    } else {
+        q.phase = 2;
+        q.w = 0;
+        q.bits = 0;
+    }
+}
+
+// next candidate in visiting order: returns false when there is none; else side (0 = A) and s
+template <int S>
+TBO_HD bool next_cand(Cands<S> &q, int &side, int &s) {
+    for (;;) {
+        if (q.phase == 2) return false;
+        if (q.bits) {
+            const int r = q.phase == 0 ? 31 - clz32(q.bits) : ffs32(q.bits) - 1;
+            q.bits &= ~(1u << r);
+            side = q.phase;
+            s = 32 * q.w + r;
+            return true;
         }
-        p.side = side;
-        p.w = -1;
-    }
-    if (w != p.w) {
-        const uint32_t *sh = side == 0 ? c.ah : c.bh, *sl = side == 0 ? c.al : c.bl;
-        p.sh0 = sh[w * S];
-        p.sh1 = sh[(w + 1) * S];
-        p.sh2 = sh[(w + 2) * S];
-        p.sl0 = sl[w * S];
-        p.sl1 = sl[(w + 1) * S];
-        p.sl2 = sl[(w + 2) * S];
-        if (GENERAL) {
-            const uint32_t *sn = side == 0 ? c.an : c.bn;
-            p.sn0 = sn[w * S];
-            p.sn1 = sn[(w + 1) * S];
-            p.sn2 = sn[(w + 2) * S];
+        if (q.phase == 0) {
+            if (q.w > (q.a_lo >> 5)) {
+                q.w--;
+                q.bits = q.A[q.w * S];
+            } else if (q.b_hi >= q.b_lo) {
+                q.phase = 1;
+                q.w = q.b_lo >> 5;
+                q.bits = q.B[q.w * S];
+            } else {
+                q.phase = 2;
+            }
+        } else {
+            if (q.w < (q.b_hi >> 5)) {
+                q.w++;
+                q.bits = q.B[q.w * S];
+            } else {
+                q.phase = 2;
+            }
         }
-        p.w = w;
     }
-    const uint32_t r = (uint32_t)s & 31u;
-    uint32_t d0 = (fsl(p.sh1, p.sh0, r) ^ p.fh0) | (fsl(p.sl1, p.sl0, r) ^ p.fl0);
-    uint32_t d1 = (fsl(p.sh2, p.sh1, r) ^ p.fh1) | (fsl(p.sl2, p.sl1, r) ^ p.fl1);
-    if (GENERAL) {
-        const uint32_t na0 = fsl(p.sn1, p.sn0, r), na1 = fsl(p.sn2, p.sn1, r);
-        d0 = (d0 & ~(na0 | p.fn0)) | (na0 ^ p.fn0);
-        d1 = (d1 & ~(na1 | p.fn1)) | (na1 ^ p.fn1);
-    }
-    if (ov < 64) {
-        d0 &= head_mask(ov);
-        d1 &= head_mask(ov - 32);
-    }
-    return popc(d0) + popc(d1);
 }
 
 // largest count c with T[c] <= limit (T grows strictly; T[0] = 0 <= limit always holds for the limits used here)
@@ -354,35 +473,22 @@ TBO_HD int cap_of(float limit, const float *T, int n_T) {
 
 // jgi/BBMergeOverlapper.java:785-836
 template <bool GENERAL, int S>
-TBO_HD float find_best_ratio(const Ctx<S> &c, int alen, int blen, int minOverlap0, int minOverlap, int minInsert,
+TBO_HD float find_best_ratio(const Ctx<S> &c, Cands<S> &q, int alen, int blen, int minOverlap0, int minOverlap, int minInsert,
                              float maxRatio, float offset, const float *T, int n_T) {
     float bestRatio = fadd(maxRatio, 0.0001f);
     const float halfmax = fmul(maxRatio, 0.5f);
     // badlimit never exceeds its value for the initial bestRatio and the longest overlap (rounding is monotone), so an
-    // alignment that shows more than cap_max mismatches on its first 64 bases fails every badlimit of this loop
+    // alignment that shows more than cap_max mismatches on its first bases fails every badlimit of this loop
     const int cap_max = cap_of(fadd(fmul(bestRatio, (float)imin(alen, blen)), (float)EXTRA_BADLIMIT), T, n_T);
-    const bool screen = !(GENERAL && c.exact);
-    Pre<GENERAL> pre;
-    pre.w = -1;
-    pre.side = -1;
-    for (int insert = alen + blen - minOverlap; insert >= minInsert; insert--) {
-        const int istart = (insert <= blen ? 0 : insert - blen);
-        const int jstart = (insert >= blen ? 0 : blen - insert);
+    build_cands<GENERAL, S>(c, alen, blen, alen + blen - minOverlap, minInsert, cap_max, q);
+    int side, s;
+    while (next_cand<S>(q, side, s)) {  // for (insert = alen + blen - minOverlap; insert >= minInsert; insert--), candidates only
+        const int insert = side == 0 ? s + blen : blen - s;
+        const int istart = side == 0 ? s : 0, jstart = side == 0 ? 0 : s;
         const int ov = imin(alen - istart, imin(blen - jstart, insert));
         int nbad, ngood;
         const float badlimit = fadd(fmul(bestRatio, (float)ov), (float)EXTRA_BADLIMIT);
-        if (screen) {
-            const int n64 = prefix64<GENERAL, S>(c, pre, istart, jstart, ov);
-            if (n64 > cap_max) continue;
-            if (!GENERAL && ov <= 64) {
-                nbad = n64;
-                ngood = ov - n64;
-            } else {
-                count_exact<GENERAL, S>(c, istart, jstart, ov, badlimit, T, nbad, ngood);
-            }
-        } else {
-            count_exact<GENERAL, S>(c, istart, jstart, ov, badlimit, T, nbad, ngood);
-        }
+        count_exact<GENERAL, S>(c, istart, jstart, ov, badlimit, T, nbad, ngood);
         const float bad = T[nbad];
         if (bad <= badlimit) {
             const float good = T[ngood];
@@ -401,8 +507,8 @@ TBO_HD float find_best_ratio(const Ctx<S> &c, int alen, int blen, int minOverlap
 // STAGE 0: both loops. STAGE 1: findBestRatio only; returns -3 and *x_io if the second loop has to run.
 // STAGE 2: the second loop, with findBestRatio's result handed in through *x_io.
 template <bool GENERAL, int STAGE, int S>
-TBO_HD int mate_by_overlap_ratio(const Ctx<S> &c, int alen, int blen, const Params &p, const float *T, int n_T, bool &ambig_out,
-                                 float *x_io) {
+TBO_HD int mate_by_overlap_ratio(const Ctx<S> &c, Cands<S> &q, int alen, int blen, const Params &p, const float *T, int n_T,
+                                 bool &ambig_out, float *x_io) {
     const int minOverlap = imax(4, imax(p.minOverlap0, p.minOverlap));
     int minOverlap0;
     {  // Tools.mid(4, minOverlap0, minOverlap): the median
@@ -415,7 +521,7 @@ TBO_HD int mate_by_overlap_ratio(const Ctx<S> &c, int alen, int blen, const Para
     {
         float x;
         if (STAGE == 2) x = *x_io;
-        else x = find_best_ratio<GENERAL, S>(c, alen, blen, minOverlap0, minOverlap, p.minInsert, maxRatio, p.offset, T, n_T);
+        else x = find_best_ratio<GENERAL, S>(c, q, alen, blen, minOverlap0, minOverlap, p.minInsert, maxRatio, p.offset, T, n_T);
         if (x > maxRatio) return -1;  // rvector[4] = 0
         if (STAGE == 1) {
             *x_io = x;
@@ -431,29 +537,16 @@ TBO_HD int mate_by_overlap_ratio(const Ctx<S> &c, int alen, int blen, const Para
     // min(bestRatio, maxRatio) <= maxRatio and ov <= minLength: the screen's cap for this loop
     const int cap_max =
         cap_of(fadd(fadd(fmul(1.2f, fmul(fmul(maxRatio, margin), (float)minLength)), 1.0f), (float)EXTRA_BADLIMIT), T, n_T);
-    const bool screen = !(GENERAL && c.exact);
-    Pre<GENERAL> pre;
-    pre.w = -1;
-    pre.side = -1;
-    for (int insert = alen + blen - minOverlap0; insert >= p.minInsert0; insert--) {
-        const int istart = (insert <= blen ? 0 : insert - blen);
-        const int jstart = (insert >= blen ? 0 : blen - insert);
+    build_cands<GENERAL, S>(c, alen, blen, alen + blen - minOverlap0, p.minInsert0, cap_max, q);
+    int side, s;
+    while (next_cand<S>(q, side, s)) {  // for (insert = alen + blen - minOverlap0; insert >= minInsert0; insert--), candidates only
+        const int insert = side == 0 ? s + blen : blen - s;
+        const int istart = side == 0 ? s : 0, jstart = side == 0 ? 0 : s;
         const int ov = imin(alen - istart, imin(blen - jstart, insert));
         const float rmin = bestRatio < maxRatio ? bestRatio : maxRatio;
         const float badlimit = fadd(fadd(fmul(1.2f, fmul(fmul(rmin, margin), (float)ov)), 1.0f), (float)EXTRA_BADLIMIT);
         int nbad, ngood;
-        if (screen) {
-            const int n64 = prefix64<GENERAL, S>(c, pre, istart, jstart, ov);
-            if (n64 > cap_max) continue;
-            if (!GENERAL && ov <= 64) {
-                nbad = n64;
-                ngood = ov - n64;
-            } else {
-                count_exact<GENERAL, S>(c, istart, jstart, ov, badlimit, T, nbad, ngood);
-            }
-        } else {
-            count_exact<GENERAL, S>(c, istart, jstart, ov, badlimit, T, nbad, ngood);
-        }
+        count_exact<GENERAL, S>(c, istart, jstart, ov, badlimit, T, nbad, ngood);
         const float bad = T[nbad];
         if (bad <= badlimit) {
             const float good = T[ngood];
@@ -483,15 +576,19 @@ TBO_HD int mate_by_overlap_ratio(const Ctx<S> &c, int alen, int blen, const Para
     return bestInsert;
 }
 
-// pack both mates of a pair into the lane's planes; arrays: planes[k * W * S], k = 0..5 (AH AL BH BL TH TL) and, if
-// GENERAL, 6..8 (AN BN TN). Returns bit 0 = a byte outside A C G T (GENERAL: outside A C G T N), bit 1 = an 'N' seen.
+// pack both mates of a pair into the lane's planes; arrays: planes[k * W * S], k = 0..7 (AH AL BH BL, two raw planes, the
+// two candidate bitmaps) and, if GENERAL, 8..10 (AN BN + a raw plane). Returns bit 0 = a byte outside A C G T (GENERAL:
+// outside A C G T N), bit 1 = an 'N' seen.
+constexpr int N_PLANES_ACGT = 8, N_PLANES_GENERAL = 11;
 template <bool GENERAL, int S>
-TBO_HD uint32_t pack_pair(const uint8_t *a, int alen, const uint8_t *b0, int blen, uint32_t *planes, int W, Ctx<S> &c) {
+TBO_HD uint32_t pack_pair(const uint8_t *a, int alen, const uint8_t *b0, int blen, uint32_t *planes, int W, Ctx<S> &c, Cands<S> &q) {
     const int P = W * S;
     uint32_t *ah = planes, *al = planes + P, *bh = planes + 2 * P, *bl = planes + 3 * P, *th = planes + 4 * P,
              *tl = planes + 5 * P;
-    uint32_t *an = GENERAL ? planes + 6 * P : nullptr, *bn = GENERAL ? planes + 7 * P : nullptr,
-             *tn = GENERAL ? planes + 8 * P : nullptr;
+    q.A = planes + 6 * P;
+    q.B = planes + 7 * P;
+    uint32_t *an = GENERAL ? planes + 8 * P : nullptr, *bn = GENERAL ? planes + 9 * P : nullptr,
+             *tn = GENERAL ? planes + 10 * P : nullptr;
     uint32_t bad = 0, n_any = 0, u0;
     int nw = pack_raw<GENERAL, S>(a, alen, th, tl, tn, W, u0, bad, n_any);
     finish_forward<S>(th, ah, alen, u0, W);

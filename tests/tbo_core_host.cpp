@@ -54,27 +54,28 @@ void tbo_host_process(const uint8_t *bases, const int64_t *offsets, int64_t n_re
         const int alen = hi[i1] - lo[i1], blen = hi[i2] - lo[i2];
         const int W = tbo::plane_words(std::max(std::max(alen, blen), 16));
         p.W = W;
-        std::vector<uint32_t> planes(9 * (size_t)W);
+        std::vector<uint32_t> planes(tbo::N_PLANES_GENERAL * (size_t)W);
         tbo::Ctx<1> c;
+        tbo::Cands<1> q;
         c.comp = comp;
         int best;
         bool ambig = false;
-        const uint32_t what = tbo::pack_pair<false, 1>(a, alen, b0, blen, planes.data(), W, c);
+        const uint32_t what = tbo::pack_pair<false, 1>(a, alen, b0, blen, planes.data(), W, c, q);
         if (what & 1u) {  // MODE 2
             path_counts[2]++;
-            tbo::pack_pair<true, 1>(a, alen, b0, blen, planes.data(), W, c);
+            tbo::pack_pair<true, 1>(a, alen, b0, blen, planes.data(), W, c, q);
             if (c.exact) path_counts[3]++;
             float x = 0;
-            best = tbo::mate_by_overlap_ratio<true, 0, 1>(c, alen, blen, p, T.data(), n_T, ambig, &x);
+            best = tbo::mate_by_overlap_ratio<true, 0, 1>(c, q, alen, blen, p, T.data(), n_T, ambig, &x);
         } else {  // MODE 0, then MODE 1 after a re-pack as on the device
             path_counts[0]++;
             float x = 0;
-            best = tbo::mate_by_overlap_ratio<false, 1, 1>(c, alen, blen, p, T.data(), n_T, ambig, &x);
+            best = tbo::mate_by_overlap_ratio<false, 1, 1>(c, q, alen, blen, p, T.data(), n_T, ambig, &x);
             if (best == -3) {
                 path_counts[1]++;
                 std::fill(planes.begin(), planes.end(), 0xDEADBEEFu);
-                tbo::pack_pair<false, 1>(a, alen, b0, blen, planes.data(), W, c);
-                best = tbo::mate_by_overlap_ratio<false, 2, 1>(c, alen, blen, p, T.data(), n_T, ambig, &x);
+                tbo::pack_pair<false, 1>(a, alen, b0, blen, planes.data(), W, c, q);
+                best = tbo::mate_by_overlap_ratio<false, 2, 1>(c, q, alen, blen, p, T.data(), n_T, ambig, &x);
             }
         }
         if (best < p.minInsert) best = -1;

@@ -81,7 +81,7 @@ def test_packing_matches_a_bytewise_restatement(host, reverse):
         if odd:
             seq[int(rng.integers(0, length))] = rng.choice(np.frombuffer(b"acgtnUuRYKM-.*@[`{", np.uint8))
         buf[start:start + length] = seq
-        W = (max(length, 16) + 31) // 32 + 3
+        W = (max(length, 16) + 31) // 32 + 4
         out = np.zeros(3 * W, np.uint32)
         what = host.tbo_host_pack(buf.ctypes.data, start, length, reverse, W, out.ctypes.data)
         assert bool(what & 1) == odd
