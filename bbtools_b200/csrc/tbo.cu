@@ -243,8 +243,8 @@ int launch_tbo(int device, int sm_count, const bbduk_tbo_cfg *cfg, const uint8_t
 #define TBO_ARGS d_bases, d_quals, d_offsets, n_pairs, d_lo, d_hi, d_flags, d_insert, p, tab.d_T, n_T, tab.d_pe, tab.d_comp, d_stats, \
                  tab.d_list, tab.d_list_n, tab.d_list_m, tab.d_list_x, tab.d_list_n + 1
     tbo_kernel<0><<<blocks, TBO_THREADS, smem6, st>>>(TBO_ARGS);
-    tbo_kernel<1><<<std::max(1, blocks / 2), TBO_THREADS, smem6, st>>>(TBO_ARGS);
-    tbo_kernel<2><<<std::max(1, blocks / 4), TBO_THREADS, smem9, st>>>(TBO_ARGS);
+    tbo_kernel<1><<<blocks, TBO_THREADS, smem6, st>>>(TBO_ARGS);
+    tbo_kernel<2><<<blocks, TBO_THREADS, smem9, st>>>(TBO_ARGS);
 #undef TBO_ARGS
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

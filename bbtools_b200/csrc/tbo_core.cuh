@@ -143,14 +143,19 @@ TBO_HD int pack_raw(const uint8_t *p, int len, uint32_t *th, uint32_t *tl, uint3
     const int nchunks = len > 0 ? (int)((u0 + (uint32_t)len + 15u) >> 4) : 0;
     uint32_t ah = 0, al = 0, an = 0;
     int wi = 0;
-    for (int c = 0; c < nchunks; c++) {
+    auto chunk = [&](int c, bool edge) {
         uint32_t x[4];
         load_chunk(q + 16 * c, x, p, p + len);
-        if (c == 0 || c == nchunks - 1) {
-            // bytes [v0, v1) of this chunk belong to the read
+        if (edge) {
+            // bytes [v0, v1) of this chunk belong to the read: bit j of m = byte j is kept
             const int v0 = imax((int)u0 - 16 * c, 0), v1 = imin((int)u0 + len - 16 * c, 16);
+            const uint32_t m = ((1u << v1) - 1u) & ~((1u << v0) - 1u);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
             for (int k = 0; k < 4; k++) {
-                const uint32_t keep = low_bytes(v1 - 4 * k) & ~low_bytes(v0 - 4 * k);
+                // nibble k -> 0xFF per kept byte lane (the partial products of the multiply land on distinct bits)
+                const uint32_t keep = ((((m >> (4 * k)) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
                 x[k] = (x[k] & keep) | (0x41414141u & ~keep);
             }
         }
@@ -180,7 +185,11 @@ TBO_HD int pack_raw(const uint8_t *p, int len, uint32_t *th, uint32_t *tl, uint3
             if (GENERAL) tn[wi * S] = an;
             wi++;
         }
-    }
+    };
+    // the first and the last chunk are peeled: every lane of a warp reaches them at the same point of the code
+    if (nchunks > 0) chunk(0, true);
+    for (int c = 1; c < nchunks - 1; c++) chunk(c, false);
+    if (nchunks > 1) chunk(nchunks - 1, true);
     if (nchunks & 1) {
         th[wi * S] = ah << 16;
         tl[wi * S] = al << 16;
@@ -321,6 +330,14 @@ TBO_HD uint32_t head_mask_fast(int n) {
     return head_mask(n);
 #endif
 }
+// head_mask for n >= 0 (a negative n gives all ones on the device, where the shift count clamps at 32)
+TBO_HD uint32_t head_mask_nonneg(int n) {
+#if defined(__CUDA_ARCH__)
+    return ~__funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t)n);
+#else
+    return n < 0 ? 0xFFFFFFFFu : head_mask(n);
+#endif
+}
 // bits r of word w whose position 32w + r lies in [lo, hi]
 TBO_HD uint32_t range_bits(int w, int lo, int hi) {
     const int r_lo = imax(lo - 32 * w, 0), r_hi = imin(hi - 32 * w, 31);
@@ -336,7 +353,8 @@ TBO_HD uint32_t scan_word(const uint32_t (&fh)[NW], const uint32_t (&fl)[NW], co
 #pragma unroll 4
 #endif
     for (uint32_t r = 0; r < 32; r++) {
-        int n = 0;
+        int n = -cap - 1;  // the sign bit of n after the counts says "at most cap mismatches"
+        // ov < 0 only for s beyond the side's range; those bits are cleared by the caller (range_bits)
         const int ov = MASKED ? imin(X - (s0 + (int)r), Y) : 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -347,10 +365,10 @@ TBO_HD uint32_t scan_word(const uint32_t (&fh)[NW], const uint32_t (&fl)[NW], co
                 const uint32_t na = fsl(vn[k + 1], vn[k], r);
                 d = (d & ~(na | fn[k])) | (na ^ fn[k]);
             }
-            if (MASKED) d &= head_mask_fast(ov - 32 * k);
+            if (MASKED) d &= (k == 0) ? head_mask_nonneg(ov) : head_mask_fast(ov - 32 * k);
             n += popc(d);
         }
-        bits |= (n <= cap ? 1u : 0u) << r;
+        bits = (bits >> 1) | ((uint32_t)n & 0x80000000u);  // after 32 steps bit r holds the verdict of shift r
     }
     return bits;
 }
