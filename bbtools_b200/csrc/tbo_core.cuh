@@ -1,6 +1,6 @@
 // tbo_core.cuh -- the per-pair arithmetic of BBDuk's trim-by-overlap step, written once for the device (tbo.cu, one lane
 // per pair, per-lane arrays interleaved in shared memory with stride S) and for a host build (S = 1) that the CPU tests
-// compare with the oracle, so that the bit-plane packing and the two insert loops can be checked without a GPU.
+// check (tests/test_tbo_core_cpu.py), so that the bit-plane packing and the two insert loops can be verified without a GPU.
 //
 // Follows jgi/BBMergeOverlapper.java:411-621 (mateByOverlapRatioJava) and :785-836 (findBestRatio); single-precision
 // evaluation order kept (no contraction). The reference adds 0.95f per matching / mismatching base and leaves its

@@ -60,6 +60,14 @@ public final class BBDukIndexGPU extends BBDukIndex {
 		return processNative(handle, bases, offsets, nReads, paired, id0, lo, hi, flags, count, stats8)==0;
 	}
 
+	/** Trim by overlap for the batch processBatch() just answered (replaces bbduk/BBDukProcessorS.java:1096-1143):
+	 * hi[] / flags[] are updated in place; stats2 += {readsTrimmedByOverlap, basesTrimmedByOverlap}. */
+	public boolean tboBatch(boolean strictOverlap, int minOverlap0, int minOverlap, int minInsert0, int minInsert, float meeFilter,
+			byte[] bases, byte[] quals, long[] offsets, long nReads, int[] lo, int[] hi, byte[] flags, int[] insert, long[] stats2){
+		final int[] cfg={strictOverlap ? 1 : 0, minOverlap0, minOverlap, minInsert0, minInsert, 33};
+		return tboNative(handle, cfg, meeFilter, bases, quals, offsets, nReads, lo, hi, flags, insert, stats2)==0;
+	}
+
 	@Override public int getValue(long kmer, long rkmer, long lengthMask, int qPos, int len, int qHDist){
 		throw new UnsupportedOperationException("per-k-mer queries are served in batches by processBatch()");
 	}
@@ -71,6 +79,8 @@ public final class BBDukIndexGPU extends BBDukIndex {
 	private static native long finalizeNative(long h);
 	private static native int processNative(long h, byte[] bases, long[] offsets, long nReads, boolean paired,
 			int[] id0, int[] lo, int[] hi, byte[] flags, int[] count, long[] stats8);
+	private static native int tboNative(long h, int[] cfg, float meeFilter, byte[] bases, byte[] quals, long[] offsets, long nReads,
+			int[] lo, int[] hi, byte[] flags, int[] insert, long[] stats2);
 	private static native int scaffoldCountsNative(long h, long[] reads, long[] bases);
 	private static native String lastErrorNative(long h);
 	private static native void destroyNative(long h);

@@ -76,6 +76,54 @@ JNIEXPORT jint JNICALL Java_bbduk_BBDukIndexGPU_processNative(JNIEnv *env, jclas
     return rc;
 }
 
+/* Replaces the tbo block of BBDukProcessorS.processList (bbduk/BBDukProcessorS.java:1096-1143 = jgi/BBDuk.java:2878-2926)
+ * for the batch that processNative just answered: hi[] and flags[] are updated in place, insert[] (may be null) gets
+ * the insert size used per pair (-1 none, -2 ambiguous), stats2 += {readsTrimmedByOverlap, basesTrimmedByOverlap}.
+ * tboCfg = {strictOverlap, minOverlap0, minOverlap, minInsert0, minInsert, qualOffset} (-1 / 0 = the reference's
+ * defaults), meeFilter 0 = default. quals may be null (reads without qualities). */
+JNIEXPORT jint JNICALL Java_bbduk_BBDukIndexGPU_tboNative(JNIEnv *env, jclass cls, jlong handle, jintArray jcfg, jfloat meeFilter,
+                                                          jbyteArray jbases, jbyteArray jquals, jlongArray joffsets, jlong nReads,
+                                                          jintArray jlo, jintArray jhi, jbyteArray jflags, jintArray jinsert,
+                                                          jlongArray jstats2) {
+    bbduk_tbo_cfg cfg;
+    jint c[6];
+    int64_t st[2] = {0, 0};
+    bbduk_b200_tbo_cfg_default(&cfg);
+    (*env)->GetIntArrayRegion(env, jcfg, 0, 6, c);
+    cfg.strict_overlap = c[0];
+    cfg.min_overlap0 = c[1];
+    cfg.min_overlap = c[2];
+    cfg.min_insert0 = c[3];
+    cfg.min_insert = c[4];
+    cfg.qual_offset = c[5];
+    cfg.mee_filter = meeFilter;
+    jbyte *b = (jbyte *)(*env)->GetPrimitiveArrayCritical(env, jbases, NULL);
+    jbyte *q = jquals ? (jbyte *)(*env)->GetPrimitiveArrayCritical(env, jquals, NULL) : NULL;
+    jlong *o = (jlong *)(*env)->GetPrimitiveArrayCritical(env, joffsets, NULL);
+    jint *lo = (jint *)(*env)->GetPrimitiveArrayCritical(env, jlo, NULL);
+    jint *hi = (jint *)(*env)->GetPrimitiveArrayCritical(env, jhi, NULL);
+    jbyte *fl = (jbyte *)(*env)->GetPrimitiveArrayCritical(env, jflags, NULL);
+    jint *ins = jinsert ? (jint *)(*env)->GetPrimitiveArrayCritical(env, jinsert, NULL) : NULL;
+    const jint rc = bbduk_b200_tbo((bbduk_handle *)(intptr_t)handle, &cfg, (const uint8_t *)b, (const uint8_t *)q,
+                                   (const int64_t *)o, (int64_t)nReads, (const int32_t *)lo, (int32_t *)hi, (uint8_t *)fl,
+                                   (int32_t *)ins, st);
+    if (jinsert) (*env)->ReleasePrimitiveArrayCritical(env, jinsert, ins, 0);
+    (*env)->ReleasePrimitiveArrayCritical(env, jflags, fl, 0);
+    (*env)->ReleasePrimitiveArrayCritical(env, jhi, hi, 0);
+    (*env)->ReleasePrimitiveArrayCritical(env, jlo, lo, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, joffsets, o, JNI_ABORT);
+    if (jquals) (*env)->ReleasePrimitiveArrayCritical(env, jquals, q, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, jbases, b, JNI_ABORT);
+    if (jstats2 && !rc) {
+        jlong v[2];
+        (*env)->GetLongArrayRegion(env, jstats2, 0, 2, v);
+        v[0] += st[0];
+        v[1] += st[1];
+        (*env)->SetLongArrayRegion(env, jstats2, 0, 2, v);
+    }
+    return rc;
+}
+
 JNIEXPORT jint JNICALL Java_bbduk_BBDukIndexGPU_scaffoldCountsNative(JNIEnv *env, jclass cls, jlong handle,
                                                                      jlongArray jreads, jlongArray jbases) {
     const jint n = (*env)->GetArrayLength(env, jreads);

@@ -11,6 +11,7 @@ typedef int32_t jint;
 typedef int64_t jlong;
 typedef int8_t jbyte;
 typedef uint8_t jboolean;
+typedef float jfloat;
 typedef jint jsize;
 typedef struct _jobject *jobject;
 typedef jobject jclass;
@@ -32,5 +33,7 @@ struct JNINativeInterface_ {
     void (*ReleasePrimitiveArrayCritical)(JNIEnv *env, jarray array, void *carray, jint mode);
     jstring (*NewStringUTF)(JNIEnv *env, const char *utf);
     void (*SetLongArrayRegion)(JNIEnv *env, jlongArray array, jsize start, jsize len, const jlong *buf);
+    void (*GetLongArrayRegion)(JNIEnv *env, jlongArray array, jsize start, jsize len, jlong *buf);
+    void (*GetIntArrayRegion)(JNIEnv *env, jintArray array, jsize start, jsize len, jint *buf);
 };
 #endif
