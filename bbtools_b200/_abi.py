@@ -91,6 +91,20 @@ class BBDukTboCfg(C.Structure):
     ]
 
 
+class BBDukQtrimCfg(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32),
+        ("qtrim_left", C.c_int32),
+        ("qtrim_right", C.c_int32),
+        ("trimq", C.c_float),
+        ("min_base_quality", C.c_int32),
+        ("max_ns", C.c_int32),
+        ("max_read_length", C.c_int32),
+        ("qual_offset", C.c_int32),
+        ("reserved", C.c_int32 * 4),
+    ]
+
+
 class BBDukStats(C.Structure):
     _fields_ = [
         ("reads_in", C.c_int64),

@@ -36,7 +36,9 @@ def parse_args(args, generation=GEN_JGI):
     cfg = default_cfg()
     cfg.generation = generation
     io = {"in1": None, "in2": None, "out1": None, "out2": None, "outm1": None, "outm2": None, "ref": [],
-          "literal": [], "stats": None, "interleaved": None, "ordered": generation == GEN_S, "ottm": False}
+          "literal": [], "stats": None, "interleaved": None, "ordered": generation == GEN_S, "ottm": False,
+          "tbo": False, "strictoverlap": True, "minoverlap": -1, "mininsert": -1,
+          "qtrim_left": False, "qtrim_right": False, "trimq": 6.0, "mbq": 0, "maxns": -1, "maxlen": 0}
     for arg in args:
         sp = arg.split("=")
         a = sp[0].lower()
@@ -195,9 +197,43 @@ def parse_args(args, generation=GEN_JGI):
             cfg.require_both_bad = not _parse_boolean(b)
         elif a in ("trimfailures", "trimfailuresto1bp"):
             cfg.trim_failures_to_1bp = _parse_boolean(b)
-        elif a in ("tbo", "trimbyoverlap"):
+        elif a in ("tbo", "trimbyoverlap"):  # jgi/BBDuk.java:380-393
+            io["tbo"] = _parse_boolean(b)
+        elif a == "strictoverlap":
+            io["strictoverlap"] = _parse_boolean(b)
+        elif a == "minoverlap":
+            io["minoverlap"] = int(b)
+        elif a == "mininsert":
+            io["mininsert"] = int(b)
+        elif a == "qtrim":  # parse/Parser.java:347-367 (window mode is not on the device path)
+            v = (b or "").lower()
+            if v == "":
+                io["qtrim_left"] = io["qtrim_right"] = True
+            elif v in ("left", "l"):
+                io["qtrim_left"], io["qtrim_right"] = True, False
+            elif v in ("right", "r"):
+                io["qtrim_left"], io["qtrim_right"] = False, True
+            elif v in ("both", "rl", "lr"):
+                io["qtrim_left"] = io["qtrim_right"] = True
+            elif v.startswith("w"):
+                raise NotImplementedError("qtrim=window is not on the device path")
+            else:
+                io["qtrim_left"] = io["qtrim_right"] = _parse_boolean(b)
+        elif a in ("trimright", "qtrimright"):
+            io["qtrim_right"] = _parse_boolean(b)
+        elif a in ("trimleft", "qtrimleft"):
+            io["qtrim_left"] = _parse_boolean(b)
+        elif a in ("trimq", "trimquality"):
+            io["trimq"] = float(b)
+        elif a in ("minbasequality", "mbq"):
+            io["mbq"] = int(b)
+        elif a == "maxns":
+            io["maxns"] = int(b)
+        elif a in ("maxlength", "maxreadlength", "maxreadlen", "maxlen"):
+            io["maxlen"] = int(b)
+        elif a == "usequality":
             if _parse_boolean(b):
-                raise NotImplementedError("tbo (BBMergeOverlapper) stays on the host in this tier (SURVEY.md 8f row 2)")
+                raise NotImplementedError("usequality=t (quality-weighted overlap) is not on the device path")
         else:
             raise ValueError(f"Unknown parameter {arg}")
     return cfg, io
@@ -364,6 +400,36 @@ class BBDukIndexGPU:
                                                    max_read_len, ptr(d_lo), ptr(d_hi), ptr(d_flags), ptr(d_insert), ptr(d_stats),
                                                    ptr(stream)), "tbo_device")
 
+    # -- quality trimming + quality / length / N filters (jgi/BBDuk.java:3074-3170) ---------------------
+    def qtrim_cfg(self, **kw):
+        from ._abi import BBDukQtrimCfg
+        c = BBDukQtrimCfg()
+        self.lib.bbduk_b200_qtrim_cfg_default(C.byref(c))
+        for k, v in kw.items():
+            setattr(c, k, v)
+        return c
+
+    def qtrim(self, bases, quals, offsets, paired, out, cfg):
+        """HOST buffers; `out` is the Outputs of process() (after tbo): lo / hi / flags are updated in place.
+        -> [readsQTrimmed, basesQTrimmed, readsQFiltered, basesQFiltered, readsNFiltered, basesNFiltered]"""
+        bases = np.ascontiguousarray(bases, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        q = None if quals is None else np.ascontiguousarray(quals, np.uint8)
+        st = np.zeros(6, np.int64)
+        self._check(self.lib.bbduk_b200_qtrim(self.h, C.byref(cfg), bases.ctypes.data, None if q is None else q.ctypes.data,
+                                              offsets.ctypes.data, len(offsets) - 1, int(bool(paired)), out.lo.ctypes.data,
+                                              out.hi.ctypes.data, out.flags.ctypes.data, st.ctypes.data), "qtrim")
+        return st
+
+    def qtrim_device(self, d_bases, d_quals, d_offsets, n_reads, paired, d_lo, d_hi, d_flags, cfg, d_stats=None, stream=None):
+        def ptr(x):
+            if x is None:
+                return None
+            return x.data_ptr() if hasattr(x, "data_ptr") else int(x)
+        self._check(self.lib.bbduk_b200_qtrim_device(self.h, C.byref(cfg), ptr(d_bases), ptr(d_quals), ptr(d_offsets), n_reads,
+                                                     int(bool(paired)), ptr(d_lo), ptr(d_hi), ptr(d_flags), ptr(d_stats),
+                                                     ptr(stream)), "qtrim_device")
+
     def set_max_read_len(self, n):
         self._check(self.lib.bbduk_b200_set_max_read_len(self.h, int(n)), "set_max_read_len")
 
@@ -404,6 +470,8 @@ class BBDuk:
             self.index.add_ref(b, off)
         self.stored_kmers = self.index.finalize()
         self.stats = None
+        self.tbo_stats = None  # [readsTrimmedByOverlap, basesTrimmedByOverlap]
+        self.qtrim_stats = None  # [readsQTrimmed, basesQTrimmed, readsQFiltered, basesQFiltered, readsNFiltered, basesNFiltered]
 
     def process_arrays(self, bases, offsets, paired):
         want_mask = bool(self.cfg.ktrim_n)
@@ -419,6 +487,11 @@ class BBDuk:
         bases, offsets = fb.arrays()
         out, st = self.process_arrays(bases, offsets, paired)
         self.stats = st
+        quals = fb.quals() if ((io["tbo"] and paired) or self._wants_qtrim()) else None
+        if io["tbo"] and paired:
+            self.tbo_stats = self._tbo(bases, quals, offsets, out)
+        if self._wants_qtrim():
+            self.qtrim_stats = self._qtrim(bases, quals, offsets, paired, out)
         for removed, p1, p2 in ((False, io["out1"], io["out2"]), (True, io["outm1"], io["outm2"])):
             if not p1:
                 continue
@@ -427,6 +500,24 @@ class BBDuk:
                           trim_removed=bool(io["ottm"])).tofile(path)
         self._write_stats()
         return st
+
+    def _tbo(self, bases, quals, offsets, out):
+        """the tbo block (jgi/BBDuk.java:2878-2926) on the batch the k-mer block just answered; updates out.hi / out.flags"""
+        io = self.io
+        cfg = self.index.tbo_cfg(strict_overlap=int(io["strictoverlap"]), min_overlap=io["minoverlap"], min_insert=io["mininsert"])
+        _, st = self.index.tbo(bases, quals, offsets, out, cfg)
+        return st
+
+    def _wants_qtrim(self):
+        io = self.io
+        return bool(io["qtrim_left"] or io["qtrim_right"] or io["mbq"] > 0 or io["maxns"] >= 0 or io["maxlen"] > 0 or io["tbo"])
+
+    def _qtrim(self, bases, quals, offsets, paired, out):
+        """quality trimming, minlen / maxlen, mbq, maxns (jgi/BBDuk.java:3074-3170); updates out.lo / out.hi / out.flags"""
+        io = self.io
+        cfg = self.index.qtrim_cfg(qtrim_left=int(io["qtrim_left"]), qtrim_right=int(io["qtrim_right"]), trimq=io["trimq"],
+                                   min_base_quality=io["mbq"], max_ns=io["maxns"], max_read_length=io["maxlen"])
+        return self.index.qtrim(bases, quals, offsets, paired, out, cfg)
 
     def _write_stats(self):
         io = self.io
@@ -457,6 +548,10 @@ class BBDuk:
         bases, offsets = pack(seqs)
         out, st = self.process_arrays(bases, offsets, paired)
         self.stats = st
+        if io["tbo"] and paired:
+            self.tbo_stats = self._tbo(bases, pack(quals)[0], offsets, out)
+        if self._wants_qtrim():
+            self.qtrim_stats = self._qtrim(bases, pack(quals)[0], offsets, paired, out)
         sinks = {}
 
         def sink(path):

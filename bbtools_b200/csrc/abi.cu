@@ -853,6 +853,110 @@ int bbduk_b200_tbo(bbduk_handle *h, const bbduk_tbo_cfg *cfg, const uint8_t *bas
     return rc;
 }
 
+void bbduk_b200_qtrim_cfg_default(bbduk_qtrim_cfg *c) {
+    if (!c) return;
+    memset(c, 0, sizeof *c);
+    c->struct_size = (int32_t)sizeof *c;
+    c->trimq = 6.0f;  // jgi/BBDuk.java:126
+    c->max_ns = -1;
+    c->qual_offset = 33;
+}
+
+static int check_qtrim_cfg(bbduk_handle *h, const bbduk_qtrim_cfg *cfg, const void *quals) {
+    if (!cfg || cfg->struct_size != (int32_t)sizeof *cfg) return set_err(h, "bad bbduk_qtrim_cfg");
+    if ((cfg->qtrim_left || cfg->qtrim_right || cfg->min_base_quality > 0) && !quals)
+        return set_err(h, "qtrim / mbq need quality bytes (reads without qualities have no device path here)");
+    if (cfg->qual_offset < 0 || cfg->qual_offset > 127) return set_err(h, "bad qual_offset");
+    return 0;
+}
+
+int bbduk_b200_qtrim_device(bbduk_handle *h, const bbduk_qtrim_cfg *cfg, const uint8_t *d_bases, const uint8_t *d_quals,
+                            const uint32_t *d_offsets, int64_t n_reads, int32_t paired, int32_t *d_lo, int32_t *d_hi,
+                            uint8_t *d_flags, int64_t *d_stats6, void *stream) {
+    if (!h) return set_err(nullptr, "handle is NULL");
+    if (check_qtrim_cfg(h, cfg, d_quals)) return 1;
+    if (n_reads < 0 || (paired && (n_reads & 1))) return set_err(h, "bad n_reads (paired input needs an even count)");
+    if (n_reads == 0) return 0;
+    if (!d_bases || !d_offsets || !d_lo || !d_hi || !d_flags) return set_err(h, "NULL input");
+    if ((reinterpret_cast<uintptr_t>(d_bases) & 15) || (reinterpret_cast<uintptr_t>(d_quals) & 15))
+        return set_err(h, "d_bases and d_quals must be 16-byte aligned");
+    CKH(cudaSetDevice(h->device));
+    if (launch_qtrim(h->sm_count, cfg, h->p, d_bases, d_quals, d_offsets, n_reads, paired ? 1 : 0, d_lo, d_hi, d_flags,
+                     reinterpret_cast<unsigned long long *>(d_stats6), (cudaStream_t)stream))
+        return set_err(h, std::string("qtrim kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    h->launches += 1;
+    return 0;
+}
+
+int bbduk_b200_qtrim(bbduk_handle *h, const bbduk_qtrim_cfg *cfg, const uint8_t *bases, const uint8_t *quals,
+                     const int64_t *offsets, int64_t n_reads, int32_t paired, int32_t *lo, int32_t *hi, uint8_t *flags,
+                     int64_t *stats6) {
+    if (!h) return set_err(nullptr, "handle is NULL");
+    if (check_qtrim_cfg(h, cfg, quals)) return 1;
+    if (n_reads < 0 || (paired && (n_reads & 1))) return set_err(h, "bad n_reads (paired input needs an even count)");
+    if (n_reads == 0) return 0;
+    if (!bases || !offsets || !lo || !hi || !flags) return set_err(h, "NULL input");
+    CKH(cudaSetDevice(h->device));
+    std::lock_guard<std::mutex> g(h->tbo_mu);  // shares the staging of the tbo entry point
+    cudaStream_t st = nullptr;
+    int64_t *d_stats = nullptr;
+    CKH(cudaMalloc(&d_stats, 6 * sizeof(int64_t)));
+    CKH(cudaMemset(d_stats, 0, 6 * sizeof(int64_t)));
+    int rc = 0;
+    int64_t r0 = 0;
+    const int per = paired ? 2 : 1;
+    std::vector<uint32_t> off32;
+    while (r0 < n_reads && !rc) {
+        int64_t r1 = std::min(n_reads, r0 + (CHUNK_READS << 1));
+        while (r1 > r0 + per && offsets[r1] - offsets[r0] > CHUNK_BYTES) r1 = r0 + std::max<int64_t>(per, ((r1 - r0) / 2 / per) * per);
+        const int64_t nr = r1 - r0, nb = offsets[r1] - offsets[r0];
+        if (nb < 0 || nb >= (1ll << 32) - 64) {
+            rc = set_err(h, "a read (pair) exceeds 4 GiB (or offsets decrease)");
+            break;
+        }
+        off32.resize(nr + 1);
+        for (int64_t i = 0; i <= nr; i++) off32[i] = (uint32_t)(offsets[r0 + i] - offsets[r0]);
+        auto need = [&](void **p, int64_t *cap, int64_t bytes) -> int {
+            if (bytes <= *cap) return 0;
+            cudaFree(*p);
+            *p = nullptr;
+            *cap = bytes + bytes / 8 + 4096;
+            return cudaMalloc(p, (size_t)*cap) == cudaSuccess ? 0 : 1;
+        };
+        auto &tb = h->tbo;
+        if (need((void **)&tb.d_bases, &tb.cap_bases, nb + 64) || (quals && need((void **)&tb.d_quals, &tb.cap_quals, nb + 64)) ||
+            need((void **)&tb.d_off, &tb.cap_off, 4 * (nr + 1)) || need((void **)&tb.d_lo, &tb.cap_lo, 4 * nr) ||
+            need((void **)&tb.d_hi, &tb.cap_hi, 4 * nr) || need((void **)&tb.d_flags, &tb.cap_flags, nr)) {
+            rc = set_err(h, "qtrim: device allocation failed");
+            break;
+        }
+#define CKQ(call)                                                                       \
+    if (!rc && (call) != cudaSuccess) rc = set_err(h, std::string(#call " failed: ") + cudaGetErrorString(cudaGetLastError()))
+        CKQ(cudaMemcpyAsync(tb.d_bases, bases + offsets[r0], (size_t)nb, cudaMemcpyHostToDevice, st));
+        if (quals) CKQ(cudaMemcpyAsync(tb.d_quals, quals + offsets[r0], (size_t)nb, cudaMemcpyHostToDevice, st));
+        CKQ(cudaMemcpyAsync(tb.d_off, off32.data(), 4 * (size_t)(nr + 1), cudaMemcpyHostToDevice, st));
+        CKQ(cudaMemcpyAsync(tb.d_lo, lo + r0, 4 * (size_t)nr, cudaMemcpyHostToDevice, st));
+        CKQ(cudaMemcpyAsync(tb.d_hi, hi + r0, 4 * (size_t)nr, cudaMemcpyHostToDevice, st));
+        CKQ(cudaMemcpyAsync(tb.d_flags, flags + r0, (size_t)nr, cudaMemcpyHostToDevice, st));
+        if (!rc)
+            rc = bbduk_b200_qtrim_device(h, cfg, tb.d_bases, quals ? tb.d_quals : nullptr, tb.d_off, nr, paired, tb.d_lo, tb.d_hi,
+                                         tb.d_flags, d_stats, st);
+        CKQ(cudaMemcpyAsync(lo + r0, tb.d_lo, 4 * (size_t)nr, cudaMemcpyDeviceToHost, st));
+        CKQ(cudaMemcpyAsync(hi + r0, tb.d_hi, 4 * (size_t)nr, cudaMemcpyDeviceToHost, st));
+        CKQ(cudaMemcpyAsync(flags + r0, tb.d_flags, (size_t)nr, cudaMemcpyDeviceToHost, st));
+        CKQ(cudaStreamSynchronize(st));
+#undef CKQ
+        r0 = r1;
+    }
+    if (!rc && stats6) {
+        int64_t v[6] = {0, 0, 0, 0, 0, 0};
+        if (cudaMemcpy(v, d_stats, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) rc = set_err(h, "qtrim: stats copy failed");
+        for (int i = 0; i < 6; i++) stats6[i] += v[i];
+    }
+    cudaFree(d_stats);
+    return rc;
+}
+
 int bbduk_b200_pack_bases(const uint8_t *bases, int64_t n, uint32_t *F, uint16_t *D) {
     if (n < 0 || (n > 0 && (!bases || !F || !D))) return set_err(nullptr, "bad pack_bases arguments");
     pack_bases(bases, n, F, D);

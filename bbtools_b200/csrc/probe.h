@@ -47,3 +47,8 @@ int launch_epilogue(const uint8_t *d_bases, const uint32_t *d_offsets, int64_t n
 int launch_tbo(int device, int sm_count, const bbduk_tbo_cfg *cfg, const uint8_t *d_bases, const uint8_t *d_quals,
                const uint32_t *d_offsets, int64_t n_reads, int max_len, const int32_t *d_lo, int32_t *d_hi, uint8_t *d_flags,
                int32_t *d_insert, unsigned long long *d_stats, cudaStream_t st);
+
+// quality trimming + quality / length / N filters (qtrim.cu); 0 ok, 1 CUDA failure
+int launch_qtrim(int sm_count, const bbduk_qtrim_cfg *cfg, const BBParams &bp, const uint8_t *d_bases, const uint8_t *d_quals,
+                 const uint32_t *d_offsets, int64_t n_reads, int paired, int32_t *d_lo, int32_t *d_hi, uint8_t *d_flags,
+                 unsigned long long *d_stats, cudaStream_t st);

@@ -71,6 +71,19 @@ class FastqBatch:
             raise RuntimeError("fastq_b200_gather failed")
         return bases, offsets
 
+    def quals(self):
+        """quality bytes in the layout of arrays()[0] (the same gather with the records pointed at their quality lines)"""
+        rq = self.rec.copy()
+        rq[1::4] = self.rec[3::4]
+        offsets = np.zeros(self.n_reads + 1, np.int64)
+        self.lib.fastq_b200_gather(self.text1.ctypes.data, self._t2(), rq.ctypes.data, self.n_reads, None,
+                                   offsets.ctypes.data, self.threads)
+        q = np.empty(int(offsets[-1]), np.uint8)
+        if self.lib.fastq_b200_gather(self.text1.ctypes.data, self._t2(), rq.ctypes.data, self.n_reads, q.ctypes.data,
+                                      offsets.ctypes.data, self.threads):
+            raise RuntimeError("fastq_b200_gather failed")
+        return q
+
     def format(self, per, lo, hi, flags, removed=False, mate_sel=0, trim_removed=False) -> np.ndarray:
         """FASTQ text of the kept (or removed) units, trimmed to [lo,hi)"""
         lo = np.ascontiguousarray(lo, np.int32)

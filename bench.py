@@ -436,6 +436,55 @@ def run_ours(args):
         tbo_info = {"reads_per_s": world * n_reads * t_steps / (float(tt.item()) * 1e-3), "ms_per_step": float(tt.item()) / t_steps,
                     "reads_trimmed_by_overlap_per_step": int(d_tst[0].item()) // (t_steps + 1)}
 
+    # ---- the quality-trimming block (qtrim=rl trimq=10) on the same batch, timed alone ----
+    qtrim_info = None
+    if args.workload == "cfg2":
+        g = torch.Generator(device=dev)
+        g.manual_seed(5 + rank)
+        posn = (torch.arange(n_reads * L, device=dev, dtype=torch.int32) % L)
+        slope = torch.randint(0, 45, (n_reads * L,), device=dev, dtype=torch.int32, generator=g)
+        d_quals = (torch.clamp(40 - (posn * slope) // L + torch.randint(-3, 4, (n_reads * L,), device=dev, dtype=torch.int32, generator=g),
+                               2, 41) + 33).to(torch.uint8)
+        del posn, slope
+        qcfg = eng.qtrim_cfg(qtrim_left=1, qtrim_right=1, trimq=10.0)
+        d_qst = torch.zeros(6, dtype=torch.int64, device=dev)
+        q_lo = torch.zeros(n_reads, dtype=torch.int32, device=dev)
+        q_hi = torch.full((n_reads,), L, dtype=torch.int32, device=dev)
+        q_fl = torch.zeros(n_reads, dtype=torch.uint8, device=dev)
+        q_steps = max(3, min(args.steps, 10))
+
+        def step_q(i):
+            d_bases, d_off = bufs[i % nbuf]
+            q_lo.zero_()
+            q_hi.fill_(L)
+            q_fl.zero_()
+            eng.qtrim_device(d_bases, d_quals, d_off, n_reads, True, q_lo, q_hi, q_fl, qcfg, d_qst, stream=stream.cuda_stream)
+        with torch.cuda.stream(stream):
+            step_q(0)
+        barrier()
+        qe = [torch.cuda.Event(enable_timing=True) for _ in range(2 * q_steps)]
+        with torch.cuda.stream(stream):
+            for i in range(q_steps):
+                d_bases, d_off = bufs[(i + 1) % nbuf]
+                q_lo.zero_()
+                q_hi.fill_(L)
+                q_fl.zero_()
+                qe[2 * i].record(stream)
+                eng.qtrim_device(d_bases, d_quals, d_off, n_reads, True, q_lo, q_hi, q_fl, qcfg, d_qst, stream=stream.cuda_stream)
+                qe[2 * i + 1].record(stream)
+        barrier()
+        q_ms = statistics.mean(qe[2 * i].elapsed_time(qe[2 * i + 1]) for i in range(q_steps))
+        tq = torch.tensor([q_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tq, op=dist.ReduceOp.MAX)
+        q_ms = float(tq.item())
+        q_bytes = 2 * L + 4 + 9 + 9  # bases + qualities + offset in; lo, hi, flags in and out
+        peak_q, _ = load_peak()
+        qtrim_info = {"reads_per_s": world * n_reads / (q_ms * 1e-3), "ms_per_launch": q_ms, "algorithmic_bytes_per_read": q_bytes,
+                      "hbm_frac": n_reads * q_bytes / (q_ms * 1e-3) / 1e9 / peak_q,
+                      "reads_qtrimmed_per_launch": int(d_qst[0].item()) // (q_steps + 1)}
+        del d_quals
+
     # ---- end to end through the C ABI with pinned host buffers ------------------------------------
     e_pairs = args.e2e_pairs
     e_reads = 2 * e_pairs
@@ -518,7 +567,8 @@ def run_ours(args):
             "config": {"workload": wl["desc"], "pairs_per_step_per_gpu": n_pairs, "read_len": L,
                        "stored_kmers": stored, "l2": f"inputs {n_reads * L / 2**20:.0f} MiB per step > 126 MB L2, "
                        f"{nbuf} alternating buffers, no flush", "table_build_s": round(t_build, 3),
-                       "parity_vs_oracle_on_timed_batch": parity, "kmer_block_plus_tbo": tbo_info},
+                       "parity_vs_oracle_on_timed_batch": parity, "kmer_block_plus_tbo": tbo_info,
+                       "qtrim_block": qtrim_info},
             "e2e": {"value": e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "pairs_per_step_per_gpu": e_pairs, "steps": e_steps},
             "gpu_launches": int(launches),

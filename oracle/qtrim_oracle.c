@@ -1,0 +1,234 @@
+/*
+ * qtrim_oracle.c -- CPU restatement of BBDuk's quality-trimming block and the per-read quality / length / N filters
+ * (first part).
+ *
+ * TEST INFRASTRUCTURE ONLY: linked by tests/, never by bbtools_b200/. PARITY UNPINNED: the reference ships no golden
+ * vectors for this step and there is no JVM here. Pinned only by an independent Python restatement in
+ * tests/test_qtrim_oracle.py.
+ *
+ * Follows, statement by statement (paths relative to /root/reference/current):
+ *   jgi/BBDuk.java:3074-3108            "Do quality trimming": trimFast of r1 and r2, minlen / maxlen, shouldRemove
+ *   jgi/BBDuk.java:3110-3170            "Do quality filtering": minbasequality, maxns, shouldRemove (minavgquality,
+ *                                       maxnrate, minconsecutivebases, minbasefrequency at their defaults = off)
+ *   jgi/BBDuk.java:3260-3289            setDiscarded, isDiscarded, isNullOrDiscarded, isNotDiscarded, shouldRemove
+ *   shared/TrimRead.java:140-169        trimFast (optimalMode=true :954, discardUnder=0)
+ *   shared/TrimRead.java:348-410        testOptimal (NPROB=0.75f :964)
+ *   shared/TrimRead.java:299-346        trimByAmount
+ *   parse/Parser.java:1757-1759, align2/QualityTools.java:650-654, :688-698   trimE, PROB_ERROR
+ *   stream/Read.java:2281-2289, :2835-2844   minQuality, countUndefined
+ * All arithmetic is IEEE single precision in the reference's evaluation order (compile with -ffp-contract=off).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+typedef struct qtrim_params {
+    int32_t qtrim_left, qtrim_right;
+    float trimq;
+    int32_t min_base_quality, max_ns, max_read_length, qual_offset;
+    /* from the BBDuk configuration */
+    int32_t min_read_length;
+    float min_len_fraction;
+    int32_t remove_pairs_if_either_bad, trim_failures_to_1bp;
+} qtrim_params;
+
+static float g_pe[128];
+static int g_pe_ready = 0;
+
+static void init_pe(void) {
+    if (g_pe_ready) return;
+    for (int i = 0; i < 128; i++) g_pe[i] = (float)pow(10.0, 0 - .1 * i); /* align2/QualityTools.java:688-698 */
+    g_pe[0] = .75f;
+    g_pe[1] = .7f;
+    g_pe_ready = 1;
+}
+
+/* align2/QualityTools.java:650-654 */
+static double phred_to_prob_error(double q) {
+    if (q <= 0) return 0.75;
+    if (q <= 1) return 0.75 - q * 0.05;
+    const double p = pow(10, -0.1 * q);
+    return p < 0.7 ? p : 0.7;
+}
+
+typedef struct qread {
+    const uint8_t *bases, *quals; /* the read's first base / quality byte (untrimmed) */
+    int lo, hi;                   /* the interval it currently keeps */
+    int discarded;
+} qread;
+
+static int is_defined(uint8_t b) { /* dna/AminoAcid.java:1289-1320 baseToNumber >= 0 */
+    const uint8_t y = (uint8_t)(b | 0x20);
+    return b < 128 && (y == 'a' || y == 'c' || y == 'g' || y == 't' || y == 'u');
+}
+
+/* shared/TrimRead.java:299-346 on the kept interval */
+static int trim_by_amount(qread *r, int left, int right, int min_len) {
+    if (left < 0) left = 0;
+    if (right < 0) right = 0;
+    const int len = r->hi - r->lo;
+    if (len < 1) return 0;
+    if (min_len < 0) min_len = 0;
+    if (min_len > len) min_len = len;
+    if (left + right + min_len > len) {
+        right = (len - min_len) > 1 ? (len - min_len) : 1;
+        left = 0;
+    }
+    r->lo += left;
+    r->hi -= right;
+    return left + right;
+}
+
+/* shared/TrimRead.java:348-410; quality bytes are (byte)(ascii - qual_offset) */
+static void test_optimal(const qread *r, float avg_error_rate, int qual_offset, int *left_out, int *right_out) {
+    const int n = r->hi - r->lo;
+    const uint8_t *bases = r->bases + r->lo, *qual = r->quals + r->lo;
+    float maxScore = 0, score = 0;
+    int maxLoc = -1, maxCount = -1, count = 0;
+    float nprob = avg_error_rate * 1.1f;
+    if (nprob > 1) nprob = 1;
+    if (nprob < 0.75f) nprob = 0.75f;
+    for (int i = 0; i < n; i++) {
+        const uint8_t b = bases[i];
+        const int8_t q = (int8_t)(qual[i] - qual_offset);
+        const float probError = (b == 'N' || q < 1) ? nprob : g_pe[q];
+        const float delta = avg_error_rate - probError;
+        score = score + delta;
+        if (score > 0) {
+            count++;
+            if (score > maxScore || (score == maxScore && count > maxCount)) {
+                maxScore = score;
+                maxCount = count;
+                maxLoc = i;
+            }
+        } else {
+            score = 0;
+            count = 0;
+        }
+    }
+    if (maxScore > 0) {
+        *left_out = maxLoc - maxCount + 1;
+        *right_out = n - maxLoc - 1;
+    } else {
+        *left_out = 0;
+        *right_out = n;
+    }
+}
+
+/* shared/TrimRead.java:140-169 with optimalMode, discardUnder = 0, trimClip = false */
+static int trim_fast(qread *r, const qtrim_params *p, float trimE) {
+    if (r->hi - r->lo < 1) return 0;
+    int a0, b0;
+    test_optimal(r, trimE, p->qual_offset, &a0, &b0);
+    return trim_by_amount(r, p->qtrim_left ? a0 : 0, p->qtrim_right ? b0 : 0, 1);
+}
+
+static void set_discarded(const qtrim_params *p, qread *r) { /* jgi/BBDuk.java:3260-3266 */
+    if (p->trim_failures_to_1bp) {
+        if (r->hi - r->lo > 1) trim_by_amount(r, 0, r->hi - r->lo - 1, 1);
+    } else {
+        r->discarded = 1;
+    }
+}
+static int is_discarded(const qtrim_params *p, const qread *r) {
+    if (!r) return 0;
+    if (r->discarded) return 1;
+    return p->trim_failures_to_1bp && (r->hi - r->lo) == 1;
+}
+static int is_null_or_discarded(const qtrim_params *p, const qread *r) { return !r || is_discarded(p, r); }
+static int is_not_discarded(const qtrim_params *p, const qread *r) { return r && !is_discarded(p, r); }
+static int should_remove(const qtrim_params *p, const qread *r1, const qread *r2) {
+    return (p->remove_pairs_if_either_bad && (is_discarded(p, r1) || is_discarded(p, r2))) ||
+           (is_discarded(p, r1) && is_null_or_discarded(p, r2));
+}
+
+/*
+ * For every unit (read, or pair 2i / 2i+1) of a batch that went through the k-mer block: reads keep [lo,hi) of their
+ * original bases; flags bit 0x01 = discarded, 0x02 = unit removed. lo / hi / flags are updated in place (0x40 = quality
+ * trimmed); stats[0..5] += readsQTrimmed, basesQTrimmed, readsQFiltered, basesQFiltered, readsNFiltered, basesNFiltered.
+ */
+void qtrim_ora_process(const uint8_t *bases, const uint8_t *quals, const int64_t *offsets, int64_t n_reads, int paired,
+                       int32_t *lo, int32_t *hi, uint8_t *flags, const qtrim_params *p, int64_t *stats) {
+    init_pe();
+    const float trimE = (float)phred_to_prob_error(p->trimq);
+    const int per = paired ? 2 : 1;
+    const int max_len = p->max_read_length > 0 ? p->max_read_length : 0x7FFFFFFF;
+    for (int64_t u = 0; u + per <= n_reads; u += per) {
+        if (flags[u] & 0x02) continue; /* remove */
+        qread rr[2];
+        int minlen[2];
+        for (int q = 0; q < per; q++) {
+            const int64_t i = u + q;
+            rr[q].bases = bases + offsets[i];
+            rr[q].quals = quals ? quals + offsets[i] : NULL;
+            rr[q].lo = lo[i];
+            rr[q].hi = hi[i];
+            rr[q].discarded = (flags[i] & 0x01) != 0;
+            const float initial = (float)(offsets[i + 1] - offsets[i]);
+            const float a = initial * p->min_len_fraction, b = (float)p->min_read_length;
+            minlen[q] = (int)(a > b ? a : b); /* jgi/BBDuk.java:2587-2593 */
+        }
+        qread *r1 = &rr[0], *r2 = per == 2 ? &rr[1] : NULL;
+        int remove = 0;
+        int qtrimmed[2] = {0, 0};
+        /* :3074-3108 */
+        if (p->qtrim_left || p->qtrim_right) {
+            for (int q = 0; q < per; q++) {
+                const int x = trim_fast(&rr[q], p, trimE);
+                stats[1] += x;
+                stats[0] += (x > 0 ? 1 : 0);
+                qtrimmed[q] = x > 0;
+            }
+        }
+        for (int q = 0; q < per; q++) {
+            if (is_not_discarded(p, &rr[q])) {
+                const int len = rr[q].hi - rr[q].lo;
+                if (len < minlen[q] || len > max_len) set_discarded(p, &rr[q]);
+            }
+        }
+        if (should_remove(p, r1, r2)) {
+            stats[1] += (r1->hi - r1->lo) + (r2 ? r2->hi - r2->lo : 0); /* basesQTrimmedT+=r1.pairLength() */
+            remove = 1;
+        }
+        /* :3110-3170 */
+        if (!remove) {
+            if (p->min_base_quality > 0) {
+                for (int q = 0; q < per; q++) {
+                    if (!rr[q].quals) continue;
+                    int mn = 41;
+                    for (int i = rr[q].lo; i < rr[q].hi; i++) {
+                        const int8_t v = (int8_t)(rr[q].quals[i] - p->qual_offset);
+                        if (v < mn) mn = v;
+                    }
+                    if (mn < p->min_base_quality) set_discarded(p, &rr[q]);
+                }
+            }
+            if (p->max_ns >= 0) {
+                for (int q = 0; q < per; q++) {
+                    int n = 0;
+                    for (int i = rr[q].lo; i < rr[q].hi; i++) n += is_defined(rr[q].bases[i]) ? 0 : 1;
+                    if (n > p->max_ns) {
+                        stats[4] += 1;
+                        stats[5] += rr[q].hi - rr[q].lo;
+                        set_discarded(p, &rr[q]);
+                    }
+                }
+            }
+            if (should_remove(p, r1, r2)) {
+                stats[3] += (r1->hi - r1->lo) + (r2 ? r2->hi - r2->lo : 0);
+                stats[2] += per;
+                remove = 1;
+            }
+        }
+        for (int q = 0; q < per; q++) {
+            const int64_t i = u + q;
+            lo[i] = rr[q].lo;
+            hi[i] = rr[q].hi;
+            uint8_t f = (uint8_t)(flags[i] & ~0x03);
+            if (rr[q].discarded) f |= 0x01;
+            if (remove) f |= 0x02;
+            if (qtrimmed[q]) f |= 0x40;
+            flags[i] = f;
+        }
+    }
+}

@@ -36,6 +36,7 @@ def test_index_and_gather_match_python(crlf, final_nl, threads):
     bases, offsets = fb.arrays()
     assert np.array_equal(np.diff(offsets), [len(s) for s in seqs])
     assert bytes(bases) == b"".join(seqs)
+    assert bytes(fb.quals()) == b"".join(quals)
     rec = fb.rec.reshape(-1, 4)
     t = bytes(text)
     for i in (0, 1, 17, 2500, 4999):

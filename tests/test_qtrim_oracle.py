@@ -1,0 +1,218 @@
+"""CPU test of the quality-trimming / quality-filter oracle (oracle/qtrim_oracle.c) against an independently written
+Python restatement of jgi/BBDuk.java:3074-3170 + shared/TrimRead.java:140-169, :299-410 that finds the kept run by
+enumerating prefix sums with numpy float32 instead of the reference's running-score loop."""
+import numpy as np
+import pytest
+
+from oracle import qtrim as oq
+
+F32 = np.float32
+PE = np.array([10.0 ** (0 - .1 * i) for i in range(128)]).astype(F32)
+PE[0], PE[1] = F32(.75), F32(.7)
+
+
+def trim_e(q):
+    if q <= 0:
+        return F32(0.75)
+    if q <= 1:
+        return F32(0.75 - q * 0.05)
+    return F32(min(0.7, 10.0 ** (-0.1 * q)))
+
+
+def py_test_optimal(bases, q, e):
+    """(left, right) of shared/TrimRead.java:348-410: Kadane over delta = e - probError, ties to the longer run"""
+    n = len(bases)
+    nprob = F32(max(min(F32(e * F32(1.1)), F32(1)), F32(0.75)))
+    best, best_loc, best_cnt = F32(0), -1, -1
+    score, count = F32(0), 0
+    for i in range(n):
+        pe = nprob if (bases[i] == ord("N") or q[i] < 1) else PE[q[i]]
+        score = F32(score + F32(e - pe))
+        if score > 0:
+            count += 1
+            if score > best or (score == best and count > best_cnt):
+                best, best_cnt, best_loc = score, count, i
+        else:
+            score, count = F32(0), 0
+    if best > 0:
+        return best_loc - best_cnt + 1, n - best_loc - 1
+    return 0, n
+
+
+def trim_by_amount(lo, hi, left, right, m):
+    left, right = max(left, 0), max(right, 0)
+    n = hi - lo
+    if n < 1:
+        return lo, hi, 0
+    m = min(n, max(m, 0))
+    if left + right + m > n:
+        right, left = max(1, n - m), 0
+    return lo + left, hi - right, left + right
+
+
+def py_block(bases, quals, offsets, paired, lo, hi, flags, p):
+    lo, hi, flags = lo.copy(), hi.copy(), flags.copy()
+    st = np.zeros(6, np.int64)
+    e = trim_e(p.trimq)
+    per = 2 if paired else 1
+    tf1, rieb = bool(p.trim_failures_to_1bp), bool(p.remove_pairs_if_either_bad)
+    maxlen = p.max_read_length if p.max_read_length > 0 else 2 ** 31 - 1
+
+    def disc(i, state):
+        return state[i] or (tf1 and hi[i] - lo[i] == 1)
+
+    for u in range(0, len(offsets) - per, per):
+        if flags[u] & 2:
+            continue
+        idx = list(range(u, u + per))
+        state = {i: bool(flags[i] & 1) for i in idx}
+        qt = {i: False for i in idx}
+
+        def set_discarded(i):
+            if tf1:
+                if hi[i] - lo[i] > 1:
+                    lo[i], hi[i], _ = trim_by_amount(lo[i], hi[i], 0, hi[i] - lo[i] - 1, 1)
+            else:
+                state[i] = True
+
+        def should_remove():
+            d = [disc(i, state) for i in idx]
+            return (rieb and any(d)) or all(d)
+
+        if p.qtrim_left or p.qtrim_right:
+            for i in idx:
+                if hi[i] - lo[i] < 1:
+                    continue
+                b = bases[offsets[i] + lo[i]:offsets[i] + hi[i]]
+                q = (quals[offsets[i] + lo[i]:offsets[i] + hi[i]].astype(np.int64) - p.qual_offset).astype(np.int8)
+                a0, b0 = py_test_optimal(b, q, e)
+                lo[i], hi[i], x = trim_by_amount(lo[i], hi[i], a0 if p.qtrim_left else 0, b0 if p.qtrim_right else 0, 1)
+                st[1] += x
+                st[0] += x > 0
+                qt[i] = x > 0
+        for i in idx:
+            if not disc(i, state):
+                n = hi[i] - lo[i]
+                L = offsets[i + 1] - offsets[i]
+                minlen = int(max(F32(F32(L) * F32(p.min_len_fraction)), F32(p.min_read_length)))
+                if n < minlen or n > maxlen:
+                    set_discarded(i)
+        remove = False
+        if should_remove():
+            st[1] += sum(hi[i] - lo[i] for i in idx)
+            remove = True
+        if not remove:
+            if p.min_base_quality > 0:
+                for i in idx:
+                    q = (quals[offsets[i] + lo[i]:offsets[i] + hi[i]].astype(np.int64) - p.qual_offset).astype(np.int8)
+                    if min([41] + list(q)) < p.min_base_quality:
+                        set_discarded(i)
+            if p.max_ns >= 0:
+                for i in idx:
+                    b = bases[offsets[i] + lo[i]:offsets[i] + hi[i]]
+                    n = sum(1 for c in b if chr(c) not in "ACGTUacgtu")
+                    if n > p.max_ns:
+                        st[4] += 1
+                        st[5] += hi[i] - lo[i]
+                        set_discarded(i)
+            if should_remove():
+                st[3] += sum(hi[i] - lo[i] for i in idx)
+                st[2] += per
+                remove = True
+        for i in idx:
+            flags[i] = (flags[i] & ~np.uint8(3)) | (1 if state[i] else 0) | (2 if remove else 0) | (0x40 if qt[i] else 0)
+    return lo, hi, flags, st
+
+
+def qual_batch(n, seed, L=80, paired=True):
+    """reads with quality profiles that decay, recover, dip in the middle; N's; a fake k-mer block in front"""
+    rng = np.random.default_rng(seed)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    lens = rng.integers(0, L + 1, n)
+    lens[rng.random(n) < 0.5] = L
+    offsets = np.zeros(n + 1, np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    bases = acgt[rng.integers(0, 4, int(offsets[-1]))].copy()
+    quals = np.zeros(len(bases), np.int64)
+    for i in range(n):
+        ln = int(lens[i])
+        kind = rng.integers(0, 6)
+        x = np.arange(ln)
+        if kind == 0:
+            q = rng.integers(25, 42, ln)
+        elif kind == 1:
+            q = np.clip(40 - (x * rng.integers(20, 60)) // max(ln, 1) + rng.integers(-4, 5, ln), 0, 41)
+        elif kind == 2:
+            q = np.clip(5 + (x * rng.integers(20, 50)) // max(ln, 1) + rng.integers(-4, 5, ln), 0, 41)
+        elif kind == 3:
+            q = rng.integers(30, 42, ln)
+            if ln > 10:
+                a = int(rng.integers(0, ln - 5))
+                q[a:a + int(rng.integers(1, 12))] = rng.integers(0, 8)
+        elif kind == 4:
+            q = rng.integers(0, 12, ln)
+        else:
+            q = rng.integers(0, 42, ln)
+        quals[offsets[i]:offsets[i + 1]] = q
+    nn = rng.random(len(bases)) < 0.02
+    bases[nn] = ord("N")
+    odd = rng.random(len(bases)) < 0.003
+    bases[odd] = rng.choice(np.frombuffer(b"acgtnRY", np.uint8), int(odd.sum()))
+    quals[nn & (rng.random(len(bases)) < 0.5)] = 0
+    lo = np.zeros(n, np.int32)
+    hi = lens.astype(np.int32)
+    cut = rng.random(n) < 0.3
+    hi[cut] = np.maximum(0, hi[cut] - rng.integers(1, 30, int(cut.sum()))).astype(np.int32)
+    cutl = rng.random(n) < 0.1
+    lo[cutl] = np.minimum(hi[cutl], rng.integers(1, 10, int(cutl.sum()))).astype(np.int32)
+    flags = np.zeros(n, np.uint8)
+    per = 2 if paired else 1
+    rem = rng.random(n // per) < 0.05
+    for q in range(per):
+        flags[q::per][rem[:len(flags[q::per])]] = 2
+    d = rng.random(n) < 0.03
+    flags[d & (flags == 0)] = 1
+    return bases, (quals + 33).astype(np.uint8), offsets, lo, hi, flags
+
+
+CASES = [dict(qtrim="rl", trimq=10.0), dict(qtrim="r", trimq=6.0), dict(qtrim="l", trimq=15.5, minlen=25),
+         dict(qtrim="rl", trimq=20.0, rieb=False), dict(qtrim="rl", trimq=10.0, tf1=True, mbq=3),
+         dict(qtrim="", mbq=5, maxns=1), dict(qtrim="r", trimq=0.5, maxns=0, maxlen=70, mlf=0.5), dict(qtrim="rl", trimq=1.0)]
+
+
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_oracle_matches_python_restatement(case):
+    paired = case % 2 == 0
+    bases, quals, offsets, lo, hi, flags = qual_batch(400, 100 + case, paired=paired)
+    p = oq.params(**CASES[case])
+    got = oq.process(bases, quals, offsets, paired, lo, hi, flags, p)
+    want = py_block(bases, quals, offsets, paired, lo, hi, flags, p)
+    for g, w, name in zip(got, want, ("lo", "hi", "flags", "stats")):
+        assert np.array_equal(g, w), name
+    assert got[3].sum() > 0
+
+
+def test_known_answers():
+    """hand-checked cases of testOptimal + trimByAmount"""
+    def one(qs, seq=None, **kw):
+        n = len(qs)
+        b = np.frombuffer((seq or "A" * n).encode(), np.uint8)
+        q = (np.array(qs) + 33).astype(np.uint8)
+        off = np.array([0, n], np.int64)
+        lo, hi, fl, st = oq.process(b, q, off, False, np.zeros(1, np.int32), np.array([n], np.int32), np.zeros(1, np.uint8),
+                                    oq.params(minlen=1, **kw))
+        return int(lo[0]), int(hi[0]), int(fl[0]), list(st)
+    # all bases better than trimq: nothing trimmed
+    assert one([30] * 20, trimq=10.0) == (0, 20, 0, [0, 0, 0, 0, 0, 0])
+    # a bad tail: the five Q2 bases go
+    assert one([30] * 15 + [2] * 5, trimq=10.0) == (0, 15, 0x40, [1, 5, 0, 0, 0, 0])
+    # bad head and tail, qtrim=r only trims the tail
+    assert one([2] * 4 + [30] * 10 + [2] * 6, qtrim="r", trimq=10.0) == (0, 14, 0x40, [1, 6, 0, 0, 0, 0])
+    assert one([2] * 4 + [30] * 10 + [2] * 6, qtrim="rl", trimq=10.0) == (4, 14, 0x40, [1, 10, 0, 0, 0, 0])
+    # everything bad: trimByAmount keeps one base (right = len - 1), then minlen=1 keeps the read
+    assert one([2] * 12, trimq=10.0) == (0, 1, 0x40, [1, 11, 0, 0, 0, 0])
+    # an N costs 0.75 - 0.1 = 6.5 good bases: after 5 good bases the run dies and the longer side is kept, after 8 it survives
+    lo, hi, fl, st = one([35] * 30, seq="A" * 5 + "N" + "A" * 24, trimq=10.0)
+    assert (lo, hi) == (6, 30)
+    lo, hi, fl, st = one([35] * 30, seq="A" * 8 + "N" + "A" * 21, trimq=10.0)
+    assert (lo, hi) == (0, 30)

@@ -56,6 +56,57 @@ def test_bbduk_tool_paired_fastq(tmp_path, extra):
     assert len(outs["native"][2]) > 0  # some pairs were removed
 
 
+@pytest.mark.parametrize("strict", [True, False])
+def test_bbduk_tool_canonical_adapter_trimming_with_tbo(tmp_path, strict):
+    """bbduk.sh in=.. in2=.. ref=adapters ktrim=r k=23 mink=11 hdist=1 tpe tbo: k-mer block, then trim by overlap"""
+    from bbtools_b200.bbduk import BBDuk
+    from bbtools_b200.fasta import read_fasta
+    from oracle import tbo as otbo
+    from oracle.oracle import Oracle
+    bases, offsets = synth.paired_adapter_reads(6000, seed=43)
+    rng = np.random.default_rng(2)
+    quals = (33 + rng.integers(12, 41, len(bases))).astype(np.uint8)
+    noisy = rng.random(len(offsets) - 1) < 0.2  # reads whose expected errors trip strictoverlap's filter
+    for i in np.nonzero(noisy)[0]:
+        quals[offsets[i]:offsets[i + 1]] = 33 + rng.integers(2, 12, offsets[i + 1] - offsets[i])
+    paths = []
+    for first, tag in ((0, b"1:N:0"), (1, b"2:N:0")):
+        path = tmp_path / f"r{first + 1}.fq"
+        with open(path, "wb") as f:
+            for i in range(first, len(offsets) - 1, 2):
+                f.write(b"@pair%d %s\n" % (i // 2, tag) + bytes(bases[offsets[i]:offsets[i + 1]]) + b"\n+\n" +
+                        bytes(quals[offsets[i]:offsets[i + 1]]) + b"\n")
+        paths.append(path)
+    common = [f"in={paths[0]}", f"in2={paths[1]}", f"ref={GOLDEN}/adapters.fa", "ktrim=r", "k=23", "mink=11", "hdist=1", "tpe",
+              "tbo", f"strictoverlap={'t' if strict else 'f'}"]
+    outs = {}
+    for mode in ("native", "python"):
+        o1, o2, m1 = (tmp_path / f"{mode}_{x}.fq" for x in ("o1", "o2", "m1"))
+        tool = BBDuk(common + [f"out={o1}", f"out2={o2}", f"outm={m1}"])
+        tool.process(native=(mode == "native"))
+        outs[mode] = tuple(open(p, "rb").read() for p in (o1, o2, m1)) + (list(tool.tbo_stats),)
+        cfg = tool.cfg
+    assert outs["native"] == outs["python"]
+    _, rb, roff = read_fasta(os.path.join(GOLDEN, "adapters.fa"))
+    ora = Oracle(cfg)
+    ora.add_ref(rb, roff)
+    ora.finalize()
+    want, _ = ora.process(bases, offsets, True)
+    whi, _, _, wst = otbo.process(bases, quals, offsets, want.lo, want.hi, want.flags, otbo.default_params(strict))
+    assert list(wst) == outs["native"][3]
+    assert wst[0] > 100
+    exp = [[], []]
+    for i in range(len(offsets) - 1):
+        if want.flags[i & ~1] & F_REMOVED:
+            continue
+        a, b = int(want.lo[i]), int(whi[i])
+        exp[i & 1].append(b"@pair%d %s\n" % (i // 2, b"1:N:0" if i % 2 == 0 else b"2:N:0") +
+                          bytes(bases[offsets[i] + a:offsets[i] + b]) + b"\n+\n" + bytes(quals[offsets[i] + a:offsets[i] + b]) + b"\n")
+    assert outs["native"][0] == b"".join(exp[0]) and outs["native"][1] == b"".join(exp[1])
+    if strict:
+        assert np.any(whi != want.hi)
+
+
 def test_bbduk_tool_single_kfilter(tmp_path):
     from bbtools_b200.bbduk import BBDuk
     ref = synth.random_reference(2, 50_000, seed=7)
