@@ -439,13 +439,17 @@ def run_ours(args):
     # ---- the quality-trimming block (qtrim=rl trimq=10) on the same batch, timed alone ----
     qtrim_info = None
     if args.workload == "cfg2":
+        # synthetic qualities: every read decays from Q40 towards its 3' end with its own slope, +-3 noise, clamped to [2,41]
         g = torch.Generator(device=dev)
         g.manual_seed(5 + rank)
-        posn = (torch.arange(n_reads * L, device=dev, dtype=torch.int32) % L)
-        slope = torch.randint(0, 45, (n_reads * L,), device=dev, dtype=torch.int32, generator=g)
-        d_quals = (torch.clamp(40 - (posn * slope) // L + torch.randint(-3, 4, (n_reads * L,), device=dev, dtype=torch.int32, generator=g),
-                               2, 41) + 33).to(torch.uint8)
-        del posn, slope
+        d_quals = torch.empty(n_reads * L, dtype=torch.uint8, device=dev)
+        posn = torch.arange(L, device=dev, dtype=torch.int32)
+        for c0 in range(0, n_reads, 1 << 20):
+            c1 = min(n_reads, c0 + (1 << 20))
+            slope = torch.randint(0, 45, (c1 - c0, 1), device=dev, dtype=torch.int32, generator=g)
+            noise = torch.randint(-3, 4, (c1 - c0, L), device=dev, dtype=torch.int32, generator=g)
+            d_quals[c0 * L:c1 * L] = (torch.clamp(40 - (posn * slope) // L + noise, 2, 41) + 33).to(torch.uint8).reshape(-1)
+        del posn, slope, noise
         qcfg = eng.qtrim_cfg(qtrim_left=1, qtrim_right=1, trimq=10.0)
         d_qst = torch.zeros(6, dtype=torch.int64, device=dev)
         q_lo = torch.zeros(n_reads, dtype=torch.int32, device=dev)

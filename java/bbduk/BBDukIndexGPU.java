@@ -68,6 +68,15 @@ public final class BBDukIndexGPU extends BBDukIndex {
 		return tboNative(handle, cfg, meeFilter, bases, quals, offsets, nReads, lo, hi, flags, insert, stats2)==0;
 	}
 
+	/** Quality trimming + minlen / maxlen / mbq / maxns for the batch processBatch() (and tboBatch()) answered
+	 * (replaces jgi/BBDuk.java:3074-3170): lo[] / hi[] / flags[] are updated in place; stats6 += {readsQTrimmed,
+	 * basesQTrimmed, readsQFiltered, basesQFiltered, readsNFiltered, basesNFiltered}. quals = Read.quality, flattened. */
+	public boolean qtrimBatch(boolean qtrimLeft, boolean qtrimRight, float trimq, int minBaseQuality, int maxNs, int maxReadLength,
+			byte[] bases, byte[] quals, long[] offsets, long nReads, boolean paired, int[] lo, int[] hi, byte[] flags, long[] stats6){
+		final int[] cfg={qtrimLeft ? 1 : 0, qtrimRight ? 1 : 0, minBaseQuality, maxNs, maxReadLength, 0};
+		return qtrimNative(handle, cfg, trimq, bases, quals, offsets, nReads, paired, lo, hi, flags, stats6)==0;
+	}
+
 	@Override public int getValue(long kmer, long rkmer, long lengthMask, int qPos, int len, int qHDist){
 		throw new UnsupportedOperationException("per-k-mer queries are served in batches by processBatch()");
 	}
@@ -81,6 +90,8 @@ public final class BBDukIndexGPU extends BBDukIndex {
 			int[] id0, int[] lo, int[] hi, byte[] flags, int[] count, long[] stats8);
 	private static native int tboNative(long h, int[] cfg, float meeFilter, byte[] bases, byte[] quals, long[] offsets, long nReads,
 			int[] lo, int[] hi, byte[] flags, int[] insert, long[] stats2);
+	private static native int qtrimNative(long h, int[] cfg, float trimq, byte[] bases, byte[] quals, long[] offsets, long nReads,
+			boolean paired, int[] lo, int[] hi, byte[] flags, long[] stats6);
 	private static native int scaffoldCountsNative(long h, long[] reads, long[] bases);
 	private static native String lastErrorNative(long h);
 	private static native void destroyNative(long h);

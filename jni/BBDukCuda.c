@@ -124,6 +124,50 @@ JNIEXPORT jint JNICALL Java_bbduk_BBDukIndexGPU_tboNative(JNIEnv *env, jclass cl
     return rc;
 }
 
+/* Replaces the quality-trimming and quality-filtering blocks of the per-pair loop (jgi/BBDuk.java:3074-3170) for the batch
+ * that processNative (and tboNative) answered: lo[], hi[] and flags[] are updated in place, stats6 += {readsQTrimmed,
+ * basesQTrimmed, readsQFiltered, basesQFiltered, readsNFiltered, basesNFiltered}.
+ * qCfg = {qtrimLeft, qtrimRight, minBaseQuality, maxNs (-1 off), maxReadLength (0 unlimited), qualOffset (0 for Read.quality)}. */
+JNIEXPORT jint JNICALL Java_bbduk_BBDukIndexGPU_qtrimNative(JNIEnv *env, jclass cls, jlong handle, jintArray jcfg, jfloat trimq,
+                                                            jbyteArray jbases, jbyteArray jquals, jlongArray joffsets, jlong nReads,
+                                                            jboolean paired, jintArray jlo, jintArray jhi, jbyteArray jflags,
+                                                            jlongArray jstats6) {
+    bbduk_qtrim_cfg cfg;
+    jint c[6];
+    int64_t st[6] = {0, 0, 0, 0, 0, 0};
+    bbduk_b200_qtrim_cfg_default(&cfg);
+    (*env)->GetIntArrayRegion(env, jcfg, 0, 6, c);
+    cfg.qtrim_left = c[0];
+    cfg.qtrim_right = c[1];
+    cfg.min_base_quality = c[2];
+    cfg.max_ns = c[3];
+    cfg.max_read_length = c[4];
+    cfg.qual_offset = c[5];
+    cfg.trimq = trimq;
+    jbyte *b = (jbyte *)(*env)->GetPrimitiveArrayCritical(env, jbases, NULL);
+    jbyte *q = jquals ? (jbyte *)(*env)->GetPrimitiveArrayCritical(env, jquals, NULL) : NULL;
+    jlong *o = (jlong *)(*env)->GetPrimitiveArrayCritical(env, joffsets, NULL);
+    jint *lo = (jint *)(*env)->GetPrimitiveArrayCritical(env, jlo, NULL);
+    jint *hi = (jint *)(*env)->GetPrimitiveArrayCritical(env, jhi, NULL);
+    jbyte *fl = (jbyte *)(*env)->GetPrimitiveArrayCritical(env, jflags, NULL);
+    const jint rc = bbduk_b200_qtrim((bbduk_handle *)(intptr_t)handle, &cfg, (const uint8_t *)b, (const uint8_t *)q,
+                                     (const int64_t *)o, (int64_t)nReads, paired ? 1 : 0, (int32_t *)lo, (int32_t *)hi,
+                                     (uint8_t *)fl, st);
+    (*env)->ReleasePrimitiveArrayCritical(env, jflags, fl, 0);
+    (*env)->ReleasePrimitiveArrayCritical(env, jhi, hi, 0);
+    (*env)->ReleasePrimitiveArrayCritical(env, jlo, lo, 0);
+    (*env)->ReleasePrimitiveArrayCritical(env, joffsets, o, JNI_ABORT);
+    if (jquals) (*env)->ReleasePrimitiveArrayCritical(env, jquals, q, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, jbases, b, JNI_ABORT);
+    if (jstats6 && !rc) {
+        jlong v[6];
+        (*env)->GetLongArrayRegion(env, jstats6, 0, 6, v);
+        for (int i = 0; i < 6; i++) v[i] += st[i];
+        (*env)->SetLongArrayRegion(env, jstats6, 0, 6, v);
+    }
+    return rc;
+}
+
 JNIEXPORT jint JNICALL Java_bbduk_BBDukIndexGPU_scaffoldCountsNative(JNIEnv *env, jclass cls, jlong handle,
                                                                      jlongArray jreads, jlongArray jbases) {
     const jint n = (*env)->GetArrayLength(env, jreads);

@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=100_000_000, help="pairs (cfg2) / half the reads (cfg3)")
     ap.add_argument("--chunk-pairs", type=int, default=4 << 20)
     ap.add_argument("--scale", type=float, default=1.0, help="cfg3: fraction of the 100 Mbp reference (the oracle's table is host RAM)")
+    ap.add_argument("--tbo", action="store_true", help="cfg2: follow the k-mer block with trim-by-overlap (the `tpe tbo` command)")
+    ap.add_argument("--qtrim", action="store_true", help="cfg2: then quality trimming qtrim=rl trimq=10 on synthetic decaying qualities")
     args = ap.parse_args()
     import torch
 
@@ -61,6 +63,21 @@ def main():
     outs = {k: torch.empty(n, dtype=torch.int32, device="cuda") for k in ("id0", "lo", "hi", "count")}
     outs["flags"] = torch.empty(n, dtype=torch.uint8, device="cuda")
     d_stats = torch.zeros(8, dtype=torch.int64, device="cuda")
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(cores)
+    tbo_tot, q_tot = np.zeros(2, np.int64), np.zeros(6, np.int64)
+    d_tst = torch.zeros(2, dtype=torch.int64, device="cuda")
+    d_qst = torch.zeros(6, dtype=torch.int64, device="cuda")
+    t_tbo = t_tbo_cpu = t_q = t_q_cpu = 0.0
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(99)
+    posn = torch.arange(L, device="cuda", dtype=torch.int32)
+
+    def sliced(fn, n_units, per):
+        """run fn(a, b) over `cores` slices of the units (the C oracles release the GIL)"""
+        edges = [per * (n_units * i // cores) for i in range(cores + 1)]
+        return list(pool.map(lambda ab: fn(*ab), zip(edges[:-1], edges[1:])))
+
     tot = {}
     crc = 0
     done = 0
@@ -91,11 +108,73 @@ def main():
             crc = zlib.crc32(got.tobytes(), crc)
         for k_, v in st.as_dict().items():
             tot[k_] = tot.get(k_, 0) + v
+        if args.tbo and args.workload == "cfg2":
+            from oracle import tbo as otbo
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            gpu.tbo_device(d_bases, None, d_off, nr, L, outs["lo"], outs["hi"], outs["flags"], None, d_tst)
+            torch.cuda.synchronize()
+            t_tbo += time.perf_counter() - t0
+            lo_h, fl_h = want.lo, want.flags
+            whi = want.hi.copy()
+            t0 = time.perf_counter()
+
+            def tbo_slice(a, b):
+                hi2, _, _, st2 = otbo.process(hb, None, ho[a:b + 1], lo_h[a:b], whi[a:b], fl_h[a:b])
+                whi[a:b] = hi2
+                return st2
+            for st2 in sliced(tbo_slice, m, 2):
+                tbo_tot += st2
+            t_tbo_cpu += time.perf_counter() - t0
+            got_hi = outs["hi"][:nr].cpu().numpy()
+            got_fl = outs["flags"][:nr].cpu().numpy()
+            mism += int(np.count_nonzero(got_hi != whi)) + int(np.count_nonzero(((got_fl & 0x20) != 0) != (whi != want.hi)))
+            crc = zlib.crc32(got_hi.tobytes(), crc)
+            want.hi[:] = whi
+            want.flags[:] = got_fl
+        if args.qtrim and args.workload == "cfg2":
+            from oracle import qtrim as oq
+            slope = torch.randint(0, 45, (nr, 1), device="cuda", dtype=torch.int32, generator=gen)
+            noise = torch.randint(-3, 4, (nr, L), device="cuda", dtype=torch.int32, generator=gen)
+            d_quals = (torch.clamp(40 - (posn * slope) // L + noise, 2, 41) + 33).to(torch.uint8).reshape(-1)
+            del slope, noise
+            qcfg = gpu.qtrim_cfg(qtrim_left=1, qtrim_right=1, trimq=10.0)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            gpu.qtrim_device(d_bases, d_quals, d_off, nr, True, outs["lo"], outs["hi"], outs["flags"], qcfg, d_qst)
+            torch.cuda.synchronize()
+            t_q += time.perf_counter() - t0
+            hq = d_quals.cpu().numpy()
+            qp = oq.params(qtrim="rl", trimq=10.0)
+            wl, wh, wf = want.lo.copy(), want.hi.copy(), want.flags.copy()
+            t0 = time.perf_counter()
+
+            def q_slice(a, b):
+                l2, h2, f2, st2 = oq.process(hb, hq, ho[a:b + 1], True, wl[a:b], wh[a:b], wf[a:b], qp)
+                wl[a:b], wh[a:b], wf[a:b] = l2, h2, f2
+                return st2
+            for st2 in sliced(q_slice, m, 2):
+                q_tot += st2
+            t_q_cpu += time.perf_counter() - t0
+            for name, w in (("lo", wl), ("hi", wh), ("flags", wf)):
+                got = outs[name][:nr].cpu().numpy()
+                mism += int(np.count_nonzero(got != w))
+                crc = zlib.crc32(got.tobytes(), crc)
+            del d_quals
         done += m
     dev_tot = dict(zip(tot.keys(), d_stats.cpu().tolist()))
     ro, bo = ora.scaffold_counts()
     rg, bg = gpu.scaffold_counts()
-    print(json.dumps({"workload": args.workload, "reads": 2 * args.pairs, "stored_kmers": stored, "mismatching_fields": mism,
+    extra = {}
+    if args.tbo:
+        extra["tbo"] = {"reads_trimmed": int(tbo_tot[0]), "bases_trimmed": int(tbo_tot[1]), "counters_equal": d_tst.cpu().tolist() == tbo_tot.tolist(),
+                        "gpu_s": round(t_tbo, 3), "oracle_s": round(t_tbo_cpu, 3)}
+        assert extra["tbo"]["counters_equal"]
+    if args.qtrim:
+        extra["qtrim"] = {"stats6": q_tot.tolist(), "counters_equal": d_qst.cpu().tolist() == q_tot.tolist(), "gpu_s": round(t_q, 3),
+                          "oracle_s": round(t_q_cpu, 3), "command": "qtrim=rl trimq=10, synthetic qualities decaying from Q40 (torch generator seed 99)"}
+        assert extra["qtrim"]["counters_equal"]
+    print(json.dumps({"workload": args.workload, "reads": 2 * args.pairs, "stored_kmers": stored, "mismatching_fields": mism, **extra,
                       "counters_equal": dev_tot == tot, "scaffold_counts_equal": bool(np.array_equal(ro, rg) and np.array_equal(bo, bg)),
                       "counters": tot, "crc32_of_results": crc, "gpu_s": round(t_gpu, 3), "oracle_s": round(t_cpu, 3),
                       "oracle_threads": cores}))
