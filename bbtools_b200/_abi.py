@@ -101,6 +101,14 @@ class BBDukQtrimCfg(C.Structure):
         ("max_ns", C.c_int32),
         ("max_read_length", C.c_int32),
         ("qual_offset", C.c_int32),
+        ("trim_poly_a", C.c_int32),
+        ("trim_poly_g_left", C.c_int32),
+        ("trim_poly_g_right", C.c_int32),
+        ("filter_poly_g", C.c_int32),
+        ("trim_poly_c_left", C.c_int32),
+        ("trim_poly_c_right", C.c_int32),
+        ("filter_poly_c", C.c_int32),
+        ("max_non_poly", C.c_int32),
         ("reserved", C.c_int32 * 4),
     ]
 

@@ -30,6 +30,15 @@ def _parse_boolean(s):
     return s.lower() == "true"
 
 
+def _parse_poly(b):
+    """parse/Parser.java:426-437"""
+    if b is None:
+        return 2
+    if b[:1].isdigit():
+        return int(b)
+    return 2 if _parse_boolean(b) else 0
+
+
 def parse_args(args, generation=GEN_JGI):
     """bbduk.sh-style argv -> (bbduk_cfg, io dict). Unknown keys raise, like the reference
     ("Unknown parameter", jgi/BBDuk.java:561)."""
@@ -38,7 +47,9 @@ def parse_args(args, generation=GEN_JGI):
     io = {"in1": None, "in2": None, "out1": None, "out2": None, "outm1": None, "outm2": None, "ref": [],
           "literal": [], "stats": None, "interleaved": None, "ordered": generation == GEN_S, "ottm": False,
           "tbo": False, "strictoverlap": True, "minoverlap": -1, "mininsert": -1,
-          "qtrim_left": False, "qtrim_right": False, "trimq": 6.0, "mbq": 0, "maxns": -1, "maxlen": 0}
+          "qtrim_left": False, "qtrim_right": False, "trimq": 6.0, "mbq": 0, "maxns": -1, "maxlen": 0,
+          "trimpolya": 0, "trimpolygleft": 0, "trimpolygright": 0, "filterpolyg": 0, "trimpolycleft": 0, "trimpolycright": 0,
+          "filterpolyc": 0, "maxnonpoly": 1}
     for arg in args:
         sp = arg.split("=")
         a = sp[0].lower()
@@ -231,6 +242,13 @@ def parse_args(args, generation=GEN_JGI):
             io["maxns"] = int(b)
         elif a in ("maxlength", "maxreadlength", "maxreadlen", "maxlen"):
             io["maxlen"] = int(b)
+        elif a in ("trimpolya", "trimpolygleft", "trimpolygright", "filterpolyg", "trimpolycleft", "trimpolycright", "filterpolyc",
+                   "maxnonpoly"):  # parse/Parser.java:386-437
+            io[a] = _parse_poly(b)
+        elif a == "trimpolyg":
+            io["trimpolygleft"] = io["trimpolygright"] = _parse_poly(b)
+        elif a == "trimpolyc":
+            io["trimpolycleft"] = io["trimpolycright"] = _parse_poly(b)
         elif a == "usequality":
             if _parse_boolean(b):
                 raise NotImplementedError("usequality=t (quality-weighted overlap) is not on the device path")
@@ -411,11 +429,12 @@ class BBDukIndexGPU:
 
     def qtrim(self, bases, quals, offsets, paired, out, cfg):
         """HOST buffers; `out` is the Outputs of process() (after tbo): lo / hi / flags are updated in place.
-        -> [readsQTrimmed, basesQTrimmed, readsQFiltered, basesQFiltered, readsNFiltered, basesNFiltered]"""
+        -> [readsQTrimmed, basesQTrimmed, readsQFiltered, basesQFiltered, readsNFiltered, basesNFiltered, readsPolyTrimmed,
+        basesPolyTrimmed]"""
         bases = np.ascontiguousarray(bases, np.uint8)
         offsets = np.ascontiguousarray(offsets, np.int64)
         q = None if quals is None else np.ascontiguousarray(quals, np.uint8)
-        st = np.zeros(6, np.int64)
+        st = np.zeros(8, np.int64)
         self._check(self.lib.bbduk_b200_qtrim(self.h, C.byref(cfg), bases.ctypes.data, None if q is None else q.ctypes.data,
                                               offsets.ctypes.data, len(offsets) - 1, int(bool(paired)), out.lo.ctypes.data,
                                               out.hi.ctypes.data, out.flags.ctypes.data, st.ctypes.data), "qtrim")
@@ -471,7 +490,7 @@ class BBDuk:
         self.stored_kmers = self.index.finalize()
         self.stats = None
         self.tbo_stats = None  # [readsTrimmedByOverlap, basesTrimmedByOverlap]
-        self.qtrim_stats = None  # [readsQTrimmed, basesQTrimmed, readsQFiltered, basesQFiltered, readsNFiltered, basesNFiltered]
+        self.qtrim_stats = None  # [reads/bases QTrimmed, reads/bases QFiltered, reads/bases NFiltered, reads/bases PolyTrimmed]
 
     def process_arrays(self, bases, offsets, paired):
         want_mask = bool(self.cfg.ktrim_n)
@@ -510,13 +529,19 @@ class BBDuk:
 
     def _wants_qtrim(self):
         io = self.io
-        return bool(io["qtrim_left"] or io["qtrim_right"] or io["mbq"] > 0 or io["maxns"] >= 0 or io["maxlen"] > 0 or io["tbo"])
+        poly = any(io[k] > 0 for k in ("trimpolya", "trimpolygleft", "trimpolygright", "filterpolyg", "trimpolycleft",
+                                       "trimpolycright", "filterpolyc"))
+        return bool(io["qtrim_left"] or io["qtrim_right"] or io["mbq"] > 0 or io["maxns"] >= 0 or io["maxlen"] > 0 or io["tbo"] or poly)
 
     def _qtrim(self, bases, quals, offsets, paired, out):
         """quality trimming, minlen / maxlen, mbq, maxns (jgi/BBDuk.java:3074-3170); updates out.lo / out.hi / out.flags"""
         io = self.io
         cfg = self.index.qtrim_cfg(qtrim_left=int(io["qtrim_left"]), qtrim_right=int(io["qtrim_right"]), trimq=io["trimq"],
-                                   min_base_quality=io["mbq"], max_ns=io["maxns"], max_read_length=io["maxlen"])
+                                   min_base_quality=io["mbq"], max_ns=io["maxns"], max_read_length=io["maxlen"],
+                                   trim_poly_a=io["trimpolya"], trim_poly_g_left=io["trimpolygleft"],
+                                   trim_poly_g_right=io["trimpolygright"], filter_poly_g=io["filterpolyg"],
+                                   trim_poly_c_left=io["trimpolycleft"], trim_poly_c_right=io["trimpolycright"],
+                                   filter_poly_c=io["filterpolyc"], max_non_poly=io["maxnonpoly"])
         return self.index.qtrim(bases, quals, offsets, paired, out, cfg)
 
     def _write_stats(self):

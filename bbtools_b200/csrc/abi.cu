@@ -860,6 +860,7 @@ void bbduk_b200_qtrim_cfg_default(bbduk_qtrim_cfg *c) {
     c->trimq = 6.0f;  // jgi/BBDuk.java:126
     c->max_ns = -1;
     c->qual_offset = 33;
+    c->max_non_poly = 1;  // parse/Parser.java:1831
 }
 
 static int check_qtrim_cfg(bbduk_handle *h, const bbduk_qtrim_cfg *cfg, const void *quals) {
@@ -872,7 +873,7 @@ static int check_qtrim_cfg(bbduk_handle *h, const bbduk_qtrim_cfg *cfg, const vo
 
 int bbduk_b200_qtrim_device(bbduk_handle *h, const bbduk_qtrim_cfg *cfg, const uint8_t *d_bases, const uint8_t *d_quals,
                             const uint32_t *d_offsets, int64_t n_reads, int32_t paired, int32_t *d_lo, int32_t *d_hi,
-                            uint8_t *d_flags, int64_t *d_stats6, void *stream) {
+                            uint8_t *d_flags, int64_t *d_stats8, void *stream) {
     if (!h) return set_err(nullptr, "handle is NULL");
     if (check_qtrim_cfg(h, cfg, d_quals)) return 1;
     if (n_reads < 0 || (paired && (n_reads & 1))) return set_err(h, "bad n_reads (paired input needs an even count)");
@@ -882,7 +883,7 @@ int bbduk_b200_qtrim_device(bbduk_handle *h, const bbduk_qtrim_cfg *cfg, const u
         return set_err(h, "d_bases and d_quals must be 16-byte aligned");
     CKH(cudaSetDevice(h->device));
     if (launch_qtrim(h->sm_count, cfg, h->p, d_bases, d_quals, d_offsets, n_reads, paired ? 1 : 0, d_lo, d_hi, d_flags,
-                     reinterpret_cast<unsigned long long *>(d_stats6), (cudaStream_t)stream))
+                     reinterpret_cast<unsigned long long *>(d_stats8), (cudaStream_t)stream))
         return set_err(h, std::string("qtrim kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
     h->launches += 1;
     return 0;
@@ -890,7 +891,7 @@ int bbduk_b200_qtrim_device(bbduk_handle *h, const bbduk_qtrim_cfg *cfg, const u
 
 int bbduk_b200_qtrim(bbduk_handle *h, const bbduk_qtrim_cfg *cfg, const uint8_t *bases, const uint8_t *quals,
                      const int64_t *offsets, int64_t n_reads, int32_t paired, int32_t *lo, int32_t *hi, uint8_t *flags,
-                     int64_t *stats6) {
+                     int64_t *stats8) {
     if (!h) return set_err(nullptr, "handle is NULL");
     if (check_qtrim_cfg(h, cfg, quals)) return 1;
     if (n_reads < 0 || (paired && (n_reads & 1))) return set_err(h, "bad n_reads (paired input needs an even count)");
@@ -900,8 +901,8 @@ int bbduk_b200_qtrim(bbduk_handle *h, const bbduk_qtrim_cfg *cfg, const uint8_t 
     std::lock_guard<std::mutex> g(h->tbo_mu);  // shares the staging of the tbo entry point
     cudaStream_t st = nullptr;
     int64_t *d_stats = nullptr;
-    CKH(cudaMalloc(&d_stats, 6 * sizeof(int64_t)));
-    CKH(cudaMemset(d_stats, 0, 6 * sizeof(int64_t)));
+    CKH(cudaMalloc(&d_stats, 8 * sizeof(int64_t)));
+    CKH(cudaMemset(d_stats, 0, 8 * sizeof(int64_t)));
     int rc = 0;
     int64_t r0 = 0;
     const int per = paired ? 2 : 1;
@@ -948,10 +949,10 @@ int bbduk_b200_qtrim(bbduk_handle *h, const bbduk_qtrim_cfg *cfg, const uint8_t 
 #undef CKQ
         r0 = r1;
     }
-    if (!rc && stats6) {
-        int64_t v[6] = {0, 0, 0, 0, 0, 0};
+    if (!rc && stats8) {
+        int64_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (cudaMemcpy(v, d_stats, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) rc = set_err(h, "qtrim: stats copy failed");
-        for (int i = 0; i < 6; i++) stats6[i] += v[i];
+        for (int i = 0; i < 8; i++) stats8[i] += v[i];
     }
     cudaFree(d_stats);
     return rc;

@@ -451,7 +451,7 @@ def run_ours(args):
             d_quals[c0 * L:c1 * L] = (torch.clamp(40 - (posn * slope) // L + noise, 2, 41) + 33).to(torch.uint8).reshape(-1)
         del posn, slope, noise
         qcfg = eng.qtrim_cfg(qtrim_left=1, qtrim_right=1, trimq=10.0)
-        d_qst = torch.zeros(6, dtype=torch.int64, device=dev)
+        d_qst = torch.zeros(8, dtype=torch.int64, device=dev)
         q_lo = torch.zeros(n_reads, dtype=torch.int32, device=dev)
         q_hi = torch.full((n_reads,), L, dtype=torch.int32, device=dev)
         q_fl = torch.zeros(n_reads, dtype=torch.uint8, device=dev)

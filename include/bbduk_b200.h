@@ -96,6 +96,7 @@ typedef struct bbduk_cfg {
 #define BBDUK_F_SPLIT     0x10 /* ksplit produced a second segment [count, len-1) */
 #define BBDUK_F_TBO       0x20 /* shortened by trim-by-overlap (bbduk_b200_tbo; jgi/BBDuk.java:2911-2924) */
 #define BBDUK_F_QTRIMMED  0x40 /* shortened by quality trimming (bbduk_b200_qtrim; jgi/BBDuk.java:3077-3090) */
+#define BBDUK_F_POLYTRIMMED 0x80 /* shortened by poly-A / poly-G / poly-C trimming (bbduk_b200_qtrim; jgi/BBDuk.java:2954-3052) */
 
 /*
  * Per-read outputs, struct of arrays, each n_reads long; any pointer may be NULL (not wanted).
@@ -262,9 +263,9 @@ BBDUK_API int bbduk_b200_tbo_device(bbduk_handle *h, const bbduk_tbo_cfg *cfg, c
                                     int32_t *d_hi, uint8_t *d_flags, int32_t *d_insert, int64_t *d_stats2, void *stream);
 
 /*
- * Quality trimming and the per-read quality / length / N filters (first part): the block that follows
- * the k-mer block, tbo and the poly-X / entropy steps in the per-pair loop, jgi/BBDuk.java:3074-3170
- * (= bbduk/BBDukProcessorS.java's copy). Parameters carry the meaning of the bbduk.sh flags; minlen, minlenfraction, rieb and
+ * Poly-X trimming, quality trimming and the per-read quality / length / N filters (first part): the
+ * blocks that follow the k-mer block and tbo in the per-pair loop, jgi/BBDuk.java:2954-3052 and :3074-3170
+ * (= bbduk/BBDukProcessorS.java's copy; entropy masking / trimming, which sits between them, must be off). Parameters carry the meaning of the bbduk.sh flags; minlen, minlenfraction, rieb and
  * trimfailuresto1bp come from the handle's bbduk_cfg, as in the reference.
  */
 typedef struct bbduk_qtrim_cfg {
@@ -276,27 +277,34 @@ typedef struct bbduk_qtrim_cfg {
     int32_t max_ns;            /* maxns= ; -1 = off */
     int32_t max_read_length;   /* maxlen= ; 0 = unlimited */
     int32_t qual_offset;       /* subtracted from every quality byte; 33 for FASTQ text, 0 for Read.quality */
+    int32_t trim_poly_a;       /* trimpolya= ; 0 = off (parse/Parser.java:386-411: a bare flag means 2) */
+    int32_t trim_poly_g_left, trim_poly_g_right, filter_poly_g; /* trimpolyg[left|right]=, filterpolyg= */
+    int32_t trim_poly_c_left, trim_poly_c_right, filter_poly_c; /* trimpolyc[left|right]=, filterpolyc= */
+    int32_t max_non_poly;      /* maxnonpoly= ; default 1 */
     int32_t reserved[4];
 } bbduk_qtrim_cfg;
 BBDUK_API void bbduk_b200_qtrim_cfg_default(bbduk_qtrim_cfg *cfg);
 
-/* Replaces, for one batch that has been through bbduk_b200_process (and bbduk_b200_tbo): TrimRead.trimFast in its default
+/* Replaces, for one batch that has been through bbduk_b200_process (and bbduk_b200_tbo): the poly-A / poly-G / poly-C blocks
+ * (trimPolyA, trimPoly, detectPolyLeft / Right, jgi/BBDuk.java:4721-4825, each followed by its minlen test and
+ * shouldRemove; the reference's poly-C filter of r2 looks at r1, :3035, and so does this), then TrimRead.trimFast in its default
  * "optimal" mode (shared/TrimRead.java:113-169, :348-410: the maximum-sum run of avgErrorRate - probError, single
  * precision, then trimByAmount(r, a, b, 1)), the minlen / maxlen test, shouldRemove, then minbasequality and maxns with
  * their shouldRemove (jgi/BBDuk.java:3074-3170; minavgquality, maxnrate, minconsecutivebases and minbasefrequency are at
  * their defaults = off). paired != 0: reads (2i, 2i+1) are mates. Units whose flags carry BBDUK_F_REMOVED are skipped.
- * lo[], hi[] and flags[] (BBDUK_F_QTRIMMED, BBDUK_F_DISCARDED, BBDUK_F_REMOVED) are updated in place;
- * stats6 += {readsQTrimmed, basesQTrimmed, readsQFiltered, basesQFiltered, readsNFiltered, basesNFiltered}.
+ * lo[], hi[] and flags[] (BBDUK_F_QTRIMMED, BBDUK_F_POLYTRIMMED, BBDUK_F_DISCARDED, BBDUK_F_REMOVED) are updated in place;
+ * stats8 += {readsQTrimmed, basesQTrimmed, readsQFiltered, basesQFiltered, readsNFiltered, basesNFiltered, readsPolyTrimmed,
+ * basesPolyTrimmed}.
  * HOST buffers; quals has the layout of bases and is required when qtrim or mbq is set. */
 BBDUK_API int bbduk_b200_qtrim(bbduk_handle *h, const bbduk_qtrim_cfg *cfg, const uint8_t *bases, const uint8_t *quals,
                                const int64_t *offsets, int64_t n_reads, int32_t paired, int32_t *lo, int32_t *hi, uint8_t *flags,
-                               int64_t *stats6);
+                               int64_t *stats8);
 
-/* Same on DEVICE buffers (32-bit offsets), asynchronous on `stream`; d_stats6 = device int64[6] to accumulate into, may
+/* Same on DEVICE buffers (32-bit offsets), asynchronous on `stream`; d_stats8 = device int64[8] to accumulate into, may
  * be NULL. */
 BBDUK_API int bbduk_b200_qtrim_device(bbduk_handle *h, const bbduk_qtrim_cfg *cfg, const uint8_t *d_bases, const uint8_t *d_quals,
                                       const uint32_t *d_offsets, int64_t n_reads, int32_t paired, int32_t *d_lo, int32_t *d_hi,
-                                      uint8_t *d_flags, int64_t *d_stats6, void *stream);
+                                      uint8_t *d_flags, int64_t *d_stats8, void *stream);
 
 /* Host helper (no GPU needed): the 2-bit packing bbduk_b200_process applies to a chunk before it crosses PCIe when
  * the tuned kernel takes the whole chunk (set BBDUK_B200_PACK_HOST=0 to ship ASCII instead). F[i] = big-endian

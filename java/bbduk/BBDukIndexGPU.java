@@ -68,13 +68,17 @@ public final class BBDukIndexGPU extends BBDukIndex {
 		return tboNative(handle, cfg, meeFilter, bases, quals, offsets, nReads, lo, hi, flags, insert, stats2)==0;
 	}
 
-	/** Quality trimming + minlen / maxlen / mbq / maxns for the batch processBatch() (and tboBatch()) answered
-	 * (replaces jgi/BBDuk.java:3074-3170): lo[] / hi[] / flags[] are updated in place; stats6 += {readsQTrimmed,
-	 * basesQTrimmed, readsQFiltered, basesQFiltered, readsNFiltered, basesNFiltered}. quals = Read.quality, flattened. */
+	/** Poly-X trimming, quality trimming and minlen / maxlen / mbq / maxns for the batch processBatch() (and tboBatch())
+	 * answered (replaces jgi/BBDuk.java:2954-3052, :3074-3170): lo[] / hi[] / flags[] are updated in place; stats8 +=
+	 * {readsQTrimmed, basesQTrimmed, readsQFiltered, basesQFiltered, readsNFiltered, basesNFiltered, readsPolyTrimmed,
+	 * basesPolyTrimmed}. quals = Read.quality, flattened. poly = {trimPolyA, trimPolyGLeft, trimPolyGRight, filterPolyG,
+	 * trimPolyCLeft, trimPolyCRight, filterPolyC, maxNonPoly}. */
 	public boolean qtrimBatch(boolean qtrimLeft, boolean qtrimRight, float trimq, int minBaseQuality, int maxNs, int maxReadLength,
-			byte[] bases, byte[] quals, long[] offsets, long nReads, boolean paired, int[] lo, int[] hi, byte[] flags, long[] stats6){
-		final int[] cfg={qtrimLeft ? 1 : 0, qtrimRight ? 1 : 0, minBaseQuality, maxNs, maxReadLength, 0};
-		return qtrimNative(handle, cfg, trimq, bases, quals, offsets, nReads, paired, lo, hi, flags, stats6)==0;
+			int[] poly, byte[] bases, byte[] quals, long[] offsets, long nReads, boolean paired, int[] lo, int[] hi, byte[] flags,
+			long[] stats8){
+		final int[] cfg={qtrimLeft ? 1 : 0, qtrimRight ? 1 : 0, minBaseQuality, maxNs, maxReadLength, 0,
+				poly[0], poly[1], poly[2], poly[3], poly[4], poly[5], poly[6], poly[7]};
+		return qtrimNative(handle, cfg, trimq, bases, quals, offsets, nReads, paired, lo, hi, flags, stats8)==0;
 	}
 
 	@Override public int getValue(long kmer, long rkmer, long lengthMask, int qPos, int len, int qHDist){
@@ -91,7 +95,7 @@ public final class BBDukIndexGPU extends BBDukIndex {
 	private static native int tboNative(long h, int[] cfg, float meeFilter, byte[] bases, byte[] quals, long[] offsets, long nReads,
 			int[] lo, int[] hi, byte[] flags, int[] insert, long[] stats2);
 	private static native int qtrimNative(long h, int[] cfg, float trimq, byte[] bases, byte[] quals, long[] offsets, long nReads,
-			boolean paired, int[] lo, int[] hi, byte[] flags, long[] stats6);
+			boolean paired, int[] lo, int[] hi, byte[] flags, long[] stats8);
 	private static native int scaffoldCountsNative(long h, long[] reads, long[] bases);
 	private static native String lastErrorNative(long h);
 	private static native void destroyNative(long h);

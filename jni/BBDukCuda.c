@@ -124,25 +124,35 @@ JNIEXPORT jint JNICALL Java_bbduk_BBDukIndexGPU_tboNative(JNIEnv *env, jclass cl
     return rc;
 }
 
-/* Replaces the quality-trimming and quality-filtering blocks of the per-pair loop (jgi/BBDuk.java:3074-3170) for the batch
- * that processNative (and tboNative) answered: lo[], hi[] and flags[] are updated in place, stats6 += {readsQTrimmed,
- * basesQTrimmed, readsQFiltered, basesQFiltered, readsNFiltered, basesNFiltered}.
- * qCfg = {qtrimLeft, qtrimRight, minBaseQuality, maxNs (-1 off), maxReadLength (0 unlimited), qualOffset (0 for Read.quality)}. */
+/* Replaces the poly-X, quality-trimming and quality-filtering blocks of the per-pair loop (jgi/BBDuk.java:2954-3052,
+ * :3074-3170) for the batch that processNative (and tboNative) answered: lo[], hi[] and flags[] are updated in place,
+ * stats8 += {readsQTrimmed, basesQTrimmed, readsQFiltered, basesQFiltered, readsNFiltered, basesNFiltered, readsPolyTrimmed,
+ * basesPolyTrimmed}. qCfg = {qtrimLeft, qtrimRight, minBaseQuality, maxNs (-1 off), maxReadLength (0 unlimited), qualOffset
+ * (0 for Read.quality), trimPolyA, trimPolyGLeft, trimPolyGRight, filterPolyG, trimPolyCLeft, trimPolyCRight, filterPolyC,
+ * maxNonPoly}. */
 JNIEXPORT jint JNICALL Java_bbduk_BBDukIndexGPU_qtrimNative(JNIEnv *env, jclass cls, jlong handle, jintArray jcfg, jfloat trimq,
                                                             jbyteArray jbases, jbyteArray jquals, jlongArray joffsets, jlong nReads,
                                                             jboolean paired, jintArray jlo, jintArray jhi, jbyteArray jflags,
-                                                            jlongArray jstats6) {
+                                                            jlongArray jstats8) {
     bbduk_qtrim_cfg cfg;
-    jint c[6];
-    int64_t st[6] = {0, 0, 0, 0, 0, 0};
+    jint c[14];
+    int64_t st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bbduk_b200_qtrim_cfg_default(&cfg);
-    (*env)->GetIntArrayRegion(env, jcfg, 0, 6, c);
+    (*env)->GetIntArrayRegion(env, jcfg, 0, 14, c);
     cfg.qtrim_left = c[0];
     cfg.qtrim_right = c[1];
     cfg.min_base_quality = c[2];
     cfg.max_ns = c[3];
     cfg.max_read_length = c[4];
     cfg.qual_offset = c[5];
+    cfg.trim_poly_a = c[6];
+    cfg.trim_poly_g_left = c[7];
+    cfg.trim_poly_g_right = c[8];
+    cfg.filter_poly_g = c[9];
+    cfg.trim_poly_c_left = c[10];
+    cfg.trim_poly_c_right = c[11];
+    cfg.filter_poly_c = c[12];
+    cfg.max_non_poly = c[13];
     cfg.trimq = trimq;
     jbyte *b = (jbyte *)(*env)->GetPrimitiveArrayCritical(env, jbases, NULL);
     jbyte *q = jquals ? (jbyte *)(*env)->GetPrimitiveArrayCritical(env, jquals, NULL) : NULL;
@@ -159,11 +169,11 @@ JNIEXPORT jint JNICALL Java_bbduk_BBDukIndexGPU_qtrimNative(JNIEnv *env, jclass 
     (*env)->ReleasePrimitiveArrayCritical(env, joffsets, o, JNI_ABORT);
     if (jquals) (*env)->ReleasePrimitiveArrayCritical(env, jquals, q, JNI_ABORT);
     (*env)->ReleasePrimitiveArrayCritical(env, jbases, b, JNI_ABORT);
-    if (jstats6 && !rc) {
-        jlong v[6];
-        (*env)->GetLongArrayRegion(env, jstats6, 0, 6, v);
-        for (int i = 0; i < 6; i++) v[i] += st[i];
-        (*env)->SetLongArrayRegion(env, jstats6, 0, 6, v);
+    if (jstats8 && !rc) {
+        jlong v[8];
+        (*env)->GetLongArrayRegion(env, jstats8, 0, 8, v);
+        for (int i = 0; i < 8; i++) v[i] += st[i];
+        (*env)->SetLongArrayRegion(env, jstats8, 0, 8, v);
     }
     return rc;
 }

@@ -12,7 +12,9 @@ class QtrimParams(C.Structure):
     _fields_ = [("qtrim_left", C.c_int32), ("qtrim_right", C.c_int32), ("trimq", C.c_float), ("min_base_quality", C.c_int32),
                 ("max_ns", C.c_int32), ("max_read_length", C.c_int32), ("qual_offset", C.c_int32),
                 ("min_read_length", C.c_int32), ("min_len_fraction", C.c_float), ("remove_pairs_if_either_bad", C.c_int32),
-                ("trim_failures_to_1bp", C.c_int32)]
+                ("trim_failures_to_1bp", C.c_int32), ("trim_poly_a", C.c_int32), ("trim_poly_g_left", C.c_int32),
+                ("trim_poly_g_right", C.c_int32), ("filter_poly_g", C.c_int32), ("trim_poly_c_left", C.c_int32),
+                ("trim_poly_c_right", C.c_int32), ("filter_poly_c", C.c_int32), ("max_non_poly", C.c_int32)]
 
 
 _LIB = None
@@ -28,24 +30,27 @@ def lib():
     return _LIB
 
 
-def params(qtrim="rl", trimq=6.0, mbq=0, maxns=-1, maxlen=0, qual_offset=33, minlen=10, mlf=0.0, rieb=True, tf1=False) -> QtrimParams:
+def params(qtrim="rl", trimq=6.0, mbq=0, maxns=-1, maxlen=0, qual_offset=33, minlen=10, mlf=0.0, rieb=True, tf1=False,
+           polya=0, polyg=(0, 0), fpolyg=0, polyc=(0, 0), fpolyc=0, maxnonpoly=1) -> QtrimParams:
     """defaults of jgi/BBDuk.java (:126 trimq, minlen 10, rieb) for the fields the block reads"""
     p = QtrimParams()
     p.qtrim_left, p.qtrim_right = int("l" in qtrim), int("r" in qtrim)
     p.trimq, p.min_base_quality, p.max_ns, p.max_read_length, p.qual_offset = trimq, mbq, maxns, maxlen, qual_offset
     p.min_read_length, p.min_len_fraction = minlen, mlf
     p.remove_pairs_if_either_bad, p.trim_failures_to_1bp = int(rieb and not tf1), int(tf1)  # jgi/BBDuk.java:631
+    p.trim_poly_a, p.filter_poly_g, p.filter_poly_c, p.max_non_poly = polya, fpolyg, fpolyc, maxnonpoly
+    (p.trim_poly_g_left, p.trim_poly_g_right), (p.trim_poly_c_left, p.trim_poly_c_right) = polyg, polyc
     return p
 
 
 def process(bases, quals, offsets, paired, lo, hi, flags, p: QtrimParams):
-    """-> (new lo, new hi, new flags, stats6)"""
+    """-> (new lo, new hi, new flags, stats8)"""
     bases = np.ascontiguousarray(bases, np.uint8)
     offsets = np.ascontiguousarray(offsets, np.int64)
     lo2 = np.array(lo, np.int32, copy=True)
     hi2 = np.array(hi, np.int32, copy=True)
     fl2 = np.array(flags, np.uint8, copy=True)
-    st = np.zeros(6, np.int64)
+    st = np.zeros(8, np.int64)
     q = None if quals is None else np.ascontiguousarray(quals, np.uint8)
     lib().qtrim_ora_process(bases.ctypes.data, None if q is None else q.ctypes.data, offsets.ctypes.data, len(offsets) - 1,
                             int(bool(paired)), lo2.ctypes.data, hi2.ctypes.data, fl2.ctypes.data, C.byref(p), st.ctypes.data)

@@ -7,6 +7,10 @@
  * tests/test_qtrim_oracle.py.
  *
  * Follows, statement by statement (paths relative to /root/reference/current):
+ *   jgi/BBDuk.java:2954-3052, :4721-4825 poly-A / poly-G / poly-C trimming and filtering (trimPolyA, trimPoly, detectPolyLeft,
+ *                                       detectPolyRight; stream/Read.java:3387-3401 countLeft / countRight), each with its
+ *                                       minlen test and shouldRemove -- including the reference's use of r1 in the
+ *                                       filterpolyc test of r2 (:3035)
  *   jgi/BBDuk.java:3074-3108            "Do quality trimming": trimFast of r1 and r2, minlen / maxlen, shouldRemove
  *   jgi/BBDuk.java:3110-3170            "Do quality filtering": minbasequality, maxns, shouldRemove (minavgquality,
  *                                       maxnrate, minconsecutivebases, minbasefrequency at their defaults = off)
@@ -30,6 +34,9 @@ typedef struct qtrim_params {
     int32_t min_read_length;
     float min_len_fraction;
     int32_t remove_pairs_if_either_bad, trim_failures_to_1bp;
+    /* poly-X (parse/Parser.java:386-411, :1815-1831) */
+    int32_t trim_poly_a, trim_poly_g_left, trim_poly_g_right, filter_poly_g, trim_poly_c_left, trim_poly_c_right, filter_poly_c,
+        max_non_poly;
 } qtrim_params;
 
 static float g_pe[128];
@@ -123,6 +130,81 @@ static int trim_fast(qread *r, const qtrim_params *p, float trimE) {
     return trim_by_amount(r, p->qtrim_left ? a0 : 0, p->qtrim_right ? b0 : 0, 1);
 }
 
+/* stream/Read.java:3387-3401 on the kept interval */
+static int count_left(const qread *r, uint8_t c) {
+    const int n = r->hi - r->lo;
+    for (int i = 0; i < n; i++)
+        if (r->bases[r->lo + i] != c) return i;
+    return n;
+}
+static int count_right(const qread *r, uint8_t c) {
+    const int n = r->hi - r->lo;
+    for (int i = n - 1; i >= 0; i--)
+        if (r->bases[r->lo + i] != c) return n - i - 1;
+    return n;
+}
+
+/* jgi/BBDuk.java:4721-4736 */
+static int trim_poly_a(qread *r, int minPoly) {
+    if (r->hi - r->lo < minPoly) return 0;
+    int la = count_left(r, 'A'), lt = count_left(r, 'T'), ra = count_right(r, 'A'), rt = count_right(r, 'T');
+    int left = la > lt ? la : lt, right = ra > rt ? ra : rt;
+    if (left < minPoly) left = 0;
+    if (right < minPoly) right = 0;
+    int trimmed = 0;
+    if (left > 0 || right > 0) trimmed = trim_by_amount(r, left, right, 1);
+    return trimmed;
+}
+
+/* jgi/BBDuk.java:4771-4791 */
+static int detect_poly_left(const qread *r, int minPoly, int maxNonPoly, uint8_t c) {
+    const int n = r->hi - r->lo;
+    if (n < minPoly) return 0;
+    int trimTo = -1;
+    for (int i = 0, polymer = 0, nonpoly = 0; i < n && nonpoly <= maxNonPoly; i++) {
+        if (r->bases[r->lo + i] == c) {
+            polymer++;
+            if (polymer >= minPoly) {
+                nonpoly = 0;
+                trimTo = i;
+            }
+        } else {
+            polymer = 0;
+            nonpoly++;
+        }
+    }
+    return trimTo + 1;
+}
+
+/* jgi/BBDuk.java:4802-4822 */
+static int detect_poly_right(const qread *r, int minPoly, int maxNonPoly, uint8_t c) {
+    const int n = r->hi - r->lo;
+    if (n < minPoly) return 0;
+    int trimTo = n;
+    for (int i = n - 1, polymer = 0, nonpoly = 0; i >= 0 && nonpoly <= maxNonPoly; i--) {
+        if (r->bases[r->lo + i] == c) {
+            polymer++;
+            if (polymer >= minPoly) {
+                nonpoly = 0;
+                trimTo = i;
+            }
+        } else {
+            polymer = 0;
+            nonpoly++;
+        }
+    }
+    return n - trimTo;
+}
+
+/* jgi/BBDuk.java:4747-4760 */
+static int trim_poly(qread *r, int minLeft, int minRight, int maxNonPoly, uint8_t c) {
+    const int left = minLeft > 0 ? detect_poly_left(r, minLeft, maxNonPoly, c) : 0;
+    const int right = minRight > 0 ? detect_poly_right(r, minRight, maxNonPoly, c) : 0;
+    int trimmed = 0;
+    if (left > 0 || right > 0) trimmed = trim_by_amount(r, left, right, 1);
+    return trimmed;
+}
+
 static void set_discarded(const qtrim_params *p, qread *r) { /* jgi/BBDuk.java:3260-3266 */
     if (p->trim_failures_to_1bp) {
         if (r->hi - r->lo > 1) trim_by_amount(r, 0, r->hi - r->lo - 1, 1);
@@ -145,7 +227,8 @@ static int should_remove(const qtrim_params *p, const qread *r1, const qread *r2
 /*
  * For every unit (read, or pair 2i / 2i+1) of a batch that went through the k-mer block: reads keep [lo,hi) of their
  * original bases; flags bit 0x01 = discarded, 0x02 = unit removed. lo / hi / flags are updated in place (0x40 = quality
- * trimmed); stats[0..5] += readsQTrimmed, basesQTrimmed, readsQFiltered, basesQFiltered, readsNFiltered, basesNFiltered.
+ * trimmed, 0x80 = poly-X trimmed); stats[0..7] += readsQTrimmed, basesQTrimmed, readsQFiltered, basesQFiltered,
+ * readsNFiltered, basesNFiltered, readsPolyTrimmed, basesPolyTrimmed.
  */
 void qtrim_ora_process(const uint8_t *bases, const uint8_t *quals, const int64_t *offsets, int64_t n_reads, int paired,
                        int32_t *lo, int32_t *hi, uint8_t *flags, const qtrim_params *p, int64_t *stats) {
@@ -170,8 +253,49 @@ void qtrim_ora_process(const uint8_t *bases, const uint8_t *quals, const int64_t
         }
         qread *r1 = &rr[0], *r2 = per == 2 ? &rr[1] : NULL;
         int remove = 0;
-        int qtrimmed[2] = {0, 0};
+        int qtrimmed[2] = {0, 0}, ptrimmed[2] = {0, 0};
+        /* :2954-2979 poly-A */
+        if (!remove && p->trim_poly_a > 0) {
+            for (int q = 0; q < per; q++) {
+                const int x = trim_poly_a(&rr[q], p->trim_poly_a);
+                stats[7] += x;
+                stats[6] += (x > 0 ? 1 : 0);
+                ptrimmed[q] |= x > 0;
+                if (rr[q].hi - rr[q].lo < minlen[q]) set_discarded(p, &rr[q]);
+            }
+            if (should_remove(p, r1, r2)) {
+                stats[7] += (r1->hi - r1->lo) + (r2 ? r2->hi - r2->lo : 0);
+                remove = 1;
+            }
+        }
+        /* :2981-3016 poly-G, :3018-3052 poly-C */
+        for (int which = 0; which < 2; which++) {
+            const uint8_t c = which == 0 ? 'G' : 'C';
+            const int tl = which == 0 ? p->trim_poly_g_left : p->trim_poly_c_left;
+            const int tr = which == 0 ? p->trim_poly_g_right : p->trim_poly_c_right;
+            const int fp = which == 0 ? p->filter_poly_g : p->filter_poly_c;
+            if (remove || !(tl > 0 || tr > 0 || fp > 0)) continue;
+            for (int q = 0; q < per; q++) {
+                /* the poly-C filter of r2 looks at r1 (:3035) */
+                const qread *probe = (which == 1 && q == 1) ? r1 : &rr[q];
+                if (fp > 0 && detect_poly_left(probe, fp, p->max_non_poly, c) >= fp) {
+                    set_discarded(p, &rr[q]);
+                    stats[6] += 1;
+                } else if (tl > 0 || tr > 0) {
+                    const int x = trim_poly(&rr[q], tl, tr, p->max_non_poly, c);
+                    stats[7] += x;
+                    stats[6] += (x > 0 ? 1 : 0);
+                    ptrimmed[q] |= x > 0;
+                    if (rr[q].hi - rr[q].lo < minlen[q]) set_discarded(p, &rr[q]);
+                }
+            }
+            if (should_remove(p, r1, r2)) {
+                stats[7] += (r1->hi - r1->lo) + (r2 ? r2->hi - r2->lo : 0);
+                remove = 1;
+            }
+        }
         /* :3074-3108 */
+        if (!remove) {
         if (p->qtrim_left || p->qtrim_right) {
             for (int q = 0; q < per; q++) {
                 const int x = trim_fast(&rr[q], p, trimE);
@@ -189,6 +313,7 @@ void qtrim_ora_process(const uint8_t *bases, const uint8_t *quals, const int64_t
         if (should_remove(p, r1, r2)) {
             stats[1] += (r1->hi - r1->lo) + (r2 ? r2->hi - r2->lo : 0); /* basesQTrimmedT+=r1.pairLength() */
             remove = 1;
+        }
         }
         /* :3110-3170 */
         if (!remove) {
@@ -228,6 +353,7 @@ void qtrim_ora_process(const uint8_t *bases, const uint8_t *quals, const int64_t
             if (rr[q].discarded) f |= 0x01;
             if (remove) f |= 0x02;
             if (qtrimmed[q]) f |= 0x40;
+            if (ptrimmed[q]) f |= 0x80;
             flags[i] = f;
         }
     }

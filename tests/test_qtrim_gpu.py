@@ -1,5 +1,5 @@
-"""GPU parity of quality trimming + the quality / length / N filters (bbduk_b200_qtrim / _qtrim_device) against the
-oracle: kept intervals, flags and the six counters, bit for bit -- including every single-precision comparison of
+"""GPU parity of poly-X trimming, quality trimming + the quality / length / N filters (bbduk_b200_qtrim / _qtrim_device) against the
+oracle: kept intervals, flags and the eight counters, bit for bit -- including every single-precision comparison of
 the running score."""
 import numpy as np
 import pytest
@@ -18,9 +18,12 @@ def engine(minlen=10, mlf=0.0, rieb=True, tf1=False, **_):
                                   trim_failures_to_1bp=int(tf1)))
 
 
-def dev_cfg(g, qtrim="rl", trimq=6.0, mbq=0, maxns=-1, maxlen=0, qual_offset=33, **_):
+def dev_cfg(g, qtrim="rl", trimq=6.0, mbq=0, maxns=-1, maxlen=0, qual_offset=33, polya=0, polyg=(0, 0), fpolyg=0, polyc=(0, 0),
+            fpolyc=0, maxnonpoly=1, **_):
     return g.qtrim_cfg(qtrim_left=int("l" in qtrim), qtrim_right=int("r" in qtrim), trimq=trimq, min_base_quality=mbq, max_ns=maxns,
-                       max_read_length=maxlen, qual_offset=qual_offset)
+                       max_read_length=maxlen, qual_offset=qual_offset, trim_poly_a=polya, trim_poly_g_left=polyg[0],
+                       trim_poly_g_right=polyg[1], filter_poly_g=fpolyg, trim_poly_c_left=polyc[0], trim_poly_c_right=polyc[1],
+                       filter_poly_c=fpolyc, max_non_poly=maxnonpoly)
 
 
 def check(case, bases, quals, offsets, paired, lo, hi, flags):
@@ -52,7 +55,7 @@ def test_numeric_qualities_and_empty_batches():
     g = engine()
     z = np.zeros(0, np.int32)
     out = Outputs(0)
-    assert list(g.qtrim(np.zeros(0, np.uint8), np.zeros(0, np.uint8), np.zeros(1, np.int64), True, out, dev_cfg(g))) == [0] * 6
+    assert list(g.qtrim(np.zeros(0, np.uint8), np.zeros(0, np.uint8), np.zeros(1, np.int64), True, out, dev_cfg(g))) == [0] * 8
     assert z.size == 0
 
 
@@ -96,7 +99,7 @@ def test_device_entry_point_and_alignment_error():
     want = oq.process(bases, quals, offsets, True, lo, hi, flags, oq.params(**case))
     d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
     d_lo, d_hi, d_fl = d(lo), d(hi), d(flags)
-    d_st = torch.zeros(6, dtype=torch.int64, device="cuda")
+    d_st = torch.zeros(8, dtype=torch.int64, device="cuda")
     d_b, d_q = d(bases), d(quals)
     g.qtrim_device(d_b, d_q, d(offsets.astype(np.int32)), len(lo), True, d_lo, d_hi, d_fl, dev_cfg(g, **case), d_st)
     torch.cuda.synchronize()

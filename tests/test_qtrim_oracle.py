@@ -1,6 +1,7 @@
-"""CPU test of the quality-trimming / quality-filter oracle (oracle/qtrim_oracle.c) against an independently written
-Python restatement of jgi/BBDuk.java:3074-3170 + shared/TrimRead.java:140-169, :299-410 that finds the kept run by
-enumerating prefix sums with numpy float32 instead of the reference's running-score loop."""
+"""CPU test of the poly-X / quality-trimming / quality-filter oracle (oracle/qtrim_oracle.c) against an independently
+written Python restatement of jgi/BBDuk.java:2954-3052, :3074-3170, :4721-4825 + shared/TrimRead.java:140-169, :299-410
+(poly-X runs found with regular expressions / string scans instead of the reference's counters), plus hand-checked cases."""
+import re
 import numpy as np
 import pytest
 
@@ -50,9 +51,30 @@ def trim_by_amount(lo, hi, left, right, m):
     return lo + left, hi - right, left + right
 
 
+def py_detect_left(seq, min_poly, max_non, c):
+    """jgi/BBDuk.java:4771-4791 on a bytes object: walk runs of c; a run of >= min_poly resets the error budget"""
+    if len(seq) < min_poly:
+        return 0
+    trim_to, non, i = -1, 0, 0
+    for m in re.finditer(b"[^" + c + b"]|" + c + b"+", seq):
+        tok = m.group()
+        if tok[:1] == c:
+            if len(tok) >= min_poly:
+                non, trim_to = 0, m.end() - 1
+        else:
+            non += 1
+            if non > max_non:
+                break
+    return trim_to + 1
+
+
+def py_detect_right(seq, min_poly, max_non, c):
+    return py_detect_left(seq[::-1], min_poly, max_non, c)
+
+
 def py_block(bases, quals, offsets, paired, lo, hi, flags, p):
     lo, hi, flags = lo.copy(), hi.copy(), flags.copy()
-    st = np.zeros(6, np.int64)
+    st = np.zeros(8, np.int64)
     e = trim_e(p.trimq)
     per = 2 if paired else 1
     tf1, rieb = bool(p.trim_failures_to_1bp), bool(p.remove_pairs_if_either_bad)
@@ -79,6 +101,65 @@ def py_block(bases, quals, offsets, paired, lo, hi, flags, p):
             d = [disc(i, state) for i in idx]
             return (rieb and any(d)) or all(d)
 
+        pt = {i: False for i in idx}
+        remove = False
+
+        def seq_of(i):
+            return bytes(bases[offsets[i] + lo[i]:offsets[i] + hi[i]])
+
+        def minlen_of(i):
+            L = offsets[i + 1] - offsets[i]
+            return int(max(F32(F32(L) * F32(p.min_len_fraction)), F32(p.min_read_length)))
+
+        def close_poly():
+            if should_remove():
+                st[7] += sum(hi[i] - lo[i] for i in idx)
+                return True
+            return False
+
+        if p.trim_poly_a > 0:
+            for i in idx:
+                sq = seq_of(i)
+                x = 0
+                if len(sq) >= p.trim_poly_a:
+                    left = max(len(sq) - len(sq.lstrip(b"A")), len(sq) - len(sq.lstrip(b"T")))
+                    right = max(len(sq) - len(sq.rstrip(b"A")), len(sq) - len(sq.rstrip(b"T")))
+                    left = left if left >= p.trim_poly_a else 0
+                    right = right if right >= p.trim_poly_a else 0
+                    if left or right:
+                        lo[i], hi[i], x = trim_by_amount(lo[i], hi[i], left, right, 1)
+                st[7] += x
+                st[6] += x > 0
+                pt[i] |= x > 0
+                if hi[i] - lo[i] < minlen_of(i):
+                    set_discarded(i)
+            remove = close_poly()
+        for c, tl, tr, fp in ((b"G", p.trim_poly_g_left, p.trim_poly_g_right, p.filter_poly_g),
+                              (b"C", p.trim_poly_c_left, p.trim_poly_c_right, p.filter_poly_c)):
+            if remove or not (tl > 0 or tr > 0 or fp > 0):
+                continue
+            for i in idx:
+                probe = idx[0] if (c == b"C" and i != idx[0]) else i  # the reference tests r1 for r2's poly-C filter
+                if fp > 0 and py_detect_left(seq_of(probe), fp, p.max_non_poly, c) >= fp:
+                    set_discarded(i)
+                    st[6] += 1
+                elif tl > 0 or tr > 0:
+                    sq = seq_of(i)
+                    left = py_detect_left(sq, tl, p.max_non_poly, c) if tl > 0 else 0
+                    right = py_detect_right(sq, tr, p.max_non_poly, c) if tr > 0 else 0
+                    x = 0
+                    if left or right:
+                        lo[i], hi[i], x = trim_by_amount(lo[i], hi[i], left, right, 1)
+                    st[7] += x
+                    st[6] += x > 0
+                    pt[i] |= x > 0
+                    if hi[i] - lo[i] < minlen_of(i):
+                        set_discarded(i)
+            remove = close_poly()
+        if remove:
+            for i in idx:
+                flags[i] = (flags[i] & ~np.uint8(3)) | (1 if state[i] else 0) | 2 | (0x80 if pt[i] else 0)
+            continue
         if p.qtrim_left or p.qtrim_right:
             for i in idx:
                 if hi[i] - lo[i] < 1:
@@ -120,7 +201,8 @@ def py_block(bases, quals, offsets, paired, lo, hi, flags, p):
                 st[2] += per
                 remove = True
         for i in idx:
-            flags[i] = (flags[i] & ~np.uint8(3)) | (1 if state[i] else 0) | (2 if remove else 0) | (0x40 if qt[i] else 0)
+            flags[i] = (flags[i] & ~np.uint8(3)) | (1 if state[i] else 0) | (2 if remove else 0) | (0x40 if qt[i] else 0) | \
+                (0x80 if pt[i] else 0)
     return lo, hi, flags, st
 
 
@@ -154,6 +236,18 @@ def qual_batch(n, seed, L=80, paired=True):
         else:
             q = rng.integers(0, 42, ln)
         quals[offsets[i]:offsets[i + 1]] = q
+    for i in range(n):  # homopolymer heads / tails, some with an interruption
+        ln = int(lens[i])
+        if ln < 12:
+            continue
+        for side in (0, 1):
+            if rng.random() < 0.25:
+                k = int(rng.integers(1, 14))
+                c = rng.choice(np.frombuffer(b"AATGGC", np.uint8))
+                seg = slice(offsets[i], offsets[i] + k) if side == 0 else slice(offsets[i + 1] - k, offsets[i + 1])
+                bases[seg] = c
+                if k > 4 and rng.random() < 0.4:
+                    bases[seg.start + int(rng.integers(1, k - 1))] = ord("A") if c != ord("A") else ord("C")
     nn = rng.random(len(bases)) < 0.02
     bases[nn] = ord("N")
     odd = rng.random(len(bases)) < 0.003
@@ -177,7 +271,10 @@ def qual_batch(n, seed, L=80, paired=True):
 
 CASES = [dict(qtrim="rl", trimq=10.0), dict(qtrim="r", trimq=6.0), dict(qtrim="l", trimq=15.5, minlen=25),
          dict(qtrim="rl", trimq=20.0, rieb=False), dict(qtrim="rl", trimq=10.0, tf1=True, mbq=3),
-         dict(qtrim="", mbq=5, maxns=1), dict(qtrim="r", trimq=0.5, maxns=0, maxlen=70, mlf=0.5), dict(qtrim="rl", trimq=1.0)]
+         dict(qtrim="", mbq=5, maxns=1), dict(qtrim="r", trimq=0.5, maxns=0, maxlen=70, mlf=0.5), dict(qtrim="rl", trimq=1.0),
+         dict(qtrim="", polya=3, minlen=30), dict(qtrim="rl", trimq=8.0, polyg=(4, 4), fpolyc=5, maxnonpoly=1),
+         dict(qtrim="", polyg=(2, 0), polyc=(0, 3), fpolyg=6, maxnonpoly=0, rieb=False),
+         dict(qtrim="r", trimq=12.0, polya=2, polyg=(3, 3), polyc=(3, 3), fpolyg=8, fpolyc=8, maxnonpoly=2, tf1=True)]
 
 
 @pytest.mark.parametrize("case", range(len(CASES)))
@@ -203,16 +300,23 @@ def test_known_answers():
                                     oq.params(minlen=1, **kw))
         return int(lo[0]), int(hi[0]), int(fl[0]), list(st)
     # all bases better than trimq: nothing trimmed
-    assert one([30] * 20, trimq=10.0) == (0, 20, 0, [0, 0, 0, 0, 0, 0])
+    assert one([30] * 20, trimq=10.0) == (0, 20, 0, [0, 0, 0, 0, 0, 0, 0, 0])
     # a bad tail: the five Q2 bases go
-    assert one([30] * 15 + [2] * 5, trimq=10.0) == (0, 15, 0x40, [1, 5, 0, 0, 0, 0])
+    assert one([30] * 15 + [2] * 5, trimq=10.0) == (0, 15, 0x40, [1, 5, 0, 0, 0, 0, 0, 0])
     # bad head and tail, qtrim=r only trims the tail
-    assert one([2] * 4 + [30] * 10 + [2] * 6, qtrim="r", trimq=10.0) == (0, 14, 0x40, [1, 6, 0, 0, 0, 0])
-    assert one([2] * 4 + [30] * 10 + [2] * 6, qtrim="rl", trimq=10.0) == (4, 14, 0x40, [1, 10, 0, 0, 0, 0])
+    assert one([2] * 4 + [30] * 10 + [2] * 6, qtrim="r", trimq=10.0) == (0, 14, 0x40, [1, 6, 0, 0, 0, 0, 0, 0])
+    assert one([2] * 4 + [30] * 10 + [2] * 6, qtrim="rl", trimq=10.0) == (4, 14, 0x40, [1, 10, 0, 0, 0, 0, 0, 0])
     # everything bad: trimByAmount keeps one base (right = len - 1), then minlen=1 keeps the read
-    assert one([2] * 12, trimq=10.0) == (0, 1, 0x40, [1, 11, 0, 0, 0, 0])
+    assert one([2] * 12, trimq=10.0) == (0, 1, 0x40, [1, 11, 0, 0, 0, 0, 0, 0])
     # an N costs 0.75 - 0.1 = 6.5 good bases: after 5 good bases the run dies and the longer side is kept, after 8 it survives
     lo, hi, fl, st = one([35] * 30, seq="A" * 5 + "N" + "A" * 24, trimq=10.0)
     assert (lo, hi) == (6, 30)
     lo, hi, fl, st = one([35] * 30, seq="A" * 8 + "N" + "A" * 21, trimq=10.0)
     assert (lo, hi) == (0, 30)
+    # poly-X: trimpolya takes A or T runs of >= 3 from both ends; trimpolyg tolerates one non-G inside the tail
+    assert one([35] * 20, seq="TTTTCGCGCGCGCGCGCAAA", qtrim="", polya=3) == (4, 17, 0x80, [0, 0, 0, 0, 0, 0, 1, 7])
+    assert one([35] * 20, seq="TTCGCGCGCGCGCGCGCGAA", qtrim="", polya=3) == (0, 20, 0, [0] * 8)
+    assert one([35] * 20, seq="ACGTACGTACGTGGGGAGGG", qtrim="", polyg=(0, 3), maxnonpoly=1) == (0, 12, 0x80, [0, 0, 0, 0, 0, 0, 1, 8])
+    assert one([35] * 20, seq="ACGTACGTACGTGGGGAGGG", qtrim="", polyg=(0, 3), maxnonpoly=0) == (0, 17, 0x80, [0, 0, 0, 0, 0, 0, 1, 3])
+    # filterpolyg discards (flag 1, unit removed 2) and counts the read, not its bases... the pair length goes to basesPoly
+    assert one([35] * 20, seq="GGGGGGGGACGTACGTACGT", qtrim="", fpolyg=6) == (0, 20, 0x03, [0, 0, 0, 0, 0, 0, 1, 20])

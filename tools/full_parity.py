@@ -65,9 +65,9 @@ def main():
     d_stats = torch.zeros(8, dtype=torch.int64, device="cuda")
     from concurrent.futures import ThreadPoolExecutor
     pool = ThreadPoolExecutor(cores)
-    tbo_tot, q_tot = np.zeros(2, np.int64), np.zeros(6, np.int64)
+    tbo_tot, q_tot = np.zeros(2, np.int64), np.zeros(8, np.int64)
     d_tst = torch.zeros(2, dtype=torch.int64, device="cuda")
-    d_qst = torch.zeros(6, dtype=torch.int64, device="cuda")
+    d_qst = torch.zeros(8, dtype=torch.int64, device="cuda")
     t_tbo = t_tbo_cpu = t_q = t_q_cpu = 0.0
     gen = torch.Generator(device="cuda")
     gen.manual_seed(99)
@@ -171,7 +171,7 @@ def main():
                         "gpu_s": round(t_tbo, 3), "oracle_s": round(t_tbo_cpu, 3)}
         assert extra["tbo"]["counters_equal"]
     if args.qtrim:
-        extra["qtrim"] = {"stats6": q_tot.tolist(), "counters_equal": d_qst.cpu().tolist() == q_tot.tolist(), "gpu_s": round(t_q, 3),
+        extra["qtrim"] = {"stats8": q_tot.tolist(), "counters_equal": d_qst.cpu().tolist() == q_tot.tolist(), "gpu_s": round(t_q, 3),
                           "oracle_s": round(t_q_cpu, 3), "command": "qtrim=rl trimq=10, synthetic qualities decaying from Q40 (torch generator seed 99)"}
         assert extra["qtrim"]["counters_equal"]
     print(json.dumps({"workload": args.workload, "reads": 2 * args.pairs, "stored_kmers": stored, "mismatching_fields": mism, **extra,
