@@ -345,17 +345,35 @@ TBO_HD uint32_t range_bits(int w, int lo, int hi) {
     return ((2u << r_hi) - 1u) & ~((1u << r_lo) - 1u);
 }
 
+// An upper bound, cheap enough for the inner loop, of the largest mismatch count a badlimit of the form a * ov + b admits:
+// T[c] >= 0.9499 * c, so c <= limit * 1.0527; fixed point with constants rounded up, + 2 for the float roundings of the
+// reference's own limit (checked against cap_of for every ov by the host test).
+struct CapLine {
+    int a_fx, b_int;  // ((a_fx * ov) >> 16) + b_int
+#if defined(__CUDACC__)
+    __host__ __device__ __forceinline__
+#endif
+    int of(int ov) const { return ((a_fx * ov) >> 16) + b_int; }
+};
+TBO_HD CapLine cap_line(float a, float b) {
+    CapLine c;
+    c.a_fx = (int)(a * 1.0527f * 65536.0f) + 2;
+    c.b_int = (int)(b * 1.0527f) + 3;
+    return c;
+}
+
 template <bool GENERAL, int NW, bool MASKED>
 TBO_HD uint32_t scan_word(const uint32_t (&fh)[NW], const uint32_t (&fl)[NW], const uint32_t (&fn)[NW], const uint32_t (&vh)[NW + 1],
-                          const uint32_t (&vl)[NW + 1], const uint32_t (&vn)[NW + 1], int X, int Y, int s0, int cap) {
+                          const uint32_t (&vl)[NW + 1], const uint32_t (&vn)[NW + 1], int X, int Y, int s0, int cap, CapLine cl) {
     uint32_t bits = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 4
 #endif
     for (uint32_t r = 0; r < 32; r++) {
-        int n = -cap - 1;  // the sign bit of n after the counts says "at most cap mismatches"
         // ov < 0 only for s beyond the side's range; those bits are cleared by the caller (range_bits)
         const int ov = MASKED ? imin(X - (s0 + (int)r), Y) : 0;
+        // the sign bit of n after the counts says "at most cap mismatches"; short overlaps get their own, smaller cap
+        int n = MASKED ? ~imin(cap, cl.of(ov)) : ~cap;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -377,7 +395,7 @@ TBO_HD uint32_t scan_word(const uint32_t (&fh)[NW], const uint32_t (&fl)[NW], co
 // sliding mate, Y = of the fixed one: ov(s) = min(X - s, Y).
 template <bool GENERAL, int S, int NW>
 TBO_HD void scan_side(const uint32_t *sh, const uint32_t *sl, const uint32_t *sn, const uint32_t *fhp, const uint32_t *flp,
-                      const uint32_t *fnp, int X, int Y, int s_lo, int s_hi, int cap, uint32_t *cand) {
+                      const uint32_t *fnp, int X, int Y, int s_lo, int s_hi, int cap, CapLine cl, uint32_t *cand) {
     if (s_hi < s_lo) return;
     uint32_t fh[NW], fl[NW], fn[NW];
     for (int k = 0; k < NW; k++) {
@@ -394,8 +412,8 @@ TBO_HD void scan_side(const uint32_t *sh, const uint32_t *sl, const uint32_t *sn
         }
         // the shortest overlap of the word is at its last s; unmasked only if no lane of the warp needs the masks
         const bool masked = any_lane(imin(X - (32 * w + 31), Y) < 32 * NW);
-        const uint32_t bits = masked ? scan_word<GENERAL, NW, true>(fh, fl, fn, vh, vl, vn, X, Y, 32 * w, cap)
-                                     : scan_word<GENERAL, NW, false>(fh, fl, fn, vh, vl, vn, X, Y, 32 * w, cap);
+        const uint32_t bits = masked ? scan_word<GENERAL, NW, true>(fh, fl, fn, vh, vl, vn, X, Y, 32 * w, cap, cl)
+                                     : scan_word<GENERAL, NW, false>(fh, fl, fn, vh, vl, vn, X, Y, 32 * w, cap, cl);
         cand[w * S] = bits & range_bits(w, s_lo, s_hi);
     }
 }
@@ -411,7 +429,7 @@ struct Cands {
 };
 
 template <bool GENERAL, int S>
-TBO_HD void build_cands(const Ctx<S> &c, int alen, int blen, int i_top, int i_bot, int cap, Cands<S> &q) {
+TBO_HD void build_cands(const Ctx<S> &c, int alen, int blen, int i_top, int i_bot, int cap, CapLine cl, Cands<S> &q) {
     q.a_hi = i_top - blen;
     q.a_lo = imax(1, i_bot - blen);
     q.b_lo = imax(0, blen - i_top);
@@ -424,12 +442,15 @@ TBO_HD void build_cands(const Ctx<S> &c, int alen, int blen, int i_top, int i_bo
     if ((GENERAL && c.exact) || cap >= imin(longest, 90)) {  // no screen: the byte path, or a cap the screen cannot beat
         for (int w = imax(q.a_lo, 0) >> 5; w <= (q.a_hi >> 5) && q.a_hi >= q.a_lo; w++) q.A[w * S] = range_bits(w, q.a_lo, q.a_hi);
         for (int w = q.b_lo >> 5; w <= (q.b_hi >> 5) && q.b_hi >= q.b_lo; w++) q.B[w * S] = range_bits(w, q.b_lo, q.b_hi);
-    } else if (cap <= 43) {
-        scan_side<GENERAL, S, 2>(c.ah, c.al, c.an, c.bh, c.bl, c.bn, alen, blen, q.a_lo, q.a_hi, cap, q.A);
-        scan_side<GENERAL, S, 2>(c.bh, c.bl, c.bn, c.ah, c.al, c.an, blen, alen, q.b_lo, q.b_hi, cap, q.B);
+    } else if (!any_lane(cap > 43)) {  // one window width per warp (a wider window than a lane needs is still a valid screen)
+        // The screen never needs the N planes: the packer codes an N as A, and with that reading a position counts as a
+        // mismatch at most as often as by the reference's N rules (N against a base: always bad there, bad here unless the
+        // base is A; N against N: bad in neither) -- a lower bound is all the screen promises.
+        scan_side<false, S, 2>(c.ah, c.al, c.an, c.bh, c.bl, c.bn, alen, blen, q.a_lo, q.a_hi, cap, cl, q.A);
+        scan_side<false, S, 2>(c.bh, c.bl, c.bn, c.ah, c.al, c.an, blen, alen, q.b_lo, q.b_hi, cap, cl, q.B);
     } else {
-        scan_side<GENERAL, S, 4>(c.ah, c.al, c.an, c.bh, c.bl, c.bn, alen, blen, q.a_lo, q.a_hi, cap, q.A);
-        scan_side<GENERAL, S, 4>(c.bh, c.bl, c.bn, c.ah, c.al, c.an, blen, alen, q.b_lo, q.b_hi, cap, q.B);
+        scan_side<false, S, 4>(c.ah, c.al, c.an, c.bh, c.bl, c.bn, alen, blen, q.a_lo, q.a_hi, cap, cl, q.A);
+        scan_side<false, S, 4>(c.bh, c.bl, c.bn, c.ah, c.al, c.an, blen, alen, q.b_lo, q.b_hi, cap, cl, q.B);
     }
     if (q.a_hi >= q.a_lo) {
         q.phase = 0;
@@ -498,7 +519,7 @@ TBO_HD float find_best_ratio(const Ctx<S> &c, Cands<S> &q, int alen, int blen, i
     // badlimit never exceeds its value for the initial bestRatio and the longest overlap (rounding is monotone), so an
     // alignment that shows more than cap_max mismatches on its first bases fails every badlimit of this loop
     const int cap_max = cap_of(fadd(fmul(bestRatio, (float)imin(alen, blen)), (float)EXTRA_BADLIMIT), T, n_T);
-    build_cands<GENERAL, S>(c, alen, blen, alen + blen - minOverlap, minInsert, cap_max, q);
+    build_cands<GENERAL, S>(c, alen, blen, alen + blen - minOverlap, minInsert, cap_max, cap_line(bestRatio, (float)EXTRA_BADLIMIT), q);
     int side, s;
     while (next_cand<S>(q, side, s)) {  // for (insert = alen + blen - minOverlap; insert >= minInsert; insert--), candidates only
         const int insert = side == 0 ? s + blen : blen - s;
@@ -555,7 +576,8 @@ TBO_HD int mate_by_overlap_ratio(const Ctx<S> &c, Cands<S> &q, int alen, int ble
     // min(bestRatio, maxRatio) <= maxRatio and ov <= minLength: the screen's cap for this loop
     const int cap_max =
         cap_of(fadd(fadd(fmul(1.2f, fmul(fmul(maxRatio, margin), (float)minLength)), 1.0f), (float)EXTRA_BADLIMIT), T, n_T);
-    build_cands<GENERAL, S>(c, alen, blen, alen + blen - minOverlap0, p.minInsert0, cap_max, q);
+    build_cands<GENERAL, S>(c, alen, blen, alen + blen - minOverlap0, p.minInsert0, cap_max,
+                            cap_line(fmul(1.2f, fmul(maxRatio, margin)), 1.0f + (float)EXTRA_BADLIMIT), q);
     int side, s;
     while (next_cand<S>(q, side, s)) {  // for (insert = alen + blen - minOverlap0; insert >= minInsert0; insert--), candidates only
         const int insert = side == 0 ? s + blen : blen - s;

@@ -22,6 +22,26 @@ int tbo_host_pack(const uint8_t *buf, int start, int len, int reverse, int W, ui
     return (bad ? 1 : 0) | (n_any ? 2 : 0);
 }
 
+// CapLine must never undercut cap_of: returns the number of overlap lengths (0..MAX_LEN) where it does, for both limit
+// formulas (loop 1: ratio * ov + 20; loop 2: 1.2 * (ratio * margin * ov) + 1 + 20) in the reference's float evaluation order
+int tbo_host_check_cap_line(float ratio, float margin) {
+    std::vector<float> T(tbo::MAX_LEN + 2);
+    T[0] = 0.0f;
+    for (size_t c = 1; c < T.size(); c++) {
+        volatile float s = T[c - 1] + 0.95f;
+        T[c] = s;
+    }
+    int bad = 0;
+    const tbo::CapLine l1 = tbo::cap_line(ratio, 20.0f), l2 = tbo::cap_line(tbo::fmul(1.2f, tbo::fmul(ratio, margin)), 21.0f);
+    for (int ov = 0; ov <= tbo::MAX_LEN; ov++) {
+        const float lim1 = tbo::fadd(tbo::fmul(ratio, (float)ov), 20.0f);
+        const float lim2 = tbo::fadd(tbo::fadd(tbo::fmul(1.2f, tbo::fmul(tbo::fmul(ratio, margin), (float)ov)), 1.0f), 20.0f);
+        if (l1.of(ov) < tbo::cap_of(lim1, T.data(), (int)T.size())) bad++;
+        if (l2.of(ov) < tbo::cap_of(lim2, T.data(), (int)T.size())) bad++;
+    }
+    return bad;
+}
+
 // same contract as oracle/tbo_oracle.c:tbo_ora_process (quals are ignored: the expectedErrors guard is not part of the core)
 void tbo_host_process(const uint8_t *bases, const int64_t *offsets, int64_t n_reads, const int32_t *lo, int32_t *hi,
                       const uint8_t *flags, int min_overlap0, int min_overlap, int min_insert0, int min_insert, float max_ratio,

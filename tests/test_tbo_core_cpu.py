@@ -68,6 +68,15 @@ def planes_of(seq, W):
     return h, l, n
 
 
+def test_cap_line_never_undercuts_the_exact_cap(host):
+    """the inner loop's linear bound on the admissible mismatch count vs cap_of, for every overlap length"""
+    host.tbo_host_check_cap_line.argtypes = [C.c_float, C.c_float]
+    rng = np.random.default_rng(1)
+    for ratio in [0.1001, 0.0501, 0.1, 0.05, 1e-4, 0.0135] + list(rng.random(200) * 0.11):
+        for margin in (5.0, 9.0):
+            assert host.tbo_host_check_cap_line(float(ratio), margin) == 0, (ratio, margin)
+
+
 @pytest.mark.parametrize("reverse", [0, 1])
 def test_packing_matches_a_bytewise_restatement(host, reverse):
     rng = np.random.default_rng(5 + reverse)
