@@ -113,6 +113,17 @@ class BBDukQtrimCfg(C.Structure):
     ]
 
 
+class BBDukEntropyCfg(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32),
+        ("cutoff", C.c_float),
+        ("k", C.c_int32),
+        ("window", C.c_int32),
+        ("high_pass", C.c_int32),
+        ("reserved", C.c_int32 * 4),
+    ]
+
+
 class BBDukStats(C.Structure):
     _fields_ = [
         ("reads_in", C.c_int64),

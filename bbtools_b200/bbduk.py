@@ -49,7 +49,7 @@ def parse_args(args, generation=GEN_JGI):
           "tbo": False, "strictoverlap": True, "minoverlap": -1, "mininsert": -1,
           "qtrim_left": False, "qtrim_right": False, "trimq": 6.0, "mbq": 0, "maxns": -1, "maxlen": 0,
           "trimpolya": 0, "trimpolygleft": 0, "trimpolygright": 0, "filterpolyg": 0, "trimpolycleft": 0, "trimpolycright": 0,
-          "filterpolyc": 0, "maxnonpoly": 1}
+          "filterpolyc": 0, "maxnonpoly": 1, "entropy": -1.0, "entropyk": 5, "entropywindow": 50}
     for arg in args:
         sp = arg.split("=")
         a = sp[0].lower()
@@ -249,6 +249,15 @@ def parse_args(args, generation=GEN_JGI):
             io["trimpolygleft"] = io["trimpolygright"] = _parse_poly(b)
         elif a == "trimpolyc":
             io["trimpolycleft"] = io["trimpolycright"] = _parse_poly(b)
+        elif a in ("minentropy", "entropy", "entropyfilter"):  # jgi/BBDuk.java:418-419
+            io["entropy"] = float(b)
+        elif a in ("entropyk", "ek"):  # parse/Parser.java:955-960
+            io["entropyk"] = int(b)
+        elif a in ("entropywindow", "ew"):
+            io["entropywindow"] = int(b)
+        elif a in ("entropymask", "maskentropy", "entropytrim", "trimentropy", "entropymark", "markentropy"):
+            if b is None or _parse_boolean(b) or b[:1].isalpha() and b.lower() not in ("f", "false"):
+                raise NotImplementedError(f"{a} is not on the device path (only the entropy= read filter is)")
         elif a == "usequality":
             if _parse_boolean(b):
                 raise NotImplementedError("usequality=t (quality-weighted overlap) is not on the device path")
@@ -449,6 +458,34 @@ class BBDukIndexGPU:
                                                      int(bool(paired)), ptr(d_lo), ptr(d_hi), ptr(d_flags), ptr(d_stats),
                                                      ptr(stream)), "qtrim_device")
 
+    # -- low-entropy read filter (jgi/BBDuk.java:3175-3186, tracker/EntropyTracker.java) -----------------
+    def entropy_cfg(self, **kw):
+        from ._abi import BBDukEntropyCfg
+        c = BBDukEntropyCfg()
+        self.lib.bbduk_b200_entropy_cfg_default(C.byref(c))
+        for k, v in kw.items():
+            setattr(c, k, v)
+        return c
+
+    def entropy(self, bases, offsets, paired, out, cfg):
+        """HOST buffers; `out` is the Outputs of process() (after tbo / qtrim): hi / flags are updated in place.
+        -> [readsEFiltered, basesEFiltered]"""
+        bases = np.ascontiguousarray(bases, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        st = np.zeros(2, np.int64)
+        self._check(self.lib.bbduk_b200_entropy(self.h, C.byref(cfg), bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1,
+                                                int(bool(paired)), out.lo.ctypes.data, out.hi.ctypes.data, out.flags.ctypes.data,
+                                                st.ctypes.data), "entropy")
+        return st
+
+    def entropy_device(self, d_bases, d_offsets, n_reads, paired, d_lo, d_hi, d_flags, cfg, d_stats=None, stream=None):
+        def ptr(x):
+            if x is None:
+                return None
+            return x.data_ptr() if hasattr(x, "data_ptr") else int(x)
+        self._check(self.lib.bbduk_b200_entropy_device(self.h, C.byref(cfg), ptr(d_bases), ptr(d_offsets), n_reads, int(bool(paired)),
+                                                       ptr(d_lo), ptr(d_hi), ptr(d_flags), ptr(d_stats), ptr(stream)), "entropy_device")
+
     def set_max_read_len(self, n):
         self._check(self.lib.bbduk_b200_set_max_read_len(self.h, int(n)), "set_max_read_len")
 
@@ -490,6 +527,7 @@ class BBDuk:
         self.stored_kmers = self.index.finalize()
         self.stats = None
         self.tbo_stats = None  # [readsTrimmedByOverlap, basesTrimmedByOverlap]
+        self.entropy_stats = None  # [readsEFiltered, basesEFiltered]
         self.qtrim_stats = None  # [reads/bases QTrimmed, reads/bases QFiltered, reads/bases NFiltered, reads/bases PolyTrimmed]
 
     def process_arrays(self, bases, offsets, paired):
@@ -511,6 +549,8 @@ class BBDuk:
             self.tbo_stats = self._tbo(bases, quals, offsets, out)
         if self._wants_qtrim():
             self.qtrim_stats = self._qtrim(bases, quals, offsets, paired, out)
+        if io["entropy"] >= 0:
+            self.entropy_stats = self._entropy(bases, offsets, paired, out)
         for removed, p1, p2 in ((False, io["out1"], io["out2"]), (True, io["outm1"], io["outm2"])):
             if not p1:
                 continue
@@ -543,6 +583,12 @@ class BBDuk:
                                    trim_poly_c_left=io["trimpolycleft"], trim_poly_c_right=io["trimpolycright"],
                                    filter_poly_c=io["filterpolyc"], max_non_poly=io["maxnonpoly"])
         return self.index.qtrim(bases, quals, offsets, paired, out, cfg)
+
+    def _entropy(self, bases, offsets, paired, out):
+        """the low-entropy read filter (jgi/BBDuk.java:3175-3186); updates out.flags"""
+        io = self.io
+        return self.index.entropy(bases, offsets, paired, out,
+                                  self.index.entropy_cfg(cutoff=io["entropy"], k=io["entropyk"], window=io["entropywindow"]))
 
     def _write_stats(self):
         io = self.io
@@ -577,6 +623,8 @@ class BBDuk:
             self.tbo_stats = self._tbo(bases, pack(quals)[0], offsets, out)
         if self._wants_qtrim():
             self.qtrim_stats = self._qtrim(bases, pack(quals)[0], offsets, paired, out)
+        if io["entropy"] >= 0:
+            self.entropy_stats = self._entropy(bases, offsets, paired, out)
         sinks = {}
 
         def sink(path):

@@ -958,6 +958,98 @@ int bbduk_b200_qtrim(bbduk_handle *h, const bbduk_qtrim_cfg *cfg, const uint8_t 
     return rc;
 }
 
+void bbduk_b200_entropy_cfg_default(bbduk_entropy_cfg *c) {
+    if (!c) return;
+    memset(c, 0, sizeof *c);
+    c->struct_size = (int32_t)sizeof *c;
+    c->cutoff = -1.0f;  // jgi/BBDuk.java:5024
+    c->k = 5;
+    c->window = 50;
+    c->high_pass = 1;
+}
+
+int bbduk_b200_entropy_device(bbduk_handle *h, const bbduk_entropy_cfg *cfg, const uint8_t *d_bases, const uint32_t *d_offsets,
+                              int64_t n_reads, int32_t paired, const int32_t *d_lo, int32_t *d_hi, uint8_t *d_flags,
+                              int64_t *d_stats2, void *stream) {
+    if (!h) return set_err(nullptr, "handle is NULL");
+    if (!cfg || cfg->struct_size != (int32_t)sizeof *cfg) return set_err(h, "bad bbduk_entropy_cfg");
+    if (n_reads < 0 || (paired && (n_reads & 1))) return set_err(h, "bad n_reads (paired input needs an even count)");
+    if (n_reads == 0) return 0;
+    if (!d_bases || !d_offsets || !d_lo || !d_hi || !d_flags) return set_err(h, "NULL input");
+    CKH(cudaSetDevice(h->device));
+    const int rc = launch_entropy(h->sm_count, cfg, h->p, d_bases, d_offsets, n_reads, paired ? 1 : 0, d_lo, d_hi, d_flags,
+                                  reinterpret_cast<unsigned long long *>(d_stats2), (cudaStream_t)stream);
+    if (rc == 2) return set_err(h, "entropy: k > 5 or window - k + 1 > 254 has no device path (and there is no CPU fallback)");
+    if (rc) return set_err(h, std::string("entropy kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    h->launches += 1;
+    return 0;
+}
+
+int bbduk_b200_entropy(bbduk_handle *h, const bbduk_entropy_cfg *cfg, const uint8_t *bases, const int64_t *offsets, int64_t n_reads,
+                       int32_t paired, const int32_t *lo, int32_t *hi, uint8_t *flags, int64_t *stats2) {
+    if (!h) return set_err(nullptr, "handle is NULL");
+    if (!cfg || cfg->struct_size != (int32_t)sizeof *cfg) return set_err(h, "bad bbduk_entropy_cfg");
+    if (n_reads < 0 || (paired && (n_reads & 1))) return set_err(h, "bad n_reads (paired input needs an even count)");
+    if (n_reads == 0) return 0;
+    if (!bases || !offsets || !lo || !hi || !flags) return set_err(h, "NULL input");
+    CKH(cudaSetDevice(h->device));
+    std::lock_guard<std::mutex> g(h->tbo_mu);  // shares the staging of the tbo entry point
+    cudaStream_t st = nullptr;
+    int64_t *d_stats = nullptr;
+    CKH(cudaMalloc(&d_stats, 2 * sizeof(int64_t)));
+    CKH(cudaMemset(d_stats, 0, 2 * sizeof(int64_t)));
+    int rc = 0;
+    int64_t r0 = 0;
+    const int per = paired ? 2 : 1;
+    std::vector<uint32_t> off32;
+    while (r0 < n_reads && !rc) {
+        int64_t r1 = std::min(n_reads, r0 + (CHUNK_READS << 1));
+        while (r1 > r0 + per && offsets[r1] - offsets[r0] > CHUNK_BYTES) r1 = r0 + std::max<int64_t>(per, ((r1 - r0) / 2 / per) * per);
+        const int64_t nr = r1 - r0, nb = offsets[r1] - offsets[r0];
+        if (nb < 0 || nb >= (1ll << 32) - 64) {
+            rc = set_err(h, "a read (pair) exceeds 4 GiB (or offsets decrease)");
+            break;
+        }
+        off32.resize(nr + 1);
+        for (int64_t i = 0; i <= nr; i++) off32[i] = (uint32_t)(offsets[r0 + i] - offsets[r0]);
+        auto need = [&](void **p, int64_t *cap, int64_t bytes) -> int {
+            if (bytes <= *cap) return 0;
+            cudaFree(*p);
+            *p = nullptr;
+            *cap = bytes + bytes / 8 + 4096;
+            return cudaMalloc(p, (size_t)*cap) == cudaSuccess ? 0 : 1;
+        };
+        auto &tb = h->tbo;
+        if (need((void **)&tb.d_bases, &tb.cap_bases, nb + 64) || need((void **)&tb.d_off, &tb.cap_off, 4 * (nr + 1)) ||
+            need((void **)&tb.d_lo, &tb.cap_lo, 4 * nr) || need((void **)&tb.d_hi, &tb.cap_hi, 4 * nr) ||
+            need((void **)&tb.d_flags, &tb.cap_flags, nr)) {
+            rc = set_err(h, "entropy: device allocation failed");
+            break;
+        }
+#define CKE(call)                                                                       \
+    if (!rc && (call) != cudaSuccess) rc = set_err(h, std::string(#call " failed: ") + cudaGetErrorString(cudaGetLastError()))
+        CKE(cudaMemcpyAsync(tb.d_bases, bases + offsets[r0], (size_t)nb, cudaMemcpyHostToDevice, st));
+        CKE(cudaMemcpyAsync(tb.d_off, off32.data(), 4 * (size_t)(nr + 1), cudaMemcpyHostToDevice, st));
+        CKE(cudaMemcpyAsync(tb.d_lo, lo + r0, 4 * (size_t)nr, cudaMemcpyHostToDevice, st));
+        CKE(cudaMemcpyAsync(tb.d_hi, hi + r0, 4 * (size_t)nr, cudaMemcpyHostToDevice, st));
+        CKE(cudaMemcpyAsync(tb.d_flags, flags + r0, (size_t)nr, cudaMemcpyHostToDevice, st));
+        if (!rc) rc = bbduk_b200_entropy_device(h, cfg, tb.d_bases, tb.d_off, nr, paired, tb.d_lo, tb.d_hi, tb.d_flags, d_stats, st);
+        CKE(cudaMemcpyAsync(hi + r0, tb.d_hi, 4 * (size_t)nr, cudaMemcpyDeviceToHost, st));
+        CKE(cudaMemcpyAsync(flags + r0, tb.d_flags, (size_t)nr, cudaMemcpyDeviceToHost, st));
+        CKE(cudaStreamSynchronize(st));
+#undef CKE
+        r0 = r1;
+    }
+    if (!rc && stats2) {
+        int64_t v[2] = {0, 0};
+        if (cudaMemcpy(v, d_stats, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) rc = set_err(h, "entropy: stats copy failed");
+        stats2[0] += v[0];
+        stats2[1] += v[1];
+    }
+    cudaFree(d_stats);
+    return rc;
+}
+
 int bbduk_b200_pack_bases(const uint8_t *bases, int64_t n, uint32_t *F, uint16_t *D) {
     if (n < 0 || (n > 0 && (!bases || !F || !D))) return set_err(nullptr, "bad pack_bases arguments");
     pack_bases(bases, n, F, D);

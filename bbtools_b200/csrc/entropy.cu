@@ -1,0 +1,173 @@
+// entropy.cu -- BBDuk's low-entropy read filter (entropy=<cutoff>) on the device: bbduk_b200_entropy / _entropy_device
+// (SURVEY.md 8f row 4).
+//
+// Replaces the "Test entropy" block of the per-pair loop (jgi/BBDuk.java:3175-3186: passes(r.bases, true), setDiscarded,
+// shouldRemove, basesEFilteredT / readsEFilteredT) with tracker/EntropyTracker.java underneath: averageEntropy (:657-703)
+// over a sliding window of `window` bases, the k-mer counts of the window kept incrementally (add :815-946) and the
+// window's entropy read off a running double-precision sum of pk*log(pk) terms (calcEntropyFast :194-201).
+//
+// One lane per read, mates on neighbouring lanes. The window's k-mer counts (4^k bytes, k <= 5: 1 KB) live in shared
+// memory, one private table per lane; a read leaves its table zeroed by walking its last window backwards instead of
+// clearing 4^k entries. The table of pk*log(pk) is built on the host with the C library's log() and handed over as a
+// kernel parameter; every double and float operation keeps the reference's order.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include <cuda_runtime.h>
+
+#include "../../include/bbduk_b200.h"
+#include "probe.h"
+
+namespace {
+
+constexpr int EN_THREADS = 64;
+constexpr int EN_MAX_WK = 254;  // counts are bytes: windowKmers + 1 must fit
+
+struct EntropyDev {
+    float cutoff;
+    int k, window, mask, space, high_pass, rieb, tf1;
+    double mult;                // entropyMult = -1 / log(windowKmers)
+    double E[EN_MAX_WK + 2];    // E[c] = (c / windowKmers) * log(c / windowKmers)
+};
+
+__device__ __forceinline__ uint32_t sym0(uint8_t b) {  // dna/AminoAcid.java symbolToNumber0: A0 C1 G2 T/U3, anything else 0
+    const uint8_t y = b | 0x20;
+    if (b >= 128) return 0;
+    return y == 'c' ? 1u : y == 'g' ? 2u : (y == 't' || y == 'u') ? 3u : 0u;
+}
+
+__global__ void __launch_bounds__(EN_THREADS)
+entropy_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ offsets, int64_t n_reads, int paired,
+               const int32_t *__restrict__ lo_in, int32_t *hi_io, uint8_t *flags_io, const EntropyDev p, unsigned long long *stats) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    double *E = reinterpret_cast<double *>(smem);
+    uint8_t *C = smem + sizeof(double) * (EN_MAX_WK + 2) + (size_t)threadIdx.x * p.space;  // this lane's counts, all zero between reads
+    for (int i = threadIdx.x; i < EN_MAX_WK + 2; i += EN_THREADS) E[i] = p.E[i];
+    {
+        uint32_t *z = reinterpret_cast<uint32_t *>(smem + sizeof(double) * (EN_MAX_WK + 2));
+        for (int i = threadIdx.x; i < EN_THREADS * p.space / 4; i += EN_THREADS) z[i] = 0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = (int64_t)gridDim.x * (EN_THREADS / 32);
+    const int64_t n_tiles = (n_reads + 31) >> 5;
+    const int k = p.k, W = p.window;
+    unsigned int s_r = 0, s_b = 0;
+    for (int64_t tile = (int64_t)blockIdx.x * (EN_THREADS / 32) + (threadIdx.x >> 5); tile < n_tiles; tile += warps_total) {
+        const int64_t r = tile * 32 + lane;
+        const bool live = r < n_reads;
+        const uint32_t o0 = live ? offsets[r] : 0u;
+        const int l = live ? lo_in[r] : 0;
+        int h = live ? hi_io[r] : 0;
+        const int f = live ? (int)flags_io[r] : BBDUK_F_REMOVED;
+        const int f_first = paired ? __shfl_sync(0xFFFFFFFFu, f, lane & ~1) : f;
+        const bool removed = !live || (f_first & BBDUK_F_REMOVED) != 0;
+        bool discarded = (f & BBDUK_F_DISCARDED) != 0;
+        const bool was_disc = discarded || (p.tf1 && h - l == 1);
+        if (!removed && !was_disc) {  // isNotDiscarded(r) && !passes(r.bases, true)
+            const int n = h - l;
+            const uint8_t *b = bases + o0 + l;
+            double esum = 0.0, sum = 0.0;
+            int div = 0;
+            uint32_t kmer = 0, kmer2 = 0;
+            const int lim = min(n, W);
+            if (n == 0) div = 1;  // one measurement of the empty tracker: 0
+            for (int i = 0; i < n; i++) {
+                kmer = ((kmer << 2) | sym0(b[i])) & (uint32_t)p.mask;
+                if (i >= k - 1) {  // the k-mer that enters on the right
+                    const uint32_t oc = C[kmer];
+                    C[kmer] = (uint8_t)(oc + 1);
+                    esum = __dsub_rn(__dadd_rn(esum, E[oc + 1]), E[oc]);
+                }
+                const int j = i - W + k - 1;
+                if (j >= 0) {
+                    kmer2 = ((kmer2 << 2) | sym0(b[j])) & (uint32_t)p.mask;
+                    if (i >= W) {  // the k-mer that leaves on the left
+                        const uint32_t oc = C[kmer2];
+                        C[kmer2] = (uint8_t)(oc - 1);
+                        esum = __dsub_rn(__dadd_rn(esum, E[oc - 1]), E[oc]);
+                    }
+                }
+                if (i >= lim - 1) {  // calcEntropyFast after the prefill and after every later base
+                    const float e1 = (float)__dmul_rn(esum, p.mult);
+                    sum = __dadd_rn(sum, (double)(e1 > 0.0f ? e1 : 0.0f));
+                    div++;
+                }
+            }
+            // leave the table zeroed: the k-mers still inside the last window
+            {
+                const int start = max(0, n - W);
+                uint32_t km = 0;
+                for (int i = start; i < n; i++) {
+                    km = ((km << 2) | sym0(b[i])) & (uint32_t)p.mask;
+                    if (i >= start + k - 1) C[km] = (uint8_t)(C[km] - 1);
+                }
+            }
+            const float e = (float)__ddiv_rn(sum, (double)max(1, div));
+            const bool passes = (p.high_pass != 0) != (e < p.cutoff);
+            if (!passes) {  // setDiscarded (jgi/BBDuk.java:3260-3266)
+                if (p.tf1) {
+                    if (h - l > 1) h = l + 1;
+                } else {
+                    discarded = true;
+                }
+            }
+        }
+        const bool d = discarded || (p.tf1 && h - l == 1);
+        const bool dm = __shfl_xor_sync(0xFFFFFFFFu, (int)d, 1) != 0;
+        const bool rem = !removed && (paired ? (p.rieb ? (d || dm) : (d && dm)) : d);
+        const int len = h - l;
+        const int lenm = __shfl_xor_sync(0xFFFFFFFFu, len, 1);
+        if (rem && (!paired || !(lane & 1))) {
+            s_b += (unsigned int)(len + (paired ? lenm : 0));
+            s_r += paired ? 2 : 1;
+        }
+        if (live && !removed) {
+            hi_io[r] = h;
+            flags_io[r] = (uint8_t)((f & ~(BBDUK_F_DISCARDED | BBDUK_F_REMOVED)) | (discarded ? BBDUK_F_DISCARDED : 0) |
+                                    (rem ? BBDUK_F_REMOVED : 0));
+        }
+    }
+    if (stats) {
+        const unsigned int tr = __reduce_add_sync(0xFFFFFFFFu, s_r), tb = __reduce_add_sync(0xFFFFFFFFu, s_b);
+        if (lane == 0 && tr) {
+            atomicAdd(stats, (unsigned long long)tr);
+            atomicAdd(stats + 1, (unsigned long long)tb);
+        }
+    }
+}
+
+}  // namespace
+
+// launcher used by abi.cu; 0 ok, 1 CUDA failure, 2 unsupported k / window
+int launch_entropy(int sm_count, const bbduk_entropy_cfg *cfg, const BBParams &bp, const uint8_t *d_bases, const uint32_t *d_offsets,
+                   int64_t n_reads, int paired, const int32_t *d_lo, int32_t *d_hi, uint8_t *d_flags, unsigned long long *d_stats,
+                   cudaStream_t st) {
+    if (n_reads < 1) return 0;
+    const int k = cfg->k > 0 ? cfg->k : 5, W = cfg->window > 0 ? cfg->window : 50;  // tracker/EntropyTracker.java:1206-1209
+    const int wk = W - k + 1;
+    if (k < 1 || k > 5 || wk < 1 || wk > EN_MAX_WK) return 2;
+    EntropyDev p;
+    memset(&p, 0, sizeof p);
+    p.cutoff = std::max(0.0f, cfg->cutoff);  // jgi/BBDuk.java:2518
+    p.k = k;
+    p.window = W;
+    p.mask = (int)~(~0u << (2 * k));
+    p.space = 1 << (2 * k);
+    p.high_pass = cfg->high_pass != 0;
+    p.rieb = bp.removePairsIfEitherBad;
+    p.tf1 = bp.trimFailuresTo1bp;
+    const double mult = 1.0 / wk;  // tracker/EntropyTracker.java:106-118
+    for (int i = 1; i < wk + 2; i++) {
+        const double pk = i * mult;
+        p.E[i] = pk * std::log(pk);
+    }
+    p.mult = -1 / std::log((double)wk);
+    const size_t smem = sizeof(double) * (EN_MAX_WK + 2) + (size_t)EN_THREADS * p.space;
+    if (cudaFuncSetAttribute(entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
+    const int64_t n_tiles = (n_reads + 31) / 32;
+    const int blocks = (int)std::min<int64_t>((n_tiles + EN_THREADS / 32 - 1) / (EN_THREADS / 32), (int64_t)sm_count * 3);
+    entropy_kernel<<<blocks, EN_THREADS, smem, st>>>(d_bases, d_offsets, n_reads, paired, d_lo, d_hi, d_flags, p, d_stats);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}

@@ -52,3 +52,8 @@ int launch_tbo(int device, int sm_count, const bbduk_tbo_cfg *cfg, const uint8_t
 int launch_qtrim(int sm_count, const bbduk_qtrim_cfg *cfg, const BBParams &bp, const uint8_t *d_bases, const uint8_t *d_quals,
                  const uint32_t *d_offsets, int64_t n_reads, int paired, int32_t *d_lo, int32_t *d_hi, uint8_t *d_flags,
                  unsigned long long *d_stats, cudaStream_t st);
+
+// low-entropy read filter (entropy.cu); 0 ok, 1 CUDA failure, 2 k / window outside the device path
+int launch_entropy(int sm_count, const bbduk_entropy_cfg *cfg, const BBParams &bp, const uint8_t *d_bases, const uint32_t *d_offsets,
+                   int64_t n_reads, int paired, const int32_t *d_lo, int32_t *d_hi, uint8_t *d_flags, unsigned long long *d_stats,
+                   cudaStream_t st);

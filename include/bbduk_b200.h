@@ -306,6 +306,34 @@ BBDUK_API int bbduk_b200_qtrim_device(bbduk_handle *h, const bbduk_qtrim_cfg *cf
                                       const uint32_t *d_offsets, int64_t n_reads, int32_t paired, int32_t *d_lo, int32_t *d_hi,
                                       uint8_t *d_flags, int64_t *d_stats8, void *stream);
 
+/*
+ * Low-entropy read filter (entropy=<cutoff>), the "Test entropy" block that follows the quality filters in the per-pair
+ * loop (jgi/BBDuk.java:3175-3186) with tracker/EntropyTracker.java underneath (average over all windows of `window`
+ * bases of the Shannon entropy of the window's k-mers, scaled to 0..1; a read passes iff highpass XOR (entropy < cutoff)).
+ * rieb and trimfailuresto1bp come from the handle's bbduk_cfg. entropymask / entropytrim / entropymark are not covered.
+ */
+typedef struct bbduk_entropy_cfg {
+    int32_t struct_size;  /* = sizeof(bbduk_entropy_cfg) */
+    float   cutoff;       /* entropy= / minentropy= ; the tracker uses max(0, cutoff) (jgi/BBDuk.java:2518) */
+    int32_t k;            /* entropyk= ; 0 -> 5 (tracker/EntropyTracker.java:1206); device path: k <= 5 */
+    int32_t window;       /* entropywindow= ; 0 -> 50; device path: window - k + 1 <= 254 */
+    int32_t high_pass;    /* entropyHighpass, default 1 */
+    int32_t reserved[4];
+} bbduk_entropy_cfg;
+BBDUK_API void bbduk_b200_entropy_cfg_default(bbduk_entropy_cfg *cfg);
+
+/* For one batch that has been through bbduk_b200_process (and tbo / qtrim): units (reads, or pairs 2i / 2i+1 if paired)
+ * whose flags carry BBDUK_F_REMOVED are skipped; reads that are not discarded are measured on their kept interval [lo,hi).
+ * flags[] (BBDUK_F_DISCARDED, BBDUK_F_REMOVED) and, with trimfailuresto1bp, hi[] are updated in place;
+ * stats2 += {readsEFiltered, basesEFiltered}. HOST buffers. */
+BBDUK_API int bbduk_b200_entropy(bbduk_handle *h, const bbduk_entropy_cfg *cfg, const uint8_t *bases, const int64_t *offsets,
+                                 int64_t n_reads, int32_t paired, const int32_t *lo, int32_t *hi, uint8_t *flags, int64_t *stats2);
+
+/* Same on DEVICE buffers (32-bit offsets), asynchronous on `stream`; d_stats2 = device int64[2], may be NULL. */
+BBDUK_API int bbduk_b200_entropy_device(bbduk_handle *h, const bbduk_entropy_cfg *cfg, const uint8_t *d_bases,
+                                        const uint32_t *d_offsets, int64_t n_reads, int32_t paired, const int32_t *d_lo,
+                                        int32_t *d_hi, uint8_t *d_flags, int64_t *d_stats2, void *stream);
+
 /* Host helper (no GPU needed): the 2-bit packing bbduk_b200_process applies to a chunk before it crosses PCIe when
  * the tuned kernel takes the whole chunk (set BBDUK_B200_PACK_HOST=0 to ship ASCII instead). F[i] = big-endian
  * 2-bit codes of bases 16i..16i+15 (A0 C1 G2 T/U3, anything else 0), D[i] = "defined" bits (bit 15-b = base 16i+b);

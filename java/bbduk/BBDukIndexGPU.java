@@ -81,6 +81,14 @@ public final class BBDukIndexGPU extends BBDukIndex {
 		return qtrimNative(handle, cfg, trimq, bases, quals, offsets, nReads, paired, lo, hi, flags, stats8)==0;
 	}
 
+	/** Low-entropy read filter for the batch the earlier calls answered (replaces jgi/BBDuk.java:3175-3186): flags[] are
+	 * updated in place; stats2 += {readsEFiltered, basesEFiltered}. */
+	public boolean entropyBatch(float cutoff, int entropyK, int entropyWindow, boolean highPass, byte[] bases, long[] offsets,
+			long nReads, boolean paired, int[] lo, int[] hi, byte[] flags, long[] stats2){
+		final int[] cfg={entropyK, entropyWindow, highPass ? 1 : 0};
+		return entropyNative(handle, cfg, cutoff, bases, offsets, nReads, paired, lo, hi, flags, stats2)==0;
+	}
+
 	@Override public int getValue(long kmer, long rkmer, long lengthMask, int qPos, int len, int qHDist){
 		throw new UnsupportedOperationException("per-k-mer queries are served in batches by processBatch()");
 	}
@@ -96,6 +104,8 @@ public final class BBDukIndexGPU extends BBDukIndex {
 			int[] lo, int[] hi, byte[] flags, int[] insert, long[] stats2);
 	private static native int qtrimNative(long h, int[] cfg, float trimq, byte[] bases, byte[] quals, long[] offsets, long nReads,
 			boolean paired, int[] lo, int[] hi, byte[] flags, long[] stats8);
+	private static native int entropyNative(long h, int[] cfg, float cutoff, byte[] bases, long[] offsets, long nReads, boolean paired,
+			int[] lo, int[] hi, byte[] flags, long[] stats2);
 	private static native int scaffoldCountsNative(long h, long[] reads, long[] bases);
 	private static native String lastErrorNative(long h);
 	private static native void destroyNative(long h);

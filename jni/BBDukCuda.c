@@ -178,6 +178,43 @@ JNIEXPORT jint JNICALL Java_bbduk_BBDukIndexGPU_qtrimNative(JNIEnv *env, jclass 
     return rc;
 }
 
+/* Replaces the "Test entropy" block of the per-pair loop (jgi/BBDuk.java:3175-3186; eTrackerT.passes(r.bases, true)) for the
+ * batch that processNative / tboNative / qtrimNative answered: flags[] (and hi[] with trimfailuresto1bp) are updated in
+ * place, stats2 += {readsEFiltered, basesEFiltered}. eCfg = {k, window, highPass}. */
+JNIEXPORT jint JNICALL Java_bbduk_BBDukIndexGPU_entropyNative(JNIEnv *env, jclass cls, jlong handle, jintArray jcfg, jfloat cutoff,
+                                                              jbyteArray jbases, jlongArray joffsets, jlong nReads, jboolean paired,
+                                                              jintArray jlo, jintArray jhi, jbyteArray jflags, jlongArray jstats2) {
+    bbduk_entropy_cfg cfg;
+    jint c[3];
+    int64_t st[2] = {0, 0};
+    bbduk_b200_entropy_cfg_default(&cfg);
+    (*env)->GetIntArrayRegion(env, jcfg, 0, 3, c);
+    cfg.k = c[0];
+    cfg.window = c[1];
+    cfg.high_pass = c[2];
+    cfg.cutoff = cutoff;
+    jbyte *b = (jbyte *)(*env)->GetPrimitiveArrayCritical(env, jbases, NULL);
+    jlong *o = (jlong *)(*env)->GetPrimitiveArrayCritical(env, joffsets, NULL);
+    jint *lo = (jint *)(*env)->GetPrimitiveArrayCritical(env, jlo, NULL);
+    jint *hi = (jint *)(*env)->GetPrimitiveArrayCritical(env, jhi, NULL);
+    jbyte *fl = (jbyte *)(*env)->GetPrimitiveArrayCritical(env, jflags, NULL);
+    const jint rc = bbduk_b200_entropy((bbduk_handle *)(intptr_t)handle, &cfg, (const uint8_t *)b, (const int64_t *)o, (int64_t)nReads,
+                                       paired ? 1 : 0, (const int32_t *)lo, (int32_t *)hi, (uint8_t *)fl, st);
+    (*env)->ReleasePrimitiveArrayCritical(env, jflags, fl, 0);
+    (*env)->ReleasePrimitiveArrayCritical(env, jhi, hi, 0);
+    (*env)->ReleasePrimitiveArrayCritical(env, jlo, lo, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, joffsets, o, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, jbases, b, JNI_ABORT);
+    if (jstats2 && !rc) {
+        jlong v[2];
+        (*env)->GetLongArrayRegion(env, jstats2, 0, 2, v);
+        v[0] += st[0];
+        v[1] += st[1];
+        (*env)->SetLongArrayRegion(env, jstats2, 0, 2, v);
+    }
+    return rc;
+}
+
 JNIEXPORT jint JNICALL Java_bbduk_BBDukIndexGPU_scaffoldCountsNative(JNIEnv *env, jclass cls, jlong handle,
                                                                      jlongArray jreads, jlongArray jbases) {
     const jint n = (*env)->GetArrayLength(env, jreads);
