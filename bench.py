@@ -489,6 +489,35 @@ def run_ours(args):
                       "reads_qtrimmed_per_launch": int(d_qst[0].item()) // (q_steps + 1)}
         del d_quals
 
+    # ---- the low-entropy read filter (entropy=0.5) on the same batch, timed alone ----
+    entropy_info = None
+    if args.workload == "cfg2":
+        ecfg = eng.entropy_cfg(cutoff=0.5)
+        d_est = torch.zeros(2, dtype=torch.int64, device=dev)
+        e_lo = torch.zeros(n_reads, dtype=torch.int32, device=dev)
+        e_hi = torch.full((n_reads,), L, dtype=torch.int32, device=dev)
+        e_fl = torch.zeros(n_reads, dtype=torch.uint8, device=dev)
+        e_steps = 3
+        with torch.cuda.stream(stream):
+            eng.entropy_device(bufs[0][0], bufs[0][1], n_reads, True, e_lo, e_hi, e_fl, ecfg, d_est, stream=stream.cuda_stream)
+        barrier()
+        ee = [torch.cuda.Event(enable_timing=True) for _ in range(2 * e_steps)]
+        with torch.cuda.stream(stream):
+            for i in range(e_steps):
+                d_bases, d_off = bufs[(i + 1) % nbuf]
+                e_fl.zero_()
+                ee[2 * i].record(stream)
+                eng.entropy_device(d_bases, d_off, n_reads, True, e_lo, e_hi, e_fl, ecfg, d_est, stream=stream.cuda_stream)
+                ee[2 * i + 1].record(stream)
+        barrier()
+        e_ms = statistics.mean(ee[2 * i].elapsed_time(ee[2 * i + 1]) for i in range(e_steps))
+        te2 = torch.tensor([e_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te2, op=dist.ReduceOp.MAX)
+        e_ms = float(te2.item())
+        entropy_info = {"reads_per_s": world * n_reads / (e_ms * 1e-3), "ms_per_launch": e_ms,
+                        "reads_filtered_per_launch": int(d_est[0].item()) // (e_steps + 1)}
+
     # ---- end to end through the C ABI with pinned host buffers ------------------------------------
     e_pairs = args.e2e_pairs
     e_reads = 2 * e_pairs
@@ -572,7 +601,7 @@ def run_ours(args):
                        "stored_kmers": stored, "l2": f"inputs {n_reads * L / 2**20:.0f} MiB per step > 126 MB L2, "
                        f"{nbuf} alternating buffers, no flush", "table_build_s": round(t_build, 3),
                        "parity_vs_oracle_on_timed_batch": parity, "kmer_block_plus_tbo": tbo_info,
-                       "qtrim_block": qtrim_info},
+                       "qtrim_block": qtrim_info, "entropy_block": entropy_info},
             "e2e": {"value": e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "pairs_per_step_per_gpu": e_pairs, "steps": e_steps},
             "gpu_launches": int(launches),
