@@ -23,10 +23,11 @@ namespace {
 
 constexpr int EN_THREADS = 64;
 constexpr int EN_MAX_WK = 254;  // counts are bytes: windowKmers + 1 must fit
+constexpr int ES_BYTES = 32 * 150 + 32;  // staged base codes per warp (with k = 5 three blocks of 64 lanes just fit one SM)
 
 struct EntropyDev {
     float cutoff;
-    int k, window, mask, space, high_pass, rieb, tf1;
+    int k, window, mask, space, high_pass, rieb, tf1, n_e;  // n_e = entries of E staged in shared memory (even)
     double mult;                // entropyMult = -1 / log(windowKmers)
     double E[EN_MAX_WK + 2];    // E[c] = (c / windowKmers) * log(c / windowKmers)
 };
@@ -37,15 +38,28 @@ __device__ __forceinline__ uint32_t sym0(uint8_t b) {  // dna/AminoAcid.java sym
     return y == 'c' ? 1u : y == 'g' ? 2u : (y == 't' || y == 'u') ? 3u : 0u;
 }
 
+// 4 ASCII bases -> their codes (A0 C1 G2 T/U3, either case) in the byte lanes, 0 for anything else.
+// With d = (c|0x20)^0x61 a base is valid iff bits 7,6,5,3 of d are 0, bit 4 equals q, and (q or bit 0 is 0), where
+// q = "bits (2,1) are 10" marks the t/u class (the same classification as probe_fast.cu's stage A).
+__device__ __forceinline__ uint32_t codes4(uint32_t w) {
+    const uint32_t codes = ((w >> 1) ^ (w >> 2)) & 0x03030303u;
+    const uint32_t d = (w | 0x20202020u) ^ 0x61616161u;
+    const uint32_t q = (d >> 2) & ~(d >> 1) & 0x01010101u;
+    const uint32_t bad = (d & 0xE8E8E8E8u) | (((d >> 4) ^ q) & 0x01010101u) | (d & ~q & 0x01010101u);
+    const uint32_t nz = (((bad & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | bad) & 0x80808080u;  // bit 7 of a lane <=> byte of bad != 0
+    return codes & ~((nz >> 7) * 0xFFu);
+}
+
 __global__ void __launch_bounds__(EN_THREADS)
 entropy_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ offsets, int64_t n_reads, int paired,
                const int32_t *__restrict__ lo_in, int32_t *hi_io, uint8_t *flags_io, const EntropyDev p, unsigned long long *stats) {
     extern __shared__ __align__(16) uint8_t smem[];
     double *E = reinterpret_cast<double *>(smem);
-    uint8_t *C = smem + sizeof(double) * (EN_MAX_WK + 2) + (size_t)threadIdx.x * p.space;  // this lane's counts, all zero between reads
-    for (int i = threadIdx.x; i < EN_MAX_WK + 2; i += EN_THREADS) E[i] = p.E[i];
+    uint8_t *C = smem + sizeof(double) * p.n_e + (size_t)threadIdx.x * p.space;  // this lane's counts, all zero between reads
+    uint8_t *Bs = smem + sizeof(double) * p.n_e + (size_t)EN_THREADS * p.space + (size_t)(threadIdx.x >> 5) * ES_BYTES;
+    for (int i = threadIdx.x; i < p.n_e; i += EN_THREADS) E[i] = p.E[i];
     {
-        uint32_t *z = reinterpret_cast<uint32_t *>(smem + sizeof(double) * (EN_MAX_WK + 2));
+        uint32_t *z = reinterpret_cast<uint32_t *>(smem + sizeof(double) * p.n_e);
         for (int i = threadIdx.x; i < EN_THREADS * p.space / 4; i += EN_THREADS) z[i] = 0;
     }
     __syncthreads();
@@ -65,16 +79,36 @@ entropy_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ o
         const bool removed = !live || (f_first & BBDUK_F_REMOVED) != 0;
         bool discarded = (f & BBDUK_F_DISCARDED) != 0;
         const bool was_disc = discarded || (p.tf1 && h - l == 1);
+        // Stage the tile's base CODES in shared memory: the 32 reads of a warp are contiguous in the batch, so the warp reads
+        // them once with coalesced 16-byte loads (per-lane byte loads thrash the few KB of L1 this kernel leaves and pull
+        // every sector through L2 many times). Tiles too long for the buffer read global memory directly.
+        const int L = live ? (int)(offsets[r + 1] - o0) : 0;
+        const int last_lane = (int)min((long long)31, (long long)(n_reads - 1 - tile * 32));
+        const uint32_t t_lo = __shfl_sync(0xFFFFFFFFu, o0, 0);
+        const uint32_t t_hi = __shfl_sync(0xFFFFFFFFu, o0 + (uint32_t)L, last_lane);
+        const uint32_t a0t = t_lo & ~15u;
+        const uint32_t nchunks = (t_hi - a0t + 15u) >> 4;
+        const bool staged = nchunks * 16u <= (uint32_t)ES_BYTES && (reinterpret_cast<uintptr_t>(bases) & 15) == 0;
+        if (staged) {
+            uint4 *dst = reinterpret_cast<uint4 *>(Bs);
+            for (uint32_t c = lane; c < nchunks; c += 32) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(bases + a0t) + c);
+                dst[c] = make_uint4(codes4(v.x), codes4(v.y), codes4(v.z), codes4(v.w));
+            }
+        }
+        __syncwarp();
         if (!removed && !was_disc) {  // isNotDiscarded(r) && !passes(r.bases, true)
             const int n = h - l;
             const uint8_t *b = bases + o0 + l;
+            const uint8_t *bs = Bs + (o0 + (uint32_t)l - a0t);
+            auto code = [&](int i) -> uint32_t { return staged ? (uint32_t)bs[i] : sym0(b[i]); };
             double esum = 0.0, sum = 0.0;
             int div = 0;
             uint32_t kmer = 0, kmer2 = 0;
             const int lim = min(n, W);
             if (n == 0) div = 1;  // one measurement of the empty tracker: 0
             for (int i = 0; i < n; i++) {
-                kmer = ((kmer << 2) | sym0(b[i])) & (uint32_t)p.mask;
+                kmer = ((kmer << 2) | code(i)) & (uint32_t)p.mask;
                 if (i >= k - 1) {  // the k-mer that enters on the right
                     const uint32_t oc = C[kmer];
                     C[kmer] = (uint8_t)(oc + 1);
@@ -82,7 +116,7 @@ entropy_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ o
                 }
                 const int j = i - W + k - 1;
                 if (j >= 0) {
-                    kmer2 = ((kmer2 << 2) | sym0(b[j])) & (uint32_t)p.mask;
+                    kmer2 = ((kmer2 << 2) | code(j)) & (uint32_t)p.mask;
                     if (i >= W) {  // the k-mer that leaves on the left
                         const uint32_t oc = C[kmer2];
                         C[kmer2] = (uint8_t)(oc - 1);
@@ -100,7 +134,7 @@ entropy_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ o
                 const int start = max(0, n - W);
                 uint32_t km = 0;
                 for (int i = start; i < n; i++) {
-                    km = ((km << 2) | sym0(b[i])) & (uint32_t)p.mask;
+                    km = ((km << 2) | code(i)) & (uint32_t)p.mask;
                     if (i >= start + k - 1) C[km] = (uint8_t)(C[km] - 1);
                 }
             }
@@ -164,7 +198,8 @@ int launch_entropy(int sm_count, const bbduk_entropy_cfg *cfg, const BBParams &b
         p.E[i] = pk * std::log(pk);
     }
     p.mult = -1 / std::log((double)wk);
-    const size_t smem = sizeof(double) * (EN_MAX_WK + 2) + (size_t)EN_THREADS * p.space;
+    p.n_e = (wk + 2 + 1) & ~1;
+    const size_t smem = sizeof(double) * p.n_e + (size_t)EN_THREADS * p.space + (size_t)(EN_THREADS / 32) * ES_BYTES;
     if (cudaFuncSetAttribute(entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
     const int64_t n_tiles = (n_reads + 31) / 32;
     const int blocks = (int)std::min<int64_t>((n_tiles + EN_THREADS / 32 - 1) / (EN_THREADS / 32), (int64_t)sm_count * 3);

@@ -107,6 +107,67 @@ def test_bbduk_tool_canonical_adapter_trimming_with_tbo(tmp_path, strict):
         assert np.any(whi != want.hi)
 
 
+def test_bbduk_tool_whole_chain(tmp_path):
+    """ktrim=r ... tpe tbo trimpolya=4 qtrim=rl trimq=10 maxns=1 entropy=0.6: every device step of the per-pair loop in the
+    reference's order (k-mer block, tbo, poly-X, quality trimming, quality / N filters, entropy filter)"""
+    from bbtools_b200.bbduk import BBDuk
+    from bbtools_b200.fasta import read_fasta
+    from oracle import entropy as oe
+    from oracle import qtrim as oq
+    from oracle import tbo as otbo
+    from oracle.oracle import Oracle
+    bases, offsets = synth.paired_adapter_reads(5000, seed=47)
+    bases = bases.copy()
+    rng = np.random.default_rng(6)
+    n = len(offsets) - 1
+    for i in np.nonzero(rng.random(n) < 0.15)[0]:  # low-complexity reads, poly-A tails
+        if rng.random() < 0.5:
+            unit = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, int(rng.integers(1, 4)))]
+            bases[offsets[i]:offsets[i + 1]] = np.tile(unit, 150)[:150]
+        else:
+            bases[offsets[i + 1] - int(rng.integers(4, 30)):offsets[i + 1]] = ord("A")
+    pos = np.arange(len(bases)) % 150
+    quals = (np.clip(40 - (pos * rng.integers(0, 45, len(bases))) // 150 + rng.integers(-3, 4, len(bases)), 2, 41) + 33).astype(np.uint8)
+    paths = []
+    for first, tag in ((0, b"1:N:0"), (1, b"2:N:0")):
+        path = tmp_path / f"r{first + 1}.fq"
+        with open(path, "wb") as f:
+            for i in range(first, n, 2):
+                f.write(b"@pair%d %s\n" % (i // 2, tag) + bytes(bases[offsets[i]:offsets[i + 1]]) + b"\n+\n" +
+                        bytes(quals[offsets[i]:offsets[i + 1]]) + b"\n")
+        paths.append(path)
+    common = [f"in={paths[0]}", f"in2={paths[1]}", f"ref={GOLDEN}/adapters.fa", "ktrim=r", "k=23", "mink=11", "hdist=1", "tpe", "tbo",
+              "trimpolya=4", "qtrim=rl", "trimq=10", "maxns=1", "entropy=0.6", "minlen=25"]
+    outs = {}
+    for mode in ("native", "python"):
+        o1, o2, m1 = (tmp_path / f"{mode}_{x}.fq" for x in ("o1", "o2", "m1"))
+        tool = BBDuk(common + [f"out={o1}", f"out2={o2}", f"outm={m1}"])
+        tool.process(native=(mode == "native"))
+        outs[mode] = tuple(open(p, "rb").read() for p in (o1, o2, m1)) + (list(tool.tbo_stats), list(tool.qtrim_stats),
+                                                                             list(tool.entropy_stats))
+        cfg = tool.cfg
+    assert outs["native"] == outs["python"]
+    _, rb, roff = read_fasta(os.path.join(GOLDEN, "adapters.fa"))
+    ora = Oracle(cfg)
+    ora.add_ref(rb, roff)
+    ora.finalize()
+    want, _ = ora.process(bases, offsets, True)
+    hi1, _, _, tst = otbo.process(bases, quals, offsets, want.lo, want.hi, want.flags)
+    fl1 = want.flags | np.where(hi1 != want.hi, np.uint8(0x20), np.uint8(0))
+    lo2, hi2, fl2, qst = oq.process(bases, quals, offsets, True, want.lo, hi1, fl1, oq.params(qtrim="rl", trimq=10.0, maxns=1, polya=4, minlen=25))
+    hi3, fl3, est = oe.process(bases, offsets, True, lo2, hi2, fl2, oe.params(cutoff=0.6))
+    assert outs["native"][3:] == (list(tst), list(qst), list(est))
+    assert tst[0] > 50 and qst[0] > 1000 and qst[6] > 100 and est[0] > 100
+    exp = [[], []]
+    for i in range(n):
+        if fl3[i & ~1] & F_REMOVED:
+            continue
+        a, b = int(lo2[i]), int(hi3[i])
+        exp[i & 1].append(b"@pair%d %s\n" % (i // 2, b"1:N:0" if i % 2 == 0 else b"2:N:0") +
+                          bytes(bases[offsets[i] + a:offsets[i] + b]) + b"\n+\n" + bytes(quals[offsets[i] + a:offsets[i] + b]) + b"\n")
+    assert outs["native"][0] == b"".join(exp[0]) and outs["native"][1] == b"".join(exp[1])
+
+
 def test_bbduk_tool_single_kfilter(tmp_path):
     from bbtools_b200.bbduk import BBDuk
     ref = synth.random_reference(2, 50_000, seed=7)
