@@ -50,12 +50,93 @@ __device__ __forceinline__ uint32_t codes4(uint32_t w) {
     return codes & ~((nz >> 7) * 0xFFu);
 }
 
+// EntropyTracker.averageEntropy(bases, allowNs = true) (tracker/EntropyTracker.java:657-703) of one read. src = the read's
+// staged codes (STAGED) or its ASCII bases. Cl = this lane's slice of the warp's count table: the count of k-mer x is the
+// byte (x & 3) of word (x >> 2) * 32 + lane, so the 32 lanes of a warp always hit 32 different banks. The window loop is
+// split where the reference's conditions change (first k-1 bases: no k-mer yet; up to `window` bases: k-mers only enter;
+// afterwards one enters and one leaves per base), so the loops carry no position tests.
+template <bool STAGED>
+__device__ __forceinline__ float average_entropy(const uint8_t *__restrict__ src, int n, uint8_t *__restrict__ Cl,
+                                                 const double *__restrict__ E, int k, int W, uint32_t mask,
+                                                 double mult) {
+    auto code = [&](int i) -> uint32_t { return STAGED ? (uint32_t)src[i] : sym0(src[i]); };
+    auto slot = [&](uint32_t x) -> uint8_t * { return Cl + (((x & ~3u) << 5) | (x & 3u)); };
+    double esum = 0.0, sum = 0.0;
+    int div = 0;
+    auto enter = [&](uint32_t x) {
+        uint8_t *c = slot(x);
+        const uint32_t oc = *c;
+        *c = (uint8_t)(oc + 1);
+        esum = __dsub_rn(__dadd_rn(esum, E[oc + 1]), E[oc]);
+    };
+    auto leave = [&](uint32_t x) {
+        uint8_t *c = slot(x);
+        const uint32_t oc = *c;
+        *c = (uint8_t)(oc - 1);
+        esum = __dsub_rn(__dadd_rn(esum, E[oc - 1]), E[oc]);
+    };
+    auto measure = [&]() {  // calcEntropyFast :194-201
+        const float e1 = (float)__dmul_rn(esum, mult);
+        sum = __dadd_rn(sum, (double)(e1 > 0.0f ? e1 : 0.0f));
+        div++;
+    };
+    uint32_t kmer = 0;
+    const int lim = min(n, W);
+    int i = 0;
+    for (; i < min(lim, k - 1); i++) kmer = ((kmer << 2) | code(i)) & mask;
+    for (; i < lim; i++) {
+        kmer = ((kmer << 2) | code(i)) & mask;
+        enter(kmer);
+    }
+    measure();  // the first window (or the whole read if it is shorter)
+    if (n > W) {
+        uint32_t kmer2 = 0;  // the reference has rolled bases 0..k-2 into kmer2 by now
+        for (int t = 0; t < k - 1; t++) kmer2 = ((kmer2 << 2) | code(t)) & mask;
+        // One k-mer enters and one leaves per base. Both count loads are issued before either store (the two slots differ
+        // unless the same k-mer enters and leaves, which is patched up in registers), the four table terms are fetched
+        // together, and the next base's codes are read ahead of the stores they could alias with; what remains serial is
+        // the reference's chain of four double-precision adds per base.
+        uint32_t c_in = i < n ? code(i) : 0u, c_out = i < n ? code(i - W + k - 1) : 0u;
+        for (; i < n; i++) {
+            kmer = ((kmer << 2) | c_in) & mask;
+            kmer2 = ((kmer2 << 2) | c_out) & mask;
+            if (i + 1 < n) {
+                c_in = code(i + 1);
+                c_out = code(i + 1 - W + k - 1);
+            }
+            uint8_t *s1 = slot(kmer), *s2 = slot(kmer2);
+            const uint32_t oc1 = *s1;
+            uint32_t oc2 = *s2;
+            if (s1 == s2) oc2 = oc1 + 1;  // it was just counted
+            const double e1a = E[oc1 + 1], e1b = E[oc1], e2a = E[oc2 - 1], e2b = E[oc2];
+            *s1 = (uint8_t)(oc1 + 1);
+            *s2 = (uint8_t)(oc2 - 1);  // same slot: ends at oc1 again
+            esum = __dsub_rn(__dadd_rn(esum, e1a), e1b);
+            esum = __dsub_rn(__dadd_rn(esum, e2a), e2b);
+            measure();
+        }
+    }
+    {  // leave the table zeroed: the k-mers still inside the last window
+        const int start = max(0, n - W);
+        uint32_t km = 0;
+        for (int t = start; t < n; t++) {
+            km = ((km << 2) | code(t)) & mask;
+            if (t >= start + k - 1) {
+                uint8_t *c = slot(km);
+                *c = (uint8_t)(*c - 1);
+            }
+        }
+    }
+    return (float)__ddiv_rn(sum, (double)max(1, div));
+}
+
 __global__ void __launch_bounds__(EN_THREADS)
 entropy_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ offsets, int64_t n_reads, int paired,
                const int32_t *__restrict__ lo_in, int32_t *hi_io, uint8_t *flags_io, const EntropyDev p, unsigned long long *stats) {
     extern __shared__ __align__(16) uint8_t smem[];
     double *E = reinterpret_cast<double *>(smem);
-    uint8_t *C = smem + sizeof(double) * p.n_e + (size_t)threadIdx.x * p.space;  // this lane's counts, all zero between reads
+    // this lane's slice of its warp's count table (all zero between reads)
+    uint8_t *Cl = smem + sizeof(double) * p.n_e + (size_t)(threadIdx.x >> 5) * 32 * p.space + (size_t)(threadIdx.x & 31) * 4;
     uint8_t *Bs = smem + sizeof(double) * p.n_e + (size_t)EN_THREADS * p.space + (size_t)(threadIdx.x >> 5) * ES_BYTES;
     for (int i = threadIdx.x; i < p.n_e; i += EN_THREADS) E[i] = p.E[i];
     {
@@ -99,46 +180,8 @@ entropy_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ o
         __syncwarp();
         if (!removed && !was_disc) {  // isNotDiscarded(r) && !passes(r.bases, true)
             const int n = h - l;
-            const uint8_t *b = bases + o0 + l;
-            const uint8_t *bs = Bs + (o0 + (uint32_t)l - a0t);
-            auto code = [&](int i) -> uint32_t { return staged ? (uint32_t)bs[i] : sym0(b[i]); };
-            double esum = 0.0, sum = 0.0;
-            int div = 0;
-            uint32_t kmer = 0, kmer2 = 0;
-            const int lim = min(n, W);
-            if (n == 0) div = 1;  // one measurement of the empty tracker: 0
-            for (int i = 0; i < n; i++) {
-                kmer = ((kmer << 2) | code(i)) & (uint32_t)p.mask;
-                if (i >= k - 1) {  // the k-mer that enters on the right
-                    const uint32_t oc = C[kmer];
-                    C[kmer] = (uint8_t)(oc + 1);
-                    esum = __dsub_rn(__dadd_rn(esum, E[oc + 1]), E[oc]);
-                }
-                const int j = i - W + k - 1;
-                if (j >= 0) {
-                    kmer2 = ((kmer2 << 2) | code(j)) & (uint32_t)p.mask;
-                    if (i >= W) {  // the k-mer that leaves on the left
-                        const uint32_t oc = C[kmer2];
-                        C[kmer2] = (uint8_t)(oc - 1);
-                        esum = __dsub_rn(__dadd_rn(esum, E[oc - 1]), E[oc]);
-                    }
-                }
-                if (i >= lim - 1) {  // calcEntropyFast after the prefill and after every later base
-                    const float e1 = (float)__dmul_rn(esum, p.mult);
-                    sum = __dadd_rn(sum, (double)(e1 > 0.0f ? e1 : 0.0f));
-                    div++;
-                }
-            }
-            // leave the table zeroed: the k-mers still inside the last window
-            {
-                const int start = max(0, n - W);
-                uint32_t km = 0;
-                for (int i = start; i < n; i++) {
-                    km = ((km << 2) | code(i)) & (uint32_t)p.mask;
-                    if (i >= start + k - 1) C[km] = (uint8_t)(C[km] - 1);
-                }
-            }
-            const float e = (float)__ddiv_rn(sum, (double)max(1, div));
+            const float e = staged ? average_entropy<true>(Bs + (o0 + (uint32_t)l - a0t), n, Cl, E, k, W, (uint32_t)p.mask, p.mult)
+                                   : average_entropy<false>(bases + o0 + l, n, Cl, E, k, W, (uint32_t)p.mask, p.mult);
             const bool passes = (p.high_pass != 0) != (e < p.cutoff);
             if (!passes) {  // setDiscarded (jgi/BBDuk.java:3260-3266)
                 if (p.tf1) {
