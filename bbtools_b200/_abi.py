@@ -109,7 +109,9 @@ class BBDukQtrimCfg(C.Structure):
         ("trim_poly_c_right", C.c_int32),
         ("filter_poly_c", C.c_int32),
         ("max_non_poly", C.c_int32),
-        ("reserved", C.c_int32 * 4),
+        ("min_avg_quality", C.c_float),
+        ("min_avg_quality_bases", C.c_int32),
+        ("reserved", C.c_int32 * 2),
     ]
 
 

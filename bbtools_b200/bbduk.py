@@ -49,7 +49,8 @@ def parse_args(args, generation=GEN_JGI):
           "tbo": False, "strictoverlap": True, "minoverlap": -1, "mininsert": -1,
           "qtrim_left": False, "qtrim_right": False, "trimq": 6.0, "mbq": 0, "maxns": -1, "maxlen": 0,
           "trimpolya": 0, "trimpolygleft": 0, "trimpolygright": 0, "filterpolyg": 0, "trimpolycleft": 0, "trimpolycright": 0,
-          "filterpolyc": 0, "maxnonpoly": 1, "entropy": -1.0, "entropyk": 5, "entropywindow": 50}
+          "filterpolyc": 0, "maxnonpoly": 1, "entropy": -1.0, "entropyk": 5, "entropywindow": 50,
+          "maq": 0.0, "maqb": 0}
     for arg in args:
         sp = arg.split("=")
         a = sp[0].lower()
@@ -236,6 +237,14 @@ def parse_args(args, generation=GEN_JGI):
             io["qtrim_left"] = _parse_boolean(b)
         elif a in ("trimq", "trimquality"):
             io["trimq"] = float(b)
+        elif a in ("minavgquality", "minaveragequality", "maq"):  # parse/Parser.java:516-526
+            if "," in b:
+                q_, n_ = b.split(",")
+                io["maq"], io["maqb"] = float(q_), int(n_)
+            else:
+                io["maq"] = float(b)
+        elif a in ("minavgqualitybases", "maqb"):
+            io["maqb"] = int(b)
         elif a in ("minbasequality", "mbq"):
             io["mbq"] = int(b)
         elif a == "maxns":
@@ -571,7 +580,8 @@ class BBDuk:
         io = self.io
         poly = any(io[k] > 0 for k in ("trimpolya", "trimpolygleft", "trimpolygright", "filterpolyg", "trimpolycleft",
                                        "trimpolycright", "filterpolyc"))
-        return bool(io["qtrim_left"] or io["qtrim_right"] or io["mbq"] > 0 or io["maxns"] >= 0 or io["maxlen"] > 0 or io["tbo"] or poly)
+        return bool(io["qtrim_left"] or io["qtrim_right"] or io["mbq"] > 0 or io["maxns"] >= 0 or io["maxlen"] > 0 or io["tbo"] or poly or
+                    io["maq"] > 0)
 
     def _qtrim(self, bases, quals, offsets, paired, out):
         """quality trimming, minlen / maxlen, mbq, maxns (jgi/BBDuk.java:3074-3170); updates out.lo / out.hi / out.flags"""
@@ -581,7 +591,8 @@ class BBDuk:
                                    trim_poly_a=io["trimpolya"], trim_poly_g_left=io["trimpolygleft"],
                                    trim_poly_g_right=io["trimpolygright"], filter_poly_g=io["filterpolyg"],
                                    trim_poly_c_left=io["trimpolycleft"], trim_poly_c_right=io["trimpolycright"],
-                                   filter_poly_c=io["filterpolyc"], max_non_poly=io["maxnonpoly"])
+                                   filter_poly_c=io["filterpolyc"], max_non_poly=io["maxnonpoly"], min_avg_quality=io["maq"],
+                                   min_avg_quality_bases=io["maqb"])
         return self.index.qtrim(bases, quals, offsets, paired, out, cfg)
 
     def _entropy(self, bases, offsets, paired, out):

@@ -865,8 +865,8 @@ void bbduk_b200_qtrim_cfg_default(bbduk_qtrim_cfg *c) {
 
 static int check_qtrim_cfg(bbduk_handle *h, const bbduk_qtrim_cfg *cfg, const void *quals) {
     if (!cfg || cfg->struct_size != (int32_t)sizeof *cfg) return set_err(h, "bad bbduk_qtrim_cfg");
-    if ((cfg->qtrim_left || cfg->qtrim_right || cfg->min_base_quality > 0) && !quals)
-        return set_err(h, "qtrim / mbq need quality bytes (reads without qualities have no device path here)");
+    if ((cfg->qtrim_left || cfg->qtrim_right || cfg->min_base_quality > 0 || cfg->min_avg_quality > 0) && !quals)
+        return set_err(h, "qtrim / mbq / maq need quality bytes (reads without qualities have no device path here)");
     if (cfg->qual_offset < 0 || cfg->qual_offset > 127) return set_err(h, "bad qual_offset");
     return 0;
 }

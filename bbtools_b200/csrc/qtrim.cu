@@ -34,7 +34,10 @@ struct QtrimDev {
     float minLenFraction;
     int rieb, tf1;
     int poly_a, poly_g_left, poly_g_right, filter_g, poly_c_left, poly_c_right, filter_c, max_non_poly;
+    int maq_on, maq_bases;
+    float maq_prob;    // discard iff expectedErrors / bases >= maq_prob  (<=> phred average < minavgquality, see launch_qtrim)
     float delta[256];  // per raw quality byte: trimE - probError (trimE - nprob for q < 1)
+    float pe[256];     // per raw quality byte: PROB_ERROR[max(q, 0)] (only staged when maq is on)
 };
 
 // shared/TrimRead.java:299-346 on a kept interval
@@ -121,6 +124,9 @@ qtrim_kernel(const uint8_t *__restrict__ bases, const uint8_t *__restrict__ qual
              int64_t n_reads, int paired, int32_t *lo_io, int32_t *hi_io, uint8_t *flags_io, const QtrimDev p,
              unsigned long long *stats) {
     __shared__ float D[256];
+    __shared__ float PEs[256];
+    if (p.maq_on)
+        for (int i = threadIdx.x; i < 256; i += QT_THREADS) PEs[i] = p.pe[i];
     __shared__ __align__(16) uint8_t Qs_all[QT ? (QT_THREADS / 32) * QS_BYTES : 16];
     uint8_t *Qs = Qs_all + (QT ? (threadIdx.x >> 5) * QS_BYTES : 0);
     for (int i = threadIdx.x; i < 256; i += QT_THREADS) D[i] = p.delta[i];
@@ -331,6 +337,18 @@ qtrim_kernel(const uint8_t *__restrict__ bases, const uint8_t *__restrict__ qual
         }
         // :3110-3148 minbasequality, maxns
         if (!gone && !rem1) {
+            if (p.maq_on && quals) {  // Read.avgQuality(false, maxBases) < minAvgQuality (stream/Read.java:2181-2226, :2985-3001)
+                const int n = h - l;
+                bool low = true;  // an empty read averages 0
+                if (n > 0) {
+                    const int limit = p.maq_bases < 1 ? n : min(p.maq_bases, n);
+                    float sum = 0.0f;
+                    for (int i = 0; i < limit; i++)
+                        if (defined_base(bases[o0 + l + i])) sum = __fadd_rn(sum, PEs[quals[o0 + l + i]]);
+                    low = __fdiv_rn(sum, (float)limit) >= p.maq_prob;
+                }
+                if (low) set_disc();
+            }
             if (p.mbq > 0 && quals) {
                 int mn = 41;
                 for (int i = l; i < h; i++) mn = min(mn, (int)(int8_t)(quals[o0 + i] - p.qual_offset));
@@ -420,6 +438,39 @@ int launch_qtrim(int sm_count, const bbduk_qtrim_cfg *cfg, const BBParams &bp, c
         }
         volatile float d = e - pe;
         p.delta[raw] = d;
+    }
+    // minavgquality: the reference tests phred(p) < maq with phred(p) = p >= 1 ? 0 : p <= 1e-6 ? 60 : -10 * log10((double)p)
+    // (align2/QualityTools.java:674-680), a predicate that only ever switches from false to true as the float p grows.
+    // maq_prob = the smallest non-negative float for which it holds, found by bisection over the float bit patterns.
+    p.maq_on = cfg->min_avg_quality > 0.0f;
+    p.maq_bases = cfg->min_avg_quality_bases;
+    p.maq_prob = 0.0f;
+    if (p.maq_on) {
+        const double maq = (double)cfg->min_avg_quality;
+        auto low = [&](uint32_t bits) {
+            float pr;
+            memcpy(&pr, &bits, 4);
+            const double prob = pr;
+            const double phred = prob >= 1 ? 0.0 : (prob <= 0.000001 ? 60.0 : -10 * std::log10(prob));
+            return phred < maq;
+        };
+        uint32_t lo_b = 0, hi_b = 0x7F800000u;  // +0 .. +inf; low(+inf) holds because maq > 0
+        if (low(lo_b)) hi_b = lo_b;
+        while (hi_b - lo_b > 1 && !low(lo_b)) {
+            const uint32_t mid = lo_b + (hi_b - lo_b) / 2;
+            if (low(mid)) hi_b = mid;
+            else lo_b = mid;
+        }
+        memcpy(&p.maq_prob, &hi_b, 4);
+        for (int raw = 0; raw < 256; raw++) {
+            const int8_t q = (int8_t)(uint8_t)(raw - cfg->qual_offset);
+            float pe = .75f;
+            if (q >= 1) {
+                pe = (float)std::pow(10.0, 0 - .1 * q);
+                if (q == 1) pe = .7f;
+            }
+            p.pe[raw] = pe;
+        }
     }
     const int64_t n_tiles = (n_reads + 31) / 32;
     const int blocks = (int)std::min<int64_t>((n_tiles + QT_THREADS / 32 - 1) / (QT_THREADS / 32), (int64_t)sm_count * 8);

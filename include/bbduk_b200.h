@@ -281,7 +281,9 @@ typedef struct bbduk_qtrim_cfg {
     int32_t trim_poly_g_left, trim_poly_g_right, filter_poly_g; /* trimpolyg[left|right]=, filterpolyg= */
     int32_t trim_poly_c_left, trim_poly_c_right, filter_poly_c; /* trimpolyc[left|right]=, filterpolyc= */
     int32_t max_non_poly;      /* maxnonpoly= ; default 1 */
-    int32_t reserved[4];
+    float   min_avg_quality;   /* maq= / minavgquality= ; 0 = off (average by error probability, stream/Read.java:2181-2226) */
+    int32_t min_avg_quality_bases; /* maq=Q,N / maqb= : only the first N bases; 0 = all */
+    int32_t reserved[2];
 } bbduk_qtrim_cfg;
 BBDUK_API void bbduk_b200_qtrim_cfg_default(bbduk_qtrim_cfg *cfg);
 
@@ -289,9 +291,11 @@ BBDUK_API void bbduk_b200_qtrim_cfg_default(bbduk_qtrim_cfg *cfg);
  * (trimPolyA, trimPoly, detectPolyLeft / Right, jgi/BBDuk.java:4721-4825, each followed by its minlen test and
  * shouldRemove; the reference's poly-C filter of r2 looks at r1, :3035, and so does this), then TrimRead.trimFast in its default
  * "optimal" mode (shared/TrimRead.java:113-169, :348-410: the maximum-sum run of avgErrorRate - probError, single
- * precision, then trimByAmount(r, a, b, 1)), the minlen / maxlen test, shouldRemove, then minbasequality and maxns with
- * their shouldRemove (jgi/BBDuk.java:3074-3170; minavgquality, maxnrate, minconsecutivebases and minbasefrequency are at
- * their defaults = off). paired != 0: reads (2i, 2i+1) are mates. Units whose flags carry BBDUK_F_REMOVED are skipped.
+ * precision, then trimByAmount(r, a, b, 1)), the minlen / maxlen test, shouldRemove, then minavgquality, minbasequality and
+ * maxns with their shouldRemove (jgi/BBDuk.java:3074-3170; maxnrate, minconsecutivebases and minbasefrequency are at their
+ * defaults = off). minavgquality compares -10*log10(expectedErrors/bases) in double precision with the threshold; the
+ * device compares the error probability with the smallest float for which that test holds (found on the host with the
+ * C library's log10), which is the same predicate. paired != 0: reads (2i, 2i+1) are mates. Units whose flags carry BBDUK_F_REMOVED are skipped.
  * lo[], hi[] and flags[] (BBDUK_F_QTRIMMED, BBDUK_F_POLYTRIMMED, BBDUK_F_DISCARDED, BBDUK_F_REMOVED) are updated in place;
  * stats8 += {readsQTrimmed, basesQTrimmed, readsQFiltered, basesQFiltered, readsNFiltered, basesNFiltered, readsPolyTrimmed,
  * basesPolyTrimmed}.

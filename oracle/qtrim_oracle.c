@@ -12,8 +12,9 @@
  *                                       minlen test and shouldRemove -- including the reference's use of r1 in the
  *                                       filterpolyc test of r2 (:3035)
  *   jgi/BBDuk.java:3074-3108            "Do quality trimming": trimFast of r1 and r2, minlen / maxlen, shouldRemove
- *   jgi/BBDuk.java:3110-3170            "Do quality filtering": minbasequality, maxns, shouldRemove (minavgquality,
- *                                       maxnrate, minconsecutivebases, minbasefrequency at their defaults = off)
+ *   jgi/BBDuk.java:3110-3170            "Do quality filtering": minavgquality (stream/Read.java:2181-2226, :2985-3001,
+ *                                       align2/QualityTools.java:674-680), minbasequality, maxns, shouldRemove (maxnrate,
+ *                                       minconsecutivebases, minbasefrequency at their defaults = off)
  *   jgi/BBDuk.java:3260-3289            setDiscarded, isDiscarded, isNullOrDiscarded, isNotDiscarded, shouldRemove
  *   shared/TrimRead.java:140-169        trimFast (optimalMode=true :954, discardUnder=0)
  *   shared/TrimRead.java:348-410        testOptimal (NPROB=0.75f :964)
@@ -37,6 +38,9 @@ typedef struct qtrim_params {
     /* poly-X (parse/Parser.java:386-411, :1815-1831) */
     int32_t trim_poly_a, trim_poly_g_left, trim_poly_g_right, filter_poly_g, trim_poly_c_left, trim_poly_c_right, filter_poly_c,
         max_non_poly;
+    /* minavgquality= (parse/Parser.java:516-526) */
+    float min_avg_quality;
+    int32_t min_avg_quality_bases;
 } qtrim_params;
 
 static float g_pe[128];
@@ -205,6 +209,26 @@ static int trim_poly(qread *r, int minLeft, int minRight, int maxNonPoly, uint8_
     return trimmed;
 }
 
+/* Read.avgQuality(false, maxBases) with AVERAGE_QUALITY_BY_PROBABILITY (stream/Read.java:2181-2226): expectedErrors over
+ * the defined bases (:2985-3001), divided by the number of bases looked at, as a phred score in double precision */
+static double avg_quality(const qread *r, int qual_offset, int max_bases) {
+    const int n = r->hi - r->lo;
+    if (n == 0) return 0;
+    const int limit = max_bases < 1 ? n : (max_bases < n ? max_bases : n);
+    float sum = 0;
+    for (int i = 0; i < limit; i++) {
+        if (is_defined(r->bases[r->lo + i])) {
+            const int8_t q = (int8_t)(r->quals[r->lo + i] - qual_offset);
+            sum += g_pe[q < 0 ? 0 : q];
+        }
+    }
+    const float pr = sum / limit;
+    const double prob = pr; /* align2/QualityTools.java:674-680 */
+    if (prob >= 1) return 0;
+    if (prob <= 0.000001) return 60;
+    return -10 * log10(prob);
+}
+
 static void set_discarded(const qtrim_params *p, qread *r) { /* jgi/BBDuk.java:3260-3266 */
     if (p->trim_failures_to_1bp) {
         if (r->hi - r->lo > 1) trim_by_amount(r, 0, r->hi - r->lo - 1, 1);
@@ -317,6 +341,11 @@ void qtrim_ora_process(const uint8_t *bases, const uint8_t *quals, const int64_t
         }
         /* :3110-3170 */
         if (!remove) {
+            if (p->min_avg_quality > 0) {
+                for (int q = 0; q < per; q++)
+                    if (rr[q].quals && avg_quality(&rr[q], p->qual_offset, p->min_avg_quality_bases) < p->min_avg_quality)
+                        set_discarded(p, &rr[q]);
+            }
             if (p->min_base_quality > 0) {
                 for (int q = 0; q < per; q++) {
                     if (!rr[q].quals) continue;

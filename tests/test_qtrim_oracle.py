@@ -1,6 +1,7 @@
 """CPU test of the poly-X / quality-trimming / quality-filter oracle (oracle/qtrim_oracle.c) against an independently
 written Python restatement of jgi/BBDuk.java:2954-3052, :3074-3170, :4721-4825 + shared/TrimRead.java:140-169, :299-410
 (poly-X runs found with regular expressions / string scans instead of the reference's counters), plus hand-checked cases."""
+import math
 import re
 import numpy as np
 import pytest
@@ -183,6 +184,23 @@ def py_block(bases, quals, offsets, paired, lo, hi, flags, p):
             st[1] += sum(hi[i] - lo[i] for i in idx)
             remove = True
         if not remove:
+            if p.min_avg_quality > 0:
+                for i in idx:
+                    n = hi[i] - lo[i]
+                    if n == 0:
+                        avg = 0.0
+                    else:
+                        lim = n if p.min_avg_quality_bases < 1 else min(n, p.min_avg_quality_bases)
+                        b = bases[offsets[i] + lo[i]:offsets[i] + lo[i] + lim]
+                        q = (quals[offsets[i] + lo[i]:offsets[i] + lo[i] + lim].astype(np.int64) - p.qual_offset).astype(np.int8)
+                        ee = F32(0)
+                        for bb, qq in zip(b, q):
+                            if chr(bb) in "ACGTUacgtu":
+                                ee = F32(ee + PE[max(int(qq), 0)])
+                        pr = float(F32(ee / F32(lim)))
+                        avg = 0.0 if pr >= 1 else 60.0 if pr <= 0.000001 else -10 * math.log10(pr)
+                    if avg < float(F32(p.min_avg_quality)):
+                        set_discarded(i)
             if p.min_base_quality > 0:
                 for i in idx:
                     q = (quals[offsets[i] + lo[i]:offsets[i] + hi[i]].astype(np.int64) - p.qual_offset).astype(np.int8)
@@ -274,7 +292,8 @@ CASES = [dict(qtrim="rl", trimq=10.0), dict(qtrim="r", trimq=6.0), dict(qtrim="l
          dict(qtrim="", mbq=5, maxns=1), dict(qtrim="r", trimq=0.5, maxns=0, maxlen=70, mlf=0.5), dict(qtrim="rl", trimq=1.0),
          dict(qtrim="", polya=3, minlen=30), dict(qtrim="rl", trimq=8.0, polyg=(4, 4), fpolyc=5, maxnonpoly=1),
          dict(qtrim="", polyg=(2, 0), polyc=(0, 3), fpolyg=6, maxnonpoly=0, rieb=False),
-         dict(qtrim="r", trimq=12.0, polya=2, polyg=(3, 3), polyc=(3, 3), fpolyg=8, fpolyc=8, maxnonpoly=2, tf1=True)]
+         dict(qtrim="r", trimq=12.0, polya=2, polyg=(3, 3), polyc=(3, 3), fpolyg=8, fpolyc=8, maxnonpoly=2, tf1=True),
+         dict(qtrim="", maq=20.0), dict(qtrim="rl", trimq=5.0, maq=13.5, maqb=40, mbq=1), dict(qtrim="", maq=7.0, rieb=False)]
 
 
 @pytest.mark.parametrize("case", range(len(CASES)))
