@@ -126,6 +126,18 @@ class BBDukEntropyCfg(C.Structure):
     ]
 
 
+class BBDukChainCfg(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32),
+        ("do_tbo", C.c_int32),
+        ("do_qtrim", C.c_int32),
+        ("do_entropy", C.c_int32),
+        ("tbo", BBDukTboCfg),
+        ("qtrim", BBDukQtrimCfg),
+        ("entropy", BBDukEntropyCfg),
+    ]
+
+
 class BBDukStats(C.Structure):
     _fields_ = [
         ("reads_in", C.c_int64),

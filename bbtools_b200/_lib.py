@@ -2,7 +2,7 @@
 import ctypes as C
 import os
 
-from ._abi import ABI_VERSION, BBDukCfg, BBDukEntropyCfg, BBDukOut, BBDukQtrimCfg, BBDukStats, BBDukTableDesc, BBDukTboCfg
+from ._abi import ABI_VERSION, BBDukCfg, BBDukChainCfg, BBDukEntropyCfg, BBDukOut, BBDukQtrimCfg, BBDukStats, BBDukTableDesc, BBDukTboCfg
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbbduk_b200.so")
@@ -44,6 +44,9 @@ SYMBOLS = [
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     ("bbduk_b200_entropy_device", C.c_int, [C.c_void_p, C.POINTER(BBDukEntropyCfg), C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("bbduk_b200_chain_cfg_default", None, [C.POINTER(BBDukChainCfg)]),
+    ("bbduk_b200_process_chain", C.c_int, [C.c_void_p, C.POINTER(BBDukChainCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                           C.c_int32, C.POINTER(BBDukOut), C.POINTER(BBDukStats), C.c_void_p, C.c_void_p, C.c_void_p]),
     ("bbduk_b200_pack_bases", C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     ("bbduk_b200_synth_reference", C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]),
     ("bbduk_b200_synth_contam", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64,

@@ -495,6 +495,30 @@ class BBDukIndexGPU:
         self._check(self.lib.bbduk_b200_entropy_device(self.h, C.byref(cfg), ptr(d_bases), ptr(d_offsets), n_reads, int(bool(paired)),
                                                        ptr(d_lo), ptr(d_hi), ptr(d_flags), ptr(d_stats), ptr(stream)), "entropy_device")
 
+    # -- the whole device part of the per-pair loop in one call -------------------------------------------
+    def process_chain(self, bases, quals, offsets, paired, tbo=None, qtrim=None, entropy=None):
+        """HOST buffers: k-mer block, then the given steps (their cfg structs, or None to skip) with ONE upload of the batch.
+        -> (Outputs, BBDukStats, tbo stats2, qtrim stats8, entropy stats2)"""
+        from ._abi import BBDukChainCfg
+        c = BBDukChainCfg()
+        self.lib.bbduk_b200_chain_cfg_default(C.byref(c))
+        for name, step in (("tbo", tbo), ("qtrim", qtrim), ("entropy", entropy)):
+            if step is not None:
+                setattr(c, "do_" + name, 1)
+                setattr(c, name, step)
+        bases = np.ascontiguousarray(bases, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        q = None if quals is None else np.ascontiguousarray(quals, np.uint8)
+        n = len(offsets) - 1
+        out = Outputs(n)
+        o = out.struct()
+        st = BBDukStats()
+        t2, q8, e2 = np.zeros(2, np.int64), np.zeros(8, np.int64), np.zeros(2, np.int64)
+        self._check(self.lib.bbduk_b200_process_chain(self.h, C.byref(c), bases.ctypes.data, None if q is None else q.ctypes.data,
+                                                      offsets.ctypes.data, n, int(bool(paired)), C.byref(o), C.byref(st),
+                                                      t2.ctypes.data, q8.ctypes.data, e2.ctypes.data), "process_chain")
+        return out, st, t2, q8, e2
+
     def set_max_read_len(self, n):
         self._check(self.lib.bbduk_b200_set_max_read_len(self.h, int(n)), "set_max_read_len")
 
@@ -551,15 +575,19 @@ class BBDuk:
         paired = bool(io["in2"] or io["interleaved"])
         per = 2 if paired else 1
         bases, offsets = fb.arrays()
-        out, st = self.process_arrays(bases, offsets, paired)
+        want_tbo, want_q, want_e = bool(io["tbo"] and paired), self._wants_qtrim(), io["entropy"] >= 0
+        if want_tbo or want_q or want_e:
+            # one upload of the batch, the steps hand lo / hi / flags to each other on the device
+            quals = fb.quals() if (want_tbo or want_q) else None
+            out, st, t2, q8, e2 = self.index.process_chain(bases, quals, offsets, paired, tbo=self._tbo_cfg() if want_tbo else None,
+                                                           qtrim=self._qtrim_cfg() if want_q else None,
+                                                           entropy=self._entropy_cfg() if want_e else None)
+            self.tbo_stats = t2 if want_tbo else None
+            self.qtrim_stats = q8 if want_q else None
+            self.entropy_stats = e2 if want_e else None
+        else:
+            out, st = self.process_arrays(bases, offsets, paired)
         self.stats = st
-        quals = fb.quals() if ((io["tbo"] and paired) or self._wants_qtrim()) else None
-        if io["tbo"] and paired:
-            self.tbo_stats = self._tbo(bases, quals, offsets, out)
-        if self._wants_qtrim():
-            self.qtrim_stats = self._qtrim(bases, quals, offsets, paired, out)
-        if io["entropy"] >= 0:
-            self.entropy_stats = self._entropy(bases, offsets, paired, out)
         for removed, p1, p2 in ((False, io["out1"], io["out2"]), (True, io["outm1"], io["outm2"])):
             if not p1:
                 continue
@@ -569,11 +597,13 @@ class BBDuk:
         self._write_stats()
         return st
 
+    def _tbo_cfg(self):
+        io = self.io
+        return self.index.tbo_cfg(strict_overlap=int(io["strictoverlap"]), min_overlap=io["minoverlap"], min_insert=io["mininsert"])
+
     def _tbo(self, bases, quals, offsets, out):
         """the tbo block (jgi/BBDuk.java:2878-2926) on the batch the k-mer block just answered; updates out.hi / out.flags"""
-        io = self.io
-        cfg = self.index.tbo_cfg(strict_overlap=int(io["strictoverlap"]), min_overlap=io["minoverlap"], min_insert=io["mininsert"])
-        _, st = self.index.tbo(bases, quals, offsets, out, cfg)
+        _, st = self.index.tbo(bases, quals, offsets, out, self._tbo_cfg())
         return st
 
     def _wants_qtrim(self):
@@ -585,21 +615,25 @@ class BBDuk:
 
     def _qtrim(self, bases, quals, offsets, paired, out):
         """quality trimming, minlen / maxlen, mbq, maxns (jgi/BBDuk.java:3074-3170); updates out.lo / out.hi / out.flags"""
+        return self.index.qtrim(bases, quals, offsets, paired, out, self._qtrim_cfg())
+
+    def _qtrim_cfg(self):
         io = self.io
-        cfg = self.index.qtrim_cfg(qtrim_left=int(io["qtrim_left"]), qtrim_right=int(io["qtrim_right"]), trimq=io["trimq"],
+        return self.index.qtrim_cfg(qtrim_left=int(io["qtrim_left"]), qtrim_right=int(io["qtrim_right"]), trimq=io["trimq"],
                                    min_base_quality=io["mbq"], max_ns=io["maxns"], max_read_length=io["maxlen"],
                                    trim_poly_a=io["trimpolya"], trim_poly_g_left=io["trimpolygleft"],
                                    trim_poly_g_right=io["trimpolygright"], filter_poly_g=io["filterpolyg"],
                                    trim_poly_c_left=io["trimpolycleft"], trim_poly_c_right=io["trimpolycright"],
                                    filter_poly_c=io["filterpolyc"], max_non_poly=io["maxnonpoly"], min_avg_quality=io["maq"],
                                    min_avg_quality_bases=io["maqb"])
-        return self.index.qtrim(bases, quals, offsets, paired, out, cfg)
+
+    def _entropy_cfg(self):
+        io = self.io
+        return self.index.entropy_cfg(cutoff=io["entropy"], k=io["entropyk"], window=io["entropywindow"])
 
     def _entropy(self, bases, offsets, paired, out):
         """the low-entropy read filter (jgi/BBDuk.java:3175-3186); updates out.flags"""
-        io = self.io
-        return self.index.entropy(bases, offsets, paired, out,
-                                  self.index.entropy_cfg(cutoff=io["entropy"], k=io["entropyk"], window=io["entropywindow"]))
+        return self.index.entropy(bases, offsets, paired, out, self._entropy_cfg())
 
     def _write_stats(self):
         io = self.io

@@ -83,7 +83,9 @@ struct bbduk_handle {
         uint8_t *d_bases = nullptr, *d_quals = nullptr, *d_flags = nullptr;
         uint32_t *d_off = nullptr;
         int32_t *d_lo = nullptr, *d_hi = nullptr, *d_insert = nullptr;
-        int64_t cap_bases = 0, cap_quals = 0, cap_flags = 0, cap_off = 0, cap_lo = 0, cap_hi = 0, cap_insert = 0;
+        int32_t *d_id0 = nullptr, *d_count = nullptr;
+        int64_t cap_bases = 0, cap_quals = 0, cap_flags = 0, cap_off = 0, cap_lo = 0, cap_hi = 0, cap_insert = 0, cap_id0 = 0,
+                cap_count = 0;
     } tbo;
     std::mutex tbo_mu;
     HostPool *pool = nullptr;  // host packing workers, created on first use
@@ -1050,6 +1052,118 @@ int bbduk_b200_entropy(bbduk_handle *h, const bbduk_entropy_cfg *cfg, const uint
     return rc;
 }
 
+void bbduk_b200_chain_cfg_default(bbduk_chain_cfg *c) {
+    if (!c) return;
+    memset(c, 0, sizeof *c);
+    c->struct_size = (int32_t)sizeof *c;
+    bbduk_b200_tbo_cfg_default(&c->tbo);
+    bbduk_b200_qtrim_cfg_default(&c->qtrim);
+    bbduk_b200_entropy_cfg_default(&c->entropy);
+}
+
+int bbduk_b200_process_chain(bbduk_handle *h, const bbduk_chain_cfg *cfg, const uint8_t *bases, const uint8_t *quals,
+                             const int64_t *offsets, int64_t n_reads, int32_t paired, const bbduk_out *out, bbduk_stats *stats,
+                             int64_t *tbo_stats2, int64_t *qtrim_stats8, int64_t *entropy_stats2) {
+    if (!h) return set_err(nullptr, "handle is NULL");
+    if (!cfg || cfg->struct_size != (int32_t)sizeof *cfg) return set_err(h, "bad bbduk_chain_cfg");
+    if (!h->finalized) return set_err(h, "process before finalize");
+    if (n_reads < 0 || (paired && (n_reads & 1))) return set_err(h, "bad n_reads (paired input needs an even count)");
+    if (h->p.mode == MODE_KMASK || h->p.mode == MODE_KSPLIT) return set_err(h, "kmask / ksplit are not chained (they rewrite bases)");
+    if (!out || !out->lo || !out->hi || !out->flags) return set_err(h, "the chain needs out->lo, out->hi and out->flags");
+    if (cfg->do_tbo && !paired) return set_err(h, "tbo needs paired reads");
+    const bool need_q = (cfg->do_tbo && quals) || (cfg->do_qtrim && (cfg->qtrim.qtrim_left || cfg->qtrim.qtrim_right ||
+                                                                     cfg->qtrim.min_base_quality > 0 || cfg->qtrim.min_avg_quality > 0));
+    if (need_q && !quals) return set_err(h, "qtrim / mbq / maq need quality bytes");
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (n_reads == 0) return 0;
+    if (!bases || !offsets) return set_err(h, "NULL input");
+    CKH(cudaSetDevice(h->device));
+    std::lock_guard<std::mutex> g(h->tbo_mu);
+    cudaStream_t st = nullptr;  // synchronous entry point: the legacy default stream
+    int64_t *d_st = nullptr;    // [0..7] k-mer block, [8..9] tbo, [10..17] qtrim, [18..19] entropy
+    CKH(cudaMalloc(&d_st, 20 * sizeof(int64_t)));
+    CKH(cudaMemset(d_st, 0, 20 * sizeof(int64_t)));
+    int rc = 0;
+    int64_t r0 = 0;
+    const int per = paired ? 2 : 1;
+    std::vector<uint32_t> off32;
+    while (r0 < n_reads && !rc) {
+        int64_t r1 = std::min(n_reads, r0 + (CHUNK_READS << 1));
+        while (r1 > r0 + per && offsets[r1] - offsets[r0] > CHUNK_BYTES) r1 = r0 + std::max<int64_t>(per, ((r1 - r0) / 2 / per) * per);
+        const int64_t nr = r1 - r0, nb = offsets[r1] - offsets[r0];
+        if (nb < 0 || nb >= (1ll << 32) - 64) {
+            rc = set_err(h, "a read (pair) exceeds 4 GiB (or offsets decrease)");
+            break;
+        }
+        int max_len = 0;
+        off32.resize(nr + 1);
+        for (int64_t i = 0; i <= nr; i++) off32[i] = (uint32_t)(offsets[r0 + i] - offsets[r0]);
+        for (int64_t i = 0; i < nr; i++) max_len = std::max(max_len, (int)(off32[i + 1] - off32[i]));
+        auto need = [&](void **p, int64_t *cap, int64_t bytes) -> int {
+            if (bytes <= *cap) return 0;
+            cudaFree(*p);
+            *p = nullptr;
+            *cap = bytes + bytes / 8 + 4096;
+            return cudaMalloc(p, (size_t)*cap) == cudaSuccess ? 0 : 1;
+        };
+        auto &tb = h->tbo;
+        if (need((void **)&tb.d_bases, &tb.cap_bases, nb + 64) || (need_q && need((void **)&tb.d_quals, &tb.cap_quals, nb + 64)) ||
+            need((void **)&tb.d_off, &tb.cap_off, 4 * (nr + 1)) || need((void **)&tb.d_lo, &tb.cap_lo, 4 * nr) ||
+            need((void **)&tb.d_hi, &tb.cap_hi, 4 * nr) || need((void **)&tb.d_flags, &tb.cap_flags, nr) ||
+            need((void **)&tb.d_insert, &tb.cap_insert, 2 * nr + 8) || (out->id0 && need((void **)&tb.d_id0, &tb.cap_id0, 4 * nr)) ||
+            (out->count && need((void **)&tb.d_count, &tb.cap_count, 4 * nr))) {
+            rc = set_err(h, "chain: device allocation failed");
+            break;
+        }
+#define CKC(call)                                                                       \
+    if (!rc && (call) != cudaSuccess) rc = set_err(h, std::string(#call " failed: ") + cudaGetErrorString(cudaGetLastError()))
+        CKC(cudaMemcpyAsync(tb.d_bases, bases + offsets[r0], (size_t)nb, cudaMemcpyHostToDevice, st));
+        if (need_q) CKC(cudaMemcpyAsync(tb.d_quals, quals + offsets[r0], (size_t)nb, cudaMemcpyHostToDevice, st));
+        CKC(cudaMemcpyAsync(tb.d_off, off32.data(), 4 * (size_t)(nr + 1), cudaMemcpyHostToDevice, st));
+        bbduk_out dout;
+        memset(&dout, 0, sizeof dout);
+        dout.lo = tb.d_lo;
+        dout.hi = tb.d_hi;
+        dout.flags = tb.d_flags;
+        dout.id0 = out->id0 ? tb.d_id0 : nullptr;
+        dout.count = out->count ? tb.d_count : nullptr;
+        const int hint = h->max_read_len_hint.exchange(max_len);
+        if (!rc) rc = bbduk_b200_process_device(h, tb.d_bases, tb.d_off, nr, paired, &dout, reinterpret_cast<bbduk_stats *>(d_st), st);
+        h->max_read_len_hint = hint;
+        if (!rc && cfg->do_tbo)
+            rc = bbduk_b200_tbo_device(h, &cfg->tbo, tb.d_bases, quals ? tb.d_quals : nullptr, tb.d_off, nr, max_len, tb.d_lo, tb.d_hi,
+                                       tb.d_flags, tb.d_insert, d_st + 8, st);
+        if (!rc && cfg->do_qtrim)
+            rc = bbduk_b200_qtrim_device(h, &cfg->qtrim, tb.d_bases, need_q ? tb.d_quals : nullptr, tb.d_off, nr, paired, tb.d_lo,
+                                         tb.d_hi, tb.d_flags, d_st + 10, st);
+        if (!rc && cfg->do_entropy)
+            rc = bbduk_b200_entropy_device(h, &cfg->entropy, tb.d_bases, tb.d_off, nr, paired, tb.d_lo, tb.d_hi, tb.d_flags, d_st + 18, st);
+        CKC(cudaMemcpyAsync(out->lo + r0, tb.d_lo, 4 * (size_t)nr, cudaMemcpyDeviceToHost, st));
+        CKC(cudaMemcpyAsync(out->hi + r0, tb.d_hi, 4 * (size_t)nr, cudaMemcpyDeviceToHost, st));
+        CKC(cudaMemcpyAsync(out->flags + r0, tb.d_flags, (size_t)nr, cudaMemcpyDeviceToHost, st));
+        if (out->id0) CKC(cudaMemcpyAsync(out->id0 + r0, tb.d_id0, 4 * (size_t)nr, cudaMemcpyDeviceToHost, st));
+        if (out->count) CKC(cudaMemcpyAsync(out->count + r0, tb.d_count, 4 * (size_t)nr, cudaMemcpyDeviceToHost, st));
+        CKC(cudaStreamSynchronize(st));
+#undef CKC
+        r0 = r1;
+    }
+    if (!rc) {
+        int64_t v[20];
+        if (cudaMemcpy(v, d_st, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) rc = set_err(h, "chain: stats copy failed");
+        if (!rc) {
+            if (stats) memcpy(stats, v, 8 * sizeof(int64_t));
+            if (tbo_stats2)
+                for (int i = 0; i < 2; i++) tbo_stats2[i] += v[8 + i];
+            if (qtrim_stats8)
+                for (int i = 0; i < 8; i++) qtrim_stats8[i] += v[10 + i];
+            if (entropy_stats2)
+                for (int i = 0; i < 2; i++) entropy_stats2[i] += v[18 + i];
+        }
+    }
+    cudaFree(d_st);
+    return rc;
+}
+
 int bbduk_b200_pack_bases(const uint8_t *bases, int64_t n, uint32_t *F, uint16_t *D) {
     if (n < 0 || (n > 0 && (!bases || !F || !D))) return set_err(nullptr, "bad pack_bases arguments");
     pack_bases(bases, n, F, D);
@@ -1083,6 +1197,8 @@ void bbduk_b200_destroy(bbduk_handle *h) {
     cudaFree(h->tbo.d_lo);
     cudaFree(h->tbo.d_hi);
     cudaFree(h->tbo.d_insert);
+    cudaFree(h->tbo.d_id0);
+    cudaFree(h->tbo.d_count);
     delete h->pool;
     delete h;
 }

@@ -549,6 +549,32 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e_value = world * e_reads * e_steps / float(te.item())
 
+    # ---- the whole chain end to end (k-mer block + tbo + qtrim=rl trimq=10) through ONE C-ABI call, host buffers ----
+    chain_info = None
+    if args.workload == "cfg2":
+        c_pairs = min(e_pairs, 1 << 20)
+        c_reads = 2 * c_pairs
+        cb, co = hb[: c_reads * L], ho[: c_reads + 1]
+        rngq = np.random.default_rng(3 + rank)
+        h_cq = torch.empty(c_reads * L, dtype=torch.uint8, pin_memory=True)
+        cq = h_cq.numpy()
+        cq[:] = (33 + np.clip(40 - (np.arange(c_reads * L, dtype=np.int32) % L) * rngq.integers(0, 45, c_reads * L, dtype=np.int32) // L,
+                              2, 41)).astype(np.uint8)
+        tcfg, qcfg2 = eng.tbo_cfg(), eng.qtrim_cfg(qtrim_left=1, qtrim_right=1, trimq=10.0)
+        eng.process_chain(cb, cq, co, True, tbo=tcfg, qtrim=qcfg2)
+        barrier()
+        t0 = time.perf_counter()
+        c_steps = 3
+        for _ in range(c_steps):
+            _, _, ct2, cq8, _ = eng.process_chain(cb, cq, co, True, tbo=tcfg, qtrim=qcfg2)
+        c_dt = time.perf_counter() - t0
+        tc = torch.tensor([c_dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        chain_info = {"reads_per_s": world * c_reads * c_steps / float(tc.item()), "pairs_per_call_per_gpu": c_pairs,
+                      "h2d_bytes_per_call": int(cb.nbytes + cq.nbytes + 4 * (c_reads + 1)), "d2h_bytes_per_call": 9 * c_reads,
+                      "reads_trimmed_by_overlap": int(ct2[0]), "reads_qtrimmed": int(cq8[0])}
+
     # ---- sanity: the timed batch agrees with the CPU oracle on a slice (checker only) -----------------
     parity = None
     if rank == 0 and (args.workload == "cfg2" or args.verify):
@@ -601,7 +627,8 @@ def run_ours(args):
                        "stored_kmers": stored, "l2": f"inputs {n_reads * L / 2**20:.0f} MiB per step > 126 MB L2, "
                        f"{nbuf} alternating buffers, no flush", "table_build_s": round(t_build, 3),
                        "parity_vs_oracle_on_timed_batch": parity, "kmer_block_plus_tbo": tbo_info,
-                       "qtrim_block": qtrim_info, "entropy_block": entropy_info},
+                       "qtrim_block": qtrim_info, "entropy_block": entropy_info,
+                       "chain_e2e_kmer_tbo_qtrim": chain_info},
             "e2e": {"value": e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "pairs_per_step_per_gpu": e_pairs, "steps": e_steps},
             "gpu_launches": int(launches),

@@ -338,6 +338,28 @@ BBDUK_API int bbduk_b200_entropy_device(bbduk_handle *h, const bbduk_entropy_cfg
                                         const uint32_t *d_offsets, int64_t n_reads, int32_t paired, const int32_t *d_lo,
                                         int32_t *d_hi, uint8_t *d_flags, int64_t *d_stats2, void *stream);
 
+/*
+ * The whole device part of the per-pair loop in ONE call: the k-mer block, then (each optional) trim by overlap, poly-X /
+ * quality trimming with the quality / length / N filters, and the low-entropy filter, in the reference's order
+ * (jgi/BBDuk.java:2727-2873, :2878-2926, :2954-3052 + :3074-3170, :3175-3186). The batch crosses PCIe once (bases, and
+ * qualities if a step needs them); the steps hand lo / hi / flags to each other on the device.
+ */
+typedef struct bbduk_chain_cfg {
+    int32_t struct_size;        /* = sizeof(bbduk_chain_cfg) */
+    int32_t do_tbo, do_qtrim, do_entropy;
+    bbduk_tbo_cfg tbo;
+    bbduk_qtrim_cfg qtrim;
+    bbduk_entropy_cfg entropy;
+} bbduk_chain_cfg;
+BBDUK_API void bbduk_b200_chain_cfg_default(bbduk_chain_cfg *cfg);
+
+/* HOST buffers, as bbduk_b200_process (ktrim / kfilter modes; kmask and ksplit rewrite bases and are not chained).
+ * out->lo, out->hi and out->flags are required, out->id0 / out->count optional. stats = the k-mer block's counters;
+ * tbo_stats2, qtrim_stats8, entropy_stats2 are added to as by the single-step entry points (any may be NULL). */
+BBDUK_API int bbduk_b200_process_chain(bbduk_handle *h, const bbduk_chain_cfg *cfg, const uint8_t *bases, const uint8_t *quals,
+                                       const int64_t *offsets, int64_t n_reads, int32_t paired, const bbduk_out *out,
+                                       bbduk_stats *stats, int64_t *tbo_stats2, int64_t *qtrim_stats8, int64_t *entropy_stats2);
+
 /* Host helper (no GPU needed): the 2-bit packing bbduk_b200_process applies to a chunk before it crosses PCIe when
  * the tuned kernel takes the whole chunk (set BBDUK_B200_PACK_HOST=0 to ship ASCII instead). F[i] = big-endian
  * 2-bit codes of bases 16i..16i+15 (A0 C1 G2 T/U3, anything else 0), D[i] = "defined" bits (bit 15-b = base 16i+b);
