@@ -106,6 +106,10 @@ public final class BBDukIndexGPU extends BBDukIndex {
 			boolean paired, int[] lo, int[] hi, byte[] flags, long[] stats8);
 	private static native int entropyNative(long h, int[] cfg, float cutoff, byte[] bases, long[] offsets, long nReads, boolean paired,
 			int[] lo, int[] hi, byte[] flags, long[] stats2);
+	/** k-mer block + tbo + poly-X / quality trimming / filters + entropy filter in one native call (one upload of the batch);
+	 * steps = {doTbo, doQtrim, doEntropy}, floats = {meeFilter, trimq, entropyCutoff}, stats28 as documented in jni/BBDukCuda.c. */
+	static native int processChainNative(long h, int[] steps, int[] tboCfg, int[] qCfg, int[] eCfg, float[] floats, byte[] bases,
+			byte[] quals, long[] offsets, long nReads, boolean paired, int[] id0, int[] lo, int[] hi, byte[] flags, long[] stats28);
 	private static native int scaffoldCountsNative(long h, long[] reads, long[] bases);
 	private static native String lastErrorNative(long h);
 	private static native void destroyNative(long h);

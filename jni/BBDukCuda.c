@@ -215,6 +215,82 @@ JNIEXPORT jint JNICALL Java_bbduk_BBDukIndexGPU_entropyNative(JNIEnv *env, jclas
     return rc;
 }
 
+/* The whole device part of the per-pair loop in one call (bbduk_b200_process_chain): k-mer block, then tbo / poly-X + quality
+ * trimming + filters / entropy filter as switched on in `steps` = {doTbo, doQtrim, doEntropy}. tboCfg, qCfg, eCfg and the
+ * three floats as in tboNative / qtrimNative / entropyNative. stats28 = 8 (k-mer block, overwritten) + 2 (tbo) + 8 (qtrim) +
+ * 2 (entropy) + 8 spare longs. */
+JNIEXPORT jint JNICALL Java_bbduk_BBDukIndexGPU_processChainNative(JNIEnv *env, jclass cls, jlong handle, jintArray jsteps,
+                                                                   jintArray jtbo, jintArray jq, jintArray je, jfloatArray jfl,
+                                                                   jbyteArray jbases, jbyteArray jquals, jlongArray joffsets,
+                                                                   jlong nReads, jboolean paired, jintArray jid0, jintArray jlo,
+                                                                   jintArray jhi, jbyteArray jflags, jlongArray jstats28) {
+    bbduk_chain_cfg cfg;
+    jint st3[3], t[6], q[14], e[3];
+    jfloat f[3];
+    bbduk_out out;
+    bbduk_stats st;
+    int64_t extra[12];
+    memset(&out, 0, sizeof out);
+    memset(extra, 0, sizeof extra);
+    bbduk_b200_chain_cfg_default(&cfg);
+    (*env)->GetIntArrayRegion(env, jsteps, 0, 3, st3);
+    (*env)->GetIntArrayRegion(env, jtbo, 0, 6, t);
+    (*env)->GetIntArrayRegion(env, jq, 0, 14, q);
+    (*env)->GetIntArrayRegion(env, je, 0, 3, e);
+    (*env)->GetFloatArrayRegion(env, jfl, 0, 3, f); /* {meeFilter, trimq, entropyCutoff} */
+    cfg.do_tbo = st3[0];
+    cfg.do_qtrim = st3[1];
+    cfg.do_entropy = st3[2];
+    cfg.tbo.strict_overlap = t[0];
+    cfg.tbo.min_overlap0 = t[1];
+    cfg.tbo.min_overlap = t[2];
+    cfg.tbo.min_insert0 = t[3];
+    cfg.tbo.min_insert = t[4];
+    cfg.tbo.qual_offset = t[5];
+    cfg.tbo.mee_filter = f[0];
+    cfg.qtrim.qtrim_left = q[0];
+    cfg.qtrim.qtrim_right = q[1];
+    cfg.qtrim.min_base_quality = q[2];
+    cfg.qtrim.max_ns = q[3];
+    cfg.qtrim.max_read_length = q[4];
+    cfg.qtrim.qual_offset = q[5];
+    cfg.qtrim.trim_poly_a = q[6];
+    cfg.qtrim.trim_poly_g_left = q[7];
+    cfg.qtrim.trim_poly_g_right = q[8];
+    cfg.qtrim.filter_poly_g = q[9];
+    cfg.qtrim.trim_poly_c_left = q[10];
+    cfg.qtrim.trim_poly_c_right = q[11];
+    cfg.qtrim.filter_poly_c = q[12];
+    cfg.qtrim.max_non_poly = q[13];
+    cfg.qtrim.trimq = f[1];
+    cfg.entropy.k = e[0];
+    cfg.entropy.window = e[1];
+    cfg.entropy.high_pass = e[2];
+    cfg.entropy.cutoff = f[2];
+    jbyte *b = (jbyte *)(*env)->GetPrimitiveArrayCritical(env, jbases, NULL);
+    jbyte *qq = jquals ? (jbyte *)(*env)->GetPrimitiveArrayCritical(env, jquals, NULL) : NULL;
+    jlong *o = (jlong *)(*env)->GetPrimitiveArrayCritical(env, joffsets, NULL);
+    if (jid0) out.id0 = (int32_t *)(*env)->GetPrimitiveArrayCritical(env, jid0, NULL);
+    out.lo = (int32_t *)(*env)->GetPrimitiveArrayCritical(env, jlo, NULL);
+    out.hi = (int32_t *)(*env)->GetPrimitiveArrayCritical(env, jhi, NULL);
+    out.flags = (uint8_t *)(*env)->GetPrimitiveArrayCritical(env, jflags, NULL);
+    const jint rc = bbduk_b200_process_chain((bbduk_handle *)(intptr_t)handle, &cfg, (const uint8_t *)b, (const uint8_t *)qq,
+                                             (const int64_t *)o, (int64_t)nReads, paired ? 1 : 0, &out, &st, extra, extra + 2,
+                                             extra + 10);
+    (*env)->ReleasePrimitiveArrayCritical(env, jflags, out.flags, 0);
+    (*env)->ReleasePrimitiveArrayCritical(env, jhi, out.hi, 0);
+    (*env)->ReleasePrimitiveArrayCritical(env, jlo, out.lo, 0);
+    if (jid0) (*env)->ReleasePrimitiveArrayCritical(env, jid0, out.id0, 0);
+    (*env)->ReleasePrimitiveArrayCritical(env, joffsets, o, JNI_ABORT);
+    if (jquals) (*env)->ReleasePrimitiveArrayCritical(env, jquals, qq, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, jbases, b, JNI_ABORT);
+    if (jstats28 && !rc) {
+        (*env)->SetLongArrayRegion(env, jstats28, 0, 8, (const jlong *)&st);
+        (*env)->SetLongArrayRegion(env, jstats28, 8, 12, (const jlong *)extra);
+    }
+    return rc;
+}
+
 JNIEXPORT jint JNICALL Java_bbduk_BBDukIndexGPU_scaffoldCountsNative(JNIEnv *env, jclass cls, jlong handle,
                                                                      jlongArray jreads, jlongArray jbases) {
     const jint n = (*env)->GetArrayLength(env, jreads);

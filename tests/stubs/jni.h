@@ -20,6 +20,7 @@ typedef jobject jarray;
 typedef jarray jintArray;
 typedef jarray jlongArray;
 typedef jarray jbyteArray;
+typedef jarray jfloatArray;
 
 #define JNI_ABORT 2
 #define JNIEXPORT __attribute__((visibility("default")))
@@ -35,5 +36,6 @@ struct JNINativeInterface_ {
     void (*SetLongArrayRegion)(JNIEnv *env, jlongArray array, jsize start, jsize len, const jlong *buf);
     void (*GetLongArrayRegion)(JNIEnv *env, jlongArray array, jsize start, jsize len, jlong *buf);
     void (*GetIntArrayRegion)(JNIEnv *env, jintArray array, jsize start, jsize len, jint *buf);
+    void (*GetFloatArrayRegion)(JNIEnv *env, jfloatArray array, jsize start, jsize len, jfloat *buf);
 };
 #endif
