@@ -112,25 +112,27 @@ __device__ __forceinline__ uint32_t bb_big_word(uint32_t t, uint32_t n_words) { 
 
 // ---- pigeonhole part filter -------------------------------------------------------------------------
 // A window can only hit the table if, on one strand, it agrees with an UNMUTATED reference k-mer on at
-// least one of hdist+1 disjoint parts (substitutions only). The filter holds the part values of every
+// least one of hdist+1 disjoint parts (substitutions only). The filter knows the parts of every
 // reference k-mer and of its reverse complement, so the query needs the forward window only.
-// The part value is the low 2w bits of a 32-bit window v; multiplying by mult = C << (32-2w) discards
-// the higher (foreign) bits for free. g = high half of h*K1 is the well-mixed hash: its top bits pick
-// the word, its low 5 bits one filter bit; a second high-half product picks the other bit. All of it
-// runs on the FMA pipe, which the shift/logic-heavy scan leaves idle.
-#define BB_PART_C 0x9E3779B1u
-__host__ __device__ __forceinline__ uint32_t bb_part_mult(int w) { return (w >= 16) ? BB_PART_C : (BB_PART_C << (32 - 2 * w)); }
-struct BBPartProbe {
-    uint32_t word, b1, b2;  // b1/b2: only their low 5 bits matter
-};
-__device__ __forceinline__ BBPartProbe bb_part_probe(uint32_t v, uint32_t mult, uint32_t n_words) {
-    const uint32_t h = v * mult;
-    const uint32_t g = __umulhi(h, 0x85EBCA77u);
-    BBPartProbe r;
-    r.word = __umulhi(g, n_words);
-    r.b1 = g;
-    r.b2 = __umulhi(h, 0xC2B2AE3Du);
-    return r;
+// It is a DIRECT bitmap over all BB_PART_WD-mers (4^9 bits = 32 KB): a part of w >= 9 bases is in the
+// filter iff each of its w-8 overlapping 9-mers is, so the scan does ONE word load per read position
+// (the 9-mer ending there: no hash, the word index and the bit are fields of the window itself) and
+// rebuilds the w-mer answer bit-parallel as the AND of w-8 consecutive position bits.
+// Bit layout: 9-mer value x (18 bits, newest base lowest) lives in word x>>5 at bit (x-1)&31, so that
+// rotating the word right by x (the funnel shift takes x mod 32) leaves the answer in bit 31, from where
+// one more funnel shift pushes it into the per-step accumulator: 6 instructions per read position.
+#define BB_PART_WD 9
+#define BB_PART_WORDS (1u << (2 * BB_PART_WD - 5))
+__host__ __device__ __forceinline__ uint32_t bb_part_word(uint32_t x) { return (x >> 5) & (BB_PART_WORDS - 1u); }
+__host__ __device__ __forceinline__ uint32_t bb_part_bit(uint32_t x) { return 1u << ((x - 1u) & 31u); }
+// v: 2-bit codes of (at least) the w bases ending at a position, newest base in the low bits
+__device__ __forceinline__ bool bb_part_test(const uint32_t *filt, uint32_t v, int w) {
+    bool ok = true;
+    for (int d = 0; d <= w - BB_PART_WD; d++) {
+        const uint32_t x = v >> (2 * d);
+        ok = ok && (filt[bb_part_word(x)] & bb_part_bit(x)) != 0;
+    }
+    return ok;
 }
 
 // ---- exact key of a window that may contain undefined bases (SURVEY.md A.2 closed form) -------------

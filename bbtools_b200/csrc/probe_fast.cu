@@ -33,6 +33,11 @@ constexpr int PAD = 2;           // zero chunks in front of the staged stream (w
 constexpr int TAIL = 4;          // zero chunks behind it (the reverse-strand words run two steps ahead)
 constexpr int MAX_FAST_LEN = 1008;
 constexpr int FAST_SMEM_LIMIT = 227 * 1024;
+// Holding back a read's candidates beyond CAND_CAP per drain (and releasing them only if all earlier ones miss) was
+// meant for the long streaks of true hits inside an adapter. Measured on cfg 2 it buys nothing at any cap from 2 to 20
+// (gpurun_out/candcap.txt: 2.84-2.91 G reads/s) -- the streak that matters is the FALSE one in front of the first true
+// hit, which has to be evaluated in full -- and its bookkeeping costs 3 % of the instructions, so it is compiled out.
+constexpr bool DEFER = false;
 constexpr int CAND_CAP = 20;         // candidates a read without undefined bases may have unresolved at a time
 constexpr int QCAP = 32 + 32 * 16;   // queue entries: the drain threshold plus one full step of all lanes
 
@@ -97,6 +102,7 @@ __device__ __forceinline__ uint64_t spread2(uint32_t m) {  // bit t -> bits (2t+
     x = (x | (x << 1)) & 0x5555555555555555ull;
     return x | (x << 1);
 }
+__device__ __forceinline__ uint32_t spread16(uint32_t m) { return (uint32_t)spread2(m & 0xFFFFu); }  // 16 bits -> 16 slots
 // reverse the order of the low `n` 2-bit slots (no complement)
 __device__ __forceinline__ uint64_t rev2(uint64_t x, int n) { return bb_rcomp(~x, n); }
 
@@ -184,6 +190,7 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
                   const uint32_t *__restrict__ pk_F, const uint16_t *__restrict__ pk_D) {
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t *filt = smem;
+    const uint8_t *filt_bytes = reinterpret_cast<const uint8_t *>(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t *filt_short = PARTS ? smem + geo.nfw : smem;  // bloom consulted by the short-k-mer tails
     const uint32_t n_short = PARTS ? geo.nsw : geo.nfw;
@@ -243,7 +250,10 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
                 if (c < nchunks) {
                     f = __ldg(pk_F + (a0 >> 4) + c);
                     dbits = __ldg(pk_D + (a0 >> 4) + c);
-                    if (dbits != 0xFFFFu) atomicOr(badw + (c >> 5), 1u << (c & 31));
+                    if (dbits != 0xFFFFu) {
+                        f &= spread16(dbits);  // undefined bases read as code 0 (jgi/BBDuk.java:3882)
+                        atomicOr(badw + (c >> 5), 1u << (c & 31));
+                    }
                 }
             } else if (c < nchunks) {
                 const uint4 v = __ldg(reinterpret_cast<const uint4 *>(a0) + c);
@@ -256,6 +266,7 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
                 dbits = 0xFFFFu;
                 if ((bw[0] | bw[1] | bw[2] | bw[3]) != 0) {  // rare: some base of the chunk is not ACGTU
                     dbits = (valid4(bw[0]) << 12) | (valid4(bw[1]) << 8) | (valid4(bw[2]) << 4) | valid4(bw[3]);
+                    f &= spread16(dbits);  // undefined bases read as code 0 (jgi/BBDuk.java:3882)
                     atomicOr(badw + (c >> 5), 1u << (c & 31));
                 }
             }
@@ -285,6 +296,44 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
         }
         const uint32_t undef_mask = __ballot_sync(0xFFFFFFFFu, has_undef);
         const bool any_undef = __any_sync(0xFFFFFFFFu, has_undef && scan);
+        // Windows with an undefined base (forbidNs off): the forward k-mer reads it as A, the reverse one as
+        // the complement of T (x = x2 = 0, jgi/BBDuk.java:3882-3888), so key = max(kmer, rkmer) can only be in
+        // the table if the window passes the part test with its undefined bases read as A (what the scan over
+        // F computes anyway) or with all of them read as T. Only the part_w-mers that CONTAIN an undefined base
+        // differ between the two readings: they are looked up here, pooled over the tile (one lane per
+        // w-mer end, one pass per chunk with an undefined base), and the rare hits are left in the lane's
+        // column of cand[] -- bit b of cand[j][lane] = "the T reading of the w-mer ending at position 16j+b
+        // passes" -- which step j picks up before it stores its own candidate bits there.
+        const bool tvar = PARTS && !PRE && any_undef && !p.forbidNs;
+        if (tvar) {
+            for (int i = lane; i < max_steps * 16; i += 32) reinterpret_cast<uint32_t *>(cand)[i] = 0u;
+            __syncwarp();
+            const int w = t.part_w;
+            const uint32_t wbits = (1u << w) - 1u;  // w <= 16
+            for (int bwi = 0; bwi < geo.nbadw; bwi++) {
+                uint32_t m = badw[bwi];
+                while (m) {
+                    const int c = bwi * 32 + __ffs(m) - 1;
+                    m &= m - 1;
+                    const int e = 16 * c + lane;  // this lane's w-mer ends at stream base e
+                    bool hit = false;
+                    if (lane < 16 + w - 1) {
+                        const uint32_t u = ~st.d16(e - 15) & wbits;  // bit t = base e-t is undefined
+                        if (u) {
+                            hit = bb_part_test(filt, st.f16(e - 15) | spread16(u), w);
+                        }
+                    }
+                    uint32_t hb = __ballot_sync(0xFFFFFFFFu, hit);
+                    while (hb) {  // rare: every lane checks whether the base lies in its own read
+                        const int ee = 16 * c + __ffs(hb) - 1;
+                        hb &= hb - 1;
+                        if (live && ee >= s && ee < s + L) cand[((ee - s) >> 4) * 32 + lane] |= (uint16_t)(1u << ((ee - s) & 15));
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        uint64_t thist = 0;  // tvar: the T-reading bits, laid out like mhist
         int qn = 0;  // warp-uniform queue fill
         // Every step's candidate bits are kept in cand[step][lane]. A read releases them to the warp queue
         // as it goes, but a read without undefined bases releases at most CAND_CAP per step: a window run
@@ -318,7 +367,8 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
         uint32_t f_m2 = 0, f_m1 = 0, f_0 = 0, r_0 = 0, r_1 = 0, r_2 = 0;
         int last_und = -(1 << 20);  // position of the most recent undefined base before the current step
         uint64_t mhist = 0;     // PARTS: part-filter results, bit 32+b = position 16j+b, lower bits = older positions
-        const uint32_t part_mult = bb_part_mult(t.part_w);
+        const int part_nd = t.part_w - BB_PART_WD;
+        uint32_t raw_prev = 0;  // PARTS: the previous step's 9-mer bits (bit b = position 16(j-1)+b)
         if (!PARTS && scan && RCOMP) {
             r_0 = pair_reverse_complement(st.f16(s - (k - 1)));
             r_1 = pair_reverse_complement(st.f16(s + 16 - (k - 1)));
@@ -333,20 +383,24 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
                 if (stepping) {
                     f_0 = st.f16(s + 16 * j);
                     if (PARTS) {
-                        uint32_t mb = 0;  // bit 15-b = position 16j+b passes
+                        uint32_t mb = 0;  // bit 15-b = the 9-mer ending at position 16j+b is in the bitmap
     #pragma unroll
                         for (int b = 0; b < 16; b++) {
-                            // the 32-bit window ending at 16j+b; the multiplier drops everything above part_w bases
+                            // the 32-bit window ending at 16j+b: bits 5..17 pick the word, bits 0..4 the bit (bbduk_dev.cuh)
                             const uint32_t v = __funnelshift_r(f_0, f_m1, 2 * (15 - b));
-                            const BBPartProbe pr = bb_part_probe(v, part_mult, geo.nfw);
-                            const uint32_t fw = filt[pr.word];
-                            const uint32_t hit = __funnelshift_r(fw, 0u, pr.b1) & __funnelshift_r(fw, 0u, pr.b2) & 1u;
-                            mb = mb * 2u + hit;
+                            const uint32_t fw = *reinterpret_cast<const uint32_t *>(filt_bytes + ((v >> 3) & (4u * (BB_PART_WORDS - 1u))));
+                            mb = __funnelshift_l(__funnelshift_r(fw, fw, v), mb, 1);
                         }
-                        mhist |= (uint64_t)(__brev(mb) >> 16) << 32;
+                        // a part of part_w bases passes iff all of its part_w-8 overlapping 9-mers do: AND of the
+                        // bit with its part_nd (<= 7) predecessors, on (this step : previous step) in one register
+                        const uint32_t raw = (__brev(mb) & 0xFFFF0000u) | raw_prev;  // bit 16+b = position 16j+b
+                        uint32_t mw = raw;
+                        for (int d = 1; d <= part_nd; d++) mw &= raw << d;
+                        raw_prev = raw >> 16;
+                        mhist |= (uint64_t)(mw >> 16) << 32;
                         cbits = (uint32_t)(mhist >> psh0);
-                    if (t.n_parts > 1) cbits |= (uint32_t)(mhist >> psh1);
-                    if (t.n_parts > 2) cbits |= (uint32_t)(mhist >> psh2) | (uint32_t)(mhist >> psh3);
+                        if (t.n_parts > 1) cbits |= (uint32_t)(mhist >> psh1);
+                        if (t.n_parts > 2) cbits |= (uint32_t)(mhist >> psh2) | (uint32_t)(mhist >> psh3);
                         cbits &= 0xFFFFu;
                         mhist >>= 16;
                         f_m1 = f_0;
@@ -384,10 +438,22 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
                         const int rem = L - 16 * j;
                         if (rem < 16) dd |= (0xFFFFu >> rem);
                         const uint32_t und = (~dd) & 0xFFFFu;  // bit 15-b = position 16j+b undefined
-                        uint32_t forced = smear_right(und, min(k, 16));  // undefined bases inside this step
+                        // undefined bases inside this step cover the k positions from themselves on (towards lower
+                        // bits); for k >= 16 that is everything at or below the highest undefined bit
+                        uint32_t forced = (k >= 16) ? (und ? ((2u << (31 - __clz(und))) - 1u) : 0u) : smear_right(und, k);
                         const int carry = k - (16 * j - last_und);     // positions of this step still covered by an older one
                         if (carry > 0) forced |= (carry >= 16) ? 0xFFFFu : ((0xFFFFu << (16 - carry)) & 0xFFFFu);
-                        cbits |= __brev(forced) >> 16;  // -> bit b
+                        uint32_t fb = __brev(forced) >> 16;  // -> bit b
+                        if (tvar) {
+                            // of the windows with an undefined base only those whose A or T reading passes the part test
+                            thist |= (uint64_t)cand[j * 32 + lane] << 32;
+                            uint32_t ext = (uint32_t)(thist >> psh0);
+                            if (t.n_parts > 1) ext |= (uint32_t)(thist >> psh1);
+                            if (t.n_parts > 2) ext |= (uint32_t)(thist >> psh2) | (uint32_t)(thist >> psh3);
+                            thist >>= 16;
+                            fb &= ext;
+                        }
+                        cbits |= fb;
                         if (und) last_und = 16 * j + 15 - (__ffs(und) - 1);
                     }
                     // keep positions k-1 <= i < L
@@ -399,7 +465,7 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
                 }
                 if (scan && j < nsteps) cand[j * 32 + lane] = (uint16_t)cbits;
                 uint32_t pb = (done || deferred) ? 0u : cbits;
-                if (!has_undef && rel + __popc(pb) > geo.cand_cap) {
+                if (DEFER && !has_undef && rel + __popc(pb) > geo.cand_cap) {
                     // keep the lowest (CAND_CAP - rel) bits, hold everything else back
                     uint32_t rest = pb;
     #pragma unroll 1
@@ -409,7 +475,7 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
                     dj = j;
                     dbits = rest;
                 }
-                rel += __popc(pb);
+                if (DEFER) rel += __popc(pb);
 
                 // pool this step's released candidates: exclusive prefix sum of the per-lane counts
                 const int cnt = __popc(pb);

@@ -272,8 +272,10 @@ __global__ void part_filter_build_kernel(const Seed *__restrict__ seeds, int64_t
             const uint64_t x = o ? r : f;
             for (int j = 0; j < n_parts; j++) {
                 const uint32_t v = (uint32_t)(x >> (2 * lags[j])) & vm;
-                const BBPartProbe pr = bb_part_probe(v, bb_part_mult(w), n_words);
-                atomicOr(filter + pr.word, (1u << (pr.b1 & 31)) | (1u << (pr.b2 & 31)));
+                for (int d = 0; d <= w - BB_PART_WD; d++) {  // every 9-mer of the part (bbduk_dev.cuh)
+                    const uint32_t y = v >> (2 * d);
+                    atomicOr(filter + bb_part_word(y), bb_part_bit(y));
+                }
             }
         }
     }
@@ -464,9 +466,11 @@ int DeviceTable::build(const BBParams &p, const std::vector<uint8_t> &ref, const
             for (int j = 0; j < PL; j++) offs[j] = j * strideL;
             for (int j = 0; j < PR; j++) offs[PL + j] = (j == PR - 1) ? k - w : a + mml + j * strideR;
         }
-        const double entries = (double)n_full * (p.rcomp ? 2 : 1) * P;
-        const uint32_t pw = 16384;  // 64 KB
-        if (w >= 9 && entries <= (double)pw * 6.0) {
+        // 9-mers the bitmap receives (an upper bound: adapter-like references repeat themselves); past half
+        // of the 4^9 values the AND over a part's 9-mers stops rejecting anything
+        const double entries = (double)n_full * (p.rcomp ? 2 : 1) * P * (w - BB_PART_WD + 1);
+        const uint32_t pw = BB_PART_WORDS;  // 32 KB
+        if (w >= BB_PART_WD && entries <= (double)pw * 16.0) {
             n_parts = P;
             part_w = w;
             for (int j = 0; j < P; j++) part_lag[j] = k - offs[j] - w;

@@ -82,6 +82,42 @@ def test_modes_paired_and_ragged(adapters, adapter_seqs, kw):
     check_scaffold_counts(o, g)
 
 
+@pytest.mark.parametrize("kw", [dict(k=23, mink=11, hdist=1, ktrim_right=1), dict(k=23, mink=11, hdist=1, ktrim_left=1),
+                                dict(k=23, hdist=1), dict(k=25, hdist=2, ktrim_right=1), dict(k=21, hdist=1, rcomp=0, ktrim_right=1),
+                                dict(k=23, hdist=1, forbid_ns=1, ktrim_right=1)],
+                         ids=lambda kw: ",".join(f"{a}={b}" for a, b in kw.items()))
+def test_undefined_bases_inside_adapters(adapter_seqs, adapters, kw):
+    """Without forbidNs the forward k-mer reads an undefined base as A and the reverse k-mer as the complement of T
+    (jgi/BBDuk.java:3882-3888), so a window with an N can hit through either reading. Every position of an adapter
+    (and of its reverse complement) is replaced by N / another IUPAC code in turn, alone, as a pair 1-12 bases apart
+    and together with one substitution, in front of and behind random flanks."""
+    o, g = engines(adapters, **kw)
+    rng = np.random.default_rng(11)
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    reads = []
+    for seq in (adapter_seqs[0], adapter_seqs[2], adapter_seqs[5]):
+        fwd = seq.encode()[:40]
+        for ad in (fwd, fwd.translate(comp)[::-1]):
+            for i in range(len(ad)):
+                for gap in (0, 1, 5, 12):
+                    a = bytearray(ad)
+                    a[i] = ord("N")
+                    if gap and i + gap < len(a):
+                        a[i + gap] = rng.choice(np.frombuffer(b"NRYn", np.uint8))
+                    if gap == 5 and i >= 3:
+                        a[i - 3] = ord("ACGT"[(b"ACGT".index(bytes([ad[i - 3]])) + 1) % 4])
+                    left = bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), int(rng.integers(0, 60))))
+                    right = bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), int(rng.integers(0, 30))))
+                    reads.append(left + bytes(a) + right)
+    off = np.zeros(len(reads) + 1, np.int64)
+    off[1:] = np.cumsum([len(r) for r in reads])
+    b = np.frombuffer(b"".join(reads), np.uint8).copy()
+    eo, _ = assert_same(o, g, b, off, False)
+    assert_same(o, g, b, off, True)
+    if not kw.get("forbid_ns"):
+        assert int((eo.fields()["id0"] > 0).sum()) > len(reads) // 4  # the cases do hit
+
+
 KMASK = [
     dict(k=23, ktrim_n=1),
     dict(k=23, mink=11, hdist=1, ktrim_n=1),
