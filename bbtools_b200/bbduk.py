@@ -496,8 +496,9 @@ class BBDukIndexGPU:
                                                        ptr(d_lo), ptr(d_hi), ptr(d_flags), ptr(d_stats), ptr(stream)), "entropy_device")
 
     # -- the whole device part of the per-pair loop in one call -------------------------------------------
-    def process_chain(self, bases, quals, offsets, paired, tbo=None, qtrim=None, entropy=None):
+    def process_chain(self, bases, quals, offsets, paired, tbo=None, qtrim=None, entropy=None, out=None):
         """HOST buffers: k-mer block, then the given steps (their cfg structs, or None to skip) with ONE upload of the batch.
+        out: caller-owned Outputs (e.g. pinned arrays; lo, hi and flags are required, arrays set to None are not downloaded).
         -> (Outputs, BBDukStats, tbo stats2, qtrim stats8, entropy stats2)"""
         from ._abi import BBDukChainCfg
         c = BBDukChainCfg()
@@ -510,7 +511,8 @@ class BBDukIndexGPU:
         offsets = np.ascontiguousarray(offsets, np.int64)
         q = None if quals is None else np.ascontiguousarray(quals, np.uint8)
         n = len(offsets) - 1
-        out = Outputs(n)
+        if out is None:
+            out = Outputs(n)
         o = out.struct()
         st = BBDukStats()
         t2, q8, e2 = np.zeros(2, np.int64), np.zeros(8, np.int64), np.zeros(2, np.int64)

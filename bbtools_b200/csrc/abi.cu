@@ -87,6 +87,12 @@ struct bbduk_handle {
         int64_t cap_bases = 0, cap_quals = 0, cap_flags = 0, cap_off = 0, cap_lo = 0, cap_hi = 0, cap_insert = 0, cap_id0 = 0,
                 cap_count = 0;
     } tbo;
+    // bbduk_b200_process_chain: second input slot + copy stream, so that the upload of chunk i+1 overlaps the kernels of chunk i
+    uint8_t *chain_bases2 = nullptr, *chain_quals2 = nullptr;
+    uint32_t *chain_off2 = nullptr;
+    int64_t chain_cap_bases2 = 0, chain_cap_quals2 = 0, chain_cap_off2 = 0;
+    cudaStream_t chain_copy = nullptr;
+    cudaEvent_t chain_in[2] = {nullptr, nullptr}, chain_free[2] = {nullptr, nullptr};
     std::mutex tbo_mu;
     HostPool *pool = nullptr;  // host packing workers, created on first use
     std::mutex pool_mu;
@@ -1084,42 +1090,80 @@ int bbduk_b200_process_chain(bbduk_handle *h, const bbduk_chain_cfg *cfg, const 
     CKH(cudaMalloc(&d_st, 20 * sizeof(int64_t)));
     CKH(cudaMemset(d_st, 0, 20 * sizeof(int64_t)));
     int rc = 0;
-    int64_t r0 = 0;
     const int per = paired ? 2 : 1;
-    std::vector<uint32_t> off32;
-    while (r0 < n_reads && !rc) {
+    // chunks: <= 2 * CHUNK_READS reads and <= CHUNK_BYTES bases each (offsets stay 32-bit on the device)
+    std::vector<int64_t> cut{0};
+    while (cut.back() < n_reads) {
+        const int64_t r0 = cut.back();
         int64_t r1 = std::min(n_reads, r0 + (CHUNK_READS << 1));
         while (r1 > r0 + per && offsets[r1] - offsets[r0] > CHUNK_BYTES) r1 = r0 + std::max<int64_t>(per, ((r1 - r0) / 2 / per) * per);
-        const int64_t nr = r1 - r0, nb = offsets[r1] - offsets[r0];
+        const int64_t nb = offsets[r1] - offsets[r0];
         if (nb < 0 || nb >= (1ll << 32) - 64) {
-            rc = set_err(h, "a read (pair) exceeds 4 GiB (or offsets decrease)");
-            break;
+            cudaFree(d_st);
+            return set_err(h, "a read (pair) exceeds 4 GiB (or offsets decrease)");
         }
+        cut.push_back(r1);
+    }
+    const int n_chunks = (int)cut.size() - 1;
+    auto &tb = h->tbo;
+#define CKC(call)                                                                       \
+    if (!rc && (call) != cudaSuccess) rc = set_err(h, std::string(#call " failed: ") + cudaGetErrorString(cudaGetLastError()))
+    if (!h->chain_copy) {
+        CKC(cudaStreamCreateWithFlags(&h->chain_copy, cudaStreamNonBlocking));  // no implicit ordering with the legacy stream
+        for (int i = 0; i < 2; i++) {
+            CKC(cudaEventCreateWithFlags(&h->chain_in[i], cudaEventDisableTiming));
+            CKC(cudaEventCreateWithFlags(&h->chain_free[i], cudaEventDisableTiming));
+        }
+    }
+    auto need = [&](void **p, int64_t *cap, int64_t bytes) -> int {
+        if (bytes <= *cap) return 0;
+        cudaFree(*p);  // synchronises the device: nothing in flight still uses the old buffer
+        *p = nullptr;
+        *cap = bytes + bytes / 8 + 4096;
+        return cudaMalloc(p, (size_t)*cap) == cudaSuccess ? 0 : 1;
+    };
+    // Two input slots (bases, qualities, offsets); results live in one set of buffers, which the compute stream
+    // downloads before the next chunk's kernels run. The copy stream uploads chunk i+1 while chunk i computes.
+    uint8_t **s_bases[2] = {&tb.d_bases, &h->chain_bases2}, **s_quals[2] = {&tb.d_quals, &h->chain_quals2};
+    uint32_t **s_off[2] = {&tb.d_off, &h->chain_off2};
+    int64_t *c_bases[2] = {&tb.cap_bases, &h->chain_cap_bases2}, *c_quals[2] = {&tb.cap_quals, &h->chain_cap_quals2},
+            *c_off[2] = {&tb.cap_off, &h->chain_cap_off2};
+    std::vector<uint32_t> off32[2];
+    int max_len_of[2] = {0, 0};
+    auto stage = [&](int ci) {  // upload chunk ci into slot ci & 1 on the copy stream
+        const int sl = ci & 1;
+        const int64_t r0 = cut[ci], nr = cut[ci + 1] - r0, nb = offsets[cut[ci + 1]] - offsets[r0];
+        if (need((void **)s_bases[sl], c_bases[sl], nb + 64) || (need_q && need((void **)s_quals[sl], c_quals[sl], nb + 64)) ||
+            need((void **)s_off[sl], c_off[sl], 4 * (nr + 1))) {
+            rc = set_err(h, "chain: device allocation failed");
+            return;
+        }
+        if (ci >= 2) CKC(cudaStreamWaitEvent(h->chain_copy, h->chain_free[sl], 0));  // chunk ci-2's kernels are done with the slot
+        CKC(cudaMemcpyAsync(*s_bases[sl], bases + offsets[r0], (size_t)nb, cudaMemcpyHostToDevice, h->chain_copy));
+        if (need_q) CKC(cudaMemcpyAsync(*s_quals[sl], quals + offsets[r0], (size_t)nb, cudaMemcpyHostToDevice, h->chain_copy));
         int max_len = 0;
-        off32.resize(nr + 1);
-        for (int64_t i = 0; i <= nr; i++) off32[i] = (uint32_t)(offsets[r0 + i] - offsets[r0]);
-        for (int64_t i = 0; i < nr; i++) max_len = std::max(max_len, (int)(off32[i + 1] - off32[i]));
-        auto need = [&](void **p, int64_t *cap, int64_t bytes) -> int {
-            if (bytes <= *cap) return 0;
-            cudaFree(*p);
-            *p = nullptr;
-            *cap = bytes + bytes / 8 + 4096;
-            return cudaMalloc(p, (size_t)*cap) == cudaSuccess ? 0 : 1;
-        };
-        auto &tb = h->tbo;
-        if (need((void **)&tb.d_bases, &tb.cap_bases, nb + 64) || (need_q && need((void **)&tb.d_quals, &tb.cap_quals, nb + 64)) ||
-            need((void **)&tb.d_off, &tb.cap_off, 4 * (nr + 1)) || need((void **)&tb.d_lo, &tb.cap_lo, 4 * nr) ||
-            need((void **)&tb.d_hi, &tb.cap_hi, 4 * nr) || need((void **)&tb.d_flags, &tb.cap_flags, nr) ||
-            need((void **)&tb.d_insert, &tb.cap_insert, 2 * nr + 8) || (out->id0 && need((void **)&tb.d_id0, &tb.cap_id0, 4 * nr)) ||
-            (out->count && need((void **)&tb.d_count, &tb.cap_count, 4 * nr))) {
+        auto &o32 = off32[sl];  // pageable: the copy below returns once it is staged, so the vector can be reused two chunks on
+        o32.resize(nr + 1);
+        for (int64_t i = 0; i <= nr; i++) o32[i] = (uint32_t)(offsets[r0 + i] - offsets[r0]);
+        for (int64_t i = 0; i < nr; i++) max_len = std::max(max_len, (int)(o32[i + 1] - o32[i]));
+        max_len_of[sl] = max_len;
+        CKC(cudaMemcpyAsync(*s_off[sl], o32.data(), 4 * (size_t)(nr + 1), cudaMemcpyHostToDevice, h->chain_copy));
+        CKC(cudaEventRecord(h->chain_in[sl], h->chain_copy));
+    };
+    if (!rc && n_chunks > 0) stage(0);
+    for (int ci = 0; ci < n_chunks && !rc; ci++) {
+        const int sl = ci & 1;
+        const int64_t r0 = cut[ci], nr = cut[ci + 1] - r0;
+        const int max_len = max_len_of[sl];
+        if (need((void **)&tb.d_lo, &tb.cap_lo, 4 * nr) || need((void **)&tb.d_hi, &tb.cap_hi, 4 * nr) ||
+            need((void **)&tb.d_flags, &tb.cap_flags, nr) || need((void **)&tb.d_insert, &tb.cap_insert, 2 * nr + 8) ||
+            (out->id0 && need((void **)&tb.d_id0, &tb.cap_id0, 4 * nr)) || (out->count && need((void **)&tb.d_count, &tb.cap_count, 4 * nr))) {
             rc = set_err(h, "chain: device allocation failed");
             break;
         }
-#define CKC(call)                                                                       \
-    if (!rc && (call) != cudaSuccess) rc = set_err(h, std::string(#call " failed: ") + cudaGetErrorString(cudaGetLastError()))
-        CKC(cudaMemcpyAsync(tb.d_bases, bases + offsets[r0], (size_t)nb, cudaMemcpyHostToDevice, st));
-        if (need_q) CKC(cudaMemcpyAsync(tb.d_quals, quals + offsets[r0], (size_t)nb, cudaMemcpyHostToDevice, st));
-        CKC(cudaMemcpyAsync(tb.d_off, off32.data(), 4 * (size_t)(nr + 1), cudaMemcpyHostToDevice, st));
+        uint8_t *d_b = *s_bases[sl], *d_q = need_q ? *s_quals[sl] : nullptr;
+        uint32_t *d_o = *s_off[sl];
+        CKC(cudaStreamWaitEvent(st, h->chain_in[sl], 0));
         bbduk_out dout;
         memset(&dout, 0, sizeof dout);
         dout.lo = tb.d_lo;
@@ -1128,25 +1172,26 @@ int bbduk_b200_process_chain(bbduk_handle *h, const bbduk_chain_cfg *cfg, const 
         dout.id0 = out->id0 ? tb.d_id0 : nullptr;
         dout.count = out->count ? tb.d_count : nullptr;
         const int hint = h->max_read_len_hint.exchange(max_len);
-        if (!rc) rc = bbduk_b200_process_device(h, tb.d_bases, tb.d_off, nr, paired, &dout, reinterpret_cast<bbduk_stats *>(d_st), st);
+        if (!rc) rc = bbduk_b200_process_device(h, d_b, d_o, nr, paired, &dout, reinterpret_cast<bbduk_stats *>(d_st), st);
         h->max_read_len_hint = hint;
         if (!rc && cfg->do_tbo)
-            rc = bbduk_b200_tbo_device(h, &cfg->tbo, tb.d_bases, quals ? tb.d_quals : nullptr, tb.d_off, nr, max_len, tb.d_lo, tb.d_hi,
-                                       tb.d_flags, tb.d_insert, d_st + 8, st);
+            rc = bbduk_b200_tbo_device(h, &cfg->tbo, d_b, quals ? d_q : nullptr, d_o, nr, max_len, tb.d_lo, tb.d_hi, tb.d_flags,
+                                       tb.d_insert, d_st + 8, st);
         if (!rc && cfg->do_qtrim)
-            rc = bbduk_b200_qtrim_device(h, &cfg->qtrim, tb.d_bases, need_q ? tb.d_quals : nullptr, tb.d_off, nr, paired, tb.d_lo,
-                                         tb.d_hi, tb.d_flags, d_st + 10, st);
+            rc = bbduk_b200_qtrim_device(h, &cfg->qtrim, d_b, d_q, d_o, nr, paired, tb.d_lo, tb.d_hi, tb.d_flags, d_st + 10, st);
         if (!rc && cfg->do_entropy)
-            rc = bbduk_b200_entropy_device(h, &cfg->entropy, tb.d_bases, tb.d_off, nr, paired, tb.d_lo, tb.d_hi, tb.d_flags, d_st + 18, st);
+            rc = bbduk_b200_entropy_device(h, &cfg->entropy, d_b, d_o, nr, paired, tb.d_lo, tb.d_hi, tb.d_flags, d_st + 18, st);
+        CKC(cudaEventRecord(h->chain_free[sl], st));
+        if (ci + 1 < n_chunks && !rc) stage(ci + 1);  // host-side offsets + upload of the next chunk while this one computes
         CKC(cudaMemcpyAsync(out->lo + r0, tb.d_lo, 4 * (size_t)nr, cudaMemcpyDeviceToHost, st));
         CKC(cudaMemcpyAsync(out->hi + r0, tb.d_hi, 4 * (size_t)nr, cudaMemcpyDeviceToHost, st));
         CKC(cudaMemcpyAsync(out->flags + r0, tb.d_flags, (size_t)nr, cudaMemcpyDeviceToHost, st));
         if (out->id0) CKC(cudaMemcpyAsync(out->id0 + r0, tb.d_id0, 4 * (size_t)nr, cudaMemcpyDeviceToHost, st));
         if (out->count) CKC(cudaMemcpyAsync(out->count + r0, tb.d_count, 4 * (size_t)nr, cudaMemcpyDeviceToHost, st));
-        CKC(cudaStreamSynchronize(st));
-#undef CKC
-        r0 = r1;
     }
+    cudaStreamSynchronize(h->chain_copy);
+    if (cudaStreamSynchronize(st) != cudaSuccess && !rc) rc = set_err(h, std::string("chain failed: ") + cudaGetErrorString(cudaGetLastError()));
+#undef CKC
     if (!rc) {
         int64_t v[20];
         if (cudaMemcpy(v, d_st, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) rc = set_err(h, "chain: stats copy failed");
@@ -1199,6 +1244,14 @@ void bbduk_b200_destroy(bbduk_handle *h) {
     cudaFree(h->tbo.d_insert);
     cudaFree(h->tbo.d_id0);
     cudaFree(h->tbo.d_count);
+    cudaFree(h->chain_bases2);
+    cudaFree(h->chain_quals2);
+    cudaFree(h->chain_off2);
+    if (h->chain_copy) cudaStreamDestroy(h->chain_copy);
+    for (int i = 0; i < 2; i++) {
+        if (h->chain_in[i]) cudaEventDestroy(h->chain_in[i]);
+        if (h->chain_free[i]) cudaEventDestroy(h->chain_free[i]);
+    }
     delete h->pool;
     delete h;
 }

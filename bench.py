@@ -561,12 +561,20 @@ def run_ours(args):
         cq[:] = (33 + np.clip(40 - (np.arange(c_reads * L, dtype=np.int32) % L) * rngq.integers(0, 45, c_reads * L, dtype=np.int32) // L,
                               2, 41)).astype(np.uint8)
         tcfg, qcfg2 = eng.tbo_cfg(), eng.qtrim_cfg(qtrim_left=1, qtrim_right=1, trimq=10.0)
-        eng.process_chain(cb, cq, co, True, tbo=tcfg, qtrim=qcfg2)
+        # caller-owned pinned result arrays, as the JNI shim's staging has them: lo, hi, flags = 9 B per read come back
+        cout = Outputs(0)
+        cout.n = c_reads
+        cpin = {"lo": torch.empty(c_reads, dtype=torch.int32, pin_memory=True),
+                "hi": torch.empty(c_reads, dtype=torch.int32, pin_memory=True),
+                "flags": torch.empty(c_reads, dtype=torch.uint8, pin_memory=True)}
+        cout.lo, cout.hi, cout.flags = (cpin[k].numpy() for k in ("lo", "hi", "flags"))
+        cout.id0 = cout.id0b = cout.count = None
+        eng.process_chain(cb, cq, co, True, tbo=tcfg, qtrim=qcfg2, out=cout)
         barrier()
         t0 = time.perf_counter()
         c_steps = 3
         for _ in range(c_steps):
-            _, _, ct2, cq8, _ = eng.process_chain(cb, cq, co, True, tbo=tcfg, qtrim=qcfg2)
+            _, _, ct2, cq8, _ = eng.process_chain(cb, cq, co, True, tbo=tcfg, qtrim=qcfg2, out=cout)
         c_dt = time.perf_counter() - t0
         tc = torch.tensor([c_dt], dtype=torch.float64, device=dev)
         if world > 1:
