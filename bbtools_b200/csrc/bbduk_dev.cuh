@@ -57,6 +57,7 @@ __device__ __forceinline__ uint32_t bb_bucket(uint32_t h, uint32_t bucket_shift)
 __device__ __forceinline__ int bb_table_get(const BBTable &t, uint64_t key) {
     uint64_t b = bb_bucket(bb_fhash64(key), t.bucket_shift);
     const uint64_t bmask = t.slot_mask >> 2;
+#pragma unroll 1  // one bucket is the normal case; unrolled copies only cost instruction-cache space
     for (int probe = 0; probe < BB_MAX_PROBE / 4; probe++) {
         const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(t.keys + 4 * b);
         const ulonglong2 k01 = __ldg(q), k23 = __ldg(q + 1);  // one sector, both halves in flight
@@ -128,6 +129,7 @@ __host__ __device__ __forceinline__ uint32_t bb_part_bit(uint32_t x) { return 1u
 // v: 2-bit codes of (at least) the w bases ending at a position, newest base in the low bits
 __device__ __forceinline__ bool bb_part_test(const uint32_t *filt, uint32_t v, int w) {
     bool ok = true;
+#pragma unroll 1
     for (int d = 0; d <= w - BB_PART_WD; d++) {
         const uint32_t x = v >> (2 * d);
         ok = ok && (filt[bb_part_word(x)] & bb_part_bit(x)) != 0;
@@ -173,6 +175,7 @@ __device__ __forceinline__ bool bb_window_key(const BBParams &p, uint64_t win, u
 // lookup continuing from a bucket whose 32 bytes the caller has already loaded
 __device__ __forceinline__ int bb_table_get_from(const BBTable &t, uint64_t b, ulonglong2 k01, ulonglong2 k23, uint64_t key) {
     const uint64_t bmask = t.slot_mask >> 2;
+#pragma unroll 1  // one bucket is the normal case; unrolled copies only cost instruction-cache space
     for (int probe = 0; probe < BB_MAX_PROBE / 4; probe++) {
         int j = -1;
         if (k01.x == key) j = 0;

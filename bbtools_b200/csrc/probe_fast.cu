@@ -242,6 +242,7 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
             continue;
         }
         // ---- A. stage + convert ---------------------------------------------------------------
+#pragma unroll 1
         for (int i = lane; i < geo.nbadw; i += 32) badw[i] = 0;
         __syncwarp();
         for (int c = lane; c < (PRE ? 0 : nchunks + TAIL); c += 32) {
@@ -287,6 +288,7 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
         bool has_undef = false;  // some chunk overlapping this read holds an undefined base
         if (!PRE && L > 0) {
             const int c0 = s >> 4, c1 = (s + L - 1) >> 4;
+#pragma unroll 1
             for (int w = c0 >> 5; w <= (c1 >> 5); w++) {
                 uint32_t m = badw[w];
                 if (w == (c0 >> 5)) m &= 0xFFFFFFFFu << (c0 & 31);
@@ -306,10 +308,12 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
         // passes" -- which step j picks up before it stores its own candidate bits there.
         const bool tvar = PARTS && !PRE && any_undef && !p.forbidNs;
         if (tvar) {
+#pragma unroll 1
             for (int i = lane; i < max_steps * 16; i += 32) reinterpret_cast<uint32_t *>(cand)[i] = 0u;
             __syncwarp();
             const int w = t.part_w;
             const uint32_t wbits = (1u << w) - 1u;  // w <= 16
+#pragma unroll 1
             for (int bwi = 0; bwi < geo.nbadw; bwi++) {
                 uint32_t m = badw[bwi];
                 while (m) {
@@ -395,6 +399,7 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
                         // bit with its part_nd (<= 7) predecessors, on (this step : previous step) in one register
                         const uint32_t raw = (__brev(mb) & 0xFFFF0000u) | raw_prev;  // bit 16+b = position 16j+b
                         uint32_t mw = raw;
+#pragma unroll 1
                         for (int d = 1; d <= part_nd; d++) mw &= raw << d;
                         raw_prev = raw >> 16;
                         mhist |= (uint64_t)(mw >> 16) << 32;
@@ -616,6 +621,7 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
                 } else {
                     RC = bb_rcomp(W, 32);
                 }
+#pragma unroll 1
                 for (int n = max(p.mink, 1); n <= nmax; n++) {
                     const uint64_t nm = (1ull << (2 * n)) - 1ull;
                     uint64_t kmer, rkmer;
