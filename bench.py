@@ -33,9 +33,9 @@ WORKLOAD = ("bbduk.sh ktrim=r k=23 mink=11 hdist=1 tpe, ref=adapters.fa, synthet
 ALG_BYTES_PER_READ = READ_LEN + 4 + 8  # bases + 4 B offset in + 8 B result out (hi + id0); table on-chip
 FALLBACK_HBM_GBS = 6650.0
 # dram__bytes_read.sum + dram__bytes_write.sum per read of the dominant kernel, from the committed `ncu --set full`
-# captures (profiles/r01m_fast_kernel_raw.txt: 652.51 MB + 37.19 MB for a 4,194,304-read launch;
+# captures (profiles/r01o_fast_kernel_raw.txt: 652.30 MB + 36.97 MB for a 4,194,304-read launch;
 # profiles/r01_e_kcount_kernel.txt: 28.33 GB + 6.91 GB for 217.6 M k-mers = 162 B per k-mer)
-NCU_TRAFFIC_BYTES_PER_READ = {"cfg2": (652506624 + 37186304) / 4194304, "cfg5": 120 * (28328275000 + 6911184000) / 217637790}
+NCU_TRAFFIC_BYTES_PER_READ = {"cfg2": (652302336 + 36971776) / 4194304, "cfg5": 120 * (28328275000 + 6911184000) / 217637790}
 
 
 def load_peak():
