@@ -38,6 +38,26 @@ FALLBACK_HBM_GBS = 6650.0
 NCU_TRAFFIC_BYTES_PER_READ = {"cfg2": (652302336 + 36971776) / 4194304, "cfg5": 120 * (28328275000 + 6911184000) / 217637790}
 
 
+# Libraries write to the process's stdout behind Python's back (NCCL prints its version line there when a communicator
+# is created), and the contract is ONE JSON line on stdout: file descriptor 1 is pointed at stderr for the whole run and
+# the line goes to a private duplicate of the original stdout.
+_JSON_OUT = None
+
+
+def claim_stdout():
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(line + "\n")
+    out.flush()
+
+
 def load_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -147,7 +167,7 @@ def run_reference(args):
     total = sum(times)
     value = 2 * n_pairs * len(times) / total
     sample = f"{2 * n_pairs} reads ({n_pairs} synthetic 2x150 pairs, seed 1) per step, {cores} threads"
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "bbduk_reads_per_s", "value": value, "unit": "reads/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
@@ -298,7 +318,7 @@ def run_kcount(args, wl):
         kern_ms = total_ms_max / args.steps
         achieved = n_reads * wl["alg_bytes"] / (kern_ms * 1e-3) / 1e9
         info = tab.table_info()
-        print(json.dumps({
+        emit(json.dumps({
             "metric": "kmercount_reads_per_s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": kern_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int64", "data": "synthetic",
@@ -657,7 +677,7 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": cpu_rate, "unit": "reads/s", "cores": cores, "kind": "port",
                                     "sample": f"{2 * cpu_pairs} reads of the same synthetic workload (seed 1), oracle C port, "
                                               f"{cores} threads"}
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -679,6 +699,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
