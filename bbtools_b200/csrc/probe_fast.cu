@@ -174,6 +174,20 @@ __device__ __forceinline__ uint32_t smear_right(uint32_t x, int n) {
 
 enum { FM_KTRIM_R = 0, FM_KTRIM_L = 1, FM_KFILTER = 2 };
 
+// Debug build only (nvcc ... -DBB_FAST_COUNT, see scratch/dbgcount.py): where the candidates of the fast kernel come from.
+// 0 tiles, 1 steps, 2 candidates queued, 3 evaluation rounds, 4 windows forced by undefined bases, 5 of them left by the
+// T-reading pre-pass, 6 iterations of the serial enqueue loop, 7 tiles with an undefined base. Compiles to nothing otherwise.
+#ifdef BB_FAST_COUNT
+__device__ unsigned long long bb_fast_dbg[16];
+#define DBG_ADD(i, v)                                                       \
+    do {                                                                    \
+        const unsigned long long v_ = (unsigned long long)(v);              \
+        if (v_) atomicAdd(&bb_fast_dbg[i], v_); /* per lane: any context */ \
+    } while (0)
+#else
+#define DBG_ADD(i, v)
+#endif
+
 // PARTS selects the scan: false = canonical k-mer against the bloom image of all keys;
 // true = forward part_w-mer against the pigeonhole part filter (see bbduk_dev.cuh), one lookup per
 // position, the hdist+1 parts of a window being the same lookup at different lags.
@@ -320,6 +334,8 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
         // column of cand[] -- bit b of cand[j][lane] = "the T reading of the w-mer ending at position 16j+b
         // passes" -- which step j picks up before it stores its own candidate bits there.
         const bool tvar = PARTS && !PRE && any_undef && !p.forbidNs;
+        DBG_ADD(0, lane == 0);
+        DBG_ADD(7, lane == 0 && any_undef);
         if (tvar) {
 #pragma unroll 1
             for (int i = lane; i < max_steps * 16; i += 32) reinterpret_cast<uint32_t *>(cand)[i] = 0u;
@@ -366,6 +382,7 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
 
         auto drain = [&](int n_take) {
             // the last n_take (<= 32) queue entries, one per lane
+            DBG_ADD(3, lane == 0);
             const uint32_t ent = (lane < n_take) ? queue[qn - n_take + lane] : 0u;
             const int owner = (int)(ent >> 11), pos = (int)(ent & 0x7FFu);
             const int s_owner = __shfl_sync(0xFFFFFFFFu, s, owner);
@@ -462,6 +479,7 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
                         const int carry = k - (16 * j - last_und);     // positions of this step still covered by an older one
                         if (carry > 0) forced |= (carry >= 16) ? 0xFFFFu : ((0xFFFFu << (16 - carry)) & 0xFFFFu);
                         uint32_t fb = __brev(forced) >> 16;  // -> bit b
+                        DBG_ADD(4, __popc(fb));
                         if (tvar) {
                             // of the windows with an undefined base only those whose A or T reading passes the part test
                             thist |= (uint64_t)cand[j * 32 + lane] << 32;
@@ -471,6 +489,7 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
                             thist >>= 16;
                             fb &= ext;
                         }
+                        DBG_ADD(5, __popc(fb));
                         cbits |= fb;
                         if (und) last_und = 16 * j + 15 - (__ffs(und) - 1);
                     }
@@ -497,6 +516,8 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
 
                 // pool this step's released candidates: exclusive prefix sum of the per-lane counts
                 const int cnt = __popc(pb);
+                DBG_ADD(1, lane == 0);
+                DBG_ADD(2, cnt);
                 int incl = cnt;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -508,6 +529,7 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
                     int w = qn + incl - cnt;
                     const uint32_t tag = ((uint32_t)lane << 11) + 16u * (uint32_t)j;
                     while (pb) {
+                        DBG_ADD(6, (__activemask() & ((1u << lane) - 1u)) == 0);
                         const int b = __ffs(pb) - 1;
                         pb &= pb - 1;
                         queue[w++] = (uint16_t)(tag + b);
@@ -810,6 +832,17 @@ FastGeom make_geom(const BBParams &p, const BBTable &t, int max_read_len, bool p
 }
 
 }  // namespace
+
+#ifdef BB_FAST_COUNT
+extern "C" __attribute__((visibility("default"))) int bbduk_b200_debug_fast_counters(unsigned long long *out16, int reset) {
+    if (cudaMemcpyFromSymbol(out16, bb_fast_dbg, sizeof(unsigned long long) * 16) != cudaSuccess) return 1;
+    if (reset) {
+        unsigned long long z[16] = {0};
+        if (cudaMemcpyToSymbol(bb_fast_dbg, z, sizeof z) != cudaSuccess) return 1;
+    }
+    return 0;
+}
+#endif
 
 // the packed stage A exists for the part-filter kernels and the canonical rcomp/k>=16 kernels
 bool packed_ok(const BBParams &p, const BBTable &t) { return parts_ok(p, t) || (p.rcomp && p.k >= 16); }

@@ -1,4 +1,5 @@
-"""debug build only: candidate economy of the fast kernel (scratch/lib_dbg.so built with -DBB_FAST_COUNT)"""
+"""debug build only: candidate economy of the fast kernel. Build probe_fast.cu with -DBB_FAST_COUNT, link it with the other
+objects of bbtools_b200/csrc/build into a library and put that in place of bbtools_b200/libbbduk_b200.so on the GPU box."""
 import ctypes as C
 import os
 import sys
@@ -22,8 +23,7 @@ outs = {"id0": torch.empty(n_reads, dtype=torch.int32, device=dev), "hi": torch.
         "flags": torch.empty(n_reads, dtype=torch.uint8, device=dev)}
 d_stats = torch.zeros(8, dtype=torch.int64, device=dev)
 stream = torch.cuda.Stream(device=dev)
-names = ["tiles", "steps", "cand_1by1", "dense_entries", "dense_bits", "rounds_1by1", "rounds_dense", "forced_before", "forced_after",
-         "enqueue_iters", "x", "tiles_undef"]
+names = ["tiles", "steps", "candidates", "rounds", "forced_before", "forced_after", "enqueue_iters", "tiles_undef"]
 for name, sub, nn in (("standard", 50, 5), ("noN", 50, 0)):
     d_bases = torch.empty(n_reads * L, dtype=torch.uint8, device=dev)
     d_off = torch.empty(n_reads + 1, dtype=torch.int32, device=dev)
