@@ -174,11 +174,15 @@ __device__ __forceinline__ uint32_t smear_right(uint32_t x, int n) {
 
 enum { FM_KTRIM_R = 0, FM_KTRIM_L = 1, FM_KFILTER = 2 };
 
-// Debug build only (nvcc ... -DBB_FAST_COUNT, see scratch/dbgcount.py): where the candidates of the fast kernel come from.
+// Debug builds only (nvcc ... -DBB_FAST_COUNT or -DBB_FAST_CLOCK, see scratch/dbgcount.py): where the candidates of the fast kernel come from.
 // 0 tiles, 1 steps, 2 candidates queued, 3 evaluation rounds, 4 windows forced by undefined bases, 5 of them left by the
-// T-reading pre-pass, 6 iterations of the serial enqueue loop, 7 tiles with an undefined base. Compiles to nothing otherwise.
-#ifdef BB_FAST_COUNT
+// T-reading pre-pass, 6 iterations of the serial enqueue loop, 7 tiles with an undefined base; warp cycles (clock64, lane 0) per
+// tile phase: 8 offsets + stage A, 9 undefined-base pre-pass, 10 scan loop incl. 11 its evaluation rounds, 12 tails, 13 stage D.
+// Compiles to nothing otherwise.
+#if defined(BB_FAST_COUNT) || defined(BB_FAST_CLOCK)
 __device__ unsigned long long bb_fast_dbg[16];
+#endif
+#ifdef BB_FAST_COUNT  // per-lane atomics on a handful of addresses: the counts are exact, the run is an order of magnitude slower
 #define DBG_ADD(i, v)                                                       \
     do {                                                                    \
         const unsigned long long v_ = (unsigned long long)(v);              \
@@ -186,6 +190,17 @@ __device__ unsigned long long bb_fast_dbg[16];
     } while (0)
 #else
 #define DBG_ADD(i, v)
+#endif
+#ifdef BB_FAST_CLOCK  // a separate build: seven atomics per warp and tile, so that the cycles mean something
+#define DBG_CLK(name) const long long name = clock64()
+#define DBG_PHASE(i, t0, t1)                                                                   \
+    do {                                                                                       \
+        if (lane == 0) atomicAdd(&bb_fast_dbg[i], (unsigned long long)((t1) - (t0)));          \
+        if (lane == 0 && (i) == 8) atomicAdd(&bb_fast_dbg[0], 1ull);                           \
+    } while (0)
+#else
+#define DBG_CLK(name)
+#define DBG_PHASE(i, t0, t1)
 #endif
 
 // PARTS selects the scan: false = canonical k-mer against the bloom image of all keys;
@@ -237,6 +252,7 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
     long long s_rk = 0, s_bk = 0, s_rf = 0, s_bf = 0, s_ro = 0, s_bo = 0, s_ri = 0, s_bi = 0;
 
     for (int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; tile < n_tiles; tile += warps_total) {
+        DBG_CLK(t_a0);
         const int64_t r = tile * 32 + lane;
         const bool live = r < n_reads;
         const uint32_t o0 = live ? offsets[r] : 0, o1 = live ? offsets[r + 1] : 0;
@@ -333,6 +349,8 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
         // w-mer end, one pass per chunk with an undefined base), and the rare hits are left in the lane's
         // column of cand[] -- bit b of cand[j][lane] = "the T reading of the w-mer ending at position 16j+b
         // passes" -- which step j picks up before it stores its own candidate bits there.
+        DBG_CLK(t_a1);
+        DBG_PHASE(8, t_a0, t_a1);
         const bool tvar = PARTS && !PRE && any_undef && !p.forbidNs;
         DBG_ADD(0, lane == 0);
         DBG_ADD(7, lane == 0 && any_undef);
@@ -366,6 +384,8 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
             }
             __syncwarp();
         }
+        DBG_CLK(t_b0);
+        DBG_PHASE(9, t_a1, t_b0);
         uint64_t thist = 0;  // tvar: the T-reading bits, laid out like mhist
         int qn = 0;  // warp-uniform queue fill
         // Every step's candidate bits are kept in cand[step][lane]. A read releases them to the warp queue
@@ -564,11 +584,16 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
             __syncwarp();
             if (qn >= 32 || (j >= max_steps - 1 && qn > 0)) {
                 // evaluate everything released so far; afterwards nothing of any lane is unresolved
+                DBG_CLK(t_r0);
                 while (qn > 0) drain(min(32, qn));
+                DBG_CLK(t_r1);
+                DBG_PHASE(11, t_r0, t_r1);
                 rel = 0;
             }
         }
 
+        DBG_CLK(t_c);
+        DBG_PHASE(10, t_b0, t_c);
         if (PRE) {
             first64[lane] = live ? pre_first[r] : ~0ull;
             lastpos[lane] = (live && pre_last) ? pre_last[r] : -1;
@@ -709,6 +734,8 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
                 ktrimmed = count > 0;
             }
         }
+        DBG_CLK(t_d);
+        DBG_PHASE(12, t_c, t_d);
         if (live && id0 > 0 && scaf_reads) {
             atomicAdd(scaf_reads + id0, 1ull);
             atomicAdd(scaf_bases + id0, (unsigned long long)L);
@@ -781,6 +808,8 @@ bbduk_fast_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
                 out.flags[r] = (uint8_t)((discarded ? BBDUK_F_DISCARDED : 0) | (remove ? BBDUK_F_REMOVED : 0) |
                                          (ktrimmed ? BBDUK_F_KTRIMMED : 0) | (tpe ? BBDUK_F_TPE : 0));
         }
+        DBG_CLK(t_e);
+        DBG_PHASE(13, t_d, t_e);
     }
     if (stats) {
         // per-warp sums with one REDUX per counter (a launch holds < 2^32 bases, so 32 bits suffice per warp)
@@ -833,7 +862,7 @@ FastGeom make_geom(const BBParams &p, const BBTable &t, int max_read_len, bool p
 
 }  // namespace
 
-#ifdef BB_FAST_COUNT
+#if defined(BB_FAST_COUNT) || defined(BB_FAST_CLOCK)
 extern "C" __attribute__((visibility("default"))) int bbduk_b200_debug_fast_counters(unsigned long long *out16, int reset) {
     if (cudaMemcpyFromSymbol(out16, bb_fast_dbg, sizeof(unsigned long long) * 16) != cudaSuccess) return 1;
     if (reset) {

@@ -475,7 +475,7 @@ int DeviceTable::build(const BBParams &p, const std::vector<uint8_t> &ref, const
             part_w = w;
             for (int j = 0; j < P; j++) part_lag[j] = k - offs[j] - w;
             part_words = pw;
-            short_words = p.useShortKmers ? 8192 : 0;  // 32 KB
+            short_words = p.useShortKmers ? 16384 : 0;  // 64 KB: at 32 KB every third tail iteration of a warp went to the table for a false positive
         }
     }
     if (alloc(slots, total_filter_words(), err, errlen)) {

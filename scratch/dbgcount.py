@@ -23,7 +23,8 @@ outs = {"id0": torch.empty(n_reads, dtype=torch.int32, device=dev), "hi": torch.
         "flags": torch.empty(n_reads, dtype=torch.uint8, device=dev)}
 d_stats = torch.zeros(8, dtype=torch.int64, device=dev)
 stream = torch.cuda.Stream(device=dev)
-names = ["tiles", "steps", "candidates", "rounds", "forced_before", "forced_after", "enqueue_iters", "tiles_undef"]
+names = ["tiles", "steps", "candidates", "rounds", "forced_before", "forced_after", "enqueue_iters", "tiles_undef",
+         "cyc_stageA", "cyc_prepass", "cyc_scanloop", "cyc_rounds_in_loop", "cyc_tails", "cyc_stageD"]
 for name, sub, nn in (("standard", 50, 5), ("noN", 50, 0)):
     d_bases = torch.empty(n_reads * L, dtype=torch.uint8, device=dev)
     d_off = torch.empty(n_reads + 1, dtype=torch.int32, device=dev)
