@@ -182,3 +182,51 @@ def test_threads_do_not_change_results(adapters):
     for name, x in a.fields().items():
         assert np.array_equal(x, c.fields()[name]), name
     assert sa.as_dict() == sc.as_dict()
+
+
+@pytest.mark.parametrize("case", [dict(k=11, hdist=1, mm=False), dict(k=11, hdist=1, mm=True), dict(k=11, mink=5, hdist=1, mm=True),
+                                  dict(k=11, hdist=1, mm=True, fn=True), dict(k=11, hdist=0, mm=False), dict(k=11, hdist=1, mm=False, rcomp=False)])
+def test_undefined_bases_inside_reference_fragments(case):
+    """The readings the GPU's undefined-base pre-pass relies on (forward k-mer: undefined = A, reverse k-mer: undefined =
+    complement of T, jgi/BBDuk.java:3882-3888; forbidNs: reset), pinned on the C oracle by the independent closed form:
+    every position of reference fragments of both strands replaced by N / IUPAC / lower-case n, alone and in pairs."""
+    rng = np.random.default_rng(5)
+    refs = _small_ref()
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    reads = []
+    for r in refs[:2]:
+        for frag in (r[:24], "".join(comp.get(c, c) for c in reversed(r[:24]))):
+            for i in range(len(frag)):
+                for gap, sym in ((0, "N"), (3, "R"), (7, "n")):
+                    s = list(frag)
+                    s[i] = "N"
+                    if gap and i + gap < len(s):
+                        s[i + gap] = sym
+                    left = "".join("ACGT"[int(x)] for x in rng.integers(0, 4, int(rng.integers(0, 12))))
+                    right = "".join("ACGT"[int(x)] for x in rng.integers(0, 4, int(rng.integers(0, 8))))
+                    reads.append(left + "".join(s) + right)
+    d = cf.Derived(k=case["k"], mink=case.get("mink", -1), hdist=case["hdist"], mm=case["mm"], rcomp=case.get("rcomp", True),
+                   fn=case.get("fn", False))
+    table = cf.build_table(d, refs)
+    rb, ro = pack([r.encode() for r in refs])
+    qb, qo = pack([r.encode() for r in reads])
+    common = dict(k=case["k"], mink=case.get("mink", -1), hdist=case["hdist"], mask_middle=int(case["mm"]),
+                  rcomp=int(case.get("rcomp", True)), forbid_ns=int(case.get("fn", False)), min_read_length=0)
+    o = Oracle(make_cfg(**common, ktrim_right=1))
+    o.add_ref(rb, ro)
+    o.finalize()
+    out, _ = o.process(qb, qo, False)
+    hits = 0
+    for i, s in enumerate(reads):
+        hi, id0 = cf.ktrim_right(d, table, s)
+        assert (out.hi[i], out.id0[i], out.lo[i]) == (hi, id0, 0), (i, s)
+        hits += id0 > 0
+    o = Oracle(make_cfg(**common, ktrim_left=1))
+    o.add_ref(rb, ro)
+    o.finalize()
+    out, _ = o.process(qb, qo, False)
+    for i, s in enumerate(reads):
+        lo, hi, id0 = cf.ktrim_left(d, table, s)
+        assert (out.lo[i], out.hi[i], out.id0[i]) == (lo, hi, id0), (i, s)
+    if not case.get("fn") and case["hdist"] > 0:
+        assert hits > len(reads) // 3  # the cases do exercise hits through windows with undefined bases
