@@ -278,16 +278,64 @@ def parse_args(args, generation=GEN_JGI):
 class BBDukIndexGPU:
     """Device-resident k-mer index + batched per-read k-mer block (the C ABI behind a Python handle)."""
 
-    def __init__(self, cfg):
+    def __init__(self, cfg, _handle=None):
         self.lib = _lib.load()
         self.cfg = cfg
-        h = C.c_void_p()
-        rc = self.lib.bbduk_b200_create(C.byref(cfg), C.byref(h))
-        if rc:
-            raise RuntimeError("bbduk_b200_create: " + self.lib.bbduk_b200_last_error(None).decode())
-        self.h = h
+        if _handle is not None:  # a handle the library created itself (bbduk_b200_replicate)
+            self.h = _handle
+        else:
+            h = C.c_void_p()
+            rc = self.lib.bbduk_b200_create(C.byref(cfg), C.byref(h))
+            if rc:
+                raise RuntimeError("bbduk_b200_create: " + self.lib.bbduk_b200_last_error(None).decode())
+            self.h = h
         self.stored_kmers = None
         self.n_scaffolds = 0
+
+    TRANSPORT = {0: "built", 1: "nccl", 2: "peer"}
+
+    def replicate(self, device_ids):
+        """In-library replication of the finished table to the listed GPUs of THIS process (bbduk_b200_replicate:
+        one NCCL broadcast per blob, or peer copies) -> one BBDukIndexGPU per device id."""
+        ids = (C.c_int32 * len(device_ids))(*device_ids)
+        hs = (C.c_void_p * len(device_ids))()
+        self._check(self.lib.bbduk_b200_replicate(self.h, ids, len(device_ids), hs), "replicate")
+        out = []
+        for i, dev in enumerate(device_ids):
+            e = BBDukIndexGPU(self.cfg, _handle=C.c_void_p(hs[i]))
+            e.stored_kmers, e.n_scaffolds, e.device = self.stored_kmers, self.n_scaffolds, dev
+            out.append(e)
+        return out
+
+    @property
+    def transport(self):
+        return self.TRANSPORT.get(int(self.lib.bbduk_b200_replica_transport(self.h)), "?")
+
+    @staticmethod
+    def process_sharded(engines, bases, offsets, paired, want_mask=False, out=None):
+        """One batch cut into len(engines) contiguous slices, slice i on engines[i] (its own GPU and host thread);
+        results in input order, counters summed (bbduk_b200_process_sharded)."""
+        lib = engines[0].lib
+        bases = np.ascontiguousarray(bases, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        n = len(offsets) - 1
+        if out is None:
+            out = Outputs(n, np.diff(offsets), want_mask=want_mask)
+        st = BBDukStats()
+        o = out.struct()
+        hs = (C.c_void_p * len(engines))(*[e.h for e in engines])
+        engines[0]._check(lib.bbduk_b200_process_sharded(hs, len(engines), bases.ctypes.data, offsets.ctypes.data, n,
+                                                         int(bool(paired)), C.byref(o), C.byref(st)), "process_sharded")
+        return out, st
+
+    @staticmethod
+    def scaffold_counts_sum(engines):
+        n = engines[0].n_scaffolds + 1
+        rc_, bc = np.zeros(n, np.int64), np.zeros(n, np.int64)
+        hs = (C.c_void_p * len(engines))(*[e.h for e in engines])
+        engines[0]._check(engines[0].lib.bbduk_b200_scaffold_counts_sum(hs, len(engines), rc_.ctypes.data, bc.ctypes.data, n),
+                          "scaffold_counts_sum")
+        return rc_, bc
 
     def _check(self, rc, what):
         if rc:

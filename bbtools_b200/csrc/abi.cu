@@ -6,8 +6,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
+
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/bbduk_b200.h"
@@ -94,6 +97,7 @@ struct bbduk_handle {
     cudaStream_t chain_copy = nullptr;
     cudaEvent_t chain_in[2] = {nullptr, nullptr}, chain_free[2] = {nullptr, nullptr};
     std::mutex tbo_mu;
+    int replicated_via = 0;    // 0 = built here, 1 = NCCL broadcast, 2 = peer copy (bbduk_b200_replicate)
     HostPool *pool = nullptr;  // host packing workers, created on first use
     std::mutex pool_mu;
     std::mutex dev_mu;
@@ -503,8 +507,10 @@ int bbduk_b200_table_commit(bbduk_handle *h) {
     return 0;
 }
 
-int bbduk_b200_process_device(bbduk_handle *h, const uint8_t *d_bases, const uint32_t *d_offsets, int64_t n_reads,
-                              int32_t paired, const bbduk_out *d_out, bbduk_stats *d_stats, void *stream) {
+// max_len_known > 0: the caller knows the longest read of the batch (the chain measures every chunk on the host);
+// 0: the handle-wide hint, else one reduction kernel + a stream synchronisation
+static int process_device_impl(bbduk_handle *h, const uint8_t *d_bases, const uint32_t *d_offsets, int64_t n_reads,
+                               int32_t paired, const bbduk_out *d_out, bbduk_stats *d_stats, void *stream, int max_len_known) {
     if (!h) return set_err(nullptr, "handle is NULL");
     if (!h->finalized) return set_err(h, "process before finalize");
     if (n_reads < 0 || (paired && (n_reads & 1))) return set_err(h, "bad n_reads");
@@ -522,7 +528,7 @@ int bbduk_b200_process_device(bbduk_handle *h, const uint8_t *d_bases, const uin
         CKH(cudaMalloc(&h->dev_handoff_n, sizeof(unsigned int) * 4));
     }
     // longest read (sizes the fast kernel's staging): caller's hint, else one reduction + sync
-    unsigned int mx = (unsigned int)std::max(0, h->max_read_len_hint.load());
+    unsigned int mx = max_len_known > 0 ? (unsigned int)max_len_known : (unsigned int)std::max(0, h->max_read_len_hint.load());
     if (mx == 0) {
         CKH(cudaMemsetAsync(h->dev_handoff_n + 1, 0, sizeof(unsigned int), st));
         max_len_kernel<<<296, 256, 0, st>>>(d_offsets, n_reads, h->dev_handoff_n + 1);
@@ -555,6 +561,11 @@ int bbduk_b200_process_device(bbduk_handle *h, const uint8_t *d_bases, const uin
     }
     return run_batch(h, d_bases, d_offsets, n_reads, n_bases, paired, *d_out, d_stats, (int)mx, h->dev_handoff,
                      h->dev_handoff_n, ds, st);
+}
+
+int bbduk_b200_process_device(bbduk_handle *h, const uint8_t *d_bases, const uint32_t *d_offsets, int64_t n_reads,
+                              int32_t paired, const bbduk_out *d_out, bbduk_stats *d_stats, void *stream) {
+    return process_device_impl(h, d_bases, d_offsets, n_reads, paired, d_out, d_stats, stream, 0);
 }
 
 int bbduk_b200_process(bbduk_handle *h, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, int32_t paired,
@@ -1076,6 +1087,8 @@ int bbduk_b200_process_chain(bbduk_handle *h, const bbduk_chain_cfg *cfg, const 
     if (n_reads < 0 || (paired && (n_reads & 1))) return set_err(h, "bad n_reads (paired input needs an even count)");
     if (h->p.mode == MODE_KMASK || h->p.mode == MODE_KSPLIT) return set_err(h, "kmask / ksplit are not chained (they rewrite bases)");
     if (!out || !out->lo || !out->hi || !out->flags) return set_err(h, "the chain needs out->lo, out->hi and out->flags");
+    if (out->id0b && h->p.mode == MODE_KTRIM_TIPS) return set_err(h, "the chain does not return out->id0b (ktrim=rl left-tip credit): pass NULL or use bbduk_b200_process");
+    if (out->id0b && n_reads > 0) memset(out->id0b, 0xFF, sizeof(int32_t) * (size_t)n_reads);  // no left-tip credit outside ktrim=rl: -1
     if (cfg->do_tbo && !paired) return set_err(h, "tbo needs paired reads");
     const bool need_q = (cfg->do_tbo && quals) || (cfg->do_qtrim && (cfg->qtrim.qtrim_left || cfg->qtrim.qtrim_right ||
                                                                      cfg->qtrim.min_base_quality > 0 || cfg->qtrim.min_avg_quality > 0));
@@ -1171,9 +1184,7 @@ int bbduk_b200_process_chain(bbduk_handle *h, const bbduk_chain_cfg *cfg, const 
         dout.flags = tb.d_flags;
         dout.id0 = out->id0 ? tb.d_id0 : nullptr;
         dout.count = out->count ? tb.d_count : nullptr;
-        const int hint = h->max_read_len_hint.exchange(max_len);
-        if (!rc) rc = bbduk_b200_process_device(h, d_b, d_o, nr, paired, &dout, reinterpret_cast<bbduk_stats *>(d_st), st);
-        h->max_read_len_hint = hint;
+        if (!rc) rc = process_device_impl(h, d_b, d_o, nr, paired, &dout, reinterpret_cast<bbduk_stats *>(d_st), st, std::max(max_len, 1));
         if (!rc && cfg->do_tbo)
             rc = bbduk_b200_tbo_device(h, &cfg->tbo, d_b, quals ? d_q : nullptr, d_o, nr, max_len, tb.d_lo, tb.d_hi, tb.d_flags,
                                        tb.d_insert, d_st + 8, st);
@@ -1254,6 +1265,225 @@ void bbduk_b200_destroy(bbduk_handle *h) {
     }
     delete h->pool;
     delete h;
+}
+
+}  // extern "C"
+
+// ---- single-process multi-GPU: table replication and read sharding inside the library --------------------------------
+// The reference drives ONE index from THREADS Java threads of one JVM (bbduk/BBDukS.java:317-319); a JNI caller has no
+// torchrun. bbduk_b200_replicate copies a finished table to other GPUs of the box -- one NCCL broadcast per blob over
+// NVLink (libnccl is resolved at run time with dlopen, so the library still loads where NCCL is absent), or
+// cudaMemcpyPeerAsync where NCCL cannot be used (a target on the source's own GPU, duplicate devices, no libnccl).
+namespace {
+
+typedef struct ncclComm *bb_ncclComm_t;
+struct NcclApi {
+    void *lib = nullptr;
+    int (*CommInitAll)(bb_ncclComm_t *, int, const int *) = nullptr;
+    int (*CommDestroy)(bb_ncclComm_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Broadcast)(const void *, void *, size_t, int /*ncclDataType_t*/, int, bb_ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+
+NcclApi *nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) {
+            api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib) break;
+        }
+        if (!api.lib) return;
+        api.CommInitAll = reinterpret_cast<decltype(api.CommInitAll)>(dlsym(api.lib, "ncclCommInitAll"));
+        api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.lib, "ncclCommDestroy"));
+        api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(dlsym(api.lib, "ncclGroupStart"));
+        api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(dlsym(api.lib, "ncclGroupEnd"));
+        api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(dlsym(api.lib, "ncclBroadcast"));
+        api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.lib, "ncclGetErrorString"));
+        api.ok = api.CommInitAll && api.CommDestroy && api.GroupStart && api.GroupEnd && api.Broadcast;
+    });
+    return api.ok ? &api : nullptr;
+}
+
+struct Blob {
+    const void *src;
+    size_t bytes;
+};
+
+}  // namespace
+
+extern "C" {
+
+int bbduk_b200_replicate(bbduk_handle *src, const int32_t *device_ids, int32_t n_devices, bbduk_handle **out) {
+    if (!src) return set_err(nullptr, "handle is NULL");
+    bbduk_handle *h = src;
+    if (!src->finalized) return set_err(src, "replicate before finalize");
+    if (n_devices < 1 || !device_ids || !out) return set_err(src, "bad replicate arguments");
+    for (int i = 0; i < n_devices; i++) out[i] = nullptr;
+    bbduk_table_desc d0;
+    if (bbduk_b200_table_describe(src, &d0)) return 1;
+    std::vector<bbduk_table_desc> dd(n_devices);
+    auto fail = [&](const std::string &m) {
+        for (int i = 0; i < n_devices; i++) {
+            bbduk_b200_destroy(out[i]);
+            out[i] = nullptr;
+        }
+        cudaSetDevice(src->device);
+        return set_err(src, m);
+    };
+    for (int i = 0; i < n_devices; i++) {
+        bbduk_cfg c = src->cfg;
+        c.device = device_ids[i];
+        if (bbduk_b200_create(&c, &out[i])) return fail(std::string("replicate: create on device ") + std::to_string(device_ids[i]) + ": " + g_err);
+        dd[i] = d0;
+        dd[i].d_keys = dd[i].d_vals = dd[i].d_filter = nullptr;
+        if (bbduk_b200_table_alloc(out[i], &dd[i])) return fail(std::string("replicate: table_alloc: ") + bbduk_b200_last_error(out[i]));
+    }
+    const Blob blobs[3] = {{d0.d_keys, sizeof(uint64_t) * (size_t)d0.n_slots},
+                           {d0.d_vals, sizeof(int32_t) * (size_t)d0.n_slots},
+                           {d0.d_filter, sizeof(uint32_t) * (size_t)d0.n_filter_words}};
+    auto dst_of = [&](int i, int b) -> void * { return b == 0 ? dd[i].d_keys : b == 1 ? dd[i].d_vals : dd[i].d_filter; };
+    // targets NCCL can serve: distinct devices, none of them the source's
+    std::vector<int> via_nccl, via_peer;
+    const char *force = getenv("BBDUK_B200_REPLICATE");  // "peer" | "nccl" (default: nccl where possible)
+    NcclApi *api = (force && !strcmp(force, "peer")) ? nullptr : nccl_api();
+    for (int i = 0; i < n_devices; i++) {
+        bool dup = device_ids[i] == src->device;
+        for (int j : via_nccl) dup = dup || device_ids[j] == device_ids[i];
+        (api && !dup ? via_nccl : via_peer).push_back(i);
+    }
+    if (force && !strcmp(force, "nccl") && !via_peer.empty() && !api) return fail("replicate: BBDUK_B200_REPLICATE=nccl but libnccl could not be loaded");
+    if (!via_nccl.empty()) {
+        const int m = (int)via_nccl.size() + 1;
+        std::vector<int> devs(m);
+        devs[0] = src->device;
+        for (int r = 1; r < m; r++) devs[r] = device_ids[via_nccl[r - 1]];
+        std::vector<bb_ncclComm_t> comms(m, nullptr);
+        std::vector<cudaStream_t> sts(m, nullptr);
+        int nrc = api->CommInitAll(comms.data(), m, devs.data());
+        std::string emsg;
+        if (nrc != 0) emsg = std::string("ncclCommInitAll: ") + (api->GetErrorString ? api->GetErrorString(nrc) : "error");
+        for (int r = 0; r < m && emsg.empty(); r++) {
+            if (cudaSetDevice(devs[r]) != cudaSuccess || cudaStreamCreateWithFlags(&sts[r], cudaStreamNonBlocking) != cudaSuccess)
+                emsg = "replicate: stream creation failed";
+        }
+        if (emsg.empty()) {
+            api->GroupStart();
+            for (int b = 0; b < 3 && nrc == 0; b++) {
+                if (blobs[b].bytes == 0) continue;
+                for (int r = 0; r < m && nrc == 0; r++) {
+                    void *mine = r == 0 ? const_cast<void *>(blobs[b].src) : dst_of(via_nccl[r - 1], b);
+                    nrc = api->Broadcast(mine, mine, blobs[b].bytes, 1 /* ncclUint8 */, 0, comms[r], sts[r]);
+                }
+            }
+            const int grc = api->GroupEnd();
+            if (nrc == 0) nrc = grc;
+            if (nrc != 0) emsg = std::string("ncclBroadcast: ") + (api->GetErrorString ? api->GetErrorString(nrc) : "error");
+        }
+        for (int r = 0; r < m; r++) {
+            if (!sts[r]) continue;
+            cudaSetDevice(devs[r]);
+            if (cudaStreamSynchronize(sts[r]) != cudaSuccess && emsg.empty()) emsg = std::string("replicate: ") + cudaGetErrorString(cudaGetLastError());
+            cudaStreamDestroy(sts[r]);
+        }
+        for (int r = 0; r < m; r++)
+            if (comms[r]) api->CommDestroy(comms[r]);
+        if (!emsg.empty()) return fail(emsg);
+        for (int i : via_nccl) out[i]->replicated_via = 1;
+    }
+    if (!via_peer.empty()) {
+        if (cudaSetDevice(src->device) != cudaSuccess) return fail("replicate: cudaSetDevice failed");
+        cudaStream_t st = nullptr;
+        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return fail("replicate: stream creation failed");
+        cudaError_t e = cudaSuccess;
+        for (int i : via_peer) {
+            if (device_ids[i] != src->device) {
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, src->device, device_ids[i]);
+                if (can) {
+                    cudaError_t pe = cudaDeviceEnablePeerAccess(device_ids[i], 0);  // already enabled is fine
+                    if (pe != cudaSuccess) cudaGetLastError();
+                }
+            }
+            for (int b = 0; b < 3 && e == cudaSuccess; b++)
+                if (blobs[b].bytes) e = cudaMemcpyPeerAsync(dst_of(i, b), device_ids[i], blobs[b].src, src->device, blobs[b].bytes, st);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        cudaStreamDestroy(st);
+        if (e != cudaSuccess) return fail(std::string("replicate: peer copy failed: ") + cudaGetErrorString(e));
+        for (int i : via_peer) out[i]->replicated_via = 2;
+    }
+    for (int i = 0; i < n_devices; i++)
+        if (bbduk_b200_table_commit(out[i])) return fail(std::string("replicate: table_commit: ") + bbduk_b200_last_error(out[i]));
+    cudaSetDevice(src->device);
+    return 0;
+}
+
+int bbduk_b200_replica_transport(bbduk_handle *h) { return h ? h->replicated_via : -1; }
+
+int bbduk_b200_process_sharded(bbduk_handle **handles, int32_t n_handles, const uint8_t *bases, const int64_t *offsets,
+                               int64_t n_reads, int32_t paired, const bbduk_out *out, bbduk_stats *stats) {
+    if (!handles || n_handles < 1 || !handles[0]) return set_err(nullptr, "bad process_sharded arguments");
+    bbduk_handle *h = handles[0];
+    for (int i = 0; i < n_handles; i++)
+        if (!handles[i]) return set_err(h, "process_sharded: NULL handle");
+    if (n_reads < 0 || (paired && (n_reads & 1))) return set_err(h, "bad n_reads (paired input needs an even count)");
+    if (!out) return set_err(h, "out is NULL");
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (n_reads == 0) return 0;
+    const int per = paired ? 2 : 1;
+    const int64_t units = n_reads / per;
+    std::vector<int> rcs(n_handles, 0);
+    std::vector<bbduk_stats> sts(n_handles);
+    std::vector<std::thread> th;
+    for (int i = 0; i < n_handles; i++) {
+        const int64_t r0 = units * i / n_handles * per, r1 = units * (i + 1) / n_handles * per;
+        th.emplace_back([=, &rcs, &sts] {
+            memset(&sts[i], 0, sizeof(bbduk_stats));
+            if (r1 <= r0) return;
+            bbduk_out o = *out;  // slices of the caller's arrays; kmask words are addressed through absolute mask_off entries
+            if (o.id0) o.id0 += r0;
+            if (o.id0b) o.id0b += r0;
+            if (o.lo) o.lo += r0;
+            if (o.hi) o.hi += r0;
+            if (o.flags) o.flags += r0;
+            if (o.count) o.count += r0;
+            if (o.mask_off) o.mask_off += r0;
+            rcs[i] = bbduk_b200_process(handles[i], bases, offsets + r0, r1 - r0, paired, &o, &sts[i]);
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int i = 0; i < n_handles; i++)
+        if (rcs[i]) return set_err(h, std::string("process_sharded: shard ") + std::to_string(i) + ": " + bbduk_b200_last_error(handles[i]));
+    if (stats) {
+        int64_t *acc = reinterpret_cast<int64_t *>(stats);
+        for (int i = 0; i < n_handles; i++) {
+            const int64_t *v = reinterpret_cast<const int64_t *>(&sts[i]);
+            for (size_t q = 0; q < sizeof(bbduk_stats) / sizeof(int64_t); q++) acc[q] += v[q];
+        }
+    }
+    return 0;
+}
+
+int bbduk_b200_scaffold_counts_sum(bbduk_handle **handles, int32_t n_handles, int64_t *read_counts, int64_t *base_counts, int32_t n) {
+    if (!handles || n_handles < 1 || !handles[0]) return set_err(nullptr, "bad scaffold_counts_sum arguments");
+    std::vector<int64_t> r(std::max(n, 0)), b(std::max(n, 0));
+    if (read_counts) std::fill(read_counts, read_counts + std::max(n, 0), 0);
+    if (base_counts) std::fill(base_counts, base_counts + std::max(n, 0), 0);
+    for (int i = 0; i < n_handles; i++) {
+        std::fill(r.begin(), r.end(), 0);
+        std::fill(b.begin(), b.end(), 0);
+        if (bbduk_b200_scaffold_counts(handles[i], r.data(), b.data(), n)) return set_err(handles[0], bbduk_b200_last_error(handles[i]));
+        for (int j = 0; j < n; j++) {
+            if (read_counts) read_counts[j] += r[j];
+            if (base_counts) base_counts[j] += b[j];
+        }
+    }
+    return 0;
 }
 
 }  // extern "C"

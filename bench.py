@@ -196,6 +196,28 @@ WORKLOADS = {
 }
 
 
+def table_checksum(eng, torch):
+    """order-independent checksum of the (key, id) pairs of the device hash array + the filter images, computed on the
+    device in slices -> (63-bit checksum, number of keys). Equal on all ranks <=> the replicas hold the same table."""
+    d = eng.table_describe()
+    keys = eng._view(d.d_keys, d.n_slots * 8).view(torch.int64)
+    vals = eng._view(d.d_vals, d.n_slots * 4).view(torch.int32)
+    filt = eng._view(d.d_filter, d.n_filter_words * 4).view(torch.int32)
+    acc, n_keys = 0, 0
+    step = 1 << 26
+    for a in range(0, d.n_slots, step):
+        k = keys[a:a + step]
+        m = k != -1
+        x = k * -7046029254386353131 + vals[a:a + step].to(torch.int64) * -4417276706812531889
+        acc = (acc + int(torch.where(m, x, torch.zeros_like(x)).sum().item())) & 0xFFFFFFFFFFFFFFFF
+        n_keys += int(m.sum().item())
+    for a in range(0, d.n_filter_words, step):
+        f = filt[a:a + step].to(torch.int64)
+        idx = torch.arange(a, a + f.numel(), device=f.device, dtype=torch.int64)
+        acc = (acc + int((f * (2 * idx + 1)).sum().item())) & 0xFFFFFFFFFFFFFFFF
+    return acc >> 1, n_keys
+
+
 def build_engine(wl, rank, local_rank, world, lib, torch):
     """table built on rank 0 and replicated by NCCL broadcast; returns (engine, stored, d_ref or None)"""
     from bbtools_b200 import make_cfg
@@ -603,9 +625,10 @@ def run_ours(args):
                       "h2d_bytes_per_call": int(cb.nbytes + cq.nbytes + 4 * (c_reads + 1)), "d2h_bytes_per_call": 9 * c_reads,
                       "reads_trimmed_by_overlap": int(ct2[0]), "reads_qtrimmed": int(cq8[0])}
 
-    # ---- sanity: the timed batch agrees with the CPU oracle on a slice (checker only) -----------------
+    # ---- sanity: EVERY rank checks a slice of its own timed batch against the CPU oracle (checker only); the flag in the
+    # line is the AND over ranks, so a rank whose replicated table arrived broken cannot hide behind rank 0 -----------
     parity = None
-    if rank == 0 and (args.workload == "cfg2" or args.verify):
+    if args.workload == "cfg2" or args.verify:
         from oracle.oracle import Oracle
         chk = 20000
         o = Oracle(make_cfg(**wl["cfg"]))
@@ -615,16 +638,28 @@ def run_ours(args):
             rb = d_ref.cpu().numpy()
             roff = np.arange(0, rb.size + 1, wl["ref"][1], dtype=np.int64)
         o.add_ref(rb, roff)
-        o.finalize()
+        stored_o = o.finalize()
         step(args.warmup + args.steps - 1)
         torch.cuda.synchronize()
         db, _ = bufs[(args.warmup + args.steps - 1) % nbuf]
         hb2 = db[: 2 * chk * L].cpu().numpy()  # the device generators are tested against synth.py byte for byte
         ho2 = np.arange(0, (2 * chk + 1) * L, L, dtype=np.int64)
-        want, _ = o.process(hb2, ho2, paired, threads=min(8, os.cpu_count() or 1))
-        parity = bool(np.array_equal(outs["hi"][: 2 * chk].cpu().numpy(), want.hi) and
-                      np.array_equal(outs["id0"][: 2 * chk].cpu().numpy(), want.id0) and
-                      np.array_equal(outs["flags"][: 2 * chk].cpu().numpy(), want.flags))
+        want, _ = o.process(hb2, ho2, paired, threads=max(1, min(8, (os.cpu_count() or 1) // world)))
+        mine = bool(np.array_equal(outs["hi"][: 2 * chk].cpu().numpy(), want.hi) and
+                    np.array_equal(outs["id0"][: 2 * chk].cpu().numpy(), want.id0) and
+                    np.array_equal(outs["flags"][: 2 * chk].cpu().numpy(), want.flags) and stored_o == stored)
+        # the replicated table itself: an order-independent checksum of (key, id) over all slots must equal rank 0's
+        csum, n_keys = table_checksum(eng, torch)
+        flag = torch.tensor([1 if mine else 0, csum, -csum, n_keys, -n_keys], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        f = flag.cpu().tolist()
+        tables_equal = (f[1] == -f[2]) and (f[3] == -f[4])  # min == max over ranks
+        parity = bool(f[0] == 1 and tables_equal)
+        parity_detail = {"ranks_checked": world, "reads_checked_per_rank": 2 * chk, "all_ranks_match_oracle": bool(f[0] == 1),
+                         "table_checksum_equal_on_all_ranks": bool(tables_equal), "table_keys": int(f[3])}
+    else:
+        parity_detail = None
 
     if rank == 0:
         peak, peak_kind = load_peak()
@@ -654,7 +689,8 @@ def run_ours(args):
             "config": {"workload": wl["desc"], "pairs_per_step_per_gpu": n_pairs, "read_len": L,
                        "stored_kmers": stored, "l2": f"inputs {n_reads * L / 2**20:.0f} MiB per step > 126 MB L2, "
                        f"{nbuf} alternating buffers, no flush", "table_build_s": round(t_build, 3),
-                       "parity_vs_oracle_on_timed_batch": parity, "kmer_block_plus_tbo": tbo_info,
+                       "parity_vs_oracle_on_timed_batch": parity, "parity_detail": parity_detail,
+                       "kmer_block_plus_tbo": tbo_info,
                        "qtrim_block": qtrim_info, "entropy_block": entropy_info,
                        "chain_e2e_kmer_tbo_qtrim": chain_info},
             "e2e": {"value": e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -207,6 +207,31 @@ BBDUK_API int bbduk_b200_table_describe(bbduk_handle *h, bbduk_table_desc *desc)
 BBDUK_API int bbduk_b200_table_alloc(bbduk_handle *h, bbduk_table_desc *desc /* in: geometry+scalars; out: pointers */);
 BBDUK_API int bbduk_b200_table_commit(bbduk_handle *h);
 
+/*
+ * Single-process multi-GPU (SURVEY.md 8b `device_ids[] / n_devices`, 8e). The reference runs THREADS ProcessThreads of ONE
+ * JVM against one shared index (bbduk/BBDukS.java:317-319, bbduk/BBDukProcessorS.java:768); a JNI caller has no torchrun.
+ * bbduk_b200_replicate gives every listed GPU its own handle holding a copy of `src`'s finished table: one NCCL
+ * broadcast per blob (keys, ids, filter images) over NVLink with ncclCommInitAll inside this process (libnccl.so.2 is
+ * resolved with dlopen at run time), or cudaMemcpyPeerAsync for targets NCCL cannot serve (a target on src's own GPU,
+ * duplicate ordinals, libnccl missing; BBDUK_B200_REPLICATE=peer forces it). out[n_devices] receives the new handles
+ * (same bbduk_cfg as src, cfg.device = device_ids[i]); destroy them with bbduk_b200_destroy. On failure nothing is
+ * left allocated. bbduk_b200_replica_transport: 0 = table built on this handle, 1 = received by NCCL broadcast,
+ * 2 = received by peer copy.
+ */
+BBDUK_API int bbduk_b200_replicate(bbduk_handle *src, const int32_t *device_ids, int32_t n_devices, bbduk_handle **out);
+BBDUK_API int bbduk_b200_replica_transport(bbduk_handle *h);
+
+/* Replaces: the split of the input among the ProcessThreads (reads are independent units): the batch is
+ * cut into n_handles contiguous slices (pairs never split), slice i runs bbduk_b200_process on handles[i] from its own
+ * host thread, results land in input order in the caller's arrays and the counters are summed as the reference sums its
+ * per-thread counters (jgi/BBDuk.java:2085-2131). HOST buffers, same contract as bbduk_b200_process. */
+BBDUK_API int bbduk_b200_process_sharded(bbduk_handle **handles, int32_t n_handles, const uint8_t *bases,
+                                         const int64_t *offsets, int64_t n_reads, int32_t paired, const bbduk_out *out,
+                                         bbduk_stats *stats);
+/* Per-scaffold hit counts summed over the handles of a replica set. */
+BBDUK_API int bbduk_b200_scaffold_counts_sum(bbduk_handle **handles, int32_t n_handles, int64_t *read_counts,
+                                             int64_t *base_counts, int32_t n);
+
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 BBDUK_API int64_t bbduk_b200_launch_count(bbduk_handle *h);
 
