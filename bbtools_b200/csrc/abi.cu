@@ -271,7 +271,7 @@ struct DirectScratch {
 // which kernel family a batch of this handle goes to
 bool uses_direct(const bbduk_handle *h, int max_read_len) {
     const BBTable t = h->table.view();
-    return !plan_fast(h->p, t, max_read_len).usable && plan_direct(h->p, t);
+    return !plan_fast2(h->p, t, max_read_len).usable && !plan_fast(h->p, t, max_read_len).usable && plan_direct(h->p, t);
 }
 
 int run_batch(bbduk_handle *h, const uint8_t *d_bases, const uint32_t *d_off, int64_t n_reads, int64_t n_bases, int paired,
@@ -281,11 +281,14 @@ int run_batch(bbduk_handle *h, const uint8_t *d_bases, const uint32_t *d_off, in
     if (n_reads <= 0) return 0;
     const BBTable t = h->table.view();
     const int64_t n_units = paired ? n_reads / 2 : n_reads;
-    const FastPlan plan = plan_fast(h->p, t, max_read_len);
+    const FastPlan plan2 = plan_fast2(h->p, t, max_read_len);
+    const FastPlan plan = plan2.usable ? plan2 : plan_fast(h->p, t, max_read_len);
     if (plan.usable && d_handoff) {
         CKH(cudaMemsetAsync(d_handoff_n, 0, sizeof(unsigned int), st));
-        const int nl = launch_fast(plan, d_bases, d_off, n_reads, paired, h->p, t, dout, d_stats, h->d_scaf_reads,
-                                   h->d_scaf_bases, d_handoff, d_handoff_n, h->sm_count, st, pk_F, pk_D);
+        const int nl = plan2.usable ? launch_fast2(plan, d_bases, d_off, n_reads, paired, h->p, t, dout, d_stats, h->d_scaf_reads,
+                                                   h->d_scaf_bases, d_handoff, d_handoff_n, h->sm_count, st, pk_F, pk_D)
+                                    : launch_fast(plan, d_bases, d_off, n_reads, paired, h->p, t, dout, d_stats, h->d_scaf_reads,
+                                                  h->d_scaf_bases, d_handoff, d_handoff_n, h->sm_count, st, pk_F, pk_D);
         if (nl < 0) return set_err(h, std::string("fast kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
         h->launches += nl;
         if (pk_F) return 0;  // packed batches are sized so that no tile is handed off
@@ -470,6 +473,7 @@ int bbduk_b200_table_describe(bbduk_handle *h, bbduk_table_desc *d) {
     d->scalars[5] = (int64_t)h->table.part_lag[0] | ((int64_t)h->table.part_lag[1] << 8) |
                     ((int64_t)h->table.part_lag[2] << 16) | ((int64_t)h->table.part_lag[3] << 24);
     d->scalars[6] = h->table.big_words;
+    d->scalars[7] = (int64_t)h->table.samp_words | ((int64_t)h->table.tail_words << 24) | ((int64_t)h->table.tail_q << 56);
     return 0;
 }
 
@@ -487,6 +491,9 @@ int bbduk_b200_table_alloc(bbduk_handle *h, bbduk_table_desc *d) {
     h->table.part_words = (uint32_t)d->scalars[2];
     h->table.short_words = (uint32_t)d->scalars[3];
     h->table.big_words = (uint32_t)d->scalars[6];
+    h->table.samp_words = (uint32_t)(d->scalars[7] & 0xFFFFFF);
+    h->table.tail_words = (uint32_t)((d->scalars[7] >> 24) & 0xFFFFFFFFll);
+    h->table.tail_q = (int32_t)((d->scalars[7] >> 56) & 0x7F);
     h->table.n_parts = (int32_t)(d->scalars[4] & 0xFF);
     h->table.part_w = (int32_t)(d->scalars[4] >> 8);
     for (int j = 0; j < 4; j++) h->table.part_lag[j] = (int32_t)((d->scalars[5] >> (8 * j)) & 0xFF);
@@ -669,7 +676,7 @@ int bbduk_b200_process(bbduk_handle *h, const uint8_t *bases, const int64_t *off
         {
             const BBTable tv = h->table.view();
             packed = h->pack_host && !want_mask && max_len <= FAST_MAX_READ_LEN && nb >= (1 << 16) &&
-                     plan_fast(h->p, tv, max_len).usable && packed_ok(h->p, tv);
+                     (plan_fast2(h->p, tv, max_len).usable || plan_fast(h->p, tv, max_len).usable) && packed_ok(h->p, tv);
             // host packing is bound by the host's memory bandwidth, the ASCII path by PCIe: every n-th chunk goes
             // ASCII (no CPU work, DMA straight from the caller's buffer) so that both resources are used
             // (never the last chunk of a call: its transfer is the tail nothing overlaps with)
@@ -1320,7 +1327,6 @@ extern "C" {
 
 int bbduk_b200_replicate(bbduk_handle *src, const int32_t *device_ids, int32_t n_devices, bbduk_handle **out) {
     if (!src) return set_err(nullptr, "handle is NULL");
-    bbduk_handle *h = src;
     if (!src->finalized) return set_err(src, "replicate before finalize");
     if (n_devices < 1 || !device_ids || !out) return set_err(src, "bad replicate arguments");
     for (int i = 0; i < n_devices; i++) out[i] = nullptr;

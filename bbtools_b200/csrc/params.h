@@ -46,11 +46,15 @@ struct BBTable {
     const int32_t *vals;    // [n_slots]; scaffold id (min over writers)
     uint64_t slot_mask;     // n_slots-1 (n_slots power of two, >= 1024)
     uint32_t bucket_shift;  // 34 - log2(n_slots): bucket = hash32 >> bucket_shift
-    // on-chip filter images, one device buffer: [canonical bloom of all keys | part filter | short-key bloom]
+    // filter images, one device buffer: [canonical bloom of all keys | part filter | short-key bloom | 8-mer byte map |
+    // tail bitmaps | L2 filter]
     const uint32_t *filter;
     uint32_t n_filter_words;  // canonical bloom words
     uint32_t part_words;      // part filter words (0 = not available for this configuration)
     uint32_t short_words;     // bloom over the short (len<k) keys only
+    uint32_t samp_words;      // byte map over all 8-mers that occur inside a reference part (sampled scan of probe_fast2.cu; 0 = none)
+    uint32_t tail_words;      // two direct bitmaps over tail_q-mers in front of the short-k-mer tails (0 = none)
+    int32_t tail_q;           // bases the tail bitmaps are indexed by = min(mink, 12)
     uint32_t big_words;       // L2-resident one-bit-per-key filter in front of an HBM-resident array (0 = none)
     int32_t n_parts;          // pigeonhole parts = hdist+1
     int32_t part_w;           // bases per part (<=16)

@@ -27,6 +27,13 @@ int launch_fast(const FastPlan &plan, const uint8_t *d_bases, const uint32_t *d_
                 unsigned long long *scaf_reads, unsigned long long *scaf_bases, int32_t *d_handoff,
                 unsigned int *d_handoff_n, int sm_count, cudaStream_t st, const uint32_t *pk_F = nullptr,
                 const uint16_t *pk_D = nullptr);
+// round-2 kernel (probe_fast2.cu): sampled pigeonhole scan; same contract as plan_fast / launch_fast, preferred where usable
+FastPlan plan_fast2(const BBParams &p, const BBTable &t, int max_read_len);
+int launch_fast2(const FastPlan &plan, const uint8_t *d_bases, const uint32_t *d_offsets, int64_t n_reads, int paired,
+                 const BBParams &p, const BBTable &t, const bbduk_out &out, bbduk_stats *d_stats,
+                 unsigned long long *scaf_reads, unsigned long long *scaf_bases, int32_t *d_handoff,
+                 unsigned int *d_handoff_n, int sm_count, cudaStream_t st, const uint32_t *pk_F = nullptr,
+                 const uint16_t *pk_D = nullptr);
 // host-packed input (hostpack.h): pk_F / pk_D replace d_bases when packed_ok() and no tile can be handed off
 bool packed_ok(const BBParams &p, const BBTable &t);
 constexpr int FAST_MAX_READ_LEN = 1008;

@@ -147,7 +147,7 @@ bbduk_direct_kernel(const uint8_t *__restrict__ bases, const uint16_t *__restric
     const int64_t n_spans = (n_bases + DP_SPAN - 1) / DP_SPAN;
     const uint64_t bmask = t.slot_mask >> 2;
     // L2-resident one-bit-per-key filter in front of the HBM probes (none for small arrays)
-    const uint32_t *bigf = t.filter + t.n_filter_words + t.part_words + t.short_words;
+    const uint32_t *bigf = t.filter + t.n_filter_words + t.part_words + t.short_words + t.samp_words + t.tail_words;
     const uint32_t big_words = t.big_words;
     const uint64_t pol_keep = dp_policy_evict_last();
 

@@ -1,0 +1,831 @@
+// probe_fast2.cu -- the sampled-pigeonhole per-read kernel (round 2) for ktrim=r, ktrim=l and kfilter with a
+// substitution-only neighbourhood whose pigeonhole parts are at least 11 bases wide (k=23 hdist<=1, k=31 hdist<=1, ...).
+//
+// Same contract as probe_fast.cu (which it replaces where it applies): it only decides WHICH read positions can hit and
+// then evaluates those with the exact key formula against the exact hash array, so results are identical by construction.
+// What changed is how few instructions the deciding takes (probe_fast.cu tests a 9-mer at EVERY read position, 6
+// instructions each, and its scan loop carries the queue bookkeeping):
+//
+//   A.  stage the tile's ASCII as a 2-bit stream F (+ defined bits D) in shared memory (as probe_fast.cu);
+//   B1. sampled scan: a window can only hit if one of its hdist+1 parts (w >= 11 bases) equals a reference part; such a
+//       part contains a whole 8-mer that starts on a 4-base boundary of the STREAM, whatever the read's phase. So the
+//       lane looks up only the byte-aligned 16-bit fields of F -- one PRMT, one byte load from a 64 KB map of all 8-mers
+//       that occur inside a reference part, one multiply-add into the hit mask; 4 lookups per 16 bases, no queue work;
+//   B2. the sample hits of all 32 reads (on random sequence 1.5 per read for adapters.fa) are pooled and confirmed 32 at
+//       a time against the 9-mer bitmap: the 2w-16 9-mers around a hit give the parts that pass entirely, whose end
+//       positions are OR-ed into the owner's seed bits S (shared memory, one column per lane);
+//   C.  candidate windows = seed bits shifted by the part lags (+ every window with an undefined base); they are released
+//       in position order, a few per read and round so that a round never exceeds 32, evaluated exactly by the pooled
+//       evaluator, and a read stops at its first confirmed hit (ktrim=r, kfilter; ktrim=l then walks down from the end);
+//   T.  short-k-mer tails: two direct bitmaps over q-mers (table.cu: tail_filter_build_kernel) say which tail lengths can
+//       hit at all -- on random reads 2 % of them -- and only those are looked up;
+//   D.  TrimRead arithmetic, minlen, pair logic, outputs (as probe_fast.cu).
+// Rolling-state semantics: jgi/BBDuk.java:3882-3900 in the closed form of SURVEY.md A.2; ktrim :3866-4013; kfilter :3395-3457.
+#include <algorithm>
+#include <cstdlib>
+
+#include "bbduk_dev.cuh"
+#include "fast_common.cuh"
+#include "probe.h"
+
+namespace {
+
+using namespace bbfast;
+
+constexpr int QCAP2 = 512;     // pooled queue entries (16 bit each): sample hits of one pass / candidates of one round
+constexpr int ITEM_CAP = 16;   // sample hits one read contributes per pass (32 x 16 = QCAP2)
+constexpr int L1_WORDS = 12;   // stream words (16 bases each) one unrolled block of the sampled scan covers
+
+struct Fast2Geom {
+    int warps;        // warps per block
+    int nch;          // staged 16-base chunks per warp (capacity, without padding)
+    int warp_bytes;   // shared memory per warp
+    int nbadw;        // words of the per-tile "chunk has an undefined base" bit mask
+    int sw;           // 32-position words of the per-lane seed bit columns
+    uint32_t part_off, samp_off, tail_off;  // word offsets of the part bitmap / 8-mer byte map / tail bitmaps in BBTable::filter
+};
+
+// OR of x << d for d in [0, n), n <= 32
+__device__ __forceinline__ uint64_t smear_left64(uint64_t x, int n) {
+    int have = 1;
+    while (have < n) {
+        const int s = min(have, n - have);
+        x |= x << s;
+        have += s;
+    }
+    return x;
+}
+
+#if defined(BB_FAST_COUNT)
+__device__ unsigned long long bb_fast2_dbg[16];
+#define DBG2(i, v)                                                  \
+    do {                                                            \
+        const unsigned long long v_ = (unsigned long long)(v);      \
+        if (v_) atomicAdd(&bb_fast2_dbg[i], v_);                    \
+    } while (0)
+#else
+#define DBG2(i, v)
+#endif
+
+// PW11: the parts are 11 bases wide (k=23 hdist=1, k=23 mm=t hdist=0): the confirmation loops are unrolled for it
+template <int FMODE, bool PACKED, bool PW11>
+__global__ void __launch_bounds__(1024, 1)
+bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ offsets, int64_t n_reads, int paired, BBParams p,
+                   BBTable t, bbduk_out out, bbduk_stats *stats, unsigned long long *scaf_reads, unsigned long long *scaf_bases,
+                   int32_t *handoff, unsigned int *handoff_n, Fast2Geom geo, const uint32_t *__restrict__ pk_F,
+                   const uint16_t *__restrict__ pk_D) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const uint8_t *samp = reinterpret_cast<const uint8_t *>(smem);        // [65536] 8-mer byte map
+    const uint32_t *filt = smem + 16384;                                   // [BB_PART_WORDS] 9-mer bitmap
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *wbase = reinterpret_cast<uint8_t *>(smem + 16384 + BB_PART_WORDS) + (size_t)warp * geo.warp_bytes;
+    unsigned long long *first64 = reinterpret_cast<unsigned long long *>(wbase);  // [32] (pos<<32 | id) of the first hit
+    int *lastpos = reinterpret_cast<int *>(first64 + 32);                         // [32] last hit position
+    uint32_t *badw = reinterpret_cast<uint32_t *>(lastpos + 32);                  // [nbadw] chunks with a non-ACGTU base
+    uint32_t *Fs = badw + geo.nbadw;
+    uint16_t *Ds = reinterpret_cast<uint16_t *>(Fs + geo.nch + PAD + TAIL);
+    uint16_t *queue = Ds + ((geo.nch + PAD + TAIL + 1) & ~1);                     // [QCAP2] (owner lane << 11) | position
+    uint32_t *S = reinterpret_cast<uint32_t *>(queue + QCAP2);                    // [sw][32] seed bits, one column per lane
+
+    {
+        const uint32_t *src = t.filter + geo.samp_off;
+        for (uint32_t i = threadIdx.x; i < 16384u; i += blockDim.x) smem[i] = __ldg(src + i);
+        src = t.filter + geo.part_off;
+        for (uint32_t i = threadIdx.x; i < BB_PART_WORDS; i += blockDim.x) smem[16384 + i] = __ldg(src + i);
+    }
+    for (int i = lane; i < PAD; i += 32) {
+        Fs[i] = 0;
+        Ds[i] = 0;
+    }
+    __syncthreads();
+
+    const Stream st{Fs, Ds};
+    const int k = p.k;
+    const int pw = PW11 ? 11 : t.part_w;          // >= 11
+    const int n9 = 2 * pw - 16;                   // 9-mers around a sample hit that decide the parts containing it
+    const uint32_t amask = (1u << (pw - 7)) - 1u; // part ends a sample hit can discover
+    const int lag0 = t.part_lag[0], lag1 = t.part_lag[1], lag2 = t.part_lag[2], lag3 = t.part_lag[t.n_parts > 3 ? 3 : 2];
+    const uint32_t *tailb1 = t.filter + geo.tail_off;
+    const uint32_t *tailb2 = tailb1 + (t.tail_words >> 1);
+    const uintptr_t base_addr = PACKED ? (uintptr_t)0 : reinterpret_cast<uintptr_t>(bases);
+    const int64_t n_tiles = (n_reads + 31) >> 5;
+    const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    long long s_rk = 0, s_bk = 0, s_rf = 0, s_bf = 0, s_ro = 0, s_bo = 0, s_ri = 0, s_bi = 0;
+
+    for (int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; tile < n_tiles; tile += warps_total) {
+        const int64_t r = tile * 32 + lane;
+        const bool live = r < n_reads;
+        const uint32_t o0 = live ? offsets[r] : 0, o1 = live ? offsets[r + 1] : 0;
+        const uint32_t tile_lo = __shfl_sync(0xFFFFFFFFu, o0, 0);
+        const int last_lane = (int)min((long long)31, (long long)(n_reads - 1 - tile * 32));
+        const uint32_t tile_hi = __shfl_sync(0xFFFFFFFFu, o1, last_lane);
+        const uintptr_t a0 = (base_addr + tile_lo) & ~(uintptr_t)15;
+        const int nchunks = (int)((base_addr + tile_hi - a0 + 15) >> 4);
+        const int L = (int)(o1 - o0);
+        const int maxL = __reduce_max_sync(0xFFFFFFFFu, L);
+        if (nchunks > geo.nch || maxL > MAX_FAST_LEN || ((maxL + 16) >> 5) + 2 > geo.sw) {
+            // tile does not fit the staging: hand its units to the generic kernel
+            if (live && (!paired || !(lane & 1))) {
+                const unsigned int w = atomicAdd(handoff_n, 1u);
+                handoff[w] = (int32_t)(paired ? (r >> 1) : r);
+            }
+            continue;
+        }
+        // ---- A. stage + convert ---------------------------------------------------------------
+#pragma unroll 1
+        for (int i = lane; i < geo.nbadw; i += 32) badw[i] = 0;
+#pragma unroll 1
+        for (int i = lane; i < geo.sw * 32; i += 32) S[i] = 0;
+        __syncwarp();
+        const uint4 *src16 = reinterpret_cast<const uint4 *>(a0);
+        uint4 n1 = make_uint4(0, 0, 0, 0), n2 = make_uint4(0, 0, 0, 0);
+        if (!PACKED) {  // the ASCII loads run two trips ahead of their use
+            if (lane < nchunks) n1 = __ldg(src16 + lane);
+            if (lane + 32 < nchunks) n2 = __ldg(src16 + lane + 32);
+        }
+#pragma unroll 1
+        for (int c = lane; c < nchunks + TAIL; c += 32) {
+            const uint4 v = n1;
+            if (!PACKED) {
+                n1 = n2;
+                if (c + 64 < nchunks) n2 = __ldg(src16 + c + 64);
+            }
+            uint32_t f = 0, dbits = 0;
+            if (PACKED) {
+                if (c < nchunks) {
+                    f = __ldg(pk_F + (a0 >> 4) + c);
+                    dbits = __ldg(pk_D + (a0 >> 4) + c);
+                    if (dbits != 0xFFFFu) {
+                        f &= spread16(dbits);  // undefined bases read as code 0 (jgi/BBDuk.java:3882)
+                        atomicOr(badw + (c >> 5), 1u << (c & 31));
+                    }
+                }
+            } else if (c < nchunks) {
+                uint32_t cw[4], bw[4];
+                classify4(v.x, cw[0], bw[0]);
+                classify4(v.y, cw[1], bw[1]);
+                classify4(v.z, cw[2], bw[2]);
+                classify4(v.w, cw[3], bw[3]);
+                f = (pack4(cw[0]) << 24) | (pack4(cw[1]) << 16) | (pack4(cw[2]) << 8) | pack4(cw[3]);
+                dbits = 0xFFFFu;
+                if ((bw[0] | bw[1] | bw[2] | bw[3]) != 0) {  // rare: some base of the chunk is not ACGTU
+                    dbits = (valid4(bw[0]) << 12) | (valid4(bw[1]) << 8) | (valid4(bw[2]) << 4) | valid4(bw[3]);
+                    f &= spread16(dbits);  // undefined bases read as code 0 (jgi/BBDuk.java:3882)
+                    atomicOr(badw + (c >> 5), 1u << (c & 31));
+                }
+            }
+            Fs[c + PAD] = f;
+            Ds[c + PAD] = (uint16_t)dbits;
+        }
+        first64[lane] = ~0ull;
+        lastpos[lane] = -1;
+        __syncwarp();
+
+        const int s = live ? (int)(base_addr + o0 - a0) : 0;  // stream base of read position 0
+        const int pairnum = (paired && (lane & 1)) ? 1 : 0;
+        const bool skip = (p.skipR1 && pairnum == 0) || (p.skipR2 && pairnum == 1);
+        const bool scan = live && L >= k && t.stored > 0 && !skip;
+        bool has_undef = false;  // some chunk overlapping this read holds an undefined base
+        if (L > 0) {
+            const int c0 = s >> 4, c1 = (s + L - 1) >> 4;
+#pragma unroll 1
+            for (int w = c0 >> 5; w <= (c1 >> 5); w++) {
+                uint32_t m = badw[w];
+                if (w == (c0 >> 5)) m &= 0xFFFFFFFFu << (c0 & 31);
+                if (w == (c1 >> 5)) m &= 0xFFFFFFFFu >> (31 - (c1 & 31));
+                has_undef |= (m != 0);
+            }
+        }
+        const uint32_t undef_mask = __ballot_sync(0xFFFFFFFFu, has_undef);
+        // Windows with an undefined base. forbidNs: all of them go to the exact evaluator (force_und). Otherwise the forward
+        // k-mer reads the base as A and the reverse k-mer as the complement of T (x = x2 = 0, jgi/BBDuk.java:3882-3888), so
+        // key = max(kmer, rkmer) can only be in the table if the window passes the part test with its undefined bases read
+        // as A -- what the scan over F finds anyway -- or with all of them read as T. Only parts that CONTAIN an undefined
+        // base differ between the readings: for every undefined base (up to 4 per read, else force_und) one pooled item
+        // looks up the 2pw-9 9-mers around it in the T reading and adds the passing part ends to the seed bits.
+        bool force_und = has_undef && scan && p.forbidNs;
+        if (!p.forbidNs && __any_sync(0xFFFFFFFFu, has_undef && scan)) {
+            uint16_t *ntmp = queue + 256;  // [4][32] this lane's undefined positions
+            int n_und = 0;
+            if (has_undef && scan) {
+                const int c0 = s >> 4, c1 = (s + L - 1) >> 4;
+#pragma unroll 1
+                for (int w = c0 >> 5; w <= (c1 >> 5); w++) {
+                    uint32_t m = badw[w];
+                    if (w == (c0 >> 5)) m &= 0xFFFFFFFFu << (c0 & 31);
+                    if (w == (c1 >> 5)) m &= 0xFFFFFFFFu >> (31 - (c1 & 31));
+                    while (m) {
+                        const int c = 32 * w + __ffs(m) - 1;
+                        m &= m - 1;
+                        uint32_t ub = __brev(~(uint32_t)Ds[c + PAD]) >> 16;  // bit b = stream base 16c+b is undefined
+                        const int first = s - 16 * c, end = s + L - 16 * c;  // the read covers [first, end) of this chunk
+                        if (first > 0) ub &= 0xFFFFu << first;
+                        if (end < 16) ub &= (1u << end) - 1u;
+                        while (ub) {
+                            const int b = __ffs(ub) - 1;
+                            ub &= ub - 1;
+                            if (n_und < 4) ntmp[n_und * 32 + lane] = (uint16_t)(16 * c + b - s);
+                            n_und++;
+                        }
+                    }
+                }
+                if (n_und > 4) {
+                    force_und = true;
+                    n_und = 0;
+                }
+            }
+            int incl = n_und;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);  // <= 128
+            __syncwarp();
+            for (int c = 0; c < n_und; c++) queue[incl - n_und + c] = (uint16_t)(((uint32_t)lane << 11) + ntmp[c * 32 + lane]);
+            __syncwarp();
+            const int nT = 2 * pw - 9;
+#pragma unroll 1
+            for (int base = 0; base < total; base += 32) {
+                const bool on = base + lane < total;
+                const uint32_t ent = on ? queue[base + lane] : 0u;
+                const int owner = (int)(ent >> 11), u = (int)(ent & 0x7FFu);
+                const int s_owner = __shfl_sync(0xFFFFFFFFu, s, owner);
+                if (on) {
+                    const int e_hi = s_owner + u + pw - 1;
+                    const uint64_t W = st.win(e_hi) | ~spread2(st.dwin(e_hi));  // undefined bases read as T
+                    uint32_t B = 0;  // bit i = the 9-mer ending at read position u - (pw-9) + i passes in the T reading
+#pragma unroll 1
+                    for (int d = 0; d < nT; d++) {
+                        const uint32_t x = (uint32_t)(W >> (2 * d));
+                        const uint32_t fw = filt[bb_part_word(x)];
+                        B = __funnelshift_l(__funnelshift_r(fw, fw, x), B, 1);
+                    }
+                    uint32_t A = B;  // bit v = the part ending at read position u + v passes
+#pragma unroll 1
+                    for (int c = 1; c < pw - 8; c++) A &= B >> c;
+                    A &= (1u << pw) - 1u;
+                    if (A) {
+                        const int sh = u & 31;
+                        uint32_t *col = S + (u >> 5) * 32 + owner;
+                        atomicOr(col, A << sh);
+                        if (sh && (A >> (32 - sh)) && (u >> 5) + 1 < geo.sw) atomicOr(col + 32, A >> (32 - sh));
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        const bool any_force = __any_sync(0xFFFFFFFFu, force_und);
+
+        // ---- B1. sampled scan --------------------------------------------------------------------
+        // sample g of the read = the 8-mer that starts at stream byte 4*w0 - 1 + g (w0 = first stream word of the read);
+        // it counts if it lies inside the read: g in [glo, ghi]
+        const int w0 = s >> 4;
+        const int nw = scan ? ((s + L - 1) >> 4) - w0 + 1 : 0;  // stream words the read touches
+        const int nwmax = __reduce_max_sync(0xFFFFFFFFu, nw);
+        const int glo = ((s + 3) >> 2) - 4 * w0 + 1, ghi = ((s + L - 8) >> 2) - 4 * w0 + 1;  // L >= k >= 11 here
+#pragma unroll 1
+        for (int blk = 0; blk * L1_WORDS < nwmax; blk++) {
+            uint32_t acc_lo = 0, acc_hi = 0;  // sample bits 48*blk + [0, 32) and + [32, 48)
+            const int wb = w0 + blk * L1_WORDS;
+            const int left = nw - blk * L1_WORDS;  // this lane's words in the block
+            uint32_t fprev = Fs[PAD + wb - 1];
+#pragma unroll
+            for (int i = 0; i < L1_WORDS; i++) {
+                if (blk * L1_WORDS + i < nwmax) {  // warp-uniform
+                    const bool mine = i < left;
+                    const uint32_t f = mine ? Fs[PAD + wb + i] : 0u;
+                    const uint32_t x0 = __byte_perm(__funnelshift_l(f, fprev, 8), 0u, 0x4410);  // (last byte of the previous word, first of this)
+                    const uint32_t x1 = __byte_perm(f, 0u, 0x4432);
+                    const uint32_t x2 = __byte_perm(f, 0u, 0x4421);
+                    const uint32_t x3 = __byte_perm(f, 0u, 0x4410);
+                    uint32_t h = (uint32_t)samp[x0] + 2u * (uint32_t)samp[x1] + 4u * (uint32_t)samp[x2] + 8u * (uint32_t)samp[x3];
+                    if (!mine) h = 0;
+                    if (i < 8)
+                        acc_lo += h << (4 * i);
+                    else
+                        acc_hi += h << (4 * (i - 8));
+                    fprev = f;
+                }
+            }
+            // keep the samples inside the read
+            {
+                const int g0 = 48 * blk;
+                const int lo_ = max(glo - g0, 0), hi_ = min(ghi - g0, 47);
+                uint64_t vm = 0;
+                if (hi_ >= lo_) vm = ((hi_ >= 63 ? ~0ull : ((1ull << (hi_ + 1)) - 1ull)) >> lo_) << lo_;
+                acc_lo &= (uint32_t)vm;
+                acc_hi &= (uint32_t)(vm >> 32);
+            }
+            DBG2(1, __popc(acc_lo) + __popc(acc_hi));
+            // ---- B2. pooled confirmation of the sample hits against the 9-mer bitmap ----------------
+            while (__any_sync(0xFFFFFFFFu, (acc_lo | acc_hi) != 0u)) {
+                const int have = __popc(acc_lo) + __popc(acc_hi);
+                const int cnt = min(have, ITEM_CAP);
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                {
+                    int w = incl - cnt;
+                    // rel = stream position of the sample start minus s = 4 * (4*w0 - 1 + g) - s
+                    const int rel0 = 4 * (4 * w0 - 1 + 48 * blk) - s;
+#pragma unroll 1
+                    for (int c = 0; c < cnt; c++) {
+                        int g;
+                        if (acc_lo) {
+                            g = __ffs(acc_lo) - 1;
+                            acc_lo &= acc_lo - 1;
+                        } else {
+                            g = 32 + __ffs(acc_hi) - 1;
+                            acc_hi &= acc_hi - 1;
+                        }
+                        queue[w++] = (uint16_t)(((uint32_t)lane << 11) + (uint32_t)(rel0 + 4 * g));
+                    }
+                }
+                __syncwarp();
+#pragma unroll 1
+                for (int base = 0; base < total; base += 32) {
+                    DBG2(2, lane == 0);
+                    const bool on = base + lane < total;
+                    const uint32_t ent = on ? queue[base + lane] : 0u;
+                    const int owner = (int)(ent >> 11), rel = (int)(ent & 0x7FFu);
+                    const int s_owner = __shfl_sync(0xFFFFFFFFu, s, owner);
+                    if (on) {
+                        // 9-mers ending at stream positions e_hi - d, d = 0 .. n9-1, e_hi = sample start + pw - 1; bit i of B =
+                        // the 9-mer ending at (sample start + 16 - pw + i) is in the bitmap (rotating the filter word right by
+                        // the 9-mer leaves its bit in bit 31, one funnel shift pushes it into B: bbduk_dev.cuh)
+                        uint32_t B = 0;
+                        if (PW11) {
+                            const uint32_t w32 = st.f16(s_owner + rel + pw - 1 - 15);  // n9 = 6: 2*5 + 18 bits of the newest 16 bases
+#pragma unroll
+                            for (int d = 0; d < 6; d++) {
+                                const uint32_t x = w32 >> (2 * d);
+                                const uint32_t fw = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(filt) + ((x >> 3) & (4u * (BB_PART_WORDS - 1u))));
+                                B = __funnelshift_l(__funnelshift_r(fw, fw, x), B, 1);
+                            }
+                        } else {
+                            const uint64_t W = st.win(s_owner + rel + pw - 1);
+#pragma unroll 1
+                            for (int d = 0; d < n9; d++) {
+                                const uint32_t x = (uint32_t)(W >> (2 * d));
+                                const uint32_t fw = filt[bb_part_word(x)];
+                                B = __funnelshift_l(__funnelshift_r(fw, fw, x), B, 1);
+                            }
+                        }
+                        uint32_t A = B;  // bit u = the part ending at (sample start + 7 + u) passes: its pw-8 9-mers are all set
+                        if (PW11) {
+                            A = B & (B >> 1) & (B >> 2);
+                        } else {
+#pragma unroll 1
+                            for (int c = 1; c < pw - 8; c++) A &= B >> c;
+                        }
+                        A &= amask;
+                        if (A) {
+                            const int e0 = rel + 7;  // read-relative end of the u = 0 part
+                            const int sh = e0 & 31;
+                            uint32_t *col = S + (e0 >> 5) * 32 + owner;
+                            atomicOr(col, A << sh);
+                            if (sh && (A >> (32 - sh)) && (e0 >> 5) + 1 < geo.sw) atomicOr(col + 32, A >> (32 - sh));
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+
+        // ---- C. candidate windows, released in position order, evaluated exactly in pooled rounds --------
+        // first the candidate bits of every 32-position word, in place of the seed bits (descending, word c needs seed word c-1)
+        const int ncw = scan ? ((L + 31) >> 5) : 0;  // 32-position words of this read
+        {
+            const int ncwmax = __reduce_max_sync(0xFFFFFFFFu, ncw);
+            uint32_t und_c = 0;  // force_und: undefined bits of word c
+            auto und_word = [&](int c) -> uint32_t {  // bit b = read position 32c+b is undefined
+                if (c < 0 || c >= ncw) return 0u;
+                const uint32_t d = (st.d16(s + 32 * c) << 16) | st.d16(s + 32 * c + 16);  // bit 31-b = position 32c+b defined
+                uint32_t u = __brev(~d);
+                const int rem = L - 32 * c;
+                if (rem < 32) u &= (1u << rem) - 1u;
+                return u;
+            };
+            if (any_force && force_und) und_c = und_word(ncwmax - 1);
+#pragma unroll 1
+            for (int c = ncwmax - 1; c >= 0; c--) {
+                const uint32_t sc = S[c * 32 + lane], sp = c > 0 ? S[(c - 1) * 32 + lane] : 0u;
+                uint32_t cb = __funnelshift_l(sp, sc, lag0);
+                if (t.n_parts > 1) cb |= __funnelshift_l(sp, sc, lag1);
+                if (t.n_parts > 2) cb |= __funnelshift_l(sp, sc, lag2) | __funnelshift_l(sp, sc, lag3);
+                if (any_force) {  // rare: every window that contains an undefined base is decided by the exact evaluator
+                    if (force_und) {
+                        const uint32_t und_p = und_word(c - 1);
+                        cb |= (uint32_t)(smear_left64(((uint64_t)und_c << 32) | und_p, k) >> 32);
+                        und_c = und_p;
+                    }
+                }
+                // keep positions k-1 <= i < L
+                const int lowcut = min(max(k - 1 - 32 * c, 0), 32), hicut = min(max(L - 32 * c, 0), 32);
+                const uint32_t mlow = lowcut >= 32 ? 0u : (0xFFFFFFFFu << lowcut), mhigh = hicut >= 32 ? 0xFFFFFFFFu : ((1u << hicut) - 1u);
+                cb &= mlow & mhigh;
+                if (c >= ncw) cb = 0;
+                S[c * 32 + lane] = cb;
+            }
+        }
+        // A round: every read that still looks for its first hit puts its next R candidates (lowest positions first) into
+        // its own R slots of the queue, R = 8, 4, 2 or 1 by the number of such reads, so that a round never exceeds 32
+        // entries; unused slots hold 0xFFFF. One pooled evaluation per round.
+        auto drain = [&](int n_take) {  // queue[0 .. n_take): one entry per lane, n_take <= 32
+            DBG2(3, lane == 0);
+            const uint32_t ent = (lane < n_take) ? queue[lane] : 0xFFFFu;
+            DBG2(4, ent != 0xFFFFu);
+            const int owner = (int)(ent >> 11), pos = (int)(ent & 0x7FFu);
+            const int s_owner = __shfl_sync(0xFFFFFFFFu, s, owner);
+            if (ent != 0xFFFFu) {
+                const int id = exact_full(st, s_owner + pos, !((undef_mask >> owner) & 1u), p, t);
+                if (id > 0) {
+                    atomicMin(first64 + owner, ((unsigned long long)pos << 32) | (unsigned int)id);
+                    if (FMODE == FM_KTRIM_L) atomicMax(lastpos + owner, pos);
+                }
+            }
+            __syncwarp();
+        };
+        auto lg_share = [](int na) -> int { return (na > 16) ? 0 : (na > 8) ? 1 : (na > 4) ? 2 : 3; };
+
+        {
+            bool done = !scan;
+            int cw = -1;
+            uint32_t creg = 0;
+            while (true) {
+                if (!done) {
+                    while (creg == 0 && cw + 1 < ncw) {
+                        cw++;
+                        creg = S[cw * 32 + lane];
+                    }
+                }
+                const bool has = !done && creg != 0;
+                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, has);
+                if (!bal) break;
+                const int na = __popc(bal), lgR = lg_share(na);
+                if (has) {
+                    const int slot = __popc(bal & lt_mask) << lgR;
+                    const uint32_t tag = ((uint32_t)lane << 11) + 32u * (uint32_t)cw;
+#pragma unroll 1
+                    for (int c = 0; c < (1 << lgR); c++) {
+                        uint32_t e = 0xFFFFu;
+                        if (creg) {
+                            e = tag + (uint32_t)(__ffs(creg) - 1);
+                            creg &= creg - 1;
+                        }
+                        queue[slot + c] = (uint16_t)e;
+                    }
+                }
+                __syncwarp();
+                drain(na << lgR);
+                if (first64[lane] != ~0ull) done = true;  // everything still unreleased lies behind the confirmed hit
+            }
+        }
+
+        int found = 0, id0 = -1, minLoc = 999999999, maxLoc = -1, count = 0;
+        int lo = 0, hi = L;
+        bool discarded = false, ktrimmed = false;
+        {
+            const unsigned long long f64 = first64[lane];
+            if (scan && f64 != ~0ull) {
+                const int pos = (int)(f64 >> 32);
+                id0 = (int)(unsigned int)f64;
+                found = 1;
+                minLoc = pos - k + 1;
+                maxLoc = pos;
+            }
+        }
+        if (FMODE == FM_KTRIM_L) {
+            // ktrim=l also needs the LAST hit: release the candidates from the read end downwards until one beyond the
+            // forward phase's last confirmed hit is confirmed
+            const int firstpos = found ? max(maxLoc, lastpos[lane]) : -1;
+            bool bdone = !found;
+            int cw = ncw;
+            uint32_t creg = 0;
+            while (true) {
+                if (!bdone) {
+                    while (creg == 0 && cw > 0) {
+                        cw--;
+                        creg = S[cw * 32 + lane];
+                    }
+                    // nothing at or below the known hit matters
+                    if (32 * cw <= firstpos) {
+                        const int keep_from = firstpos + 1 - 32 * cw;  // positions >= firstpos+1
+                        creg = keep_from >= 32 ? 0u : (creg & (0xFFFFFFFFu << keep_from));
+                        if (creg == 0) bdone = true;
+                    }
+                }
+                const bool has = !bdone && creg != 0;
+                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, has);
+                if (!bal) break;
+                const int na = __popc(bal), lgR = lg_share(na);
+                if (has) {
+                    const int slot = __popc(bal & lt_mask) << lgR;
+                    const uint32_t tag = ((uint32_t)lane << 11) + 32u * (uint32_t)cw;
+#pragma unroll 1
+                    for (int c = 0; c < (1 << lgR); c++) {
+                        uint32_t e = 0xFFFFu;
+                        if (creg) {
+                            const int b = 31 - __clz(creg);
+                            e = tag + (uint32_t)b;
+                            creg &= ~(1u << b);
+                        }
+                        queue[slot + c] = (uint16_t)e;
+                    }
+                }
+                __syncwarp();
+                drain(na << lgR);
+                if (lastpos[lane] > firstpos) bdone = true;  // the highest hit of a round is the last hit of the read
+            }
+            if (found) maxLoc = max(firstpos, lastpos[lane]);
+        }
+
+        if (FMODE == FM_KFILTER) {  // countSetKmers with maxBadKmers==0 (jgi/BBDuk.java:3395-3457)
+            count = found;
+            discarded = found > 0;
+        } else {
+            // ---- T. short-k-mer tails (jgi/BBDuk.java:3910-3975) ---------------------------------------
+            // ktrim guard (:3868): reads shorter than k still get the tails
+            const bool tscan = live && t.stored > 0 && p.useShortKmers && L >= max(1, min(k, p.mink)) && !found && !skip;
+            int minLocX = 999999999, maxLocX = -1;
+            if (found) {
+                minLocX = minLoc + k;
+                maxLocX = maxLoc - k;
+            }
+            if (__any_sync(0xFFFFFFFFu, tscan)) {
+                // All tail k-mers of a read are sub-windows of ONE 32-base window: the suffix tails (ktrim=r) of the
+                // window ending at the last base, the prefix tails (ktrim=l) of the window ending at base min(k,L)-1.
+                // The tails read undefined bases as code 0 / complement 0 ("no N handling in tails").
+                const int nmax = (FMODE == FM_KTRIM_R) ? min(k - 1, L) : min(k, L);
+                const int nlo = max(p.mink, 1);
+                const int e = (FMODE == FM_KTRIM_R) ? (s + L - 1) : (s + nmax - 1);
+                uint64_t W = 0, RC = 0;
+                uint32_t todo = 0;  // bit n = the tail of n bases has to be looked up
+                if (tscan) {
+                    W = st.win(e);  // slot t = base e-t
+                    bool undef_here = false;
+                    if (has_undef) {
+                        const uint32_t dw = st.dwin(e);
+                        const uint32_t need = nmax >= 32 ? 0xFFFFFFFFu : ((1u << nmax) - 1u);
+                        undef_here = (dw & need) != need;
+                        const uint64_t E = spread2(dw);
+                        W &= E;
+                        RC = bb_rcomp(W, 32) & rev2(E, 32);
+                    } else {
+                        RC = bb_rcomp(W, 32);
+                    }
+                    const uint32_t all = (nmax >= nlo) ? ((nmax >= 31 ? 0xFFFFFFFFu : ((1u << (nmax + 1)) - 1u)) & ~((1u << nlo) - 1u)) : 0u;
+                    if (t.tail_words == 0 || undef_here) {
+                        todo = all;
+                    } else {
+                        const int q = t.tail_q;
+                        const uint32_t qm = (1u << (2 * q)) - 1u;  // q <= 12
+                        const int ntop = min(nmax, k - 1);
+                        // one bitmap (b_all) is tested once and decides all lengths, the other (b_len) once per length;
+                        // ktrim=r: b_all = type II on the read's last q bases, b_len = type I on read[L-n : L-n+q];
+                        // ktrim=l (mirror image): b_all = type I on read[0:q], b_len = type II on read[n-q : n]
+                        const uint32_t *b_all = (FMODE == FM_KTRIM_R) ? tailb2 : tailb1, *b_len = (FMODE == FM_KTRIM_R) ? tailb1 : tailb2;
+                        const uint32_t va = (FMODE == FM_KTRIM_R) ? ((uint32_t)W & qm) : ((uint32_t)(W >> (2 * max(nmax - q, 0))) & qm);
+                        const uint32_t wa = __ldg(b_all + (va >> 5));
+#pragma unroll 1
+                        for (int n = nlo; n <= ntop; n += 4) {  // four lookups in flight
+                            uint32_t v[4], wv[4];
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const int sh = (FMODE == FM_KTRIM_R) ? 2 * (n + j - q) : 2 * (nmax - n - j);
+                                v[j] = (uint32_t)(W >> (sh & 63)) & qm;
+                                wv[j] = (n + j <= ntop) ? __ldg(b_len + (v[j] >> 5)) : 0u;
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; j++) todo |= ((wv[j] >> (v[j] & 31u)) & 1u) << ((n + j) & 31);
+                        }
+                        if (nmax < q || ((wa >> (va & 31u)) & 1u)) todo = all;
+                        if (FMODE == FM_KTRIM_L && nmax == k) todo |= (k >= 31 ? 0x80000000u : (1u << k));  // a prefix of k bases is a full-length key
+                        todo &= all;
+                    }
+                    DBG2(5, __popc(todo));
+                }
+#pragma unroll 1
+                while (__any_sync(0xFFFFFFFFu, todo != 0u)) {
+                    if (todo) {
+                        const int n = __ffs(todo) - 1;  // ascending lengths, the reference's order
+                        todo &= todo - 1;
+                        const uint64_t nm = (1ull << (2 * n)) - 1ull;
+                        uint64_t kmer, rkmer;
+                        int i;
+                        if (FMODE == FM_KTRIM_R) {  // last n bases; reference loop index i = L-n
+                            kmer = W & nm;
+                            rkmer = RC >> (2 * (32 - n));
+                            i = L - n;
+                        } else {  // first n bases; reference loop index i = n-1
+                            kmer = (W >> (2 * (nmax - n))) & nm;
+                            rkmer = (RC >> (2 * (32 - nmax))) & nm;
+                            i = n - 1;
+                        }
+                        const uint64_t key = bb_to_value(p, kmer, rkmer, 1ull << (2 * n));
+                        const int id = bb_table_get(t, key);
+                        if (id > 0) {
+                            if (id0 < 0) id0 = id;
+                            if (FMODE == FM_KTRIM_R) {
+                                minLoc = i;
+                                minLocX = min(minLocX, L);
+                                maxLoc = L - 1;
+                                maxLocX = max(maxLocX, i - 1);
+                            } else {
+                                minLoc = 0;
+                                minLocX = min(minLocX, i + 1);
+                                maxLoc = max(maxLoc, i);
+                                maxLocX = max(maxLocX, 0);
+                            }
+                            found++;
+                        }
+                    }
+                }
+            }
+            if (found) {  // :3981-4012
+                if (p.trimPad != 0) {
+                    maxLoc = mid3(0, maxLoc + p.trimPad, L);
+                    minLoc = mid3(0, minLoc - p.trimPad, L);
+                    maxLocX = mid3(0, maxLocX + p.trimPad, L);
+                    minLocX = mid3(0, minLocX - p.trimPad, L);
+                }
+                if (FMODE == FM_KTRIM_L) {
+                    const int leftLoc = p.ktrimExclusive ? maxLocX + 1 : maxLoc + 1;
+                    count = trim_amounts(lo, hi, leftLoc, 0, 1);  // trimToPosition(r, leftLoc, L-1, 1)
+                } else {
+                    const int rightLoc = p.ktrimExclusive ? minLocX - 1 : minLoc - 1;
+                    count = trim_amounts(lo, hi, 0, L - rightLoc - 1, 1);
+                }
+                ktrimmed = count > 0;
+            }
+        }
+        if (live && id0 > 0 && scaf_reads) {
+            atomicAdd(scaf_reads + id0, 1ull);
+            atomicAdd(scaf_bases + id0, (unsigned long long)L);
+        }
+
+        // ---- D. per-read minlen, pair logic (jgi/BBDuk.java:2750-2813, :2844-2871), outputs ------
+        const bool active = live && t.stored > 0;  // doKmerTrimming / doKmerFiltering need stored k-mers
+        const int minlenR = (int)fmaxf(__fmul_rn((float)L, p.minLenFraction), (float)p.minReadLength);
+        const int len_pre = hi - lo;  // rlen1 / rlen2: captured before setDiscarded
+        if (active && (FMODE == FM_KFILTER ? discarded : (len_pre < minlenR))) {
+            // setDiscarded (jgi/BBDuk.java:3260-3266)
+            if (p.trimFailuresTo1bp) {
+                discarded = false;
+                if (hi - lo > 1) trim_amounts(lo, hi, 0, hi - lo - 1, 1);
+            } else {
+                discarded = true;
+            }
+        }
+        int len_cur = hi - lo;
+        const bool disc_eff = discarded || (p.trimFailuresTo1bp && len_cur == 1);
+        const bool disc_mate = __shfl_xor_sync(0xFFFFFFFFu, (int)disc_eff, 1) != 0;
+        const int len_pre_mate = __shfl_xor_sync(0xFFFFFFFFu, len_pre, 1);
+        const int len_cur_mate = __shfl_xor_sync(0xFFFFFFFFu, len_cur, 1);
+        const int cnt_mate = __shfl_xor_sync(0xFFFFFFFFu, count, 1);
+        const int L_mate = __shfl_xor_sync(0xFFFFFFFFu, L, 1);
+        const bool remove = paired ? (p.removePairsIfEitherBad ? (disc_eff || disc_mate) : (disc_eff && disc_mate)) : disc_eff;
+        bool tpe = false;
+        int x_tpe = 0;
+        if (FMODE == FM_KTRIM_R && paired && active && !remove && p.trimPairsEvenly && (count + cnt_mate) > 0 &&
+            len_cur > len_cur_mate) {
+            // the longer mate is cut to the shorter one's length: trimToPosition(longer, 0, shorterLen-1, 1)
+            x_tpe = trim_amounts(lo, hi, 0, len_cur - len_cur_mate, 1);
+            tpe = true;
+            len_cur = hi - lo;
+        }
+        const int x_tpe_mate = __shfl_xor_sync(0xFFFFFFFFu, x_tpe, 1);
+        const bool tpe_mate = __shfl_xor_sync(0xFFFFFFFFu, (int)tpe, 1) != 0;  // never inside a short-circuit
+        const bool tpe_pair = paired && (tpe || tpe_mate);
+        if (active && (!paired || !(lane & 1))) {  // one lane per unit accounts
+            if (FMODE != FM_KFILTER) {
+                int xsum = count + (paired ? cnt_mate : 0);
+                int rkt = (count > 0) + ((paired && cnt_mate > 0) ? 1 : 0);
+                if (remove) {
+                    xsum += len_pre + (paired ? len_pre_mate : 0);
+                    rkt = paired ? 2 : 1;
+                } else if (tpe_pair) {
+                    if (rkt < 2) rkt++;
+                    xsum += x_tpe + x_tpe_mate;
+                }
+                s_bk += xsum;
+                s_rk += rkt;
+            } else if (remove) {
+                s_rf += paired ? 2 : 1;
+                s_bf += L + (paired ? L_mate : 0);
+            }
+        }
+        if (live) {
+            s_ri += 1;
+            s_bi += L;
+            if (!remove) {
+                s_ro += 1;
+                s_bo += len_cur;
+            }
+            if (out.id0) out.id0[r] = id0;
+            if (out.id0b) out.id0b[r] = -1;
+            if (out.lo) out.lo[r] = lo;
+            if (out.hi) out.hi[r] = hi;
+            if (out.count) out.count[r] = count;
+            if (out.flags)
+                out.flags[r] = (uint8_t)((discarded ? BBDUK_F_DISCARDED : 0) | (remove ? BBDUK_F_REMOVED : 0) |
+                                         (ktrimmed ? BBDUK_F_KTRIMMED : 0) | (tpe ? BBDUK_F_TPE : 0));
+        }
+    }
+    if (stats) {
+        const unsigned int v[8] = {(unsigned int)s_ri, (unsigned int)s_bi, (unsigned int)s_rk, (unsigned int)s_bk,
+                                   (unsigned int)s_rf, (unsigned int)s_bf, (unsigned int)s_ro, (unsigned int)s_bo};
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const unsigned int x = __reduce_add_sync(0xFFFFFFFFu, v[q]);
+            if (lane == 0 && x) atomicAdd((unsigned long long *)stats + q, (unsigned long long)x);
+        }
+    }
+}
+
+Fast2Geom make_geom2(const BBTable &t, int max_read_len) {
+    Fast2Geom g;
+    const int lmax = std::max(max_read_len, 16);
+    g.nch = (32 * lmax + 15 + 15) / 16 + 1;
+    g.nbadw = (g.nch + 31) / 32 + 1;
+    g.sw = ((lmax + 16) >> 5) + 2;
+    int wb = 32 * 8 + 32 * 4 + g.nbadw * 4 + (g.nch + PAD + TAIL) * 4 + ((g.nch + PAD + TAIL + 1) & ~1) * 2 + QCAP2 * 2 + g.sw * 32 * 4;
+    wb = (wb + 15) & ~15;
+    g.warp_bytes = wb;
+    g.part_off = t.n_filter_words;
+    g.samp_off = t.n_filter_words + t.part_words + t.short_words;
+    g.tail_off = g.samp_off + t.samp_words;
+    const int avail = FAST_SMEM_LIMIT - (16384 + (int)BB_PART_WORDS) * 4 - 64;
+    g.warps = std::min(32, avail / wb);
+    return g;
+}
+
+}  // namespace
+
+#if defined(BB_FAST_COUNT)
+extern "C" __attribute__((visibility("default"))) int bbduk_b200_debug_fast2_counters(unsigned long long *out16, int reset) {
+    if (cudaMemcpyFromSymbol(out16, bb_fast2_dbg, sizeof(unsigned long long) * 16) != cudaSuccess) return 1;
+    if (reset) {
+        unsigned long long z[16] = {0};
+        if (cudaMemcpyToSymbol(bb_fast2_dbg, z, sizeof z) != cudaSuccess) return 1;
+    }
+    return 0;
+}
+#endif
+
+FastPlan plan_fast2(const BBParams &p, const BBTable &t, int max_read_len) {
+    FastPlan pl{false, max_read_len, 0, 0};
+    static const bool enabled = [] {
+        const char *e = getenv("BBDUK_B200_FAST2");
+        return !(e && atoi(e) == 0);
+    }();
+    if (!enabled) return pl;
+    const bool mode_ok = (p.mode == MODE_KTRIM) || (p.mode == MODE_KFILTER && p.maxBadKmers0 == 0);
+    if (!mode_ok) return pl;
+    if (p.qHammingDistance != 0 || (p.useShortKmers && p.qHammingDistance2 != 0)) return pl;
+    if (p.speed != 0 || p.qSkip != 1 || p.restrictLeft != 0 || p.restrictRight != 0) return pl;
+    if (p.kbig > p.k || p.minKmerFraction != 0.0f) return pl;
+    if (p.editDistance != 0 || t.part_words == 0 || t.n_parts < 1 || t.samp_words == 0 || t.part_w < 11) return pl;
+    if (max_read_len > MAX_FAST_LEN) max_read_len = MAX_FAST_LEN;
+    const Fast2Geom g = make_geom2(t, max_read_len);
+    if (g.warps < 8) return pl;
+    pl.usable = true;
+    pl.max_read_len = max_read_len;
+    pl.smem_bytes = (16384 + (int)BB_PART_WORDS) * 4 + g.warps * g.warp_bytes + 64;
+    pl.filter_words = 16384 + (int)BB_PART_WORDS;
+    return pl;
+}
+
+int launch_fast2(const FastPlan &plan, const uint8_t *d_bases, const uint32_t *d_offsets, int64_t n_reads, int paired,
+                 const BBParams &p, const BBTable &t, const bbduk_out &out, bbduk_stats *d_stats, unsigned long long *scaf_reads,
+                 unsigned long long *scaf_bases, int32_t *d_handoff, unsigned int *d_handoff_n, int sm_count, cudaStream_t st,
+                 const uint32_t *pk_F, const uint16_t *pk_D) {
+    const Fast2Geom g = make_geom2(t, plan.max_read_len);
+    const int threads = g.warps * 32;
+    const int64_t n_tiles = (n_reads + 31) / 32;
+    const int blocks = (int)std::min<int64_t>(sm_count, (n_tiles + g.warps - 1) / g.warps);
+    auto go = [&](auto kern) -> int {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes) != cudaSuccess) return -1;
+        kern<<<blocks, threads, plan.smem_bytes, st>>>(d_bases, d_offsets, n_reads, paired, p, t, out, d_stats, scaf_reads,
+                                                       scaf_bases, d_handoff, d_handoff_n, g, pk_F, pk_D);
+        return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    };
+    const bool pw11 = t.part_w == 11;
+#define BB_GO2(FM, PK) (pw11 ? go(bbduk_fast2_kernel<FM, PK, true>) : go(bbduk_fast2_kernel<FM, PK, false>))
+    if (pk_F) {
+        if (!pk_D) return -1;
+        if (p.mode == MODE_KFILTER) return BB_GO2(FM_KFILTER, true);
+        if (p.ktrimLeft) return BB_GO2(FM_KTRIM_L, true);
+        return BB_GO2(FM_KTRIM_R, true);
+    }
+    if (p.mode == MODE_KFILTER) return BB_GO2(FM_KFILTER, false);
+    if (p.ktrimLeft) return BB_GO2(FM_KTRIM_L, false);
+    return BB_GO2(FM_KTRIM_R, false);
+#undef BB_GO2
+}

@@ -36,7 +36,8 @@ struct Seed {
     uint64_t kmer;
     int32_t id;
     int8_t extra;  // next reference base (0..3) or -1; "extraBase" of jgi/BBDuk.java:2277
-    int8_t pad[3];
+    int8_t kind;   // short seeds: 1 = prefix of a scaffold's first k-mer, 2 = suffix of its last k-mer
+    int8_t pad[2];
 };
 
 // ---- pass 1: reference scan (jgi/BBDuk.java:2210-2288 addToMap(Read,skip)) --------------------------
@@ -96,6 +97,7 @@ __global__ void ref_seed_kernel(const uint8_t *__restrict__ bases, const int64_t
         sd.kmer = kmer;
         sd.id = id;
         sd.extra = (int8_t)extra;
+        sd.kind = 0;
         full_seeds[w] = sd;
     }
     if (p.useShortKmers) {
@@ -109,6 +111,7 @@ __global__ void ref_seed_kernel(const uint8_t *__restrict__ bases, const int64_t
                 sd.kmer = km;
                 sd.id = id;
                 sd.extra = (int8_t)eb;
+                sd.kind = 1;
                 short_seeds[(int64_t)n * cap_short + w] = sd;
             }
         }
@@ -120,6 +123,7 @@ __global__ void ref_seed_kernel(const uint8_t *__restrict__ bases, const int64_t
                 sd.kmer = km;
                 sd.id = id;
                 sd.extra = (int8_t)extra;
+                sd.kind = 2;
                 short_seeds[(int64_t)n * cap_short + w] = sd;
             }
         }
@@ -262,7 +266,8 @@ __global__ void short_filter_build_kernel(const uint64_t *__restrict__ keys, int
 
 // part filter: the part values of every full-length reference k-mer, both strands (if rcomp)
 __global__ void part_filter_build_kernel(const Seed *__restrict__ seeds, int64_t n, int k, int rcomp, int n_parts, int w,
-                                         int lag0, int lag1, int lag2, int lag3, uint32_t *filter, uint32_t n_words) {
+                                         int lag0, int lag1, int lag2, int lag3, uint32_t *filter, uint32_t n_words,
+                                         uint8_t *samp) {
     const int lags[4] = {lag0, lag1, lag2, lag3};
     const uint32_t vm = (w >= 16) ? 0xFFFFFFFFu : ((1u << (2 * w)) - 1u);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -275,8 +280,53 @@ __global__ void part_filter_build_kernel(const Seed *__restrict__ seeds, int64_t
                 for (int d = 0; d <= w - BB_PART_WD; d++) {  // every 9-mer of the part (bbduk_dev.cuh)
                     const uint32_t y = v >> (2 * d);
                     atomicOr(filter + bb_part_word(y), bb_part_bit(y));
+                    if (samp) {  // both 8-mers of the 9-mer: every 8-mer inside a part is covered (probe_fast2.cu)
+                        samp[(y >> 2) & 0xFFFFu] = 1;
+                        samp[y & 0xFFFFu] = 1;
+                    }
                 }
             }
+        }
+    }
+}
+
+// Tail bitmaps (probe_fast2.cu): the short k-mers are the prefixes S[0:n] of every scaffold's first k-mer and the suffixes
+// of its last k-mer, n = mink..k-1, each with its hdist2 substitution neighbourhood, stored canonically. A read's last n
+// bases can only match one of them if (type I) read[L-n : L-n+q] lies within hdist2 substitutions of the FIRST q bases of
+// a prefix string or of the reverse complement of a suffix string, or (type II) the read's last q bases lie within hdist2
+// of the LAST q bases of a suffix string or of the reverse complement of a prefix string (q = min(mink, 12); ktrim=l uses
+// the mirror image). B1 = bitmap of the type-I q-mers, B2 = of the type-II q-mers, each 4^q bits, direct-addressed.
+__device__ __forceinline__ void tail_set(uint32_t *bm, uint32_t v) { atomicOr(bm + (v >> 5), 1u << (v & 31u)); }
+__device__ void tail_ball(uint32_t *bm, uint32_t v, int q, int dist) {  // every q-mer within `dist` (<= 3) substitutions of v
+    tail_set(bm, v);
+    if (dist < 1) return;
+    for (int i = 0; i < q; i++)
+        for (uint32_t a = 1; a < 4; a++) {
+            const uint32_t v1 = v ^ (a << (2 * i));
+            tail_set(bm, v1);
+            if (dist < 2) continue;
+            for (int j = i + 1; j < q; j++)
+                for (uint32_t b = 1; b < 4; b++) {
+                    const uint32_t v2 = v1 ^ (b << (2 * j));
+                    tail_set(bm, v2);
+                    if (dist < 3) continue;
+                    for (int l = j + 1; l < q; l++)
+                        for (uint32_t c = 1; c < 4; c++) tail_set(bm, v2 ^ (c << (2 * l)));
+                }
+        }
+}
+__global__ void tail_filter_build_kernel(const Seed *__restrict__ seeds, int64_t n, int len, int q, int dist, int rcomp,
+                                         uint32_t *b1, uint32_t *b2) {
+    const uint32_t qm = (q >= 16) ? 0xFFFFFFFFu : ((1u << (2 * q)) - 1u);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const Seed sd = seeds[i];
+        const uint32_t first = (uint32_t)(sd.kmer >> (2 * (len - q))) & qm, last = (uint32_t)sd.kmer & qm;
+        if (sd.kind == 1) {
+            tail_ball(b1, first, q, dist);
+            if (rcomp) tail_ball(b2, (uint32_t)bb_rcomp(first, q), q, dist);
+        } else {
+            tail_ball(b2, last, q, dist);
+            if (rcomp) tail_ball(b1, (uint32_t)bb_rcomp(last, q), q, dist);
         }
     }
 }
@@ -339,6 +389,9 @@ BBTable DeviceTable::view() const {
     t.part_words = part_words;
     t.short_words = short_words;
     t.big_words = big_words;
+    t.samp_words = samp_words;
+    t.tail_words = tail_words;
+    t.tail_q = tail_q;
     t.n_parts = n_parts;
     t.part_w = part_w;
     for (int j = 0; j < 4; j++) t.part_lag[j] = part_lag[j];
@@ -448,8 +501,8 @@ int DeviceTable::build(const BBParams &p, const std::vector<uint8_t> &ref, const
     // pigeonhole part geometry (substitution neighbourhoods only): hdist+1 disjoint parts of w bases that
     // avoid the masked middle; part j ends lag[j] bases before the window end
     n_filter_words = filter_words;
-    part_words = short_words = 0;
-    n_parts = part_w = 0;
+    part_words = short_words = samp_words = tail_words = 0;
+    n_parts = part_w = tail_q = 0;
     if (!edits && dist_full <= 3 && n_full > 0) {
         const int P = dist_full + 1, k = p.k, mml = p.midMaskLen;
         int offs[4] = {0, 0, 0, 0}, w = 0;
@@ -476,6 +529,14 @@ int DeviceTable::build(const BBParams &p, const std::vector<uint8_t> &ref, const
             for (int j = 0; j < P; j++) part_lag[j] = k - offs[j] - w;
             part_words = pw;
             short_words = p.useShortKmers ? 16384 : 0;  // 64 KB: at 32 KB every third tail iteration of a warp went to the table for a false positive
+            // probe_fast2.cu: the sampled scan needs a part to hold a 4-aligned 8-mer whatever its phase (w >= 11)
+            samp_words = (w >= 11) ? 16384 : 0;  // 4^8 bytes
+            tail_q = 0;
+            tail_words = 0;
+            if (samp_words && p.useShortKmers && dist_short <= 3 && p.mink >= 1) {
+                tail_q = std::min(p.mink, 12);
+                tail_words = 2 * std::max<uint32_t>(1u, (1u << (2 * tail_q)) >> 5);
+            }
         }
     }
     if (alloc(slots, total_filter_words(), err, errlen)) {
@@ -487,7 +548,15 @@ int DeviceTable::build(const BBParams &p, const std::vector<uint8_t> &ref, const
     CKC(cudaMemsetAsync(d_filter, 0, sizeof(uint32_t) * total_filter_words(), st));
     if (part_words) {
         part_filter_build_kernel<<<296, 256, 0, st>>>(d_full, n_full, p.k, p.rcomp, n_parts, part_w, part_lag[0], part_lag[1],
-                                                      part_lag[2], part_lag[3], d_filter + n_filter_words, part_words);
+                                                      part_lag[2], part_lag[3], d_filter + n_filter_words, part_words,
+                                                      samp_words ? reinterpret_cast<uint8_t *>(d_filter + n_filter_words + part_words + short_words)
+                                                                 : nullptr);
+        (*launches)++;
+    }
+    if (tail_words) {
+        uint32_t *b1 = d_filter + n_filter_words + part_words + short_words + samp_words;
+        tail_filter_build_kernel<<<64, 64, 0, st>>>(d_short + (int64_t)(p.k - 1) * cap_short, (int64_t)h_cnt[1 + p.k - 1], p.k - 1,
+                                                    tail_q, dist_short, p.rcomp, b1, b1 + tail_words / 2);
         (*launches)++;
     }
 

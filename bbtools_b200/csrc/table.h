@@ -14,9 +14,11 @@ struct DeviceTable {
     int64_t n_slots = 0;
     uint32_t n_filter_words = 0;  // canonical bloom words; the buffer also holds part_words + short_words
     uint32_t part_words = 0, short_words = 0;
+    uint32_t samp_words = 0, tail_words = 0;  // probe_fast2.cu: 8-mer byte map, tail bitmaps (params.h)
+    int32_t tail_q = 0;
     uint32_t big_words = 0;  // L2-resident filter for HBM-resident arrays, last segment of d_filter
     int32_t n_parts = 0, part_w = 0, part_lag[4] = {0, 0, 0, 0};
-    uint32_t total_filter_words() const { return n_filter_words + part_words + short_words + big_words; }
+    uint32_t total_filter_words() const { return n_filter_words + part_words + short_words + samp_words + tail_words + big_words; }
     int32_t n_scaffolds = 0;
     int64_t stored = 0;     // distinct keys ("Added N kmers", jgi/BBDuk.java:1973)
     int64_t ref_kmers = 0;  // refKmers (jgi/BBDuk.java:1956)
