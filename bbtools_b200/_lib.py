@@ -5,7 +5,8 @@ import os
 from ._abi import ABI_VERSION, BBDukCfg, BBDukChainCfg, BBDukEntropyCfg, BBDukOut, BBDukQtrimCfg, BBDukStats, BBDukTableDesc, BBDukTboCfg
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbbduk_b200.so")
+# BBDUK_B200_LIB: another build of the same library (e.g. the -DBB_FAST_COUNT debug build, `make -C bbtools_b200/csrc debug`)
+LIB_PATH = os.environ.get("BBDUK_B200_LIB") or os.path.join(_HERE, "libbbduk_b200.so")
 
 # every symbol include/bbduk_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [

@@ -56,6 +56,16 @@ __device__ __forceinline__ uint64_t smear_left64(uint64_t x, int n) {
     return x;
 }
 
+// Out-of-line helpers: the per-tile loop has to fit the 32 KB instruction cache with 8 warps per scheduler in different
+// phases of it, so everything that runs a few times per tile at most is one shared copy behind a call.
+__device__ __noinline__ int warp_scan_incl(int v, int lane) {  // inclusive prefix sum over the warp
+#pragma unroll 1
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xFFFFFFFFu, v, o);
+        if (lane >= o) v += u;
+    }
+    return v;
+}
 #if defined(BB_FAST_COUNT)
 __device__ unsigned long long bb_fast2_dbg[16];
 #define DBG2(i, v)                                                  \
@@ -79,8 +89,9 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
     const uint32_t *filt = smem + 16384;                                   // [BB_PART_WORDS] 9-mer bitmap
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t *wbase = reinterpret_cast<uint8_t *>(smem + 16384 + BB_PART_WORDS) + (size_t)warp * geo.warp_bytes;
-    unsigned long long *first64 = reinterpret_cast<unsigned long long *>(wbase);  // [32] (pos<<32 | id) of the first hit
-    int *lastpos = reinterpret_cast<int *>(first64 + 32);                         // [32] last hit position
+    uint32_t *first32 = reinterpret_cast<uint32_t *>(wbase);                      // [32] (pos << 22 | id) of the first hit, ~0 = none
+    uint32_t *owners = first32 + 32;                                              // [32] evaluation rounds: lane of the rank-th releasing read
+    int *lastpos = reinterpret_cast<int *>(owners + 32);                          // [32] last hit position
     uint32_t *badw = reinterpret_cast<uint32_t *>(lastpos + 32);                  // [nbadw] chunks with a non-ACGTU base
     uint32_t *Fs = badw + geo.nbadw;
     uint16_t *Ds = reinterpret_cast<uint16_t *>(Fs + geo.nch + PAD + TAIL);
@@ -178,7 +189,7 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
             Fs[c + PAD] = f;
             Ds[c + PAD] = (uint16_t)dbits;
         }
-        first64[lane] = ~0ull;
+        first32[lane] = ~0u;
         lastpos[lane] = -1;
         __syncwarp();
 
@@ -235,13 +246,10 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
                     n_und = 0;
                 }
             }
-            int incl = n_und;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                if (lane >= o) incl += v;
-            }
+            const int incl = warp_scan_incl(n_und, lane);
             const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);  // <= 128
+            DBG2(7, lane == 0 ? total : 0);
+            DBG2(8, lane == 0);
             __syncwarp();
             for (int c = 0; c < n_und; c++) queue[incl - n_und + c] = (uint16_t)(((uint32_t)lane << 11) + ntmp[c * 32 + lane]);
             __syncwarp();
@@ -323,12 +331,7 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
             while (__any_sync(0xFFFFFFFFu, (acc_lo | acc_hi) != 0u)) {
                 const int have = __popc(acc_lo) + __popc(acc_hi);
                 const int cnt = min(have, ITEM_CAP);
-                int incl = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                    if (lane >= o) incl += v;
-                }
+                const int incl = warp_scan_incl(cnt, lane);
                 const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
                 {
                     int w = incl - cnt;
@@ -400,7 +403,8 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
 
         // ---- C. candidate windows, released in position order, evaluated exactly in pooled rounds --------
         // first the candidate bits of every 32-position word, in place of the seed bits (descending, word c needs seed word c-1)
-        const int ncw = scan ? ((L + 31) >> 5) : 0;  // 32-position words of this read
+        const int ncw = scan ? ((L + 31) >> 5) : 0;  // 32-position words of this read (<= 32)
+        uint32_t nzw = 0;                             // bit c = candidate word c is not empty
         {
             const int ncwmax = __reduce_max_sync(0xFFFFFFFFu, ncw);
             uint32_t und_c = 0;  // force_und: undefined bits of word c
@@ -432,59 +436,72 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
                 cb &= mlow & mhigh;
                 if (c >= ncw) cb = 0;
                 S[c * 32 + lane] = cb;
+                nzw |= (cb != 0u ? 1u : 0u) << c;
             }
         }
-        // A round: every read that still looks for its first hit puts its next R candidates (lowest positions first) into
-        // its own R slots of the queue, R = 8, 4, 2 or 1 by the number of such reads, so that a round never exceeds 32
-        // entries; unused slots hold 0xFFFF. One pooled evaluation per round.
-        auto drain = [&](int n_take) {  // queue[0 .. n_take): one entry per lane, n_take <= 32
+        // A round: the reads that still look for their first hit share the 32 lanes: with na such reads each gets R = 8, 4, 2
+        // or 1 lanes, lane j evaluates the (j mod R)-th lowest unreleased candidate of the (j div R)-th read. Nothing is
+        // queued: the evaluating lane fetches the owner's current candidate word by shuffle and skips to its own bit.
+        // down: highest candidates first (ktrim=l's search for the last hit).
+        auto round = [&](bool has, int cw, uint32_t &creg, bool down) -> bool {
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, has);
+            if (!bal) return false;
+            const int na = __popc(bal);
+            // (measured: giving each read floor(32/na) lanes instead of a power of two evaluates more candidates behind
+            // the first hit than it saves rounds: 2.09 vs 1.81 ms per 8.4 M cfg-2 reads)
+            // (a cap of 4 lanes changes nothing, 2 lanes cost 3 %, 1 lane 20 %)
+            const int lgR = (na > 16) ? 0 : (na > 8) ? 1 : (na > 4) ? 2 : 3;
             DBG2(3, lane == 0);
-            const uint32_t ent = (lane < n_take) ? queue[lane] : 0xFFFFu;
-            DBG2(4, ent != 0xFFFFu);
-            const int owner = (int)(ent >> 11), pos = (int)(ent & 0x7FFu);
+            DBG2(6, lane == 0 ? na : 0);
+            if (has) owners[__popc(bal & lt_mask)] = (uint32_t)lane;
+            __syncwarp();
+            const bool on = lane < (na << lgR);
+            const int owner = on ? (int)owners[lane >> lgR] : 0;
+            uint32_t x = __shfl_sync(0xFFFFFFFFu, creg, owner);
+            const int cw_o = __shfl_sync(0xFFFFFFFFu, cw, owner);
             const int s_owner = __shfl_sync(0xFFFFFFFFu, s, owner);
-            if (ent != 0xFFFFu) {
+            const int idx = lane & ((1 << lgR) - 1);
+            if (down) {
+#pragma unroll 1
+                for (int c = 0; c < idx && x; c++) x &= ~(0x80000000u >> __clz(x));
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < idx; c++) x &= x - 1;
+            }
+            if (on && x) {
+                DBG2(4, 1);
+                const int pos = 32 * cw_o + (down ? 31 - __clz(x) : __ffs(x) - 1);
                 const int id = exact_full(st, s_owner + pos, !((undef_mask >> owner) & 1u), p, t);
                 if (id > 0) {
-                    atomicMin(first64 + owner, ((unsigned long long)pos << 32) | (unsigned int)id);
+                    atomicMin(first32 + owner, ((uint32_t)pos << 22) | (uint32_t)id);
                     if (FMODE == FM_KTRIM_L) atomicMax(lastpos + owner, pos);
                 }
             }
+            if (has) {  // the candidates this round took
+                if (down) {
+#pragma unroll 1
+                    for (int c = 0; c < (1 << lgR) && creg; c++) creg &= ~(0x80000000u >> __clz(creg));
+                } else {
+#pragma unroll 1
+                    for (int c = 0; c < (1 << lgR) && creg; c++) creg &= creg - 1;
+                }
+            }
             __syncwarp();
+            return true;
         };
-        auto lg_share = [](int na) -> int { return (na > 16) ? 0 : (na > 8) ? 1 : (na > 4) ? 2 : 3; };
 
         {
             bool done = !scan;
-            int cw = -1;
+            int cw = 0;
             uint32_t creg = 0;
             while (true) {
-                if (!done) {
-                    while (creg == 0 && cw + 1 < ncw) {
-                        cw++;
-                        creg = S[cw * 32 + lane];
-                    }
+                if (!done && creg == 0 && nzw) {
+                    cw = __ffs(nzw) - 1;
+                    nzw &= nzw - 1;
+                    creg = S[cw * 32 + lane];
                 }
-                const bool has = !done && creg != 0;
-                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, has);
-                if (!bal) break;
-                const int na = __popc(bal), lgR = lg_share(na);
-                if (has) {
-                    const int slot = __popc(bal & lt_mask) << lgR;
-                    const uint32_t tag = ((uint32_t)lane << 11) + 32u * (uint32_t)cw;
-#pragma unroll 1
-                    for (int c = 0; c < (1 << lgR); c++) {
-                        uint32_t e = 0xFFFFu;
-                        if (creg) {
-                            e = tag + (uint32_t)(__ffs(creg) - 1);
-                            creg &= creg - 1;
-                        }
-                        queue[slot + c] = (uint16_t)e;
-                    }
-                }
-                __syncwarp();
-                drain(na << lgR);
-                if (first64[lane] != ~0ull) done = true;  // everything still unreleased lies behind the confirmed hit
+                if (!round(!done && creg != 0, cw, creg, false)) break;
+                if (first32[lane] != ~0u) done = true;  // everything still unreleased lies behind the confirmed hit
             }
         }
 
@@ -492,10 +509,10 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
         int lo = 0, hi = L;
         bool discarded = false, ktrimmed = false;
         {
-            const unsigned long long f64 = first64[lane];
-            if (scan && f64 != ~0ull) {
-                const int pos = (int)(f64 >> 32);
-                id0 = (int)(unsigned int)f64;
+            const uint32_t f32 = first32[lane];
+            if (scan && f32 != ~0u) {
+                const int pos = (int)(f32 >> 22);
+                id0 = (int)(f32 & 0x3FFFFFu);
                 found = 1;
                 minLoc = pos - k + 1;
                 maxLoc = pos;
@@ -506,41 +523,31 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
             // forward phase's last confirmed hit is confirmed
             const int firstpos = found ? max(maxLoc, lastpos[lane]) : -1;
             bool bdone = !found;
-            int cw = ncw;
+            // candidate words from the top; nothing at or below the known hit matters
+            uint32_t nzd = 0;
+            if (found) {
+#pragma unroll 1
+                for (int c = firstpos >> 5; c < ncw; c++) nzd |= (S[c * 32 + lane] != 0u ? 1u : 0u) << c;
+            }
+            int cw = 0;
             uint32_t creg = 0;
             while (true) {
-                if (!bdone) {
-                    while (creg == 0 && cw > 0) {
-                        cw--;
+                if (!bdone && creg == 0) {
+                    if (nzd) {
+                        cw = 31 - __clz(nzd);
+                        nzd &= ~(1u << cw);
                         creg = S[cw * 32 + lane];
-                    }
-                    // nothing at or below the known hit matters
-                    if (32 * cw <= firstpos) {
-                        const int keep_from = firstpos + 1 - 32 * cw;  // positions >= firstpos+1
-                        creg = keep_from >= 32 ? 0u : (creg & (0xFFFFFFFFu << keep_from));
-                        if (creg == 0) bdone = true;
-                    }
-                }
-                const bool has = !bdone && creg != 0;
-                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, has);
-                if (!bal) break;
-                const int na = __popc(bal), lgR = lg_share(na);
-                if (has) {
-                    const int slot = __popc(bal & lt_mask) << lgR;
-                    const uint32_t tag = ((uint32_t)lane << 11) + 32u * (uint32_t)cw;
-#pragma unroll 1
-                    for (int c = 0; c < (1 << lgR); c++) {
-                        uint32_t e = 0xFFFFu;
-                        if (creg) {
-                            const int b = 31 - __clz(creg);
-                            e = tag + (uint32_t)b;
-                            creg &= ~(1u << b);
+                        if (32 * cw <= firstpos) {
+                            const int keep_from = firstpos + 1 - 32 * cw;  // positions >= firstpos+1
+                            creg = keep_from >= 32 ? 0u : (creg & (0xFFFFFFFFu << keep_from));
                         }
-                        queue[slot + c] = (uint16_t)e;
                     }
+                    if (creg == 0 && nzd == 0) bdone = true;
                 }
-                __syncwarp();
-                drain(na << lgR);
+                if (!round(!bdone && creg != 0, cw, creg, true)) {
+                    if (!__any_sync(0xFFFFFFFFu, !bdone)) break;
+                    continue;
+                }
                 if (lastpos[lane] > firstpos) bdone = true;  // the highest hit of a round is the last hit of the read
             }
             if (found) maxLoc = max(firstpos, lastpos[lane]);
@@ -792,6 +799,7 @@ FastPlan plan_fast2(const BBParams &p, const BBTable &t, int max_read_len) {
     if (p.speed != 0 || p.qSkip != 1 || p.restrictLeft != 0 || p.restrictRight != 0) return pl;
     if (p.kbig > p.k || p.minKmerFraction != 0.0f) return pl;
     if (p.editDistance != 0 || t.part_words == 0 || t.n_parts < 1 || t.samp_words == 0 || t.part_w < 11) return pl;
+    if (t.n_scaffolds >= (1 << 22)) return pl;  // the first hit of a read is kept as (position << 22 | id) in one 32-bit word
     if (max_read_len > MAX_FAST_LEN) max_read_len = MAX_FAST_LEN;
     const Fast2Geom g = make_geom2(t, max_read_len);
     if (g.warps < 8) return pl;
