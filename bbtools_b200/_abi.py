@@ -60,7 +60,8 @@ class BBDukCfg(C.Structure):
         ("trim_failures_to_1bp", C.c_int32),
         ("device", C.c_int32),
         ("table_load_pct", C.c_int32),
-        ("reserved", C.c_int32 * 7),
+        ("minlen2", C.c_int32),
+        ("reserved", C.c_int32 * 6),
     ]
 
 

@@ -126,6 +126,8 @@ def parse_args(args, generation=GEN_JGI):
         elif a in ("mm", "maskmiddle"):
             if b is None or b[:1].isalpha():
                 cfg.mask_middle = _parse_boolean(b)
+                if not cfg.mask_middle:  # `mm=5 mm=f` ends with maskMiddle=false and midMaskLen=0 (bbduk/BBDukParser.java:232-236)
+                    cfg.mid_mask_len = 0
             else:
                 cfg.mid_mask_len = int(b)
                 cfg.mask_middle = int(b) > 0

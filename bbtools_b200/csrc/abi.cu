@@ -1431,6 +1431,35 @@ int bbduk_b200_replicate(bbduk_handle *src, const int32_t *device_ids, int32_t n
 
 int bbduk_b200_replica_transport(bbduk_handle *h) { return h ? h->replicated_via : -1; }
 
+int64_t bbduk_b200_ref_kmers(bbduk_handle *h) { return (h && h->finalized) ? h->table.ref_kmers : -1; }
+
+int bbduk_b200_table_export(bbduk_handle *h, uint64_t *keys, int32_t *ids, int64_t cap, int64_t *n_out) {
+    if (!h) return set_err(nullptr, "handle is NULL");
+    if (!h->finalized) return set_err(h, "table_export before finalize");
+    if (cap < 0 || (cap > 0 && (!keys || !ids))) return set_err(h, "bad table_export arguments");
+    CKH(cudaSetDevice(h->device));
+    CKH(cudaDeviceSynchronize());
+    int64_t n = 0;
+    const int64_t step = 1 << 22;  // slots per staging copy
+    std::vector<uint64_t> hk((size_t)std::min<int64_t>(step, h->table.n_slots));
+    std::vector<int32_t> hv(hk.size());
+    for (int64_t a = 0; a < h->table.n_slots; a += step) {
+        const int64_t m = std::min<int64_t>(step, h->table.n_slots - a);
+        CKH(cudaMemcpy(hk.data(), h->table.d_keys + a, sizeof(uint64_t) * (size_t)m, cudaMemcpyDeviceToHost));
+        CKH(cudaMemcpy(hv.data(), h->table.d_vals + a, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < m; i++) {
+            if (hk[i] == BB_EMPTY_KEY) continue;
+            if (n < cap) {
+                keys[n] = hk[i];
+                ids[n] = hv[i];
+            }
+            n++;
+        }
+    }
+    if (n_out) *n_out = n;
+    return 0;
+}
+
 int bbduk_b200_process_sharded(bbduk_handle **handles, int32_t n_handles, const uint8_t *bases, const int64_t *offsets,
                                int64_t n_reads, int32_t paired, const bbduk_out *out, bbduk_stats *stats) {
     if (!handles || n_handles < 1 || !handles[0]) return set_err(nullptr, "bad process_sharded arguments");

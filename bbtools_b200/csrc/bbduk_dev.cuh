@@ -36,8 +36,20 @@ __device__ __forceinline__ uint64_t bb_to_value(const BBParams &p, uint64_t kmer
     const uint64_t v = p.rcomp ? (kmer > rkmer ? kmer : rkmer) : kmer;
     return (v & p.middleMask) | lengthMask;
 }
-// (key & Long.MAX_VALUE) % 17 speed filter (jgi/BBDuk.java:4702-4713)
+// speed= filter. jgi.BBDuk (bbdukOld.sh): (key & Long.MAX_VALUE) % 17 >= speed (jgi/BBDuk.java:4702-4713). bbduk.BBDukS
+// (bbduk.sh) with its default index: speed < 2 || ((hash64plus2(key) >> 16) & 15) + 1 >= speed
+// (bbduk/BBDukIndexMask2.java:566-577, shared/Tools.java:5482-5497: MurmurHash3 finalizer, sign bit cleared, top values folded).
+__host__ __device__ __forceinline__ uint64_t bb_hash64plus2(uint64_t key) {
+    key ^= key >> 33;
+    key *= 0xff51afd7ed558ccdull;
+    key ^= key >> 33;
+    key *= 0xc4ceb9fe1a85ec53ull;
+    key ^= key >> 33;
+    key &= 0x7FFFFFFFFFFFFFFFull;
+    return key < 0x7FFFF800FFFFFFFFull ? key : (key - 0x7FFFF800FFFFFFFFull) * 64ull;
+}
 __device__ __forceinline__ bool bb_passes_speed(const BBParams &p, uint64_t key) {
+    if (p.speedMask2) return p.speed < 2 || (int)((bb_hash64plus2(key) >> 16) & 15ull) + 1 >= p.speed;
     return p.speed < 1 || (int)((key & 0x7FFFFFFFFFFFFFFFull) % 17ull) >= p.speed;
 }
 

@@ -45,6 +45,7 @@ int derive_params(const bbduk_cfg *c, BBParams *p, char *err, int errlen) {
     p->restrictLeft = std::max(c->restrict_left, 0);
     p->restrictRight = std::max(c->restrict_right, 0);
     p->speed = c->speed;
+    p->speedMask2 = (c->generation == BBDUK_GEN_S) ? 1 : 0;
     p->qSkip = c->qskip;
     p->skipR1 = c->skip_r1 != 0;
     p->skipR2 = c->skip_r2 != 0;
@@ -91,6 +92,10 @@ int derive_params(const bbduk_cfg *c, BBParams *p, char *err, int errlen) {
     p->minlen = k - 1;
     p->minminlen = p->mink - 1;
     p->minlen2 = mm ? (k - mml) / 2 : k;  // computed BEFORE useShortKmers switches maskMiddle off (:836 vs :849-856)
+    if (c->minlen2 > 0) {  // a host that marshals already-derived parser fields (java/bbduk/BBDukIndexGPU.java) hands in its own
+        if (c->minlen2 > k) return fail(err, errlen, "cfg.minlen2 must not exceed k");
+        p->minlen2 = c->minlen2;
+    }
     p->shift2 = 2 * k - 2;
     p->mask = (2 * k > 63) ? ~0ull : ~((~0ull) << (2 * k));
     p->kmask = 1ull << (2 * k);

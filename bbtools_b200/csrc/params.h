@@ -28,6 +28,7 @@ struct BBParams {
     int32_t minSkip, maxSkip;
     // query behaviour
     int32_t forbidNs, rcomp, speed, qSkip;
+    int32_t speedMask2;  // speed= follows bbduk.BBDukS's default index (hash bits 16-19, bbduk/BBDukIndexMask2.java:566-577) instead of jgi.BBDuk's key%17
     int32_t restrictLeft, restrictRight, skipR1, skipR2;
     int32_t mode;  // BBMode
     int32_t ktrimLeft, ktrimRight, ktrimExclusive, trimPad;

@@ -85,7 +85,11 @@ typedef struct bbduk_cfg {
     int32_t trim_failures_to_1bp; /* tossbrokenreads-style "trimfailuresto1bp" (jgi/BBDuk.java:3260-3266) */
     int32_t device;               /* CUDA device ordinal; -1 = current device */
     int32_t table_load_pct;       /* device table load factor in percent (layout only, no effect on results); 0 -> 50 */
-    int32_t reserved[7];
+    int32_t minlen2;              /* 0 = derive it. > 0: the caller has derived its constants already and hands in ITS minlen2:
+                                     bbduk/BBDukParser.java:276 computes minlen2 from maskMiddle BEFORE useShortKmers / kbig>k
+                                     switch maskMiddle off (:239-242, :290-294), so a host that marshals the parser's final
+                                     maskMiddle / midMaskLen could not reproduce it (forbidNs and the distances are idempotent) */
+    int32_t reserved[6];
 } bbduk_cfg;
 
 /* per-read flag bits written to bbduk_out.flags */
@@ -231,6 +235,14 @@ BBDUK_API int bbduk_b200_process_sharded(bbduk_handle **handles, int32_t n_handl
 /* Per-scaffold hit counts summed over the handles of a replica set. */
 BBDUK_API int bbduk_b200_scaffold_counts_sum(bbduk_handle **handles, int32_t n_handles, int64_t *read_counts,
                                              int64_t *base_counts, int32_t n);
+
+/* Replaces: AbstractKmerTable.dumpKmersAsBytes behind BBDukIndex.dump (bbduk/BBDukIndex.java:77, bbduk/BBDukLoader.java:161-166):
+ * copies the stored (key, scaffold id) pairs to HOST arrays of `cap` entries, in table order (compare as a set). The key
+ * carries its length marker (toValue, bbduk/BBDukIndexMask2.java:533-545). *n_out = number of stored keys; entries beyond
+ * cap are not written (call with cap = stored_kmers). */
+BBDUK_API int bbduk_b200_table_export(bbduk_handle *h, uint64_t *keys, int32_t *ids, int64_t cap, int64_t *n_out);
+/* refKmers of the finished table (the loader's count of reference k-mers seen, bbduk/BBDukLoader.java:461). */
+BBDUK_API int64_t bbduk_b200_ref_kmers(bbduk_handle *h);
 
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 BBDUK_API int64_t bbduk_b200_launch_count(bbduk_handle *h);

@@ -150,6 +150,7 @@ struct ora {
     int hammingDistance, hammingDistance2, editDistance, editDistance2, qHammingDistance, qHammingDistance2;
     int minSkip, maxSkip, forbidNs, rcomp;
     int restrictLeft, restrictRight, speed, qSkip, skipR1, skipR2;
+    int speedMask2; /* generation == BBDUK_GEN_S: the speed= rule of bbduk/BBDukIndexMask2.java */
     int ktrimLeft, ktrimRight, ktrimN, ksplit, ktrimExclusive, kfilter, trimPad;
     int findBestMatch, kmaskFullyCovered, kmaskLowercase, trimSymbol;
     int maxBadKmers0, removePairsIfEitherBad, trimPairsEvenly, trimFailuresTo1bp;
@@ -226,6 +227,7 @@ struct ora *ora_create(const bbduk_cfg *c) {
     o->restrictRight = imax(c->restrict_right, 0);
     o->findBestMatch = c->find_best_match; /* rename is host-side; (rename || findBestMatch_) */
     o->speed = c->speed;
+    o->speedMask2 = (c->generation == BBDUK_GEN_S);
     o->qSkip = c->qskip;
     o->skipR1 = c->skip_r1;
     o->skipR2 = c->skip_r2;
@@ -288,6 +290,7 @@ struct ora *ora_create(const bbduk_cfg *c) {
     o->minlen = o->k - 1;
     o->minminlen = o->mink - 1;
     o->minlen2 = (o->maskMiddle ? (o->k - o->midMaskLen) / 2 : o->k); /* note: before usk disables mm */
+    if (c->minlen2 > 0 && c->minlen2 <= o->k) o->minlen2 = c->minlen2; /* include/bbduk_b200.h: a host's own derived value */
     o->shift = 2 * o->k;
     o->shift2 = o->shift - 2;
     o->mask = (o->shift > 63 ? -1LL : ~(jlong)(((ulong64)-1LL) << o->shift));
@@ -354,11 +357,24 @@ static inline jlong toValue(const struct ora *o, jlong kmer, jlong rkmer, jlong 
 }
 /* :4693-4695 */
 static inline jlong rcomp_(jlong kmer, int len) { return reverseComplementBinaryFast(kmer, len); }
-/* :4702-4713 */
+/* shared/Tools.java:5482-5497 hash64plus2 (MurmurHash3 finalizer, sign bit cleared, the top values folded) */
+static inline jlong hash64plus2(jlong key0) {
+    ulong64 key = (ulong64)key0;
+    key ^= key >> 33;
+    key *= 0xff51afd7ed558ccdULL;
+    key ^= key >> 33;
+    key *= 0xc4ceb9fe1a85ec53ULL;
+    key ^= key >> 33;
+    key &= 0x7FFFFFFFFFFFFFFFULL;
+    return (jlong)(key < 0x7FFFF800FFFFFFFFULL ? key : (key - 0x7FFFF800FFFFFFFFULL) * 64ULL);
+}
+/* jgi.BBDuk :4702-4713 (key%17); bbduk.BBDukS's default index bbduk/BBDukIndexMask2.java:566-577 (hash bits 16-19) */
 static inline int passesSpeed(const struct ora *o, jlong key) {
+    if (o->speedMask2) return o->speed < 2 || (((hash64plus2(key) >> 16) & 15) + 1) >= o->speed;
     return o->speed < 1 || ((key & INT64_MAX) % 17) >= o->speed;
 }
 static inline int failsSpeed(const struct ora *o, jlong key) {
+    if (o->speedMask2) return o->speed > 1 && (((hash64plus2(key) >> 16) & 15) + 1) < o->speed;
     return o->speed > 0 && ((key & INT64_MAX) % 17) < o->speed;
 }
 
