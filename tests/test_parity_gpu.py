@@ -63,6 +63,8 @@ MODES = [
     dict(k=40),                                                             # k>31 -> countSetKmersBig
     dict(k=23, qhdist=1, ktrim_right=1),
     dict(k=20, speed=5),
+    dict(k=20, speed=5, generation=1),                                      # bbduk.BBDukS speed= rule (hash bits 16-19)
+    dict(k=23, speed=9, generation=1, ktrim_right=1),
     dict(k=20, qskip=3, ktrim_right=1),
     dict(k=19, rcomp=0, ktrim_right=1, mid_mask_len=3),
     dict(k=27, hdist=2, ktrim_right=1),                                     # cfg 4 table (8.4 M keys)

@@ -60,6 +60,7 @@ if "--phases" in sys.argv:
             marks.append((i, "C-ktriml"))
     marks.sort()
     ph = {}
+    phs = {}
     for (f, ln), v in agg.items():
         if f == "probe_fast2.cu":
             name = "setup"
@@ -73,6 +74,7 @@ if "--phases" in sys.argv:
         else:
             name = f
         ph[name] = ph.get(name, 0) + v[0]
+        phs[name] = phs.get(name, 0) + v[1]
     print("--- phases")
     for k_, v in sorted(ph.items(), key=lambda kv: -kv[1]):
-        print(f"{v / tiles:8.1f} {100 * v / tot:5.1f}%  {k_}")
+        print(f"{v / tiles:8.1f} {100 * v / tot:5.1f}%  samples {100 * phs[k_] / max(tots, 1):5.1f}%  {k_}")
