@@ -61,7 +61,7 @@ def _small_ref():
     return ["ACGTTGCATGGATCCAGTACGATTACAGGCAT", "TTGACCAGTNNACGGATACCATGACGTTAGCAAT", "GATTACA"]
 
 
-def _reads(rng, refs, n, maxlen=60):
+def _reads(rng, refs, n, maxlen=60, fragmax=30):
     out = []
     alpha = "ACGT" * 10 + "NnacgtRY"
     for _ in range(n):
@@ -70,7 +70,7 @@ def _reads(rng, refs, n, maxlen=60):
         if L > 6 and rng.random() < 0.7:
             r = refs[int(rng.integers(0, len(refs)))]
             a = int(rng.integers(0, len(r) - 4))
-            frag = r[a:a + int(rng.integers(4, 30))]
+            frag = r[a:a + int(rng.integers(4, fragmax))]
             if rng.random() < 0.4:
                 frag = "".join({"A": "T", "C": "G", "G": "C", "T": "A"}.get(c, c) for c in reversed(frag))
             pos = int(rng.integers(0, L))
@@ -230,3 +230,150 @@ def test_undefined_bases_inside_reference_fragments(case):
         assert (out.lo[i], out.hi[i], out.id0[i]) == (lo, hi, id0), (i, s)
     if not case.get("fn") and case["hdist"] > 0:
         assert hits > len(reads) // 3  # the cases do exercise hits through windows with undefined bases
+
+
+# ---- the modes and query options served only by the generic GPU kernel, against the closed form --------------------
+def _long_ref():
+    rng = np.random.default_rng(23)
+    return ["".join("ACGT"[int(x)] for x in rng.integers(0, 4, n)) for n in (70, 55, 90, 64)] + _small_ref()[1:2]
+
+
+def _cf_pair(refs, n_reads, maxlen, seed, gen=0, trimming=True, fragmax=30, **case):
+    rng = np.random.default_rng(seed)
+    reads = _reads(rng, refs, n_reads, maxlen, fragmax)
+    d = cf.Derived(k=case["k"], mink=case.get("mink", -1), hdist=case.get("hdist", 0), mm=case.get("mm", True),
+                   rcomp=case.get("rcomp", True), fn=case.get("fn", False), generation=gen, qhdist=case.get("qhdist", 0),
+                   qskip=case.get("qskip", 1), speed=case.get("speed", 0), trimming=trimming)
+    table = cf.build_table(d, refs)
+    rb, ro = pack([r.encode() for r in refs])
+    qb, qo = pack([r.encode() for r in reads])
+    common = dict(k=case["k"], mink=case.get("mink", -1), hdist=case.get("hdist", 0), mask_middle=int(case.get("mm", True)),
+                  rcomp=int(case.get("rcomp", True)), forbid_ns=int(case.get("fn", False)), min_read_length=0,
+                  qhdist=case.get("qhdist", 0), qskip=case.get("qskip", 1), speed=case.get("speed", 0), generation=gen)
+
+    def run(**mode):
+        o = Oracle(make_cfg(**common, **mode))
+        o.add_ref(rb, ro)
+        n = o.finalize()
+        keys, vals = o.dump_table()
+        assert n == len(table) and dict(zip((int(x) for x in keys), (int(x) for x in vals))) == table
+        return o.process(qb, qo, False)[0]
+
+    return d, table, reads, run
+
+
+QUERY_CASES = [
+    dict(k=11, hdist=0, mm=True, qhdist=1),
+    dict(k=11, hdist=0, mm=False, qhdist=1, rcomp=False),
+    dict(k=9, mink=5, hdist=0, qhdist=1),
+    dict(k=11, hdist=1, qskip=3),
+    dict(k=11, hdist=1, speed=5),
+    dict(k=11, hdist=1, speed=5, gen=1),
+    dict(k=11, hdist=0, mm=False, speed=12, gen=1),
+    dict(k=11, hdist=1, speed=9, fn=True),
+]
+
+
+@pytest.mark.parametrize("case", QUERY_CASES, ids=lambda c: ",".join(f"{a}={b}" for a, b in c.items()))
+def test_closed_form_query_options(case):
+    """qhdist (the reference's symbol-major, slot-minor depth-first order, first hit wins), qskip and both speed= rules,
+    through ktrim=r and kfilter."""
+    case = dict(case)
+    gen = case.pop("gen", 0)
+    d, table, reads, run = _cf_pair(_small_ref(), 160, 60, 31, gen=gen, **case)
+    out = run(ktrim_right=1)
+    for i, s in enumerate(reads):
+        L = len(s)
+        want_hi, want_id = L, -1
+        if L >= max(1, min(d.k, d.mink) if d.usk else d.k) and table:
+            hits = [(j, cf.probe(d, table, s, j)) for j in range(L)]
+            hits = [(j, h) for j, h in hits if h is not None and h > 0]
+            if hits:
+                want_id = hits[0][1]
+                _, want_hi = cf.trim_by_amount(L, 0, L - (min(j - d.k + 1 for j, _ in hits) - 1) - 1)
+            elif d.usk:
+                found = [(L - n, cf.tail_probe(d, table, s[L - n:], L - n)) for n in range(d.mink, min(d.k - 1, L) + 1)]
+                found = [(j, h) for j, h in found if h > 0]
+                if found:
+                    want_id = found[0][1]
+                    _, want_hi = cf.trim_by_amount(L, 0, L - (found[-1][0] - 1) - 1)
+        assert (out.hi[i], out.id0[i]) == (want_hi, want_id), (i, s)
+    if "mink" not in case:
+        out = run()
+        for i, s in enumerate(reads):
+            cnt, cid = 0, -1
+            if len(s) >= d.k and table:
+                for j in range(len(s)):
+                    h = cf.probe(d, table, s, j)
+                    if h is not None and h > 0:
+                        cnt, cid = 1, h
+                        break
+            assert (out.count[i], out.id0[i]) == (cnt, cid), (i, s)
+
+
+@pytest.mark.parametrize("case", [dict(k=11, hdist=1), dict(k=11, mink=5, hdist=1), dict(k=9, mink=4, hdist=0), dict(k=11, hdist=0, fn=True),
+                                  dict(k=11, hdist=1, mm=False, rcomp=False), dict(k=11, hdist=0, qhdist=1)],
+                         ids=lambda c: ",".join(f"{a}={b}" for a, b in c.items()))
+def test_closed_form_ktrim_tips(case):
+    """ktrimTips: two passes split at the original middle, the left one over what the right one left; windows that straddle
+    the start of a pass read the unseen bases as zero bits (jgi/BBDuk.java:3686-3858)."""
+    d, table, reads, run = _cf_pair(_small_ref(), 300, 70, 37, **case)
+    out = run(ktrim_left=1, ktrim_right=1)
+    nz = 0
+    for i, s in enumerate(reads):
+        lo, hi, id_r, id_l, x = cf.ktrim_tips(d, table, s)
+        ids = [j for j in (id_r, id_l) if j > 0] + [-1, -1]
+        assert (out.lo[i], out.hi[i], out.id0[i], out.id0b[i], out.count[i]) == (lo, hi, ids[0], ids[1], x), (i, s)
+        nz += x > 0
+    assert nz > 30
+    out = run(ktrim_left=1, ktrim_right=1, restrict_left=25, restrict_right=20)
+    for i, s in enumerate(reads):
+        lo, hi, id_r, id_l, x = cf.ktrim_tips(d, table, s, 25, 20)
+        assert (out.lo[i], out.hi[i], out.count[i]) == (lo, hi, x), (i, s)
+
+
+@pytest.mark.parametrize("case", [dict(k=11, hdist=1), dict(k=11, mink=5, hdist=1), dict(k=9, mink=4, hdist=0, fn=True)],
+                         ids=lambda c: ",".join(f"{a}={b}" for a, b in c.items()))
+def test_closed_form_ksplit(case):
+    d, table, reads, run = _cf_pair(_small_ref(), 300, 70, 41, **case)
+    out = run(ksplit=1)
+    n_split = 0
+    for i, s in enumerate(reads):
+        lo, hi, split, at, id0 = cf.ksplit(d, table, s)
+        assert (out.lo[i], out.hi[i], bool(out.flags[i] & 16), out.id0[i]) == (lo, hi, split, id0), (i, s)
+        if split:
+            assert out.count[i] == at
+            n_split += 1
+    assert n_split > 10
+
+
+@pytest.mark.parametrize("case", [dict(k=11, hdist=0), dict(k=11, hdist=1, mm=False), dict(k=11, hdist=0, fn=True, qskip=2)],
+                         ids=lambda c: ",".join(f"{a}={b}" for a, b in c.items()))
+def test_closed_form_covered_bases_and_best_match(case):
+    d, table, reads, run = _cf_pair(_small_ref(), 250, 70, 43, trimming=False, **case)
+    frac = 0.3
+    out = run(min_covered_fraction=frac)
+    for i, s in enumerate(reads):
+        need = int(np.ceil(float(np.float32(frac) * np.float32(len(s)))))
+        cnt, cid = cf.covered_bases(d, table, s, need)
+        assert (out.count[i], out.id0[i], bool(out.flags[i] & 1)) == (cnt, cid, cnt >= need), (i, s)  # an empty read needs 0 bases and is discarded, as in the reference
+    out = run(find_best_match=1)
+    for i, s in enumerate(reads):
+        bid = cf.best_match(d, table, s)
+        assert (out.count[i], out.id0[i], bool(out.flags[i] & 1)) == (bid, bid, bid > 0), (i, s)
+
+
+@pytest.mark.parametrize("case,mb", [(dict(k=36, hdist=0), 0), (dict(k=40, hdist=0), 2), (dict(k=33, hdist=1, fn=True), 0)],
+                         ids=["k=36", "k=40,mbk=2", "k=33,hdist=1,fn"])
+def test_closed_form_count_big(case, mb):
+    """k > 31: runs of consecutive 31-mer hits (jgi/BBDuk.java:3596-3677)."""
+    refs = _long_ref()
+    d, table, reads, run = _cf_pair(refs, 400, 110, 47, trimming=False, fragmax=95, **case)
+    assert d.kbig == case["k"] and d.k == 31
+    out = run(max_bad_kmers=mb)
+    n_hit = 0
+    for i, s in enumerate(reads):
+        cnt, cid = cf.count_big(d, table, s, mb)
+        assert (out.count[i], out.id0[i], bool(out.flags[i] & 1)) == (cnt, cid, cnt > mb), (i, s)
+        n_hit += cnt > 0
+    assert n_hit > 5
