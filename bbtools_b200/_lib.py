@@ -27,11 +27,14 @@ SYMBOLS = [
     ("bbduk_b200_table_commit", C.c_int, [C.c_void_p]),
     ("bbduk_b200_replicate", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     ("bbduk_b200_replica_transport", C.c_int, [C.c_void_p]),
+    ("bbduk_b200_process_packed", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                            C.POINTER(BBDukOut), C.POINTER(BBDukStats)]),
     ("bbduk_b200_process_sharded", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                              C.POINTER(BBDukOut), C.POINTER(BBDukStats)]),
     ("bbduk_b200_scaffold_counts_sum", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]),
     ("bbduk_b200_table_export", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     ("bbduk_b200_ref_kmers", C.c_int64, [C.c_void_p]),
+    ("bbduk_b200_transfer_bytes", C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     ("bbduk_b200_launch_count", C.c_int64, [C.c_void_p]),
     ("bbduk_b200_last_error", C.c_char_p, [C.c_void_p]),
     ("bbduk_b200_destroy", None, [C.c_void_p]),

@@ -439,6 +439,29 @@ class BBDukIndexGPU:
                                                 C.byref(o), C.byref(st)), "process")
         return out, st
 
+    def pack(self, bases):
+        """the 2-bit stream F and the defined bits D of concatenated ASCII bases (bbduk_b200_pack_bases), as a packing parser would hold them"""
+        bases = np.ascontiguousarray(bases, np.uint8)
+        g = (len(bases) + 15) // 16
+        F = np.zeros(g + 16, np.uint32)
+        D = np.zeros(g + 32, np.uint16)
+        self._check(self.lib.bbduk_b200_pack_bases(bases.ctypes.data, len(bases), F.ctypes.data, D.ctypes.data), "pack_bases")
+        return F, D
+
+    def process_packed(self, F, D, offsets, paired, out=None):
+        """HOST 2-bit stream + defined bits in, host struct-of-arrays out (bbduk_b200_process_packed)."""
+        F = np.ascontiguousarray(F, np.uint32)
+        D = np.ascontiguousarray(D, np.uint16)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        n = len(offsets) - 1
+        if out is None:
+            out = Outputs(n, np.diff(offsets))
+        st = BBDukStats()
+        o = out.struct()
+        self._check(self.lib.bbduk_b200_process_packed(self.h, F.ctypes.data, D.ctypes.data, offsets.ctypes.data, n,
+                                                       int(bool(paired)), C.byref(o), C.byref(st)), "process_packed")
+        return out, st
+
     def process_device(self, d_bases, d_offsets, n_reads, paired, d_out, d_stats=None, stream=None):
         """DEVICE buffers (torch tensors or raw pointers); d_out: dict name -> tensor/pointer."""
         def ptr(x):
@@ -580,6 +603,12 @@ class BBDukIndexGPU:
         bc = np.zeros(n, np.int64)
         self._check(self.lib.bbduk_b200_scaffold_counts(self.h, rc_.ctypes.data, bc.ctypes.data, n), "scaffold_counts")
         return rc_, bc
+
+    def transfer_bytes(self):
+        """(host->device, device->host) bytes process() / process_packed() have moved so far"""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.bbduk_b200_transfer_bytes(self.h, C.byref(a), C.byref(b)), "transfer_bytes")
+        return a.value, b.value
 
     @property
     def launches(self):

@@ -67,6 +67,7 @@ struct bbduk_handle {
     Slot slots[N_SLOTS];
     std::atomic<int> next_slot{0};
     std::atomic<int64_t> launches{0};
+    std::atomic<int64_t> h2d_bytes{0}, d2h_bytes{0};  // bytes bbduk_b200_process / _process_packed moved across PCIe
     std::atomic<int> max_read_len_hint{0};
     bool trace = false;     // BBDUK_B200_TRACE=1: per-chunk host timings on stderr
     bool ascii_every_set = false;
@@ -129,6 +130,25 @@ int set_err(bbduk_handle *h, const std::string &m) {
 __global__ void off64_to_32_kernel(const int64_t *__restrict__ off64, int64_t base, uint32_t *__restrict__ off32, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) off32[i] = (uint32_t)(off64[i] - base);
+}
+// host-packed input for a mode the tuned kernels do not serve: spell the 2-bit stream out again (undefined -> 'N')
+__global__ void unpack_kernel(const uint32_t *__restrict__ F, const uint16_t *__restrict__ D, uint8_t *__restrict__ bases, int64_t groups) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= groups) return;
+    const uint32_t f = F[g], d = D[g];
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        uint32_t x = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int b = 4 * q + j;
+            const uint32_t ch = ((d >> (15 - b)) & 1u) ? ((0x54474341u >> (8 * ((f >> (30 - 2 * b)) & 3u))) & 0xFFu) : (uint32_t)'N';
+            x |= ch << (8 * j);
+        }
+        w[q] = x;
+    }
+    reinterpret_cast<uint4 *>(bases)[g] = make_uint4(w[0], w[1], w[2], w[3]);
 }
 __global__ void maskoff_rebase_kernel(int64_t *off, int64_t base, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -575,12 +595,15 @@ int bbduk_b200_process_device(bbduk_handle *h, const uint8_t *d_bases, const uin
     return process_device_impl(h, d_bases, d_offsets, n_reads, paired, d_out, d_stats, stream, 0);
 }
 
-int bbduk_b200_process(bbduk_handle *h, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, int32_t paired,
-                       const bbduk_out *out, bbduk_stats *stats) {
+// bases != NULL: ASCII input (bbduk_b200_process). Otherwise pre_F / pre_D: the caller's own 2-bit stream + defined bits over the
+// concatenated bases (bbduk_b200_process_packed); a chunk then starts at the 16-base group its first read begins in.
+static int process_host_impl(bbduk_handle *h, const uint8_t *bases, const uint32_t *pre_F, const uint16_t *pre_D, const int64_t *offsets,
+                             int64_t n_reads, int32_t paired, const bbduk_out *out, bbduk_stats *stats) {
     if (!h) return set_err(nullptr, "handle is NULL");
     if (!h->finalized) return set_err(h, "process before finalize");
     if (n_reads < 0 || (paired && (n_reads & 1))) return set_err(h, "bad n_reads (paired input needs an even count)");
-    if (n_reads > 0 && (!bases || !offsets)) return set_err(h, "NULL input");
+    const bool pre = bases == nullptr;
+    if (n_reads > 0 && ((!bases && !(pre_F && pre_D)) || !offsets)) return set_err(h, "NULL input");
     if (check_mode_inputs(h, paired, out)) return 1;
     if (stats) memset(stats, 0, sizeof *stats);
     if (n_reads == 0) return 0;
@@ -601,8 +624,12 @@ int bbduk_b200_process(bbduk_handle *h, const uint8_t *bases, const int64_t *off
     bool src_pinned = false;
     {
         cudaPointerAttributes pa;
-        if (cudaPointerGetAttributes(&pa, bases) == cudaSuccess) src_pinned = pa.type == cudaMemoryTypeHost;
+        if (cudaPointerGetAttributes(&pa, pre ? (const void *)pre_F : (const void *)bases) == cudaSuccess) src_pinned = pa.type == cudaMemoryTypeHost;
         cudaGetLastError();
+        if (pre && src_pinned) {
+            src_pinned = cudaPointerGetAttributes(&pa, pre_D) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+            cudaGetLastError();
+        }
     }
     std::vector<Slot *> used;
     const int per = paired ? 2 : 1;
@@ -611,7 +638,10 @@ int bbduk_b200_process(bbduk_handle *h, const uint8_t *bases, const int64_t *off
         // chunk [r0, r1): bounded reads and bytes, pairs never split
         int64_t r1 = std::min(n_reads, r0 + CHUNK_READS);
         while (r1 > r0 + per && offsets[r1] - offsets[r0] > CHUNK_BYTES) r1 = r0 + std::max<int64_t>(per, ((r1 - r0) / 2 / per) * per);
-        const int64_t nb = offsets[r1] - offsets[r0];
+        // packed input: the chunk's stream starts at the group its first read begins in, so offsets are rebased to that group
+        const int64_t gfirst = pre ? (offsets[r0] >> 4) : 0;
+        const int64_t obase = pre ? 16 * gfirst : offsets[r0];
+        const int64_t nb = offsets[r1] - obase;
         if (nb >= (1ll << 32) - 64) {
             rc = set_err(h, "a single read (pair) exceeds 4 GiB");
             break;
@@ -675,17 +705,42 @@ int bbduk_b200_process(bbduk_handle *h, const uint8_t *bases, const int64_t *off
         bool packed = false;
         {
             const BBTable tv = h->table.view();
-            packed = h->pack_host && !want_mask && max_len <= FAST_MAX_READ_LEN && nb >= (1 << 16) &&
+            packed = (pre || (h->pack_host && nb >= (1 << 16))) && !want_mask && max_len <= FAST_MAX_READ_LEN &&
                      (plan_fast2(h->p, tv, max_len).usable || plan_fast(h->p, tv, max_len).usable) && packed_ok(h->p, tv);
             // host packing is bound by the host's memory bandwidth, the ASCII path by PCIe: every n-th chunk goes
             // ASCII (no CPU work, DMA straight from the caller's buffer) so that both resources are used
             // (never the last chunk of a call: its transfer is the tail nothing overlaps with)
-            if (packed && src_pinned && h->ascii_every > 0 && (chunk_no % h->ascii_every) == h->ascii_every - 1 && r1 < n_reads)
+            if (!pre && packed && src_pinned && h->ascii_every > 0 && (chunk_no % h->ascii_every) == h->ascii_every - 1 && r1 < n_reads)
                 packed = false;
             chunk_no++;
         }
-        if (packed && !rc) rc = ensure_packed(h, s, nr, nb);
-        if (packed && !rc) {
+        if ((packed || pre) && !rc) rc = ensure_packed(h, s, nr, nb);
+        if (pre && !rc) {
+            // the caller's stream: rebase the offsets (and, when the arrays are not page-locked, stage them) on the workers
+            std::lock_guard<std::mutex> pg(h->pool_mu);
+            const int64_t *osrc = offsets + r0;
+            const int64_t groups = (nb + 15) / 16;
+            Slot *sp = &s;
+            const bool stage = !src_pinned;
+            const uint32_t *fsrc = pre_F + gfirst;
+            const uint16_t *dsrc = pre_D + gfirst;
+            h->pool->run([=](int part, int n_parts) {
+                const int64_t i0 = (nr + 1) * part / n_parts, i1 = (nr + 1) * (part + 1) / n_parts;
+                for (int64_t i = i0; i < i1; i++) sp->h_off32[i] = (uint32_t)(osrc[i] - obase);
+                if (stage) {
+                    const int64_t g0 = groups * part / n_parts, g1 = groups * (part + 1) / n_parts;
+                    memcpy(sp->h_F + g0, fsrc + g0, sizeof(uint32_t) * (size_t)(g1 - g0));
+                    memcpy(sp->h_D + g0, dsrc + g0, sizeof(uint16_t) * (size_t)(g1 - g0));
+                }
+            });
+            CKL((h->h2d_bytes += (int64_t)(sizeof(uint32_t) * groups), cudaMemcpyAsync(s.d_F, stage ? s.h_F : fsrc, sizeof(uint32_t) * groups, cudaMemcpyHostToDevice, st)));
+            CKL((h->h2d_bytes += (int64_t)(sizeof(uint16_t) * groups), cudaMemcpyAsync(s.d_D, stage ? s.h_D : dsrc, sizeof(uint16_t) * groups, cudaMemcpyHostToDevice, st)));
+            CKL((h->h2d_bytes += (int64_t)(sizeof(uint32_t) * (nr + 1)), cudaMemcpyAsync(s.d_off32, s.h_off32, sizeof(uint32_t) * (nr + 1), cudaMemcpyHostToDevice, st)));
+            if (!packed && !rc) {  // a mode the tuned kernels do not serve: spell the stream out on the device
+                unpack_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(s.d_F, s.d_D, s.d_bases, groups);
+                h->launches += 1;
+            }
+        } else if (packed && !rc) {
             std::lock_guard<std::mutex> pg(h->pool_mu);
             const uint8_t *src = bases + offsets[r0];
             const int64_t *osrc = offsets + r0;
@@ -703,12 +758,12 @@ int bbduk_b200_process(bbduk_handle *h, const uint8_t *bases, const int64_t *off
             if (h->trace)
                 fprintf(stderr, "[bbduk_b200] packed %lld bases in %.3f ms on %d threads\n", (long long)nb,
                         1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_pack0).count(), h->pool->size());
-            CKL(cudaMemcpyAsync(s.d_F, s.h_F, sizeof(uint32_t) * groups, cudaMemcpyHostToDevice, st));
-            CKL(cudaMemcpyAsync(s.d_D, s.h_D, sizeof(uint16_t) * groups, cudaMemcpyHostToDevice, st));
-            CKL(cudaMemcpyAsync(s.d_off32, s.h_off32, sizeof(uint32_t) * (nr + 1), cudaMemcpyHostToDevice, st));
+            CKL((h->h2d_bytes += (int64_t)(sizeof(uint32_t) * groups), cudaMemcpyAsync(s.d_F, s.h_F, sizeof(uint32_t) * groups, cudaMemcpyHostToDevice, st)));
+            CKL((h->h2d_bytes += (int64_t)(sizeof(uint16_t) * groups), cudaMemcpyAsync(s.d_D, s.h_D, sizeof(uint16_t) * groups, cudaMemcpyHostToDevice, st)));
+            CKL((h->h2d_bytes += (int64_t)(sizeof(uint32_t) * (nr + 1)), cudaMemcpyAsync(s.d_off32, s.h_off32, sizeof(uint32_t) * (nr + 1), cudaMemcpyHostToDevice, st)));
         } else {
-            CKL(cudaMemcpyAsync(s.d_bases, bases + offsets[r0], (size_t)nb, cudaMemcpyHostToDevice, st));
-            CKL(cudaMemcpyAsync(s.d_off64, offsets + r0, sizeof(int64_t) * (nr + 1), cudaMemcpyHostToDevice, st));
+            CKL((h->h2d_bytes += (int64_t)((size_t)nb), cudaMemcpyAsync(s.d_bases, bases + offsets[r0], (size_t)nb, cudaMemcpyHostToDevice, st)));
+            CKL((h->h2d_bytes += (int64_t)(sizeof(int64_t) * (nr + 1)), cudaMemcpyAsync(s.d_off64, offsets + r0, sizeof(int64_t) * (nr + 1), cudaMemcpyHostToDevice, st)));
             if (!rc) {
                 off64_to_32_kernel<<<(unsigned)((nr + 1 + 255) / 256), 256, 0, st>>>(s.d_off64, offsets[r0], s.d_off32, nr + 1);
                 h->launches += 1;
@@ -723,7 +778,7 @@ int bbduk_b200_process(bbduk_handle *h, const uint8_t *bases, const int64_t *off
         dout.flags = out->flags ? s.d_flags : nullptr;
         dout.count = out->count ? s.d_count : nullptr;
         if (want_mask) {
-            CKL(cudaMemcpyAsync(s.d_maskoff, out->mask_off + r0, sizeof(int64_t) * (nr + 1), cudaMemcpyHostToDevice, st));
+            CKL((h->h2d_bytes += (int64_t)(sizeof(int64_t) * (nr + 1)), cudaMemcpyAsync(s.d_maskoff, out->mask_off + r0, sizeof(int64_t) * (nr + 1), cudaMemcpyHostToDevice, st)));
             if (!rc) {
                 maskoff_rebase_kernel<<<(unsigned)((nr + 1 + 255) / 256), 256, 0, st>>>(s.d_maskoff, mw0, nr + 1);
                 h->launches += 1;
@@ -735,14 +790,14 @@ int bbduk_b200_process(bbduk_handle *h, const uint8_t *bases, const int64_t *off
             rc = run_batch(h, s.d_bases, s.d_off32, nr, nb, paired, dout, d_stats, max_len, s.d_handoff, s.d_handoff_n,
                            DirectScratch{s.d_first64, s.d_lastpos, s.d_sbits}, st, packed ? s.d_F : nullptr,
                            packed ? s.d_D : nullptr);
-        if (out->id0) CKL(cudaMemcpyAsync(out->id0 + r0, s.d_id0, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, st));
-        if (out->id0b) CKL(cudaMemcpyAsync(out->id0b + r0, s.d_id0b, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, st));
-        if (out->lo) CKL(cudaMemcpyAsync(out->lo + r0, s.d_lo, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, st));
-        if (out->hi) CKL(cudaMemcpyAsync(out->hi + r0, s.d_hi, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, st));
-        if (out->count) CKL(cudaMemcpyAsync(out->count + r0, s.d_count, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, st));
-        if (out->flags) CKL(cudaMemcpyAsync(out->flags + r0, s.d_flags, (size_t)nr, cudaMemcpyDeviceToHost, st));
+        if (out->id0) CKL((h->d2h_bytes += (int64_t)(sizeof(int32_t) * nr), cudaMemcpyAsync(out->id0 + r0, s.d_id0, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, st)));
+        if (out->id0b) CKL((h->d2h_bytes += (int64_t)(sizeof(int32_t) * nr), cudaMemcpyAsync(out->id0b + r0, s.d_id0b, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, st)));
+        if (out->lo) CKL((h->d2h_bytes += (int64_t)(sizeof(int32_t) * nr), cudaMemcpyAsync(out->lo + r0, s.d_lo, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, st)));
+        if (out->hi) CKL((h->d2h_bytes += (int64_t)(sizeof(int32_t) * nr), cudaMemcpyAsync(out->hi + r0, s.d_hi, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, st)));
+        if (out->count) CKL((h->d2h_bytes += (int64_t)(sizeof(int32_t) * nr), cudaMemcpyAsync(out->count + r0, s.d_count, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, st)));
+        if (out->flags) CKL((h->d2h_bytes += (int64_t)((size_t)nr), cudaMemcpyAsync(out->flags + r0, s.d_flags, (size_t)nr, cudaMemcpyDeviceToHost, st)));
         if (want_mask && mw > 0)
-            CKL(cudaMemcpyAsync(out->maskbits + mw0, s.d_maskbits, sizeof(uint32_t) * mw, cudaMemcpyDeviceToHost, st));
+            CKL((h->d2h_bytes += (int64_t)(sizeof(uint32_t) * mw), cudaMemcpyAsync(out->maskbits + mw0, s.d_maskbits, sizeof(uint32_t) * mw, cudaMemcpyDeviceToHost, st)));
         CKL(cudaEventRecord(s.done, st));
 #undef CKL
         used.push_back(&s);
@@ -763,6 +818,22 @@ int bbduk_b200_process(bbduk_handle *h, const uint8_t *bases, const int64_t *off
         if (e != cudaSuccess) rc = set_err(h, std::string("CUDA error after process: ") + cudaGetErrorString(e));
     }
     return rc;
+}
+
+int bbduk_b200_process(bbduk_handle *h, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, int32_t paired,
+                       const bbduk_out *out, bbduk_stats *stats) {
+    if (h && n_reads > 0 && !bases) return set_err(h, "NULL input");
+    static const uint8_t none = 0;
+    return process_host_impl(h, bases ? bases : &none, nullptr, nullptr, offsets, n_reads, paired, out, stats);
+}
+
+int bbduk_b200_process_packed(bbduk_handle *h, const uint32_t *F, const uint16_t *D, const int64_t *offsets, int64_t n_reads,
+                              int32_t paired, const bbduk_out *out, bbduk_stats *stats) {
+    if (h && n_reads > 0 && (!F || !D)) return set_err(h, "NULL input");
+    if (h && h->finalized && h->p.mode == MODE_KMASK) return set_err(h, "packed input does not carry the bases' case: kmask needs the ASCII entry");
+    static const uint32_t nf = 0;
+    static const uint16_t nd = 0;
+    return process_host_impl(h, nullptr, F ? F : &nf, D ? D : &nd, offsets, n_reads, paired, out, stats);
 }
 
 int bbduk_b200_scaffold_counts(bbduk_handle *h, int64_t *read_counts, int64_t *base_counts, int32_t n) {
@@ -1230,6 +1301,13 @@ int bbduk_b200_process_chain(bbduk_handle *h, const bbduk_chain_cfg *cfg, const 
 int bbduk_b200_pack_bases(const uint8_t *bases, int64_t n, uint32_t *F, uint16_t *D) {
     if (n < 0 || (n > 0 && (!bases || !F || !D))) return set_err(nullptr, "bad pack_bases arguments");
     pack_bases(bases, n, F, D);
+    return 0;
+}
+
+int bbduk_b200_transfer_bytes(bbduk_handle *h, int64_t *h2d, int64_t *d2h) {
+    if (!h) return set_err(nullptr, "handle is NULL");
+    if (h2d) *h2d = h->h2d_bytes.load();
+    if (d2h) *d2h = h->d2h_bytes.load();
     return 0;
 }
 

@@ -1,6 +1,7 @@
 // hostpack.cpp -- see hostpack.h. AVX2 path selected at run time on x86-64; portable scalar path otherwise.
 #include "hostpack.h"
 
+#include <cstdlib>
 #include <cstring>
 
 #if defined(__x86_64__)
@@ -107,6 +108,73 @@ __attribute__((target("avx2"))) void pack_avx2(const uint8_t *b, int64_t n, int6
     }
     if (g < g1) pack_scalar(b, n, g, g1, F, D);
 }
+// AVX-512 VBMI: 64 bases per step. One 128-entry byte table lookup (vpermi2b) turns ASCII into (code | 0x80 if undefined),
+// two multiply-adds pack 4 codes per byte, one byte permute gathers the 16 packed bytes (4 F words, big-endian inside a word),
+// and the defined bits come straight out of a byte-test mask of the per-16-byte reversed vector (bit 15-b = base b).
+struct Lut512 {
+    alignas(64) uint8_t lo[64], hi[64];
+    Lut512() {
+        for (int i = 0; i < 128; i++) {
+            const uint8_t v = g_tab.valid[i] ? g_tab.code[i] : (uint8_t)0x80;
+            (i < 64 ? lo[i] : hi[i - 64]) = v;
+        }
+    }
+};
+const Lut512 g_lut512;
+
+__attribute__((target("avx512f,avx512bw,avx512vbmi,avx512vl"))) static inline void pack64(const uint8_t *src, const __m512i lutlo,
+                                                                                          const __m512i luthi, __m128i &f4, uint64_t &d4) {
+    const __m512i v = _mm512_loadu_si512(src);
+    const __mmask64 high = _mm512_movepi8_mask(v);                          // bytes >= 128: undefined
+    __m512i t = _mm512_permutex2var_epi8(lutlo, v, luthi);                  // index = low 7 bits
+    t = _mm512_mask_mov_epi8(t, high, _mm512_set1_epi8((char)0x80));
+    const __m512i c = _mm512_and_si512(t, _mm512_set1_epi8(3));            // undefined -> code 0 (table value 0x80)
+    const __m512i p4 = _mm512_madd_epi16(_mm512_maddubs_epi16(c, _mm512_set1_epi16(0x0104)), _mm512_set1_epi32(0x00010010));
+    // byte 4j of p4 = bases 4j..4j+3; F word w (16 bases) = bytes (16w+0, 16w+4, 16w+8, 16w+12) most significant first
+    const __m512i gather = _mm512_castsi128_si512(_mm_setr_epi8(12, 8, 4, 0, 28, 24, 20, 16, 44, 40, 36, 32, 60, 56, 52, 48));
+    f4 = _mm512_castsi512_si128(_mm512_permutexvar_epi8(gather, p4));
+    const __m512i rev = _mm512_broadcast_i32x4(_mm_setr_epi8(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0));
+    d4 = ~(uint64_t)_mm512_movepi8_mask(_mm512_shuffle_epi8(t, rev));       // bit 7 set = undefined
+}
+
+__attribute__((target("avx512f,avx512bw,avx512vbmi,avx512vl"))) void pack_avx512(const uint8_t *b, int64_t n, int64_t g0, int64_t g1,
+                                                                                  uint32_t *F, uint16_t *D) {
+    const __m512i lutlo = _mm512_load_si512(g_lut512.lo), luthi = _mm512_load_si512(g_lut512.hi);
+    int64_t g = g0;
+    const int64_t full = n / 16;
+    const int64_t stop = g1 < full ? g1 : full;
+    // peel to a 64-byte boundary of F and D (32 groups make one line of D and two of F)
+    while (g + 4 <= stop && (((reinterpret_cast<uintptr_t>(F + g)) & 63) != 0 || ((reinterpret_cast<uintptr_t>(D + g)) & 63) != 0)) {
+        __m128i f4;
+        uint64_t d4;
+        pack64(b + g * 16, lutlo, luthi, f4, d4);
+        _mm_storeu_si128(reinterpret_cast<__m128i *>(F + g), f4);
+        memcpy(D + g, &d4, 8);
+        g += 4;
+    }
+    if ((reinterpret_cast<uintptr_t>(F + g) & 63) == 0 && (reinterpret_cast<uintptr_t>(D + g) & 63) == 0) {
+        for (; g + 32 <= stop; g += 32) {  // 512 bases: two lines of F, one of D, streamed past the cache
+            __m128i f[8];
+            alignas(64) uint64_t d[8];
+#pragma GCC unroll 8
+            for (int q = 0; q < 8; q++) pack64(b + (g + 4 * q) * 16, lutlo, luthi, f[q], d[q]);
+            const __m512i fa = _mm512_inserti64x4(_mm512_castsi256_si512(_mm256_set_m128i(f[1], f[0])), _mm256_set_m128i(f[3], f[2]), 1);
+            const __m512i fb = _mm512_inserti64x4(_mm512_castsi256_si512(_mm256_set_m128i(f[5], f[4])), _mm256_set_m128i(f[7], f[6]), 1);
+            _mm512_stream_si512(reinterpret_cast<__m512i *>(F + g), fa);
+            _mm512_stream_si512(reinterpret_cast<__m512i *>(F + g + 16), fb);
+            _mm512_stream_si512(reinterpret_cast<__m512i *>(D + g), _mm512_load_si512(d));
+        }
+        _mm_sfence();
+    }
+    for (; g + 4 <= stop; g += 4) {
+        __m128i f4;
+        uint64_t d4;
+        pack64(b + g * 16, lutlo, luthi, f4, d4);
+        _mm_storeu_si128(reinterpret_cast<__m128i *>(F + g), f4);
+        memcpy(D + g, &d4, 8);
+    }
+    if (g < g1) pack_scalar(b, n, g, g1, F, D);
+}
 #endif
 
 }  // namespace
@@ -114,6 +182,11 @@ __attribute__((target("avx2"))) void pack_avx2(const uint8_t *b, int64_t n, int6
 void pack_bases_range(const uint8_t *bases, int64_t n, int64_t g0, int64_t g1, uint32_t *F, uint16_t *D) {
 #if defined(__x86_64__)
     static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    static const bool have_vbmi = __builtin_cpu_supports("avx512vbmi") && __builtin_cpu_supports("avx512bw") && !getenv("BBDUK_B200_NO_AVX512");
+    if (have_vbmi) {
+        pack_avx512(bases, n, g0, g1, F, D);
+        return;
+    }
     if (have_avx2) {
         pack_avx2(bases, n, g0, g1, F, D);
         return;

@@ -54,7 +54,8 @@ struct BBTable {
     uint32_t part_words;      // part filter words (0 = not available for this configuration)
     uint32_t short_words;     // bloom over the short (len<k) keys only
     uint32_t samp_words;      // byte map over all 8-mers that occur inside a reference part (sampled scan of probe_fast2.cu; 0 = none)
-    uint32_t tail_words;      // two direct bitmaps over tail_q-mers in front of the short-k-mer tails (0 = none)
+    uint32_t tail_words;      // two direct bitmaps over tail_q-mers in front of the short-k-mer tails (0 = none), followed (tail_q >= 9)
+                              // by their two 8-mer level-0 images of BB_TAIL0_WORDS words each
     int32_t tail_q;           // bases the tail bitmaps are indexed by = min(mink, 12)
     uint32_t big_words;       // L2-resident one-bit-per-key filter in front of an HBM-resident array (0 = none)
     int32_t n_parts;          // pigeonhole parts = hdist+1
@@ -65,6 +66,7 @@ struct BBTable {
 };
 
 #define BB_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+#define BB_TAIL0_WORDS 2048u  // 4^8 bits
 
 // returns 0 on success, else writes a message (reference's assertion texts) into err
 int derive_params(const struct bbduk_cfg *cfg, BBParams *p, char *err, int errlen);

@@ -35,6 +35,7 @@ using namespace bbfast;
 constexpr int QCAP2 = 512;     // pooled queue entries (16 bit each): sample hits of one pass / candidates of one round
 constexpr int ITEM_CAP = 16;   // sample hits one read contributes per pass (32 x 16 = QCAP2)
 constexpr int L1_WORDS = 12;   // stream words (16 bases each) one unrolled block of the sampled scan covers
+constexpr int SPELL_WORDS = 256;  // the "what do these four codes spell" table of stage A
 
 struct Fast2Geom {
     int warps;        // warps per block
@@ -43,6 +44,7 @@ struct Fast2Geom {
     int nbadw;        // words of the per-tile "chunk has an undefined base" bit mask
     int sw;           // 32-position words of the per-lane seed bit columns
     uint32_t part_off, samp_off, tail_off;  // word offsets of the part bitmap / 8-mer byte map / tail bitmaps in BBTable::filter
+    uint32_t tail0_off;  // word offset of this mode's 8-mer level-0 tail bitmap in BBTable::filter; 0 = none
 };
 
 // OR of x << d for d in [0, n), n <= 32
@@ -85,14 +87,21 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
                    int32_t *handoff, unsigned int *handoff_n, Fast2Geom geo, const uint32_t *__restrict__ pk_F,
                    const uint16_t *__restrict__ pk_D) {
     extern __shared__ __align__(16) uint32_t smem[];
-    const uint8_t *samp = reinterpret_cast<const uint8_t *>(smem);        // [65536] 8-mer byte map
-    const uint32_t *filt = smem + 16384;                                   // [BB_PART_WORDS] 9-mer bitmap
+    // [256] the four upper-case bases a packed byte of F stands for (base 0 = bits 7:6 = lowest address): stage A proves a
+    // word of ASCII valid by comparing it with what its own codes spell
+    uint32_t *spell = smem;
+    const uint8_t *samp = reinterpret_cast<const uint8_t *>(smem + SPELL_WORDS);  // [65536] 8-mer byte map
+    const uint32_t *filt = smem + SPELL_WORDS + 16384;                              // [BB_PART_WORDS] 9-mer bitmap
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t *wbase = reinterpret_cast<uint8_t *>(smem + 16384 + BB_PART_WORDS) + (size_t)warp * geo.warp_bytes;
+    // [BB_TAIL0_WORDS] 8-mer level-0 image of the tail bitmap that is asked once per tail length (none: the tails go to L2 directly)
+    const uint32_t *tail0 = smem + SPELL_WORDS + 16384 + BB_PART_WORDS;
+    const uint32_t tail0_words = geo.tail0_off ? BB_TAIL0_WORDS : 0u;
+    uint8_t *wbase = reinterpret_cast<uint8_t *>(smem + SPELL_WORDS + 16384 + BB_PART_WORDS + tail0_words) + (size_t)warp * geo.warp_bytes;
     uint32_t *first32 = reinterpret_cast<uint32_t *>(wbase);                      // [32] (pos << 22 | id) of the first hit, ~0 = none
     uint32_t *owners = first32 + 32;                                              // [32] evaluation rounds: lane of the rank-th releasing read
     int *lastpos = reinterpret_cast<int *>(owners + 32);                          // [32] last hit position
-    uint32_t *badw = reinterpret_cast<uint32_t *>(lastpos + 32);                  // [nbadw] chunks with a non-ACGTU base
+    uint32_t *misc = reinterpret_cast<uint32_t *>(lastpos + 32);                  // [4] misc[0] != 0: the tile has a seed bit
+    uint32_t *badw = misc + 4;                                                    // [nbadw] chunks with a non-ACGTU base
     uint32_t *Fs = badw + geo.nbadw;
     uint16_t *Ds = reinterpret_cast<uint16_t *>(Fs + geo.nch + PAD + TAIL);
     uint16_t *queue = Ds + ((geo.nch + PAD + TAIL + 1) & ~1);                     // [QCAP2] (owner lane << 11) | position
@@ -100,9 +109,17 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
 
     {
         const uint32_t *src = t.filter + geo.samp_off;
-        for (uint32_t i = threadIdx.x; i < 16384u; i += blockDim.x) smem[i] = __ldg(src + i);
+        for (uint32_t i = threadIdx.x; i < 16384u; i += blockDim.x) smem[SPELL_WORDS + i] = __ldg(src + i);
         src = t.filter + geo.part_off;
-        for (uint32_t i = threadIdx.x; i < BB_PART_WORDS; i += blockDim.x) smem[16384 + i] = __ldg(src + i);
+        for (uint32_t i = threadIdx.x; i < BB_PART_WORDS; i += blockDim.x) smem[SPELL_WORDS + 16384 + i] = __ldg(src + i);
+        src = t.filter + geo.tail0_off;
+        for (uint32_t i = threadIdx.x; i < tail0_words; i += blockDim.x) smem[SPELL_WORDS + 16384 + BB_PART_WORDS + i] = __ldg(src + i);
+        for (uint32_t i = threadIdx.x; i < (uint32_t)SPELL_WORDS; i += blockDim.x) {
+            uint32_t e = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) e |= ((0x54474341u >> (8 * ((i >> (6 - 2 * j)) & 3u))) & 0xFFu) << (8 * j);  // "ACGT"
+            spell[i] = e;
+        }
     }
     for (int i = lane; i < PAD; i += 32) {
         Fs[i] = 0;
@@ -117,7 +134,7 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
     const uint32_t amask = (1u << (pw - 7)) - 1u; // part ends a sample hit can discover
     const int lag0 = t.part_lag[0], lag1 = t.part_lag[1], lag2 = t.part_lag[2], lag3 = t.part_lag[t.n_parts > 3 ? 3 : 2];
     const uint32_t *tailb1 = t.filter + geo.tail_off;
-    const uint32_t *tailb2 = tailb1 + (t.tail_words >> 1);
+    const uint32_t *tailb2 = tailb1 + max(1u, (1u << (2 * t.tail_q)) >> 5);
     const uintptr_t base_addr = PACKED ? (uintptr_t)0 : reinterpret_cast<uintptr_t>(bases);
     const int64_t n_tiles = (n_reads + 31) >> 5;
     const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -173,17 +190,29 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
                     }
                 }
             } else if (c < nchunks) {
-                uint32_t cw[4], bw[4];
-                classify4(v.x, cw[0], bw[0]);
-                classify4(v.y, cw[1], bw[1]);
-                classify4(v.z, cw[2], bw[2]);
-                classify4(v.w, cw[3], bw[3]);
-                f = (pack4(cw[0]) << 24) | (pack4(cw[1]) << 16) | (pack4(cw[2]) << 8) | pack4(cw[3]);
+                // codes = ((w >> 1) ^ (w >> 2)) & 3 per byte; one multiply packs four of them into the product's top byte
+                // (bits 23:22 of the product are always zero, so product >> 22 is that byte times 4: the table offset).
+                // A word is A C G T only (either case) iff it equals what its codes spell; anything else (N, IUPAC, U) takes
+                // the exact classification below.
+                const uint32_t aw[4] = {v.x, v.y, v.z, v.w};
+                uint32_t pr[4], odd = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    pr[j] = (((aw[j] >> 1) ^ (aw[j] >> 2)) & 0x03030303u) * 0x40100401u;
+                    const uint32_t e = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(spell) + (pr[j] >> 22));
+                    odd |= (aw[j] & 0xDFDFDFDFu) ^ e;
+                }
+                f = __byte_perm(__byte_perm(pr[2], pr[3], 0x0037), __byte_perm(pr[0], pr[1], 0x0037), 0x5410);
                 dbits = 0xFFFFu;
-                if ((bw[0] | bw[1] | bw[2] | bw[3]) != 0) {  // rare: some base of the chunk is not ACGTU
-                    dbits = (valid4(bw[0]) << 12) | (valid4(bw[1]) << 8) | (valid4(bw[2]) << 4) | valid4(bw[3]);
-                    f &= spread16(dbits);  // undefined bases read as code 0 (jgi/BBDuk.java:3882)
-                    atomicOr(badw + (c >> 5), 1u << (c & 31));
+                if (odd != 0) {  // rare: some base of the chunk is not ACGT
+                    uint32_t cw, bw[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) classify4(aw[j], cw, bw[j]);
+                    if ((bw[0] | bw[1] | bw[2] | bw[3]) != 0) {  // and not U either
+                        dbits = (valid4(bw[0]) << 12) | (valid4(bw[1]) << 8) | (valid4(bw[2]) << 4) | valid4(bw[3]);
+                        f &= spread16(dbits);  // undefined bases read as code 0 (jgi/BBDuk.java:3882)
+                        atomicOr(badw + (c >> 5), 1u << (c & 31));
+                    }
                 }
             }
             Fs[c + PAD] = f;
@@ -191,6 +220,7 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
         }
         first32[lane] = ~0u;
         lastpos[lane] = -1;
+        if (lane == 0) misc[0] = 0u;
         __syncwarp();
 
         const int s = live ? (int)(base_addr + o0 - a0) : 0;  // stream base of read position 0
@@ -275,6 +305,7 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
                     for (int c = 1; c < pw - 8; c++) A &= B >> c;
                     A &= (1u << pw) - 1u;
                     if (A) {
+                        misc[0] = 1u;
                         const int sh = u & 31;
                         uint32_t *col = S + (u >> 5) * 32 + owner;
                         atomicOr(col, A << sh);
@@ -389,6 +420,7 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
                         }
                         A &= amask;
                         if (A) {
+                            misc[0] = 1u;
                             const int e0 = rel + 7;  // read-relative end of the u = 0 part
                             const int sh = e0 & 31;
                             uint32_t *col = S + (e0 >> 5) * 32 + owner;
@@ -417,8 +449,10 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
                 return u;
             };
             if (any_force && force_und) und_c = und_word(ncwmax - 1);
+            // no seed bit in the whole tile and nothing forced (most tiles of reads without adapters): S is all zero already
+            const int c_top = (any_force || misc[0] != 0u) ? ncwmax - 1 : -1;
 #pragma unroll 1
-            for (int c = ncwmax - 1; c >= 0; c--) {
+            for (int c = c_top; c >= 0; c--) {
                 const uint32_t sc = S[c * 32 + lane], sp = c > 0 ? S[(c - 1) * 32 + lane] : 0u;
                 uint32_t cb = __funnelshift_l(sp, sc, lag0);
                 if (t.n_parts > 1) cb |= __funnelshift_l(sp, sc, lag1);
@@ -600,17 +634,43 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
                         const uint32_t *b_all = (FMODE == FM_KTRIM_R) ? tailb2 : tailb1, *b_len = (FMODE == FM_KTRIM_R) ? tailb1 : tailb2;
                         const uint32_t va = (FMODE == FM_KTRIM_R) ? ((uint32_t)W & qm) : ((uint32_t)(W >> (2 * max(nmax - q, 0))) & qm);
                         const uint32_t wa = __ldg(b_all + (va >> 5));
+                        uint32_t ask = (ntop >= nlo) ? ((ntop >= 31 ? 0xFFFFFFFFu : ((1u << (ntop + 1)) - 1u)) & ~((1u << nlo) - 1u)) : 0u;
+                        if (tail0_words) {
+                            // level 0 in shared memory: only lengths whose q-mer starts with an 8-mer that some listed q-mer
+                            // starts with go on to the full bitmap in L2 (on random reads one length in ten)
+                            // the 8 leading bases of the q-mer of length n are 16 bits of W: from bit 2(n-8) (ktrim=r: the q-mer is
+                            // read[L-n : L-n+q]) or from bit 2(nmax-n+q-8) (ktrim=l: read[n-q : n]); four independent lookups per trip
+                            const uint32_t wlo = (uint32_t)W, whi = (uint32_t)(W >> 32);
+                            uint32_t pass = 0;
 #pragma unroll 1
-                        for (int n = nlo; n <= ntop; n += 4) {  // four lookups in flight
+                            for (int n = nlo; n <= ntop; n += 4) {
+                                uint32_t u[4], w0[4];
+#pragma unroll
+                                for (int j = 0; j < 4; j++) {
+                                    const int sh = (FMODE == FM_KTRIM_R) ? 2 * (n + j - 8) : 2 * (nmax - n - j + q - 8);
+                                    const uint32_t lo_ = (sh & 32) ? whi : wlo, hi_ = (sh & 32) ? 0u : whi;
+                                    u[j] = __funnelshift_r(lo_, hi_, sh & 31) & 0xFFFFu;
+                                    w0[j] = tail0[u[j] >> 5];
+                                }
+#pragma unroll
+                                for (int j = 0; j < 4; j++) pass |= ((w0[j] >> (u[j] & 31u)) & 1u) << ((n + j) & 31);
+                            }
+                            ask &= pass;
+                        }
+#pragma unroll 1
+                        while (ask) {  // up to four lookups in flight
                             uint32_t v[4], wv[4];
+                            int nn[4];
 #pragma unroll
                             for (int j = 0; j < 4; j++) {
-                                const int sh = (FMODE == FM_KTRIM_R) ? 2 * (n + j - q) : 2 * (nmax - n - j);
+                                nn[j] = ask ? __ffs(ask) - 1 : -1;
+                                ask &= ask - 1;
+                                const int sh = (FMODE == FM_KTRIM_R) ? 2 * (nn[j] - q) : 2 * (nmax - nn[j]);
                                 v[j] = (uint32_t)(W >> (sh & 63)) & qm;
-                                wv[j] = (n + j <= ntop) ? __ldg(b_len + (v[j] >> 5)) : 0u;
+                                wv[j] = nn[j] >= 0 ? __ldg(b_len + (v[j] >> 5)) : 0u;
                             }
 #pragma unroll
-                            for (int j = 0; j < 4; j++) todo |= ((wv[j] >> (v[j] & 31u)) & 1u) << ((n + j) & 31);
+                            for (int j = 0; j < 4; j++) todo |= ((wv[j] >> (v[j] & 31u)) & 1u) << (nn[j] & 31);
                         }
                         if (nmax < q || ((wa >> (va & 31u)) & 1u)) todo = all;
                         if (FMODE == FM_KTRIM_L && nmax == k) todo |= (k >= 31 ? 0x80000000u : (1u << k));  // a prefix of k bases is a full-length key
@@ -618,39 +678,74 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
                     }
                     DBG2(5, __popc(todo));
                 }
+                // The lookups of all 32 reads share the lanes: (read, length) pairs are queued and evaluated 32 at a time, so a read
+                // whose tail holds an undefined base (all its lengths are asked) costs the warp one round, not a dozen dependent
+                // trips to L2. A hit leaves its length in the owner's hit mask and (smallest length << 22 | id) in first32; the
+                // reference's loop (ascending lengths, :3929-3975) is then replayed from the mask in closed form.
+                if (__any_sync(0xFFFFFFFFu, todo != 0u)) {
+                    uint32_t *hitm = reinterpret_cast<uint32_t *>(lastpos);
+                    hitm[lane] = 0u;
+                    first32[lane] = ~0u;
+                    __syncwarp();
 #pragma unroll 1
-                while (__any_sync(0xFFFFFFFFu, todo != 0u)) {
-                    if (todo) {
-                        const int n = __ffs(todo) - 1;  // ascending lengths, the reference's order
-                        todo &= todo - 1;
-                        const uint64_t nm = (1ull << (2 * n)) - 1ull;
-                        uint64_t kmer, rkmer;
-                        int i;
-                        if (FMODE == FM_KTRIM_R) {  // last n bases; reference loop index i = L-n
-                            kmer = W & nm;
-                            rkmer = RC >> (2 * (32 - n));
-                            i = L - n;
-                        } else {  // first n bases; reference loop index i = n-1
-                            kmer = (W >> (2 * (nmax - n))) & nm;
-                            rkmer = (RC >> (2 * (32 - nmax))) & nm;
-                            i = n - 1;
-                        }
-                        const uint64_t key = bb_to_value(p, kmer, rkmer, 1ull << (2 * n));
-                        const int id = bb_table_get(t, key);
-                        if (id > 0) {
-                            if (id0 < 0) id0 = id;
-                            if (FMODE == FM_KTRIM_R) {
-                                minLoc = i;
-                                minLocX = min(minLocX, L);
-                                maxLoc = L - 1;
-                                maxLocX = max(maxLocX, i - 1);
-                            } else {
-                                minLoc = 0;
-                                minLocX = min(minLocX, i + 1);
-                                maxLoc = max(maxLoc, i);
-                                maxLocX = max(maxLocX, 0);
+                    while (__any_sync(0xFFFFFFFFu, todo != 0u)) {
+                        const int cnt = min(__popc(todo), ITEM_CAP);
+                        const int incl = warp_scan_incl(cnt, lane);
+                        const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                        {
+                            int w = incl - cnt;
+#pragma unroll 1
+                            for (int c = 0; c < cnt; c++) {
+                                queue[w++] = (uint16_t)(((uint32_t)lane << 11) + (uint32_t)(__ffs(todo) - 1));
+                                todo &= todo - 1;
                             }
-                            found++;
+                        }
+                        __syncwarp();
+#pragma unroll 1
+                        for (int base = 0; base < total; base += 32) {
+                            const bool on = base + lane < total;
+                            const uint32_t ent = on ? queue[base + lane] : 0u;
+                            const int owner = (int)(ent >> 11), n = (int)(ent & 0x7FFu);
+                            const uint64_t Wo = ((uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)(W >> 32), owner) << 32) |
+                                                __shfl_sync(0xFFFFFFFFu, (uint32_t)W, owner);
+                            const uint64_t RCo = ((uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)(RC >> 32), owner) << 32) |
+                                                 __shfl_sync(0xFFFFFFFFu, (uint32_t)RC, owner);
+                            const int nmax_o = (FMODE == FM_KTRIM_R) ? 1 : __shfl_sync(0xFFFFFFFFu, min(k, L), owner);
+                            if (on) {
+                                const uint64_t nm = (1ull << (2 * n)) - 1ull;
+                                uint64_t kmer, rkmer;
+                                if (FMODE == FM_KTRIM_R) {  // last n bases
+                                    kmer = Wo & nm;
+                                    rkmer = RCo >> (2 * (32 - n));
+                                } else {  // first n bases
+                                    kmer = (Wo >> (2 * (nmax_o - n))) & nm;
+                                    rkmer = (RCo >> (2 * (32 - nmax_o))) & nm;
+                                }
+                                const int id = bb_table_get(t, bb_to_value(p, kmer, rkmer, 1ull << (2 * n)));
+                                if (id > 0) {
+                                    atomicOr(hitm + owner, 1u << n);
+                                    atomicMin(first32 + owner, ((uint32_t)n << 22) | (uint32_t)id);
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    const uint32_t hm = hitm[lane];
+                    if (hm) {
+                        // lengths n_lo..n_hi hit; reference loop index i = L-n (ktrim=r, descending) or n-1 (ktrim=l, ascending)
+                        const int n_lo = __ffs(hm) - 1, n_hi = 31 - __clz(hm);
+                        if (id0 < 0) id0 = (int)(first32[lane] & 0x3FFFFFu);
+                        found += __popc(hm);
+                        if (FMODE == FM_KTRIM_R) {
+                            minLoc = L - n_hi;
+                            minLocX = min(minLocX, L);
+                            maxLoc = L - 1;
+                            maxLocX = max(maxLocX, L - n_lo - 1);
+                        } else {
+                            minLoc = 0;
+                            minLocX = min(minLocX, n_lo);
+                            maxLoc = max(maxLoc, n_hi - 1);
+                            maxLocX = max(maxLocX, 0);
                         }
                     }
                 }
@@ -756,19 +851,28 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
     }
 }
 
-Fast2Geom make_geom2(const BBTable &t, int max_read_len) {
+Fast2Geom make_geom2(const BBParams &p, const BBTable &t, int max_read_len) {
     Fast2Geom g;
     const int lmax = std::max(max_read_len, 16);
     g.nch = (32 * lmax + 15 + 15) / 16 + 1;
     g.nbadw = (g.nch + 31) / 32 + 1;
     g.sw = ((lmax + 16) >> 5) + 2;
-    int wb = 32 * 8 + 32 * 4 + g.nbadw * 4 + (g.nch + PAD + TAIL) * 4 + ((g.nch + PAD + TAIL + 1) & ~1) * 2 + QCAP2 * 2 + g.sw * 32 * 4;
+    int wb = 32 * 8 + 32 * 4 + 16 + g.nbadw * 4 + (g.nch + PAD + TAIL) * 4 + ((g.nch + PAD + TAIL + 1) & ~1) * 2 + QCAP2 * 2 + g.sw * 32 * 4;
     wb = (wb + 15) & ~15;
     g.warp_bytes = wb;
     g.part_off = t.n_filter_words;
     g.samp_off = t.n_filter_words + t.part_words + t.short_words;
     g.tail_off = g.samp_off + t.samp_words;
-    const int avail = FAST_SMEM_LIMIT - (16384 + (int)BB_PART_WORDS) * 4 - 64;
+    // the 8-mer level-0 image of the per-length tail bitmap: type I (first) for ktrim=r, type II (second) for ktrim=l
+    const uint32_t tail_main = std::max<uint32_t>(1u, (1u << (2 * t.tail_q)) >> 5);
+    static const bool use_tail0 = [] {
+        const char *e = getenv("BBDUK_B200_TAIL0");
+        return !(e && atoi(e) == 0);
+    }();
+    g.tail0_off = 0;
+    if (use_tail0 && p.mode == MODE_KTRIM && p.useShortKmers && t.tail_words >= 2 * tail_main + 2 * BB_TAIL0_WORDS)
+        g.tail0_off = g.tail_off + 2 * tail_main + (p.ktrimLeft ? BB_TAIL0_WORDS : 0u);
+    const int avail = FAST_SMEM_LIMIT - (SPELL_WORDS + 16384 + (int)BB_PART_WORDS + (g.tail0_off ? (int)BB_TAIL0_WORDS : 0)) * 4 - 64;
     g.warps = std::min(32, avail / wb);
     return g;
 }
@@ -801,11 +905,11 @@ FastPlan plan_fast2(const BBParams &p, const BBTable &t, int max_read_len) {
     if (p.editDistance != 0 || t.part_words == 0 || t.n_parts < 1 || t.samp_words == 0 || t.part_w < 11) return pl;
     if (t.n_scaffolds >= (1 << 22)) return pl;  // the first hit of a read is kept as (position << 22 | id) in one 32-bit word
     if (max_read_len > MAX_FAST_LEN) max_read_len = MAX_FAST_LEN;
-    const Fast2Geom g = make_geom2(t, max_read_len);
+    const Fast2Geom g = make_geom2(p, t, max_read_len);
     if (g.warps < 8) return pl;
     pl.usable = true;
     pl.max_read_len = max_read_len;
-    pl.smem_bytes = (16384 + (int)BB_PART_WORDS) * 4 + g.warps * g.warp_bytes + 64;
+    pl.smem_bytes = (SPELL_WORDS + 16384 + (int)BB_PART_WORDS + (g.tail0_off ? (int)BB_TAIL0_WORDS : 0)) * 4 + g.warps * g.warp_bytes + 64;
     pl.filter_words = 16384 + (int)BB_PART_WORDS;
     return pl;
 }
@@ -814,7 +918,7 @@ int launch_fast2(const FastPlan &plan, const uint8_t *d_bases, const uint32_t *d
                  const BBParams &p, const BBTable &t, const bbduk_out &out, bbduk_stats *d_stats, unsigned long long *scaf_reads,
                  unsigned long long *scaf_bases, int32_t *d_handoff, unsigned int *d_handoff_n, int sm_count, cudaStream_t st,
                  const uint32_t *pk_F, const uint16_t *pk_D) {
-    const Fast2Geom g = make_geom2(t, plan.max_read_len);
+    const Fast2Geom g = make_geom2(p, t, plan.max_read_len);
     const int threads = g.warps * 32;
     const int64_t n_tiles = (n_reads + 31) / 32;
     const int blocks = (int)std::min<int64_t>(sm_count, (n_tiles + g.warps - 1) / g.warps);

@@ -331,6 +331,21 @@ __global__ void tail_filter_build_kernel(const Seed *__restrict__ seeds, int64_t
     }
 }
 
+// Level-0 images of the two tail bitmaps for the shared memory of probe_fast2.cu: bit (v >> 2(q-8)) of an 8-mer bitmap is set
+// iff some q-mer v with that 8-base prefix is set in the full bitmap (q >= 9). 2048 words each, behind B1 | B2.
+__global__ void tail_prefix_kernel(const uint32_t *__restrict__ b, int64_t words, int q, uint32_t *l0) {
+    const int sh = 2 * (q - 8);
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t m = b[w];
+        while (m) {
+            const uint32_t v = (uint32_t)(32 * w) + (uint32_t)(__ffs(m) - 1);
+            m &= m - 1;
+            const uint32_t u = v >> sh;
+            atomicOr(l0 + (u >> 5), 1u << (u & 31u));
+        }
+    }
+}
+
 static int64_t pow2ceil(int64_t x) {
     int64_t p = 1024;
     while (p < x) p <<= 1;
@@ -536,6 +551,7 @@ int DeviceTable::build(const BBParams &p, const std::vector<uint8_t> &ref, const
             if (samp_words && p.useShortKmers && dist_short <= 3 && p.mink >= 1) {
                 tail_q = std::min(p.mink, 12);
                 tail_words = 2 * std::max<uint32_t>(1u, (1u << (2 * tail_q)) >> 5);
+                if (tail_q >= 9) tail_words += 2 * BB_TAIL0_WORDS;  // 8-mer level-0 images of both bitmaps (tail_prefix_kernel)
             }
         }
     }
@@ -555,9 +571,15 @@ int DeviceTable::build(const BBParams &p, const std::vector<uint8_t> &ref, const
     }
     if (tail_words) {
         uint32_t *b1 = d_filter + n_filter_words + part_words + short_words + samp_words;
+        const uint32_t main_words = std::max<uint32_t>(1u, (1u << (2 * tail_q)) >> 5);
         tail_filter_build_kernel<<<64, 64, 0, st>>>(d_short + (int64_t)(p.k - 1) * cap_short, (int64_t)h_cnt[1 + p.k - 1], p.k - 1,
-                                                    tail_q, dist_short, p.rcomp, b1, b1 + tail_words / 2);
+                                                    tail_q, dist_short, p.rcomp, b1, b1 + main_words);
         (*launches)++;
+        if (tail_words > 2 * main_words) {
+            tail_prefix_kernel<<<296, 256, 0, st>>>(b1, main_words, tail_q, b1 + 2 * main_words);
+            tail_prefix_kernel<<<296, 256, 0, st>>>(b1 + main_words, main_words, tail_q, b1 + 2 * main_words + BB_TAIL0_WORDS);
+            (*launches) += 2;
+        }
     }
 
     auto launch_expand = [&](const Seed *seeds, int64_t n, int len, int dist, int use_extra) -> int {

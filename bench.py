@@ -181,7 +181,7 @@ def run_reference(args):
 # ---- workloads (BASELINE.json configs) ---------------------------------------------------
 # alg_bytes: ALGORITHMIC bytes per read = L + 12 + 8*P*[table in HBM]
 WORKLOADS = {
-    "cfg2": dict(cfg=CFG, paired=True, read_len=READ_LEN, alg_bytes=READ_LEN + 4 + 8, kernel="bbduk_fast_kernel",
+    "cfg2": dict(cfg=CFG, paired=True, read_len=READ_LEN, alg_bytes=READ_LEN + 4 + 8, kernel="bbduk_fast2_kernel",
                  desc=WORKLOAD, stored=217135),
     "cfg3": dict(cfg=dict(k=31), paired=False, read_len=READ_LEN, alg_bytes=READ_LEN + 12 + 8 * 120, kernel="bbduk_direct_kernel",
                  desc="bbduk.sh k=31 (kfilter, mm=t) vs 100 x 1 Mbp synthetic reference (seed 7), synthetic 150 bp SE reads, "
@@ -335,12 +335,26 @@ def run_kcount(args, wl):
         exch_ms = 1e3 * (time.perf_counter() - t0)
     else:
         uniq = st["unique_kmers"]
+    cpu_line = None
+    if rank == 0 and world == 1 and args.cpu_pairs > 0:
+        # the counting oracle (CPU restatement of KmerTableSet's loop, single-threaded by construction) on the head of the batch
+        from oracle.kcount import KCountOracle
+        c_reads = min(n_reads, 1 << 20)
+        cb = bufs[0][0][: c_reads * L].cpu().numpy()
+        co = np.arange(0, (c_reads + 1) * L, L, dtype=np.int64)
+        ko = KCountOracle(31, True)
+        t0 = time.perf_counter()
+        ko.add_reads(cb, co)
+        cpu_line = {"value": c_reads / (time.perf_counter() - t0), "unit": "reads/s", "cores": 1, "kind": "port",
+                    "sample": f"{c_reads} reads of the same synthetic workload, counting oracle (C port), 1 thread"}
+        del ko
     if rank == 0:
         peak, peak_kind = load_peak()
         kern_ms = total_ms_max / args.steps
         achieved = n_reads * wl["alg_bytes"] / (kern_ms * 1e-3) / 1e9
         info = tab.table_info()
         emit(json.dumps({
+            **({"cpu_baseline": cpu_line} if cpu_line else {}),
             "metric": "kmercount_reads_per_s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": kern_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int64", "data": "synthetic",
@@ -581,15 +595,46 @@ def run_ours(args):
     for _ in range(2):
         eng.process(hb, ho, paired, out=hout)
     barrier()
+    x0 = eng.transfer_bytes()
     t0 = time.perf_counter()
     for _ in range(e_steps):
         _, est = eng.process(hb, ho, paired, out=hout)
     torch.cuda.synchronize()
     e_dt = time.perf_counter() - t0
+    x1 = eng.transfer_bytes()
+    # what really crossed PCIe per step, counted inside the library (packed chunks 0.375 B/base, ASCII chunks 1 B/base)
+    h2d_wire, d2h_wire = (x1[0] - x0[0]) // e_steps, (x1[1] - x0[1]) // e_steps
     te = torch.tensor([e_dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e_value = world * e_reads * e_steps / float(te.item())
+
+    # ---- the same call for a host that already holds its reads 2-bit packed (bbduk_b200_process_packed): the stream is
+    # packed once outside the timed region, as a packing FASTQ parser would hand it over ----------------------------------
+    packed_info = None
+    if args.workload == "cfg2":
+        ng = (e_reads * L + 15) // 16
+        h_F = torch.empty(ng + 16, dtype=torch.int32, pin_memory=True)
+        h_D = torch.empty(ng + 32, dtype=torch.int16, pin_memory=True)
+        assert lib.bbduk_b200_pack_bases(hb.ctypes.data, hb.size, h_F.data_ptr(), h_D.data_ptr()) == 0
+        nF, nD = h_F.numpy().view(np.uint32), h_D.numpy().view(np.uint16)
+        for _ in range(2):
+            eng.process_packed(nF, nD, ho, paired, out=hout)
+        barrier()
+        y0 = eng.transfer_bytes()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            eng.process_packed(nF, nD, ho, paired, out=hout)
+        torch.cuda.synchronize()
+        p_dt = time.perf_counter() - t0
+        y1 = eng.transfer_bytes()
+        tp = torch.tensor([p_dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        packed_info = {"reads_per_s": world * e_reads * e_steps / float(tp.item()), "pairs_per_step_per_gpu": e_pairs,
+                       "h2d_bytes_per_step": (y1[0] - y0[0]) // e_steps, "d2h_bytes_per_step": (y1[1] - y0[1]) // e_steps,
+                       "note": "bbduk_b200_process_packed: 2-bit stream + defined bits packed by the caller (outside the timed region)"}
+        del h_F, h_D
 
     # ---- the whole chain end to end (k-mer block + tbo + qtrim=rl trimq=10) through ONE C-ABI call, host buffers ----
     chain_info = None
@@ -628,6 +673,7 @@ def run_ours(args):
     # ---- sanity: EVERY rank checks a slice of its own timed batch against the CPU oracle (checker only); the flag in the
     # line is the AND over ranks, so a rank whose replicated table arrived broken cannot hide behind rank 0 -----------
     parity = None
+    o = None
     if args.workload == "cfg2" or args.verify:
         from oracle.oracle import Oracle
         chk = 20000
@@ -668,19 +714,15 @@ def run_ours(args):
         cores = os.cpu_count() or 1
         cpu_pairs = args.cpu_pairs
         cpu_rate = None
-        if world == 1 and cpu_pairs > 0 and args.workload == "cfg2":
-            # the sample is the head of the timed workload, copied back from the device generator
-            from oracle.oracle import Oracle as _Or
+        if world == 1 and cpu_pairs > 0 and o is not None:
+            # the sample is the head of the timed workload, copied back from the device generator; the oracle (CPU restatement,
+            # all host cores) is the one the parity check above built (cfg 3 / 4: only with --verify, its table takes minutes)
             cpu_pairs = min(cpu_pairs, n_pairs)
             cb = bufs[0][0][: 2 * cpu_pairs * L].cpu().numpy()
             co = np.arange(0, (2 * cpu_pairs + 1) * L, L, dtype=np.int64)
-            oo = _Or(make_cfg(**wl["cfg"]))
-            rb, roff = adapters_ref()
-            oo.add_ref(rb, roff)
-            oo.finalize()
-            oo.process(cb[: 4000 * L], co[:4001], True, threads=cores)
+            o.process(cb[: 4000 * L], co[:4001], paired, threads=cores)
             t0 = time.perf_counter()
-            oo.process(cb, co, True, threads=cores)
+            o.process(cb, co, paired, threads=cores)
             cpu_rate = 2 * cpu_pairs / (time.perf_counter() - t0)
         line = {
             "metric": "bbduk_reads_per_s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
@@ -692,9 +734,12 @@ def run_ours(args):
                        "parity_vs_oracle_on_timed_batch": parity, "parity_detail": parity_detail,
                        "kmer_block_plus_tbo": tbo_info,
                        "qtrim_block": qtrim_info, "entropy_block": entropy_info,
-                       "chain_e2e_kmer_tbo_qtrim": chain_info},
-            "e2e": {"value": e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "pairs_per_step_per_gpu": e_pairs, "steps": e_steps},
+                       "chain_e2e_kmer_tbo_qtrim": chain_info, "e2e_packed_input": packed_info},
+            "e2e": {"value": e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d_wire), "d2h_bytes_per_step": int(d2h_wire),
+                    "host_input_bytes_per_step": h2d, "host_output_bytes_per_step": d2h,
+                    "pairs_per_step_per_gpu": e_pairs, "steps": e_steps,
+                    "note": "ASCII bases + int64 offsets in pinned host memory in, id0/hi/flags out, through bbduk_b200_process; "
+                            "h2d/d2h = bytes that crossed PCIe as counted by the library (most chunks cross 2-bit packed)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -726,7 +771,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs-per-step", type=int, default=8 << 20, help="pairs per GPU per step (HBM-resident)")
-    ap.add_argument("--e2e-pairs", type=int, default=2 << 20, help="pairs per GPU per end-to-end step (host buffers)")
+    ap.add_argument("--e2e-pairs", type=int, default=0, help="pairs per GPU per end-to-end step (host buffers); 0 = the same batch as --pairs-per-step")
     ap.add_argument("--cpu-pairs", type=int, default=4 << 20, help="pairs of the cpu_baseline sample (0 = skip)")
     ap.add_argument("--ref-pairs", type=int, default=1 << 19, help="pairs per step of --impl reference")
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS),
@@ -735,6 +780,8 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.e2e_pairs <= 0:
+        args.e2e_pairs = args.pairs_per_step if args.workload != "cfg5" else min(args.pairs_per_step, 2 << 20)
     claim_stdout()
     if args.impl == "reference":
         run_reference(args)

@@ -188,6 +188,15 @@ BBDUK_API int bbduk_b200_finalize(bbduk_handle *h, int64_t *stored_kmers);
 BBDUK_API int bbduk_b200_process(bbduk_handle *h, const uint8_t *bases, const int64_t *offsets, int64_t n_reads,
                        int32_t paired, const bbduk_out *out, bbduk_stats *stats);
 
+/* The same call for a host that already holds its reads 2-bit packed (e.g. a FASTQ parser that packs while it scans, the
+ * role of stream/FastqStreamer.java + dna/AminoAcid.java:269-285 fused): F = big-endian 2-bit codes, 16 bases per word, D =
+ * defined bits (bit 15-b = base b of the group), both over the CONCATENATED bases exactly as bbduk_b200_pack_bases writes them
+ * (group g = bases [16g, 16g+16)); offsets as in bbduk_b200_process. 0.375 B/base cross PCIe instead of 1 and no host
+ * packing pass runs. Modes the tuned kernels do not serve are spelled out again on the device (undefined -> 'N'); kmask,
+ * whose output depends on the bases' case, is refused. */
+BBDUK_API int bbduk_b200_process_packed(bbduk_handle *h, const uint32_t *F, const uint16_t *D, const int64_t *offsets,
+                                        int64_t n_reads, int32_t paired, const bbduk_out *out, bbduk_stats *stats);
+
 /* Same, on DEVICE buffers (bases, 32-bit offsets[n_reads+1], outputs), asynchronous on `stream`
  * (a cudaStream_t, NULL = default stream). total bases < 4 GiB per call. d_stats: device
  * bbduk_stats to accumulate into, may be NULL. */
@@ -243,6 +252,10 @@ BBDUK_API int bbduk_b200_scaffold_counts_sum(bbduk_handle **handles, int32_t n_h
 BBDUK_API int bbduk_b200_table_export(bbduk_handle *h, uint64_t *keys, int32_t *ids, int64_t cap, int64_t *n_out);
 /* refKmers of the finished table (the loader's count of reference k-mers seen, bbduk/BBDukLoader.java:461). */
 BBDUK_API int64_t bbduk_b200_ref_kmers(bbduk_handle *h);
+
+/* Bytes bbduk_b200_process / bbduk_b200_process_packed have copied host->device and device->host on this handle so far
+ * (what really crossed PCIe: packed chunks count 0.375 B/base, ASCII chunks 1; bench.py's e2e.h2d_bytes_per_step). */
+BBDUK_API int bbduk_b200_transfer_bytes(bbduk_handle *h, int64_t *h2d, int64_t *d2h);
 
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 BBDUK_API int64_t bbduk_b200_launch_count(bbduk_handle *h);

@@ -250,3 +250,42 @@ def test_concurrent_callers_share_one_table(adapters):
     for w, x in zip(want, got):
         for name, a in w.fields().items():
             assert np.array_equal(a, x.fields()[name]), name
+
+
+@pytest.mark.parametrize("kw", [dict(k=23, mink=11, hdist=1, ktrim_right=1, trim_pairs_evenly=1), dict(k=23, mink=11, hdist=1, ktrim_left=1),
+                                dict(k=31), dict(k=25, find_best_match=1), dict(k=23, mink=11, hdist=1, ktrim_left=1, ktrim_right=1)],
+                         ids=lambda kw: ",".join(f"{a}={b}" for a, b in kw.items()))
+def test_packed_host_input(adapters, adapter_seqs, kw):
+    """bbduk_b200_process_packed: the caller's own 2-bit stream + defined bits (as bbduk_b200_pack_bases writes them) give the
+    oracle's results, for the tuned kernels (which read the stream as it is) and for the other modes (spelled out again on the
+    device), on multi-chunk batches whose chunks start in the middle of a 16-base group."""
+    o, g = engines(adapters, **kw)
+    for (b, off), paired in ((synth.paired_adapter_reads(6000, seed=13), True),
+                             (synth.ragged_reads(5000, seed=14, adapter=adapter_seqs[1].encode()), False)):
+        eo, so = o.process(b, off, paired, threads=8)
+        F, D = g.pack(b)
+        eg, sg = g.process_packed(F, D, off, paired)
+        for name, x in eo.fields().items():
+            assert np.array_equal(x, eg.fields()[name]), name
+        assert so.as_dict() == sg.as_dict()
+    # 2.2 M ragged reads: several chunks (1 Mi reads each), chunk starts not aligned to a group
+    rb, ro = synth.ragged_reads(40000, seed=15, adapter=adapter_seqs[0].encode(), max_len=90)
+    reps = 56
+    big = np.tile(rb, reps)
+    boff = np.concatenate([[0], (ro[1:][None, :] + (np.arange(reps) * ro[-1])[:, None]).ravel()]).astype(np.int64)
+    F, D = g.pack(big)
+    eg, sg = g.process_packed(F, D, boff, False)
+    ea, sa = g.process(big, boff, False)
+    for name, x in ea.fields().items():
+        assert np.array_equal(x, eg.fields()[name]), name
+    assert sa.as_dict() == sg.as_dict()
+    eo, _ = o.process(rb, ro, False, threads=8)
+    assert np.array_equal(eg.fields()["hi"][-len(ro) + 1:], eo.fields()["hi"])
+
+
+def test_packed_host_input_refuses_kmask(adapters):
+    _, g = engines(adapters, k=23, ktrim_n=1)
+    b, off = synth.paired_adapter_reads(100, seed=2)
+    F, D = g.pack(b)
+    with pytest.raises(RuntimeError, match="kmask"):
+        g.process_packed(F, D, off, True)
