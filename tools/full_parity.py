@@ -4,7 +4,9 @@ device, processed by the CUDA path, and every result record is compared with the
 the same bytes. Nothing is ever written to disk. Prints one JSON summary line.
 
     python tools/full_parity.py --workload cfg2 --pairs 100000000          # 100 M synthetic 2x150 bp pairs
+    python tools/full_parity.py --workload cfg3 --pairs 250000000                # 500 M reads vs the 100 Mbp reference
     python tools/full_parity.py --workload cfg3 --pairs 50000000 --scale 0.02   # cfg-3 shape, 2 Mbp reference
+    python tools/full_parity.py --workload cfg4 --pairs 100000000               # k=27 hdist=2 vs 100 x 1 kbp (2.9e8 keys)
 """
 import argparse
 import ctypes as C
@@ -22,7 +24,7 @@ import numpy as np  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4"])
     ap.add_argument("--pairs", type=int, default=100_000_000, help="pairs (cfg2) / half the reads (cfg3)")
     ap.add_argument("--chunk-pairs", type=int, default=4 << 20)
     ap.add_argument("--scale", type=float, default=1.0, help="cfg3: fraction of the 100 Mbp reference (the oracle's table is host RAM)")
@@ -42,6 +44,14 @@ def main():
         kw = dict(k=23, mink=11, hdist=1, ktrim_right=1, trim_pairs_evenly=1)
         _, rb, roff = read_fasta(os.path.join(ROOT, "tests", "golden", "adapters.fa"))
         paired, d_ref = True, None
+    elif args.workload == "cfg4":
+        kw = dict(k=27, hdist=2)
+        n_scaf, scaf_len = 100, 1000
+        d_ref = torch.empty(n_scaf * scaf_len, dtype=torch.uint8, device="cuda")
+        assert lib.bbduk_b200_synth_reference(d_ref.data_ptr(), d_ref.numel(), C.c_uint64(9), None) == 0
+        rb = d_ref.cpu().numpy()
+        roff = np.arange(0, rb.size + 1, scaf_len, dtype=np.int64)
+        paired = True
     else:
         kw = dict(k=31)
         n_scaf, scaf_len = 100, int(1_000_000 * args.scale)
@@ -86,7 +96,7 @@ def main():
     while done < args.pairs:
         m = min(cp, args.pairs - done)
         nr = 2 * m
-        if args.workload == "cfg2":
+        if args.workload in ("cfg2", "cfg4"):
             rc = lib.bbduk_b200_synth_pairs(d_bases.data_ptr(), d_off.data_ptr(), m, done, L, C.c_uint64(1), 50, 5, None)
         else:
             rc = lib.bbduk_b200_synth_contam(d_bases.data_ptr(), d_off.data_ptr(), nr, 2 * done, L, d_ref.data_ptr(), d_ref.numel(),
