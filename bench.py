@@ -33,9 +33,17 @@ WORKLOAD = ("bbduk.sh ktrim=r k=23 mink=11 hdist=1 tpe, ref=adapters.fa, synthet
 ALG_BYTES_PER_READ = READ_LEN + 4 + 8  # bases + 4 B offset in + 8 B result out (hi + id0); table on-chip
 FALLBACK_HBM_GBS = 6650.0
 # dram__bytes_read.sum + dram__bytes_write.sum per read of the dominant kernel, from the committed `ncu --set full`
-# captures (profiles/r01o_fast_kernel_raw.txt: 652.30 MB + 36.97 MB for a 4,194,304-read launch;
-# profiles/r01_e_kcount_kernel.txt: 28.33 GB + 6.91 GB for 217.6 M k-mers = 162 B per k-mer)
-NCU_TRAFFIC_BYTES_PER_READ = {"cfg2": (652302336 + 36971776) / 4194304, "cfg5": 120 * (28328275000 + 6911184000) / 217637790}
+# captures of the same workloads (a profiler cannot run inside the timed bench; the captures are re-taken whenever the
+# kernel changes and the JSON line names the file: roofline.traffic_source);
+# cfg 5: profiles/r01_e_kcount_kernel.txt: 28.33 GB + 6.91 GB for 217.6 M k-mers = 162 B per k-mer
+NCU_TRAFFIC_BYTES_PER_READ = {"cfg2": (1302081000 + 74900224) / 8388608,  # profiles/r02j_fast2_kernel_raw.txt: an 8,388,608-read launch of bbduk_fast2_kernel
+                              # profiles/r02_cfg3_direct_kernel_details.txt / r02_cfg4_...: 4,194,304-read launches of bbduk_direct_kernel
+                              "cfg3": (30556543000 + 93049088) / 4194304, "cfg4": (35478975000 + 113840128) / 4194304,
+                              "cfg5": 120 * (28328275000 + 6911184000) / 217637790}
+
+
+TRAFFIC_SOURCE = {"cfg2": "profiles/r02j_fast2_kernel_raw.txt", "cfg3": "profiles/r02_cfg3_direct_kernel_details.txt",
+                  "cfg4": "profiles/r02_cfg4_direct_kernel_details.txt", "cfg5": "profiles/r01_e_kcount_kernel.txt"}
 
 
 # Libraries write to the process's stdout behind Python's back (NCCL prints its version line there when a communicator
@@ -609,6 +617,35 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e_value = world * e_reads * e_steps / float(te.item())
 
+    # ---- what bounds the host-buffer path on this box: the packer on all host threads and a plain pinned H2D copy ------------
+    limits = None
+    if args.workload == "cfg2" and rank == 0:
+        from concurrent.futures import ThreadPoolExecutor
+        nthr = max(1, (os.cpu_count() or 1) // max(1, world))
+        nb_ = min(hb.size, 1 << 30) // (16 * 32 * nthr) * (16 * 32 * nthr)
+        if nb_ > 0:
+            gF = np.empty(nb_ // 16 + 64, np.uint32)
+            gD = np.empty(nb_ // 16 + 64, np.uint16)
+            sl = nb_ // nthr
+
+            def one(i):
+                lib.bbduk_b200_pack_bases(hb.ctypes.data + i * sl, sl, gF.ctypes.data + 4 * (i * sl // 16), gD.ctypes.data + 2 * (i * sl // 16))
+            with ThreadPoolExecutor(nthr) as ex:
+                list(ex.map(one, range(nthr)))
+                t0 = time.perf_counter()
+                list(ex.map(one, range(nthr)))
+                pack_gbs = nb_ / (time.perf_counter() - t0) / 1e9
+            d_tmp = torch.empty(nb_, dtype=torch.uint8, device=dev)
+            d_tmp.copy_(h_bases[:nb_], non_blocking=True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            d_tmp.copy_(h_bases[:nb_], non_blocking=True)
+            torch.cuda.synchronize()
+            h2d_gbs = nb_ / (time.perf_counter() - t0) / 1e9
+            del d_tmp, gF, gD
+            limits = {"host_pack_gb_per_s_ascii_in": round(pack_gbs, 1), "host_threads": nthr, "pinned_h2d_gb_per_s": round(h2d_gbs, 1),
+                      "reads_per_s_if_all_chunks_packed": round(pack_gbs * 1e9 / L), "reads_per_s_if_all_chunks_ascii": round(h2d_gbs * 1e9 / (L + 8))}
+
     # ---- the same call for a host that already holds its reads 2-bit packed (bbduk_b200_process_packed): the stream is
     # packed once outside the timed region, as a packing FASTQ parser would hand it over ----------------------------------
     packed_info = None
@@ -637,7 +674,7 @@ def run_ours(args):
         del h_F, h_D
 
     # ---- the whole chain end to end (k-mer block + tbo + qtrim=rl trimq=10) through ONE C-ABI call, host buffers ----
-    chain_info = None
+    chain_info = chain_tbo_info = None
     if args.workload == "cfg2":
         c_pairs = min(e_pairs, 1 << 20)
         c_reads = 2 * c_pairs
@@ -666,6 +703,19 @@ def run_ours(args):
         tc = torch.tensor([c_dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        # exactly BASELINE.json configs[1] (`ktrim=r k=23 mink=11 hdist=1 tpe tbo`): k-mer block + trim by overlap, no qualities
+        eng.process_chain(cb, None, co, True, tbo=tcfg, out=cout)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(c_steps):
+            _, _, ct2b, _, _ = eng.process_chain(cb, None, co, True, tbo=tcfg, out=cout)
+        cb_dt = time.perf_counter() - t0
+        tcb = torch.tensor([cb_dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tcb, op=dist.ReduceOp.MAX)
+        chain_tbo_info = {"reads_per_s": world * c_reads * c_steps / float(tcb.item()), "pairs_per_call_per_gpu": c_pairs,
+                          "h2d_bytes_per_call": int(cb.nbytes + 4 * (c_reads + 1)), "d2h_bytes_per_call": 9 * c_reads,
+                          "reads_trimmed_by_overlap": int(ct2b[0])}
         chain_info = {"reads_per_s": world * c_reads * c_steps / float(tc.item()), "pairs_per_call_per_gpu": c_pairs,
                       "h2d_bytes_per_call": int(cb.nbytes + cq.nbytes + 4 * (c_reads + 1)), "d2h_bytes_per_call": 9 * c_reads,
                       "reads_trimmed_by_overlap": int(ct2[0]), "reads_qtrimmed": int(cq8[0])}
@@ -734,7 +784,7 @@ def run_ours(args):
                        "parity_vs_oracle_on_timed_batch": parity, "parity_detail": parity_detail,
                        "kmer_block_plus_tbo": tbo_info,
                        "qtrim_block": qtrim_info, "entropy_block": entropy_info,
-                       "chain_e2e_kmer_tbo_qtrim": chain_info, "e2e_packed_input": packed_info},
+                       "chain_e2e_kmer_tbo": chain_tbo_info, "chain_e2e_kmer_tbo_qtrim": chain_info, "e2e_packed_input": packed_info, "e2e_host_limits": limits},
             "e2e": {"value": e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d_wire), "d2h_bytes_per_step": int(d2h_wire),
                     "host_input_bytes_per_step": h2d, "host_output_bytes_per_step": d2h,
                     "pairs_per_step_per_gpu": e_pairs, "steps": e_steps,
@@ -746,6 +796,7 @@ def run_ours(args):
                          "traffic": (NCU_TRAFFIC_BYTES_PER_READ[args.workload] * n_reads
                                      if args.workload in NCU_TRAFFIC_BYTES_PER_READ else None),
                          "traffic_unit": "bytes per launch (ncu dram read+write per read x reads per launch)",
+                         "traffic_source": TRAFFIC_SOURCE.get(args.workload),
                          "peak_source": peak_kind, "kernel": wl["kernel"],
                          "algorithmic_bytes_per_read": wl["alg_bytes"], "ms_per_launch": kern_ms},
         }
