@@ -129,7 +129,7 @@ __device__ __forceinline__ uint32_t smear_right(uint32_t x, int n) {
     return (uint32_t)x;
 }
 
-enum { FM_KTRIM_R = 0, FM_KTRIM_L = 1, FM_KFILTER = 2 };
+enum { FM_KTRIM_R = 0, FM_KTRIM_L = 1, FM_KFILTER = 2, FM_KMASK = 3 };
 
 
 }  // namespace bbfast

@@ -23,6 +23,7 @@
 // Rolling-state semantics: jgi/BBDuk.java:3882-3900 in the closed form of SURVEY.md A.2; ktrim :3866-4013; kfilter :3395-3457.
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "bbduk_dev.cuh"
 #include "fast_common.cuh"
@@ -45,6 +46,7 @@ struct Fast2Geom {
     int sw;           // 32-position words of the per-lane seed bit columns
     uint32_t part_off, samp_off, tail_off;  // word offsets of the part bitmap / 8-mer byte map / tail bitmaps in BBTable::filter
     uint32_t tail0_off;  // word offset of this mode's 8-mer level-0 tail bitmap in BBTable::filter; 0 = none
+    int mw;              // kmask: 32-position words of the per-lane mask bit columns (= sw), else 0
 };
 
 // OR of x << d for d in [0, n), n <= 32
@@ -56,6 +58,19 @@ __device__ __forceinline__ uint64_t smear_left64(uint64_t x, int n) {
         have += s;
     }
     return x;
+}
+
+// sets bits a..b (inclusive, a <= b, at most two words apart) of a lane's bit column (word w of lane l at col[w * 32])
+__device__ __forceinline__ void or_range(uint32_t *col, int a, int b) {
+    const int wa = a >> 5, wb = b >> 5;
+    const uint32_t ma = 0xFFFFFFFFu << (a & 31), mb = 0xFFFFFFFFu >> (31 - (b & 31));
+    if (wa == wb) {
+        atomicOr(col + wa * 32, ma & mb);
+    } else {
+        atomicOr(col + wa * 32, ma);
+        for (int w = wa + 1; w < wb; w++) atomicOr(col + w * 32, 0xFFFFFFFFu);
+        atomicOr(col + wb * 32, mb);
+    }
 }
 
 // Out-of-line helpers: the per-tile loop has to fit the 32 KB instruction cache with 8 warps per scheduler in different
@@ -106,6 +121,7 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
     uint16_t *Ds = reinterpret_cast<uint16_t *>(Fs + geo.nch + PAD + TAIL);
     uint16_t *queue = Ds + ((geo.nch + PAD + TAIL + 1) & ~1);                     // [QCAP2] (owner lane << 11) | position
     uint32_t *S = reinterpret_cast<uint32_t *>(queue + QCAP2);                    // [sw][32] seed bits, one column per lane
+    uint32_t *M = S + geo.sw * 32;                                                // [mw][32] kmask: covered bases, one column per lane
 
     {
         const uint32_t *src = t.filter + geo.samp_off;
@@ -164,7 +180,7 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
 #pragma unroll 1
         for (int i = lane; i < geo.nbadw; i += 32) badw[i] = 0;
 #pragma unroll 1
-        for (int i = lane; i < geo.sw * 32; i += 32) S[i] = 0;
+        for (int i = lane; i < (geo.sw + geo.mw) * 32; i += 32) S[i] = 0;  // S and, behind it, M
         __syncwarp();
         const uint4 *src16 = reinterpret_cast<const uint4 *>(a0);
         uint4 n1 = make_uint4(0, 0, 0, 0), n2 = make_uint4(0, 0, 0, 0);
@@ -509,6 +525,7 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
                 if (id > 0) {
                     atomicMin(first32 + owner, ((uint32_t)pos << 22) | (uint32_t)id);
                     if (FMODE == FM_KTRIM_L) atomicMax(lastpos + owner, pos);
+                    if (FMODE == FM_KMASK) or_range(M + owner, max(0, pos - k + 1), pos);  // bs.set(max(0, i-(k-1)), i+1), trimpad 0
                 }
             }
             if (has) {  // the candidates this round took
@@ -535,7 +552,7 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
                     creg = S[cw * 32 + lane];
                 }
                 if (!round(!done && creg != 0, cw, creg, false)) break;
-                if (first32[lane] != ~0u) done = true;  // everything still unreleased lies behind the confirmed hit
+                if (FMODE != FM_KMASK && first32[lane] != ~0u) done = true;  // everything still unreleased lies behind the confirmed hit
             }
         }
 
@@ -591,21 +608,20 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
             count = found;
             discarded = found > 0;
         } else {
-            // ---- T. short-k-mer tails (jgi/BBDuk.java:3910-3975) ---------------------------------------
-            // ktrim guard (:3868): reads shorter than k still get the tails
-            const bool tscan = live && t.stored > 0 && p.useShortKmers && L >= max(1, min(k, p.mink)) && !found && !skip;
-            int minLocX = 999999999, maxLocX = -1;
-            if (found) {
-                minLocX = minLoc + k;
-                maxLocX = maxLoc - k;
-            }
-            if (__any_sync(0xFFFFFFFFu, tscan)) {
+            // ---- T. short-k-mer tails (jgi/BBDuk.java:3910-3975; kmask :4080-4150) -------------------------
+            // One side at a time: RIGHT = the suffixes of the read (lengths mink..k-1), else its prefixes (mink..k). Leaves the
+            // lengths that hit in hm and the id of the shortest one in idt. Called by all lanes.
+            auto tails = [&](auto right_tag, const bool tscan, uint32_t &hm, int &idt) {
+                constexpr bool RIGHT = decltype(right_tag)::value;
+                hm = 0u;
+                idt = -1;
+                if (!__any_sync(0xFFFFFFFFu, tscan)) return;
                 // All tail k-mers of a read are sub-windows of ONE 32-base window: the suffix tails (ktrim=r) of the
                 // window ending at the last base, the prefix tails (ktrim=l) of the window ending at base min(k,L)-1.
                 // The tails read undefined bases as code 0 / complement 0 ("no N handling in tails").
-                const int nmax = (FMODE == FM_KTRIM_R) ? min(k - 1, L) : min(k, L);
+                const int nmax = (RIGHT) ? min(k - 1, L) : min(k, L);
                 const int nlo = max(p.mink, 1);
-                const int e = (FMODE == FM_KTRIM_R) ? (s + L - 1) : (s + nmax - 1);
+                const int e = (RIGHT) ? (s + L - 1) : (s + nmax - 1);
                 uint64_t W = 0, RC = 0;
                 uint32_t todo = 0;  // bit n = the tail of n bases has to be looked up
                 if (tscan) {
@@ -631,11 +647,11 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
                         // one bitmap (b_all) is tested once and decides all lengths, the other (b_len) once per length;
                         // ktrim=r: b_all = type II on the read's last q bases, b_len = type I on read[L-n : L-n+q];
                         // ktrim=l (mirror image): b_all = type I on read[0:q], b_len = type II on read[n-q : n]
-                        const uint32_t *b_all = (FMODE == FM_KTRIM_R) ? tailb2 : tailb1, *b_len = (FMODE == FM_KTRIM_R) ? tailb1 : tailb2;
-                        const uint32_t va = (FMODE == FM_KTRIM_R) ? ((uint32_t)W & qm) : ((uint32_t)(W >> (2 * max(nmax - q, 0))) & qm);
+                        const uint32_t *b_all = (RIGHT) ? tailb2 : tailb1, *b_len = (RIGHT) ? tailb1 : tailb2;
+                        const uint32_t va = (RIGHT) ? ((uint32_t)W & qm) : ((uint32_t)(W >> (2 * max(nmax - q, 0))) & qm);
                         const uint32_t wa = __ldg(b_all + (va >> 5));
                         uint32_t ask = (ntop >= nlo) ? ((ntop >= 31 ? 0xFFFFFFFFu : ((1u << (ntop + 1)) - 1u)) & ~((1u << nlo) - 1u)) : 0u;
-                        if (tail0_words) {
+                        if (tail0_words && RIGHT == (p.ktrimLeft == 0)) {
                             // level 0 in shared memory: only lengths whose q-mer starts with an 8-mer that some listed q-mer
                             // starts with go on to the full bitmap in L2 (on random reads one length in ten)
                             // the 8 leading bases of the q-mer of length n are 16 bits of W: from bit 2(n-8) (ktrim=r: the q-mer is
@@ -647,7 +663,7 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
                                 uint32_t u[4], w0[4];
 #pragma unroll
                                 for (int j = 0; j < 4; j++) {
-                                    const int sh = (FMODE == FM_KTRIM_R) ? 2 * (n + j - 8) : 2 * (nmax - n - j + q - 8);
+                                    const int sh = (RIGHT) ? 2 * (n + j - 8) : 2 * (nmax - n - j + q - 8);
                                     const uint32_t lo_ = (sh & 32) ? whi : wlo, hi_ = (sh & 32) ? 0u : whi;
                                     u[j] = __funnelshift_r(lo_, hi_, sh & 31) & 0xFFFFu;
                                     w0[j] = tail0[u[j] >> 5];
@@ -665,7 +681,7 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
                             for (int j = 0; j < 4; j++) {
                                 nn[j] = ask ? __ffs(ask) - 1 : -1;
                                 ask &= ask - 1;
-                                const int sh = (FMODE == FM_KTRIM_R) ? 2 * (nn[j] - q) : 2 * (nmax - nn[j]);
+                                const int sh = (RIGHT) ? 2 * (nn[j] - q) : 2 * (nmax - nn[j]);
                                 v[j] = (uint32_t)(W >> (sh & 63)) & qm;
                                 wv[j] = nn[j] >= 0 ? __ldg(b_len + (v[j] >> 5)) : 0u;
                             }
@@ -673,7 +689,7 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
                             for (int j = 0; j < 4; j++) todo |= ((wv[j] >> (v[j] & 31u)) & 1u) << (nn[j] & 31);
                         }
                         if (nmax < q || ((wa >> (va & 31u)) & 1u)) todo = all;
-                        if (FMODE == FM_KTRIM_L && nmax == k) todo |= (k >= 31 ? 0x80000000u : (1u << k));  // a prefix of k bases is a full-length key
+                        if (!RIGHT && nmax == k) todo |= (k >= 31 ? 0x80000000u : (1u << k));  // a prefix of k bases is a full-length key
                         todo &= all;
                     }
                     DBG2(5, __popc(todo));
@@ -710,11 +726,11 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
                                                 __shfl_sync(0xFFFFFFFFu, (uint32_t)W, owner);
                             const uint64_t RCo = ((uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)(RC >> 32), owner) << 32) |
                                                  __shfl_sync(0xFFFFFFFFu, (uint32_t)RC, owner);
-                            const int nmax_o = (FMODE == FM_KTRIM_R) ? 1 : __shfl_sync(0xFFFFFFFFu, min(k, L), owner);
+                            const int nmax_o = (RIGHT) ? 1 : __shfl_sync(0xFFFFFFFFu, min(k, L), owner);
                             if (on) {
                                 const uint64_t nm = (1ull << (2 * n)) - 1ull;
                                 uint64_t kmer, rkmer;
-                                if (FMODE == FM_KTRIM_R) {  // last n bases
+                                if (RIGHT) {  // last n bases
                                     kmer = Wo & nm;
                                     rkmer = RCo >> (2 * (32 - n));
                                 } else {  // first n bases
@@ -730,27 +746,52 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
                         }
                         __syncwarp();
                     }
-                    const uint32_t hm = hitm[lane];
-                    if (hm) {
-                        // lengths n_lo..n_hi hit; reference loop index i = L-n (ktrim=r, descending) or n-1 (ktrim=l, ascending)
-                        const int n_lo = __ffs(hm) - 1, n_hi = 31 - __clz(hm);
-                        if (id0 < 0) id0 = (int)(first32[lane] & 0x3FFFFFu);
-                        found += __popc(hm);
-                        if (FMODE == FM_KTRIM_R) {
-                            minLoc = L - n_hi;
-                            minLocX = min(minLocX, L);
-                            maxLoc = L - 1;
-                            maxLocX = max(maxLocX, L - n_lo - 1);
-                        } else {
-                            minLoc = 0;
-                            minLocX = min(minLocX, n_lo);
-                            maxLoc = max(maxLoc, n_hi - 1);
-                            maxLocX = max(maxLocX, 0);
-                        }
+                    hm = hitm[lane];
+                    if (hm) idt = (int)(first32[lane] & 0x3FFFFFu);
+                }
+            };
+            int minLocX = 999999999, maxLocX = -1;
+            if (found) {
+                minLocX = minLoc + k;
+                maxLocX = maxLoc - k;
+            }
+            uint32_t hm = 0, hm2 = 0;
+            int idt = -1, idt2 = -1;
+            if (FMODE == FM_KMASK) {
+                // kmask scans both sides whatever the full-length scan found (:4080); reads shorter than k are left alone (:4027)
+                const bool tscan = live && t.stored > 0 && p.useShortKmers && L >= k && !skip;
+                tails(std::false_type{}, tscan, hm, idt);   // prefixes first, as the reference
+                tails(std::true_type{}, tscan, hm2, idt2);
+                if (hm | hm2) {
+                    if (id0 < 0) id0 = hm ? idt : idt2;
+                    found += __popc(hm) + __popc(hm2);
+                    if (hm) or_range(M + lane, 0, (31 - __clz(hm)) - 1);          // bs.set(0, min(L, i+1)), i = n-1
+                    if (hm2) or_range(M + lane, L - (31 - __clz(hm2)), L - 1);    // bs.set(i, L), i = L-n
+                }
+            } else {
+                // ktrim guard (:3868): reads shorter than k still get the tails
+                const bool tscan = live && t.stored > 0 && p.useShortKmers && L >= max(1, min(k, p.mink)) && !found && !skip;
+                if (FMODE == FM_KTRIM_R) tails(std::true_type{}, tscan, hm, idt);
+                else tails(std::false_type{}, tscan, hm, idt);
+                if (hm) {
+                    // lengths n_lo..n_hi hit; reference loop index i = L-n (ktrim=r, descending) or n-1 (ktrim=l, ascending)
+                    const int n_lo = __ffs(hm) - 1, n_hi = 31 - __clz(hm);
+                    if (id0 < 0) id0 = idt;
+                    found += __popc(hm);
+                    if (FMODE == FM_KTRIM_R) {
+                        minLoc = L - n_hi;
+                        minLocX = min(minLocX, L);
+                        maxLoc = L - 1;
+                        maxLocX = max(maxLocX, L - n_lo - 1);
+                    } else {
+                        minLoc = 0;
+                        minLocX = min(minLocX, n_lo);
+                        maxLoc = max(maxLoc, n_hi - 1);
+                        maxLocX = max(maxLocX, 0);
                     }
                 }
             }
-            if (found) {  // :3981-4012
+            if (found && FMODE != FM_KMASK) {  // :3981-4012
                 if (p.trimPad != 0) {
                     maxLoc = mid3(0, maxLoc + p.trimPad, L);
                     minLoc = mid3(0, minLoc - p.trimPad, L);
@@ -766,6 +807,18 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
                 }
                 ktrimmed = count > 0;
             }
+        }
+        if (FMODE == FM_KMASK) {  // cardinality of the BitSet; the mask words go out as they are (zero when nothing was found, :4170)
+            const int nw = (L + 31) >> 5;
+            uint32_t *dst = (live && out.maskbits && out.mask_off) ? out.maskbits + out.mask_off[r] : nullptr;
+#pragma unroll 1
+            for (int w = 0; w < nw; w++) {
+                const uint32_t m = found ? M[w * 32 + lane] : 0u;
+                count += __popc(m);
+                if (dst) dst[w] = m;
+            }
+            ktrimmed = count > 0;
+            if (!found) id0 = -1;
         }
         if (live && id0 > 0 && scaf_reads) {
             atomicAdd(scaf_reads + id0, 1ull);
@@ -810,8 +863,10 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
                 int xsum = count + (paired ? cnt_mate : 0);
                 int rkt = (count > 0) + ((paired && cnt_mate > 0) ? 1 : 0);
                 if (remove) {
-                    xsum += len_pre + (paired ? len_pre_mate : 0);
-                    rkt = paired ? 2 : 1;
+                    if (FMODE != FM_KMASK) {
+                        xsum += len_pre + (paired ? len_pre_mate : 0);
+                        rkt = paired ? 2 : 1;
+                    }
                 } else if (tpe_pair) {
                     if (rkt < 2) rkt++;
                     xsum += x_tpe + x_tpe_mate;
@@ -857,7 +912,8 @@ Fast2Geom make_geom2(const BBParams &p, const BBTable &t, int max_read_len) {
     g.nch = (32 * lmax + 15 + 15) / 16 + 1;
     g.nbadw = (g.nch + 31) / 32 + 1;
     g.sw = ((lmax + 16) >> 5) + 2;
-    int wb = 32 * 8 + 32 * 4 + 16 + g.nbadw * 4 + (g.nch + PAD + TAIL) * 4 + ((g.nch + PAD + TAIL + 1) & ~1) * 2 + QCAP2 * 2 + g.sw * 32 * 4;
+    g.mw = p.mode == MODE_KMASK ? g.sw : 0;
+    int wb = 32 * 8 + 32 * 4 + 16 + g.nbadw * 4 + (g.nch + PAD + TAIL) * 4 + ((g.nch + PAD + TAIL + 1) & ~1) * 2 + QCAP2 * 2 + g.sw * 32 * 4 + g.mw * 32 * 4;
     wb = (wb + 15) & ~15;
     g.warp_bytes = wb;
     g.part_off = t.n_filter_words;
@@ -897,7 +953,9 @@ FastPlan plan_fast2(const BBParams &p, const BBTable &t, int max_read_len) {
         return !(e && atoi(e) == 0);
     }();
     if (!enabled) return pl;
-    const bool mode_ok = (p.mode == MODE_KTRIM) || (p.mode == MODE_KFILTER && p.maxBadKmers0 == 0);
+    // kmask: the plain BitSet mode without padding (kmaskfullycovered and trimpad stay with the generic kernel)
+    const bool mode_ok = (p.mode == MODE_KTRIM) || (p.mode == MODE_KFILTER && p.maxBadKmers0 == 0) ||
+                         (p.mode == MODE_KMASK && !p.kmaskFullyCovered && p.trimPad == 0);
     if (!mode_ok) return pl;
     if (p.qHammingDistance != 0 || (p.useShortKmers && p.qHammingDistance2 != 0)) return pl;
     if (p.speed != 0 || p.qSkip != 1 || p.restrictLeft != 0 || p.restrictRight != 0) return pl;
@@ -930,6 +988,7 @@ int launch_fast2(const FastPlan &plan, const uint8_t *d_bases, const uint32_t *d
     };
     const bool pw11 = t.part_w == 11;
 #define BB_GO2(FM, PK) (pw11 ? go(bbduk_fast2_kernel<FM, PK, true>) : go(bbduk_fast2_kernel<FM, PK, false>))
+    if (p.mode == MODE_KMASK) return pk_F ? -1 : BB_GO2(FM_KMASK, false);  // the host entry never packs for kmask (case matters to its caller)
     if (pk_F) {
         if (!pk_D) return -1;
         if (p.mode == MODE_KFILTER) return BB_GO2(FM_KFILTER, true);

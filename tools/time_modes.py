@@ -19,7 +19,7 @@ MODES = [
     ("k=31 kfilter (tuned)", dict(k=31)),
     ("ktrim=r k=23 (cfg 1 flags: hdist 0, maskmiddle, forbidNs; tuned)", dict(k=23, ktrim_right=1)),
     ("ktrim tips k=23 mink=11 hdist=1 (generic)", dict(k=23, mink=11, hdist=1, ktrim_left=1, ktrim_right=1)),
-    ("kmask ktrim=N k=23 mink=11 hdist=1 (generic)", dict(k=23, mink=11, hdist=1, ktrim_n=1)),
+    ("kmask ktrim=N k=23 mink=11 hdist=1 (tuned since r02l)", dict(k=23, mink=11, hdist=1, ktrim_n=1)),
     ("kfilter mbk=2 k=31 (generic)", dict(k=31, max_bad_kmers=2, mask_middle=0)),
     ("kfilter mcf=0.2 k=25 (generic)", dict(k=25, min_covered_fraction=0.2)),
     ("findbestmatch k=25 (generic)", dict(k=25, find_best_match=1)),
