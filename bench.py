@@ -127,6 +127,34 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def pin_to_gpu_numa_node(local_rank, ranks_on_node):
+    """One process per GPU: keep this rank's threads (and so its first-touch host buffers and the library's packing pool, whose
+    threads inherit the mask) on the NUMA node the GPU hangs off, instead of letting 8 ranks roam over both sockets.
+    BBDUK_B200_NUMA=0 switches it off. Returns a short description for the JSON line."""
+    if os.environ.get("BBDUK_B200_NUMA", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+        return "off"
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return "no numa node reported"
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if len(allowed) < 2:
+            return f"node {node}: too few cpus"
+        os.sched_setaffinity(0, allowed)
+        return f"node {node}: {len(allowed)} cpus"
+    except Exception as e:  # a VM without the sysfs entries: leave the scheduler alone
+        return f"unavailable ({type(e).__name__})"
+
+
 def adapters_ref():
     from bbtools_b200.fasta import read_fasta
     _, b, off = read_fasta(os.path.join(ROOT, "tests", "golden", "adapters.fa"))
@@ -400,6 +428,7 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = pin_to_gpu_numa_node(local_rank, world) if world > 1 else "single rank: not pinned"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -784,7 +813,7 @@ def run_ours(args):
                        "parity_vs_oracle_on_timed_batch": parity, "parity_detail": parity_detail,
                        "kmer_block_plus_tbo": tbo_info,
                        "qtrim_block": qtrim_info, "entropy_block": entropy_info,
-                       "chain_e2e_kmer_tbo": chain_tbo_info, "chain_e2e_kmer_tbo_qtrim": chain_info, "e2e_packed_input": packed_info, "e2e_host_limits": limits},
+                       "chain_e2e_kmer_tbo": chain_tbo_info, "chain_e2e_kmer_tbo_qtrim": chain_info, "e2e_packed_input": packed_info, "e2e_host_limits": limits, "host_numa_pinning": numa},
             "e2e": {"value": e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d_wire), "d2h_bytes_per_step": int(d2h_wire),
                     "host_input_bytes_per_step": h2d, "host_output_bytes_per_step": d2h,
                     "pairs_per_step_per_gpu": e_pairs, "steps": e_steps,
