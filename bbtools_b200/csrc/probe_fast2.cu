@@ -94,8 +94,10 @@ __device__ unsigned long long bb_fast2_dbg[16];
 #define DBG2(i, v)
 #endif
 
-// PW11: the parts are 11 bases wide (k=23 hdist=1, k=23 mm=t hdist=0): the confirmation loops are unrolled for it
-template <int FMODE, bool PACKED, bool PW11>
+// PW11: the parts are 11 bases wide (k=23 hdist=1, k=23 mm=t hdist=0): the confirmation loops are unrolled for it.
+// FN = forbidNs: every window with an undefined base is forced to the exact evaluator; otherwise the all-T pre-pass runs instead --
+// each build carries only its own path (the kernel is bound by instruction fetch)
+template <int FMODE, bool PACKED, bool PW11, bool FN>
 __global__ void __launch_bounds__(1024, 1)
 bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ offsets, int64_t n_reads, int paired, BBParams p,
                    BBTable t, bbduk_out out, bbduk_stats *stats, unsigned long long *scaf_reads, unsigned long long *scaf_bases,
@@ -261,10 +263,13 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
         // as A -- what the scan over F finds anyway -- or with all of them read as T. Only parts that CONTAIN an undefined
         // base differ between the readings: for every undefined base (up to 4 per read, else force_und) one pooled item
         // looks up the 2pw-9 9-mers around it in the T reading and adds the passing part ends to the seed bits.
-        bool force_und = has_undef && scan && p.forbidNs;
-        if (!p.forbidNs && __any_sync(0xFFFFFFFFu, has_undef && scan)) {
-            uint16_t *ntmp = queue + 256;  // [4][32] this lane's undefined positions
-            int n_und = 0;
+        const bool force_und = FN && has_undef && scan;
+        if (!FN && __any_sync(0xFFFFFFFFu, has_undef && scan)) {
+            uint16_t *ntmp = queue + 256;  // [4][32] this lane's undefined positions of this pass
+            int skip_n = 0;                // positions earlier passes have dealt with (a pass takes four per read)
+            bool more;
+          do {
+            int n_und = 0, seen = 0;
             if (has_undef && scan) {
                 const int c0 = s >> 4, c1 = (s + L - 1) >> 4;
 #pragma unroll 1
@@ -282,16 +287,14 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
                         while (ub) {
                             const int b = __ffs(ub) - 1;
                             ub &= ub - 1;
-                            if (n_und < 4) ntmp[n_und * 32 + lane] = (uint16_t)(16 * c + b - s);
-                            n_und++;
+                            if (seen >= skip_n && n_und < 4) ntmp[n_und++ * 32 + lane] = (uint16_t)(16 * c + b - s);
+                            seen++;
                         }
                     }
                 }
-                if (n_und > 4) {
-                    force_und = true;
-                    n_und = 0;
-                }
             }
+            more = seen > skip_n + 4;
+            skip_n += 4;
             const int incl = warp_scan_incl(n_und, lane);
             const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);  // <= 128
             DBG2(7, lane == 0 ? total : 0);
@@ -330,8 +333,9 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
                 }
             }
             __syncwarp();
+          } while (__any_sync(0xFFFFFFFFu, more));
         }
-        const bool any_force = __any_sync(0xFFFFFFFFu, force_und);
+        const bool any_force = FN && __any_sync(0xFFFFFFFFu, force_und);
 
         // ---- B1. sampled scan --------------------------------------------------------------------
         // sample g of the read = the 8-mer that starts at stream byte 4*w0 - 1 + g (w0 = first stream word of the read);
@@ -346,23 +350,29 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
             const int wb = w0 + blk * L1_WORDS;
             const int left = nw - blk * L1_WORDS;  // this lane's words in the block
             uint32_t fprev = Fs[PAD + wb - 1];
+#pragma unroll 1
+            for (int i0 = 0; i0 < L1_WORDS; i0 += 2) {  // partly unrolled: the fully unrolled loop is 6 KB of a 32 KB instruction cache
+                uint32_t acc = 0;
 #pragma unroll
-            for (int i = 0; i < L1_WORDS; i++) {
-                if (blk * L1_WORDS + i < nwmax) {  // warp-uniform
-                    const bool mine = i < left;
-                    const uint32_t f = mine ? Fs[PAD + wb + i] : 0u;
-                    const uint32_t x0 = __byte_perm(__funnelshift_l(f, fprev, 8), 0u, 0x4410);  // (last byte of the previous word, first of this)
-                    const uint32_t x1 = __byte_perm(f, 0u, 0x4432);
-                    const uint32_t x2 = __byte_perm(f, 0u, 0x4421);
-                    const uint32_t x3 = __byte_perm(f, 0u, 0x4410);
-                    uint32_t h = (uint32_t)samp[x0] + 2u * (uint32_t)samp[x1] + 4u * (uint32_t)samp[x2] + 8u * (uint32_t)samp[x3];
-                    if (!mine) h = 0;
-                    if (i < 8)
-                        acc_lo += h << (4 * i);
-                    else
-                        acc_hi += h << (4 * (i - 8));
-                    fprev = f;
+                for (int j = 0; j < 2; j++) {
+                    const int i = i0 + j;
+                    if (blk * L1_WORDS + i < nwmax) {  // warp-uniform
+                        const bool mine = i < left;
+                        const uint32_t f = mine ? Fs[PAD + wb + i] : 0u;
+                        const uint32_t x0 = __byte_perm(__funnelshift_l(f, fprev, 8), 0u, 0x4410);  // (last byte of the previous word, first of this)
+                        const uint32_t x1 = __byte_perm(f, 0u, 0x4432);
+                        const uint32_t x2 = __byte_perm(f, 0u, 0x4421);
+                        const uint32_t x3 = __byte_perm(f, 0u, 0x4410);
+                        uint32_t h = (uint32_t)samp[x0] + 2u * (uint32_t)samp[x1] + 4u * (uint32_t)samp[x2] + 8u * (uint32_t)samp[x3];
+                        if (!mine) h = 0;
+                        acc += h << (4 * j);
+                        fprev = f;
+                    }
                 }
+                if (i0 < 8)
+                    acc_lo += acc << (4 * i0);
+                else
+                    acc_hi += acc << (4 * (i0 - 8));
             }
             // keep the samples inside the read
             {
@@ -464,7 +474,7 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
                 if (rem < 32) u &= (1u << rem) - 1u;
                 return u;
             };
-            if (any_force && force_und) und_c = und_word(ncwmax - 1);
+            if (FN && any_force && force_und) und_c = und_word(ncwmax - 1);
             // no seed bit in the whole tile and nothing forced (most tiles of reads without adapters): S is all zero already
             const int c_top = (any_force || misc[0] != 0u) ? ncwmax - 1 : -1;
 #pragma unroll 1
@@ -473,7 +483,7 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
                 uint32_t cb = __funnelshift_l(sp, sc, lag0);
                 if (t.n_parts > 1) cb |= __funnelshift_l(sp, sc, lag1);
                 if (t.n_parts > 2) cb |= __funnelshift_l(sp, sc, lag2) | __funnelshift_l(sp, sc, lag3);
-                if (any_force) {  // rare: every window that contains an undefined base is decided by the exact evaluator
+                if (FN && any_force) {  // every window that contains an undefined base is decided by the exact evaluator
                     if (force_und) {
                         const uint32_t und_p = und_word(c - 1);
                         cb |= (uint32_t)(smear_left64(((uint64_t)und_c << 32) | und_p, k) >> 32);
@@ -659,26 +669,26 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
                             const uint32_t wlo = (uint32_t)W, whi = (uint32_t)(W >> 32);
                             uint32_t pass = 0;
 #pragma unroll 1
-                            for (int n = nlo; n <= ntop; n += 4) {
-                                uint32_t u[4], w0[4];
+                            for (int n = nlo; n <= ntop; n += 2) {
+                                uint32_t u[2], w0[2];
 #pragma unroll
-                                for (int j = 0; j < 4; j++) {
+                                for (int j = 0; j < 2; j++) {
                                     const int sh = (RIGHT) ? 2 * (n + j - 8) : 2 * (nmax - n - j + q - 8);
                                     const uint32_t lo_ = (sh & 32) ? whi : wlo, hi_ = (sh & 32) ? 0u : whi;
                                     u[j] = __funnelshift_r(lo_, hi_, sh & 31) & 0xFFFFu;
                                     w0[j] = tail0[u[j] >> 5];
                                 }
 #pragma unroll
-                                for (int j = 0; j < 4; j++) pass |= ((w0[j] >> (u[j] & 31u)) & 1u) << ((n + j) & 31);
+                                for (int j = 0; j < 2; j++) pass |= ((w0[j] >> (u[j] & 31u)) & 1u) << ((n + j) & 31);
                             }
                             ask &= pass;
                         }
 #pragma unroll 1
                         while (ask) {  // up to four lookups in flight
-                            uint32_t v[4], wv[4];
-                            int nn[4];
+                            uint32_t v[2], wv[2];
+                            int nn[2];
 #pragma unroll
-                            for (int j = 0; j < 4; j++) {
+                            for (int j = 0; j < 2; j++) {
                                 nn[j] = ask ? __ffs(ask) - 1 : -1;
                                 ask &= ask - 1;
                                 const int sh = (RIGHT) ? 2 * (nn[j] - q) : 2 * (nmax - nn[j]);
@@ -686,7 +696,7 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
                                 wv[j] = nn[j] >= 0 ? __ldg(b_len + (v[j] >> 5)) : 0u;
                             }
 #pragma unroll
-                            for (int j = 0; j < 4; j++) todo |= ((wv[j] >> (v[j] & 31u)) & 1u) << (nn[j] & 31);
+                            for (int j = 0; j < 2; j++) todo |= ((wv[j] >> (v[j] & 31u)) & 1u) << (nn[j] & 31);
                         }
                         if (nmax < q || ((wa >> (va & 31u)) & 1u)) todo = all;
                         if (!RIGHT && nmax == k) todo |= (k >= 31 ? 0x80000000u : (1u << k));  // a prefix of k bases is a full-length key
@@ -987,7 +997,10 @@ int launch_fast2(const FastPlan &plan, const uint8_t *d_bases, const uint32_t *d
         return cudaGetLastError() == cudaSuccess ? 1 : -1;
     };
     const bool pw11 = t.part_w == 11;
-#define BB_GO2(FM, PK) (pw11 ? go(bbduk_fast2_kernel<FM, PK, true>) : go(bbduk_fast2_kernel<FM, PK, false>))
+    const bool fn = p.forbidNs != 0;
+#define BB_GO2(FM, PK)                                                                                                  \
+    (pw11 ? (fn ? go(bbduk_fast2_kernel<FM, PK, true, true>) : go(bbduk_fast2_kernel<FM, PK, true, false>))             \
+          : (fn ? go(bbduk_fast2_kernel<FM, PK, false, true>) : go(bbduk_fast2_kernel<FM, PK, false, false>)))
     if (p.mode == MODE_KMASK) return pk_F ? -1 : BB_GO2(FM_KMASK, false);  // the host entry never packs for kmask (case matters to its caller)
     if (pk_F) {
         if (!pk_D) return -1;
