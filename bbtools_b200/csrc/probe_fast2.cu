@@ -33,8 +33,8 @@ namespace {
 
 using namespace bbfast;
 
-constexpr int QCAP2 = 512;     // pooled queue entries (16 bit each): sample hits of one pass / candidates of one round
-constexpr int ITEM_CAP = 16;   // sample hits one read contributes per pass (32 x 16 = QCAP2)
+constexpr int QCAP2 = 256;     // pooled queue entries (16 bit each): sample hits / tail lengths of one pass (512 B per warp: 32 warps fit)
+constexpr int ITEM_CAP = 8;    // items one read contributes per pass (32 x 8 = QCAP2)
 constexpr int L1_WORDS = 12;   // stream words (16 bases each) one unrolled block of the sampled scan covers
 constexpr int SPELL_WORDS = 256;  // the "what do these four codes spell" table of stage A
 
@@ -265,7 +265,7 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
         // looks up the 2pw-9 9-mers around it in the T reading and adds the passing part ends to the seed bits.
         const bool force_und = FN && has_undef && scan;
         if (!FN && __any_sync(0xFFFFFFFFu, has_undef && scan)) {
-            uint16_t *ntmp = queue + 256;  // [4][32] this lane's undefined positions of this pass
+            uint16_t *ntmp = queue + 128;  // [4][32] this lane's undefined positions of this pass (the pass queues at most 128 items in front of it)
             int skip_n = 0;                // positions earlier passes have dealt with (a pass takes four per read)
             bool more;
           do {
@@ -940,6 +940,11 @@ Fast2Geom make_geom2(const BBParams &p, const BBTable &t, int max_read_len) {
         g.tail0_off = g.tail_off + 2 * tail_main + (p.ktrimLeft ? BB_TAIL0_WORDS : 0u);
     const int avail = FAST_SMEM_LIMIT - (SPELL_WORDS + 16384 + (int)BB_PART_WORDS + (g.tail0_off ? (int)BB_TAIL0_WORDS : 0)) * 4 - 64;
     g.warps = std::min(32, avail / wb);
+    static const int warp_cap = [] {  // A/B knob: fewer warps = fewer phases of the loop in flight per scheduler
+        const char *e = getenv("BBDUK_B200_FAST2_WARPS");
+        return e ? atoi(e) : 0;
+    }();
+    if (warp_cap >= 8) g.warps = std::min(g.warps, warp_cap);
     return g;
 }
 
