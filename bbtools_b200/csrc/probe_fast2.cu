@@ -178,6 +178,16 @@ bbduk_fast2_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict
             }
             continue;
         }
+        // this warp's NEXT tile on its way from DRAM to L2 while this one is worked on (its ASCII is as long as this tile's to a
+        // first approximation: a prefetch is only a hint, a wrong guess costs nothing but the line)
+        if (!PACKED) {
+            const int64_t rn0 = (tile + warps_total) * 32;
+            if (rn0 < n_reads) {
+                const uintptr_t an = (base_addr + __ldg(offsets + rn0)) & ~(uintptr_t)127;
+                const int nl = (int)((tile_hi - tile_lo + 255) >> 7);
+                for (int i = lane; i < nl; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(an + (uintptr_t)i * 128));
+            }
+        }
         // ---- A. stage + convert ---------------------------------------------------------------
 #pragma unroll 1
         for (int i = lane; i < geo.nbadw; i += 32) badw[i] = 0;

@@ -36,13 +36,13 @@ FALLBACK_HBM_GBS = 6650.0
 # captures of the same workloads (a profiler cannot run inside the timed bench; the captures are re-taken whenever the
 # kernel changes and the JSON line names the file: roofline.traffic_source);
 # cfg 5: profiles/r01_e_kcount_kernel.txt: 28.33 GB + 6.91 GB for 217.6 M k-mers = 162 B per k-mer
-NCU_TRAFFIC_BYTES_PER_READ = {"cfg2": (1302081000 + 74900224) / 8388608,  # profiles/r02j_fast2_kernel_raw.txt: an 8,388,608-read launch of bbduk_fast2_kernel
+NCU_TRAFFIC_BYTES_PER_READ = {"cfg2": (1299953000 + 75363840) / 8388608,  # profiles/r02n_fast2_kernel_raw.txt: an 8,388,608-read launch of bbduk_fast2_kernel
                               # profiles/r02_cfg3_direct_kernel_details.txt / r02_cfg4_...: 4,194,304-read launches of bbduk_direct_kernel
                               "cfg3": (30556543000 + 93049088) / 4194304, "cfg4": (35478975000 + 113840128) / 4194304,
                               "cfg5": 120 * (28328275000 + 6911184000) / 217637790}
 
 
-TRAFFIC_SOURCE = {"cfg2": "profiles/r02j_fast2_kernel_raw.txt", "cfg3": "profiles/r02_cfg3_direct_kernel_details.txt",
+TRAFFIC_SOURCE = {"cfg2": "profiles/r02n_fast2_kernel_raw.txt", "cfg3": "profiles/r02_cfg3_direct_kernel_details.txt",
                   "cfg4": "profiles/r02_cfg4_direct_kernel_details.txt", "cfg5": "profiles/r01_e_kcount_kernel.txt"}
 
 
