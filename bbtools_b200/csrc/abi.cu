@@ -71,7 +71,14 @@ struct bbduk_handle {
     std::atomic<int> max_read_len_hint{0};
     bool trace = false;     // BBDUK_B200_TRACE=1: per-chunk host timings on stderr
     bool ascii_every_set = false;
-    int ascii_every = 3;    // BBDUK_B200_ASCII_EVERY=n: every n-th chunk crosses PCIe as ASCII (0 = never)
+    int ascii_every = 3;    // BBDUK_B200_ASCII_EVERY=n: every n-th chunk crosses PCIe as ASCII (0 = never); unset = adaptive
+    // adaptive share of ASCII chunks: the workers' packing rate is measured (seconds per base, moving average) and set against
+    // the link (BBDUK_B200_PCIE_GBS, default 52): packing a chunk costs tp of CPU and 0.375 tb of link, shipping it as ASCII
+    // costs tb of link and no CPU; both resources are busy the same time when x = (tp - 0.375 tb) / (tp + 0.625 tb) of the
+    // chunks go ASCII
+    double pack_s_per_base = 0.0;
+    double ascii_acc = 0.0;
+    double pcie_gbs = 52.0;
     bool pack_host = true;  // BBDUK_B200_PACK_HOST=0 keeps the bases ASCII across PCIe
     std::mutex err_mu;
     std::string err;
@@ -420,6 +427,9 @@ int bbduk_b200_create(const bbduk_cfg *cfg, bbduk_handle **out) {
         h->ascii_every = std::max(0, atoi(e));
         h->ascii_every_set = true;
     }
+    if (const char *e = getenv("BBDUK_B200_PCIE_GBS")) {
+        if (atof(e) > 1.0) h->pcie_gbs = atof(e);
+    }
     *out = h;
     return 0;
 }
@@ -710,8 +720,19 @@ static int process_host_impl(bbduk_handle *h, const uint8_t *bases, const uint32
             // host packing is bound by the host's memory bandwidth, the ASCII path by PCIe: every n-th chunk goes
             // ASCII (no CPU work, DMA straight from the caller's buffer) so that both resources are used
             // (never the last chunk of a call: its transfer is the tail nothing overlaps with)
-            if (!pre && packed && src_pinned && h->ascii_every > 0 && (chunk_no % h->ascii_every) == h->ascii_every - 1 && r1 < n_reads)
-                packed = false;
+            if (!pre && packed && src_pinned && r1 < n_reads) {
+                if (h->ascii_every_set || h->pack_s_per_base <= 0.0) {  // fixed share (or nothing measured yet)
+                    if (h->ascii_every > 0 && (chunk_no % h->ascii_every) == h->ascii_every - 1) packed = false;
+                } else {
+                    const double tp = h->pack_s_per_base, tb = 1.0 / (h->pcie_gbs * 1e9);
+                    const double x = std::min(0.75, std::max(0.0, (tp - 0.375 * tb) / (tp + 0.625 * tb)));
+                    h->ascii_acc += x;
+                    if (h->ascii_acc >= 1.0) {
+                        h->ascii_acc -= 1.0;
+                        packed = false;
+                    }
+                }
+            }
             chunk_no++;
         }
         if ((packed || pre) && !rc) rc = ensure_packed(h, s, nr, nb);
@@ -755,9 +776,12 @@ static int process_host_impl(bbduk_handle *h, const uint8_t *bases, const uint32
                 const int64_t i0 = (nr + 1) * part / n_parts, i1 = (nr + 1) * (part + 1) / n_parts;
                 for (int64_t i = i0; i < i1; i++) sp->h_off32[i] = (uint32_t)(osrc[i] - osrc[0]);
             });
-            if (h->trace)
-                fprintf(stderr, "[bbduk_b200] packed %lld bases in %.3f ms on %d threads\n", (long long)nb,
-                        1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_pack0).count(), h->pool->size());
+            {
+                const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_pack0).count();
+                if (nb > (1 << 20)) h->pack_s_per_base = h->pack_s_per_base <= 0.0 ? dt / (double)nb : 0.75 * h->pack_s_per_base + 0.25 * dt / (double)nb;
+                if (h->trace)
+                    fprintf(stderr, "[bbduk_b200] packed %lld bases in %.3f ms on %d threads\n", (long long)nb, 1e3 * dt, h->pool->size());
+            }
             CKL((h->h2d_bytes += (int64_t)(sizeof(uint32_t) * groups), cudaMemcpyAsync(s.d_F, s.h_F, sizeof(uint32_t) * groups, cudaMemcpyHostToDevice, st)));
             CKL((h->h2d_bytes += (int64_t)(sizeof(uint16_t) * groups), cudaMemcpyAsync(s.d_D, s.h_D, sizeof(uint16_t) * groups, cudaMemcpyHostToDevice, st)));
             CKL((h->h2d_bytes += (int64_t)(sizeof(uint32_t) * (nr + 1)), cudaMemcpyAsync(s.d_off32, s.h_off32, sizeof(uint32_t) * (nr + 1), cudaMemcpyHostToDevice, st)));
