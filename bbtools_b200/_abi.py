@@ -3,7 +3,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 GEN_JGI = 0
 GEN_S = 1
 
@@ -112,7 +112,10 @@ class BBDukQtrimCfg(C.Structure):
         ("max_non_poly", C.c_int32),
         ("min_avg_quality", C.c_float),
         ("min_avg_quality_bases", C.c_int32),
-        ("reserved", C.c_int32 * 2),
+        ("max_n_rate", C.c_float),
+        ("min_consecutive_bases", C.c_int32),
+        ("min_base_frequency", C.c_float),
+        ("reserved", C.c_int32 * 1),
     ]
 
 

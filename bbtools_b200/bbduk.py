@@ -50,7 +50,7 @@ def parse_args(args, generation=GEN_JGI):
           "qtrim_left": False, "qtrim_right": False, "trimq": 6.0, "mbq": 0, "maxns": -1, "maxlen": 0,
           "trimpolya": 0, "trimpolygleft": 0, "trimpolygright": 0, "filterpolyg": 0, "trimpolycleft": 0, "trimpolycright": 0,
           "filterpolyc": 0, "maxnonpoly": 1, "entropy": -1.0, "entropyk": 5, "entropywindow": 50,
-          "maq": 0.0, "maqb": 0}
+          "maq": 0.0, "maqb": 0, "maxnrate": 1.0, "mcb": 0, "minbasefrequency": 0.0}
     for arg in args:
         sp = arg.split("=")
         a = sp[0].lower()
@@ -251,6 +251,13 @@ def parse_args(args, generation=GEN_JGI):
             io["mbq"] = int(b)
         elif a == "maxns":
             io["maxns"] = int(b)
+        elif a in ("maxnrate", "maxnfraction"):  # parse/Parser.java:510-513: a fraction, or a percentage when above 1
+            v = float(b)
+            io["maxnrate"] = v / 100 if v > 1 else (v if v >= 0 else 1.0)  # unset / negative = 1 = off (jgi/BBDuk.java:629)
+        elif a in ("minconsecutivebases", "mcb"):
+            io["mcb"] = int(b)
+        elif a == "minbasefrequency":  # jgi/BBDuk.java:465-466
+            io["minbasefrequency"] = float(b)
         elif a in ("maxlength", "maxreadlength", "maxreadlen", "maxlen"):
             io["maxlen"] = int(b)
         elif a in ("trimpolya", "trimpolygleft", "trimpolygright", "filterpolyg", "trimpolycleft", "trimpolycright", "filterpolyc",
@@ -692,7 +699,7 @@ class BBDuk:
         poly = any(io[k] > 0 for k in ("trimpolya", "trimpolygleft", "trimpolygright", "filterpolyg", "trimpolycleft",
                                        "trimpolycright", "filterpolyc"))
         return bool(io["qtrim_left"] or io["qtrim_right"] or io["mbq"] > 0 or io["maxns"] >= 0 or io["maxlen"] > 0 or io["tbo"] or poly or
-                    io["maq"] > 0)
+                    io["maq"] > 0 or io["maxnrate"] < 1 or io["mcb"] > 0 or io["minbasefrequency"] > 0)
 
     def _qtrim(self, bases, quals, offsets, paired, out):
         """quality trimming, minlen / maxlen, mbq, maxns (jgi/BBDuk.java:3074-3170); updates out.lo / out.hi / out.flags"""
@@ -706,7 +713,8 @@ class BBDuk:
                                    trim_poly_g_right=io["trimpolygright"], filter_poly_g=io["filterpolyg"],
                                    trim_poly_c_left=io["trimpolycleft"], trim_poly_c_right=io["trimpolycright"],
                                    filter_poly_c=io["filterpolyc"], max_non_poly=io["maxnonpoly"], min_avg_quality=io["maq"],
-                                   min_avg_quality_bases=io["maqb"])
+                                   min_avg_quality_bases=io["maqb"], max_n_rate=io["maxnrate"], min_consecutive_bases=io["mcb"],
+                                   min_base_frequency=io["minbasefrequency"])
 
     def _entropy_cfg(self):
         io = self.io

@@ -982,6 +982,7 @@ void bbduk_b200_qtrim_cfg_default(bbduk_qtrim_cfg *c) {
     c->max_ns = -1;
     c->qual_offset = 33;
     c->max_non_poly = 1;  // parse/Parser.java:1831
+    c->max_n_rate = 1.0f; // jgi/BBDuk.java:629: unset = 1 = no-op
 }
 
 static int check_qtrim_cfg(bbduk_handle *h, const bbduk_qtrim_cfg *cfg, const void *quals) {

@@ -35,6 +35,8 @@ struct QtrimDev {
     int rieb, tf1;
     int poly_a, poly_g_left, poly_g_right, filter_g, poly_c_left, poly_c_right, filter_c, max_non_poly;
     int maq_on, maq_bases;
+    float max_n_rate, min_base_freq;  // maxnrate (>= 1 = off), minbasefrequency (0 = off)
+    int mcb;                          // minconsecutivebases (0 = off)
     float maq_prob;    // discard iff expectedErrors / bases >= maq_prob  (<=> phred average < minavgquality, see launch_qtrim)
     float delta[256];  // per raw quality byte: trimE - probError (trimE - nprob for q < 1)
     float pe[256];     // per raw quality byte: PROB_ERROR[max(q, 0)] (only staged when maq is on)
@@ -363,6 +365,38 @@ qtrim_kernel(const uint8_t *__restrict__ bases, const uint8_t *__restrict__ qual
                     set_disc();
                 }
             }
+            // :3138-3149 the same as a fraction of the read length; r.discarded() is the raw flag (no double count after maxns)
+            if (p.max_n_rate < 1.0f && !discarded) {
+                int nu = 0;
+                for (int i = l; i < h; i++) nu += defined_base(bases[o0 + i]) ? 0 : 1;
+                if ((float)nu > __fmul_rn(p.max_n_rate, (float)(h - l))) {
+                    s_rn += 1;
+                    s_bn += (unsigned int)(h - l);
+                    set_disc();
+                }
+            }
+            // :3151-3154 Read.hasMinConsecutiveBases (stream/Read.java:2846-2858): some run of mcb defined bases
+            if (p.mcb > 0 && !is_disc()) {
+                int run = 0;
+                bool ok = false;
+                for (int i = l; i < h && !ok; i++) {
+                    run = defined_base(bases[o0 + i]) ? run + 1 : 0;
+                    ok = run >= p.mcb;
+                }
+                if (!ok) set_disc();
+            }
+            // :3156-3159 Read.minBaseCount (stream/Read.java:2864-2874): upper-case A, C, G, T only
+            if (p.min_base_freq > 0.0f) {
+                int na = 0, nc = 0, ng = 0, nt = 0;
+                for (int i = l; i < h; i++) {
+                    const uint8_t b = bases[o0 + i];
+                    na += b == 'A';
+                    nc += b == 'C';
+                    ng += b == 'G';
+                    nt += b == 'T';
+                }
+                if ((float)min(min(na, nc), min(ng, nt)) < __fmul_rn(p.min_base_freq, (float)(h - l))) set_disc();
+            }
         }
         // :3162-3167 shouldRemove after quality filtering
         const bool d2 = is_disc();
@@ -411,6 +445,9 @@ int launch_qtrim(int sm_count, const bbduk_qtrim_cfg *cfg, const BBParams &bp, c
     p.qtrim_right = cfg->qtrim_right != 0;
     p.mbq = cfg->min_base_quality;
     p.max_ns = cfg->max_ns;
+    p.max_n_rate = cfg->max_n_rate;
+    p.mcb = cfg->min_consecutive_bases;
+    p.min_base_freq = cfg->min_base_frequency;
     p.max_len = cfg->max_read_length > 0 ? cfg->max_read_length : 0x7FFFFFFF;
     p.qual_offset = cfg->qual_offset;
     p.minReadLength = bp.minReadLength;

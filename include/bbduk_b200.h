@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define BBDUK_B200_ABI_VERSION 1
+#define BBDUK_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define BBDUK_API __attribute__((visibility("default")))
@@ -333,7 +333,13 @@ typedef struct bbduk_qtrim_cfg {
     int32_t max_non_poly;      /* maxnonpoly= ; default 1 */
     float   min_avg_quality;   /* maq= / minavgquality= ; 0 = off (average by error probability, stream/Read.java:2181-2226) */
     int32_t min_avg_quality_bases; /* maq=Q,N / maqb= : only the first N bases; 0 = all */
-    int32_t reserved[2];
+    float   max_n_rate;        /* maxnrate= / maxnfraction= ; a read with more than rate * length undefined bases is discarded
+                                  (jgi/BBDuk.java:3138-3149); >= 1 (the default, 1) = off */
+    int32_t min_consecutive_bases; /* mcb= / minconsecutivebases= ; reads without a run of that many defined bases are discarded
+                                  (jgi/BBDuk.java:3151-3154, stream/Read.java:2846-2858); 0 = off */
+    float   min_base_frequency; /* minbasefrequency= ; reads whose rarest of A C G T (upper case, stream/Read.java:2864-2874)
+                                  occurs fewer than frequency * length times are discarded (jgi/BBDuk.java:3156-3159); 0 = off */
+    int32_t reserved[1];
 } bbduk_qtrim_cfg;
 BBDUK_API void bbduk_b200_qtrim_cfg_default(bbduk_qtrim_cfg *cfg);
 
@@ -342,7 +348,7 @@ BBDUK_API void bbduk_b200_qtrim_cfg_default(bbduk_qtrim_cfg *cfg);
  * shouldRemove; the reference's poly-C filter of r2 looks at r1, :3035, and so does this), then TrimRead.trimFast in its default
  * "optimal" mode (shared/TrimRead.java:113-169, :348-410: the maximum-sum run of avgErrorRate - probError, single
  * precision, then trimByAmount(r, a, b, 1)), the minlen / maxlen test, shouldRemove, then minavgquality, minbasequality and
- * maxns with their shouldRemove (jgi/BBDuk.java:3074-3170; maxnrate, minconsecutivebases and minbasefrequency are at their
+ * maxns, maxnrate, minconsecutivebases and minbasefrequency with their shouldRemove (jgi/BBDuk.java:3074-3170; (the rest is at its
  * defaults = off). minavgquality compares -10*log10(expectedErrors/bases) in double precision with the threshold; the
  * device compares the error probability with the smallest float for which that test holds (found on the host with the
  * C library's log10), which is the same predicate. paired != 0: reads (2i, 2i+1) are mates. Units whose flags carry BBDUK_F_REMOVED are skipped.

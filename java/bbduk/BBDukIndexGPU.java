@@ -358,12 +358,14 @@ public final class BBDukIndexGPU extends BBDukIndex {
 	 * answered (replaces jgi/BBDuk.java:2954-3052, :3074-3170): lo[] / hi[] / flags[] are updated in place; stats8 +=
 	 * {readsQTrimmed, basesQTrimmed, readsQFiltered, basesQFiltered, readsNFiltered, basesNFiltered, readsPolyTrimmed,
 	 * basesPolyTrimmed}. quals = Read.quality, flattened. poly = {trimPolyA, trimPolyGLeft, trimPolyGRight, filterPolyG,
-	 * trimPolyCLeft, trimPolyCRight, filterPolyC, maxNonPoly}. */
+	 * trimPolyCLeft, trimPolyCRight, filterPolyC, maxNonPoly}. maxNRate (>= 1 = off), minConsecutiveBases and minBaseFrequency
+	 * (0 = off) are the filters of jgi/BBDuk.java:3138-3159; the two rates travel as raw float bits in the int vector. */
 	boolean qtrimBatch(long h, boolean qtrimLeft, boolean qtrimRight, float trimq, int minBaseQuality, int maxNs, int maxReadLength,
-			int[] poly, byte[] bases, byte[] quals, long[] offsets, long nReads, boolean paired, int[] lo, int[] hi, byte[] flags,
-			long[] stats8){
+			int[] poly, float maxNRate, int minConsecutiveBases, float minBaseFrequency, byte[] bases, byte[] quals, long[] offsets,
+			long nReads, boolean paired, int[] lo, int[] hi, byte[] flags, long[] stats8){
 		final int[] cfg={qtrimLeft ? 1 : 0, qtrimRight ? 1 : 0, minBaseQuality, maxNs, maxReadLength, 0,
-				poly[0], poly[1], poly[2], poly[3], poly[4], poly[5], poly[6], poly[7]};
+				poly[0], poly[1], poly[2], poly[3], poly[4], poly[5], poly[6], poly[7],
+				minConsecutiveBases, Float.floatToRawIntBits(maxNRate), Float.floatToRawIntBits(minBaseFrequency)};
 		return qtrimNative(h, cfg, trimq, bases, quals, offsets, nReads, paired, lo, hi, flags, stats8)==0;
 	}
 

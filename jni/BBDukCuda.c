@@ -247,7 +247,7 @@ JNIEXPORT jint JNICALL Java_bbduk_BBDukIndexGPU_tboNative(JNIEnv *env, jclass cl
  * stats8 += {readsQTrimmed, basesQTrimmed, readsQFiltered, basesQFiltered, readsNFiltered, basesNFiltered, readsPolyTrimmed,
  * basesPolyTrimmed}. qCfg = {qtrimLeft, qtrimRight, minBaseQuality, maxNs (-1 off), maxReadLength (0 unlimited), qualOffset
  * (0 for Read.quality), trimPolyA, trimPolyGLeft, trimPolyGRight, filterPolyG, trimPolyCLeft, trimPolyCRight, filterPolyC,
- * maxNonPoly}. */
+ * maxNonPoly, minConsecutiveBases, floatToRawIntBits(maxNRate), floatToRawIntBits(minBaseFrequency)} (17 ints). */
 static void qcfg_from(const jint *c, jfloat trimq, bbduk_qtrim_cfg *cfg) {
     bbduk_b200_qtrim_cfg_default(cfg);
     cfg->qtrim_left = c[0];
@@ -264,6 +264,14 @@ static void qcfg_from(const jint *c, jfloat trimq, bbduk_qtrim_cfg *cfg) {
     cfg->trim_poly_c_right = c[11];
     cfg->filter_poly_c = c[12];
     cfg->max_non_poly = c[13];
+    cfg->min_consecutive_bases = c[14];
+    { /* the two rates travel as Float.floatToRawIntBits in the int vector */
+        union { jint i; float f; } u;
+        u.i = c[15];
+        cfg->max_n_rate = u.f;
+        u.i = c[16];
+        cfg->min_base_frequency = u.f;
+    }
     cfg->trimq = trimq;
 }
 
@@ -272,13 +280,13 @@ JNIEXPORT jint JNICALL Java_bbduk_BBDukIndexGPU_qtrimNative(JNIEnv *env, jclass 
                                                             jboolean paired, jintArray jlo, jintArray jhi, jbyteArray jflags,
                                                             jlongArray jstats8) {
     bbduk_qtrim_cfg cfg;
-    jint c[14];
+    jint c[17];
     int64_t st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint8_t *b, *q, *fl;
     int64_t *o;
     int32_t *lo, *hi;
     const size_t n = (size_t)(nReads > 0 ? nReads : 0);
-    (*env)->GetIntArrayRegion(env, jcfg, 0, 14, c);
+    (*env)->GetIntArrayRegion(env, jcfg, 0, 17, c);
     qcfg_from(c, trimq, &cfg);
     if (stage_in(env, jbases, jquals, joffsets, nReads, &b, &q, &o) || stage_state(env, jlo, jhi, jflags, n, &lo, &hi, &fl)) return 1;
     const jint rc = bbduk_b200_qtrim(H(handle), &cfg, b, q, o, (int64_t)nReads, paired ? 1 : 0, lo, hi, fl, st);
@@ -328,7 +336,7 @@ JNIEXPORT jint JNICALL Java_bbduk_BBDukIndexGPU_processChainNative(JNIEnv *env, 
                                                                    jlong nReads, jboolean paired, jintArray jid0, jintArray jlo,
                                                                    jintArray jhi, jbyteArray jflags, jlongArray jstats28) {
     bbduk_chain_cfg cfg;
-    jint st3[3], t[6], q[14], e[3];
+    jint st3[3], t[6], q[17], e[3];
     jfloat f[3];
     bbduk_out out;
     bbduk_stats st;
@@ -341,7 +349,7 @@ JNIEXPORT jint JNICALL Java_bbduk_BBDukIndexGPU_processChainNative(JNIEnv *env, 
     bbduk_b200_chain_cfg_default(&cfg);
     (*env)->GetIntArrayRegion(env, jsteps, 0, 3, st3);
     (*env)->GetIntArrayRegion(env, jtbo, 0, 6, t);
-    (*env)->GetIntArrayRegion(env, jq, 0, 14, q);
+    (*env)->GetIntArrayRegion(env, jq, 0, 17, q);
     (*env)->GetIntArrayRegion(env, je, 0, 3, e);
     (*env)->GetFloatArrayRegion(env, jfl, 0, 3, f); /* {meeFilter, trimq, entropyCutoff} */
     cfg.do_tbo = st3[0];

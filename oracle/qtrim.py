@@ -15,7 +15,8 @@ class QtrimParams(C.Structure):
                 ("trim_failures_to_1bp", C.c_int32), ("trim_poly_a", C.c_int32), ("trim_poly_g_left", C.c_int32),
                 ("trim_poly_g_right", C.c_int32), ("filter_poly_g", C.c_int32), ("trim_poly_c_left", C.c_int32),
                 ("trim_poly_c_right", C.c_int32), ("filter_poly_c", C.c_int32), ("max_non_poly", C.c_int32),
-                ("min_avg_quality", C.c_float), ("min_avg_quality_bases", C.c_int32)]
+                ("min_avg_quality", C.c_float), ("min_avg_quality_bases", C.c_int32),
+                ("max_n_rate", C.c_float), ("min_consecutive_bases", C.c_int32), ("min_base_frequency", C.c_float)]
 
 
 _LIB = None
@@ -32,7 +33,8 @@ def lib():
 
 
 def params(qtrim="rl", trimq=6.0, mbq=0, maxns=-1, maxlen=0, qual_offset=33, minlen=10, mlf=0.0, rieb=True, tf1=False,
-           polya=0, polyg=(0, 0), fpolyg=0, polyc=(0, 0), fpolyc=0, maxnonpoly=1, maq=0.0, maqb=0) -> QtrimParams:
+           polya=0, polyg=(0, 0), fpolyg=0, polyc=(0, 0), fpolyc=0, maxnonpoly=1, maq=0.0, maqb=0, maxnrate=1.0, mcb=0,
+           mbf=0.0) -> QtrimParams:
     """defaults of jgi/BBDuk.java (:126 trimq, minlen 10, rieb) for the fields the block reads"""
     p = QtrimParams()
     p.qtrim_left, p.qtrim_right = int("l" in qtrim), int("r" in qtrim)
@@ -42,6 +44,7 @@ def params(qtrim="rl", trimq=6.0, mbq=0, maxns=-1, maxlen=0, qual_offset=33, min
     p.trim_poly_a, p.filter_poly_g, p.filter_poly_c, p.max_non_poly = polya, fpolyg, fpolyc, maxnonpoly
     (p.trim_poly_g_left, p.trim_poly_g_right), (p.trim_poly_c_left, p.trim_poly_c_right) = polyg, polyc
     p.min_avg_quality, p.min_avg_quality_bases = maq, maqb
+    p.max_n_rate, p.min_consecutive_bases, p.min_base_frequency = maxnrate, mcb, mbf
     return p
 
 

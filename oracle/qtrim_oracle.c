@@ -41,6 +41,10 @@ typedef struct qtrim_params {
     /* minavgquality= (parse/Parser.java:516-526) */
     float min_avg_quality;
     int32_t min_avg_quality_bases;
+    /* maxnrate= (>= 1 = off), minconsecutivebases=, minbasefrequency= (jgi/BBDuk.java:3138-3159) */
+    float max_n_rate;
+    int32_t min_consecutive_bases;
+    float min_base_frequency;
 } qtrim_params;
 
 static float g_pe[128];
@@ -366,6 +370,55 @@ void qtrim_ora_process(const uint8_t *bases, const uint8_t *quals, const int64_t
                         stats[5] += rr[q].hi - rr[q].lo;
                         set_discarded(p, &rr[q]);
                     }
+                }
+            }
+            /* jgi/BBDuk.java:3136-3149: the same as a fraction of the read length; r.discarded() is the raw flag */
+            if (p->max_n_rate < 1) {
+                for (int q = 0; q < per; q++) {
+                    if (rr[q].discarded) continue;
+                    int n = 0;
+                    for (int i = rr[q].lo; i < rr[q].hi; i++) n += is_defined(rr[q].bases[i]) ? 0 : 1;
+                    if ((float)n > p->max_n_rate * (float)(rr[q].hi - rr[q].lo)) {
+                        stats[4] += 1;
+                        stats[5] += rr[q].hi - rr[q].lo;
+                        set_discarded(p, &rr[q]);
+                    }
+                }
+            }
+            /* :3150-3154, stream/Read.java:2846-2858 hasMinConsecutiveBases */
+            if (p->min_consecutive_bases > 0) {
+                for (int q = 0; q < per; q++) {
+                    if (!is_not_discarded(p, &rr[q])) continue;
+                    int len = 0, ok = 0;
+                    for (int i = rr[q].lo; i < rr[q].hi; i++) {
+                        if (!is_defined(rr[q].bases[i])) {
+                            len = 0;
+                        } else {
+                            len++;
+                            if (len >= p->min_consecutive_bases) {
+                                ok = 1;
+                                break;
+                            }
+                        }
+                    }
+                    if (!ok) set_discarded(p, &rr[q]);
+                }
+            }
+            /* :3155-3159, stream/Read.java:2864-2874 minBaseCount: upper-case A C G T only */
+            if (p->min_base_frequency > 0) {
+                for (int q = 0; q < per; q++) {
+                    int a = 0, c = 0, g = 0, t = 0;
+                    for (int i = rr[q].lo; i < rr[q].hi; i++) {
+                        const uint8_t b = rr[q].bases[i];
+                        if (b == 'A') a++;
+                        else if (b == 'C') c++;
+                        else if (b == 'G') g++;
+                        else if (b == 'T') t++;
+                    }
+                    int mn = a < c ? a : c;
+                    if (g < mn) mn = g;
+                    if (t < mn) mn = t;
+                    if ((float)mn < p->min_base_frequency * (float)(rr[q].hi - rr[q].lo)) set_discarded(p, &rr[q]);
                 }
             }
             if (should_remove(p, r1, r2)) {

@@ -33,7 +33,8 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/*.h but not exported"
     assert sorted(s[0] for s in _lib.SYMBOLS) == names  # the binding covers the header exactly
-    assert lib.bbduk_b200_version() == 1
+    from bbtools_b200._abi import ABI_VERSION
+    assert lib.bbduk_b200_version() == ABI_VERSION == 2
 
 
 def test_cfg_struct_layout_matches_header():

@@ -19,11 +19,12 @@ def engine(minlen=10, mlf=0.0, rieb=True, tf1=False, **_):
 
 
 def dev_cfg(g, qtrim="rl", trimq=6.0, mbq=0, maxns=-1, maxlen=0, qual_offset=33, polya=0, polyg=(0, 0), fpolyg=0, polyc=(0, 0),
-            fpolyc=0, maxnonpoly=1, maq=0.0, maqb=0, **_):
+            fpolyc=0, maxnonpoly=1, maq=0.0, maqb=0, maxnrate=1.0, mcb=0, mbf=0.0, **_):
     return g.qtrim_cfg(qtrim_left=int("l" in qtrim), qtrim_right=int("r" in qtrim), trimq=trimq, min_base_quality=mbq, max_ns=maxns,
                        max_read_length=maxlen, qual_offset=qual_offset, trim_poly_a=polya, trim_poly_g_left=polyg[0],
                        trim_poly_g_right=polyg[1], filter_poly_g=fpolyg, trim_poly_c_left=polyc[0], trim_poly_c_right=polyc[1],
-                       filter_poly_c=fpolyc, max_non_poly=maxnonpoly, min_avg_quality=maq, min_avg_quality_bases=maqb)
+                       filter_poly_c=fpolyc, max_non_poly=maxnonpoly, min_avg_quality=maq, min_avg_quality_bases=maqb,
+                       max_n_rate=maxnrate, min_consecutive_bases=mcb, min_base_frequency=mbf)
 
 
 def check(case, bases, quals, offsets, paired, lo, hi, flags):

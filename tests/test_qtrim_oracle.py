@@ -214,6 +214,30 @@ def py_block(bases, quals, offsets, paired, lo, hi, flags, p):
                         st[4] += 1
                         st[5] += hi[i] - lo[i]
                         set_discarded(i)
+            if float(F32(p.max_n_rate)) < 1:  # the raw discarded flag guards against a double count (jgi/BBDuk.java:3138-3149)
+                for i in idx:
+                    if state[i]:
+                        continue
+                    b = bases[offsets[i] + lo[i]:offsets[i] + hi[i]]
+                    n = sum(1 for c in b if chr(c) not in "ACGTUacgtu")
+                    if F32(n) > F32(F32(p.max_n_rate) * F32(len(b))):
+                        st[4] += 1
+                        st[5] += hi[i] - lo[i]
+                        set_discarded(i)
+            if p.min_consecutive_bases > 0:  # some run of that many defined bases (stream/Read.java:2846-2858)
+                for i in idx:
+                    if disc(i, state):
+                        continue
+                    b = bytes(bases[offsets[i] + lo[i]:offsets[i] + hi[i]]).decode("latin1")
+                    runs = "".join("x" if c in "ACGTUacgtu" else " " for c in b).split()
+                    if max([0] + [len(r) for r in runs]) < p.min_consecutive_bases:
+                        set_discarded(i)
+            if float(F32(p.min_base_frequency)) > 0:  # the rarest of upper-case A C G T (stream/Read.java:2864-2874)
+                for i in idx:
+                    b = bytes(bases[offsets[i] + lo[i]:offsets[i] + hi[i]])
+                    mn = min(b.count(c) for c in (b"A", b"C", b"G", b"T"))
+                    if F32(mn) < F32(F32(p.min_base_frequency) * F32(len(b))):
+                        set_discarded(i)
             if should_remove():
                 st[3] += sum(hi[i] - lo[i] for i in idx)
                 st[2] += per
@@ -293,7 +317,9 @@ CASES = [dict(qtrim="rl", trimq=10.0), dict(qtrim="r", trimq=6.0), dict(qtrim="l
          dict(qtrim="", polya=3, minlen=30), dict(qtrim="rl", trimq=8.0, polyg=(4, 4), fpolyc=5, maxnonpoly=1),
          dict(qtrim="", polyg=(2, 0), polyc=(0, 3), fpolyg=6, maxnonpoly=0, rieb=False),
          dict(qtrim="r", trimq=12.0, polya=2, polyg=(3, 3), polyc=(3, 3), fpolyg=8, fpolyc=8, maxnonpoly=2, tf1=True),
-         dict(qtrim="", maq=20.0), dict(qtrim="rl", trimq=5.0, maq=13.5, maqb=40, mbq=1), dict(qtrim="", maq=7.0, rieb=False)]
+         dict(qtrim="", maq=20.0), dict(qtrim="rl", trimq=5.0, maq=13.5, maqb=40, mbq=1), dict(qtrim="", maq=7.0, rieb=False),
+         dict(qtrim="", maxnrate=0.02), dict(qtrim="r", trimq=8.0, maxns=1, maxnrate=0.01, rieb=False), dict(qtrim="", mcb=30),
+         dict(qtrim="rl", trimq=10.0, mcb=12, tf1=True), dict(qtrim="", mbf=0.18), dict(qtrim="r", trimq=6.0, mbf=0.1, mcb=20, maxnrate=0.05)]
 
 
 @pytest.mark.parametrize("case", range(len(CASES)))
