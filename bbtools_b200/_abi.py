@@ -115,7 +115,9 @@ class BBDukQtrimCfg(C.Structure):
         ("max_n_rate", C.c_float),
         ("min_consecutive_bases", C.c_int32),
         ("min_base_frequency", C.c_float),
-        ("reserved", C.c_int32 * 1),
+        ("trim_mode", C.c_int32),
+        ("window_length", C.c_int32),
+        ("min_good_interval", C.c_int32),
     ]
 
 

@@ -50,7 +50,8 @@ def parse_args(args, generation=GEN_JGI):
           "qtrim_left": False, "qtrim_right": False, "trimq": 6.0, "mbq": 0, "maxns": -1, "maxlen": 0,
           "trimpolya": 0, "trimpolygleft": 0, "trimpolygright": 0, "filterpolyg": 0, "trimpolycleft": 0, "trimpolycright": 0,
           "filterpolyc": 0, "maxnonpoly": 1, "entropy": -1.0, "entropyk": 5, "entropywindow": 50,
-          "maq": 0.0, "maqb": 0, "maxnrate": 1.0, "mcb": 0, "minbasefrequency": 0.0}
+          "maq": 0.0, "maqb": 0, "maxnrate": 1.0, "mcb": 0, "minbasefrequency": 0.0,
+          "trim_mode": 0, "window_length": 4, "min_good_interval": 2}
     for arg in args:
         sp = arg.split("=")
         a = sp[0].lower()
@@ -219,7 +220,7 @@ def parse_args(args, generation=GEN_JGI):
             io["minoverlap"] = int(b)
         elif a == "mininsert":
             io["mininsert"] = int(b)
-        elif a == "qtrim":  # parse/Parser.java:347-367 (window mode is not on the device path)
+        elif a == "qtrim":  # parse/Parser.java:347-367
             v = (b or "").lower()
             if v == "":
                 io["qtrim_left"] = io["qtrim_right"] = True
@@ -229,10 +230,26 @@ def parse_args(args, generation=GEN_JGI):
                 io["qtrim_left"], io["qtrim_right"] = False, True
             elif v in ("both", "rl", "lr"):
                 io["qtrim_left"] = io["qtrim_right"] = True
-            elif v.startswith("w"):
-                raise NotImplementedError("qtrim=window is not on the device path")
+            elif v in ("window", "w") or v.startswith("window,") or v.startswith("w,"):  # right end only, TrimRead.windowMode
+                io["qtrim_left"], io["qtrim_right"] = False, True
+                io["trim_mode"] = 1
+                parts = v.split(",")
+                if len(parts) > 1:
+                    io["window_length"] = int(parts[1])
+            elif v[:1].isdigit():  # qtrim=<number> sets trimq and trims the right end (parse/Parser.java:364-366)
+                io["trimq"] = float(v)
+                io["qtrim_right"] = True
             else:
                 io["qtrim_left"] = io["qtrim_right"] = _parse_boolean(b)
+        elif a in ("optitrim", "otf", "otm"):  # parse/Parser.java:368-375 (a numeric optimalBias is not supported here)
+            if b and (b[0] == "." or b[0].isdigit()):
+                raise NotImplementedError("optitrim=<bias> (TrimRead.optimalBias) is not on the device path")
+            if _parse_boolean(b):
+                io["trim_mode"] = 0
+            elif io["trim_mode"] == 0:
+                io["trim_mode"] = 2
+        elif a == "trimgoodinterval":
+            io["min_good_interval"] = int(b)
         elif a in ("trimright", "qtrimright"):
             io["qtrim_right"] = _parse_boolean(b)
         elif a in ("trimleft", "qtrimleft"):
@@ -714,7 +731,8 @@ class BBDuk:
                                    trim_poly_c_left=io["trimpolycleft"], trim_poly_c_right=io["trimpolycright"],
                                    filter_poly_c=io["filterpolyc"], max_non_poly=io["maxnonpoly"], min_avg_quality=io["maq"],
                                    min_avg_quality_bases=io["maqb"], max_n_rate=io["maxnrate"], min_consecutive_bases=io["mcb"],
-                                   min_base_frequency=io["minbasefrequency"])
+                                   min_base_frequency=io["minbasefrequency"], trim_mode=io["trim_mode"],
+                                   window_length=io["window_length"], min_good_interval=io["min_good_interval"])
 
     def _entropy_cfg(self):
         io = self.io

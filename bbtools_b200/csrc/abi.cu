@@ -983,12 +983,15 @@ void bbduk_b200_qtrim_cfg_default(bbduk_qtrim_cfg *c) {
     c->qual_offset = 33;
     c->max_non_poly = 1;  // parse/Parser.java:1831
     c->max_n_rate = 1.0f; // jgi/BBDuk.java:629: unset = 1 = no-op
+    c->window_length = 4;     // shared/TrimRead.java:961
+    c->min_good_interval = 2; // shared/TrimRead.java:949
 }
 
 static int check_qtrim_cfg(bbduk_handle *h, const bbduk_qtrim_cfg *cfg, const void *quals) {
     if (!cfg || cfg->struct_size != (int32_t)sizeof *cfg) return set_err(h, "bad bbduk_qtrim_cfg");
-    if ((cfg->qtrim_left || cfg->qtrim_right || cfg->min_base_quality > 0 || cfg->min_avg_quality > 0) && !quals)
-        return set_err(h, "qtrim / mbq / maq need quality bytes (reads without qualities have no device path here)");
+    (void)quals;  // reads without qualities: trimming falls back to N's, mbq / maq do not apply (as in the reference)
+    if (cfg->trim_mode < 0 || cfg->trim_mode > 2 || cfg->window_length < 1 || cfg->min_good_interval < 0)
+        return set_err(h, "bad trim_mode / window_length / min_good_interval");
     if (cfg->qual_offset < 0 || cfg->qual_offset > 127) return set_err(h, "bad qual_offset");
     return 0;
 }

@@ -37,6 +37,9 @@ struct QtrimDev {
     int maq_on, maq_bases;
     float max_n_rate, min_base_freq;  // maxnrate (>= 1 = off), minbasefrequency (0 = off)
     int mcb;                          // minconsecutivebases (0 = off)
+    int alt_trim;                     // quality trimming by another rule than the staged optimal scan: 1 = window, 2 = optitrim=f,
+                                      // 3 = optimal without qualities (N's only); 0 = none
+    int trimq_byte, window, good_interval, n_only_off;  // (byte)trimq; n_only_off: the no-quality rule trims nothing
     float maq_prob;    // discard iff expectedErrors / bases >= maq_prob  (<=> phred average < minavgquality, see launch_qtrim)
     float delta[256];  // per raw quality byte: trimE - probError (trimE - nprob for q < 1)
     float pe[256];     // per raw quality byte: PROB_ERROR[max(q, 0)] (only staged when maq is on)
@@ -251,6 +254,83 @@ qtrim_kernel(const uint8_t *__restrict__ bases, const uint8_t *__restrict__ qual
                 }
             }
             __syncwarp();
+        }
+        if (!QT && p.alt_trim && !gone && h - l >= 1) {
+            // the other rules of TrimRead.trimFast (shared/TrimRead.java:153-171): rare modes, plain per-lane loops
+            const int n = h - l;
+            const uint8_t *bb = bases + o0 + l;
+            const uint8_t *qq = quals ? quals + o0 + l : nullptr;
+            auto qv = [&](int i) { return (int)(int8_t)(uint8_t)(qq[i] - p.qual_offset); };
+            auto left_n = [&]() {  // testLeftN :477-489
+                int good = 0, lastBad = -1;
+                for (int i = 0; i < n && good < p.good_interval; i++) {
+                    if (bb[i] != 'N') good++;
+                    else { good = 0; lastBad = i; }
+                }
+                return lastBad + 1;
+            };
+            auto right_n = [&]() {  // testRightN :491-503
+                int good = 0, lastBad = n;
+                for (int i = n - 1; i >= 0 && good < p.good_interval; i--) {
+                    if (bb[i] != 'N') good++;
+                    else { good = 0; lastBad = i; }
+                }
+                return n - lastBad;
+            };
+            int a = 0, b = 0;
+            if (p.alt_trim == 3) {  // testOptimal without qualities (:352): avgErrorRate >= 1 trims nothing
+                if (!p.n_only_off) {
+                    a = left_n();
+                    b = right_n();
+                }
+                a = p.qtrim_left ? a : 0;
+                b = p.qtrim_right ? b : 0;
+            } else if (p.alt_trim == 1) {  // testRightWindow :438-455
+                if (p.qtrim_right) {
+                    if (!qq || n < p.window) {
+                        b = p.trimq_byte > 0 ? 0 : right_n();
+                    } else {
+                        const int thresh = max(p.window * p.trimq_byte, 1);
+                        int sum = 0;
+                        for (int i = 0, j = -p.window; i < n; i++, j++) {
+                            sum += qv(i);
+                            if (j >= -1) {
+                                if (j >= 0) sum -= qv(j);
+                                if (sum < thresh) {
+                                    b = n - j - 1;
+                                    break;
+                                }
+                            }
+                        }
+                    }
+                }
+            } else {  // testLeft / testRight :416-475
+                if (p.qtrim_left) {
+                    if (!qq) {
+                        a = p.trimq_byte < 0 ? 0 : left_n();
+                    } else {
+                        int good = 0, lastBad = -1;
+                        for (int i = 0; i < n && good < p.good_interval; i++) {
+                            if (qv(i) > p.trimq_byte) good++;
+                            else { good = 0; lastBad = i; }
+                        }
+                        a = lastBad + 1;
+                    }
+                }
+                if (p.qtrim_right) {
+                    if (!qq) {
+                        b = p.trimq_byte < 0 ? 0 : right_n();
+                    } else {
+                        int good = 0, lastBad = n;
+                        for (int i = n - 1; i >= 0 && good < p.good_interval; i--) {
+                            if (qv(i) > p.trimq_byte) good++;
+                            else { good = 0; lastBad = i; }
+                        }
+                        b = n - lastBad;
+                    }
+                }
+            }
+            x = trim_amounts(l, h, a, b, 1);  // trimFast -> trimByAmount(r, a, b, 1)
         }
         if (QT && !gone && h - l >= 1) {
             // testOptimal (shared/TrimRead.java:348-410) over [l,h)
@@ -511,7 +591,16 @@ int launch_qtrim(int sm_count, const bbduk_qtrim_cfg *cfg, const BBParams &bp, c
     }
     const int64_t n_tiles = (n_reads + 31) / 32;
     const int blocks = (int)std::min<int64_t>((n_tiles + QT_THREADS / 32 - 1) / (QT_THREADS / 32), (int64_t)sm_count * 8);
-    const bool qt = p.qtrim_left || p.qtrim_right;
+    // which trimming rule runs: the staged optimal scan needs qualities and the default mode; the other rules (and reads
+    // without qualities) take the plain per-lane path of the non-QT kernels
+    const bool want_trim = p.qtrim_left || p.qtrim_right;
+    p.trimq_byte = (int)(int8_t)(int)cfg->trimq;  // Java's (byte)trimq
+    p.window = cfg->window_length;
+    p.good_interval = cfg->min_good_interval;
+    p.n_only_off = e >= 1.0f;
+    p.alt_trim = !want_trim ? 0 : cfg->trim_mode == 1 ? 1 : cfg->trim_mode == 2 ? 2 : (d_quals ? 0 : 3);
+    if (cfg->trim_mode == 1) p.qtrim_left = 0;  // window mode trims the right end only (parse/Parser.java:352-357)
+    const bool qt = want_trim && !p.alt_trim;
     const bool poly = p.poly_a > 0 || p.poly_g_left > 0 || p.poly_g_right > 0 || p.filter_g > 0 || p.poly_c_left > 0 ||
                       p.poly_c_right > 0 || p.filter_c > 0;
 #define QT_GO(A, B) qtrim_kernel<A, B><<<blocks, QT_THREADS, 0, st>>>(d_bases, d_quals, d_offsets, n_reads, paired, d_lo, d_hi, d_flags, p, d_stats)

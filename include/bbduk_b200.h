@@ -339,7 +339,12 @@ typedef struct bbduk_qtrim_cfg {
                                   (jgi/BBDuk.java:3151-3154, stream/Read.java:2846-2858); 0 = off */
     float   min_base_frequency; /* minbasefrequency= ; reads whose rarest of A C G T (upper case, stream/Read.java:2864-2874)
                                   occurs fewer than frequency * length times are discarded (jgi/BBDuk.java:3156-3159); 0 = off */
-    int32_t reserved[1];
+    int32_t trim_mode;         /* 0 = optimal (TrimRead.optimalMode, the default), 1 = qtrim=window / w[,N] (right end only: the
+                                  first window whose quality sum is below window * trimq, shared/TrimRead.java:438-455),
+                                  2 = optitrim=f (testLeft / testRight: trim through the last base of quality <= trimq that is
+                                  met before min_good_interval good ones in a row, :416-475) */
+    int32_t window_length;     /* qtrim=w,N ; default 4 */
+    int32_t min_good_interval; /* trimgoodinterval= ; default 2 */
 } bbduk_qtrim_cfg;
 BBDUK_API void bbduk_b200_qtrim_cfg_default(bbduk_qtrim_cfg *cfg);
 
@@ -349,7 +354,9 @@ BBDUK_API void bbduk_b200_qtrim_cfg_default(bbduk_qtrim_cfg *cfg);
  * "optimal" mode (shared/TrimRead.java:113-169, :348-410: the maximum-sum run of avgErrorRate - probError, single
  * precision, then trimByAmount(r, a, b, 1)), the minlen / maxlen test, shouldRemove, then minavgquality, minbasequality and
  * maxns, maxnrate, minconsecutivebases and minbasefrequency with their shouldRemove (jgi/BBDuk.java:3074-3170; (the rest is at its
- * defaults = off). minavgquality compares -10*log10(expectedErrors/bases) in double precision with the threshold; the
+ * defaults = off). Reads WITHOUT qualities (quals = NULL): the trimming rules fall back to trimming N's
+ * (testLeftN / testRightN, :348-353, :416-418, :438-440, :457-459, :477-503) and minavgquality / minbasequality do not apply.
+ * minavgquality compares -10*log10(expectedErrors/bases) in double precision with the threshold; the
  * device compares the error probability with the smallest float for which that test holds (found on the host with the
  * C library's log10), which is the same predicate. paired != 0: reads (2i, 2i+1) are mates. Units whose flags carry BBDUK_F_REMOVED are skipped.
  * lo[], hi[] and flags[] (BBDUK_F_QTRIMMED, BBDUK_F_POLYTRIMMED, BBDUK_F_DISCARDED, BBDUK_F_REMOVED) are updated in place;

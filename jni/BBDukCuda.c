@@ -247,7 +247,7 @@ JNIEXPORT jint JNICALL Java_bbduk_BBDukIndexGPU_tboNative(JNIEnv *env, jclass cl
  * stats8 += {readsQTrimmed, basesQTrimmed, readsQFiltered, basesQFiltered, readsNFiltered, basesNFiltered, readsPolyTrimmed,
  * basesPolyTrimmed}. qCfg = {qtrimLeft, qtrimRight, minBaseQuality, maxNs (-1 off), maxReadLength (0 unlimited), qualOffset
  * (0 for Read.quality), trimPolyA, trimPolyGLeft, trimPolyGRight, filterPolyG, trimPolyCLeft, trimPolyCRight, filterPolyC,
- * maxNonPoly, minConsecutiveBases, floatToRawIntBits(maxNRate), floatToRawIntBits(minBaseFrequency)} (17 ints). */
+ * maxNonPoly, minConsecutiveBases, floatToRawIntBits(maxNRate), floatToRawIntBits(minBaseFrequency)} (17 ints; the trimming rule stays TrimRead's default, optimal). */
 static void qcfg_from(const jint *c, jfloat trimq, bbduk_qtrim_cfg *cfg) {
     bbduk_b200_qtrim_cfg_default(cfg);
     cfg->qtrim_left = c[0];

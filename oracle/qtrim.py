@@ -16,7 +16,8 @@ class QtrimParams(C.Structure):
                 ("trim_poly_g_right", C.c_int32), ("filter_poly_g", C.c_int32), ("trim_poly_c_left", C.c_int32),
                 ("trim_poly_c_right", C.c_int32), ("filter_poly_c", C.c_int32), ("max_non_poly", C.c_int32),
                 ("min_avg_quality", C.c_float), ("min_avg_quality_bases", C.c_int32),
-                ("max_n_rate", C.c_float), ("min_consecutive_bases", C.c_int32), ("min_base_frequency", C.c_float)]
+                ("max_n_rate", C.c_float), ("min_consecutive_bases", C.c_int32), ("min_base_frequency", C.c_float),
+                ("trim_mode", C.c_int32), ("window_length", C.c_int32), ("min_good_interval", C.c_int32)]
 
 
 _LIB = None
@@ -34,7 +35,7 @@ def lib():
 
 def params(qtrim="rl", trimq=6.0, mbq=0, maxns=-1, maxlen=0, qual_offset=33, minlen=10, mlf=0.0, rieb=True, tf1=False,
            polya=0, polyg=(0, 0), fpolyg=0, polyc=(0, 0), fpolyc=0, maxnonpoly=1, maq=0.0, maqb=0, maxnrate=1.0, mcb=0,
-           mbf=0.0) -> QtrimParams:
+           mbf=0.0, mode=0, window=4, goodinterval=2) -> QtrimParams:
     """defaults of jgi/BBDuk.java (:126 trimq, minlen 10, rieb) for the fields the block reads"""
     p = QtrimParams()
     p.qtrim_left, p.qtrim_right = int("l" in qtrim), int("r" in qtrim)
@@ -45,6 +46,9 @@ def params(qtrim="rl", trimq=6.0, mbq=0, maxns=-1, maxlen=0, qual_offset=33, min
     (p.trim_poly_g_left, p.trim_poly_g_right), (p.trim_poly_c_left, p.trim_poly_c_right) = polyg, polyc
     p.min_avg_quality, p.min_avg_quality_bases = maq, maqb
     p.max_n_rate, p.min_consecutive_bases, p.min_base_frequency = maxnrate, mcb, mbf
+    p.trim_mode, p.window_length, p.min_good_interval = mode, window, goodinterval
+    if mode == 1:  # qtrim=w trims the right end only (parse/Parser.java:352-357)
+        p.qtrim_left, p.qtrim_right = 0, 1
     return p
 
 

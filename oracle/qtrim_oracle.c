@@ -45,6 +45,8 @@ typedef struct qtrim_params {
     float max_n_rate;
     int32_t min_consecutive_bases;
     float min_base_frequency;
+    /* TrimRead's static modes: 0 = optimalMode (default), 1 = windowMode (qtrim=w[,N]), 2 = neither (optitrim=f) */
+    int32_t trim_mode, window_length, min_good_interval;
 } qtrim_params;
 
 static float g_pe[128];
@@ -130,12 +132,93 @@ static void test_optimal(const qread *r, float avg_error_rate, int qual_offset, 
     }
 }
 
-/* shared/TrimRead.java:140-169 with optimalMode, discardUnder = 0, trimClip = false */
+/* shared/TrimRead.java:477-489 */
+static int test_left_n(const uint8_t *bases, int n, int minGoodInterval) {
+    if (n == 0) return 0;
+    int good = 0, lastBad = -1;
+    for (int i = 0; i < n && good < minGoodInterval; i++) {
+        if (bases[i] != 'N') good++;
+        else { good = 0; lastBad = i; }
+    }
+    return lastBad + 1;
+}
+/* shared/TrimRead.java:491-503 */
+static int test_right_n(const uint8_t *bases, int n, int minGoodInterval) {
+    if (n == 0) return 0;
+    int good = 0, lastBad = n;
+    for (int i = n - 1; i >= 0 && good < minGoodInterval; i--) {
+        if (bases[i] != 'N') good++;
+        else { good = 0; lastBad = i; }
+    }
+    return n - lastBad;
+}
+/* shared/TrimRead.java:416-436 */
+static int test_left(const uint8_t *bases, const uint8_t *qual, int n, int8_t trimq, int qual_offset, int minGoodInterval) {
+    if (n == 0) return 0;
+    if (!qual) return trimq < 0 ? 0 : test_left_n(bases, n, minGoodInterval);
+    int good = 0, lastBad = -1;
+    for (int i = 0; i < n && good < minGoodInterval; i++) {
+        const int8_t q = (int8_t)(qual[i] - qual_offset);
+        if (q > trimq) good++;
+        else { good = 0; lastBad = i; }
+    }
+    return lastBad + 1;
+}
+/* shared/TrimRead.java:457-475 */
+static int test_right(const uint8_t *bases, const uint8_t *qual, int n, int8_t trimq, int qual_offset, int minGoodInterval) {
+    if (n == 0) return 0;
+    if (!qual) return trimq < 0 ? 0 : test_right_n(bases, n, minGoodInterval);
+    int good = 0, lastBad = n;
+    for (int i = n - 1; i >= 0 && good < minGoodInterval; i--) {
+        const int8_t q = (int8_t)(qual[i] - qual_offset);
+        if (q > trimq) good++;
+        else { good = 0; lastBad = i; }
+    }
+    return n - lastBad;
+}
+/* shared/TrimRead.java:438-455 */
+static int test_right_window(const uint8_t *bases, const uint8_t *qual, int n, int8_t trimq, int qual_offset, int window,
+                             int minGoodInterval) {
+    if (n == 0) return 0;
+    if (!qual || n < window) return trimq > 0 ? 0 : test_right_n(bases, n, minGoodInterval);
+    int thresh = window * trimq;
+    if (thresh < 1) thresh = 1;
+    int sum = 0;
+    for (int i = 0, j = -window; i < n; i++, j++) {
+        sum += (int8_t)(qual[i] - qual_offset);
+        if (j >= -1) {
+            if (j >= 0) sum -= (int8_t)(qual[j] - qual_offset);
+            if (sum < thresh) return n - j - 1;
+        }
+    }
+    return 0;
+}
+
+/* shared/TrimRead.java:140-171 with discardUnder = 0, trimClip = false */
 static int trim_fast(qread *r, const qtrim_params *p, float trimE) {
-    if (r->hi - r->lo < 1) return 0;
-    int a0, b0;
-    test_optimal(r, trimE, p->qual_offset, &a0, &b0);
-    return trim_by_amount(r, p->qtrim_left ? a0 : 0, p->qtrim_right ? b0 : 0, 1);
+    const int n = r->hi - r->lo;
+    if (n < 1) return 0;
+    const uint8_t *bases = r->bases + r->lo, *qual = r->quals ? r->quals + r->lo : NULL;
+    const int8_t tq = (int8_t)(int)p->trimq; /* (byte)trimq */
+    int a, b;
+    if (p->trim_mode == 0) {
+        int a0, b0;
+        if (!qual) { /* :352 */
+            a0 = trimE >= 1 ? 0 : test_left_n(bases, n, p->min_good_interval);
+            b0 = trimE >= 1 ? 0 : test_right_n(bases, n, p->min_good_interval);
+        } else {
+            test_optimal(r, trimE, p->qual_offset, &a0, &b0);
+        }
+        a = p->qtrim_left ? a0 : 0;
+        b = p->qtrim_right ? b0 : 0;
+    } else if (p->trim_mode == 1) {
+        a = 0;
+        b = p->qtrim_right ? test_right_window(bases, qual, n, tq, p->qual_offset, p->window_length, p->min_good_interval) : 0;
+    } else {
+        a = p->qtrim_left ? test_left(bases, qual, n, tq, p->qual_offset, p->min_good_interval) : 0;
+        b = p->qtrim_right ? test_right(bases, qual, n, tq, p->qual_offset, p->min_good_interval) : 0;
+    }
+    return trim_by_amount(r, a, b, 1);
 }
 
 /* stream/Read.java:3387-3401 on the kept interval */

@@ -7,7 +7,7 @@ import pytest
 from bbtools_b200 import make_cfg, synth
 from bbtools_b200._abi import Outputs
 from oracle import qtrim as oq
-from test_qtrim_oracle import CASES, qual_batch
+from test_qtrim_oracle import CASES, NOQUAL_CASES, qual_batch
 
 pytestmark = pytest.mark.gpu
 
@@ -19,12 +19,13 @@ def engine(minlen=10, mlf=0.0, rieb=True, tf1=False, **_):
 
 
 def dev_cfg(g, qtrim="rl", trimq=6.0, mbq=0, maxns=-1, maxlen=0, qual_offset=33, polya=0, polyg=(0, 0), fpolyg=0, polyc=(0, 0),
-            fpolyc=0, maxnonpoly=1, maq=0.0, maqb=0, maxnrate=1.0, mcb=0, mbf=0.0, **_):
+            fpolyc=0, maxnonpoly=1, maq=0.0, maqb=0, maxnrate=1.0, mcb=0, mbf=0.0, mode=0, window=4, goodinterval=2, **_):
     return g.qtrim_cfg(qtrim_left=int("l" in qtrim), qtrim_right=int("r" in qtrim), trimq=trimq, min_base_quality=mbq, max_ns=maxns,
                        max_read_length=maxlen, qual_offset=qual_offset, trim_poly_a=polya, trim_poly_g_left=polyg[0],
                        trim_poly_g_right=polyg[1], filter_poly_g=fpolyg, trim_poly_c_left=polyc[0], trim_poly_c_right=polyc[1],
                        filter_poly_c=fpolyc, max_non_poly=maxnonpoly, min_avg_quality=maq, min_avg_quality_bases=maqb,
-                       max_n_rate=maxnrate, min_consecutive_bases=mcb, min_base_frequency=mbf)
+                       max_n_rate=maxnrate, min_consecutive_bases=mcb, min_base_frequency=mbf, trim_mode=mode, window_length=window,
+                       min_good_interval=goodinterval)
 
 
 def check(case, bases, quals, offsets, paired, lo, hi, flags):
@@ -46,6 +47,19 @@ def test_ragged_reads(case):
     bases, quals, offsets, lo, hi, flags = qual_batch(6000, 200 + case, L=170, paired=paired)
     st = check(CASES[case], bases, quals, offsets, paired, lo, hi, flags)
     assert st.sum() > 100
+
+
+@pytest.mark.parametrize("case", range(len(NOQUAL_CASES)))
+def test_reads_without_qualities(case):
+    """quals = NULL: the trimming rules fall back to N's, mbq / maq do not apply (shared/TrimRead.java:352, :418, :440, :459)"""
+    paired = case % 2 == 1
+    bases, _, offsets, lo, hi, flags = qual_batch(5000, 400 + case, L=150, paired=paired)
+    rng = np.random.default_rng(case)
+    for i in np.nonzero(rng.random(len(offsets) - 1) < 0.5)[0]:
+        a, b = offsets[i], offsets[i + 1]
+        bases[a:a + min(int(rng.integers(0, 6)), b - a)] = ord("N")
+        bases[max(a, b - int(rng.integers(0, 6))):b] = ord("N")
+    check(NOQUAL_CASES[case], bases, None, offsets, paired, lo, hi, flags)
 
 
 def test_numeric_qualities_and_empty_batches():
@@ -108,5 +122,11 @@ def test_device_entry_point_and_alignment_error():
     assert np.array_equal(d_fl.cpu().numpy(), want[2]) and d_st.cpu().tolist() == list(want[3])
     with pytest.raises(RuntimeError, match="16-byte aligned"):
         g.qtrim_device(d_b[1:], d_q[1:], d(offsets.astype(np.int32)), len(lo), True, d_lo, d_hi, d_fl, dev_cfg(g, **case), d_st)
-    with pytest.raises(RuntimeError, match="quality bytes"):
-        g.qtrim_device(d_b, None, d(offsets.astype(np.int32)), len(lo), True, d_lo, d_hi, d_fl, dev_cfg(g, **case), d_st)
+    # no quality array: the device entry trims N's instead (reads without qualities), mbq does not apply
+    want = oq.process(bases, None, offsets, True, lo, hi, flags, oq.params(**case))
+    d_lo, d_hi, d_fl = d(lo), d(hi), d(flags)
+    d_st.zero_()
+    g.qtrim_device(d_b, None, d(offsets.astype(np.int32)), len(lo), True, d_lo, d_hi, d_fl, dev_cfg(g, **case), d_st)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_lo.cpu().numpy(), want[0]) and np.array_equal(d_hi.cpu().numpy(), want[1])
+    assert np.array_equal(d_fl.cpu().numpy(), want[2]) and d_st.cpu().tolist() == list(want[3])

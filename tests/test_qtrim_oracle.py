@@ -52,6 +52,47 @@ def trim_by_amount(lo, hi, left, right, m):
     return lo + left, hi - right, left + right
 
 
+def py_run_ends(good, interval):
+    """(bases to cut on the left, on the right) for testLeft / testRight and their N-only versions (shared/TrimRead.java:416-503):
+    walk inwards from an end until `interval` good symbols in a row; cut through the last bad one met on the way"""
+    n = len(good)
+
+    def walk(seq):
+        run, last_bad = 0, -1
+        for i, g in enumerate(seq):
+            if run >= interval:
+                break
+            if g:
+                run += 1
+            else:
+                run, last_bad = 0, i
+        return last_bad + 1
+    return (walk(good), walk(good[::-1])) if n else (0, 0)
+
+
+def py_trim_amounts(b, q, e, p):
+    """the (left, right) amounts of TrimRead.trimFast for each of its three modes, with or without qualities"""
+    n = len(b)
+    tq = int(np.int8(int(p.trimq)))
+    n_good = [c != ord("N") for c in b]
+    if p.trim_mode == 0:
+        if q is None:
+            return (0, 0) if e >= 1 else py_run_ends(n_good, p.min_good_interval)
+        return py_test_optimal(b, q, e)
+    if p.trim_mode == 1:  # the first window of `window_length` qualities whose sum is below window * trimq: cut from its start
+        w = p.window_length
+        if q is None or n < w:
+            return 0, (0 if tq > 0 else py_run_ends(n_good, p.min_good_interval)[1])
+        thresh = max(w * tq, 1)
+        for start in range(0, n - w + 1):
+            if int(np.sum(q[start:start + w].astype(np.int64))) < thresh:
+                return 0, n - start
+        return 0, 0
+    if q is None:
+        return (0, 0) if tq < 0 else py_run_ends(n_good, p.min_good_interval)
+    return py_run_ends([int(x) > tq for x in q], p.min_good_interval)
+
+
 def py_detect_left(seq, min_poly, max_non, c):
     """jgi/BBDuk.java:4771-4791 on a bytes object: walk runs of c; a run of >= min_poly resets the error budget"""
     if len(seq) < min_poly:
@@ -166,8 +207,8 @@ def py_block(bases, quals, offsets, paired, lo, hi, flags, p):
                 if hi[i] - lo[i] < 1:
                     continue
                 b = bases[offsets[i] + lo[i]:offsets[i] + hi[i]]
-                q = (quals[offsets[i] + lo[i]:offsets[i] + hi[i]].astype(np.int64) - p.qual_offset).astype(np.int8)
-                a0, b0 = py_test_optimal(b, q, e)
+                q = None if quals is None else (quals[offsets[i] + lo[i]:offsets[i] + hi[i]].astype(np.int64) - p.qual_offset).astype(np.int8)
+                a0, b0 = py_trim_amounts(b, q, e, p)
                 lo[i], hi[i], x = trim_by_amount(lo[i], hi[i], a0 if p.qtrim_left else 0, b0 if p.qtrim_right else 0, 1)
                 st[1] += x
                 st[0] += x > 0
@@ -319,7 +360,12 @@ CASES = [dict(qtrim="rl", trimq=10.0), dict(qtrim="r", trimq=6.0), dict(qtrim="l
          dict(qtrim="r", trimq=12.0, polya=2, polyg=(3, 3), polyc=(3, 3), fpolyg=8, fpolyc=8, maxnonpoly=2, tf1=True),
          dict(qtrim="", maq=20.0), dict(qtrim="rl", trimq=5.0, maq=13.5, maqb=40, mbq=1), dict(qtrim="", maq=7.0, rieb=False),
          dict(qtrim="", maxnrate=0.02), dict(qtrim="r", trimq=8.0, maxns=1, maxnrate=0.01, rieb=False), dict(qtrim="", mcb=30),
-         dict(qtrim="rl", trimq=10.0, mcb=12, tf1=True), dict(qtrim="", mbf=0.18), dict(qtrim="r", trimq=6.0, mbf=0.1, mcb=20, maxnrate=0.05)]
+         dict(qtrim="rl", trimq=10.0, mcb=12, tf1=True), dict(qtrim="", mbf=0.18), dict(qtrim="r", trimq=6.0, mbf=0.1, mcb=20, maxnrate=0.05),
+         dict(qtrim="r", trimq=12.0, mode=1), dict(qtrim="r", trimq=20.0, mode=1, window=7, rieb=False), dict(qtrim="rl", trimq=10.0, mode=2),
+         dict(qtrim="l", trimq=15.0, mode=2, goodinterval=4, minlen=20), dict(qtrim="r", trimq=8.9, mode=2, goodinterval=1)]
+# the same rules on reads WITHOUT qualities (N's only), run with quals=None
+NOQUAL_CASES = [dict(qtrim="rl", trimq=10.0), dict(qtrim="r", trimq=6.0, mode=2), dict(qtrim="rl", trimq=0.0, mode=1), dict(qtrim="l", trimq=5.0, mode=2, goodinterval=3),
+                dict(qtrim="rl", trimq=-1.0, mode=2), dict(qtrim="rl", trimq=10.0, maxns=2, mcb=25)]
 
 
 @pytest.mark.parametrize("case", range(len(CASES)))
@@ -332,6 +378,45 @@ def test_oracle_matches_python_restatement(case):
     for g, w, name in zip(got, want, ("lo", "hi", "flags", "stats")):
         assert np.array_equal(g, w), name
     assert got[3].sum() > 0
+
+
+@pytest.mark.parametrize("case", range(len(NOQUAL_CASES)))
+def test_oracle_matches_python_restatement_without_qualities(case):
+    """reads without qualities: every trimming rule falls back to trimming N's (shared/TrimRead.java:352, :418, :440, :459)"""
+    paired = case % 2 == 1
+    bases, _, offsets, lo, hi, flags = qual_batch(400, 300 + case, paired=paired)
+    rng = np.random.default_rng(case)
+    ends = rng.random(len(offsets) - 1) < 0.5  # N's at the read ends, where the N-only rules look
+    for i in np.nonzero(ends)[0]:
+        a, b = offsets[i], offsets[i + 1]
+        k = int(rng.integers(0, 6))
+        bases[a:a + min(k, b - a)] = ord("N")
+        bases[max(a, b - int(rng.integers(0, 6))):b] = ord("N")
+    p = oq.params(**NOQUAL_CASES[case])
+    got = oq.process(bases, None, offsets, paired, lo, hi, flags, p)
+    want = py_block(bases, None, offsets, paired, lo, hi, flags, p)
+    for g, w, name in zip(got, want, ("lo", "hi", "flags", "stats")):
+        assert np.array_equal(g, w), name
+
+
+def test_trim_mode_known_answers():
+    """hand-checked cases of the window rule and of testLeft / testRight"""
+    def one(qs, **kw):
+        n = len(qs)
+        b = np.frombuffer(("A" * n).encode(), np.uint8)
+        q = (np.array(qs) + 33).astype(np.uint8)
+        off = np.array([0, n], np.int64)
+        lo, hi, _, _ = oq.process(b, q, off, False, np.zeros(1, np.int32), np.array([n], np.int32), np.zeros(1, np.uint8),
+                                  oq.params(minlen=1, **kw))
+        return int(lo[0]), int(hi[0])
+    # window of 4 below 4 * 10 first at positions 12..15 (30 30 2 2 = 64 >= 40; 30 2 2 2 = 36 < 40 starts at 11)
+    assert one([30] * 12 + [2] * 8, qtrim="r", trimq=10.0, mode=1) == (0, 11)
+    assert one([30] * 20, qtrim="r", trimq=10.0, mode=1) == (0, 20)
+    assert one([5, 5, 5, 5] + [30] * 10, qtrim="r", trimq=10.0, mode=1) == (0, 1)  # the very first window fails: one base is kept
+    # optitrim=f: walk in from each end until 2 good bases in a row; cut through the last bad one seen
+    assert one([2, 30, 2, 30, 30, 30, 30, 2, 30, 30], qtrim="rl", trimq=10.0, mode=2) == (3, 10)
+    assert one([30, 30, 30, 2, 30], qtrim="rl", trimq=10.0, mode=2) == (0, 3)
+    assert one([30, 2, 30, 30], qtrim="l", trimq=10.0, mode=2, goodinterval=1) == (0, 4)
 
 
 def test_known_answers():
