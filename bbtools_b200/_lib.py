@@ -53,6 +53,11 @@ SYMBOLS = [
     ("bbduk_b200_entropy_cfg_default", None, [C.POINTER(BBDukEntropyCfg)]),
     ("bbduk_b200_entropy", C.c_int, [C.c_void_p, C.POINTER(BBDukEntropyCfg), C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("bbduk_b200_entropy_mask", C.c_int, [C.c_void_p, C.POINTER(BBDukEntropyCfg), C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("bbduk_b200_entropy_mask_device", C.c_int, [C.c_void_p, C.POINTER(BBDukEntropyCfg), C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
+                                                 C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                 C.c_void_p]),
     ("bbduk_b200_entropy_device", C.c_int, [C.c_void_p, C.POINTER(BBDukEntropyCfg), C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("bbduk_b200_chain_cfg_default", None, [C.POINTER(BBDukChainCfg)]),

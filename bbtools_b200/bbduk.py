@@ -49,7 +49,7 @@ def parse_args(args, generation=GEN_JGI):
           "tbo": False, "strictoverlap": True, "minoverlap": -1, "mininsert": -1,
           "qtrim_left": False, "qtrim_right": False, "trimq": 6.0, "mbq": 0, "maxns": -1, "maxlen": 0,
           "trimpolya": 0, "trimpolygleft": 0, "trimpolygright": 0, "filterpolyg": 0, "trimpolycleft": 0, "trimpolycright": 0,
-          "filterpolyc": 0, "maxnonpoly": 1, "entropy": -1.0, "entropyk": 5, "entropywindow": 50,
+          "filterpolyc": 0, "maxnonpoly": 1, "entropy": -1.0, "entropyk": 5, "entropywindow": 50, "entropymask": 0, "entropytrim": False,
           "maq": 0.0, "maqb": 0, "maxnrate": 1.0, "mcb": 0, "minbasefrequency": 0.0,
           "trim_mode": 0, "window_length": 4, "min_good_interval": 2}
     for arg in args:
@@ -286,6 +286,12 @@ def parse_args(args, generation=GEN_JGI):
             io["trimpolycleft"] = io["trimpolycright"] = _parse_poly(b)
         elif a in ("minentropy", "entropy", "entropyfilter"):  # jgi/BBDuk.java:418-419
             io["entropy"] = float(b)
+        elif a in ("entropymask", "maskentropy"):  # jgi/BBDuk.java:422-432: 1 = to N, 2 = to lower case
+            v = (b or "").lower()
+            io["entropymask"] = 1 if b is None else 2 if v in ("lc", "lowercase") else 0 if v == "filter" else int(_parse_boolean(b))
+        elif a in ("entropytrim", "trimentropy"):  # jgi/BBDuk.java:433-434, parseEnd :4846-4852 (any end = both ends, :4448-4478)
+            v = (b or "rl").lower()
+            io["entropytrim"] = v in ("right", "r", "left", "l", "rl", "lr", "both", "b") or _parse_boolean(b)
         elif a in ("entropyk", "ek"):  # parse/Parser.java:955-960
             io["entropyk"] = int(b)
         elif a in ("entropywindow", "ew"):
@@ -584,6 +590,23 @@ class BBDukIndexGPU:
                                                 st.ctypes.data), "entropy")
         return st
 
+    def entropy_mask(self, bases, offsets, paired, out, cfg, mode):
+        """entropymask (mode 1: to N, 2: to lower case) / entropytrim (mode 3) on HOST buffers; `out` is the Outputs so far: mode 3
+        updates out.lo / out.hi. -> (mask words, mask_off, [readsEFiltered, basesEFiltered]); bit j of a read's words = base j of
+        its kept interval"""
+        bases = np.ascontiguousarray(bases, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        words = (np.diff(offsets) + 31) // 32
+        mask_off = np.zeros(len(offsets), np.int64)
+        np.cumsum(words, out=mask_off[1:])
+        bits = np.zeros(max(1, int(mask_off[-1])), np.uint32)
+        st = np.zeros(2, np.int64)
+        self._check(self.lib.bbduk_b200_entropy_mask(self.h, C.byref(cfg), int(mode), bases.ctypes.data, offsets.ctypes.data,
+                                                     len(offsets) - 1, int(bool(paired)), out.lo.ctypes.data, out.hi.ctypes.data,
+                                                     out.flags.ctypes.data, bits.ctypes.data, mask_off.ctypes.data, st.ctypes.data),
+                    "entropy_mask")
+        return bits, mask_off, st
+
     def entropy_device(self, d_bases, d_offsets, n_reads, paired, d_lo, d_hi, d_flags, cfg, d_stats=None, stream=None):
         def ptr(x):
             if x is None:
@@ -754,7 +777,13 @@ class BBDuk:
 
     def process(self, native=True):
         io = self.io
-        if native and not self.cfg.ktrim_n and not self.cfg.ksplit:
+        e_mode = 3 if io["entropytrim"] else io["entropymask"]  # entropy masking / trimming rewrites bases: plain-Python feed
+        if e_mode:
+            if io["entropy"] < 0:
+                raise ValueError("Entropy masking/trimming operations require the entropy flag to be set.")  # jgi/BBDuk.java:1028
+            if any(io[x] for x in ("trimpolya", "trimpolygleft", "trimpolygright", "filterpolyg", "trimpolycleft", "trimpolycright", "filterpolyc")):
+                raise NotImplementedError("entropy masking / trimming together with poly-X steps (they sit on either side of it in one launch)")
+        if native and not self.cfg.ktrim_n and not self.cfg.ksplit and not e_mode:
             return self.process_native()
         n1, s1, q1 = read_fastq(io["in1"])
         paired = False
@@ -773,9 +802,24 @@ class BBDuk:
         self.stats = st
         if io["tbo"] and paired:
             self.tbo_stats = self._tbo(bases, pack(quals)[0], offsets, out)
+        if e_mode:  # jgi/BBDuk.java:3055-3067: before quality trimming; the later entropy FILTER is then off (:3175)
+            bits, moff, self.entropy_stats = self.index.entropy_mask(bases, offsets, paired, out, self._entropy_cfg(), e_mode)
+            if e_mode != 3:  # maskFromBitset :4505-4526: an N stays an N (and keeps its quality), lower case stays as it is
+                qarr = pack(quals)[0]
+                for i in range(len(seqs)):
+                    a = int(offsets[i]) + int(out.lo[i])
+                    for j in range(int(out.hi[i]) - int(out.lo[i])):
+                        if (int(bits[moff[i] + (j >> 5)]) >> (j & 31)) & 1:
+                            if e_mode == 1 and bases[a + j] != ord("N"):
+                                bases[a + j] = ord("N")
+                                qarr[a + j] = 33
+                            elif e_mode == 2:
+                                bases[a + j] = ord(chr(bases[a + j]).lower())
+                seqs = [bytes(bases[offsets[i]:offsets[i + 1]]) for i in range(len(seqs))]
+                quals = [bytes(qarr[offsets[i]:offsets[i + 1]]) for i in range(len(seqs))]
         if self._wants_qtrim():
             self.qtrim_stats = self._qtrim(bases, pack(quals)[0], offsets, paired, out)
-        if io["entropy"] >= 0:
+        if io["entropy"] >= 0 and not e_mode:
             self.entropy_stats = self._entropy(bases, offsets, paired, out)
         sinks = {}
 

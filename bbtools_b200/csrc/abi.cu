@@ -95,8 +95,10 @@ struct bbduk_handle {
         uint32_t *d_off = nullptr;
         int32_t *d_lo = nullptr, *d_hi = nullptr, *d_insert = nullptr;
         int32_t *d_id0 = nullptr, *d_count = nullptr;
+        uint32_t *d_mask = nullptr;   // entropy masking: mask words of the chunk
+        int64_t *d_maskoff = nullptr; // and their per-read word offsets
         int64_t cap_bases = 0, cap_quals = 0, cap_flags = 0, cap_off = 0, cap_lo = 0, cap_hi = 0, cap_insert = 0, cap_id0 = 0,
-                cap_count = 0;
+                cap_count = 0, cap_mask = 0, cap_maskoff = 0;
     } tbo;
     // bbduk_b200_process_chain: second input slot + copy stream, so that the upload of chunk i+1 overlaps the kernels of chunk i
     uint8_t *chain_bases2 = nullptr, *chain_quals2 = nullptr;
@@ -1110,8 +1112,46 @@ int bbduk_b200_entropy_device(bbduk_handle *h, const bbduk_entropy_cfg *cfg, con
     return 0;
 }
 
+int bbduk_b200_entropy_mask_device(bbduk_handle *h, const bbduk_entropy_cfg *cfg, int32_t mode, const uint8_t *d_bases,
+                                   const uint32_t *d_offsets, int64_t n_reads, int32_t paired, int32_t *d_lo, int32_t *d_hi,
+                                   const uint8_t *d_flags, uint32_t *d_maskbits, const int64_t *d_mask_off, int64_t *d_stats2,
+                                   void *stream) {
+    if (!h) return set_err(nullptr, "handle is NULL");
+    if (!cfg || cfg->struct_size != (int32_t)sizeof *cfg) return set_err(h, "bad bbduk_entropy_cfg");
+    if (mode < 1 || mode > 3) return set_err(h, "entropy_mask: mode must be 1 (mask to N), 2 (mask to lower case) or 3 (trim)");
+    if (n_reads < 0 || (paired && (n_reads & 1))) return set_err(h, "bad n_reads (paired input needs an even count)");
+    if (n_reads == 0) return 0;
+    if (!d_bases || !d_offsets || !d_lo || !d_hi || !d_flags || !d_maskbits || !d_mask_off) return set_err(h, "NULL input");
+    CKH(cudaSetDevice(h->device));
+    const int rc = launch_entropy_mask(h->sm_count, cfg, h->p, d_bases, d_offsets, n_reads, paired ? 1 : 0, d_lo, d_hi,
+                                       const_cast<uint8_t *>(d_flags), mode, d_maskbits, d_mask_off,
+                                       reinterpret_cast<unsigned long long *>(d_stats2), (cudaStream_t)stream);
+    if (rc == 2) return set_err(h, "entropy: k > 5 or window - k + 1 > 254 has no device path (and there is no CPU fallback)");
+    if (rc) return set_err(h, std::string("entropy mask kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    h->launches += 1;
+    return 0;
+}
+
+static int entropy_host_impl(bbduk_handle *h, const bbduk_entropy_cfg *cfg, const uint8_t *bases, const int64_t *offsets, int64_t n_reads,
+                             int32_t paired, int32_t *lo, int32_t *hi, uint8_t *flags, int64_t *stats2, int mode, uint32_t *maskbits,
+                             const int64_t *mask_off);
+
 int bbduk_b200_entropy(bbduk_handle *h, const bbduk_entropy_cfg *cfg, const uint8_t *bases, const int64_t *offsets, int64_t n_reads,
                        int32_t paired, const int32_t *lo, int32_t *hi, uint8_t *flags, int64_t *stats2) {
+    return entropy_host_impl(h, cfg, bases, offsets, n_reads, paired, const_cast<int32_t *>(lo), hi, flags, stats2, 0, nullptr, nullptr);
+}
+
+int bbduk_b200_entropy_mask(bbduk_handle *h, const bbduk_entropy_cfg *cfg, int32_t mode, const uint8_t *bases, const int64_t *offsets,
+                            int64_t n_reads, int32_t paired, int32_t *lo, int32_t *hi, const uint8_t *flags, uint32_t *maskbits,
+                            const int64_t *mask_off, int64_t *stats2) {
+    if (h && (mode < 1 || mode > 3)) return set_err(h, "entropy_mask: mode must be 1 (mask to N), 2 (mask to lower case) or 3 (trim)");
+    if (h && n_reads > 0 && (!maskbits || !mask_off)) return set_err(h, "NULL input");
+    return entropy_host_impl(h, cfg, bases, offsets, n_reads, paired, lo, hi, const_cast<uint8_t *>(flags), stats2, mode, maskbits, mask_off);
+}
+
+static int entropy_host_impl(bbduk_handle *h, const bbduk_entropy_cfg *cfg, const uint8_t *bases, const int64_t *offsets, int64_t n_reads,
+                             int32_t paired, int32_t *lo, int32_t *hi, uint8_t *flags, int64_t *stats2, int mode, uint32_t *maskbits,
+                             const int64_t *mask_off) {
     if (!h) return set_err(nullptr, "handle is NULL");
     if (!cfg || cfg->struct_size != (int32_t)sizeof *cfg) return set_err(h, "bad bbduk_entropy_cfg");
     if (n_reads < 0 || (paired && (n_reads & 1))) return set_err(h, "bad n_reads (paired input needs an even count)");
@@ -1151,6 +1191,11 @@ int bbduk_b200_entropy(bbduk_handle *h, const bbduk_entropy_cfg *cfg, const uint
             rc = set_err(h, "entropy: device allocation failed");
             break;
         }
+        const int64_t mw0 = mode ? mask_off[r0] : 0, mw = mode ? mask_off[r1] - mw0 : 0;
+        if (mode && (mw < 0 || need((void **)&tb.d_mask, &tb.cap_mask, 4 * (mw + 1)) || need((void **)&tb.d_maskoff, &tb.cap_maskoff, 8 * (nr + 1)))) {
+            rc = set_err(h, "entropy: mask staging failed");
+            break;
+        }
 #define CKE(call)                                                                       \
     if (!rc && (call) != cudaSuccess) rc = set_err(h, std::string(#call " failed: ") + cudaGetErrorString(cudaGetLastError()))
         CKE(cudaMemcpyAsync(tb.d_bases, bases + offsets[r0], (size_t)nb, cudaMemcpyHostToDevice, st));
@@ -1158,9 +1203,23 @@ int bbduk_b200_entropy(bbduk_handle *h, const bbduk_entropy_cfg *cfg, const uint
         CKE(cudaMemcpyAsync(tb.d_lo, lo + r0, 4 * (size_t)nr, cudaMemcpyHostToDevice, st));
         CKE(cudaMemcpyAsync(tb.d_hi, hi + r0, 4 * (size_t)nr, cudaMemcpyHostToDevice, st));
         CKE(cudaMemcpyAsync(tb.d_flags, flags + r0, (size_t)nr, cudaMemcpyHostToDevice, st));
+        if (mode) {
+            CKE(cudaMemcpyAsync(tb.d_maskoff, mask_off + r0, 8 * (size_t)(nr + 1), cudaMemcpyHostToDevice, st));
+            if (!rc) {
+                maskoff_rebase_kernel<<<(unsigned)((nr + 1 + 255) / 256), 256, 0, st>>>(tb.d_maskoff, mw0, nr + 1);
+                h->launches += 1;
+            }
+            if (!rc)
+                rc = bbduk_b200_entropy_mask_device(h, cfg, mode, tb.d_bases, tb.d_off, nr, paired, tb.d_lo, tb.d_hi, tb.d_flags, tb.d_mask,
+                                                    tb.d_maskoff, d_stats, st);
+            if (mw > 0) CKE(cudaMemcpyAsync(maskbits + mw0, tb.d_mask, 4 * (size_t)mw, cudaMemcpyDeviceToHost, st));
+            if (mode == 3) CKE(cudaMemcpyAsync(lo + r0, tb.d_lo, 4 * (size_t)nr, cudaMemcpyDeviceToHost, st));
+            if (mode == 3) CKE(cudaMemcpyAsync(hi + r0, tb.d_hi, 4 * (size_t)nr, cudaMemcpyDeviceToHost, st));
+        } else {
         if (!rc) rc = bbduk_b200_entropy_device(h, cfg, tb.d_bases, tb.d_off, nr, paired, tb.d_lo, tb.d_hi, tb.d_flags, d_stats, st);
         CKE(cudaMemcpyAsync(hi + r0, tb.d_hi, 4 * (size_t)nr, cudaMemcpyDeviceToHost, st));
         CKE(cudaMemcpyAsync(flags + r0, tb.d_flags, (size_t)nr, cudaMemcpyDeviceToHost, st));
+        }
         CKE(cudaStreamSynchronize(st));
 #undef CKE
         r0 = r1;

@@ -64,3 +64,6 @@ int launch_qtrim(int sm_count, const bbduk_qtrim_cfg *cfg, const BBParams &bp, c
 int launch_entropy(int sm_count, const bbduk_entropy_cfg *cfg, const BBParams &bp, const uint8_t *d_bases, const uint32_t *d_offsets,
                    int64_t n_reads, int paired, const int32_t *d_lo, int32_t *d_hi, uint8_t *d_flags, unsigned long long *d_stats,
                    cudaStream_t st);
+int launch_entropy_mask(int sm_count, const bbduk_entropy_cfg *cfg, const BBParams &bp, const uint8_t *d_bases,
+                        const uint32_t *d_offsets, int64_t n_reads, int paired, int32_t *d_lo, int32_t *d_hi, uint8_t *d_flags,
+                        int mode, uint32_t *d_maskbits, const int64_t *d_mask_off, unsigned long long *d_stats, cudaStream_t st);

@@ -401,6 +401,24 @@ BBDUK_API int bbduk_b200_entropy_device(bbduk_handle *h, const bbduk_entropy_cfg
                                         const uint32_t *d_offsets, int64_t n_reads, int32_t paired, const int32_t *d_lo,
                                         int32_t *d_hi, uint8_t *d_flags, int64_t *d_stats2, void *stream);
 
+/* Entropy masking / trimming (entropymask=t|lc, entropytrim=; jgi/BBDuk.java:3055-3067, :4432-4478, :4505-4526; the step sits
+ * between the poly-X block and quality trimming): every full window of `window` bases without an undefined base whose entropy
+ * fails the cutoff marks its bases. mode 1: the marked bases are to become 'N' (quality 0), mode 2: lower case -- the call
+ * writes the mark bits (bit j of the read's mask words = base j of its kept interval [lo,hi)) to maskbits[mask_off[i] ..],
+ * mask_off[n_reads+1] in 32-bit words with room for ceil(read length / 32) words per read, and the caller rewrites its
+ * bases; mode 3: the marked runs at both ends are trimmed (TrimRead.trimByAmount(r, left, right, 1)): lo[] / hi[] are updated
+ * and the mask words come back zero. Reads of removed units or discarded reads are skipped.
+ * stats2 += {readsEFiltered, basesEFiltered} = reads with / number of bases changed (an N stays an N, lower case stays lower
+ * case) or trimmed. HOST buffers. */
+BBDUK_API int bbduk_b200_entropy_mask(bbduk_handle *h, const bbduk_entropy_cfg *cfg, int32_t mode, const uint8_t *bases,
+                                      const int64_t *offsets, int64_t n_reads, int32_t paired, int32_t *lo, int32_t *hi,
+                                      const uint8_t *flags, uint32_t *maskbits, const int64_t *mask_off, int64_t *stats2);
+/* Same on DEVICE buffers (32-bit offsets, mask_off relative to d_maskbits), asynchronous on `stream`. */
+BBDUK_API int bbduk_b200_entropy_mask_device(bbduk_handle *h, const bbduk_entropy_cfg *cfg, int32_t mode, const uint8_t *d_bases,
+                                             const uint32_t *d_offsets, int64_t n_reads, int32_t paired, int32_t *d_lo,
+                                             int32_t *d_hi, const uint8_t *d_flags, uint32_t *d_maskbits,
+                                             const int64_t *d_mask_off, int64_t *d_stats2, void *stream);
+
 /*
  * The whole device part of the per-pair loop in ONE call: the k-mer block, then (each optional) trim by overlap, poly-X /
  * quality trimming with the quality / length / N filters, and the low-entropy filter, in the reference's order

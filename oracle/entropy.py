@@ -23,6 +23,8 @@ def lib():
         L.entropy_ora_values.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.entropy_ora_process.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.POINTER(EntropyParams), C.c_void_p]
+        L.entropy_ora_mask.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.POINTER(EntropyParams), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -56,3 +58,20 @@ def process(bases, offsets, paired, lo, hi, flags, p: EntropyParams):
     lib().entropy_ora_process(bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1, int(bool(paired)), lo.ctypes.data,
                               hi2.ctypes.data, fl2.ctypes.data, C.byref(p), st.ctypes.data)
     return hi2, fl2, st
+
+
+def mask(bases, offsets, paired, lo, hi, flags, p: EntropyParams, mode):
+    """entropymask (mode 1: N, 2: lower case) / entropytrim (mode 3) -> (new lo, new hi, mask words, mask_off, [readsEFiltered, basesEFiltered])"""
+    bases = np.ascontiguousarray(bases, np.uint8)
+    offsets = np.ascontiguousarray(offsets, np.int64)
+    lo2 = np.array(lo, np.int32, copy=True)
+    hi2 = np.array(hi, np.int32, copy=True)
+    fl = np.ascontiguousarray(flags, np.uint8)
+    words = (np.diff(offsets) + 31) // 32
+    mask_off = np.zeros(len(offsets), np.int64)
+    np.cumsum(words, out=mask_off[1:])
+    bits = np.zeros(max(1, int(mask_off[-1])), np.uint32)
+    st = np.zeros(2, np.int64)
+    lib().entropy_ora_mask(bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1, int(bool(paired)), lo2.ctypes.data, hi2.ctypes.data,
+                           fl.ctypes.data, C.byref(p), int(mode), bits.ctypes.data, mask_off.ctypes.data, st.ctypes.data)
+    return lo2, hi2, bits, mask_off, st

@@ -46,6 +46,11 @@ static int sym0(uint8_t b) { /* dna/AminoAcid.java symbolToNumber0: A0 C1 G2 T/U
     return y == 'c' ? 1 : y == 'g' ? 2 : (y == 't' || y == 'u') ? 3 : 0;
 }
 
+static int is_def(uint8_t b) { /* dna/AminoAcid.java isFullyDefined: A C G T U, either case */
+    const uint8_t y = (uint8_t)(b | 0x20);
+    return b < 128 && (y == 'a' || y == 'c' || y == 'g' || y == 't' || y == 'u');
+}
+
 static void et_init(etracker *t, int k, int window) {
     t->k = k;
     t->windowBases = window;
@@ -77,6 +82,7 @@ static void et_add(etracker *t, uint8_t b) { /* :815-946 */
         t->ring[t->pos] = b;
         const int n = sym0(b);
         t->kmer = ((t->kmer << 2) | n) & t->mask;
+        if (!is_def(b)) t->ns++;
         if (t->len >= t->k) {
             const short oldCount = t->counts[t->kmer];
             if (oldCount < 1) t->unique++;
@@ -89,6 +95,7 @@ static void et_add(etracker *t, uint8_t b) { /* :815-946 */
         const int n2 = sym0(b2);
         t->kmer2 = ((t->kmer2 << 2) | n2) & t->mask;
         if (t->len > t->windowBases) {
+            if (!is_def(oldBase)) t->ns--;
             const short oldCount = t->counts[t->kmer2];
             const short newCount = t->counts[t->kmer2] = (short)(oldCount - 1);
             if (newCount < 1) t->unique--;
@@ -183,6 +190,77 @@ void entropy_ora_process(const uint8_t *bases, const int64_t *offsets, int64_t n
             if (remove) f |= 0x02;
             flags[u + q] = f;
         }
+    }
+    free(t.entropy);
+    free(t.counts);
+    free(t.ring);
+}
+
+/*
+ * jgi/BBDuk.java:3055-3067 with maskLowEntropy (:4432-4446) / trimLowEntropy (:4448-4478) and maskFromBitset (:4505-4526) for every
+ * read that is not discarded and whose unit is not removed. mode 1: mask to N, 2: mask to lower case, 3: trim. The BitSet of a
+ * read goes to maskbits + mask_off[i] (bit j = base j of the kept interval; zero in mode 3, where lo / hi change instead);
+ * stats[0..1] += readsEFiltered, basesEFiltered.
+ */
+void entropy_ora_mask(const uint8_t *bases, const int64_t *offsets, int64_t n_reads, int paired, int32_t *lo, int32_t *hi,
+                      const uint8_t *flags, const entropy_params *p, int mode, uint32_t *maskbits, const int64_t *mask_off,
+                      int64_t *stats) {
+    etracker t;
+    et_init(&t, p->k, p->window);
+    const float cutoff = p->cutoff > 0 ? p->cutoff : 0;
+    const int per = paired ? 2 : 1;
+    for (int64_t i = 0; i < n_reads; i++) {
+        const int64_t u = i - (i % per);
+        uint32_t *bs = maskbits + mask_off[i];
+        const int full = (int)(offsets[i + 1] - offsets[i]);
+        for (int w = 0; w < (full + 31) / 32; w++) bs[w] = 0;
+        if (flags[u] & 0x02) continue;
+        const int n = hi[i] - lo[i];
+        const int is_disc = (flags[i] & 0x01) || (p->trim_failures_to_1bp && n == 1);
+        if (is_disc) continue; /* isNotDiscarded */
+        if (n < t.windowBases) continue;
+        const uint8_t *b = bases + offsets[i] + lo[i];
+        et_clear(&t);
+        for (int j = 0, min = t.windowBases - 1; j < n; j++) {
+            et_add(&t, b[j]);
+            if (j >= min && t.ns < 1) {
+                const float e = et_calc(&t);
+                const int passes = (p->high_pass != 0) ^ (e < cutoff);
+                if (!passes)
+                    for (int q = t.len - t.windowBases; q <= t.len - 1; q++) bs[q >> 5] |= 1u << (q & 31); /* leftPos..rightPos */
+            }
+        }
+        int masked = 0;
+        if (mode == 3) {
+            int left = 0, right = 0;
+            for (int j = 0; j < n; j++) {
+                if ((bs[j >> 5] >> (j & 31)) & 1u) left++;
+                else break;
+            }
+            for (int j = n - 1; j >= 0; j--) {
+                if ((bs[j >> 5] >> (j & 31)) & 1u) right++;
+                else break;
+            }
+            for (int w = 0; w < (full + 31) / 32; w++) bs[w] = 0;
+            if (left || right) { /* TrimRead.trimByAmount(r, left, right, 1), shared/TrimRead.java:299-346 */
+                const int minLen = n < 1 ? n : 1;
+                if (left + right + minLen > n) {
+                    right = n - minLen > 1 ? n - minLen : 1;
+                    left = 0;
+                }
+                lo[i] += left;
+                hi[i] -= right;
+                masked = left + right;
+            }
+        } else {
+            for (int j = 0; j < n; j++) {
+                if (!((bs[j >> 5] >> (j & 31)) & 1u)) continue;
+                if (mode == 1) masked += b[j] != 'N';
+                else masked += !(b[j] >= 'a' && b[j] <= 'z') && b[j] != 'N';
+            }
+        }
+        stats[1] += masked;
+        stats[0] += masked > 0;
     }
     free(t.entropy);
     free(t.counts);

@@ -59,3 +59,29 @@ def test_device_entry_point_and_limits():
     out.lo[:], out.hi[:], out.flags[:] = lo, hi, flags
     with pytest.raises(RuntimeError, match="no device path"):
         g.entropy(bases, offsets, True, out, g.entropy_cfg(cutoff=0.5, k=6))
+
+
+MASK_CASES = [dict(cutoff=0.5), dict(cutoff=0.75, k=4, window=30, tf1=True), dict(cutoff=0.35, k=3, window=20), dict(cutoff=0.6, high_pass=False, k=2, window=12),
+              dict(cutoff=0.8, k=5, window=120)]
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("case", range(len(MASK_CASES)))
+def test_entropy_mask_and_trim(case, mode):
+    """bbduk_b200_entropy_mask: mark bits, lo / hi (trim mode) and the two counters against the oracle, bit for bit"""
+    c = MASK_CASES[case]
+    paired = case % 2 == 0
+    bases, offsets, lo, hi, flags = entropy_batch(8000, 500 + case, L=170)
+    if paired:
+        flags[0::2][np.arange(4000) % 19 == 0] = 2
+        flags[1::2][np.arange(4000) % 19 == 0] = 2
+    g = engine(**c)
+    wlo, whi, wbits, woff, wst = oe.mask(bases, offsets, paired, lo, hi, flags, oe.params(**c), mode)
+    out = Outputs(len(lo))
+    out.lo[:], out.hi[:], out.flags[:] = lo, hi, flags
+    bits, moff, st = g.entropy_mask(bases, offsets, paired, out, g.entropy_cfg(cutoff=c["cutoff"], k=c.get("k", 5), window=c.get("window", 50),
+                                                                              high_pass=int(c.get("high_pass", True))), mode)
+    assert np.array_equal(moff, woff)
+    assert np.array_equal(bits, wbits), f"{np.count_nonzero(bits != wbits)} mask words differ"
+    assert np.array_equal(out.lo, wlo) and np.array_equal(out.hi, whi) and np.array_equal(out.flags, flags)
+    assert list(st) == list(wst) and wst[1] > 1000

@@ -170,3 +170,78 @@ def test_filter_block_matches_python(case):
     assert np.array_equal(ghi, whi) and np.array_equal(gfl, wfl) and list(gst) == list(wst)
     if case.get("cutoff", 0) > 0 and case.get("high_pass", True):
         assert gst[0] > 20
+
+
+def py_low_entropy_mask(seq, k, window, cutoff, high_pass=True):
+    """positions maskLowEntropy marks (jgi/BBDuk.java:4432-4446): every full window without an undefined base whose entropy fails
+    the cutoff. The window's entropy is computed FROM SCRATCH (counts of its k-mers, the table terms summed in sorted order), so
+    only windows whose from-scratch and running-sum entropies could straddle the cutoff are ambiguous; those are reported."""
+    n, wk = len(seq), window - k + 1
+    marked, ambiguous = set(), set()
+    if n < window:
+        return marked, ambiguous
+    codes = [CODE.get(b, 0) for b in seq]
+    for i in range(window - 1, n):
+        a = i - window + 1
+        if any(b not in CODE for b in seq[a:i + 1]):
+            continue
+        c = {}
+        for j in range(a + k - 1, i + 1):
+            km = tuple(codes[j - k + 1:j + 1])
+            c[km] = c.get(km, 0) + 1
+        h = -sum((v / wk) * math.log(v / wk) for v in sorted(c.values())) / math.log(wk)
+        h = max(h, 0.0)
+        if abs(h - cutoff) < 1e-5:
+            ambiguous.update(range(a, i + 1))
+        if not (high_pass ^ (h < cutoff)):
+            marked.update(range(a, i + 1))
+    return marked, ambiguous
+
+
+@pytest.mark.parametrize("case", [dict(cutoff=0.5), dict(cutoff=0.75, k=4, window=30), dict(cutoff=0.35, k=3, window=20, tf1=True),
+                                  dict(cutoff=0.6, high_pass=False, k=2, window=12)])
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_mask_and_trim_match_from_scratch_windows(case, mode):
+    """entropymask / entropytrim: the oracle's BitSet against windows measured from scratch; counts and trims from the marks"""
+    bases, offsets, lo, hi, flags = entropy_batch(300, 21, L=100)
+    flags[0::2][np.arange(150) % 13 == 0] = 2
+    flags[1::2][np.arange(150) % 13 == 0] = 2
+    p = oe.params(**case)
+    glo, ghi, bits, moff, st = oe.mask(bases, offsets, True, lo, hi, flags, p, mode)
+    cutoff = float(np.float32(max(0.0, p.cutoff)))
+    n_marked = reads = total = 0
+    for i in range(len(lo)):
+        seq = bytes(bases[offsets[i] + lo[i]:offsets[i] + hi[i]])
+        n = len(seq)
+        got = {j for j in range(n) if (int(bits[moff[i] + (j >> 5)]) >> (j & 31)) & 1}
+        skip = bool(flags[i - i % 2] & 2) or bool(flags[i] & 1) or (p.trim_failures_to_1bp and n == 1)
+        if skip:
+            assert not got and glo[i] == lo[i] and ghi[i] == hi[i]
+            continue
+        want, amb = py_low_entropy_mask(seq, p.k, p.window, cutoff, bool(p.high_pass))
+        if mode == 3:
+            assert not got
+            if amb:
+                continue
+            left = next((j for j in range(n) if j not in want), n)
+            right = next((j for j in range(n) if (n - 1 - j) not in want), n)
+            if left or right:
+                if left + right + min(n, 1) > n:
+                    left, right = 0, max(1, n - min(n, 1))
+                assert (glo[i], ghi[i]) == (lo[i] + left, hi[i] - right), (i, seq)
+                total += left + right
+                reads += 1
+            else:
+                assert (glo[i], ghi[i]) == (lo[i], hi[i])
+        else:
+            assert got - amb == want - amb, (i, seq)
+            n_marked += len(got)
+            if not amb:
+                x = sum(1 for j in got if seq[j:j + 1] != b"N" and (mode == 1 or not seq[j:j + 1].islower()))
+                total += x
+                reads += x > 0
+    assert (n_marked > 500) if mode != 3 else (reads > 10)
+    if mode != 3:
+        assert st[1] >= total and st[0] >= reads  # (reads with an ambiguous window are not in our count)
+    else:
+        assert st[1] >= total and st[0] >= reads

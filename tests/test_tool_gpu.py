@@ -186,3 +186,50 @@ def test_bbduk_tool_single_kfilter(tmp_path):
     assert res["native"] == res["python"]
     assert 1000 < res["native"][2]["reads_kfiltered"] < 1500
     assert res["native"][0].count(b"\n") + res["native"][1].count(b"\n") == 4 * 5000
+
+
+@pytest.mark.parametrize("flag,mode", [("entropymask", 1), ("entropymask=lc", 2), ("entropytrim=rl", 3)])
+def test_bbduk_tool_entropy_mask_and_trim(tmp_path, flag, mode):
+    """ktrim=r ... entropy=0.6 entropymask / entropytrim: the k-mer block, then low-entropy windows masked (to N with quality 0, or
+    to lower case) or trimmed from both ends (jgi/BBDuk.java:3055-3067); records and counters against the oracles"""
+    from bbtools_b200.bbduk import BBDuk
+    from bbtools_b200.fasta import read_fasta
+    from oracle import entropy as oe
+    from oracle.oracle import Oracle
+    from test_entropy_oracle import entropy_batch
+    bases, offsets, _, _, _ = entropy_batch(3000, 77, L=140)
+    keep = np.diff(offsets) > 0
+    seqs = [bytes(bases[offsets[i]:offsets[i + 1]]) for i in range(len(keep)) if keep[i]]
+    bases = np.frombuffer(b"".join(seqs), np.uint8).copy()
+    offsets = np.zeros(len(seqs) + 1, np.int64)
+    offsets[1:] = np.cumsum([len(s) for s in seqs])
+    path = tmp_path / "r.fq"
+    with open(path, "wb") as f:
+        for i, s in enumerate(seqs):
+            f.write(b"@r%d\n" % i + s + b"\n+\n" + b"I" * len(s) + b"\n")
+    o1, m1 = tmp_path / "o.fq", tmp_path / "m.fq"
+    tool = BBDuk([f"in={path}", f"ref={GOLDEN}/adapters.fa", "ktrim=r", "k=23", "mink=11", "hdist=1", "entropy=0.6", flag, "minlen=1",
+                  f"out={o1}", f"outm={m1}"])
+    tool.process()
+    _, rb, roff = read_fasta(os.path.join(GOLDEN, "adapters.fa"))
+    ora = Oracle(tool.cfg)
+    ora.add_ref(rb, roff)
+    ora.finalize()
+    want, _ = ora.process(bases, offsets, False)
+    wlo, whi, bits, moff, wst = oe.mask(bases, offsets, False, want.lo, want.hi, want.flags, oe.params(cutoff=0.6, rieb=True), mode)
+    assert list(tool.entropy_stats) == list(wst) and wst[1] > 200
+    exp = [[], []]
+    for i, s in enumerate(seqs):
+        s, q = bytearray(s), bytearray(b"I" * len(s))
+        for j in range(int(want.hi[i]) - int(want.lo[i])):
+            if (int(bits[moff[i] + (j >> 5)]) >> (j & 31)) & 1:
+                p = int(want.lo[i]) + j
+                if mode == 1 and s[p] != ord("N"):
+                    s[p], q[p] = ord("N"), 33
+                elif mode == 2:
+                    s[p:p + 1] = bytes(s[p:p + 1]).lower()
+        rem = bool(want.flags[i] & F_REMOVED)
+        a, b = (0, len(s)) if rem else (int(wlo[i]), int(whi[i]))
+        exp[1 if rem else 0].append(b"@r%d\n" % i + bytes(s[a:b]) + b"\n+\n" + bytes(q[a:b]) + b"\n")
+    assert open(o1, "rb").read() == b"".join(exp[0])
+    assert (open(m1, "rb").read() if os.path.exists(m1) else b"") == b"".join(exp[1])
