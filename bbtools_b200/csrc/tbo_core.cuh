@@ -297,7 +297,8 @@ TBO_HD void count_exact(const Ctx<S> &c, int istart, int jstart, int ov, float b
 // against r2' from base 0 ("side A"); afterwards r2' slides (from s = blen - insert, s rising) against r1 from base 0
 // ("side B"). The screen runs BEFORE the insert loops and out of their order: for every s of a side it counts the
 // mismatches (GENERAL: by the reference's N rules) among the first min(ov, 32*NW) bases and sets bit s of the lane's
-// candidate bitmap if they do not exceed `cap`, the largest count any badlimit of the coming loop admits. All lanes of a
+// candidate bitmap if they do not exceed `cap`, the largest count with which an alignment can still change the state
+// of the coming loop. All lanes of a
 // warp walk the same (word, shift) sequence, so the warp stays on one code path whatever the lengths of its pairs:
 // per word index the fixed mate's NW words and the sliding mate's NW+1 words sit in registers and one alignment costs
 // 2*NW funnel shifts, 2*NW logic ops and NW popc. The insert loops then visit the set bits only.
@@ -322,22 +323,6 @@ TBO_HD int ffs32(uint32_t x) {
     return __builtin_ffs((int)x);
 #endif
 }
-// head_mask without selects on the device: a right shift clamped at 32
-TBO_HD uint32_t head_mask_fast(int n) {
-#if defined(__CUDA_ARCH__)
-    return ~__funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t)imax(n, 0));
-#else
-    return head_mask(n);
-#endif
-}
-// head_mask for n >= 0 (a negative n gives all ones on the device, where the shift count clamps at 32)
-TBO_HD uint32_t head_mask_nonneg(int n) {
-#if defined(__CUDA_ARCH__)
-    return ~__funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t)n);
-#else
-    return n < 0 ? 0xFFFFFFFFu : head_mask(n);
-#endif
-}
 // bits r of word w whose position 32w + r lies in [lo, hi]
 TBO_HD uint32_t range_bits(int w, int lo, int hi) {
     const int r_lo = imax(lo - 32 * w, 0), r_hi = imin(hi - 32 * w, 31);
@@ -355,6 +340,9 @@ struct CapLine {
 #endif
     int of(int ov) const { return ((a_fx * ov) >> 16) + b_int; }
 };
+// the same for a limit on the ratio: (T[c] + offset) / ov < ratio  =>  c <= of(ov)
+TBO_HD CapLine cap_line(float a, float b);
+TBO_HD CapLine ratio_cap_line(float ratio, float offset) { return cap_line(ratio, offset < 0.0f ? -offset : 0.0f); }
 TBO_HD CapLine cap_line(float a, float b) {
     CapLine c;
     c.a_fx = (int)(a * 1.0527f * 65536.0f) + 2;
@@ -362,18 +350,19 @@ TBO_HD CapLine cap_line(float a, float b) {
     return c;
 }
 
+// One word of candidate bits: shifts r = 0..31 of the sliding mate's words v* against the fixed mate's first NW words f*.
+// ncap = ~cap of the word (the sign bit of ncap + count says "at most cap mismatches"). MASKED: positions beyond either
+// mate's end do not count -- vv are the sliding mate's validity words (they shift with it), fm the fixed mate's.
 template <bool GENERAL, int NW, bool MASKED>
-TBO_HD uint32_t scan_word(const uint32_t (&fh)[NW], const uint32_t (&fl)[NW], const uint32_t (&fn)[NW], const uint32_t (&vh)[NW + 1],
-                          const uint32_t (&vl)[NW + 1], const uint32_t (&vn)[NW + 1], int X, int Y, int s0, int cap, CapLine cl) {
+TBO_HD uint32_t scan_word(const uint32_t (&fh)[NW], const uint32_t (&fl)[NW], const uint32_t (&fn)[NW], const uint32_t (&fm)[NW],
+                          const uint32_t (&vh)[NW + 1], const uint32_t (&vl)[NW + 1], const uint32_t (&vn)[NW + 1],
+                          const uint32_t (&vv)[NW + 1], int ncap) {
     uint32_t bits = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 4
 #endif
     for (uint32_t r = 0; r < 32; r++) {
-        // ov < 0 only for s beyond the side's range; those bits are cleared by the caller (range_bits)
-        const int ov = MASKED ? imin(X - (s0 + (int)r), Y) : 0;
-        // the sign bit of n after the counts says "at most cap mismatches"; short overlaps get their own, smaller cap
-        int n = MASKED ? ~imin(cap, cl.of(ov)) : ~cap;
+        int n = ncap;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -383,7 +372,7 @@ TBO_HD uint32_t scan_word(const uint32_t (&fh)[NW], const uint32_t (&fl)[NW], co
                 const uint32_t na = fsl(vn[k + 1], vn[k], r);
                 d = (d & ~(na | fn[k])) | (na ^ fn[k]);
             }
-            if (MASKED) d &= (k == 0) ? head_mask_nonneg(ov) : head_mask_fast(ov - 32 * k);
+            if (MASKED) d &= fsl(vv[k + 1], vv[k], r) & fm[k];
             n += popc(d);
         }
         bits = (bits >> 1) | ((uint32_t)n & 0x80000000u);  // after 32 steps bit r holds the verdict of shift r
@@ -392,28 +381,32 @@ TBO_HD uint32_t scan_word(const uint32_t (&fh)[NW], const uint32_t (&fl)[NW], co
 }
 
 // candidate bits of one side for s in [s_lo, s_hi] (words s_lo>>5 .. s_hi>>5 of cand are written). X = length of the
-// sliding mate, Y = of the fixed one: ov(s) = min(X - s, Y).
+// sliding mate, Y = of the fixed one: ov(s) = min(X - s, Y). Every word gets the cap of its longest overlap (s = 32w):
+// cl.of grows with ov, so that cap admits whatever the cap of a later s of the word admits.
 template <bool GENERAL, int S, int NW>
 TBO_HD void scan_side(const uint32_t *sh, const uint32_t *sl, const uint32_t *sn, const uint32_t *fhp, const uint32_t *flp,
                       const uint32_t *fnp, int X, int Y, int s_lo, int s_hi, int cap, CapLine cl, uint32_t *cand) {
     if (s_hi < s_lo) return;
-    uint32_t fh[NW], fl[NW], fn[NW];
+    uint32_t fh[NW], fl[NW], fn[NW], fm[NW];
     for (int k = 0; k < NW; k++) {
         fh[k] = fhp[k * S];
         fl[k] = flp[k * S];
         fn[k] = GENERAL ? fnp[k * S] : 0u;
+        fm[k] = head_mask(Y - 32 * k);
     }
     for (int w = s_lo >> 5; w <= (s_hi >> 5); w++) {
-        uint32_t vh[NW + 1], vl[NW + 1], vn[NW + 1];
+        uint32_t vh[NW + 1], vl[NW + 1], vn[NW + 1], vv[NW + 1];
         for (int k = 0; k <= NW; k++) {
             vh[k] = sh[(w + k) * S];
             vl[k] = sl[(w + k) * S];
             vn[k] = GENERAL ? sn[(w + k) * S] : 0u;
+            vv[k] = head_mask(X - 32 * (w + k));
         }
+        const int ncap = ~imin(cap, cl.of(imax(imin(X - 32 * w, Y), 0)));
         // the shortest overlap of the word is at its last s; unmasked only if no lane of the warp needs the masks
         const bool masked = any_lane(imin(X - (32 * w + 31), Y) < 32 * NW);
-        const uint32_t bits = masked ? scan_word<GENERAL, NW, true>(fh, fl, fn, vh, vl, vn, X, Y, 32 * w, cap, cl)
-                                     : scan_word<GENERAL, NW, false>(fh, fl, fn, vh, vl, vn, X, Y, 32 * w, cap, cl);
+        const uint32_t bits = masked ? scan_word<GENERAL, NW, true>(fh, fl, fn, fm, vh, vl, vn, vv, ncap)
+                                     : scan_word<GENERAL, NW, false>(fh, fl, fn, fm, vh, vl, vn, vv, ncap);
         cand[w * S] = bits & range_bits(w, s_lo, s_hi);
     }
 }
@@ -428,6 +421,9 @@ struct Cands {
     uint32_t bits;
 };
 
+#ifndef TBO_CAP_NW1
+#define TBO_CAP_NW1 20
+#endif
 template <bool GENERAL, int S>
 TBO_HD void build_cands(const Ctx<S> &c, int alen, int blen, int i_top, int i_bot, int cap, CapLine cl, Cands<S> &q) {
     q.a_hi = i_top - blen;
@@ -442,7 +438,12 @@ TBO_HD void build_cands(const Ctx<S> &c, int alen, int blen, int i_top, int i_bo
     if ((GENERAL && c.exact) || cap >= imin(longest, 90)) {  // no screen: the byte path, or a cap the screen cannot beat
         for (int w = imax(q.a_lo, 0) >> 5; w <= (q.a_hi >> 5) && q.a_hi >= q.a_lo; w++) q.A[w * S] = range_bits(w, q.a_lo, q.a_hi);
         for (int w = q.b_lo >> 5; w <= (q.b_hi >> 5) && q.b_hi >= q.b_lo; w++) q.B[w * S] = range_bits(w, q.b_lo, q.b_hi);
-    } else if (!any_lane(cap > 43)) {  // one window width per warp (a wider window than a lane needs is still a valid screen)
+    } else if (!any_lane(cap > TBO_CAP_NW1)) {  // one window width per warp (a wider window than a lane needs is still a valid screen)
+        // 32 bases already reject a chance alignment (24 expected mismatches) with probability > 0.9 at this cap; the few
+        // that slip through cost one exact count each, less than a second window on every alignment
+        scan_side<false, S, 1>(c.ah, c.al, c.an, c.bh, c.bl, c.bn, alen, blen, q.a_lo, q.a_hi, cap, cl, q.A);
+        scan_side<false, S, 1>(c.bh, c.bl, c.bn, c.ah, c.al, c.an, blen, alen, q.b_lo, q.b_hi, cap, cl, q.B);
+    } else if (!any_lane(cap > 43)) {
         // The screen never needs the N planes: the packer codes an N as A, and with that reading a position counts as a
         // mismatch at most as often as by the reference's N rules (N against a base: always bad there, bad here unless the
         // base is A; N against N: bad in neither) -- a lower bound is all the screen promises.
@@ -516,10 +517,13 @@ TBO_HD float find_best_ratio(const Ctx<S> &c, Cands<S> &q, int alen, int blen, i
                              float maxRatio, float offset, const float *T, int n_T) {
     float bestRatio = fadd(maxRatio, 0.0001f);
     const float halfmax = fmul(maxRatio, 0.5f);
-    // badlimit never exceeds its value for the initial bestRatio and the longest overlap (rounding is monotone), so an
-    // alignment that shows more than cap_max mismatches on its first bases fails every badlimit of this loop
-    const int cap_max = cap_of(fadd(fmul(bestRatio, (float)imin(alen, blen)), (float)EXTRA_BADLIMIT), T, n_T);
-    build_cands<GENERAL, S>(c, alen, blen, alen + blen - minOverlap, minInsert, cap_max, cap_line(bestRatio, (float)EXTRA_BADLIMIT), q);
+    // An alignment changes this loop's state only if it has no mismatch at all or its ratio (bad + offset) / ov is below
+    // the running bestRatio, which never exceeds its initial value; the far looser badlimit (+20) only bounds the
+    // reference's counting. So the screen admits the counts c with c = 0 or T[c] + offset < bestRatio0 * ov, i.e.
+    // (T[c] >= 0.9499 c) c <= ratio_cap_line(ov); checked against the float evaluation for every ov by the host test.
+    const CapLine cl = ratio_cap_line(bestRatio, offset);
+    const int cap_max = cl.of(imin(alen, blen));
+    build_cands<GENERAL, S>(c, alen, blen, alen + blen - minOverlap, minInsert, cap_max, cl, q);
     int side, s;
     while (next_cand<S>(q, side, s)) {  // for (insert = alen + blen - minOverlap; insert >= minInsert; insert--), candidates only
         const int insert = side == 0 ? s + blen : blen - s;

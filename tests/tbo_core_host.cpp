@@ -42,6 +42,26 @@ int tbo_host_check_cap_line(float ratio, float margin) {
     return bad;
 }
 
+// ratio_cap_line must admit every count that can lower findBestRatio's running ratio: returns the number of overlap
+// lengths where some c >= 1 with (T[c] + offset) / ov < ratio (the reference's float evaluation) exceeds of(ov)
+int tbo_host_check_ratio_cap_line(float ratio, float offset) {
+    std::vector<float> T(tbo::MAX_LEN + 2);
+    T[0] = 0.0f;
+    for (size_t c = 1; c < T.size(); c++) {
+        volatile float s = T[c - 1] + 0.95f;
+        T[c] = s;
+    }
+    int bad = 0;
+    const tbo::CapLine l = tbo::ratio_cap_line(ratio, offset);
+    for (int ov = 1; ov <= tbo::MAX_LEN; ov++) {
+        int cmax = 0;
+        for (int c = 1; c <= ov; c++)
+            if (tbo::fdiv(tbo::fadd(T[c], offset), (float)ov) < ratio) cmax = c;
+        if (l.of(ov) < cmax) bad++;
+    }
+    return bad;
+}
+
 // same contract as oracle/tbo_oracle.c:tbo_ora_process (quals are ignored: the expectedErrors guard is not part of the core)
 void tbo_host_process(const uint8_t *bases, const int64_t *offsets, int64_t n_reads, const int32_t *lo, int32_t *hi,
                       const uint8_t *flags, int min_overlap0, int min_overlap, int min_insert0, int min_insert, float max_ratio,

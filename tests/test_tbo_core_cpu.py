@@ -77,6 +77,15 @@ def test_cap_line_never_undercuts_the_exact_cap(host):
             assert host.tbo_host_check_cap_line(float(ratio), margin) == 0, (ratio, margin)
 
 
+def test_ratio_cap_line_admits_every_count_that_can_lower_the_best_ratio(host):
+    """findBestRatio's screen: a count c >= 1 only matters if (T[c] + offset) / ov < bestRatio0"""
+    host.tbo_host_check_ratio_cap_line.argtypes = [C.c_float, C.c_float]
+    rng = np.random.default_rng(2)
+    for ratio in [0.1001, 0.0501, 0.1, 0.05, 1e-4, 0.0135, 0.3] + list(rng.random(100) * 0.2):
+        for offset in (0.4, 0.5, 0.0, 0.55, -0.3):
+            assert host.tbo_host_check_ratio_cap_line(float(ratio), offset) == 0, (ratio, offset)
+
+
 @pytest.mark.parametrize("reverse", [0, 1])
 def test_packing_matches_a_bytewise_restatement(host, reverse):
     rng = np.random.default_rng(5 + reverse)
@@ -165,3 +174,37 @@ def test_cfg2_pairs_and_long_ragged_reads_match_the_oracle(host):
     for g, w in zip(got[:4], want):
         assert np.array_equal(g, w)
     assert want[3][0] > 20
+
+
+def test_borderline_mismatch_rates_and_repeats_match_the_oracle(host):
+    """overlaps whose mismatch ratio straddles maxRatio (the screen's cap is derived from it) and tandem repeats, where
+    many alignments of one pair compete"""
+    rng = np.random.default_rng(77)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    seqs = []
+    for i in range(3000):
+        n1, n2 = (int(x) for x in rng.integers(60, 260, 2))
+        ins = int(rng.integers(20, n1 + n2))
+        if i % 4 == 0:  # tandem repeat of a short unit, with a few point changes
+            unit = acgt[rng.integers(0, 4, int(rng.integers(1, 9)))]
+            frag = np.tile(unit, ins // len(unit) + 1)[:ins].copy()
+        else:
+            frag = acgt[rng.integers(0, 4, ins)]
+        r1 = np.concatenate([frag, acgt[rng.integers(0, 4, 300)]])[:n1].copy()
+        r2 = np.concatenate([COMP[frag[::-1]], acgt[rng.integers(0, 4, 300)]])[:n2].copy()
+        rate = rng.random() * 0.2
+        for r in (r1, r2):
+            hit = rng.random(len(r)) < rate / 2
+            r[hit] = acgt[rng.integers(0, 4, int(hit.sum()))]
+        seqs += [r1, r2]
+    bases = np.concatenate(seqs).astype(np.uint8)
+    offsets = np.zeros(len(seqs) + 1, np.int64)
+    np.cumsum([len(x) for x in seqs], out=offsets[1:])
+    L = np.diff(offsets).astype(np.int32)
+    z, f = np.zeros(len(L), np.int32), np.zeros(len(L), np.uint8)
+    for p in (otbo.default_params(True), otbo.default_params(False)):
+        want = otbo.process(bases, None, offsets, z, L, f, p)
+        got = run_host(host, bases, offsets, z, L, f, p)
+        for g, w in zip(got[:4], want):
+            assert np.array_equal(g, w)
+        assert 200 < want[3][0] < 5000  # some pairs trimmed, some not
