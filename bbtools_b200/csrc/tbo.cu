@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(TBO_THREADS)
 tbo_kernel(const uint8_t *__restrict__ bases, const uint8_t *__restrict__ quals, const uint32_t *__restrict__ offsets,
            int64_t n_pairs, const int32_t *__restrict__ lo, int32_t *hi, uint8_t *flags, int32_t *insert_out, TboDev p,
            const float *__restrict__ T_g, int n_T, const float *__restrict__ prob_error_g, const uint8_t *__restrict__ comp_g,
-           unsigned long long *stats, int32_t *list_g, unsigned int *list_g_n, int32_t *list_m, float *list_m_x,
+           unsigned long long *stats, int32_t *list_g, unsigned int *list_g_n, int32_t *list_m, tbo::Handoff *list_m_x,
            unsigned int *list_m_n) {
     constexpr bool GENERAL = MODE == 2;
     constexpr int S = TBO_THREADS;
@@ -90,7 +90,7 @@ tbo_kernel(const uint8_t *__restrict__ bases, const uint8_t *__restrict__ quals,
                 list_g[atomicAdd(list_g_n, 1u)] = (int32_t)pair;
                 continue;
             }
-            float x = MODE == 1 ? list_m_x[item] : 0.0f;
+            tbo::Handoff x = MODE == 1 ? list_m_x[item] : tbo::Handoff{0.0f, -1};
             best = tbo::mate_by_overlap_ratio<GENERAL, MODE == 0 ? 1 : MODE == 1 ? 2 : 0, S>(c, q, alen, blen, p, T, n_T, ambig, &x);
             if (MODE == 0 && best == -3) {  // the second loop runs in the compacted launch
                 const unsigned int w = atomicAdd(list_m_n, 1u);
@@ -130,7 +130,7 @@ struct TboTables {
     float *d_T = nullptr, *d_pe = nullptr;
     uint8_t *d_comp = nullptr;
     int32_t *d_list = nullptr, *d_list_m = nullptr;  // pairs left to the general launch / to the second-loop launch
-    float *d_list_x = nullptr;
+    tbo::Handoff *d_list_x = nullptr;
     unsigned int *d_list_n = nullptr;                // [0] general, [1] second loop
     int64_t list_cap = 0;
     int device = -1;
@@ -151,7 +151,7 @@ int get_tables(int device, int64_t n_pairs, TboTables *out) {
                 t.list_cap = n_pairs + n_pairs / 8 + 1024;
                 if (cudaMalloc(&t.d_list, sizeof(int32_t) * t.list_cap) != cudaSuccess ||
                     cudaMalloc(&t.d_list_m, sizeof(int32_t) * t.list_cap) != cudaSuccess ||
-                    cudaMalloc(&t.d_list_x, sizeof(float) * t.list_cap) != cudaSuccess)
+                    cudaMalloc(&t.d_list_x, sizeof(tbo::Handoff) * t.list_cap) != cudaSuccess)
                     return 1;
             }
             *out = t;
@@ -189,7 +189,7 @@ int get_tables(int device, int64_t n_pairs, TboTables *out) {
     t.list_cap = n_pairs + n_pairs / 8 + 1024;
     if (cudaMalloc(&t.d_list, sizeof(int32_t) * t.list_cap) != cudaSuccess ||
         cudaMalloc(&t.d_list_m, sizeof(int32_t) * t.list_cap) != cudaSuccess ||
-        cudaMalloc(&t.d_list_x, sizeof(float) * t.list_cap) != cudaSuccess || cudaMalloc(&t.d_list_n, 2 * sizeof(unsigned int)) != cudaSuccess)
+        cudaMalloc(&t.d_list_x, sizeof(tbo::Handoff) * t.list_cap) != cudaSuccess || cudaMalloc(&t.d_list_n, 2 * sizeof(unsigned int)) != cudaSuccess)
         return 1;
     g_tabs.push_back(t);
     *out = t;

@@ -383,9 +383,17 @@ TBO_HD uint32_t scan_word(const uint32_t (&fh)[NW], const uint32_t (&fl)[NW], co
 // candidate bits of one side for s in [s_lo, s_hi] (words s_lo>>5 .. s_hi>>5 of cand are written). X = length of the
 // sliding mate, Y = of the fixed one: ov(s) = min(X - s, Y). Every word gets the cap of its longest overlap (s = 32w):
 // cl.of grows with ov, so that cap admits whatever the cap of a later s of the word admits.
+// Words on the far side of `cut` (tight_below: words below it, else words from it on) belong to alignments the loop
+// visits after the one that set maxRatio; they get the tighter cap (cap2, cl2) -- see mate_by_overlap_ratio.
+struct Cap2 {
+    int cut_word;      // a word index
+    bool tight_below;  // which side of cut_word is tight
+    int cap;
+    CapLine cl;
+};
 template <bool GENERAL, int S, int NW>
 TBO_HD void scan_side(const uint32_t *sh, const uint32_t *sl, const uint32_t *sn, const uint32_t *fhp, const uint32_t *flp,
-                      const uint32_t *fnp, int X, int Y, int s_lo, int s_hi, int cap, CapLine cl, uint32_t *cand) {
+                      const uint32_t *fnp, int X, int Y, int s_lo, int s_hi, int cap, CapLine cl, const Cap2 &c2, uint32_t *cand) {
     if (s_hi < s_lo) return;
     uint32_t fh[NW], fl[NW], fn[NW], fm[NW];
     for (int k = 0; k < NW; k++) {
@@ -402,7 +410,10 @@ TBO_HD void scan_side(const uint32_t *sh, const uint32_t *sl, const uint32_t *sn
             vn[k] = GENERAL ? sn[(w + k) * S] : 0u;
             vv[k] = head_mask(X - 32 * (w + k));
         }
-        const int ncap = ~imin(cap, cl.of(imax(imin(X - 32 * w, Y), 0)));
+        const int ov0 = imax(imin(X - 32 * w, Y), 0);
+        int cap_w = imin(cap, cl.of(ov0));
+        if (c2.tight_below ? (w < c2.cut_word) : (w >= c2.cut_word)) cap_w = imin(cap_w, imin(c2.cap, c2.cl.of(ov0)));
+        const int ncap = ~cap_w;
         // the shortest overlap of the word is at its last s; unmasked only if no lane of the warp needs the masks
         const bool masked = any_lane(imin(X - (32 * w + 31), Y) < 32 * NW);
         const uint32_t bits = masked ? scan_word<GENERAL, NW, true>(fh, fl, fn, fm, vh, vl, vn, vv, ncap)
@@ -425,7 +436,8 @@ struct Cands {
 #define TBO_CAP_NW1 20
 #endif
 template <bool GENERAL, int S>
-TBO_HD void build_cands(const Ctx<S> &c, int alen, int blen, int i_top, int i_bot, int cap, CapLine cl, Cands<S> &q) {
+TBO_HD void build_cands(const Ctx<S> &c, int alen, int blen, int i_top, int i_bot, int cap, CapLine cl, Cands<S> &q,
+                        int i_tight = -(1 << 30), int cap_tight = 0, CapLine cl_tight = CapLine{0, 0}) {
     q.a_hi = i_top - blen;
     q.a_lo = imax(1, i_bot - blen);
     q.b_lo = imax(0, blen - i_top);
@@ -435,23 +447,32 @@ TBO_HD void build_cands(const Ctx<S> &c, int alen, int blen, int i_top, int i_bo
         q.b_hi = q.b_lo - 1;
     }
     const int longest = imin(alen, blen);
+    // inserts below i_tight take the tight cap. Side A: s = insert - blen < i_tight - blen, rounded down to a word so
+    // that the word holding the boundary stays loose; side B: s = blen - insert > blen - i_tight, rounded up likewise.
+    Cap2 ca, cb;
+    ca.tight_below = true;
+    ca.cut_word = imax(i_tight - blen, 0) >> 5;
+    cb.tight_below = false;
+    cb.cut_word = blen - i_tight < 0 ? 0 : ((blen - i_tight) >> 5) + 1;
+    ca.cap = cb.cap = cap_tight;
+    ca.cl = cb.cl = cl_tight;
     if ((GENERAL && c.exact) || cap >= imin(longest, 90)) {  // no screen: the byte path, or a cap the screen cannot beat
         for (int w = imax(q.a_lo, 0) >> 5; w <= (q.a_hi >> 5) && q.a_hi >= q.a_lo; w++) q.A[w * S] = range_bits(w, q.a_lo, q.a_hi);
         for (int w = q.b_lo >> 5; w <= (q.b_hi >> 5) && q.b_hi >= q.b_lo; w++) q.B[w * S] = range_bits(w, q.b_lo, q.b_hi);
     } else if (!any_lane(cap > TBO_CAP_NW1)) {  // one window width per warp (a wider window than a lane needs is still a valid screen)
-        // 32 bases already reject a chance alignment (24 expected mismatches) with probability > 0.9 at this cap; the few
-        // that slip through cost one exact count each, less than a second window on every alignment
-        scan_side<false, S, 1>(c.ah, c.al, c.an, c.bh, c.bl, c.bn, alen, blen, q.a_lo, q.a_hi, cap, cl, q.A);
-        scan_side<false, S, 1>(c.bh, c.bl, c.bn, c.ah, c.al, c.an, blen, alen, q.b_lo, q.b_hi, cap, cl, q.B);
-    } else if (!any_lane(cap > 43)) {
         // The screen never needs the N planes: the packer codes an N as A, and with that reading a position counts as a
         // mismatch at most as often as by the reference's N rules (N against a base: always bad there, bad here unless the
         // base is A; N against N: bad in neither) -- a lower bound is all the screen promises.
-        scan_side<false, S, 2>(c.ah, c.al, c.an, c.bh, c.bl, c.bn, alen, blen, q.a_lo, q.a_hi, cap, cl, q.A);
-        scan_side<false, S, 2>(c.bh, c.bl, c.bn, c.ah, c.al, c.an, blen, alen, q.b_lo, q.b_hi, cap, cl, q.B);
+        // 32 bases already reject a chance alignment (24 expected mismatches) with probability > 0.9 at this cap; the few
+        // that slip through cost one exact count each, less than a second window on every alignment
+        scan_side<false, S, 1>(c.ah, c.al, c.an, c.bh, c.bl, c.bn, alen, blen, q.a_lo, q.a_hi, cap, cl, ca, q.A);
+        scan_side<false, S, 1>(c.bh, c.bl, c.bn, c.ah, c.al, c.an, blen, alen, q.b_lo, q.b_hi, cap, cl, cb, q.B);
+    } else if (!any_lane(cap > 43)) {
+        scan_side<false, S, 2>(c.ah, c.al, c.an, c.bh, c.bl, c.bn, alen, blen, q.a_lo, q.a_hi, cap, cl, ca, q.A);
+        scan_side<false, S, 2>(c.bh, c.bl, c.bn, c.ah, c.al, c.an, blen, alen, q.b_lo, q.b_hi, cap, cl, cb, q.B);
     } else {
-        scan_side<false, S, 4>(c.ah, c.al, c.an, c.bh, c.bl, c.bn, alen, blen, q.a_lo, q.a_hi, cap, cl, q.A);
-        scan_side<false, S, 4>(c.bh, c.bl, c.bn, c.ah, c.al, c.an, blen, alen, q.b_lo, q.b_hi, cap, cl, q.B);
+        scan_side<false, S, 4>(c.ah, c.al, c.an, c.bh, c.bl, c.bn, alen, blen, q.a_lo, q.a_hi, cap, cl, ca, q.A);
+        scan_side<false, S, 4>(c.bh, c.bl, c.bn, c.ah, c.al, c.an, blen, alen, q.b_lo, q.b_hi, cap, cl, cb, q.B);
     }
     if (q.a_hi >= q.a_lo) {
         q.phase = 0;
@@ -514,7 +535,8 @@ TBO_HD int cap_of(float limit, const float *T, int n_T) {
 // jgi/BBMergeOverlapper.java:785-836
 template <bool GENERAL, int S>
 TBO_HD float find_best_ratio(const Ctx<S> &c, Cands<S> &q, int alen, int blen, int minOverlap0, int minOverlap, int minInsert,
-                             float maxRatio, float offset, const float *T, int n_T) {
+                             float maxRatio, float offset, const float *T, int n_T, int &best_ins) {
+    best_ins = -1;  // the insert whose ratio is returned (if any alignment lowered the initial value)
     float bestRatio = fadd(maxRatio, 0.0001f);
     const float halfmax = fmul(maxRatio, 0.5f);
     // An alignment changes this loop's state only if it has no mismatch at all or its ratio (bad + offset) / ov is below
@@ -539,6 +561,7 @@ TBO_HD float find_best_ratio(const Ctx<S> &c, Cands<S> &q, int alen, int blen, i
             const float ratio = fdiv(fadd(bad, offset), (float)ov);
             if (ratio < bestRatio) {
                 bestRatio = ratio;
+                best_ins = insert;
                 if (good >= (float)minOverlap && ratio < halfmax) return bestRatio;
             }
         }
@@ -547,11 +570,15 @@ TBO_HD float find_best_ratio(const Ctx<S> &c, Cands<S> &q, int alen, int blen, i
 }
 
 // jgi/BBMergeOverlapper.java:411-621 (TAG_CUSTOM = MAKE_VECTOR = false); returns bestInsert, sets ambig
-// STAGE 0: both loops. STAGE 1: findBestRatio only; returns -3 and *x_io if the second loop has to run.
-// STAGE 2: the second loop, with findBestRatio's result handed in through *x_io.
+// STAGE 0: both loops. STAGE 1: findBestRatio only; returns -3 and *h if the second loop has to run.
+// STAGE 2: the second loop, with findBestRatio's result handed in through *h.
+struct Handoff {
+    float x;   // findBestRatio's ratio
+    int ins;   // the insert that has it
+};
 template <bool GENERAL, int STAGE, int S>
 TBO_HD int mate_by_overlap_ratio(const Ctx<S> &c, Cands<S> &q, int alen, int blen, const Params &p, const float *T, int n_T,
-                                 bool &ambig_out, float *x_io) {
+                                 bool &ambig_out, Handoff *h) {
     const int minOverlap = imax(4, imax(p.minOverlap0, p.minOverlap));
     int minOverlap0;
     {  // Tools.mid(4, minOverlap0, minOverlap): the median
@@ -560,14 +587,20 @@ TBO_HD int mate_by_overlap_ratio(const Ctx<S> &c, Cands<S> &q, int alen, int ble
     }
     const int minLength = imin(alen, blen);
     float maxRatio = p.maxRatio;
+    int x_ins;
     ambig_out = false;
     {
         float x;
-        if (STAGE == 2) x = *x_io;
-        else x = find_best_ratio<GENERAL, S>(c, q, alen, blen, minOverlap0, minOverlap, p.minInsert, maxRatio, p.offset, T, n_T);
+        if (STAGE == 2) {
+            x = h->x;
+            x_ins = h->ins;
+        } else {
+            x = find_best_ratio<GENERAL, S>(c, q, alen, blen, minOverlap0, minOverlap, p.minInsert, maxRatio, p.offset, T, n_T, x_ins);
+        }
         if (x > maxRatio) return -1;  // rvector[4] = 0
         if (STAGE == 1) {
-            *x_io = x;
+            h->x = x;
+            h->ins = x_ins;
             return -3;
         }
         maxRatio = x < maxRatio ? x : maxRatio;
@@ -577,11 +610,18 @@ TBO_HD int mate_by_overlap_ratio(const Ctx<S> &c, Cands<S> &q, int alen, int ble
     int bestInsert = -1;
     float bestRatio = 1.0f, secondBestRatio = 1.0f;
     bool ambig = false;
-    // min(bestRatio, maxRatio) <= maxRatio and ov <= minLength: the screen's cap for this loop
+    // min(bestRatio, maxRatio) <= maxRatio and ov <= minLength: the screen's cap for this loop.
+    // maxRatio is now the ratio of the alignment at insert x_ins (x <= p.maxRatio got us here, and an x below the initial
+    // value is always some alignment's ratio). That alignment is visited by this loop too, passes its badlimit (bad <
+    // x * ov) and leaves bestRatio <= maxRatio. Every alignment visited after it -- the inserts below x_ins -- then changes
+    // the state only if it has no mismatch or ratio < bestRatio * margin <= maxRatio * margin: those inserts get the cap
+    // of that ratio test. (Before x_ins bestRatio may still be anything up to 1 and only the badlimit bounds the count.)
     const int cap_max =
         cap_of(fadd(fadd(fmul(1.2f, fmul(fmul(maxRatio, margin), (float)minLength)), 1.0f), (float)EXTRA_BADLIMIT), T, n_T);
+    const CapLine cl_t = ratio_cap_line(fmul(maxRatio, margin), offset);
     build_cands<GENERAL, S>(c, alen, blen, alen + blen - minOverlap0, p.minInsert0, cap_max,
-                            cap_line(fmul(1.2f, fmul(maxRatio, margin)), 1.0f + (float)EXTRA_BADLIMIT), q);
+                            cap_line(fmul(1.2f, fmul(maxRatio, margin)), 1.0f + (float)EXTRA_BADLIMIT), q, x_ins, cl_t.of(minLength),
+                            cl_t);
     int side, s;
     while (next_cand<S>(q, side, s)) {  // for (insert = alen + blen - minOverlap0; insert >= minInsert0; insert--), candidates only
         const int insert = side == 0 ? s + blen : blen - s;

@@ -105,11 +105,11 @@ void tbo_host_process(const uint8_t *bases, const int64_t *offsets, int64_t n_re
             path_counts[2]++;
             tbo::pack_pair<true, 1>(a, alen, b0, blen, planes.data(), W, c, q);
             if (c.exact) path_counts[3]++;
-            float x = 0;
+            tbo::Handoff x{0.0f, -1};
             best = tbo::mate_by_overlap_ratio<true, 0, 1>(c, q, alen, blen, p, T.data(), n_T, ambig, &x);
         } else {  // MODE 0, then MODE 1 after a re-pack as on the device
             path_counts[0]++;
-            float x = 0;
+            tbo::Handoff x{0.0f, -1};
             best = tbo::mate_by_overlap_ratio<false, 1, 1>(c, q, alen, blen, p, T.data(), n_T, ambig, &x);
             if (best == -3) {
                 path_counts[1]++;
