@@ -50,6 +50,33 @@ __device__ __forceinline__ uint32_t codes4(uint32_t w) {
     return codes & ~((nz >> 7) * 0xFFu);
 }
 
+// The tile's bases -> codes in shared memory. Four 16-byte loads per lane are in flight at a time: with six warps per SM
+// a loop that waits for every load on its own spends a third of the kernel here.
+__device__ __forceinline__ void stage_codes(const uint8_t *__restrict__ src16, uint32_t nchunks, uint8_t *Bs, int lane) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(src16);
+    uint4 *dst = reinterpret_cast<uint4 *>(Bs);
+    uint32_t c = lane;
+    for (; c + 96 < nchunks; c += 128) {
+        uint4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = __ldg(src + c + 32 * j);
+#pragma unroll
+        for (int j = 0; j < 4; j++) dst[c + 32 * j] = make_uint4(codes4(v[j].x), codes4(v[j].y), codes4(v[j].z), codes4(v[j].w));
+    }
+    for (; c < nchunks; c += 32) {
+        const uint4 v = __ldg(src + c);
+        dst[c] = make_uint4(codes4(v.x), codes4(v.y), codes4(v.z), codes4(v.w));
+    }
+}
+// pull the warp's next tile into L2 while this one is being worked on (one 128-byte line per lane and round)
+__device__ __forceinline__ void prefetch_tile(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ offsets, int64_t n_reads,
+                                              int64_t tile, int lane) {
+    if (tile * 32 >= n_reads) return;
+    const int64_t r1 = tile * 32 + 32 < n_reads ? tile * 32 + 32 : n_reads;
+    const uint32_t b0 = __ldg(offsets + tile * 32) & ~127u, b1 = __ldg(offsets + r1);
+    for (uint32_t a = b0 + 128u * (uint32_t)lane; a < b1; a += 128u * 32u) asm volatile("prefetch.global.L2 [%0];" ::"l"(bases + a));
+}
+
 // EntropyTracker.averageEntropy(bases, allowNs = true) (tracker/EntropyTracker.java:657-703) of one read. src = the read's
 // staged codes (STAGED) or its ASCII bases. Cl = this lane's slice of the warp's count table: the count of k-mer x is the
 // byte (x & 3) of word (x >> 2) * 32 + lane, so the 32 lanes of a warp always hit 32 different banks. The window loop is
@@ -84,20 +111,36 @@ __device__ __forceinline__ float average_entropy(const uint8_t *__restrict__ src
     const int lim = min(n, W);
     int i = 0;
     for (; i < min(lim, k - 1); i++) kmer = ((kmer << 2) | code(i)) & mask;
-    for (; i < lim; i++) {
+    // Both loops are software-pipelined by hand: the only serial part of a base is the reference's chain of double-precision
+    // adds (two while the first window fills, four afterwards). The counts and table terms of base i+1 are fetched while
+    // the adds of base i are in flight; with six warps per SM nothing else would cover those latencies.
+    if (i < lim) {
         kmer = ((kmer << 2) | code(i)) & mask;
-        enter(kmer);
+        uint8_t *s = slot(kmer);
+        uint32_t oc = *s;
+        *s = (uint8_t)(oc + 1);
+        double ea = E[oc + 1], eb = E[oc];
+        for (i++; i < lim; i++) {
+            kmer = ((kmer << 2) | code(i)) & mask;
+            s = slot(kmer);
+            oc = *s;
+            esum = __dsub_rn(__dadd_rn(esum, ea), eb);
+            *s = (uint8_t)(oc + 1);
+            ea = E[oc + 1];
+            eb = E[oc];
+        }
+        esum = __dsub_rn(__dadd_rn(esum, ea), eb);
     }
     measure();  // the first window (or the whole read if it is shorter)
     if (n > W) {
         uint32_t kmer2 = 0;  // the reference has rolled bases 0..k-2 into kmer2 by now
         for (int t = 0; t < k - 1; t++) kmer2 = ((kmer2 << 2) | code(t)) & mask;
         // One k-mer enters and one leaves per base. Both count loads are issued before either store (the two slots differ
-        // unless the same k-mer enters and leaves, which is patched up in registers), the four table terms are fetched
-        // together, and the next base's codes are read ahead of the stores they could alias with; what remains serial is
-        // the reference's chain of four double-precision adds per base.
-        uint32_t c_in = i < n ? code(i) : 0u, c_out = i < n ? code(i - W + k - 1) : 0u;
-        for (; i < n; i++) {
+        // unless the same k-mer enters and leaves, which is patched up in registers) and the next base's codes are read
+        // ahead of the stores they could alias with.
+        uint32_t c_in = code(i), c_out = code(i - W + k - 1);
+        double e1a, e1b, e2a, e2b;
+        {
             kmer = ((kmer << 2) | c_in) & mask;
             kmer2 = ((kmer2 << 2) | c_out) & mask;
             if (i + 1 < n) {
@@ -108,23 +151,41 @@ __device__ __forceinline__ float average_entropy(const uint8_t *__restrict__ src
             const uint32_t oc1 = *s1;
             uint32_t oc2 = *s2;
             if (s1 == s2) oc2 = oc1 + 1;  // it was just counted
-            const double e1a = E[oc1 + 1], e1b = E[oc1], e2a = E[oc2 - 1], e2b = E[oc2];
             *s1 = (uint8_t)(oc1 + 1);
             *s2 = (uint8_t)(oc2 - 1);  // same slot: ends at oc1 again
+            e1a = E[oc1 + 1], e1b = E[oc1], e2a = E[oc2 - 1], e2b = E[oc2];
+        }
+        for (i++; i < n; i++) {
+            kmer = ((kmer << 2) | c_in) & mask;
+            kmer2 = ((kmer2 << 2) | c_out) & mask;
+            if (i + 1 < n) {
+                c_in = code(i + 1);
+                c_out = code(i + 1 - W + k - 1);
+            }
+            uint8_t *s1 = slot(kmer), *s2 = slot(kmer2);
+            const uint32_t oc1 = *s1;
+            uint32_t oc2 = *s2;
+            // the previous base's adds run while this base's counts arrive
             esum = __dsub_rn(__dadd_rn(esum, e1a), e1b);
             esum = __dsub_rn(__dadd_rn(esum, e2a), e2b);
             measure();
+            if (s1 == s2) oc2 = oc1 + 1;
+            *s1 = (uint8_t)(oc1 + 1);
+            *s2 = (uint8_t)(oc2 - 1);
+            e1a = E[oc1 + 1], e1b = E[oc1], e2a = E[oc2 - 1], e2b = E[oc2];
         }
+        esum = __dsub_rn(__dadd_rn(esum, e1a), e1b);
+        esum = __dsub_rn(__dadd_rn(esum, e2a), e2b);
+        measure();
     }
-    {  // leave the table zeroed: the k-mers still inside the last window
+    {  // leave the table zeroed: the k-mers still inside the last window are the only non-zero counts
         const int start = max(0, n - W);
         uint32_t km = 0;
-        for (int t = start; t < n; t++) {
+        int t = start;
+        for (; t < min(n, start + k - 1); t++) km = ((km << 2) | code(t)) & mask;
+        for (; t < n; t++) {
             km = ((km << 2) | code(t)) & mask;
-            if (t >= start + k - 1) {
-                uint8_t *c = slot(km);
-                *c = (uint8_t)(*c - 1);
-            }
+            *slot(km) = 0;
         }
     }
     return (float)__ddiv_rn(sum, (double)max(1, div));
@@ -170,13 +231,8 @@ entropy_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ o
         const uint32_t a0t = t_lo & ~15u;
         const uint32_t nchunks = (t_hi - a0t + 15u) >> 4;
         const bool staged = nchunks * 16u <= (uint32_t)ES_BYTES && (reinterpret_cast<uintptr_t>(bases) & 15) == 0;
-        if (staged) {
-            uint4 *dst = reinterpret_cast<uint4 *>(Bs);
-            for (uint32_t c = lane; c < nchunks; c += 32) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(bases + a0t) + c);
-                dst[c] = make_uint4(codes4(v.x), codes4(v.y), codes4(v.z), codes4(v.w));
-            }
-        }
+        if (staged) stage_codes(bases + a0t, nchunks, Bs, lane);
+        prefetch_tile(bases, offsets, n_reads, tile + warps_total, lane);
         __syncwarp();
         if (!removed && !was_disc) {  // isNotDiscarded(r) && !passes(r.bases, true)
             const int n = h - l;
