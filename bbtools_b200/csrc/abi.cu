@@ -682,6 +682,9 @@ static int process_host_impl(bbduk_handle *h, const uint8_t *bases, const uint32
                 h->pool = new HostPool(share < 0 ? std::max(1, -share) : std::max(1, std::min(32, hc / share)));
                 // few packing workers per GPU (many ranks on one host): lean on PCIe more
                 if (!h->ascii_every_set) h->ascii_every = h->pool->size() >= 12 ? 3 : h->pool->size() >= 6 ? 2 : 1;
+                // four workers or fewer per GPU (eight ranks on a 32-core host): packing loses to plain DMA whatever the
+                // share (tools/e2e_mix_sweep.py, profiles/r02p_e2e_mix_sweep_8gpu.jsonl), so the share stays fixed
+                if (!h->ascii_every_set && h->pool->size() < 6) h->ascii_every_set = true;
             }
             std::atomic<int> mx{0};
             std::atomic<bool> bad{false};
