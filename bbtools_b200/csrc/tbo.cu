@@ -60,6 +60,15 @@ tbo_kernel(const uint8_t *__restrict__ bases, const uint8_t *__restrict__ quals,
     const int64_t n_items = MODE == 2 ? (int64_t)*list_g_n : MODE == 1 ? (int64_t)*list_m_n : n_pairs;
     for (int64_t item = (int64_t)blockIdx.x * TBO_THREADS + threadIdx.x; item < n_items; item += (int64_t)gridDim.x * TBO_THREADS) {
         const int64_t pair = MODE == 2 ? (int64_t)list_g[item] : MODE == 1 ? (int64_t)list_m[item] : item;
+        if (MODE == 0) {  // the block's next 128 pairs are one contiguous stretch of the batch: pull it into L2 meanwhile
+            const int64_t nxt = item - threadIdx.x + (int64_t)gridDim.x * TBO_THREADS;
+            if (nxt < n_items) {
+                const int64_t last = nxt + TBO_THREADS < n_items ? nxt + TBO_THREADS : n_items;
+                const uint32_t b0p = offsets[2 * nxt] & ~127u, b1p = offsets[2 * last];
+                for (uint32_t a_ = b0p + 128u * threadIdx.x; a_ < b1p; a_ += 128u * TBO_THREADS)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(bases + a_));
+            }
+        }
         const int64_t i1 = 2 * pair, i2 = i1 + 1;
         int best = -1;
         bool ambig = false;

@@ -359,7 +359,7 @@ TBO_HD uint32_t scan_word(const uint32_t (&fh)[NW], const uint32_t (&fl)[NW], co
                           const uint32_t (&vv)[NW + 1], int ncap) {
     uint32_t bits = 0;
 #if defined(__CUDA_ARCH__)
-#pragma unroll 4
+#pragma unroll(NW == 1 ? 8 : 4)
 #endif
     for (uint32_t r = 0; r < 32; r++) {
         int n = ncap;
@@ -375,9 +375,9 @@ TBO_HD uint32_t scan_word(const uint32_t (&fh)[NW], const uint32_t (&fl)[NW], co
             if (MASKED) d &= fsl(vv[k + 1], vv[k], r) & fm[k];
             n += popc(d);
         }
-        bits = (bits >> 1) | ((uint32_t)n & 0x80000000u);  // after 32 steps bit r holds the verdict of shift r
+        bits = fsl((uint32_t)n, bits, 1);  // one funnel shift takes n's sign bit in: after 32 steps bit 31-r holds the verdict of shift r
     }
-    return bits;
+    return brev(bits);
 }
 
 // candidate bits of one side for s in [s_lo, s_hi] (words s_lo>>5 .. s_hi>>5 of cand are written). X = length of the
