@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=100_000_000, help="pairs (cfg2) / half the reads (cfg3)")
     ap.add_argument("--chunk-pairs", type=int, default=4 << 20)
     ap.add_argument("--scale", type=float, default=1.0, help="cfg3: fraction of the 100 Mbp reference (the oracle's table is host RAM)")
+    ap.add_argument("--mode", default="ktrimr", choices=["ktrimr", "ktriml", "kfilter", "kmask"],
+                    help="cfg2 reads and adapters through another mode of the tuned kernel (ktrim=l, kfilter, ktrim=N)")
     ap.add_argument("--tbo", action="store_true", help="cfg2: follow the k-mer block with trim-by-overlap (the `tpe tbo` command)")
     ap.add_argument("--qtrim", action="store_true", help="cfg2: then quality trimming qtrim=rl trimq=10 on synthetic decaying qualities")
     args = ap.parse_args()
@@ -41,7 +43,10 @@ def main():
     L = 150
     cores = os.cpu_count() or 1
     if args.workload == "cfg2":
-        kw = dict(k=23, mink=11, hdist=1, ktrim_right=1, trim_pairs_evenly=1)
+        kw = {"ktrimr": dict(k=23, mink=11, hdist=1, ktrim_right=1, trim_pairs_evenly=1),
+              "ktriml": dict(k=23, mink=11, hdist=1, ktrim_left=1),
+              "kfilter": dict(k=23, hdist=1),
+              "kmask": dict(k=23, mink=11, hdist=1, ktrim_n=1)}[args.mode]
         _, rb, roff = read_fasta(os.path.join(ROOT, "tests", "golden", "adapters.fa"))
         paired, d_ref = True, None
     elif args.workload == "cfg4":
@@ -73,6 +78,11 @@ def main():
     outs = {k: torch.empty(n, dtype=torch.int32, device="cuda") for k in ("id0", "lo", "hi", "count")}
     outs["flags"] = torch.empty(n, dtype=torch.uint8, device="cuda")
     d_stats = torch.zeros(8, dtype=torch.int64, device="cuda")
+    want_mask = args.workload == "cfg2" and args.mode == "kmask"
+    if want_mask:
+        words = (L + 31) // 32
+        outs["mask_off"] = torch.arange(0, (n + 1) * words, words, dtype=torch.int64, device="cuda")
+        outs["maskbits"] = torch.zeros(n * words, dtype=torch.int32, device="cuda")
     from concurrent.futures import ThreadPoolExecutor
     pool = ThreadPoolExecutor(cores)
     tbo_tot, q_tot = np.zeros(2, np.int64), np.zeros(8, np.int64)
@@ -110,11 +120,15 @@ def main():
         hb = d_bases[: nr * L].cpu().numpy()
         ho = np.arange(0, (nr + 1) * L, L, dtype=np.int64)
         t0 = time.perf_counter()
-        want, st = ora.process(hb, ho, paired, threads=cores)
+        want, st = ora.process(hb, ho, paired, threads=cores, want_mask=want_mask)
         t_cpu += time.perf_counter() - t0
         for name in ("id0", "lo", "hi", "count", "flags"):
             got = outs[name][:nr].cpu().numpy()
             mism += int(np.count_nonzero(got != want.fields()[name]))
+            crc = zlib.crc32(got.tobytes(), crc)
+        if want_mask:
+            got = outs["maskbits"][: nr * words].cpu().numpy().view(np.uint32)
+            mism += int(np.count_nonzero(got != want.maskbits))
             crc = zlib.crc32(got.tobytes(), crc)
         for k_, v in st.as_dict().items():
             tot[k_] = tot.get(k_, 0) + v
@@ -184,6 +198,9 @@ def main():
         extra["qtrim"] = {"stats8": q_tot.tolist(), "counters_equal": d_qst.cpu().tolist() == q_tot.tolist(), "gpu_s": round(t_q, 3),
                           "oracle_s": round(t_q_cpu, 3), "command": "qtrim=rl trimq=10, synthetic qualities decaying from Q40 (torch generator seed 99)"}
         assert extra["qtrim"]["counters_equal"]
+    if args.workload == "cfg2" and args.mode != "ktrimr":
+        extra["mode"] = args.mode
+        extra["engine_flags"] = kw
     print(json.dumps({"workload": args.workload, "reads": 2 * args.pairs, "stored_kmers": stored, "mismatching_fields": mism, **extra,
                       "counters_equal": dev_tot == tot, "scaffold_counts_equal": bool(np.array_equal(ro, rg) and np.array_equal(bo, bg)),
                       "counters": tot, "crc32_of_results": crc, "gpu_s": round(t_gpu, 3), "oracle_s": round(t_cpu, 3),
