@@ -695,35 +695,52 @@ class BBDuk:
         want_mask = bool(self.cfg.ktrim_n)
         return self.index.process(bases, offsets, paired, want_mask=want_mask)
 
-    def process_native(self):
-        """FASTQ in / FASTQ out through the native feed (include/fastq_b200.h); ktrim / kfilter modes"""
-        from .fastq import FastqBatch, load_text
+    def process_native(self, block_bytes=None):
+        """FASTQ in / FASTQ out through the native feed (include/fastq_b200.h); ktrim / kfilter modes.
+        The input is streamed in blocks of `block_bytes` of text per file (default 256 MiB, BBDUK_B200_FEED_BLOCK overrides):
+        whole records only, the same number from both mate files; outputs are appended block by block, counters summed."""
+        import os
+
+        from ._abi import BBDukStats
+        from .fastq import FastqBatch, iter_fastq_blocks
         io = self.io
-        fb = FastqBatch(load_text(io["in1"]), load_text(io["in2"]) if io["in2"] else None)
         paired = bool(io["in2"] or io["interleaved"])
         per = 2 if paired else 1
-        bases, offsets = fb.arrays()
         want_tbo, want_q, want_e = bool(io["tbo"] and paired), self._wants_qtrim(), io["entropy"] >= 0
-        if want_tbo or want_q or want_e:
-            # one upload of the batch, the steps hand lo / hi / flags to each other on the device
-            quals = fb.quals() if (want_tbo or want_q) else None
-            out, st, t2, q8, e2 = self.index.process_chain(bases, quals, offsets, paired, tbo=self._tbo_cfg() if want_tbo else None,
-                                                           qtrim=self._qtrim_cfg() if want_q else None,
-                                                           entropy=self._entropy_cfg() if want_e else None)
-            self.tbo_stats = t2 if want_tbo else None
-            self.qtrim_stats = q8 if want_q else None
-            self.entropy_stats = e2 if want_e else None
-        else:
-            out, st = self.process_arrays(bases, offsets, paired)
-        self.stats = st
-        for removed, p1, p2 in ((False, io["out1"], io["out2"]), (True, io["outm1"], io["outm2"])):
-            if not p1:
-                continue
-            for path, sel in (((p1, 1), (p2, 2)) if p2 else ((p1, 0),)):
-                fb.format(per, out.lo, out.hi, out.flags, removed=removed, mate_sel=sel,
-                          trim_removed=bool(io["ottm"])).tofile(path)
+        block = int(block_bytes or os.environ.get("BBDUK_B200_FEED_BLOCK", 256 << 20))
+        total = BBDukStats()
+        sums = {"tbo": np.zeros(2, np.int64), "q": np.zeros(8, np.int64), "e": np.zeros(2, np.int64)}
+        routes = [(removed, path, sel) for removed, p1, p2 in ((False, io["out1"], io["out2"]), (True, io["outm1"], io["outm2"])) if p1
+                  for path, sel in (((p1, 1), (p2, 2)) if p2 else ((p1, 0),))]
+        files = {path: open(path, "wb") for _, path, _ in routes}
+        try:
+            for text1, text2 in iter_fastq_blocks(io["in1"], io["in2"] or None, block, unit=per):
+                fb = FastqBatch(text1, text2)
+                bases, offsets = fb.arrays()
+                if want_tbo or want_q or want_e:
+                    # one upload of the batch, the steps hand lo / hi / flags to each other on the device
+                    quals = fb.quals() if (want_tbo or want_q) else None
+                    out, st, t2, q8, e2 = self.index.process_chain(bases, quals, offsets, paired, tbo=self._tbo_cfg() if want_tbo else None,
+                                                                   qtrim=self._qtrim_cfg() if want_q else None,
+                                                                   entropy=self._entropy_cfg() if want_e else None)
+                    for key, v in (("tbo", t2), ("q", q8), ("e", e2)):
+                        if v is not None:
+                            sums[key] += np.asarray(v, np.int64)
+                else:
+                    out, st = self.process_arrays(bases, offsets, paired)
+                for name, _ in BBDukStats._fields_:
+                    setattr(total, name, getattr(total, name) + getattr(st, name))
+                for removed, path, sel in routes:
+                    fb.format(per, out.lo, out.hi, out.flags, removed=removed, mate_sel=sel, trim_removed=bool(io["ottm"])).tofile(files[path])
+        finally:
+            for f in files.values():
+                f.close()
+        self.tbo_stats = sums["tbo"] if want_tbo else None
+        self.qtrim_stats = sums["q"] if want_q else None
+        self.entropy_stats = sums["e"] if want_e else None
+        self.stats = total
         self._write_stats()
-        return st
+        return total
 
     def _tbo_cfg(self):
         io = self.io

@@ -19,6 +19,91 @@ def load_text(path) -> np.ndarray:
     return np.fromfile(path, np.uint8)
 
 
+class _BlockReader:
+    """a text file (plain or .gz) read in bounded blocks; the bytes of an incomplete last record are carried over"""
+
+    def __init__(self, path, block_bytes):
+        self.f = gzip.open(path, "rb") if str(path).endswith(".gz") else open(path, "rb")
+        self.block = int(block_bytes)
+        self.carry = np.zeros(0, np.uint8)
+        self.final = False
+
+    def fill(self):
+        """append one block to what is held; -> the held text"""
+        if not self.final:
+            new = np.frombuffer(self.f.read(self.block), np.uint8)
+            if new.size < self.block:
+                self.final = True  # a short read ends the file (gzip streams included: read() blocks until block or EOF)
+            self.carry = np.concatenate([self.carry, new]) if self.carry.size else new
+        return self.carry
+
+    def take(self, n_bytes):
+        self.carry = self.carry[n_bytes:]
+
+    def close(self):
+        self.f.close()
+
+
+def iter_fastq_blocks(path1, path2=None, block_bytes=256 << 20, unit=1, threads=0):
+    """Bounded streaming of one (single / interleaved: unit=2) or two (mates) FASTQ files: yields (text1, text2 or None)
+    slices that hold whole records only -- the same number in both files, a multiple of `unit` in a single file -- using
+    fastq_b200_index's final=0 / consumed contract. A file that ends inside a record, or mate files of different record
+    counts, raise ValueError."""
+    lib = _lib.load()
+    threads = threads or min(32, os.cpu_count() or 1)
+    r1 = _BlockReader(path1, block_bytes)
+    r2 = _BlockReader(path2, block_bytes) if path2 else None
+
+    def complete(text, final, max_records=1 << 62):
+        """-> (complete records, at most max_records; the bytes they cover)"""
+        got, used = C.c_int64(), C.c_int64()
+        if text.size == 0:
+            return 0, 0
+        text = np.ascontiguousarray(text)
+        if lib.fastq_b200_index(text.ctypes.data, text.size, int(final), max_records, 1, 0, None, C.byref(got), C.byref(used), threads):
+            raise ValueError("malformed FASTQ")
+        n = int(got.value)
+        if n == 0:
+            return 0, 0
+        rec = np.zeros(4 * n, np.int64)  # the count-only call does not report the bytes covered
+        if lib.fastq_b200_index(text.ctypes.data, text.size, int(final), n, 1, 0, rec.ctypes.data, C.byref(got), C.byref(used), threads) \
+                or got.value != n:
+            raise ValueError("malformed FASTQ")
+        return n, int(used.value)
+
+    try:
+        while True:
+            t1 = r1.fill()
+            t2 = r2.fill() if r2 else None
+            n1, u1 = complete(t1, r1.final)
+            if r2:
+                n2, u2 = complete(t2, r2.final)
+                n = min(n1, n2)
+                if n < n1:
+                    _, u1 = complete(t1, r1.final, n)
+                if n < n2:
+                    _, u2 = complete(t2, r2.final, n)
+            else:
+                n = n1 if r1.final else n1 - n1 % unit
+                if n < n1:
+                    _, u1 = complete(t1, r1.final, n)
+            if n > 0:
+                yield t1[:u1], (t2[:u2] if r2 else None)
+                r1.take(u1)
+                if r2:
+                    r2.take(u2)
+            done = r1.final and (r2 is None or r2.final)
+            if done:
+                rest = [r.carry for r in (r1, r2) if r is not None]
+                if any(np.any((x != 10) & (x != 13)) for x in rest):  # anything but line ends left over
+                    raise ValueError("FASTQ input ends inside a record, or the mate files hold different numbers of records")
+                return
+    finally:
+        r1.close()
+        if r2:
+            r2.close()
+
+
 class FastqBatch:
     """records of one (single/interleaved) or two (mates) FASTQ texts, indexed natively"""
 

@@ -96,3 +96,54 @@ def test_malformed_and_empty():
         FastqBatch(np.frombuffer(b"r\nACGT\n+\nIIII\n", np.uint8))  # no '@'
     with pytest.raises(ValueError):
         FastqBatch(np.frombuffer(b"@r\nACGT\n-\nIIII\n", np.uint8))  # no '+'
+
+
+@pytest.mark.parametrize("block,gz,final_nl", [(997, False, True), (4096, True, False), (50, False, False), (1 << 20, False, True)])
+def test_bounded_streaming_of_mate_files(tmp_path, block, gz, final_nl):
+    """iter_fastq_blocks: whole records only, the same number from both files whatever their byte sizes, nothing lost"""
+    import gzip
+
+    from bbtools_b200.fastq import iter_fastq_blocks
+    t1, n1, s1, q1 = make_fastq(1200, 11, final_newline=final_nl)
+    t2, n2, s2, q2 = make_fastq(1200, 12, crlf=True, final_newline=final_nl, max_len=40)  # much shorter records
+    p1, p2 = tmp_path / ("a.fq.gz" if gz else "a.fq"), tmp_path / "b.fq"
+    with (gzip.open(p1, "wb") if gz else open(p1, "wb")) as f:
+        f.write(t1.tobytes())
+    with open(p2, "wb") as f:
+        f.write(t2.tobytes())
+    seqs = []
+    got1, got2 = [], []
+    for x1, x2 in iter_fastq_blocks(str(p1), str(p2), block_bytes=block):
+        fb = FastqBatch(x1, x2)
+        assert fb.n_reads > 0 and fb.n_reads % 2 == 0
+        b, off = fb.arrays()
+        seqs += [b[off[i]:off[i + 1]].tobytes() for i in range(fb.n_reads)]
+        got1.append(x1.tobytes())
+        got2.append(x2.tobytes())
+    assert seqs[0::2] == s1 and seqs[1::2] == s2
+    assert b"".join(got1) == t1.tobytes() and b"".join(got2) == t2.tobytes()
+    # single interleaved file: blocks hold whole pairs
+    n_tot = 0
+    for x1, x2 in iter_fastq_blocks(str(p2), None, block_bytes=block, unit=2):
+        assert x2 is None
+        n = FastqBatch(x1).n_reads
+        assert n % 2 == 0
+        n_tot += n
+    assert n_tot == 1200
+
+
+def test_bounded_streaming_reports_truncated_and_unequal_inputs(tmp_path):
+    from bbtools_b200.fastq import iter_fastq_blocks
+    t1, *_ = make_fastq(300, 21)
+    t2, *_ = make_fastq(299, 22)
+    p1, p2, p3 = tmp_path / "a.fq", tmp_path / "b.fq", tmp_path / "c.fq"
+    open(p1, "wb").write(t1.tobytes())
+    open(p2, "wb").write(t2.tobytes())
+    open(p3, "wb").write(t1.tobytes()[:-200] if t1.tobytes()[-201:-200] != b"\n" else t1.tobytes()[:-199])
+    with pytest.raises(ValueError):
+        list(iter_fastq_blocks(str(p1), str(p2), block_bytes=2000))  # 300 vs 299 records
+    with pytest.raises(ValueError):
+        list(iter_fastq_blocks(str(p3), None, block_bytes=2000))  # ends inside a record
+    assert list(iter_fastq_blocks(str(tmp_path / "a.fq"), None, block_bytes=10 ** 9))[0][0].size == t1.size
+    open(tmp_path / "e.fq", "wb").close()
+    assert list(iter_fastq_blocks(str(tmp_path / "e.fq"), None, block_bytes=100)) == []

@@ -233,3 +233,33 @@ def test_bbduk_tool_entropy_mask_and_trim(tmp_path, flag, mode):
         exp[1 if rem else 0].append(b"@r%d\n" % i + bytes(s[a:b]) + b"\n+\n" + bytes(q[a:b]) + b"\n")
     assert open(o1, "rb").read() == b"".join(exp[0])
     assert (open(m1, "rb").read() if os.path.exists(m1) else b"") == b"".join(exp[1])
+
+
+def test_bbduk_tool_streams_the_input_in_bounded_blocks(tmp_path, monkeypatch):
+    """the native feed with blocks far smaller than the files (one gzipped): the same outputs, counters and stats file as
+    the plain-Python feed that holds everything at once; the k-mer block followed by tbo + quality trimming"""
+    import gzip
+
+    from bbtools_b200.bbduk import BBDuk
+    bases, offsets = synth.paired_adapter_reads(6000, seed=43)
+    r1, r2 = tmp_path / "r1.fq.gz", tmp_path / "r2.fq"
+    write_fastq(tmp_path / "r1.fq", bases, offsets, 0, 2, b"1:N:0 a longer header so that the two files drift apart")
+    write_fastq(r2, bases, offsets, 1, 2, b"2")
+    with gzip.open(r1, "wb") as f:
+        f.write(open(tmp_path / "r1.fq", "rb").read())
+    for extra in ([], ["tbo", "qtrim=rl", "trimq=10", "minlen=30"]):
+        common = [f"in={r1}", f"in2={r2}", f"ref={GOLDEN}/adapters.fa", "ktrim=r", "k=23", "mink=11", "hdist=1", "tpe"] + extra
+        outs = {}
+        for mode in ("native", "python"):
+            o1, o2, m1, m2 = (tmp_path / f"{mode}_{x}.fq" for x in ("o1", "o2", "m1", "m2"))
+            tool = BBDuk(common + [f"out={o1}", f"out2={o2}", f"outm={m1}", f"outm2={m2}", f"stats={tmp_path}/{mode}.stats"])
+            if mode == "native":
+                monkeypatch.setenv("BBDUK_B200_FEED_BLOCK", "50000")  # ~40 blocks
+            else:
+                monkeypatch.delenv("BBDUK_B200_FEED_BLOCK", raising=False)
+            st = tool.process(native=(mode == "native"))
+            outs[mode] = tuple(open(p, "rb").read() for p in (o1, o2, m1, m2)) + (open(f"{tmp_path}/{mode}.stats").read(), st.as_dict(),
+                                                                                   None if tool.tbo_stats is None else list(tool.tbo_stats),
+                                                                                   None if tool.qtrim_stats is None else list(tool.qtrim_stats))
+        assert outs["native"] == outs["python"], extra
+        assert len(outs["native"][0]) > 100000 and len(outs["native"][2]) > 0
