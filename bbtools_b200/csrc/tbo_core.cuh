@@ -345,6 +345,7 @@ TBO_HD CapLine cap_line(float a, float b);
 TBO_HD CapLine ratio_cap_line(float ratio, float offset) { return cap_line(ratio, offset < 0.0f ? -offset : 0.0f); }
 TBO_HD CapLine cap_line(float a, float b) {
     CapLine c;
+    if (a > 2.0f) a = 2.0f;  // a count never exceeds ov, so a slope above 1 already admits everything (and a_fx * ov stays in range)
     c.a_fx = (int)(a * 1.0527f * 65536.0f) + 2;
     c.b_int = (int)(b * 1.0527f) + 3;
     return c;

@@ -81,7 +81,7 @@ def test_ratio_cap_line_admits_every_count_that_can_lower_the_best_ratio(host):
     """findBestRatio's screen: a count c >= 1 only matters if (T[c] + offset) / ov < bestRatio0"""
     host.tbo_host_check_ratio_cap_line.argtypes = [C.c_float, C.c_float]
     rng = np.random.default_rng(2)
-    for ratio in [0.1001, 0.0501, 0.1, 0.05, 1e-4, 0.0135, 0.3] + list(rng.random(100) * 0.2):
+    for ratio in [0.1001, 0.0501, 0.1, 0.05, 1e-4, 0.0135, 0.3, 0.45, 0.9, 1.5, 40.0] + list(rng.random(100) * 0.2):
         for offset in (0.4, 0.5, 0.0, 0.55, -0.3):
             assert host.tbo_host_check_ratio_cap_line(float(ratio), offset) == 0, (ratio, offset)
 
