@@ -2,7 +2,14 @@
 """Stress of the host build of bbtools_b200/csrc/tbo_core.cuh (tests/tbo_core_host.cpp) against the tbo oracle on CPU:
 tandem repeats, internal duplications, mismatch rates straddling maxRatio, N, and (odd seeds) random maxRatio / margin /
 offset / minSecondRatio.  python tools/stress_tbo_core.py FIRST_SEED LAST_SEED   (4000 pairs x 2 parameter sets per seed)"""
-import os; ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, os.path.join(ROOT, 'tests')); sys.path.insert(0, ROOT)
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+sys.path.insert(0, ROOT)
 import test_tbo_core_cpu as t
 from oracle import tbo as otbo
 host = t.host.__wrapped__()
