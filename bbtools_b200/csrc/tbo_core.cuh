@@ -461,9 +461,9 @@ TBO_HD void build_cands(const Ctx<S> &c, int alen, int blen, int i_top, int i_bo
         for (int w = imax(q.a_lo, 0) >> 5; w <= (q.a_hi >> 5) && q.a_hi >= q.a_lo; w++) q.A[w * S] = range_bits(w, q.a_lo, q.a_hi);
         for (int w = q.b_lo >> 5; w <= (q.b_hi >> 5) && q.b_hi >= q.b_lo; w++) q.B[w * S] = range_bits(w, q.b_lo, q.b_hi);
     } else if (!any_lane(cap > TBO_CAP_NW1)) {  // one window width per warp (a wider window than a lane needs is still a valid screen)
-        // The screen never needs the N planes: the packer codes an N as A, and with that reading a position counts as a
-        // mismatch at most as often as by the reference's N rules (N against a base: always bad there, bad here unless the
-        // base is A; N against N: bad in neither) -- a lower bound is all the screen promises.
+        // The screen never needs the N planes: an N reads as A in both mates (pack_pair), and with that reading a position
+        // counts as a mismatch at most as often as by the reference's N rules (N against a base: always bad there, bad here
+        // unless the base is A; N against N: bad in neither) -- a lower bound is all the screen promises.
         // 32 bases already reject a chance alignment (24 expected mismatches) with probability > 0.9 at this cap; the few
         // that slip through cost one exact count each, less than a second window on every alignment
         scan_side<false, S, 1>(c.ah, c.al, c.an, c.bh, c.bl, c.bn, alen, blen, q.a_lo, q.a_hi, cap, cl, ca, q.A);
@@ -682,7 +682,17 @@ TBO_HD uint32_t pack_pair(const uint8_t *a, int alen, const uint8_t *b0, int ble
     nw = pack_raw<GENERAL, S>(b0, blen, th, tl, tn, W, u0, bad, n_any);
     finish_reverse<S>(th, bh, blen, u0, nw, W, true);
     finish_reverse<S>(tl, bl, blen, u0, nw, W, true);
-    if (GENERAL) finish_reverse<S>(tn, bn, blen, u0, nw, W, false);
+    if (GENERAL) {
+        finish_reverse<S>(tn, bn, blen, u0, nw, W, false);
+        // An N of r2' must read as A like an N of r1 (the packer's N -> A was complemented to T above): the screen counts
+        // code differences without the N planes, and N against N is no mismatch for the reference. (The exact counts mask
+        // both code planes with the N planes, so nothing else sees these bits.)
+        for (int w = 0; w < W; w++) {
+            const uint32_t keep = ~bn[w * S];
+            bh[w * S] &= keep;
+            bl[w * S] &= keep;
+        }
+    }
     c.ah = ah;
     c.al = al;
     c.an = an;

@@ -208,3 +208,28 @@ def test_borderline_mismatch_rates_and_repeats_match_the_oracle(host):
         for g, w in zip(got[:4], want):
             assert np.array_equal(g, w)
         assert 200 < want[3][0] < 5000  # some pairs trimmed, some not
+
+
+def test_coincident_ns_do_not_count_against_the_screen(host):
+    """N against N is no mismatch for the reference; the screen reads an N as A in BOTH mates (r2' included), so a true
+    overlap full of coincident Ns must survive it"""
+    rng = np.random.default_rng(5)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    seqs = []
+    for i in range(400):
+        ins = int(rng.integers(60, 140))
+        frag = acgt[rng.integers(0, 4, ins)].copy()
+        frag[rng.random(ins) < (0.05 + 0.3 * rng.random())] = ord("N")  # the same fragment positions are N in both mates
+        r1 = np.concatenate([frag, acgt[rng.integers(0, 4, 200)]])[:150].copy()
+        r2 = np.concatenate([COMP[frag[::-1]], acgt[rng.integers(0, 4, 200)]])[:150].copy()
+        seqs += [r1, r2]
+    bases = np.concatenate(seqs).astype(np.uint8)
+    offsets = np.arange(0, 150 * len(seqs) + 1, 150, dtype=np.int64)
+    L = np.full(len(seqs), 150, np.int32)
+    z, f = np.zeros(len(L), np.int32), np.zeros(len(L), np.uint8)
+    for p in (otbo.default_params(True), otbo.default_params(False)):
+        want = otbo.process(bases, None, offsets, z, L, f, p)
+        got = run_host(host, bases, offsets, z, L, f, p)
+        for g, w in zip(got[:4], want):
+            assert np.array_equal(g, w)
+        assert want[3][0] > 100

@@ -109,3 +109,36 @@ def test_device_entry_point():
     torch.cuda.synchronize()
     assert np.array_equal(d_hi.cpu().numpy(), whi)
     assert d_st.cpu().tolist() == list(wst)
+
+
+@pytest.mark.parametrize("strict", [True, False])
+def test_coincident_ns_and_borderline_mismatch_rates(strict):
+    """true overlaps full of Ns at the SAME fragment positions in both mates (N against N is no mismatch, the screen must not
+    count it), mismatch rates straddling maxRatio, tandem repeats"""
+    rng = np.random.default_rng(5)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    comp, _ = otbo.tables()
+    seqs = []
+    for i in range(3000):
+        n1, n2 = (int(x) for x in rng.integers(60, 260, 2))
+        ins = int(rng.integers(20, n1 + n2))
+        if i % 4 == 0:
+            unit = acgt[rng.integers(0, 4, int(rng.integers(1, 9)))]
+            frag = np.tile(unit, ins // len(unit) + 1)[:ins].copy()
+        else:
+            frag = acgt[rng.integers(0, 4, ins)].copy()
+        if i % 3 == 0:
+            frag[rng.random(ins) < (0.05 + 0.3 * rng.random())] = ord("N")
+        r1 = np.concatenate([frag, acgt[rng.integers(0, 4, 300)]])[:n1].copy()
+        r2 = np.concatenate([comp[frag[::-1]], acgt[rng.integers(0, 4, 300)]])[:n2].copy()
+        rate = rng.random() * 0.2
+        for r in (r1, r2):
+            hit = rng.random(len(r)) < rate / 2
+            r[hit] = acgt[rng.integers(0, 4, int(hit.sum()))]
+        seqs += [r1, r2]
+    bases = np.concatenate(seqs).astype(np.uint8)
+    offsets = np.zeros(len(seqs) + 1, np.int64)
+    np.cumsum([len(x) for x in seqs], out=offsets[1:])
+    L = np.diff(offsets).astype(np.int32)
+    st = check(engine(), bases, None, offsets, np.zeros(len(L), np.int32), L, np.zeros(len(L), np.uint8), strict)
+    assert st[0] > 500

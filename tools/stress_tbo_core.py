@@ -31,6 +31,9 @@ def gen(seed, npairs):
             if len(frag) < ins: frag = np.concatenate([frag, acgt[rng.integers(0,4,ins-len(frag))]])
         else:
             frag = acgt[rng.integers(0, 4, ins)]
+        if i % 7 == 3:  # the same fragment positions are N in both mates
+            frag = frag.copy()
+            frag[rng.random(len(frag)) < 0.05 + 0.3 * rng.random()] = ord('N')
         r1 = np.concatenate([frag, acgt[rng.integers(0, 4, 400)]])[:n1].copy()
         r2 = np.concatenate([COMP[frag[::-1]], acgt[rng.integers(0, 4, 400)]])[:n2].copy()
         rate = rng.random() * 0.25
