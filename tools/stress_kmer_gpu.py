@@ -28,6 +28,34 @@ CONFIGS = [
 ALPHABETS = [b"ACGT", b"ACGTN", b"ACGTNNNN", b"ACGTNacgtnRYKMUu", b"ACGTacgt"]
 
 
+def adapter_concatenations(rng, rb, roff, n_reads, alpha):
+    """reads made of adapter sequences of either strand glued together (every window a candidate, most of them hits), with
+    a few point changes from `alpha`: the worst case for the candidate queues of the tuned kernel"""
+    comp = np.arange(256, dtype=np.uint8)
+    for x, y in zip(b"ACGTacgt", b"TGCAtgca"):
+        comp[x] = y
+    al = np.frombuffer(alpha, np.uint8)
+    n_ref = len(roff) - 1
+    seqs = []
+    for _ in range(n_reads):
+        want = int(rng.integers(0, 301))
+        parts, have = [], 0
+        while have < want:
+            a = int(rng.integers(0, n_ref))
+            frag = rb[roff[a]:roff[a + 1]]
+            if rng.random() < 0.5:
+                frag = comp[frag[::-1]]
+            parts.append(frag)
+            have += len(frag)
+        s = (np.concatenate(parts)[:want] if parts else np.zeros(0, np.uint8)).copy()
+        hit = rng.random(len(s)) < rng.choice([0.0, 0.01, 0.04])
+        s[hit] = al[rng.integers(0, len(al), int(hit.sum()))]
+        seqs.append(s)
+    off = np.zeros(n_reads + 1, np.int64)
+    np.cumsum([len(x) for x in seqs], out=off[1:])
+    return (np.concatenate(seqs) if seqs else np.zeros(0, np.uint8)).astype(np.uint8), off
+
+
 def main():
     from test_parity_gpu import assert_same, check_scaffold_counts
 
@@ -51,7 +79,10 @@ def main():
             alpha = ALPHABETS[int(rng.integers(0, len(ALPHABETS)))]
             a = int(rng.integers(0, n_ref))
             adapter = rb[roff[a]:roff[a + 1]]
-            b, off = synth.ragged_reads(n_reads, seed=1000 * seed + ci, min_len=0, max_len=300, alphabet=alpha, adapter=adapter)
+            if (seed + ci) % 3 == 2:
+                b, off = adapter_concatenations(rng, rb, roff, n_reads // 4, alpha)
+            else:
+                b, off = synth.ragged_reads(n_reads, seed=1000 * seed + ci, min_len=0, max_len=300, alphabet=alpha, adapter=adapter)
             paired = bool(rng.integers(0, 2))
             want_mask = bool(kw.get("ktrim_n"))
             assert_same(o, g, b, off, paired, want_mask=want_mask, threads=16)
