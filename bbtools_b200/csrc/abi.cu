@@ -104,6 +104,12 @@ struct bbduk_handle {
     uint8_t *chain_bases2 = nullptr, *chain_quals2 = nullptr;
     uint32_t *chain_off2 = nullptr;
     int64_t chain_cap_bases2 = 0, chain_cap_quals2 = 0, chain_cap_off2 = 0;
+    // packed upload of the chain (chunks made of A C G T N only): pinned host staging + device streams per input slot
+    uint32_t *chain_hF[2] = {nullptr, nullptr}, *chain_dF[2] = {nullptr, nullptr};
+    uint16_t *chain_hD[2] = {nullptr, nullptr}, *chain_dD[2] = {nullptr, nullptr};
+    uint32_t *chain_hoff[2] = {nullptr, nullptr};
+    int64_t chain_cap_hg[2] = {0, 0}, chain_cap_dg[2] = {0, 0}, chain_cap_hoff[2] = {0, 0};
+    int64_t *chain_dst = nullptr;
     cudaStream_t chain_copy = nullptr;
     cudaEvent_t chain_in[2] = {nullptr, nullptr}, chain_free[2] = {nullptr, nullptr};
     std::mutex tbo_mu;
@@ -549,7 +555,8 @@ int bbduk_b200_table_commit(bbduk_handle *h) {
 // max_len_known > 0: the caller knows the longest read of the batch (the chain measures every chunk on the host);
 // 0: the handle-wide hint, else one reduction kernel + a stream synchronisation
 static int process_device_impl(bbduk_handle *h, const uint8_t *d_bases, const uint32_t *d_offsets, int64_t n_reads,
-                               int32_t paired, const bbduk_out *d_out, bbduk_stats *d_stats, void *stream, int max_len_known) {
+                               int32_t paired, const bbduk_out *d_out, bbduk_stats *d_stats, void *stream, int max_len_known,
+                               const uint32_t *pk_F = nullptr, const uint16_t *pk_D = nullptr) {
     if (!h) return set_err(nullptr, "handle is NULL");
     if (!h->finalized) return set_err(h, "process before finalize");
     if (n_reads < 0 || (paired && (n_reads & 1))) return set_err(h, "bad n_reads");
@@ -598,8 +605,14 @@ static int process_device_impl(bbduk_handle *h, const uint8_t *d_bases, const ui
         }
         ds = DirectScratch{h->dev_first64, h->dev_lastpos, h->dev_sbits};
     }
+    if (pk_F) {  // the tuned kernels read the 2-bit stream directly when no tile can be handed off; else the ASCII copy serves
+        const BBTable tv = h->table.view();
+        const bool ok = pk_D && (int)mx <= FAST_MAX_READ_LEN && (plan_fast2(h->p, tv, (int)mx).usable || plan_fast(h->p, tv, (int)mx).usable) &&
+                        packed_ok(h->p, tv) && !(d_out->maskbits);
+        if (!ok) pk_F = nullptr, pk_D = nullptr;
+    }
     return run_batch(h, d_bases, d_offsets, n_reads, n_bases, paired, *d_out, d_stats, (int)mx, h->dev_handoff,
-                     h->dev_handoff_n, ds, st);
+                     h->dev_handoff_n, ds, st, pk_F, pk_D);
 }
 
 int bbduk_b200_process_device(bbduk_handle *h, const uint8_t *d_bases, const uint32_t *d_offsets, int64_t n_reads,
@@ -609,6 +622,22 @@ int bbduk_b200_process_device(bbduk_handle *h, const uint8_t *d_bases, const uin
 
 // bases != NULL: ASCII input (bbduk_b200_process). Otherwise pre_F / pre_D: the caller's own 2-bit stream + defined bits over the
 // concatenated bases (bbduk_b200_process_packed); a chunk then starts at the 16-base group its first read begins in.
+// the handle's host worker pool (caller holds h->pool_mu)
+static void ensure_pool(bbduk_handle *h) {
+    if (h->pool) return;
+    // one process per GPU: share the host cores among the ranks of this node (torchrun exports the count)
+    int share = 1;
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) share = std::max(1, atoi(e));
+    if (const char *e = getenv("BBDUK_B200_HOST_THREADS")) share = -atoi(e);
+    const int hc = (int)std::thread::hardware_concurrency();
+    h->pool = new HostPool(share < 0 ? std::max(1, -share) : std::max(1, std::min(32, hc / share)));
+    // few packing workers per GPU (many ranks on one host): lean on PCIe more
+    if (!h->ascii_every_set) h->ascii_every = h->pool->size() >= 12 ? 3 : h->pool->size() >= 6 ? 2 : 1;
+    // four workers or fewer per GPU (eight ranks on a 32-core host): packing loses to plain DMA whatever the
+    // share (tools/e2e_mix_sweep.py, profiles/r02p_e2e_mix_sweep_8gpu.jsonl), so the share stays fixed
+    if (!h->ascii_every_set && h->pool->size() < 6) h->ascii_every_set = true;
+}
+
 static int process_host_impl(bbduk_handle *h, const uint8_t *bases, const uint32_t *pre_F, const uint16_t *pre_D, const int64_t *offsets,
                              int64_t n_reads, int32_t paired, const bbduk_out *out, bbduk_stats *stats) {
     if (!h) return set_err(nullptr, "handle is NULL");
@@ -673,19 +702,7 @@ static int process_host_impl(bbduk_handle *h, const uint8_t *bases, const uint32
         int max_len = 0;
         {
             std::lock_guard<std::mutex> pg(h->pool_mu);
-            if (!h->pool) {
-                // one process per GPU: share the host cores among the ranks of this node (torchrun exports the count)
-                int share = 1;
-                if (const char *e = getenv("LOCAL_WORLD_SIZE")) share = std::max(1, atoi(e));
-                if (const char *e = getenv("BBDUK_B200_HOST_THREADS")) share = -atoi(e);
-                const int hc = (int)std::thread::hardware_concurrency();
-                h->pool = new HostPool(share < 0 ? std::max(1, -share) : std::max(1, std::min(32, hc / share)));
-                // few packing workers per GPU (many ranks on one host): lean on PCIe more
-                if (!h->ascii_every_set) h->ascii_every = h->pool->size() >= 12 ? 3 : h->pool->size() >= 6 ? 2 : 1;
-                // four workers or fewer per GPU (eight ranks on a 32-core host): packing loses to plain DMA whatever the
-                // share (tools/e2e_mix_sweep.py, profiles/r02p_e2e_mix_sweep_8gpu.jsonl), so the share stays fixed
-                if (!h->ascii_every_set && h->pool->size() < 6) h->ascii_every_set = true;
-            }
+            ensure_pool(h);
             std::atomic<int> mx{0};
             std::atomic<bool> bad{false};
             const int64_t *osrc = offsets + r0;
@@ -1267,20 +1284,20 @@ int bbduk_b200_process_chain(bbduk_handle *h, const bbduk_chain_cfg *cfg, const 
     CKH(cudaSetDevice(h->device));
     std::lock_guard<std::mutex> g(h->tbo_mu);
     cudaStream_t st = nullptr;  // synchronous entry point: the legacy default stream
-    int64_t *d_st = nullptr;    // [0..7] k-mer block, [8..9] tbo, [10..17] qtrim, [18..19] entropy
-    CKH(cudaMalloc(&d_st, 20 * sizeof(int64_t)));
+    if (!h->chain_dst) CKH(cudaMalloc(&h->chain_dst, 20 * sizeof(int64_t)));  // kept with the handle: cudaFree would synchronise every call
+    int64_t *d_st = h->chain_dst;  // [0..7] k-mer block, [8..9] tbo, [10..17] qtrim, [18..19] entropy
     CKH(cudaMemset(d_st, 0, 20 * sizeof(int64_t)));
     int rc = 0;
     const int per = paired ? 2 : 1;
-    // chunks: <= 2 * CHUNK_READS reads and <= CHUNK_BYTES bases each (offsets stay 32-bit on the device)
+    // chunks: <= CHUNK_READS / 2 reads and <= CHUNK_BYTES bases each (offsets stay 32-bit on the device); small, so that the
+    // host packing of chunk i+1, the upload of chunk i and the kernels of chunk i-1 overlap already in a call of a few chunks
     std::vector<int64_t> cut{0};
     while (cut.back() < n_reads) {
         const int64_t r0 = cut.back();
-        int64_t r1 = std::min(n_reads, r0 + (CHUNK_READS << 1));
+        int64_t r1 = std::min(n_reads, r0 + (CHUNK_READS >> 1));
         while (r1 > r0 + per && offsets[r1] - offsets[r0] > CHUNK_BYTES) r1 = r0 + std::max<int64_t>(per, ((r1 - r0) / 2 / per) * per);
         const int64_t nb = offsets[r1] - offsets[r0];
         if (nb < 0 || nb >= (1ll << 32) - 64) {
-            cudaFree(d_st);
             return set_err(h, "a read (pair) exceeds 4 GiB (or offsets decrease)");
         }
         cut.push_back(r1);
@@ -1309,26 +1326,91 @@ int bbduk_b200_process_chain(bbduk_handle *h, const bbduk_chain_cfg *cfg, const 
     uint32_t **s_off[2] = {&tb.d_off, &h->chain_off2};
     int64_t *c_bases[2] = {&tb.cap_bases, &h->chain_cap_bases2}, *c_quals[2] = {&tb.cap_quals, &h->chain_cap_quals2},
             *c_off[2] = {&tb.cap_off, &h->chain_cap_off2};
-    std::vector<uint32_t> off32[2];
     int max_len_of[2] = {0, 0};
+    bool packed_of[2] = {false, false};
+    // Chunks made of A C G T N only cross PCIe as 2-bit codes + defined bits (0.375 B per base instead of 1), packed by the
+    // host workers, and are spelled out again on the device for the steps that read ASCII; the first chunk that holds
+    // anything else (lower case, IUPAC, U) ends the packing for the rest of the call.
+    bool try_pack = h->pack_host;
+    {
+        std::lock_guard<std::mutex> pg(h->pool_mu);
+        ensure_pool(h);
+    }
+    auto need_host = [&](void **p, int64_t *cap, int64_t bytes) -> int {
+        if (bytes <= *cap) return 0;
+        if (*p) cudaFreeHost(*p);
+        *p = nullptr;
+        *cap = bytes + bytes / 8 + 4096;
+        return cudaMallocHost(p, (size_t)*cap) == cudaSuccess ? 0 : 1;
+    };
     auto stage = [&](int ci) {  // upload chunk ci into slot ci & 1 on the copy stream
         const int sl = ci & 1;
         const int64_t r0 = cut[ci], nr = cut[ci + 1] - r0, nb = offsets[cut[ci + 1]] - offsets[r0];
+        const int64_t groups = (nb + 15) / 16;
         if (need((void **)s_bases[sl], c_bases[sl], nb + 64) || (need_q && need((void **)s_quals[sl], c_quals[sl], nb + 64)) ||
-            need((void **)s_off[sl], c_off[sl], 4 * (nr + 1))) {
-            rc = set_err(h, "chain: device allocation failed");
+            need((void **)s_off[sl], c_off[sl], 4 * (nr + 1)) || need_host((void **)&h->chain_hoff[sl], &h->chain_cap_hoff[sl], 4 * (nr + 1))) {
+            rc = set_err(h, "chain: allocation failed");
             return;
         }
+        // every ascii_every-th chunk crosses as ASCII (no CPU work): packing is bound by the host's memory bandwidth, the
+        // ASCII chunks by PCIe, and both run at the same time
+        bool packed = try_pack && nb >= (1 << 16) && !(h->ascii_every > 0 && n_chunks > 2 && (ci % h->ascii_every) == h->ascii_every - 1);
+        if (packed) {
+            int64_t cap_h = h->chain_cap_hg[sl], cap_h2 = h->chain_cap_hg[sl], cap_d = h->chain_cap_dg[sl], cap_d2 = h->chain_cap_dg[sl];
+            if (need_host((void **)&h->chain_hF[sl], &cap_h, 4 * (groups + 64)) || need_host((void **)&h->chain_hD[sl], &cap_h2, 4 * (groups + 64)) ||
+                need((void **)&h->chain_dF[sl], &cap_d, 4 * (groups + 64)) || need((void **)&h->chain_dD[sl], &cap_d2, 4 * (groups + 64))) {
+                rc = set_err(h, "chain: allocation failed");
+                return;
+            }
+            h->chain_cap_hg[sl] = std::min(cap_h, cap_h2);
+            h->chain_cap_dg[sl] = std::min(cap_d, cap_d2);
+        }
+        // the slot's host staging is free once chunk ci-2's uploads are done
+        if (ci >= 2) cudaEventSynchronize(h->chain_in[sl]);
+        std::atomic<int> mx{0};
+        std::atomic<bool> plain{true};
+        {
+            std::lock_guard<std::mutex> pg(h->pool_mu);
+            const uint8_t *src = bases + offsets[r0];
+            const int64_t *osrc = offsets + r0;
+            uint32_t *o32 = h->chain_hoff[sl], *hF = h->chain_hF[sl];
+            uint16_t *hD = h->chain_hD[sl];
+            h->pool->run([&, src, osrc, o32, hF, hD](int part, int n_parts) {
+                const int64_t i0 = (nr + 1) * part / n_parts, i1 = (nr + 1) * (part + 1) / n_parts;
+                int m = 0;
+                for (int64_t i = i0; i < i1; i++) {
+                    o32[i] = (uint32_t)(osrc[i] - osrc[0]);
+                    if (i < nr) m = std::max<int64_t>(m, std::min<int64_t>(osrc[i + 1] - osrc[i], 0x7FFFFFFF));
+                }
+                int cur = mx.load();
+                while (m > cur && !mx.compare_exchange_weak(cur, m)) {
+                }
+                if (packed) {
+                    const int64_t gb = (groups + 31) / 32;
+                    const int64_t g0 = std::min(groups, gb * part / n_parts * 32), g1 = std::min(groups, gb * (part + 1) / n_parts * 32);
+                    if (!pack_bases_range_plain(src, nb, g0, g1, hF, hD)) plain = false;
+                }
+            });
+        }
+        if (packed && !plain.load()) {
+            packed = false;
+            try_pack = false;
+        }
+        max_len_of[sl] = mx.load();
+        packed_of[sl] = packed;
         if (ci >= 2) CKC(cudaStreamWaitEvent(h->chain_copy, h->chain_free[sl], 0));  // chunk ci-2's kernels are done with the slot
-        CKC(cudaMemcpyAsync(*s_bases[sl], bases + offsets[r0], (size_t)nb, cudaMemcpyHostToDevice, h->chain_copy));
-        if (need_q) CKC(cudaMemcpyAsync(*s_quals[sl], quals + offsets[r0], (size_t)nb, cudaMemcpyHostToDevice, h->chain_copy));
-        int max_len = 0;
-        auto &o32 = off32[sl];  // pageable: the copy below returns once it is staged, so the vector can be reused two chunks on
-        o32.resize(nr + 1);
-        for (int64_t i = 0; i <= nr; i++) o32[i] = (uint32_t)(offsets[r0 + i] - offsets[r0]);
-        for (int64_t i = 0; i < nr; i++) max_len = std::max(max_len, (int)(o32[i + 1] - o32[i]));
-        max_len_of[sl] = max_len;
-        CKC(cudaMemcpyAsync(*s_off[sl], o32.data(), 4 * (size_t)(nr + 1), cudaMemcpyHostToDevice, h->chain_copy));
+        if (packed) {
+            CKC((h->h2d_bytes += 4 * groups, cudaMemcpyAsync(h->chain_dF[sl], h->chain_hF[sl], 4 * (size_t)groups, cudaMemcpyHostToDevice, h->chain_copy)));
+            CKC((h->h2d_bytes += 2 * groups, cudaMemcpyAsync(h->chain_dD[sl], h->chain_hD[sl], 2 * (size_t)groups, cudaMemcpyHostToDevice, h->chain_copy)));
+            if (!rc) {
+                unpack_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, h->chain_copy>>>(h->chain_dF[sl], h->chain_dD[sl], *s_bases[sl], groups);
+                h->launches += 1;
+            }
+        } else {
+            CKC((h->h2d_bytes += nb, cudaMemcpyAsync(*s_bases[sl], bases + offsets[r0], (size_t)nb, cudaMemcpyHostToDevice, h->chain_copy)));
+        }
+        if (need_q) CKC((h->h2d_bytes += nb, cudaMemcpyAsync(*s_quals[sl], quals + offsets[r0], (size_t)nb, cudaMemcpyHostToDevice, h->chain_copy)));
+        CKC((h->h2d_bytes += 4 * (nr + 1), cudaMemcpyAsync(*s_off[sl], h->chain_hoff[sl], 4 * (size_t)(nr + 1), cudaMemcpyHostToDevice, h->chain_copy)));
         CKC(cudaEventRecord(h->chain_in[sl], h->chain_copy));
     };
     if (!rc && n_chunks > 0) stage(0);
@@ -1352,7 +1434,9 @@ int bbduk_b200_process_chain(bbduk_handle *h, const bbduk_chain_cfg *cfg, const 
         dout.flags = tb.d_flags;
         dout.id0 = out->id0 ? tb.d_id0 : nullptr;
         dout.count = out->count ? tb.d_count : nullptr;
-        if (!rc) rc = process_device_impl(h, d_b, d_o, nr, paired, &dout, reinterpret_cast<bbduk_stats *>(d_st), st, std::max(max_len, 1));
+        if (!rc)
+            rc = process_device_impl(h, d_b, d_o, nr, paired, &dout, reinterpret_cast<bbduk_stats *>(d_st), st, std::max(max_len, 1),
+                                     packed_of[sl] ? h->chain_dF[sl] : nullptr, packed_of[sl] ? h->chain_dD[sl] : nullptr);
         if (!rc && cfg->do_tbo)
             rc = bbduk_b200_tbo_device(h, &cfg->tbo, d_b, quals ? d_q : nullptr, d_o, nr, max_len, tb.d_lo, tb.d_hi, tb.d_flags,
                                        tb.d_insert, d_st + 8, st);
@@ -1384,7 +1468,6 @@ int bbduk_b200_process_chain(bbduk_handle *h, const bbduk_chain_cfg *cfg, const 
                 for (int i = 0; i < 2; i++) entropy_stats2[i] += v[18 + i];
         }
     }
-    cudaFree(d_st);
     return rc;
 }
 
@@ -1433,6 +1516,14 @@ void bbduk_b200_destroy(bbduk_handle *h) {
     cudaFree(h->chain_bases2);
     cudaFree(h->chain_quals2);
     cudaFree(h->chain_off2);
+    cudaFree(h->chain_dst);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(h->chain_dF[i]);
+        cudaFree(h->chain_dD[i]);
+        if (h->chain_hF[i]) cudaFreeHost(h->chain_hF[i]);
+        if (h->chain_hD[i]) cudaFreeHost(h->chain_hD[i]);
+        if (h->chain_hoff[i]) cudaFreeHost(h->chain_hoff[i]);
+    }
     if (h->chain_copy) cudaStreamDestroy(h->chain_copy);
     for (int i = 0; i < 2; i++) {
         if (h->chain_in[i]) cudaEventDestroy(h->chain_in[i]);

@@ -197,6 +197,66 @@ void pack_bases_range(const uint8_t *bases, int64_t n, int64_t g0, int64_t g1, u
 
 void pack_bases(const uint8_t *bases, int64_t n, uint32_t *F, uint16_t *D) { pack_bases_range(bases, n, 0, (n + 15) / 16, F, D); }
 
+namespace {
+// every byte of b[i0, i1) is one of A C G T N (upper case): then F + D lose nothing (codes spell A C G T, undefined = N)
+bool plain_scalar(const uint8_t *b, int64_t i0, int64_t i1) {
+    for (int64_t i = i0; i < i1; i++) {
+        const uint8_t c = b[i];
+        if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == 'N')) return false;
+    }
+    return true;
+}
+#if defined(__x86_64__)
+__attribute__((target("avx512f,avx512bw"))) bool plain_avx512(const uint8_t *b, int64_t i0, int64_t i1) {
+    __mmask64 bad = 0;
+    int64_t i = i0;
+    const __m512i A = _mm512_set1_epi8('A'), Cc = _mm512_set1_epi8('C'), G = _mm512_set1_epi8('G'), T = _mm512_set1_epi8('T'),
+                  N = _mm512_set1_epi8('N');
+    for (; i + 64 <= i1; i += 64) {
+        const __m512i v = _mm512_loadu_si512(b + i);
+        const __mmask64 ok = _mm512_cmpeq_epi8_mask(v, A) | _mm512_cmpeq_epi8_mask(v, Cc) | _mm512_cmpeq_epi8_mask(v, G) |
+                             _mm512_cmpeq_epi8_mask(v, T) | _mm512_cmpeq_epi8_mask(v, N);
+        bad |= ~ok;
+    }
+    return bad == 0 && plain_scalar(b, i, i1);
+}
+__attribute__((target("avx2"))) bool plain_avx2(const uint8_t *b, int64_t i0, int64_t i1) {
+    __m256i all = _mm256_set1_epi8((char)0xFF);
+    int64_t i = i0;
+    const __m256i A = _mm256_set1_epi8('A'), Cc = _mm256_set1_epi8('C'), G = _mm256_set1_epi8('G'), T = _mm256_set1_epi8('T'),
+                  N = _mm256_set1_epi8('N');
+    for (; i + 32 <= i1; i += 32) {
+        const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(b + i));
+        const __m256i ok = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(v, A), _mm256_cmpeq_epi8(v, Cc)),
+                                           _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(v, G), _mm256_cmpeq_epi8(v, T)),
+                                                           _mm256_cmpeq_epi8(v, N)));
+        all = _mm256_and_si256(all, ok);
+    }
+    return _mm256_movemask_epi8(all) == -1 && plain_scalar(b, i, i1);
+}
+#endif
+bool plain_range(const uint8_t *b, int64_t i0, int64_t i1) {
+#if defined(__x86_64__)
+    static const bool have_512 = __builtin_cpu_supports("avx512bw") && !getenv("BBDUK_B200_NO_AVX512");
+    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    if (have_512) return plain_avx512(b, i0, i1);
+    if (have_avx2) return plain_avx2(b, i0, i1);
+#endif
+    return plain_scalar(b, i0, i1);
+}
+}  // namespace
+
+bool pack_bases_range_plain(const uint8_t *bases, int64_t n, int64_t g0, int64_t g1, uint32_t *F, uint16_t *D) {
+    // 64 KB of bases at a time: the check re-reads what the packer has just pulled into the cache
+    bool plain = true;
+    for (int64_t g = g0; g < g1; g += 4096) {
+        const int64_t ge = g + 4096 < g1 ? g + 4096 : g1;
+        pack_bases_range(bases, n, g, ge, F, D);
+        if (plain) plain = plain_range(bases, 16 * g, 16 * ge < n ? 16 * ge : n);
+    }
+    return plain;
+}
+
 HostPool::HostPool(int n_threads) {
     for (int i = 1; i < n_threads; i++) workers.emplace_back([this, i] { loop(i); });
 }

@@ -14,6 +14,9 @@
 void pack_bases(const uint8_t *bases, int64_t n, uint32_t *F, uint16_t *D);
 // groups [g0, g1) only (one worker's share)
 void pack_bases_range(const uint8_t *bases, int64_t n, int64_t g0, int64_t g1, uint32_t *F, uint16_t *D);
+// the same, and: is every byte of the range one of A C G T N (upper case)? Then the device can spell the bases out again
+// from F + D (undefined -> 'N') and nothing is lost for the steps that read ASCII (tbo, quality trimming, entropy).
+bool pack_bases_range_plain(const uint8_t *bases, int64_t n, int64_t g0, int64_t g1, uint32_t *F, uint16_t *D);
 
 // small persistent worker pool (the caller's thread takes part)
 class HostPool {
