@@ -80,6 +80,12 @@ def main():
         ecfg = g.entropy_cfg(cutoff=0.7)
         ge = g.entropy(b, off, True, got, ecfg)
         print("ok tbo qtrim entropy", list(gt), list(gq)[:2], list(ge), flush=True)
+        # the same steps through the chain entry (packed upload + unpack_kernel when the batch is plain A C G T N)
+        co, cst, ct2, cq8, ce2 = g.process_chain(b, q, off, True, tbo=g.tbo_cfg(), qtrim=g.qtrim_cfg(qtrim_left=1, qtrim_right=1, trimq=10.0),
+                                                  entropy=ecfg)
+        assert np.array_equal(co.lo, got.lo) and np.array_equal(co.hi, got.hi) and np.array_equal(co.flags, got.flags)
+        assert list(ct2) == list(gt) and list(cq8) == list(gq) and list(ce2) == list(ge)
+        print("ok chain", flush=True)
     if which in ("all", "kcount"):
         from bbtools_b200.kcount import KmerTableSetGPU
         from oracle.kcount import KCountOracle
