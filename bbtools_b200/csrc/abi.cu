@@ -46,7 +46,8 @@ struct Slot {
     uint32_t *h_F = nullptr, *d_F = nullptr;
     uint16_t *h_D = nullptr, *d_D = nullptr;
     uint32_t *h_off32 = nullptr;
-    int64_t cap_groups = 0, cap_hoff = 0;
+    uint64_t *h_exc = nullptr, *d_exc = nullptr;  // groups with an undefined base, (group << 16 | D): what travels instead of D
+    int64_t cap_groups = 0, cap_hoff = 0, cap_exc = 0;
     int64_t cap_bases = 0, cap_reads = 0, cap_maskwords = 0, cap_sbits = 0;
     std::mutex mu;
 };
@@ -80,6 +81,7 @@ struct bbduk_handle {
     double ascii_acc = 0.0;
     double pcie_gbs = 52.0;
     bool pack_host = true;  // BBDUK_B200_PACK_HOST=0 keeps the bases ASCII across PCIe
+    bool sparse_d = true;   // BBDUK_B200_SPARSE_D=0 uploads the defined bits as an array instead of all-ones + exceptions
     std::mutex err_mu;
     std::string err;
     // per-thread-stream scratch for process_device
@@ -146,6 +148,11 @@ __global__ void off64_to_32_kernel(const int64_t *__restrict__ off64, int64_t ba
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) off32[i] = (uint32_t)(off64[i] - base);
 }
+// defined bits on the device = all ones (a memset) + the listed exceptions
+__global__ void defined_exceptions_kernel(const uint64_t *__restrict__ exc, int64_t n, uint16_t *__restrict__ D) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) D[exc[i] >> 16] = (uint16_t)(exc[i] & 0xFFFFu);
+}
 // host-packed input for a mode the tuned kernels do not serve: spell the 2-bit stream out again (undefined -> 'N')
 __global__ void unpack_kernel(const uint32_t *__restrict__ F, const uint16_t *__restrict__ D, uint8_t *__restrict__ bases, int64_t groups) {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -199,6 +206,10 @@ void free_slot(Slot &s) {
     cudaFreeHost(s.h_F);
     cudaFreeHost(s.h_D);
     cudaFreeHost(s.h_off32);
+    cudaFree(s.d_exc);
+    cudaFreeHost(s.h_exc);
+    s.d_exc = s.h_exc = nullptr;
+    s.cap_exc = 0;
     s.d_F = s.h_F = s.h_off32 = nullptr;
     s.d_D = s.h_D = nullptr;
     s.cap_groups = s.cap_hoff = 0;
@@ -286,6 +297,12 @@ int ensure_packed(bbduk_handle *h, Slot &s, int64_t n_reads, int64_t n_bases) {
         CKH(cudaMalloc(&s.d_D, sizeof(uint16_t) * s.cap_groups));
         CKH(cudaHostAlloc(&s.h_F, sizeof(uint32_t) * s.cap_groups, cudaHostAllocDefault));
         CKH(cudaHostAlloc(&s.h_D, sizeof(uint16_t) * s.cap_groups, cudaHostAllocDefault));
+        cudaFree(s.d_exc);
+        cudaFreeHost(s.h_exc);
+        s.d_exc = s.h_exc = nullptr;
+        s.cap_exc = s.cap_groups / 16 + 64 * 64;  // more undefined groups than that: the array travels instead
+        CKH(cudaMalloc(&s.d_exc, sizeof(uint64_t) * s.cap_exc));
+        CKH(cudaHostAlloc(&s.h_exc, sizeof(uint64_t) * s.cap_exc, cudaHostAllocDefault));
     }
     if (n_reads + 1 > s.cap_hoff) {
         cudaFreeHost(s.h_off32);
@@ -430,6 +447,7 @@ int bbduk_b200_create(const bbduk_cfg *cfg, bbduk_handle **out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
     if (const char *e = getenv("BBDUK_B200_PACK_HOST")) h->pack_host = atoi(e) != 0;
+    if (const char *e = getenv("BBDUK_B200_SPARSE_D")) h->sparse_d = atoi(e) != 0;
     if (const char *e = getenv("BBDUK_B200_TRACE")) h->trace = atoi(e) != 0;
     if (const char *e = getenv("BBDUK_B200_ASCII_EVERY")) {
         h->ascii_every = std::max(0, atoi(e));
@@ -622,6 +640,41 @@ int bbduk_b200_process_device(bbduk_handle *h, const uint8_t *d_bases, const uin
 
 // bases != NULL: ASCII input (bbduk_b200_process). Otherwise pre_F / pre_D: the caller's own 2-bit stream + defined bits over the
 // concatenated bases (bbduk_b200_process_packed); a chunk then starts at the 16-base group its first read begins in.
+// Defined bits of a packed chunk onto the device. cnt != NULL: the workers listed the groups with an undefined base in their
+// regions of s.h_exc (R entries each); if none overflowed, the device array is a memset to all ones + those exceptions
+// (0.05 % undefined bases: 1 % of the groups, 8 bytes each, instead of 2 bytes for every group). Otherwise the array itself
+// travels: from `direct` (the caller's page-locked array) if given, else from s.h_D (if `fill` is given it is copied there
+// first -- a worker skipped its share because it expected the exception path).
+static int upload_defined(bbduk_handle *h, Slot &s, const int64_t *cnt, int n_parts, int64_t R, int64_t groups, const uint16_t *direct,
+                          const uint16_t *fill, cudaStream_t st) {
+    bool sparse = cnt != nullptr;
+    int64_t total = 0;
+    if (sparse)
+        for (int p = 0; p < n_parts; p++) {
+            if (cnt[p] < 0) sparse = false;
+            else total += cnt[p];
+        }
+    if (sparse) {
+        int64_t at = 0;
+        for (int p = 0; p < n_parts; p++) {
+            if (cnt[p] > 0 && at != (int64_t)p * R) memmove(s.h_exc + at, s.h_exc + (int64_t)p * R, sizeof(uint64_t) * (size_t)cnt[p]);
+            at += cnt[p];
+        }
+        CKH(cudaMemsetAsync(s.d_D, 0xFF, sizeof(uint16_t) * (size_t)groups, st));
+        if (total > 0) {
+            h->h2d_bytes += (int64_t)(sizeof(uint64_t) * total);
+            CKH(cudaMemcpyAsync(s.d_exc, s.h_exc, sizeof(uint64_t) * (size_t)total, cudaMemcpyHostToDevice, st));
+            defined_exceptions_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(s.d_exc, total, s.d_D);
+            h->launches += 1;
+        }
+        return 0;
+    }
+    if (!direct && fill && cnt) memcpy(s.h_D, fill, sizeof(uint16_t) * (size_t)groups);  // rare: dense undefined bases in a staged chunk
+    h->h2d_bytes += (int64_t)(sizeof(uint16_t) * groups);
+    CKH(cudaMemcpyAsync(s.d_D, direct ? direct : s.h_D, sizeof(uint16_t) * (size_t)groups, cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
 // the handle's host worker pool (caller holds h->pool_mu)
 static void ensure_pool(bbduk_handle *h) {
     if (h->pool) return;
@@ -746,8 +799,10 @@ static int process_host_impl(bbduk_handle *h, const uint8_t *bases, const uint32
                 if (h->ascii_every_set || h->pack_s_per_base <= 0.0) {  // fixed share (or nothing measured yet)
                     if (h->ascii_every > 0 && (chunk_no % h->ascii_every) == h->ascii_every - 1) packed = false;
                 } else {
-                    const double tp = h->pack_s_per_base, tb = 1.0 / (h->pcie_gbs * 1e9);
-                    const double x = std::min(0.75, std::max(0.0, (tp - 0.375 * tb) / (tp + 0.625 * tb)));
+                    // a packed base costs tp of the workers and cp bytes of the link (2 bits + its defined bit, or next to
+                    // nothing for the latter when only the exceptions travel); an ASCII base costs one byte of the link
+                    const double tp = h->pack_s_per_base, tb = 1.0 / (h->pcie_gbs * 1e9), cp = h->sparse_d ? 0.26 : 0.375;
+                    const double x = std::min(0.75, std::max(0.0, (tp - cp * tb) / (tp + (1.0 - cp) * tb)));
                     h->ascii_acc += x;
                     if (h->ascii_acc >= 1.0) {
                         h->ascii_acc -= 1.0;
@@ -767,17 +822,20 @@ static int process_host_impl(bbduk_handle *h, const uint8_t *bases, const uint32
             const bool stage = !src_pinned;
             const uint32_t *fsrc = pre_F + gfirst;
             const uint16_t *dsrc = pre_D + gfirst;
+            std::vector<int64_t> cnt(h->pool->size(), 0);
+            int64_t *cntp = cnt.data();
+            const int64_t R = s.cap_exc / h->pool->size();
+            const bool sparse = h->sparse_d;
             h->pool->run([=](int part, int n_parts) {
                 const int64_t i0 = (nr + 1) * part / n_parts, i1 = (nr + 1) * (part + 1) / n_parts;
                 for (int64_t i = i0; i < i1; i++) sp->h_off32[i] = (uint32_t)(osrc[i] - obase);
-                if (stage) {
-                    const int64_t g0 = groups * part / n_parts, g1 = groups * (part + 1) / n_parts;
-                    memcpy(sp->h_F + g0, fsrc + g0, sizeof(uint32_t) * (size_t)(g1 - g0));
-                    memcpy(sp->h_D + g0, dsrc + g0, sizeof(uint16_t) * (size_t)(g1 - g0));
-                }
+                const int64_t g0 = groups * part / n_parts, g1 = groups * (part + 1) / n_parts;
+                if (stage) memcpy(sp->h_F + g0, fsrc + g0, sizeof(uint32_t) * (size_t)(g1 - g0));
+                if (sparse) cntp[part] = list_undefined_groups(dsrc, g0, g1, sp->h_exc + part * R, R);
+                if (stage && (!sparse || cntp[part] < 0)) memcpy(sp->h_D + g0, dsrc + g0, sizeof(uint16_t) * (size_t)(g1 - g0));
             });
             CKL((h->h2d_bytes += (int64_t)(sizeof(uint32_t) * groups), cudaMemcpyAsync(s.d_F, stage ? s.h_F : fsrc, sizeof(uint32_t) * groups, cudaMemcpyHostToDevice, st)));
-            CKL((h->h2d_bytes += (int64_t)(sizeof(uint16_t) * groups), cudaMemcpyAsync(s.d_D, stage ? s.h_D : dsrc, sizeof(uint16_t) * groups, cudaMemcpyHostToDevice, st)));
+            if (!rc) rc = upload_defined(h, s, sparse ? cntp : nullptr, (int)cnt.size(), R, groups, stage ? nullptr : dsrc, dsrc, st);
             CKL((h->h2d_bytes += (int64_t)(sizeof(uint32_t) * (nr + 1)), cudaMemcpyAsync(s.d_off32, s.h_off32, sizeof(uint32_t) * (nr + 1), cudaMemcpyHostToDevice, st)));
             if (!packed && !rc) {  // a mode the tuned kernels do not serve: spell the stream out on the device
                 unpack_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(s.d_F, s.d_D, s.d_bases, groups);
@@ -789,12 +847,17 @@ static int process_host_impl(bbduk_handle *h, const uint8_t *bases, const uint32
             const int64_t *osrc = offsets + r0;
             const int64_t groups = (nb + 15) / 16;
             Slot *sp = &s;
+            std::vector<int64_t> cnt(h->pool->size(), 0);
+            int64_t *cntp = cnt.data();
+            const int64_t R = s.cap_exc / h->pool->size();
+            const bool sparse = h->sparse_d;
             const auto t_pack0 = std::chrono::steady_clock::now();
             h->pool->run([=](int part, int n_parts) {
                 // worker ranges start on 512-base boundaries so that the packer can stream whole cache lines
                 const int64_t gb = (groups + 31) / 32;
                 const int64_t g0 = std::min(groups, gb * part / n_parts * 32), g1 = std::min(groups, gb * (part + 1) / n_parts * 32);
-                pack_bases_range(src, nb, g0, g1, sp->h_F, sp->h_D);
+                if (sparse) cntp[part] = pack_bases_range_listing(src, nb, g0, g1, sp->h_F, sp->h_D, sp->h_exc + part * R, R);
+                else pack_bases_range(src, nb, g0, g1, sp->h_F, sp->h_D);
                 const int64_t i0 = (nr + 1) * part / n_parts, i1 = (nr + 1) * (part + 1) / n_parts;
                 for (int64_t i = i0; i < i1; i++) sp->h_off32[i] = (uint32_t)(osrc[i] - osrc[0]);
             });
@@ -805,7 +868,7 @@ static int process_host_impl(bbduk_handle *h, const uint8_t *bases, const uint32
                     fprintf(stderr, "[bbduk_b200] packed %lld bases in %.3f ms on %d threads\n", (long long)nb, 1e3 * dt, h->pool->size());
             }
             CKL((h->h2d_bytes += (int64_t)(sizeof(uint32_t) * groups), cudaMemcpyAsync(s.d_F, s.h_F, sizeof(uint32_t) * groups, cudaMemcpyHostToDevice, st)));
-            CKL((h->h2d_bytes += (int64_t)(sizeof(uint16_t) * groups), cudaMemcpyAsync(s.d_D, s.h_D, sizeof(uint16_t) * groups, cudaMemcpyHostToDevice, st)));
+            if (!rc) rc = upload_defined(h, s, sparse ? cntp : nullptr, (int)cnt.size(), R, groups, nullptr, nullptr, st);
             CKL((h->h2d_bytes += (int64_t)(sizeof(uint32_t) * (nr + 1)), cudaMemcpyAsync(s.d_off32, s.h_off32, sizeof(uint32_t) * (nr + 1), cudaMemcpyHostToDevice, st)));
         } else {
             CKL((h->h2d_bytes += (int64_t)((size_t)nb), cudaMemcpyAsync(s.d_bases, bases + offsets[r0], (size_t)nb, cudaMemcpyHostToDevice, st)));

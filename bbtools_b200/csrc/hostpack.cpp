@@ -137,8 +137,26 @@ __attribute__((target("avx512f,avx512bw,avx512vbmi,avx512vl"))) static inline vo
     d4 = ~(uint64_t)_mm512_movepi8_mask(_mm512_shuffle_epi8(t, rev));       // bit 7 set = undefined
 }
 
+// groups with an undefined base, collected while their defined bits are still in a register
+struct ExcOut {
+    uint64_t *out;
+    int64_t cap, n;
+    bool overflow;
+    inline void add4(int64_t g, uint64_t d4) {  // d4 = the D values of groups g..g+3, 16 bits each
+        for (int j = 0; j < 4; j++) {
+            const uint64_t dj = (d4 >> (16 * j)) & 0xFFFFu;
+            if (dj == 0xFFFFu) continue;
+            if (n >= cap) {
+                overflow = true;
+                return;
+            }
+            out[n++] = ((uint64_t)(g + j) << 16) | dj;
+        }
+    }
+};
+
 __attribute__((target("avx512f,avx512bw,avx512vbmi,avx512vl"))) void pack_avx512(const uint8_t *b, int64_t n, int64_t g0, int64_t g1,
-                                                                                  uint32_t *F, uint16_t *D) {
+                                                                                  uint32_t *F, uint16_t *D, ExcOut *ex) {
     const __m512i lutlo = _mm512_load_si512(g_lut512.lo), luthi = _mm512_load_si512(g_lut512.hi);
     int64_t g = g0;
     const int64_t full = n / 16;
@@ -150,6 +168,7 @@ __attribute__((target("avx512f,avx512bw,avx512vbmi,avx512vl"))) void pack_avx512
         pack64(b + g * 16, lutlo, luthi, f4, d4);
         _mm_storeu_si128(reinterpret_cast<__m128i *>(F + g), f4);
         memcpy(D + g, &d4, 8);
+        if (ex && d4 != ~0ull) ex->add4(g, d4);
         g += 4;
     }
     if ((reinterpret_cast<uintptr_t>(F + g) & 63) == 0 && (reinterpret_cast<uintptr_t>(D + g) & 63) == 0) {
@@ -158,6 +177,9 @@ __attribute__((target("avx512f,avx512bw,avx512vbmi,avx512vl"))) void pack_avx512
             alignas(64) uint64_t d[8];
 #pragma GCC unroll 8
             for (int q = 0; q < 8; q++) pack64(b + (g + 4 * q) * 16, lutlo, luthi, f[q], d[q]);
+            if (ex && (d[0] & d[1] & d[2] & d[3] & d[4] & d[5] & d[6] & d[7]) != ~0ull)
+                for (int q = 0; q < 8; q++)
+                    if (d[q] != ~0ull) ex->add4(g + 4 * q, d[q]);
             const __m512i fa = _mm512_inserti64x4(_mm512_castsi256_si512(_mm256_set_m128i(f[1], f[0])), _mm256_set_m128i(f[3], f[2]), 1);
             const __m512i fb = _mm512_inserti64x4(_mm512_castsi256_si512(_mm256_set_m128i(f[5], f[4])), _mm256_set_m128i(f[7], f[6]), 1);
             _mm512_stream_si512(reinterpret_cast<__m512i *>(F + g), fa);
@@ -172,27 +194,53 @@ __attribute__((target("avx512f,avx512bw,avx512vbmi,avx512vl"))) void pack_avx512
         pack64(b + g * 16, lutlo, luthi, f4, d4);
         _mm_storeu_si128(reinterpret_cast<__m128i *>(F + g), f4);
         memcpy(D + g, &d4, 8);
+        if (ex && d4 != ~0ull) ex->add4(g, d4);
     }
-    if (g < g1) pack_scalar(b, n, g, g1, F, D);
+    if (g < g1) {
+        pack_scalar(b, n, g, g1, F, D);
+        if (ex)
+            for (; g < g1; g++)
+                if (D[g] != 0xFFFFu) ex->add4(g, 0xFFFFFFFFFFFF0000ull | D[g]);
+    }
 }
 #endif
 
 }  // namespace
 
-void pack_bases_range(const uint8_t *bases, int64_t n, int64_t g0, int64_t g1, uint32_t *F, uint16_t *D) {
+static void pack_range_impl(const uint8_t *bases, int64_t n, int64_t g0, int64_t g1, uint32_t *F, uint16_t *D, ExcOut *ex) {
 #if defined(__x86_64__)
     static const bool have_avx2 = __builtin_cpu_supports("avx2");
     static const bool have_vbmi = __builtin_cpu_supports("avx512vbmi") && __builtin_cpu_supports("avx512bw") && !getenv("BBDUK_B200_NO_AVX512");
     if (have_vbmi) {
-        pack_avx512(bases, n, g0, g1, F, D);
+        pack_avx512(bases, n, g0, g1, F, D, ex);
         return;
     }
+#endif
+    if (ex) {  // the other packers do not collect: list from the array they wrote
+        pack_range_impl(bases, n, g0, g1, F, D, nullptr);
+        const int64_t c = list_undefined_groups(D, g0, g1, ex->out + ex->n, ex->cap - ex->n);
+        if (c < 0) ex->overflow = true;
+        else ex->n += c;
+        return;
+    }
+#if defined(__x86_64__)
     if (have_avx2) {
         pack_avx2(bases, n, g0, g1, F, D);
         return;
     }
 #endif
     pack_scalar(bases, n, g0, g1, F, D);
+}
+
+void pack_bases_range(const uint8_t *bases, int64_t n, int64_t g0, int64_t g1, uint32_t *F, uint16_t *D) {
+    pack_range_impl(bases, n, g0, g1, F, D, nullptr);
+}
+
+int64_t pack_bases_range_listing(const uint8_t *bases, int64_t n, int64_t g0, int64_t g1, uint32_t *F, uint16_t *D, uint64_t *exc,
+                                 int64_t cap) {
+    ExcOut ex{exc, cap, 0, false};
+    pack_range_impl(bases, n, g0, g1, F, D, &ex);
+    return ex.overflow ? -1 : ex.n;
 }
 
 void pack_bases(const uint8_t *bases, int64_t n, uint32_t *F, uint16_t *D) { pack_bases_range(bases, n, 0, (n + 15) / 16, F, D); }
@@ -255,6 +303,28 @@ bool pack_bases_range_plain(const uint8_t *bases, int64_t n, int64_t g0, int64_t
         if (plain) plain = plain_range(bases, 16 * g, 16 * ge < n ? 16 * ge : n);
     }
     return plain;
+}
+
+int64_t list_undefined_groups(const uint16_t *D, int64_t g0, int64_t g1, uint64_t *out, int64_t cap) {
+    int64_t n = 0, g = g0;
+    auto one = [&](int64_t i) -> bool {
+        if (D[i] == 0xFFFFu) return true;
+        if (n >= cap) return false;
+        out[n++] = ((uint64_t)i << 16) | D[i];
+        return true;
+    };
+    for (; g < g1 && (reinterpret_cast<uintptr_t>(D + g) & 7); g++)
+        if (!one(g)) return -1;
+    for (; g + 4 <= g1; g += 4) {
+        uint64_t w;
+        memcpy(&w, D + g, 8);
+        if (w == ~0ull) continue;
+        for (int j = 0; j < 4; j++)
+            if (!one(g + j)) return -1;
+    }
+    for (; g < g1; g++)
+        if (!one(g)) return -1;
+    return n;
 }
 
 HostPool::HostPool(int n_threads) {

@@ -14,9 +14,16 @@
 void pack_bases(const uint8_t *bases, int64_t n, uint32_t *F, uint16_t *D);
 // groups [g0, g1) only (one worker's share)
 void pack_bases_range(const uint8_t *bases, int64_t n, int64_t g0, int64_t g1, uint32_t *F, uint16_t *D);
-// the same, and: is every byte of the range one of A C G T N (upper case)? Then the device can spell the bases out again
+// the same, and the groups with an undefined base listed as by list_undefined_groups (while their bits are in a register)
+int64_t pack_bases_range_listing(const uint8_t *bases, int64_t n, int64_t g0, int64_t g1, uint32_t *F, uint16_t *D, uint64_t *exc,
+                                 int64_t cap);
+// the same as pack_bases_range, and: is every byte of the range one of A C G T N (upper case)? Then the device can spell the bases out again
 // from F + D (undefined -> 'N') and nothing is lost for the steps that read ASCII (tbo, quality trimming, entropy).
 bool pack_bases_range_plain(const uint8_t *bases, int64_t n, int64_t g0, int64_t g1, uint32_t *F, uint16_t *D);
+
+// The defined bits are almost all ones: list the groups of [g0, g1) whose D is not 0xFFFF as (group << 16 | D) words.
+// Returns their number, or -1 if there are more than cap (then the array itself has to travel).
+int64_t list_undefined_groups(const uint16_t *D, int64_t g0, int64_t g1, uint64_t *out, int64_t cap);
 
 // small persistent worker pool (the caller's thread takes part)
 class HostPool {
