@@ -985,7 +985,7 @@ int bbduk_b200_tbo_device(bbduk_handle *h, const bbduk_tbo_cfg *cfg, const uint8
                               d_insert, reinterpret_cast<unsigned long long *>(d_stats2), (cudaStream_t)stream);
     if (rc == 2) return set_err(h, "tbo: a read is longer than 1008 bases (no device path, and no CPU fallback)");
     if (rc) return set_err(h, std::string("tbo kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
-    h->launches += 3;
+    h->launches += 4;
     return 0;
 }
 

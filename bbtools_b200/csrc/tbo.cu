@@ -30,19 +30,24 @@ __device__ __forceinline__ bool fully_defined(uint8_t b) {
     return b < 128 && (y == 'a' || y == 'c' || y == 'g' || y == 't' || y == 'u');
 }
 
-// Three launches keep the lanes of a warp on one code path with similar trip counts:
+// Four launches keep the lanes of a warp on one code path with similar trip counts:
 //   MODE 0  every pair whose mates are made of A C G T only: pack, findBestRatio. ~70 % of the pairs end here (no overlap
 //           worth a second look); the others go to list M with their ratio; pairs with an N or any other byte go to list G.
 //   MODE 1  list M, compacted: the second insert loop of mateByOverlapRatioJava.
-//   MODE 2  list G, compacted: both loops with the N planes / the exact byte path.
+//   MODE 2  list G, compacted: findBestRatio with the N planes / the exact byte path; survivors go to list G2.
+//   MODE 3  list G2, compacted: the second insert loop of those (in one launch with MODE 2's work the warps ran at 9 of 32
+//           lanes: most pairs are done after findBestRatio).
 template <int MODE>
 __global__ void __launch_bounds__(TBO_THREADS)
 tbo_kernel(const uint8_t *__restrict__ bases, const uint8_t *__restrict__ quals, const uint32_t *__restrict__ offsets,
            int64_t n_pairs, const int32_t *__restrict__ lo, int32_t *hi, uint8_t *flags, int32_t *insert_out, TboDev p,
            const float *__restrict__ T_g, int n_T, const float *__restrict__ prob_error_g, const uint8_t *__restrict__ comp_g,
-           unsigned long long *stats, int32_t *list_g, unsigned int *list_g_n, int32_t *list_m, tbo::Handoff *list_m_x,
-           unsigned int *list_m_n) {
-    constexpr bool GENERAL = MODE == 2;
+           unsigned long long *stats, int32_t *list_g, unsigned int *list_g_n, const int32_t *in_list, const tbo::Handoff *in_x,
+           const unsigned int *in_n, int32_t *out_list, tbo::Handoff *out_x, unsigned int *out_n) {
+    // list_g: where MODE 0 leaves the pairs it cannot pack; in_*: the launch's compacted input (MODE 1, 2, 3); out_*: where a
+    // findBestRatio launch (MODE 0, 2) leaves the pairs whose second loop has to run
+    constexpr bool GENERAL = MODE >= 2;
+    constexpr int STAGE = (MODE == 0 || MODE == 2) ? 1 : 2;
     constexpr int S = TBO_THREADS;
     extern __shared__ __align__(16) uint32_t smem[];
     float *T = reinterpret_cast<float *>(smem);
@@ -57,9 +62,9 @@ tbo_kernel(const uint8_t *__restrict__ bases, const uint8_t *__restrict__ quals,
     __syncthreads();
     const int W = p.W;
     unsigned long long n_trim = 0, b_trim = 0;
-    const int64_t n_items = MODE == 2 ? (int64_t)*list_g_n : MODE == 1 ? (int64_t)*list_m_n : n_pairs;
+    const int64_t n_items = MODE == 0 ? n_pairs : (int64_t)*in_n;
     for (int64_t item = (int64_t)blockIdx.x * TBO_THREADS + threadIdx.x; item < n_items; item += (int64_t)gridDim.x * TBO_THREADS) {
-        const int64_t pair = MODE == 2 ? (int64_t)list_g[item] : MODE == 1 ? (int64_t)list_m[item] : item;
+        const int64_t pair = MODE == 0 ? item : (int64_t)in_list[item];
         if (MODE == 0) {  // the block's next 128 pairs are one contiguous stretch of the batch: pull it into L2 meanwhile
             const int64_t nxt = item - threadIdx.x + (int64_t)gridDim.x * TBO_THREADS;
             if (nxt < n_items) {
@@ -80,7 +85,7 @@ tbo_kernel(const uint8_t *__restrict__ bases, const uint8_t *__restrict__ quals,
         bool run = !removed;
         // expectedErrors(r1, r2) < meeFilter (jgi/BBDuk.java:2878, stream/Read.java:2985-3003); a sum of <= 1008 terms
         // of at most 0.75 cannot reach a filter above 756, so the default of strictoverlap=f skips the loop
-        if (MODE != 1 && run && quals && p.meeFilter <= 0.75f * TBO_MAX_LEN) {
+        if (STAGE == 1 && run && quals && p.meeFilter <= 0.75f * TBO_MAX_LEN) {
             float ea = 0.0f, eb = 0.0f;
             const uint8_t *qa = quals + offsets[i1] + lo1, *qb = quals + offsets[i2] + lo2;
             for (int i = 0; i < alen; i++)
@@ -99,12 +104,12 @@ tbo_kernel(const uint8_t *__restrict__ bases, const uint8_t *__restrict__ quals,
                 list_g[atomicAdd(list_g_n, 1u)] = (int32_t)pair;
                 continue;
             }
-            tbo::Handoff x = MODE == 1 ? list_m_x[item] : tbo::Handoff{0.0f, -1};
-            best = tbo::mate_by_overlap_ratio<GENERAL, MODE == 0 ? 1 : MODE == 1 ? 2 : 0, S>(c, q, alen, blen, p, T, n_T, ambig, &x);
-            if (MODE == 0 && best == -3) {  // the second loop runs in the compacted launch
-                const unsigned int w = atomicAdd(list_m_n, 1u);
-                list_m[w] = (int32_t)pair;
-                list_m_x[w] = x;
+            tbo::Handoff x = STAGE == 2 ? in_x[item] : tbo::Handoff{0.0f, -1};
+            best = tbo::mate_by_overlap_ratio<GENERAL, STAGE, S>(c, q, alen, blen, p, T, n_T, ambig, &x);
+            if (STAGE == 1 && best == -3) {  // the second loop runs in the compacted launch
+                const unsigned int w = atomicAdd(out_n, 1u);
+                out_list[w] = (int32_t)pair;
+                out_x[w] = x;
                 continue;
             }
             if (best < p.minInsert) best = -1;
@@ -140,7 +145,7 @@ struct TboTables {
     uint8_t *d_comp = nullptr;
     int32_t *d_list = nullptr, *d_list_m = nullptr;  // pairs left to the general launch / to the second-loop launch
     tbo::Handoff *d_list_x = nullptr;
-    unsigned int *d_list_n = nullptr;                // [0] general, [1] second loop
+    unsigned int *d_list_n = nullptr;                // [0] list G, [1] list M, [2] list G2
     int64_t list_cap = 0;
     int device = -1;
     float incr = 0;
@@ -198,7 +203,7 @@ int get_tables(int device, int64_t n_pairs, TboTables *out) {
     t.list_cap = n_pairs + n_pairs / 8 + 1024;
     if (cudaMalloc(&t.d_list, sizeof(int32_t) * t.list_cap) != cudaSuccess ||
         cudaMalloc(&t.d_list_m, sizeof(int32_t) * t.list_cap) != cudaSuccess ||
-        cudaMalloc(&t.d_list_x, sizeof(tbo::Handoff) * t.list_cap) != cudaSuccess || cudaMalloc(&t.d_list_n, 2 * sizeof(unsigned int)) != cudaSuccess)
+        cudaMalloc(&t.d_list_x, sizeof(tbo::Handoff) * t.list_cap) != cudaSuccess || cudaMalloc(&t.d_list_n, 4 * sizeof(unsigned int)) != cudaSuccess)
         return 1;
     g_tabs.push_back(t);
     *out = t;
@@ -244,16 +249,20 @@ int launch_tbo(int device, int sm_count, const bbduk_tbo_cfg *cfg, const uint8_t
     const size_t smem9 = smem_fixed + sizeof(uint32_t) * tbo::N_PLANES_GENERAL * (size_t)p.W * TBO_THREADS;
     if (cudaFuncSetAttribute(tbo_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6) != cudaSuccess ||
         cudaFuncSetAttribute(tbo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6) != cudaSuccess ||
-        cudaFuncSetAttribute(tbo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem9) != cudaSuccess)
+        cudaFuncSetAttribute(tbo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem9) != cudaSuccess ||
+        cudaFuncSetAttribute(tbo_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem9) != cudaSuccess)
         return 1;
     const int64_t n_pairs = n_reads / 2;
     const int blocks = (int)std::min<int64_t>((n_pairs + TBO_THREADS - 1) / TBO_THREADS, (int64_t)sm_count * 8);
-    if (cudaMemsetAsync(tab.d_list_n, 0, 2 * sizeof(unsigned int), st) != cudaSuccess) return 1;
-#define TBO_ARGS d_bases, d_quals, d_offsets, n_pairs, d_lo, d_hi, d_flags, d_insert, p, tab.d_T, n_T, tab.d_pe, tab.d_comp, d_stats, \
-                 tab.d_list, tab.d_list_n, tab.d_list_m, tab.d_list_x, tab.d_list_n + 1
-    tbo_kernel<0><<<blocks, TBO_THREADS, smem6, st>>>(TBO_ARGS);
-    tbo_kernel<1><<<blocks, TBO_THREADS, smem6, st>>>(TBO_ARGS);
-    tbo_kernel<2><<<blocks, TBO_THREADS, smem9, st>>>(TBO_ARGS);
+    // counters: [0] list G (pairs with N / other bytes), [1] list M (second loop of the A C G T pairs), [2] list G2 (second loop
+    // of the G pairs; it reuses M's arrays, which launch 1 has consumed by then)
+    if (cudaMemsetAsync(tab.d_list_n, 0, 4 * sizeof(unsigned int), st) != cudaSuccess) return 1;
+    unsigned int *n_g = tab.d_list_n, *n_m = tab.d_list_n + 1, *n_g2 = tab.d_list_n + 2;
+#define TBO_ARGS d_bases, d_quals, d_offsets, n_pairs, d_lo, d_hi, d_flags, d_insert, p, tab.d_T, n_T, tab.d_pe, tab.d_comp, d_stats, tab.d_list, n_g
+    tbo_kernel<0><<<blocks, TBO_THREADS, smem6, st>>>(TBO_ARGS, nullptr, nullptr, nullptr, tab.d_list_m, tab.d_list_x, n_m);
+    tbo_kernel<1><<<blocks, TBO_THREADS, smem6, st>>>(TBO_ARGS, tab.d_list_m, tab.d_list_x, n_m, nullptr, nullptr, nullptr);
+    tbo_kernel<2><<<blocks, TBO_THREADS, smem9, st>>>(TBO_ARGS, tab.d_list, nullptr, n_g, tab.d_list_m, tab.d_list_x, n_g2);
+    tbo_kernel<3><<<blocks, TBO_THREADS, smem9, st>>>(TBO_ARGS, tab.d_list_m, tab.d_list_x, n_g2, nullptr, nullptr, nullptr);
 #undef TBO_ARGS
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

@@ -1,5 +1,5 @@
 // Host build of bbtools_b200/csrc/tbo_core.cuh (stride 1): the same packing, screening and insert loops the device lanes
-// run, driven pair by pair the way tbo.cu's three launches do. TEST INFRASTRUCTURE: compiled by tests/test_tbo_core_cpu.py
+// run, driven pair by pair the way tbo.cu's four launches do. TEST INFRASTRUCTURE: compiled by tests/test_tbo_core_cpu.py
 // with g++ and compared with the oracle; nothing in bbtools_b200 loads it.
 #include <cmath>
 #include <cstdint>
@@ -101,12 +101,17 @@ void tbo_host_process(const uint8_t *bases, const int64_t *offsets, int64_t n_re
         int best;
         bool ambig = false;
         const uint32_t what = tbo::pack_pair<false, 1>(a, alen, b0, blen, planes.data(), W, c, q);
-        if (what & 1u) {  // MODE 2
+        if (what & 1u) {  // MODE 2, then MODE 3 after a re-pack as on the device
             path_counts[2]++;
             tbo::pack_pair<true, 1>(a, alen, b0, blen, planes.data(), W, c, q);
             if (c.exact) path_counts[3]++;
             tbo::Handoff x{0.0f, -1};
-            best = tbo::mate_by_overlap_ratio<true, 0, 1>(c, q, alen, blen, p, T.data(), n_T, ambig, &x);
+            best = tbo::mate_by_overlap_ratio<true, 1, 1>(c, q, alen, blen, p, T.data(), n_T, ambig, &x);
+            if (best == -3) {
+                std::fill(planes.begin(), planes.end(), 0xDEADBEEFu);
+                tbo::pack_pair<true, 1>(a, alen, b0, blen, planes.data(), W, c, q);
+                best = tbo::mate_by_overlap_ratio<true, 2, 1>(c, q, alen, blen, p, T.data(), n_T, ambig, &x);
+            }
         } else {  // MODE 0, then MODE 1 after a re-pack as on the device
             path_counts[0]++;
             tbo::Handoff x{0.0f, -1};
