@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Stress of the host build of bbtools_b200/csrc/tbo_core.cuh (tests/tbo_core_host.cpp) against the tbo oracle on CPU:
 tandem repeats, internal duplications, mismatch rates straddling maxRatio, N, and (odd seeds) random maxRatio / margin /
-offset / minSecondRatio.  python tools/stress_tbo_core.py FIRST_SEED LAST_SEED   (4000 pairs x 2 parameter sets per seed)"""
+offset / minSecondRatio.  python tools/stress_tbo_core.py FIRST_SEED LAST_SEED [gpu]   (4000 pairs x 2 parameter sets per seed;
+"gpu": the same pairs through bbduk_b200_tbo on the device, strict and loose defaults)"""
 import os
 import sys
 
@@ -46,8 +47,19 @@ def gen(seed, npairs):
     offsets = np.zeros(len(seqs) + 1, np.int64); np.cumsum([len(x) for x in seqs], out=offsets[1:])
     return bases, offsets
 tot = 0
+GPU = len(sys.argv) > 3 and sys.argv[3] == "gpu"  # third argument "gpu": the device kernels (default parameters only) instead of the host build
+if GPU:
+    import test_tbo_gpu as tg
+    eng = tg.engine()
 for seed in range(int(sys.argv[1]), int(sys.argv[2])):
     bases, offsets = gen(seed, 4000)
+    if GPU:
+        L = np.diff(offsets).astype(np.int32)
+        for strict in (True, False):
+            st = tg.check(eng, bases, None, offsets, np.zeros(len(L), np.int32), L, np.zeros(len(L), np.uint8), strict)
+            tot += st[0]
+        print(seed, "ok (gpu)", tot, flush=True)
+        continue
     L = np.diff(offsets).astype(np.int32); z = np.zeros(len(L), np.int32); f = np.zeros(len(L), np.uint8)
     rng = np.random.default_rng(1000 + seed)
     for strict in (True, False):
