@@ -16,8 +16,9 @@ _LIB = None
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "libbbduk_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("bbduk_oracle.c", "kcount_oracle.c", "tbo_oracle.c", "qtrim_oracle.c", "entropy_oracle.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("bbduk_oracle.c", "kcount_oracle.c", "tbo_oracle.c", "qtrim_oracle.c", "entropy_oracle.c", "seal_oracle.c", "Makefile")]
     srcs.append(os.path.join(_HERE, "..", "include", "bbduk_b200.h"))
+    srcs.append(os.path.join(_HERE, "..", "include", "seal_b200.h"))
     stale = (not os.path.exists(so)) or any(
         os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     if force or stale:

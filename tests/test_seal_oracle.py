@@ -1,0 +1,193 @@
+"""CPU tests of the Seal oracle (oracle/seal_oracle.c): hand-computed cases and an independent closed-form Python
+restatement (oracle/seal.py:ClosedFormSeal) over randomized references, reads and option sets.
+Reference: jgi/Seal.java:1760-1946 (loader), :2186-2276, :2386-2606, :2654-2708, :2864-2907 (matching)."""
+import numpy as np
+import pytest
+
+from oracle import seal as S
+
+
+def pack(strs):
+    off = np.zeros(len(strs) + 1, np.int64)
+    off[1:] = np.cumsum([len(s) for s in strs])
+    return np.frombuffer("".join(strs).encode(), np.uint8).copy(), off
+
+
+def rand_seq(rng, n, alphabet="ACGT"):
+    return "".join(rng.choice(list(alphabet), n))
+
+
+def make_case(seed, n_refs=6, ref_len=300, n_frag=60, read_len=100, paired=True, k=31, n_rate=0.01):
+    """References that share stretches (multi-id k-mers) + reads sampled from them with errors, Ns and junk."""
+    rng = np.random.default_rng(seed)
+    shared = rand_seq(rng, 80)
+    refs = []
+    for r in range(n_refs):
+        s = rand_seq(rng, ref_len)
+        if r % 2 == 0:
+            p = int(rng.integers(0, ref_len - 80))
+            s = s[:p] + shared + s[p + 80:]
+        if r == 3:
+            s = s[:50] + "N" + s[51:120] + "R" + s[121:]
+        refs.append(s)
+    refs.append(refs[1][:150])  # a reference contained in another
+    refs.append("ACGT" * 3)     # shorter than k for k=31
+    comp = str.maketrans("ACGTN", "TGCAN")
+
+    def sample():
+        r = rng.integers(0, 10)
+        if r == 0:
+            s = rand_seq(rng, read_len)
+        else:
+            src = refs[int(rng.integers(0, len(refs) - 1))]
+            L = int(min(len(src), rng.integers(k - 2, read_len + 1)))
+            p = int(rng.integers(0, len(src) - L + 1))
+            s = src[p:p + L]
+            if rng.integers(0, 4) == 0:  # chimera of two references
+                src2 = refs[int(rng.integers(0, n_refs))]
+                s = s[:L // 2] + src2[:L - L // 2]
+            if rng.integers(0, 2):
+                s = s.translate(comp)[::-1]
+        s = list(s)
+        for i in range(len(s)):
+            u = rng.random()
+            if u < n_rate:
+                s[i] = "N"
+            elif u < n_rate * 1.5:
+                s[i] = rng.choice(list("acgtRYn."))
+            elif u < n_rate * 3:
+                s[i] = rng.choice(list("ACGT"))
+        return "".join(s)
+
+    reads = [sample() for _ in range(n_frag * (2 if paired else 1))]
+    if len(reads) > 4:
+        reads[2] = ""
+        reads[3] = "ACG"
+    return refs, reads
+
+
+OPTION_SETS = [
+    dict(),
+    dict(k=31, ambig_mode=S.AMBIG_ALL),
+    dict(k=25, ambig_mode=S.AMBIG_FIRST, clearzone=3),
+    dict(k=27, ambig_mode=S.AMBIG_TOSS, mask_middle=0),
+    dict(k=21, hdist=1, mask_middle=1, mid_mask_len=3),
+    dict(k=13, hdist=2, mask_middle=0, ambig_mode=S.AMBIG_ALL),
+    dict(k=20, hdist=1, forbid_ns=1, clearzone_fraction=0.1),
+    dict(k=31, keep_pairs_together=0),
+    dict(k=24, keep_pairs_together=0, ambig_mode=S.AMBIG_ALL, clearzone=5, min_kmer_hits=3),
+    dict(k=31, match_mode=S.MATCH_FIRST),
+    dict(k=31, match_mode=S.MATCH_UNIQUE, ambig_mode=S.AMBIG_ALL),
+    dict(k=23, restrict_left=60),
+    dict(k=23, restrict_right=50, keep_pairs_together=0),
+    dict(k=31, qskip=3),
+    dict(k=31, speed=6),
+    dict(k=31, rskip=4),
+    dict(k=31, min_kmer_fraction=0.3),
+    dict(k=19, rcomp=0, clearzone_fraction=0.05, clearzone=2),
+    dict(k=5, mask_middle=0, ambig_mode=S.AMBIG_ALL, ids_stride=8),
+    dict(k=31, mid_mask_len=5, hdist=1),
+]
+
+
+def compare(cfg, refs, reads, paired, first_id=7):
+    ora = S.SealOracle(cfg)
+    ora.add_ref(*pack(refs))
+    v = ora.finalize()
+    cf = S.ClosedFormSeal(cfg)
+    cf.add_ref(refs)
+    assert cf.finalize() == v
+    ck, ci = cf.table_arrays()
+    ok, oi = ora.table()
+    assert np.array_equal(ck, ok) and np.array_equal(ci, oi)
+    res, st = ora.process(*pack(reads), paired, first_id)
+    units, cst, sc = cf.process(reads, paired, first_id)
+    assert len(units) == len(res.n_assigned)
+    stride = cfg.ids_stride
+    for u, (got, sites, mx) in enumerate(units):
+        assert res.n_assigned[u] == len(got), u
+        assert res.first_id[u] == (got[0] if got else 0), u
+        assert res.n_sites[u] == sites and res.max_hits[u] == mx, u
+        want = (got + [0] * stride)[:stride]
+        assert list(res.ids[u * stride:(u + 1) * stride]) == want, u
+    assert st.as_dict() == cst
+    for a, b in zip(ora.scaffold_counts(), sc):
+        assert np.array_equal(a, b)
+    return res, st
+
+
+@pytest.mark.parametrize("i", range(len(OPTION_SETS)))
+def test_oracle_vs_closed_form(i):
+    kw = OPTION_SETS[i]
+    cfg = S.make_cfg(**kw)
+    small = cfg.hdist == 2
+    refs, reads = make_case(100 + i, n_refs=3 if small else 6, ref_len=120 if small else 300, n_frag=30, k=cfg.k)
+    res, st = compare(cfg, refs, reads, paired=True)
+    assert st.reads_matched > 0
+    refs, reads = make_case(200 + i, n_refs=3 if small else 5, ref_len=120 if small else 300, n_frag=25, paired=False, k=cfg.k)
+    compare(cfg, refs, reads, paired=False)
+
+
+def test_hand_computed():
+    # two references sharing their first 40 bases; k=31 no middle mask: a read over the shared part hits both 10 times
+    rng = np.random.default_rng(5)
+    shared = rand_seq(rng, 40)
+    a, b = shared + "A" + rand_seq(rng, 59), shared + "C" + rand_seq(rng, 59)
+    cfg = S.make_cfg(k=31, mask_middle=0, ambig_mode=S.AMBIG_ALL)
+    ora = S.SealOracle(cfg)
+    ora.add_ref(*pack([a, b]))
+    stored, entries, refk = ora.finalize()
+    assert refk == 140 and entries == 140 and stored == 130  # 10 shared 31-mers
+    reads = [shared, a[20:80], b[:31], "N" * 50]
+    res, st = ora.process(*pack(reads), False, 0)
+    assert list(res.n_assigned) == [2, 1, 2, 0]
+    assert list(res.max_hits) == [10, 30, 1, 0]
+    assert list(res.n_sites) == [2, 1, 2, 0]
+    assert list(res.first_id) == [1, 1, 1, 0]
+    # a[20:80]: all 30 windows contain a[40], the first base that differs: id 1 only
+    assert st.as_dict() == dict(reads_in=4, bases_in=40 + 60 + 31 + 50, reads_matched=3, bases_matched=131,
+                                reads_unmatched=1, bases_unmatched=50)
+    r, bs, fr, am = ora.scaffold_counts()
+    assert list(r) == [0, 3, 2] and list(fr) == [0, 3, 2] and list(am) == [0, 2, 2]
+    assert list(bs) == [0, 131, 71]
+    # ambig=random: pair id picks finalList[numericID % sites]
+    cfg = S.make_cfg(k=31, mask_middle=0)
+    ora = S.SealOracle(cfg)
+    ora.add_ref(*pack([a, b]))
+    ora.finalize()
+    for nid in range(4):
+        res, _ = ora.process(*pack([shared]), False, nid)
+        assert res.first_id[0] == 1 + nid % 2 and res.n_assigned[0] == 1
+    # a[5:70]: 35 windows, the 5 that start at a[5..9] lie inside the shared part: 35 hits for id 1, 5 for id 2;
+    # thresh = max - cz: a clear zone of 30 lets id 2 through, 29 does not
+    for cz, want in ((30, [1, 2]), (29, [1, 0])):
+        cfg = S.make_cfg(k=31, mask_middle=0, ambig_mode=S.AMBIG_ALL, clearzone=cz)
+        ora = S.SealOracle(cfg)
+        ora.add_ref(*pack([a, b]))
+        ora.finalize()
+        res, _ = ora.process(*pack([a[5:70]]), False, 0)
+        assert res.max_hits[0] == 35 and list(res.ids[:2]) == want
+
+
+def test_default_middle_mask_and_n():
+    # default mm=t, k=31: the middle base is a wildcard, and with forbidn a window is probed once 15 bases follow an N
+    rng = np.random.default_rng(9)
+    a = rand_seq(rng, 80)
+    cfg = S.make_cfg()
+    ora = S.SealOracle(cfg)
+    ora.add_ref(*pack([a]))
+    ora.finalize()
+    r = list(a[:31])
+    r[15] = "ACGT"[("ACGT".index(r[15]) + 1) & 3]
+    res, _ = ora.process(*pack(["".join(r)]), False, 0)
+    assert res.max_hits[0] == 1
+    r[14] = "ACGT"[("ACGT".index(r[14]) + 1) & 3]
+    res, _ = ora.process(*pack(["".join(r)]), False, 0)
+    assert res.max_hits[0] == 0
+    cf = S.ClosedFormSeal(cfg)
+    cf.add_ref([a])
+    cf.finalize()
+    read = a[:20] + "N" + a[21:70]
+    res, _ = ora.process(*pack([read]), False, 0)
+    units, _, _ = cf.process([read], False, 0)
+    assert units[0][2] == res.max_hits[0]
