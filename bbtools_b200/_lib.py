@@ -3,6 +3,7 @@ import ctypes as C
 import os
 
 from ._abi import ABI_VERSION, BBDukCfg, BBDukChainCfg, BBDukEntropyCfg, BBDukOut, BBDukQtrimCfg, BBDukStats, BBDukTableDesc, BBDukTboCfg
+from .seal import SealCfg, SealOut, SealStats
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # BBDUK_B200_LIB: another build of the same library (e.g. the -DBB_FAST_COUNT debug build, `make -C bbtools_b200/csrc debug`)
@@ -82,6 +83,21 @@ SYMBOLS = [
                                           C.c_uint64, C.c_int32, C.c_void_p]),
     ("kcount_b200_last_error", C.c_char_p, [C.c_void_p]),
     ("kcount_b200_destroy", None, [C.c_void_p]),
+    # include/seal_b200.h
+    ("seal_b200_cfg_default", None, [C.POINTER(SealCfg)]),
+    ("seal_b200_create", C.c_int, [C.POINTER(SealCfg), C.POINTER(C.c_void_p)]),
+    ("seal_b200_add_ref", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    ("seal_b200_finalize", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("seal_b200_n_units", C.c_int64, [C.c_void_p, C.c_int64, C.c_int32]),
+    ("seal_b200_process", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.POINTER(SealOut),
+                                    C.POINTER(SealStats)]),
+    ("seal_b200_process_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.POINTER(SealOut),
+                                           C.c_void_p, C.c_void_p]),
+    ("seal_b200_scaffold_counts", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    ("seal_b200_table_export", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    ("seal_b200_launch_count", C.c_int64, [C.c_void_p]),
+    ("seal_b200_last_error", C.c_char_p, [C.c_void_p]),
+    ("seal_b200_destroy", None, [C.c_void_p]),
     # include/fastq_b200.h
     ("fastq_b200_index", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
                                    C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int32]),

@@ -10,90 +10,8 @@ import numpy as np
 
 from .oracle import build
 
-AMBIG_ALL, AMBIG_FIRST, AMBIG_TOSS, AMBIG_RANDOM = 1, 2, 3, 4
-MATCH_ALL, MATCH_FIRST, MATCH_UNIQUE = 1, 2, 3
-
-
-class SealCfg(C.Structure):
-    """include/seal_b200.h seal_cfg (keep the field order in sync with the header)."""
-    _fields_ = [
-        ("struct_size", C.c_int32),
-        ("k", C.c_int32),
-        ("rcomp", C.c_int32),
-        ("mask_middle", C.c_int32),
-        ("mid_mask_len", C.c_int32),
-        ("forbid_ns", C.c_int32),
-        ("hdist", C.c_int32),
-        ("speed", C.c_int32),
-        ("qskip", C.c_int32),
-        ("rskip", C.c_int32),
-        ("restrict_left", C.c_int32),
-        ("restrict_right", C.c_int32),
-        ("ambig_mode", C.c_int32),
-        ("match_mode", C.c_int32),
-        ("keep_pairs_together", C.c_int32),
-        ("clearzone", C.c_int32),
-        ("clearzone_fraction", C.c_float),
-        ("min_kmer_hits", C.c_int32),
-        ("min_kmer_fraction", C.c_float),
-        ("device", C.c_int32),
-        ("table_load_pct", C.c_int32),
-        ("ids_stride", C.c_int32),
-        ("reserved", C.c_int32 * 6),
-    ]
-
-
-class SealOut(C.Structure):
-    _fields_ = [("n_assigned", C.c_void_p), ("first_id", C.c_void_p), ("n_sites", C.c_void_p), ("max_hits", C.c_void_p),
-                ("ids", C.c_void_p)]
-
-
-class SealStats(C.Structure):
-    _fields_ = [("reads_in", C.c_int64), ("bases_in", C.c_int64), ("reads_matched", C.c_int64), ("bases_matched", C.c_int64),
-                ("reads_unmatched", C.c_int64), ("bases_unmatched", C.c_int64), ("reserved", C.c_int64 * 2)]
-
-    def as_dict(self):
-        return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}
-
-
-def make_cfg(**kw) -> SealCfg:
-    """Seal's defaults (jgi/Seal.java:104-128, :3088-3098) with overrides."""
-    c = SealCfg()
-    c.struct_size = C.sizeof(SealCfg)
-    c.k, c.rcomp, c.mask_middle, c.mid_mask_len, c.forbid_ns, c.hdist = 31, 1, 1, 0, 0, 0
-    c.ambig_mode, c.match_mode, c.keep_pairs_together = AMBIG_RANDOM, MATCH_ALL, 1
-    c.min_kmer_hits, c.table_load_pct, c.ids_stride = 1, 50, 4
-    for k, v in kw.items():
-        if not hasattr(c, k):
-            raise KeyError(k)
-        setattr(c, k, v)
-    return c
-
-
-class SealResult:
-    def __init__(self, n_units, stride):
-        self.n_assigned = np.zeros(n_units, np.int32)
-        self.first_id = np.zeros(n_units, np.int32)
-        self.n_sites = np.zeros(n_units, np.int32)
-        self.max_hits = np.zeros(n_units, np.int32)
-        self.ids = np.zeros(max(1, n_units * max(stride, 0)), np.int32)
-        self.stride = stride
-
-    def struct(self):
-        o = SealOut()
-        o.n_assigned, o.first_id = self.n_assigned.ctypes.data, self.first_id.ctypes.data
-        o.n_sites, o.max_hits = self.n_sites.ctypes.data, self.max_hits.ctypes.data
-        o.ids = self.ids.ctypes.data if self.stride > 0 else None
-        return o
-
-    def fields(self):
-        return {"n_assigned": self.n_assigned, "first_id": self.first_id, "n_sites": self.n_sites, "max_hits": self.max_hits,
-                "ids": self.ids}
-
-
-def n_units(cfg, n_reads, paired):
-    return n_reads // 2 if (paired and cfg.keep_pairs_together) else n_reads
-
+from bbtools_b200.seal import (AMBIG_ALL, AMBIG_FIRST, AMBIG_RANDOM, AMBIG_TOSS, MATCH_ALL, MATCH_FIRST, MATCH_UNIQUE, SealCfg, SealOut,  # noqa: F401
+                               SealResult, SealStats, make_cfg, n_units)
 
 _LIB = None
 

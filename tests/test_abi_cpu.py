@@ -21,6 +21,8 @@ def header_symbols():
     names = set(re.findall(r"BBDUK_API[^;(]*?\b(bbduk_b200_\w+)\s*\(", text))
     text = open(os.path.join(ROOT, "include", "kcount_b200.h")).read()
     names |= set(re.findall(r"KCOUNT_API[^;(]*?\b(kcount_b200_\w+)\s*\(", text))
+    text = open(os.path.join(ROOT, "include", "seal_b200.h")).read()
+    names |= set(re.findall(r"SEAL_API[^;(]*?\b(seal_b200_\w+)\s*\(", text))
     text = open(os.path.join(ROOT, "include", "fastq_b200.h")).read()
     names |= set(re.findall(r"FASTQ_API[^;(]*?\b(fastq_b200_\w+)\s*\(", text))
     return sorted(names)
