@@ -13,7 +13,8 @@
 // are in flight together, and the lookups land in a per-warp hit buffer in position order. The warp then folds the
 // buffer into the pair's list of distinct ids in first-seen order with counts (the reference's idList + countArray),
 // batching equal single-id hits of 32 positions into one update, and applies the clear zone, the minimum hit rule and
-// the ambiguous mode collectively. Lists live in shared memory (64 ids) and spill to a per-warp global scratch.
+// the ambiguous mode collectively. Lists live in shared memory (128 ids behind a per-warp hash; a key's value list is
+// added 32 ids at a time, one per lane) and spill to a per-warp global scratch.
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -48,7 +49,9 @@ struct SealTable {
 
 constexpr int SL_WARPS = 8;          // warps per block
 constexpr int SL_CH = 256;           // positions per chunk
-constexpr int SL_LCAP = 64;          // list entries in shared memory
+constexpr int SL_LCAP = 128;         // list entries in shared memory
+constexpr int SL_HASH_BITS = 8;
+constexpr int SL_HASH = 1 << SL_HASH_BITS;  // slots of the per-warp hash over them
 constexpr int SL_SPILL = 1024;       // list entries in the per-warp global scratch
 constexpr int SL_BLOCKS_PER_SM = 3;  // 80 registers x 256 threads: three blocks are resident
 
@@ -189,17 +192,21 @@ __global__ void sl_unmark_kernel(const int32_t *__restrict__ in, int32_t *out, i
 }
 
 // ---- matching ----------------------------------------------------------------------------------------------------
-// A unit's distinct ids in first-seen order with their counts: entries [0, SL_LCAP) in shared memory, the rest in
-// the warp's global scratch. All members are warp-uniform; every method is called by the whole warp.
+// A unit's distinct ids in first-seen order with their counts (the reference's idList + countArray): entries
+// [0, SL_LCAP) in shared memory behind a per-warp open-addressed hash id -> entry (SL_HASH slots, at most half full),
+// the rest in the warp's global scratch, searched linearly. n / last_* / overflow are warp-uniform.
 struct SlList {
     int32_t *s_id, *s_cnt;  // shared
     int32_t *g_id, *g_cnt;  // global spill
+    int32_t *h_id, *h_j;    // shared hash over the entries below SL_LCAP (the list being filled owns it)
     int n, last_id, last_j, overflow;
 
-    __device__ __forceinline__ void reset() {
+    __device__ __forceinline__ void reset(int lane) {
         n = 0;
         last_id = 0;
         last_j = -1;
+        for (int s = lane; s < SL_HASH; s += 32) h_id[s] = 0;
+        __syncwarp();
     }
     __device__ __forceinline__ int32_t id_at(int j) const { return j < SL_LCAP ? s_id[j] : g_id[j - SL_LCAP]; }
     __device__ __forceinline__ int32_t cnt_at(int j) const { return j < SL_LCAP ? s_cnt[j] : g_cnt[j - SL_LCAP]; }
@@ -207,17 +214,59 @@ struct SlList {
         if (j < SL_LCAP) s_cnt[j] += c;
         else g_cnt[j - SL_LCAP] += c;
     }
-    // hits[id] += c; first sight appends (jgi/Seal.java:2895-2898)
+    __device__ __forceinline__ void put(int j, int32_t id) {
+        if (j < SL_LCAP) {
+            s_id[j] = id;
+            s_cnt[j] = 0;
+            unsigned slot = ((unsigned)id * 0x9E3779B1u) >> (32 - SL_HASH_BITS);
+            for (;;) {  // ids are >= 1, 0 = empty; lanes of one batch may race for a slot
+                const int old = atomicCAS(h_id + slot, 0, id);
+                if (old == 0) {
+                    h_j[slot] = j;
+                    break;
+                }
+                slot = (slot + 1) & (SL_HASH - 1);
+            }
+        } else {
+            g_id[j - SL_LCAP] = id;
+            g_cnt[j - SL_LCAP] = 0;
+        }
+    }
+    // entry of `id` among the hashed entries, -1 if absent (per lane, any id)
+    __device__ __forceinline__ int find_hashed(int32_t id) const {
+        unsigned slot = ((unsigned)id * 0x9E3779B1u) >> (32 - SL_HASH_BITS);
+        for (;;) {
+            const int32_t x = h_id[slot];
+            if (x == id) return h_j[slot];
+            if (x == 0) return -1;
+            slot = (slot + 1) & (SL_HASH - 1);
+        }
+    }
+    // entry of `id` anywhere in the list, -1 if absent (per lane; the spill part is searched serially)
+    __device__ __forceinline__ int find_any(int32_t id) const {
+        int j = find_hashed(id);
+        if (j < 0)
+            for (int t = SL_LCAP; t < n; t++)
+                if (g_id[t - SL_LCAP] == id) return t;
+        return j;
+    }
+    __device__ __forceinline__ void bump_atomic(int j, int c) {
+        if (j < SL_LCAP) atomicAdd(s_cnt + j, c);
+        else atomicAdd(g_cnt + (j - SL_LCAP), c);
+    }
+    // hits[id] += c for one warp-uniform id; first sight appends (jgi/Seal.java:2895-2898)
     __device__ __forceinline__ void add(int32_t id, int c, int lane) {
         if (id != last_id) {
-            int found = -1;
-            for (int base = 0; base < n; base += 32) {
-                const int j = base + lane;
-                const int32_t x = j < n ? id_at(j) : 0;
-                const unsigned m = __ballot_sync(0xffffffffu, x == id);
-                if (m) {
-                    found = base + __ffs(m) - 1;
-                    break;
+            int found = find_hashed(id);
+            if (found < 0 && n > SL_LCAP) {
+                for (int base = SL_LCAP; base < n; base += 32) {
+                    const int j = base + lane;
+                    const int32_t x = j < n ? g_id[j - SL_LCAP] : 0;
+                    const unsigned m = __ballot_sync(0xffffffffu, x == id);
+                    if (m) {
+                        found = base + __ffs(m) - 1;
+                        break;
+                    }
                 }
             }
             if (found < 0) {
@@ -226,21 +275,53 @@ struct SlList {
                     return;
                 }
                 found = n++;
-                if (lane == 0) {
-                    if (found < SL_LCAP) {
-                        s_id[found] = id;
-                        s_cnt[found] = 0;
-                    } else {
-                        g_id[found - SL_LCAP] = id;
-                        g_cnt[found - SL_LCAP] = 0;
-                    }
-                }
+                if (lane == 0) put(found, id);
             }
             last_id = id;
             last_j = found;
         }
         if (lane == 0) bump(last_j, c);
         __syncwarp();
+    }
+    // hits[id] += c for every id of one key's value list (ascending ids, the last one carries bit 31): 32 ids per step,
+    // one per lane; new ids are appended in list order
+    __device__ __forceinline__ void add_list(const int32_t *__restrict__ ent, int64_t q, int c, int lane) {
+        last_id = 0;
+        last_j = -1;
+        for (;;) {
+            const int32_t e = __ldg(ent + q + lane);  // the entry array is padded by 32 words
+            const unsigned endm = __ballot_sync(0xffffffffu, e < 0);
+            const int nval = endm ? __ffs(endm) : 32;
+            const bool valid = lane < nval;
+            const int32_t id = e & 0x7FFFFFFF;
+            int j = -1;
+            if (valid) {
+                j = find_hashed(id);
+                if (j < 0)
+                    for (int t = SL_LCAP; t < n; t++)
+                        if (g_id[t - SL_LCAP] == id) {
+                            j = t;
+                            break;
+                        }
+            }
+            const unsigned newm = __ballot_sync(0xffffffffu, valid && j < 0);
+            if (newm) {
+                const int total = __popc(newm);
+                if (n + total > SL_LCAP + SL_SPILL) {
+                    overflow = 1;
+                    return;
+                }
+                if (valid && j < 0) {
+                    j = n + __popc(newm & ((1u << lane) - 1u));
+                    put(j, id);
+                }
+                n += total;
+            }
+            if (valid) bump(j, c);
+            __syncwarp();
+            if (endm) break;
+            q += 32;
+        }
     }
     __device__ __forceinline__ int max_count(int lane) const {
         int m = 0;
@@ -254,6 +335,8 @@ struct SlWarpSmem {
     int32_t hit[SL_CH];
     int32_t id[2][SL_LCAP];
     int32_t cnt[2][SL_LCAP];
+    int32_t h_id[SL_HASH];
+    int32_t h_j[SL_HASH];
 };
 
 // findBestMatch (jgi/Seal.java:2864-2907) of one read into `list`; returns numValidKmers (stream/Read.java:1673-1683)
@@ -271,7 +354,11 @@ __device__ int sl_scan_read(const SealParams &p, const SealTable &tb, const uint
         const int ce = min(hi, cs + SL_CH), n = ce - cs;
         const int sb = max(lo, cs - k);
         __syncwarp();
-        for (int j = lane; j < ce - sb; j += 32) sm.bytes[j] = bases[sb + j];
+        for (int j = lane; j < ce - sb; j += 32) {  // classify every base once: code | defined<<2 | isN<<3 | complement<<4
+            const uint32_t b = bases[sb + j];
+            const uint32_t def = bb_defined(b) ? 1u : 0u, x = def ? bb_code_raw(b) : 0u;
+            sm.bytes[j] = (uint8_t)(x | (def << 2) | ((b == 'N' ? 1u : 0u) << 3) | ((def ? 3u - x : 0u) << 4));
+        }
         __syncwarp();
         const int S = (n + 31) >> 5;
         const int p0 = cs + lane * S, p1 = min(ce, p0 + S);
@@ -285,11 +372,11 @@ __device__ int sl_scan_read(const SealParams &p, const SealTable &tb, const uint
                     len = 0;
                 }
                 const uint32_t b = sm.bytes[i - sb];
-                const bool def = bb_defined(b);
-                const uint64_t x = def ? bb_code_raw(b) : 0u, x2 = def ? 3u - bb_code_raw(b) : 0u;
+                const bool def = (b & 4u) != 0;
+                const uint64_t x = b & 3u, x2 = b >> 4;
                 kmer = ((kmer << 2) | x) & p.mask;
-                rkmer = ((rkmer >> 2) | (x2 << p.shift2)) & p.mask;
-                if (b == 'N' && p.forbidNs) {
+                rkmer = (rkmer >> 2) | (x2 << p.shift2);  // never exceeds 2k bits
+                if ((b & 8u) && p.forbidNs) {
                     len = 0;
                     rkmer = 0;
                 } else len++;
@@ -321,22 +408,51 @@ __device__ int sl_scan_read(const SealParams &p, const SealTable &tb, const uint
                         done = true;
                     }
                 }
-                while (hm) {
-                    const int l = __ffs(hm) - 1;
-                    const int32_t hv = __shfl_sync(0xffffffffu, v, l);
-                    if (hv > 0) {
-                        const unsigned same = __ballot_sync(0xffffffffu, v == hv) & hm;
+                if (hm) {
+                    // Positions whose ids are all listed already only add to counts, which commutes: they are applied
+                    // in parallel (equal single ids batched, value lists walked one per lane with atomics). Positions
+                    // that bring a new id follow in position order, so the list keeps the reference's first-seen order.
+                    const bool mine = (hm >> lane) & 1u;
+                    bool known = true;
+                    if (mine) {
+                        if (v > 0) known = list.find_any(v) >= 0;
+                        else {
+                            int64_t q = -(int64_t)v - 2;
+                            for (;;) {
+                                const int32_t e = __ldg(tb.ent_ids + q);
+                                if (list.find_any(e & 0x7FFFFFFF) < 0) {
+                                    known = false;
+                                    break;
+                                }
+                                if (e < 0) break;
+                                q++;
+                            }
+                        }
+                    }
+                    unsigned slow = __ballot_sync(0xffffffffu, mine && !known);
+                    unsigned fs = __ballot_sync(0xffffffffu, mine && known && v > 0);
+                    while (fs) {
+                        const int32_t hv = __shfl_sync(0xffffffffu, v, __ffs(fs) - 1);
+                        const unsigned same = __ballot_sync(0xffffffffu, v == hv) & fs;
                         list.add(hv, __popc(same), lane);
-                        hm &= ~same;
-                    } else {
-                        int64_t q = -(int64_t)hv - 2;
+                        fs &= ~same;
+                    }
+                    if (mine && known && v < 0) {
+                        int64_t q = -(int64_t)v - 2;
                         for (;;) {
                             const int32_t e = __ldg(tb.ent_ids + q);
-                            list.add(e & 0x7FFFFFFF, 1, lane);
+                            list.bump_atomic(list.find_any(e & 0x7FFFFFFF), 1);
                             if (e < 0) break;
                             q++;
                         }
-                        hm &= ~(1u << l);
+                    }
+                    __syncwarp();
+                    while (slow) {
+                        const int32_t hv = __shfl_sync(0xffffffffu, v, __ffs(slow) - 1);
+                        const unsigned same = __ballot_sync(0xffffffffu, v == hv) & slow;  // same id, or the same key's list
+                        if (hv > 0) list.add(hv, __popc(same), lane);
+                        else list.add_list(tb.ent_ids, -(int64_t)hv - 2, __popc(same), lane);
+                        slow &= ~same;
                     }
                 }
                 if (done) break;
@@ -442,7 +558,7 @@ __device__ __forceinline__ int sl_minhits(const SealParams &p, int nk) {
     return max(p.minKmerHits, (int)__fmul_rn(p.mkf, (float)nk));  // :2223
 }
 
-__global__ void __launch_bounds__(SL_WARPS * 32)
+__global__ void __launch_bounds__(SL_WARPS * 32, SL_BLOCKS_PER_SM)
 seal_match_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ offsets, int64_t n_frag, int paired,
                   long long first_numeric_id, SealParams p, SealTable tb, int table_empty, seal_out out, int32_t *spill,
                   unsigned long long *sc_reads, unsigned long long *sc_bases, unsigned long long *sc_frags,
@@ -461,6 +577,8 @@ seal_match_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
     B.s_cnt = sm.cnt[1];
     B.g_id = sp + 2 * SL_SPILL;
     B.g_cnt = sp + 3 * SL_SPILL;
+    A.h_id = B.h_id = sm.h_id;
+    A.h_j = B.h_j = sm.h_j;
     A.overflow = B.overflow = 0;
     SlAcc acc = {0, 0, 0, 0, 0, 0};
     const bool want_valid = p.czf > 0;
@@ -473,7 +591,7 @@ seal_match_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
         const long long nid = first_numeric_id + f;
         acc.reads_in += 1 + (paired ? 1 : 0);
         acc.bases_in += (unsigned long long)(L1 + L2);
-        A.reset();
+        A.reset(lane);
         if (p.kpt) {
             int nv = sl_scan_read(p, tb, bases + o0, L1, A, sm, lane, want_valid, table_empty);
             if (paired) nv += sl_scan_read(p, tb, bases + o1, L2, A, sm, lane, want_valid, table_empty);
@@ -486,7 +604,7 @@ seal_match_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
             const int max1 = A.max_count(lane);
             int nv2 = 0, max2 = 0;
             if (paired) {
-                B.reset();
+                B.reset(lane);
                 nv2 = sl_scan_read(p, tb, bases + o1, L2, B, sm, lane, want_valid, table_empty);
                 max2 = B.max_count(lane);
             }
@@ -827,7 +945,8 @@ int seal_b200_finalize(seal_handle *h, int64_t *v) {
         SCK(cudaMemcpy(&last_keep, d_keep + n_pairs - 1, 4, cudaMemcpyDeviceToHost));
         n_entries = (int64_t)last_pos + last_keep;
         SCK(cudaMalloc(&h->d_ekeys, (size_t)n_entries * 8));
-        SCK(cudaMalloc(&h->d_eids, (size_t)n_entries * 4));
+        SCK(cudaMalloc(&h->d_eids, (size_t)(n_entries + 32) * 4));
+        SCK(cudaMemset(h->d_eids + n_entries, 0, 32 * 4));
         sl_scatter_kernel<<<blocks_g, 256>>>(d_k0, d_i0, d_keep, d_pos, n_pairs, h->d_ekeys, h->d_eids);
         sl_count_heads_kernel<<<blocks_g, 256>>>(h->d_ekeys, n_entries, d_ctr + 3);
         h->launches += 6;
@@ -857,7 +976,7 @@ int seal_b200_finalize(seal_handle *h, int64_t *v) {
     } else {
         // lookups never dereference ent_ids without a multi-id key, but keep the pointers valid
         SCK(cudaMalloc(&h->d_ekeys, 8));
-        SCK(cudaMalloc(&h->d_eids, 4));
+        SCK(cudaMalloc(&h->d_eids, 33 * 4));
     }
     const size_t a = (size_t)h->n_seqs + 1;
     SCK(cudaMalloc(&h->d_sc, 4 * a * sizeof(unsigned long long)));

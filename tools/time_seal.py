@@ -2,8 +2,9 @@
 
   python tools/time_seal.py [--refs 2000] [--ref-len 5000] [--pairs 1048576] [--iters 5] [--check 20000]
 
-Reads are 150 bp pieces of the references (either strand, 1 % substitutions, 0.1 % N); every fourth reference is a
-mutated copy of a piece of one common sequence, so some k-mers carry several ids. Prints one JSON line."""
+Reads are 150 bp pieces of the references (either strand, 1 % substitutions, 0.1 % N). --mode strains: groups of four
+references 2 % apart (k-mers with 1-4 ids); --mode many: a quarter of the references are pieces of one sequence (value
+lists of hundreds of ids, the worst case for the per-pair lists). Prints one JSON line."""
 import argparse
 import ctypes as C
 import json
@@ -21,19 +22,28 @@ from bbtools_b200 import _lib  # noqa: E402
 from bbtools_b200 import seal as PS  # noqa: E402
 
 
-def workload(n_refs, ref_len, n_pairs, seed=1):
+def workload(n_refs, ref_len, n_pairs, seed=1, mode="strains"):
     rng = np.random.default_rng(seed)
     acgt = np.frombuffer(b"ACGT", np.uint8)
-    common = acgt[rng.integers(0, 4, ref_len + ref_len // 2)]
     refs = np.empty((n_refs, ref_len), np.uint8)
-    for r in range(n_refs):
-        if r % 4 == 0:
-            p = int(rng.integers(0, ref_len // 2))
-            refs[r] = common[p:p + ref_len]
-            q = rng.integers(0, ref_len, max(1, ref_len // 100))
-            refs[r, q] = acgt[rng.integers(0, 4, len(q))]
-        else:
-            refs[r] = acgt[rng.integers(0, 4, ref_len)]
+    if mode == "strains":  # groups of four references 2 % apart: k-mers carry 1-4 ids
+        for r in range(n_refs):
+            if r % 4 == 0:
+                refs[r] = acgt[rng.integers(0, 4, ref_len)]
+            else:
+                refs[r] = refs[r - r % 4]
+                q = rng.integers(0, ref_len, max(1, ref_len // 50))
+                refs[r, q] = acgt[rng.integers(0, 4, len(q))]
+    else:  # "many": every fourth reference is a 1 %-mutated piece of ONE sequence: value lists of hundreds of ids
+        common = acgt[rng.integers(0, 4, ref_len + ref_len // 2)]
+        for r in range(n_refs):
+            if r % 4 == 0:
+                p = int(rng.integers(0, ref_len // 2))
+                refs[r] = common[p:p + ref_len]
+                q = rng.integers(0, ref_len, max(1, ref_len // 100))
+                refs[r, q] = acgt[rng.integers(0, 4, len(q))]
+            else:
+                refs[r] = acgt[rng.integers(0, 4, ref_len)]
     n = 2 * n_pairs
     src = rng.integers(0, n_refs, n_pairs).repeat(2)
     pos = rng.integers(0, ref_len - 150, n)
@@ -57,8 +67,9 @@ def main():
     ap.add_argument("--pairs", type=int, default=1 << 20)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--check", type=int, default=20000)
+    ap.add_argument("--mode", default="strains", choices=["strains", "many"])
     a = ap.parse_args()
-    refs, mat = workload(a.refs, a.ref_len, a.pairs)
+    refs, mat = workload(a.refs, a.ref_len, a.pairs, mode=a.mode)
     n = mat.shape[0]
     cfg = PS.make_cfg(ambig_mode=PS.AMBIG_RANDOM)
     g = PS.SealIndexGPU(cfg)
@@ -96,7 +107,7 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.iters
     r = d_res.cpu().numpy()
-    line = {"workload": f"seal k=31 mm=t ambig=random, {a.refs} refs x {a.ref_len} bp, {a.pairs} pairs x 2 x 150 bp",
+    line = {"workload": f"seal k=31 mm=t ambig=random, {a.refs} refs x {a.ref_len} bp ({a.mode}), {a.pairs} pairs x 2 x 150 bp",
             "stored_kmers": stored, "entries": entries, "build_s": round(t_build, 3), "ms_per_batch": round(ms, 3),
             "reads_per_s": round(n / (ms * 1e-3)), "assigned_pairs": int((r[:nu] > 0).sum()), "ambiguous_pairs": int((r[2 * nu:3 * nu] > 1).sum())}
     if a.check > 0:
@@ -105,7 +116,9 @@ def main():
         o.add_ref(refs.reshape(-1), roff)
         o.finalize()
         m = min(a.check, nu) * 2
+        t0 = time.time()
         want, _ = o.process(mat[:m].reshape(-1), off[:m + 1], True, 0)
+        line["oracle_reads_per_s_1core"] = round(m / (time.time() - t0))
         h = m // 2
         ok = (np.array_equal(r[:h], want.n_assigned) and np.array_equal(r[nu:nu + h], want.first_id)
               and np.array_equal(r[2 * nu:2 * nu + h], want.n_sites) and np.array_equal(r[3 * nu:3 * nu + h], want.max_hits)
