@@ -53,6 +53,9 @@ constexpr int SL_LCAP = 128;         // list entries in shared memory
 constexpr int SL_HASH_BITS = 8;
 constexpr int SL_HASH = 1 << SL_HASH_BITS;  // slots of the per-warp hash over them
 constexpr int SL_SPILL = 1024;       // list entries in the per-warp global scratch
+constexpr int SL_GHASH_BITS = 11;
+constexpr int SL_GHASH = 1 << SL_GHASH_BITS;  // slots of the per-warp global hash over them
+constexpr int SL_SCRATCH = 4 * SL_SPILL + 2 * SL_GHASH;  // int32 words of global scratch per warp
 constexpr int SL_BLOCKS_PER_SM = 3;  // 80 registers x 256 threads: three blocks are resident
 
 __device__ __forceinline__ uint64_t sl_to_value(const SealParams &p, uint64_t kmer, uint64_t rkmer) {
@@ -197,29 +200,39 @@ __global__ void sl_unmark_kernel(const int32_t *__restrict__ in, int32_t *out, i
 // the rest in the warp's global scratch, searched linearly. n / last_* / overflow are warp-uniform.
 struct SlList {
     int32_t *s_id, *s_cnt;  // shared
-    int32_t *g_id, *g_cnt;  // global spill
+    int32_t *g_id, *g_cnt;  // global spill (read with ld.cg, counted with atomics: never through a stale L1 line)
     int32_t *h_id, *h_j;    // shared hash over the entries below SL_LCAP (the list being filled owns it)
-    int n, last_id, last_j, overflow;
+    int32_t *gh_id, *gh_j;  // global hash over the spilled entries (same owner)
+    int n, last_id, last_j, overflow, g_dirty;
 
+    __device__ __forceinline__ void clear_global_hash(int lane) {
+        for (int s = lane; s < SL_GHASH; s += 32) gh_id[s] = 0;
+        g_dirty = 0;
+    }
     __device__ __forceinline__ void reset(int lane) {
         n = 0;
         last_id = 0;
         last_j = -1;
         for (int s = lane; s < SL_HASH; s += 32) h_id[s] = 0;
+        if (g_dirty) clear_global_hash(lane);
         __syncwarp();
     }
-    __device__ __forceinline__ int32_t id_at(int j) const { return j < SL_LCAP ? s_id[j] : g_id[j - SL_LCAP]; }
-    __device__ __forceinline__ int32_t cnt_at(int j) const { return j < SL_LCAP ? s_cnt[j] : g_cnt[j - SL_LCAP]; }
+    __device__ __forceinline__ int32_t id_at(int j) const { return j < SL_LCAP ? s_id[j] : __ldcg(g_id + (j - SL_LCAP)); }
+    __device__ __forceinline__ int32_t cnt_at(int j) const { return j < SL_LCAP ? s_cnt[j] : __ldcg(g_cnt + (j - SL_LCAP)); }
     __device__ __forceinline__ void bump(int j, int c) {
         if (j < SL_LCAP) s_cnt[j] += c;
-        else g_cnt[j - SL_LCAP] += c;
+        else atomicAdd(g_cnt + (j - SL_LCAP), c);
     }
-    __device__ __forceinline__ void put(int j, int32_t id) {
+    __device__ __forceinline__ void bump_atomic(int j, int c) {
+        if (j < SL_LCAP) atomicAdd(s_cnt + j, c);
+        else atomicAdd(g_cnt + (j - SL_LCAP), c);
+    }
+    __device__ __forceinline__ void put(int j, int32_t id) {  // ids are >= 1, 0 = empty; lanes of one batch may race for a slot
         if (j < SL_LCAP) {
             s_id[j] = id;
             s_cnt[j] = 0;
             unsigned slot = ((unsigned)id * 0x9E3779B1u) >> (32 - SL_HASH_BITS);
-            for (;;) {  // ids are >= 1, 0 = empty; lanes of one batch may race for a slot
+            for (;;) {
                 const int old = atomicCAS(h_id + slot, 0, id);
                 if (old == 0) {
                     h_j[slot] = j;
@@ -230,9 +243,18 @@ struct SlList {
         } else {
             g_id[j - SL_LCAP] = id;
             g_cnt[j - SL_LCAP] = 0;
+            unsigned slot = ((unsigned)id * 0x9E3779B1u) >> (32 - SL_GHASH_BITS);
+            for (;;) {
+                const int old = atomicCAS(gh_id + slot, 0, id);
+                if (old == 0) {
+                    gh_j[slot] = j;
+                    break;
+                }
+                slot = (slot + 1) & (SL_GHASH - 1);
+            }
         }
     }
-    // entry of `id` among the hashed entries, -1 if absent (per lane, any id)
+    // entry of `id` among the hashed entries in shared memory, -1 if absent (per lane, any id)
     __device__ __forceinline__ int find_hashed(int32_t id) const {
         unsigned slot = ((unsigned)id * 0x9E3779B1u) >> (32 - SL_HASH_BITS);
         for (;;) {
@@ -242,39 +264,29 @@ struct SlList {
             slot = (slot + 1) & (SL_HASH - 1);
         }
     }
-    // entry of `id` anywhere in the list, -1 if absent (per lane; the spill part is searched serially)
+    // entry of `id` anywhere in the list, -1 if absent (per lane, any id)
     __device__ __forceinline__ int find_any(int32_t id) const {
-        int j = find_hashed(id);
-        if (j < 0)
-            for (int t = SL_LCAP; t < n; t++)
-                if (g_id[t - SL_LCAP] == id) return t;
-        return j;
-    }
-    __device__ __forceinline__ void bump_atomic(int j, int c) {
-        if (j < SL_LCAP) atomicAdd(s_cnt + j, c);
-        else atomicAdd(g_cnt + (j - SL_LCAP), c);
+        const int j = find_hashed(id);
+        if (j >= 0 || n <= SL_LCAP) return j;
+        unsigned slot = ((unsigned)id * 0x9E3779B1u) >> (32 - SL_GHASH_BITS);
+        for (;;) {
+            const int32_t x = __ldcg(gh_id + slot);
+            if (x == id) return __ldcg(gh_j + slot);
+            if (x == 0) return -1;
+            slot = (slot + 1) & (SL_GHASH - 1);
+        }
     }
     // hits[id] += c for one warp-uniform id; first sight appends (jgi/Seal.java:2895-2898)
     __device__ __forceinline__ void add(int32_t id, int c, int lane) {
         if (id != last_id) {
-            int found = find_hashed(id);
-            if (found < 0 && n > SL_LCAP) {
-                for (int base = SL_LCAP; base < n; base += 32) {
-                    const int j = base + lane;
-                    const int32_t x = j < n ? g_id[j - SL_LCAP] : 0;
-                    const unsigned m = __ballot_sync(0xffffffffu, x == id);
-                    if (m) {
-                        found = base + __ffs(m) - 1;
-                        break;
-                    }
-                }
-            }
+            int found = find_any(id);
             if (found < 0) {
                 if (n >= SL_LCAP + SL_SPILL) {
                     overflow = 1;
                     return;
                 }
                 found = n++;
+                if (found >= SL_LCAP) g_dirty = 1;
                 if (lane == 0) put(found, id);
             }
             last_id = id;
@@ -296,13 +308,7 @@ struct SlList {
             const int32_t id = e & 0x7FFFFFFF;
             int j = -1;
             if (valid) {
-                j = find_hashed(id);
-                if (j < 0)
-                    for (int t = SL_LCAP; t < n; t++)
-                        if (g_id[t - SL_LCAP] == id) {
-                            j = t;
-                            break;
-                        }
+                j = find_any(id);
             }
             const unsigned newm = __ballot_sync(0xffffffffu, valid && j < 0);
             if (newm) {
@@ -316,6 +322,7 @@ struct SlList {
                     put(j, id);
                 }
                 n += total;
+                if (n > SL_LCAP) g_dirty = 1;
             }
             if (valid) bump(j, c);
             __syncwarp();
@@ -568,7 +575,7 @@ seal_match_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
     const int64_t warp = (int64_t)blockIdx.x * SL_WARPS + wib, n_warps = (int64_t)gridDim.x * SL_WARPS;
     SlWarpSmem &sm = smem[wib];
     SlList A, B;
-    int32_t *sp = spill + warp * (4 * SL_SPILL);
+    int32_t *sp = spill + warp * (int64_t)SL_SCRATCH;
     A.s_id = sm.id[0];
     A.s_cnt = sm.cnt[0];
     A.g_id = sp;
@@ -579,6 +586,10 @@ seal_match_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
     B.g_cnt = sp + 3 * SL_SPILL;
     A.h_id = B.h_id = sm.h_id;
     A.h_j = B.h_j = sm.h_j;
+    A.gh_id = B.gh_id = sp + 4 * SL_SPILL;
+    A.gh_j = B.gh_j = sp + 4 * SL_SPILL + SL_GHASH;
+    A.clear_global_hash(lane);
+    B.g_dirty = 0;
     A.overflow = B.overflow = 0;
     SlAcc acc = {0, 0, 0, 0, 0, 0};
     const bool want_valid = p.czf > 0;
@@ -604,8 +615,10 @@ seal_match_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
             const int max1 = A.max_count(lane);
             int nv2 = 0, max2 = 0;
             if (paired) {
+                B.g_dirty = A.g_dirty;  // one global hash serves both lists: whoever fills owns it
                 B.reset(lane);
                 nv2 = sl_scan_read(p, tb, bases + o1, L2, B, sm, lane, want_valid, table_empty);
+                A.g_dirty = B.g_dirty;
                 max2 = B.max_count(lane);
             }
             sl_assign(p, A, max1, sl_cz(p, nv1), sl_minhits(p, max(L1 - k + 1, 0)), i1, nid, 1, L1, max1 >= max2, false, out,
@@ -984,7 +997,7 @@ int seal_b200_finalize(seal_handle *h, int64_t *v) {
     SCK(cudaMalloc(&h->d_stats, 8 * sizeof(unsigned long long)));
     SCK(cudaMalloc(&h->d_err, sizeof(int)));
     SCK(cudaMemset(h->d_err, 0, sizeof(int)));
-    SCK(cudaMalloc(&h->d_spill, (size_t)grid_for(h) * SL_WARPS * 4 * SL_SPILL * sizeof(int32_t)));
+    SCK(cudaMalloc(&h->d_spill, (size_t)grid_for(h) * SL_WARPS * SL_SCRATCH * sizeof(int32_t)));
     SCK(cudaDeviceSynchronize());
     h->finalized = true;
     std::vector<uint8_t>().swap(h->ref);
