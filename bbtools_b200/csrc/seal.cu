@@ -48,7 +48,7 @@ struct SealTable {
 };
 
 constexpr int SL_WARPS = 8;          // warps per block
-constexpr int SL_CH = 256;           // positions per chunk
+constexpr int SL_CH = 160;           // positions per chunk (five per lane for 150 bp reads)
 constexpr int SL_LCAP = 128;         // list entries in shared memory
 constexpr int SL_HASH_BITS = 8;
 constexpr int SL_HASH = 1 << SL_HASH_BITS;  // slots of the per-warp hash over them
@@ -339,7 +339,7 @@ struct SlList {
 
 struct SlWarpSmem {
     uint8_t bytes[SL_CH + 64];
-    int32_t hit[SL_CH];
+    uint64_t hit[SL_CH];  // pass A: the position's key (0 = nothing to probe); pass B: the value found, sign-extended
     int32_t id[2][SL_LCAP];
     int32_t cnt[2][SL_LCAP];
     int32_t h_id[SL_HASH];
@@ -348,7 +348,7 @@ struct SlWarpSmem {
 
 // findBestMatch (jgi/Seal.java:2864-2907) of one read into `list`; returns numValidKmers (stream/Read.java:1673-1683)
 // when want_valid, else 0.
-__device__ int sl_scan_read(const SealParams &p, const SealTable &tb, const uint8_t *__restrict__ bases, int L, SlList &list,
+__device__ __forceinline__ int sl_scan_read(const SealParams &p, const SealTable &tb, const uint8_t *__restrict__ bases, int L, SlList &list,
                             SlWarpSmem &sm, int lane, bool want_valid, bool table_empty) {
     const int k = p.k;
     if (L < k) return 0;  // no window, no valid k-mer
@@ -372,14 +372,13 @@ __device__ int sl_scan_read(const SealParams &p, const SealTable &tb, const uint
         if (p0 < p1) {
             uint64_t kmer = 0, rkmer = 0;
             int len = 0, dlen = 0;
-            for (int i = max(sb, p0 - k); i < p1; i++) {
+            auto roll = [&](int i) {
                 if (i == start) {  // the reference's registers start here
                     kmer = 0;
                     rkmer = 0;
                     len = 0;
                 }
                 const uint32_t b = sm.bytes[i - sb];
-                const bool def = (b & 4u) != 0;
                 const uint64_t x = b & 3u, x2 = b >> 4;
                 kmer = ((kmer << 2) | x) & p.mask;
                 rkmer = (rkmer >> 2) | (x2 << p.shift2);  // never exceeds 2k bits
@@ -387,25 +386,44 @@ __device__ int sl_scan_read(const SealParams &p, const SealTable &tb, const uint
                     len = 0;
                     rkmer = 0;
                 } else len++;
-                dlen = def ? dlen + 1 : 0;
-                if (i >= p0) {
-                    nvalid += (dlen >= k) ? 1 : 0;
-                    int32_t v = 0;
-                    if (!done && i >= start && i < stop && len >= p.minlen2 && i >= k - 1 && !(p.qskip > 1 && (i % p.qskip != 0))) {
-                        const uint64_t key = sl_to_value(p, kmer, rkmer);
-                        if (sl_passes_speed(p.speed, key)) {
-                            v = bb_table_get(tb.t, key);
-                            if (v == -1) v = 0;
-                        }
-                    }
-                    sm.hit[i - cs] = v;
+                if (want_valid) dlen = (b & 4u) ? dlen + 1 : 0;
+            };
+            // warm-up over the k positions in front of the lane's run: the same trip count on every lane, so the probing
+            // iterations below stay converged
+            for (int t = 0; t < k; t++) {
+                const int i = p0 - k + t;
+                if (i >= sb) roll(i);
+            }
+            // pass A: keys of the lane's positions; both sectors a probe will touch (the bucket's keys and its values) are
+            // prefetched, so the probes of pass B overlap instead of paying two dependent DRAM trips each
+            for (int i = p0; i < p1; i++) {
+                roll(i);
+                if (want_valid) nvalid += (dlen >= k) ? 1 : 0;
+                uint64_t key = 0;
+                if (!done && i >= start && i < stop && len >= p.minlen2 && i >= k - 1 && !(p.qskip > 1 && (i % p.qskip != 0))) {
+                    key = sl_to_value(p, kmer, rkmer);
+                    if (sl_passes_speed(p.speed, key)) {
+                        const uint64_t bkt = bb_bucket(bb_fhash64(key), tb.t.bucket_shift);
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(tb.t.keys + 4 * bkt));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(tb.t.vals + 4 * bkt));
+                    } else key = 0;
                 }
+                sm.hit[i - cs] = key;
+            }
+            for (int i = p0; i < p1; i++) {  // pass B
+                const uint64_t key = sm.hit[i - cs];
+                int32_t v = 0;
+                if (key) {
+                    v = bb_table_get(tb.t, key);
+                    if (v == -1) v = 0;
+                }
+                sm.hit[i - cs] = (uint64_t)(int64_t)v;
             }
         }
         __syncwarp();
         if (!done) {
             for (int c = 0; c < n; c += 32) {
-                const int32_t v = (c + lane < n) ? sm.hit[c + lane] : 0;
+                const int32_t v = (c + lane < n) ? (int32_t)sm.hit[c + lane] : 0;
                 unsigned hm = __ballot_sync(0xffffffffu, v != 0);
                 if (p.match != SEAL_MATCH_ALL) {  // break after the first (single-id) hit (:2902)
                     const unsigned sm_ = p.match == SEAL_MATCH_FIRST ? hm : __ballot_sync(0xffffffffu, v > 0);
@@ -421,16 +439,23 @@ __device__ int sl_scan_read(const SealParams &p, const SealTable &tb, const uint
                     // that bring a new id follow in position order, so the list keeps the reference's first-seen order.
                     const bool mine = (hm >> lane) & 1u;
                     bool known = true;
+                    int j0 = 0, j1 = 0, j2 = 0, j3 = 0, nl = 0;  // entries of the first four ids of my value list
                     if (mine) {
                         if (v > 0) known = list.find_any(v) >= 0;
                         else {
                             int64_t q = -(int64_t)v - 2;
                             for (;;) {
                                 const int32_t e = __ldg(tb.ent_ids + q);
-                                if (list.find_any(e & 0x7FFFFFFF) < 0) {
+                                const int j = list.find_any(e & 0x7FFFFFFF);
+                                if (j < 0) {
                                     known = false;
                                     break;
                                 }
+                                if (nl == 0) j0 = j;
+                                else if (nl == 1) j1 = j;
+                                else if (nl == 2) j2 = j;
+                                else if (nl == 3) j3 = j;
+                                nl++;
                                 if (e < 0) break;
                                 q++;
                             }
@@ -445,12 +470,19 @@ __device__ int sl_scan_read(const SealParams &p, const SealTable &tb, const uint
                         fs &= ~same;
                     }
                     if (mine && known && v < 0) {
-                        int64_t q = -(int64_t)v - 2;
-                        for (;;) {
-                            const int32_t e = __ldg(tb.ent_ids + q);
-                            list.bump_atomic(list.find_any(e & 0x7FFFFFFF), 1);
-                            if (e < 0) break;
-                            q++;
+                        if (nl <= 4) {
+                            list.bump_atomic(j0, 1);
+                            if (nl > 1) list.bump_atomic(j1, 1);
+                            if (nl > 2) list.bump_atomic(j2, 1);
+                            if (nl > 3) list.bump_atomic(j3, 1);
+                        } else {
+                            int64_t q = -(int64_t)v - 2;
+                            for (;;) {
+                                const int32_t e = __ldg(tb.ent_ids + q);
+                                list.bump_atomic(list.find_any(e & 0x7FFFFFFF), 1);
+                                if (e < 0) break;
+                                q++;
+                            }
                         }
                     }
                     __syncwarp();
@@ -476,7 +508,7 @@ struct SlAcc {
 
 // filterTopScaffolds_withClearzone + the start/stop choice + the counters of assignTogether / assignIndependently
 // (jgi/Seal.java:2697-2708, :2393-2408, :2414-2449). count_below: the pair is "unmatched" when max < minhits (kpt only).
-__device__ void sl_assign(const SealParams &p, const SlList &list, int mx, int cz, int minhits, int64_t unit, long long numericID,
+__device__ __forceinline__ void sl_assign(const SealParams &p, const SlList &list, int mx, int cz, int minhits, int64_t unit, long long numericID,
                           int readSum, int lenSum, bool frag, bool count_below, const seal_out &out, unsigned long long *sc_reads,
                           unsigned long long *sc_bases, unsigned long long *sc_frags, unsigned long long *sc_ambig, SlAcc &acc,
                           int lane) {
@@ -557,6 +589,9 @@ __device__ void sl_assign(const SealParams &p, const SlList &list, int mx, int c
     }
 }
 
+// the second storage is in use after the scans iff a second read was scanned apart from the first
+__device__ __forceinline__ bool m_last_is_second(int nm, int kpt) { return nm == 2 && !kpt; }
+
 __device__ __forceinline__ int sl_cz(const SealParams &p, int nvalid) {
     if (!(p.czf > 0)) return p.clearzone;
     return max(p.clearzone, (int)ceilf(__fmul_rn(p.czf, (float)nvalid)));  // :2213-2214
@@ -574,58 +609,83 @@ seal_match_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t warp = (int64_t)blockIdx.x * SL_WARPS + wib, n_warps = (int64_t)gridDim.x * SL_WARPS;
     SlWarpSmem &sm = smem[wib];
-    SlList A, B;
+    // one list object, two storages: the second one holds read 2's list when pairs are not kept together (read 1's
+    // list must survive until both maxima are known, jgi/Seal.java:2507, :2576). One call site each for the scan and
+    // the assignment keeps the kernel's code small.
+    SlList cur;
     int32_t *sp = spill + warp * (int64_t)SL_SCRATCH;
-    A.s_id = sm.id[0];
-    A.s_cnt = sm.cnt[0];
-    A.g_id = sp;
-    A.g_cnt = sp + SL_SPILL;
-    B.s_id = sm.id[1];
-    B.s_cnt = sm.cnt[1];
-    B.g_id = sp + 2 * SL_SPILL;
-    B.g_cnt = sp + 3 * SL_SPILL;
-    A.h_id = B.h_id = sm.h_id;
-    A.h_j = B.h_j = sm.h_j;
-    A.gh_id = B.gh_id = sp + 4 * SL_SPILL;
-    A.gh_j = B.gh_j = sp + 4 * SL_SPILL + SL_GHASH;
-    A.clear_global_hash(lane);
-    B.g_dirty = 0;
-    A.overflow = B.overflow = 0;
+    auto use = [&](int which) {
+        cur.s_id = sm.id[which];
+        cur.s_cnt = sm.cnt[which];
+        cur.g_id = sp + which * 2 * SL_SPILL;
+        cur.g_cnt = cur.g_id + SL_SPILL;
+    };
+    cur.h_id = sm.h_id;
+    cur.h_j = sm.h_j;
+    cur.gh_id = sp + 4 * SL_SPILL;
+    cur.gh_j = sp + 4 * SL_SPILL + SL_GHASH;
+    cur.clear_global_hash(lane);
+    cur.overflow = 0;
     SlAcc acc = {0, 0, 0, 0, 0, 0};
     const bool want_valid = p.czf > 0;
     const int k = p.k;
+    const int nm = paired ? 2 : 1;
     for (int64_t f = warp; f < n_frag; f += n_warps) {
         const int64_t i1 = paired ? 2 * f : f;
         const uint32_t o0 = offsets[i1], o1 = offsets[i1 + 1];
         const uint32_t o2 = paired ? offsets[i1 + 2] : o1;
         const int L1 = (int)(o1 - o0), L2 = (int)(o2 - o1);
         const long long nid = first_numeric_id + f;
-        acc.reads_in += 1 + (paired ? 1 : 0);
+        acc.reads_in += nm;
         acc.bases_in += (unsigned long long)(L1 + L2);
-        A.reset(lane);
-        if (p.kpt) {
-            int nv = sl_scan_read(p, tb, bases + o0, L1, A, sm, lane, want_valid, table_empty);
-            if (paired) nv += sl_scan_read(p, tb, bases + o1, L2, A, sm, lane, want_valid, table_empty);
-            const int mx = A.max_count(lane);
-            const int nk = max(L1 - k + 1, 0) + (paired ? max(L2 - k + 1, 0) : 0);
-            sl_assign(p, A, mx, sl_cz(p, nv), sl_minhits(p, nk), f, nid, 1 + (paired ? 1 : 0), L1 + L2, true, true, out, sc_reads,
-                      sc_bases, sc_frags, sc_ambig, acc, lane);
-        } else {
-            const int nv1 = sl_scan_read(p, tb, bases + o0, L1, A, sm, lane, want_valid, table_empty);
-            const int max1 = A.max_count(lane);
-            int nv2 = 0, max2 = 0;
-            if (paired) {
-                B.g_dirty = A.g_dirty;  // one global hash serves both lists: whoever fills owns it
-                B.reset(lane);
-                nv2 = sl_scan_read(p, tb, bases + o1, L2, B, sm, lane, want_valid, table_empty);
-                A.g_dirty = B.g_dirty;
-                max2 = B.max_count(lane);
+        int nv1 = 0, nv2 = 0, max1 = 0, max2 = 0, n1 = 0, n2 = 0;
+        use(0);
+        cur.reset(lane);
+        for (int m = 0; m < nm; m++) {
+            if (m == 1 && !p.kpt) {
+                n1 = cur.n;
+                max1 = cur.max_count(lane);
+                use(1);
+                cur.reset(lane);  // the hashes now serve read 2's list; read 1's entries are only read by index from here on
             }
-            sl_assign(p, A, max1, sl_cz(p, nv1), sl_minhits(p, max(L1 - k + 1, 0)), i1, nid, 1, L1, max1 >= max2, false, out,
-                      sc_reads, sc_bases, sc_frags, sc_ambig, acc, lane);
-            if (paired)
-                sl_assign(p, B, max2, sl_cz(p, nv2), sl_minhits(p, max(L2 - k + 1, 0)), i1 + 1, nid, 1, L2, max2 > max1, false, out,
-                          sc_reads, sc_bases, sc_frags, sc_ambig, acc, lane);
+            const int nv = sl_scan_read(p, tb, bases + (m ? o1 : o0), m ? L2 : L1, cur, sm, lane, want_valid, table_empty);
+            if (m) nv2 = nv;
+            else nv1 = nv;
+        }
+        if (m_last_is_second(nm, p.kpt)) {
+            n2 = cur.n;
+            max2 = cur.max_count(lane);
+        } else {
+            n1 = cur.n;
+            max1 = cur.max_count(lane);
+        }
+        const int nk1 = max(L1 - k + 1, 0), nk2 = paired ? max(L2 - k + 1, 0) : 0;
+        const int na = p.kpt ? 1 : nm;
+        for (int m = 0; m < na; m++) {
+            int mx, nv, nk, rs, ls;
+            int64_t unit;
+            bool frag;
+            if (p.kpt) {
+                mx = max1;
+                nv = nv1 + nv2;
+                nk = nk1 + nk2;
+                rs = nm;
+                ls = L1 + L2;
+                unit = f;
+                frag = true;
+            } else {
+                use(m);
+                cur.n = m ? n2 : n1;
+                mx = m ? max2 : max1;
+                nv = m ? nv2 : nv1;
+                nk = m ? nk2 : nk1;
+                rs = 1;
+                ls = m ? L2 : L1;
+                unit = i1 + m;
+                frag = m ? (max2 > max1) : (max1 >= max2);
+            }
+            sl_assign(p, cur, mx, sl_cz(p, nv), sl_minhits(p, nk), unit, nid, rs, ls, frag, p.kpt != 0, out, sc_reads, sc_bases, sc_frags,
+                      sc_ambig, acc, lane);
         }
         __syncwarp();
     }
@@ -642,7 +702,7 @@ seal_match_kernel(const uint8_t *__restrict__ bases, const uint32_t *__restrict_
             atomicAdd(stats + 4, acc.reads_u);
             atomicAdd(stats + 5, acc.bases_u);
         }
-        if (A.overflow || B.overflow) *err = 1;
+        if (cur.overflow) *err = 1;
     }
 }
 

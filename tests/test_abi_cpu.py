@@ -154,7 +154,7 @@ def test_host_packer_matches_the_codec_tables():
         assert F[g] == 0xDEADBEEF and D[g] == 0xBEEF  # nothing written past the end
 
 
-@pytest.mark.parametrize("shim", ["BBDukCuda.c", "KCountCuda.c"])
+@pytest.mark.parametrize("shim", ["BBDukCuda.c", "KCountCuda.c", "SealCuda.c"])
 def test_jni_shims_compile_and_link_against_the_c_abi(shim, tmp_path):
     """No JDK in the image: the shims are compiled with a stub jni.h (tests/stubs) and linked against the library,
     so that every C-ABI call they make is checked against the real prototypes and resolves."""
