@@ -56,7 +56,10 @@ constexpr int SL_SPILL = 1024;       // list entries in the per-warp global scra
 constexpr int SL_GHASH_BITS = 11;
 constexpr int SL_GHASH = 1 << SL_GHASH_BITS;  // slots of the per-warp global hash over them
 constexpr int SL_SCRATCH = 4 * SL_SPILL + 2 * SL_GHASH;  // int32 words of global scratch per warp
-constexpr int SL_BLOCKS_PER_SM = 3;  // 80 registers x 256 threads: three blocks are resident
+#ifndef SL_BLOCKS
+#define SL_BLOCKS 3
+#endif
+constexpr int SL_BLOCKS_PER_SM = SL_BLOCKS;  // 80 registers x 256 threads: three blocks are resident
 
 __device__ __forceinline__ uint64_t sl_to_value(const SealParams &p, uint64_t kmer, uint64_t rkmer) {
     const uint64_t v = p.rcomp ? (kmer > rkmer ? kmer : rkmer) : kmer;
@@ -416,6 +419,7 @@ __device__ __forceinline__ int sl_scan_read(const SealParams &p, const SealTable
                 if (key) {
                     v = bb_table_get(tb.t, key);
                     if (v == -1) v = 0;
+                    if (v < 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(tb.ent_ids + (-(int64_t)v - 2)));  // the fold reads it next
                 }
                 sm.hit[i - cs] = (uint64_t)(int64_t)v;
             }

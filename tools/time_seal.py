@@ -110,6 +110,15 @@ def main():
     line = {"workload": f"seal k=31 mm=t ambig=random, {a.refs} refs x {a.ref_len} bp ({a.mode}), {a.pairs} pairs x 2 x 150 bp",
             "stored_kmers": stored, "entries": entries, "build_s": round(t_build, 3), "ms_per_batch": round(ms, 3),
             "reads_per_s": round(n / (ms * 1e-3)), "assigned_pairs": int((r[:nu] > 0).sum()), "ambiguous_pairs": int((r[2 * nu:3 * nu] > 1).sum())}
+    # algorithmic bytes per read: its bases + one 32-byte bucket sector per probed k-mer (L - k + 1) + 12 B of results
+    per_read = 150 + (150 - cfg.k + 1) * 32 + 12
+    try:
+        peak, src = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        peak, src = 7700.0, "fallback"
+    ach = per_read * n / (ms * 1e-3) / 1e9
+    line["roofline"] = {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "peak_source": src, "unit": "GB/s",
+                        "frac": round(ach / peak, 4), "algorithmic_bytes_per_read": per_read}
     if a.check > 0:
         from oracle import seal as S
         o = S.SealOracle(cfg)
