@@ -160,3 +160,126 @@ class SealIndexGPU:
     @property
     def launches(self):
         return int(self.lib.seal_b200_launch_count(self.h))
+
+
+# ---- seal.sh's flag surface (jgi/Seal.java:150-380) -------------------------------------------------------------------
+def _parse_bool(b):
+    """shared/Parse.java parseBoolean: a bare flag is true; t/true/1 and f/false/0."""
+    if b is None:
+        return True
+    x = b.lower()
+    if x in ("t", "true", "1"):
+        return True
+    if x in ("f", "false", "0"):
+        return False
+    raise ValueError(f"not a boolean: {b}")
+
+
+_AMBIG = {"keep": AMBIG_FIRST, "best": AMBIG_FIRST, "first": AMBIG_FIRST, "all": AMBIG_ALL, "random": AMBIG_RANDOM, "rand": AMBIG_RANDOM,
+          "toss": AMBIG_TOSS, "discard": AMBIG_TOSS, "remove": AMBIG_TOSS}
+_MATCH = {"all": MATCH_ALL, "best": MATCH_ALL, "first": MATCH_FIRST, "unique": MATCH_UNIQUE, "firstunique": MATCH_UNIQUE}
+_INT_FLAGS = {"k": "k", "hdist": "hdist", "hammingdistance": "hdist", "skip": "rskip", "refskip": "rskip", "rskip": "rskip",
+              "qskip": "qskip", "speed": "speed", "minkmerhits": "min_kmer_hits", "minhits": "min_kmer_hits", "mh": "min_kmer_hits",
+              "mkh": "min_kmer_hits", "restrictleft": "restrict_left", "restrictright": "restrict_right"}
+_IGNORED = {"forest", "array", "array2", "array1", "arrayh", "hybrid", "arrayhf", "hybridfast", "ways", "ordered", "ord", "showspeed",
+            "ss", "prealloc", "preallocate", "initialsize", "nzo", "nonzeroonly", "statscolumns", "columns", "cols", "threads", "t"}
+_FILES = {"in", "in1", "in2", "ref", "literal", "out", "outm", "outu", "pattern", "stats", "refstats", "rpkm"}
+
+
+def parse_seal_args(args, device=0):
+    """seal.sh key=value flags -> (SealCfg, {file flags}). Same names, aliases and defaults as jgi/Seal.java:150-380;
+    flags of paths the device does not serve raise ValueError instead of being ignored."""
+    kw = {}
+    files = {}
+    for arg in args:
+        a, _, b = arg.partition("=")
+        a = a.lower()
+        b = b if _ else None
+        if b is not None and b.lower() == "null":
+            b = None
+        if a in _INT_FLAGS:
+            kw[_INT_FLAGS[a]] = int(b)
+        elif a in ("minkmerfraction", "minfraction", "mkf"):
+            kw["min_kmer_fraction"] = float(b)
+        elif a in ("mm", "maskmiddle"):
+            if b is None or b[0].isalpha():  # :255-261
+                kw["mask_middle"] = 1 if _parse_bool(b) else 0
+            else:
+                kw["mid_mask_len"] = int(b)
+                kw["mask_middle"] = 1 if int(b) > 0 else 0
+        elif a == "rcomp":
+            kw["rcomp"] = 1 if _parse_bool(b) else 0
+        elif a in ("forbidns", "forbidn", "fn"):
+            kw["forbid_ns"] = 1 if _parse_bool(b) else 0
+        elif a in ("ambiguous", "ambig"):
+            if b is None or b.lower() not in _AMBIG:
+                raise ValueError(arg)
+            kw["ambig_mode"] = _AMBIG[b.lower()]
+        elif a in ("match", "mode"):
+            if b is None or b.lower() not in _MATCH:
+                raise ValueError(arg)
+            kw["match_mode"] = _MATCH[b.lower()]
+        elif a in ("findbestmatch", "fbm"):
+            kw["match_mode"] = MATCH_ALL if _parse_bool(b) else MATCH_FIRST
+        elif a in ("firstuniquematch", "fum"):
+            if _parse_bool(b):
+                kw["match_mode"] = MATCH_UNIQUE
+        elif a in ("keeppairstogether", "kpt"):
+            kw["keep_pairs_together"] = 1 if _parse_bool(b) else 0
+        elif a in ("clearzone", "cz"):
+            if "." in b:  # :357-362
+                kw["clearzone_fraction"] = float(b)
+            else:
+                kw["clearzone"] = int(b)
+        elif a in ("clearzonefraction", "czf"):
+            kw["clearzone_fraction"] = float(b)
+        elif a in ("qhdist", "queryhammingdistance", "edits", "edist", "editdistance"):
+            if int(b) != 0:
+                raise ValueError(f"{a}={b}: not served by the device path (include/seal_b200.h)")
+        elif a in ("processcontainedref", "countvector", "trackbarcodes", "ecco", "ecc", "rename"):
+            if _parse_bool(b):
+                raise ValueError(f"{a}: not served by the device path (include/seal_b200.h)")
+        elif a in _FILES:
+            files[a] = b
+        elif a in _IGNORED:
+            pass
+        else:
+            raise ValueError(f"unknown flag: {arg}")
+    k = kw.get("k", 31)
+    if not 0 < k < 32:
+        raise ValueError("k must be at least 1; default is 31.")  # :225
+    if not 0 <= kw.get("hdist", 0) < 4:
+        raise ValueError("hamming distance must be between 0 and 3; default is 0.")  # :229
+    if not 0 <= kw.get("speed", 0) <= 16:
+        raise ValueError("Speed range is 0 to 16.")  # :243
+    return make_cfg(device=device, **kw), files
+
+
+def process_sharded(engine, bases, offsets, paired, first_numeric_id=0, group=None):
+    """N ranks, one engine (SealIndexGPU built from the same reference) per rank: this rank matches its contiguous slice
+    of the batch, the per-unit results come back in input order on every rank, totals and per-reference counters are
+    summed -- as Seal sums its ProcessThreads' counters (jgi/Seal.java:1640-1680). No per-read collective.
+    -> (fields dict, stats dict, [reads, bases, frags, ambig] of THIS call)."""
+    import torch
+    import torch.distributed as dist
+
+    from .shard import gather_in_order, shard_reads, sum_stats
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    bases = np.ascontiguousarray(bases, np.uint8)
+    offsets = np.ascontiguousarray(offsets, np.int64)
+    r0, r1, loff = shard_reads(offsets, paired, world, rank)
+    before = [x.copy() for x in engine.scaffold_counts()]
+    first = first_numeric_id + (r0 // 2 if paired else r0)  # Read.numericID counts pairs
+    res, st = engine.process(bases[offsets[r0]:offsets[r1]], loff, paired, first)
+    stride = max(res.stride, 0)
+    n_local = len(res.n_assigned)
+    local = {k: v for k, v in res.fields().items() if k != "ids"}
+    local["ids"] = res.ids[:n_local * stride]
+    merged = gather_in_order(local, group)
+    total = sum_stats(st.as_dict(), group)
+    delta = np.stack([a - b for a, b in zip(engine.scaffold_counts(), before)])
+    t = torch.from_numpy(delta)
+    if dist.get_backend(group) == "nccl":
+        t = t.cuda()
+    dist.all_reduce(t, group=group)
+    return merged, total, list(t.cpu().numpy())

@@ -1,0 +1,97 @@
+"""CPU tests of the Seal host side: seal.sh's flag surface (jgi/Seal.java:150-380) and the N>1 logic (world_size-2 gloo,
+the oracle standing in for the per-GPU engine): sharded == unsharded, including ambig=random, which depends on the
+pair's global numericID."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from bbtools_b200 import seal as PS
+from test_seal_oracle import make_case, pack
+
+
+def test_defaults_match_seal():
+    c, files = PS.parse_seal_args(["in=r.fq", "ref=a.fa,b.fa", "out=m.fq"])
+    d = PS.make_cfg()
+    for name, _ in PS.SealCfg._fields_:
+        if name != "reserved":
+            assert getattr(c, name) == getattr(d, name), name
+    assert (c.k, c.rcomp, c.mask_middle, c.hdist, c.ambig_mode, c.match_mode, c.keep_pairs_together, c.min_kmer_hits) == \
+        (31, 1, 1, 0, PS.AMBIG_RANDOM, PS.MATCH_ALL, 1, 1)
+    assert files == {"in": "r.fq", "ref": "a.fa,b.fa", "out": "m.fq"}
+
+
+@pytest.mark.parametrize("args,want", [
+    (["k=25", "hammingdistance=1", "mm=f"], dict(k=25, hdist=1, mask_middle=0)),
+    (["mm=3"], dict(mask_middle=1, mid_mask_len=3)),
+    (["mm=0"], dict(mask_middle=0, mid_mask_len=0)),
+    (["maskmiddle"], dict(mask_middle=1)),
+    (["ambig=toss", "match=unique"], dict(ambig_mode=PS.AMBIG_TOSS, match_mode=PS.MATCH_UNIQUE)),
+    (["ambiguous=Best", "mode=first"], dict(ambig_mode=PS.AMBIG_FIRST, match_mode=PS.MATCH_FIRST)),
+    (["ambig=all", "fbm=f"], dict(ambig_mode=PS.AMBIG_ALL, match_mode=PS.MATCH_FIRST)),
+    (["fum"], dict(match_mode=PS.MATCH_UNIQUE)),
+    (["kpt=f", "cz=7", "mkh=3", "mkf=0.25"], dict(keep_pairs_together=0, clearzone=7, min_kmer_hits=3, min_kmer_fraction=0.25)),
+    (["clearzone=0.1"], dict(clearzone=0, clearzone_fraction=np.float32(0.1))),
+    (["czf=0.05", "rskip=3", "qskip=2", "speed=4"], dict(clearzone_fraction=np.float32(0.05), rskip=3, qskip=2, speed=4)),
+    (["restrictleft=50", "restrictright=40", "fn", "rcomp=f"], dict(restrict_left=50, restrict_right=40, forbid_ns=1, rcomp=0)),
+    (["edist=0", "qhdist=0", "arrayhf=t", "ordered", "prealloc=0.5"], dict()),
+])
+def test_flags(args, want):
+    c, _ = PS.parse_seal_args(args)
+    d = PS.make_cfg(**{k: (float(v) if isinstance(v, np.floating) else v) for k, v in want.items()})
+    for name, _ in PS.SealCfg._fields_:
+        if name != "reserved":
+            assert getattr(c, name) == getattr(d, name), name
+
+
+@pytest.mark.parametrize("args", [["edist=1"], ["qhdist=2"], ["processcontainedref=t"], ["countvector"], ["ambig=sometimes"],
+                                  ["match"], ["k=32"], ["hdist=4"], ["speed=17"], ["nonsense=1"]])
+def test_rejected_flags(args):
+    with pytest.raises(ValueError):
+        PS.parse_seal_args(args)
+
+
+def _worker(rank, world, port, kw, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import seal as S  # the checker stands in for the per-GPU engine in this CPU test
+    cfg = PS.make_cfg(**kw)
+    refs, reads = make_case(21, n_refs=8, ref_len=400, n_frag=301, k=cfg.k, read_len=120)
+    o = S.SealOracle(cfg)
+    o.add_ref(*pack(refs))
+    o.finalize()
+    b, off = pack(reads)
+    merged, total, counts = PS.process_sharded(o, b, off, True, first_numeric_id=1000)
+    if rank == 0:
+        q.put((merged, total, counts))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(keep_pairs_together=0, ambig_mode=PS.AMBIG_ALL, clearzone=4)])
+def test_two_ranks_equal_one(kw):
+    from oracle import seal as S
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, kw, q)) for r in range(2)]
+    [p.start() for p in procs]
+    merged, total, counts = q.get(timeout=180)
+    [p.join(timeout=60) for p in procs]
+    cfg = PS.make_cfg(**kw)
+    refs, reads = make_case(21, n_refs=8, ref_len=400, n_frag=301, k=cfg.k, read_len=120)
+    o = S.SealOracle(cfg)
+    o.add_ref(*pack(refs))
+    o.finalize()
+    want, wst = o.process(*pack(reads), True, 1000)
+    for name, x in want.fields().items():
+        assert np.array_equal(merged[name], x), name
+    assert total == wst.as_dict()
+    for a, c in zip(counts, o.scaffold_counts()):
+        assert np.array_equal(a, c)
+    assert (want.n_sites > 1).any()  # ambiguous pairs are in the batch: ambig=random used the global pair index
