@@ -283,3 +283,33 @@ def process_sharded(engine, bases, offsets, paired, first_numeric_id=0, group=No
         t = t.cuda()
     dist.all_reduce(t, group=group)
     return merged, total, list(t.cpu().numpy())
+
+
+def format_stats(names, stats, counts, in1, in2=None, columns=5, nonzero_only=True):
+    """The `stats=` file of seal.sh (jgi/Seal.java:899-950 writeStats): one line per reference sequence, sorted by
+    bases, then reads (both descending), then name (structures/StringCount.java:36-40); percentages with five decimals.
+    names[i] belongs to id i+1; stats = seal_stats as a dict; counts = [reads, bases, frags, ambig] by id."""
+    reads, bases, _, ambig = counts
+    rows = []
+    asum = 0
+    for i, name in enumerate(names, start=1):
+        if reads[i] > 0 or not nonzero_only:
+            asum += int(ambig[i])
+            rows.append((name, int(reads[i]), int(bases[i]), int(ambig[i])))
+    rows.sort(key=lambda r: r[0])
+    rows.sort(key=lambda r: (-r[2], -r[1]))  # stable: ties keep the name order
+    rmult = 100.0 / (stats["reads_in"] if stats["reads_in"] > 0 else 1)
+    bmult = 100.0 / (stats["bases_in"] if stats["bases_in"] > 0 else 1)
+    out = ["#File\t" + in1 + ("" if in2 is None else "\t" + in2) + "\n"]
+    if columns == 3:
+        out.append("#Total\t%d\n" % stats["reads_in"])
+        out.append("#Matched\t%d\t%.5f%%\n" % (stats["reads_matched"], rmult * stats["reads_matched"]))
+        out.append("#Name\tReads\tReadsPct\n")
+        out += ["%s\t%d\t%.5f%%\n" % (n, r, r * rmult) for n, r, _, _ in rows]
+    else:
+        out.append("#Total\t%d\t%d\n" % (stats["reads_in"], stats["bases_in"]))
+        # the reference's format string consumes three of its five arguments (:941)
+        out.append("#Matched\t%d\t%.5f%%\t%d\n" % (stats["reads_matched"], rmult * stats["reads_matched"], stats["bases_matched"]))
+        out.append("#Name\tReads\tReadsPct\tBases\tBasesPct\tAmbigReads\n")
+        out += ["%s\t%d\t%.5f%%\t%d\t%.5f%%\t%d\n" % (n, r, r * rmult, b, b * bmult, a) for n, r, b, a in rows]
+    return "".join(out)

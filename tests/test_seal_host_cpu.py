@@ -95,3 +95,18 @@ def test_two_ranks_equal_one(kw):
     for a, c in zip(counts, o.scaffold_counts()):
         assert np.array_equal(a, c)
     assert (want.n_sites > 1).any()  # ambiguous pairs are in the batch: ambig=random used the global pair index
+
+
+def test_stats_file_format():
+    names = ["zeta", "alpha", "beta", "gamma"]
+    counts = [np.array([0, 4, 10, 4, 0]), np.array([0, 600, 1500, 600, 0]), np.array([0, 2, 5, 2, 0]), np.array([0, 1, 0, 2, 0])]
+    st = dict(reads_in=40, bases_in=6000, reads_matched=18, bases_matched=2700, reads_unmatched=22, bases_unmatched=3300)
+    txt = PS.format_stats(names, st, counts, "r1.fq", "r2.fq")
+    assert txt == ("#File\tr1.fq\tr2.fq\n#Total\t40\t6000\n#Matched\t18\t45.00000%\t2700\n"
+                   "#Name\tReads\tReadsPct\tBases\tBasesPct\tAmbigReads\n"
+                   "alpha\t10\t25.00000%\t1500\t25.00000%\t0\n"
+                   "beta\t4\t10.00000%\t600\t10.00000%\t2\n"      # ties on bases and reads: by name
+                   "zeta\t4\t10.00000%\t600\t10.00000%\t1\n")
+    txt3 = PS.format_stats(names, st, counts, "r.fq", columns=3, nonzero_only=False)
+    assert txt3.splitlines()[:4] == ["#File\tr.fq", "#Total\t40", "#Matched\t18\t45.00000%", "#Name\tReads\tReadsPct"]
+    assert txt3.splitlines()[-1] == "gamma\t0\t0.00000%" and len(txt3.splitlines()) == 8
