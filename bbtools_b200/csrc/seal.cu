@@ -2,8 +2,8 @@
 //
 // Table (replaces kmer.HashArrayHybridFast behind jgi/Seal.java:1760-1946): the loader emits every (key, id) entry
 // of every reference k-mer (with its Hamming ball) position-parallel, two stable radix sorts order them by key then
-// id, duplicates are dropped, and the distinct keys go into the same 32-byte-bucket hash array the BBDuk kernels
-// probe (bbduk_dev.cuh). A key with one id stores the id itself (one sector per lookup, the common case); a key with
+// id, duplicates are dropped, and the distinct keys go into a bucketed hash array (four slots per bucket, keys and
+// values in one 64-byte line). A key with one id stores the id itself (one line per lookup, the common case); a key with
 // several stores -(p+2), p = its first entry in the sorted id array whose last entry of a list carries bit 31.
 // A key's ids are ascending, which is the order the reference's per-way loader appends them in.
 //
@@ -42,10 +42,37 @@ struct SealParams {
     uint64_t mask, middleMask, kmask;
 };
 
+// Hash array of Seal's table: buckets of four slots, keys and values in ONE 64-byte line (a probe of this table is a random
+// DRAM access, and DRAM moves 64-byte bursts: with the BBDuk layout -- keys and values in separate arrays -- every hit
+// cost two bursts). Linear probing over buckets; slots fill in order and nothing is deleted, so an empty last slot ends
+// the search (same rule as bb_table_get).
+struct __align__(64) SlBucket {
+    uint64_t keys[4];
+    int32_t vals[4];
+    int32_t pad[4];
+};
 struct SealTable {
-    BBTable t;                // keys / vals / slot_mask / bucket_shift only
+    const SlBucket *bk;
+    uint64_t bmask;           // buckets - 1 (power of two)
+    uint32_t bucket_shift;    // bucket = hash32 >> bucket_shift
     const int32_t *ent_ids;   // sorted entries' ids, bit 31 = last id of its key
 };
+__device__ __forceinline__ int32_t sl_table_get(const SealTable &t, uint64_t key) {
+    uint64_t b = bb_bucket(bb_fhash64(key), t.bucket_shift);
+#pragma unroll 1
+    for (int probe = 0; probe < BB_MAX_PROBE / 4; probe++) {
+        const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(t.bk[b].keys);
+        const ulonglong2 k01 = __ldg(q), k23 = __ldg(q + 1);
+        const int4 v = __ldg(reinterpret_cast<const int4 *>(t.bk[b].vals));  // same line: in flight with the keys
+        if (k01.x == key) return v.x;
+        if (k01.y == key) return v.y;
+        if (k23.x == key) return v.z;
+        if (k23.y == key) return v.w;
+        if (k23.y == BB_EMPTY_KEY) return 0;
+        b = (b + 1) & t.bmask;
+    }
+    return 0;
+}
 
 constexpr int SL_WARPS = 8;          // warps per block
 constexpr int SL_CH = 160;           // positions per chunk (five per lane for 150 bp reads)
@@ -169,15 +196,16 @@ __global__ void sl_count_heads_kernel(const uint64_t *__restrict__ keys, int64_t
         c += (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
     if (c) atomicAdd(heads, c);
 }
-__global__ void sl_fill_kernel(uint64_t *keys, int32_t *vals, int64_t n) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        keys[i] = BB_EMPTY_KEY;
-        vals[i] = 0x7FFFFFFF;
+__global__ void sl_fill_kernel(SlBucket *bk, int64_t n_buckets) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 4 * n_buckets; i += (int64_t)gridDim.x * blockDim.x) {
+        bk[i >> 2].keys[i & 3] = BB_EMPTY_KEY;
+        bk[i >> 2].vals[i & 3] = 0;
+        bk[i >> 2].pad[i & 3] = 0;
     }
 }
 // one thread per sorted entry; the first entry of a key inserts it. Distinct keys only, so every put creates its slot.
-__global__ void sl_insert_kernel(const uint64_t *__restrict__ ekeys, int32_t *eids, int64_t n, uint64_t *keys, int32_t *vals,
-                                 uint64_t slot_mask, uint32_t bucket_shift, int *overflow) {
+__global__ void sl_insert_kernel(const uint64_t *__restrict__ ekeys, int32_t *eids, int64_t n, SlBucket *bk, uint64_t bmask,
+                                 uint32_t bucket_shift, int *overflow) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const uint64_t key = ekeys[i];
         if (i > 0 && ekeys[i - 1] == key) continue;
@@ -189,7 +217,21 @@ __global__ void sl_insert_kernel(const uint64_t *__restrict__ ekeys, int32_t *ei
             val = (int32_t)(-(i + 2));
             eids[i + m - 1] |= (int32_t)0x80000000;
         }
-        bb_table_put(keys, vals, slot_mask, bucket_shift, key, val, overflow);
+        uint64_t b = bb_bucket(bb_fhash64(key), bucket_shift);
+        bool placed = false;
+        for (int probe = 0; probe < BB_MAX_PROBE / 4 && !placed; probe++) {
+            for (int j = 0; j < 4 && !placed; j++) {  // in slot order, so a bucket's slots fill in order
+                if (bk[b].keys[j] != BB_EMPTY_KEY) continue;
+                const unsigned long long old =
+                    atomicCAS((unsigned long long *)&bk[b].keys[j], (unsigned long long)BB_EMPTY_KEY, (unsigned long long)key);
+                if (old == BB_EMPTY_KEY) {
+                    bk[b].vals[j] = val;
+                    placed = true;
+                }
+            }
+            b = (b + 1) & bmask;
+        }
+        if (!placed) *overflow = 1;
     }
 }
 __global__ void sl_unmark_kernel(const int32_t *__restrict__ in, int32_t *out, int64_t n) {
@@ -406,9 +448,9 @@ __device__ __forceinline__ int sl_scan_read(const SealParams &p, const SealTable
                 if (!done && i >= start && i < stop && len >= p.minlen2 && i >= k - 1 && !(p.qskip > 1 && (i % p.qskip != 0))) {
                     key = sl_to_value(p, kmer, rkmer);
                     if (sl_passes_speed(p.speed, key)) {
-                        const uint64_t bkt = bb_bucket(bb_fhash64(key), tb.t.bucket_shift);
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(tb.t.keys + 4 * bkt));
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(tb.t.vals + 4 * bkt));
+                        const uint64_t bkt = bb_bucket(bb_fhash64(key), tb.bucket_shift);
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(tb.bk[bkt].keys));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(tb.bk[bkt].vals));
                     } else key = 0;
                 }
                 sm.hit[i - cs] = key;
@@ -417,8 +459,7 @@ __device__ __forceinline__ int sl_scan_read(const SealParams &p, const SealTable
                 const uint64_t key = sm.hit[i - cs];
                 int32_t v = 0;
                 if (key) {
-                    v = bb_table_get(tb.t, key);
-                    if (v == -1) v = 0;
+                    v = sl_table_get(tb, key);
                     if (v < 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(tb.ent_ids + (-(int64_t)v - 2)));  // the fold reads it next
                 }
                 sm.hit[i - cs] = (uint64_t)(int64_t)v;
@@ -722,8 +763,7 @@ struct seal_handle {
     std::vector<int64_t> off{0};
     bool finalized = false;
     // table
-    uint64_t *d_keys = nullptr;
-    int32_t *d_vals = nullptr;
+    SlBucket *d_bk = nullptr;
     int64_t n_slots = 0;
     uint64_t *d_ekeys = nullptr;  // sorted distinct (key, id) entries
     int32_t *d_eids = nullptr;
@@ -772,25 +812,22 @@ uint32_t shift_of(uint64_t slot_mask) {
 SealTable view(const seal_handle *h) {
     SealTable t;
     memset(&t, 0, sizeof t);
-    t.t.keys = h->d_keys;
-    t.t.vals = h->d_vals;
-    t.t.slot_mask = (uint64_t)h->n_slots - 1;
-    t.t.bucket_shift = shift_of(t.t.slot_mask);
+    t.bk = h->d_bk;
+    t.bmask = (uint64_t)(h->n_slots >> 2) - 1;
+    t.bucket_shift = shift_of((uint64_t)h->n_slots - 1);
     t.ent_ids = h->d_eids;
     return t;
 }
 
 void release_table(seal_handle *h) {
-    cudaFree(h->d_keys);
-    cudaFree(h->d_vals);
+    cudaFree(h->d_bk);
     cudaFree(h->d_ekeys);
     cudaFree(h->d_eids);
     cudaFree(h->d_spill);
     cudaFree(h->d_sc);
     cudaFree(h->d_stats);
     cudaFree(h->d_err);
-    h->d_keys = nullptr;
-    h->d_vals = nullptr;
+    h->d_bk = nullptr;
     h->d_ekeys = nullptr;
     h->d_eids = nullptr;
     h->d_spill = nullptr;
@@ -1036,15 +1073,14 @@ int seal_b200_finalize(seal_handle *h, int64_t *v) {
     int load = h->c.table_load_pct;
     if (load < 10 || load > 90) load = 50;
     h->n_slots = std::max<int64_t>(1024, pow2ceil64(stored * 100 / load + 4));
-    SCK(cudaMalloc(&h->d_keys, (size_t)h->n_slots * 8));
-    SCK(cudaMalloc(&h->d_vals, (size_t)h->n_slots * 4));
-    sl_fill_kernel<<<blocks_g, 256>>>(h->d_keys, h->d_vals, h->n_slots);
+    SCK(cudaMalloc(&h->d_bk, (size_t)(h->n_slots >> 2) * sizeof(SlBucket)));
+    sl_fill_kernel<<<blocks_g, 256>>>(h->d_bk, h->n_slots >> 2);
     h->launches += 1;
     if (n_entries > 0) {
         SCK(cudaMalloc(&d_ovf, sizeof(int)));
         SCK(cudaMemset(d_ovf, 0, sizeof(int)));
         const uint64_t slot_mask = (uint64_t)h->n_slots - 1;
-        sl_insert_kernel<<<blocks_g, 256>>>(h->d_ekeys, h->d_eids, n_entries, h->d_keys, h->d_vals, slot_mask, shift_of(slot_mask), d_ovf);
+        sl_insert_kernel<<<blocks_g, 256>>>(h->d_ekeys, h->d_eids, n_entries, h->d_bk, (slot_mask >> 2), shift_of(slot_mask), d_ovf);
         h->launches += 1;
         SCK(cudaGetLastError());
         int ovf = 0;
