@@ -180,10 +180,52 @@ def cpu_reference_rate(n_pairs, threads, seed=1, first_pair=0, repeats=1):
     return best
 
 
+def seal_inputs(wl, n_pairs, read_seed=None):
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import time_seal
+    n_refs, ref_len, seed = wl["refs"]
+    refs, mat = time_seal.workload(n_refs, ref_len, n_pairs, seed=seed, read_seed=read_seed)
+    return refs.reshape(-1), np.arange(n_refs + 1, dtype=np.int64) * ref_len, mat
+
+
+def run_reference_seal(args):
+    """--impl reference --workload seal: the Seal oracle (C restatement of jgi.Seal's matching block, one thread) on a
+    bounded sample of the same workload"""
+    from bbtools_b200 import seal as PS
+    from oracle import seal as S
+    wl = WORKLOADS["seal"]
+    n_pairs = min(args.ref_pairs, 20000)
+    rb, roff, mat = seal_inputs(wl, n_pairs)
+    o = S.SealOracle(PS.make_cfg())
+    o.add_ref(rb, roff)
+    o.finalize()
+    off = np.arange(2 * n_pairs + 1, dtype=np.int64) * READ_LEN
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        o.process(mat.reshape(-1), off, True, 0)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = 2 * n_pairs * len(times) / total
+    sample = f"{2 * n_pairs} reads ({n_pairs} pairs of the same synthetic workload) per step, 1 thread"
+    emit(json.dumps({
+        "impl": "reference", "metric": "seal_reads_per_s", "value": value, "unit": "reads/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "pairs_per_step": n_pairs,
+                   "note": "CPU restatement (C port, sorted array + binary search as the map) of jgi.Seal's matching block; no JVM in the image"},
+        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload == "seal":
+        return run_reference_seal(args)
     cores = os.cpu_count() or 1
     n_pairs = args.ref_pairs
     times = []
@@ -229,6 +271,11 @@ WORKLOADS = {
     "cfg5": dict(paired=False, read_len=READ_LEN, alg_bytes=READ_LEN + 4 + 8 * 120, kernel="kcount_kernel",
                  desc="kmercountexact.sh k=31, synthetic 150 bp SE reads sampled from a 100 Mbp genome (seed 11), 0.1 % subs (cfg 5)",
                  genome=100_000_000),
+    # SURVEY.md 8f row 4 (no BASELINE.json config): Seal's multi-value table + per-pair assignment, tools/time_seal.py's workload
+    "seal": dict(paired=True, read_len=READ_LEN, alg_bytes=READ_LEN + 12 + 8 * 120, kernel="seal_match_kernel",
+                 desc="seal.sh k=31 (mm=t, ambig=random, kpt=t) vs 2000 x 5 kbp synthetic references in strain groups of four 2 % apart "
+                      "(seed 1), synthetic 2x150 bp PE sampled from them, 1 % subs, 0.1 % N (SURVEY 8f row 4)",
+                 refs=(2000, 5000, 1)),
 }
 
 
@@ -412,6 +459,136 @@ def run_kcount(args, wl):
         dist.destroy_process_group()
 
 
+def run_seal(args, wl):
+    """a step = seal_match_kernel over one HBM-resident batch of pairs (every rank its own read sample,
+    its own replica of the table built from the same references; no per-read collective)"""
+    import torch
+    import torch.distributed as dist
+
+    from bbtools_b200 import _lib
+    from bbtools_b200 import seal as PS
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    L = wl["read_len"]
+    n_pairs = min(args.pairs_per_step, 1 << 20)
+    n_reads = 2 * n_pairs
+    rb, roff, mat = seal_inputs(wl, n_pairs, read_seed=None if rank == 0 else 100 + rank)
+    cfg = PS.make_cfg(device=local_rank)
+    eng = PS.SealIndexGPU(cfg)
+    eng.add_ref(rb, roff)
+    t0 = time.perf_counter()
+    stored, entries, _ = eng.finalize()
+    build_s = time.perf_counter() - t0
+    off = np.arange(n_reads + 1, dtype=np.int64) * L
+    d_b = torch.from_numpy(np.concatenate([mat.reshape(-1), np.zeros(16, np.uint8)])).to(dev)
+    d_off = torch.from_numpy(off.astype(np.uint32).view(np.int32)).to(dev)
+    nu, stride = n_pairs, cfg.ids_stride
+    d_res = torch.zeros(nu * (4 + stride), dtype=torch.int32, device=dev)
+    d_stats = torch.zeros(8, dtype=torch.int64, device=dev)
+    out = PS.SealOut()
+    base = d_res.data_ptr()
+    out.n_assigned, out.first_id, out.n_sites, out.max_hits, out.ids = base, base + 4 * nu, base + 8 * nu, base + 12 * nu, base + 16 * nu
+    stream = torch.cuda.Stream(device=dev)
+
+    def step(i):
+        rc = lib.seal_b200_process_device(eng.h, d_b.data_ptr(), d_off.data_ptr(), n_reads, 1, 0, C.byref(out), d_stats.data_ptr(),
+                                          stream.cuda_stream)
+        if rc:
+            raise RuntimeError(lib.seal_b200_last_error(eng.h).decode())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = eng.launches
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    with torch.cuda.stream(stream):
+        ev[0].record(stream)
+        for i in range(args.steps):
+            step(args.warmup + i)
+            ev[i + 1].record(stream)
+    barrier()
+    launches = eng.launches - l0
+    clocks = sampler.stop()
+    total_ms = ev[0].elapsed_time(ev[args.steps])
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms_max = float(tmax.item())
+    value = world * n_reads * args.steps / (total_ms_max * 1e-3)
+    # every rank checks the head of ITS timed batch against the oracle; AND over ranks
+    from oracle import seal as S
+    ora = S.SealOracle(cfg)
+    ora.add_ref(rb, roff)
+    ora.finalize()
+    h = min(4000, n_pairs)
+    t0 = time.perf_counter()
+    want, _ = ora.process(mat[:2 * h].reshape(-1), off[:2 * h + 1], True, 0)
+    cpu_dt = time.perf_counter() - t0
+    r = d_res.cpu().numpy()
+    ok = (np.array_equal(r[:h], want.n_assigned) and np.array_equal(r[nu:nu + h], want.first_id)
+          and np.array_equal(r[2 * nu:2 * nu + h], want.n_sites) and np.array_equal(r[3 * nu:3 * nu + h], want.max_hits)
+          and np.array_equal(r[4 * nu:4 * nu + h * stride], want.ids))
+    okt = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+    if world > 1:
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    # end to end: host buffers through seal_b200_process (H2D + kernel + D2H inside the timed region)
+    e_pairs = min(args.e2e_pairs, n_pairs, 1 << 19)
+    hb, ho = mat[:2 * e_pairs].reshape(-1), off[:2 * e_pairs + 1]
+    eng.process(hb, ho, True, 0)
+    barrier()
+    e_steps = 3
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        eng.process(hb, ho, True, 0)
+    e_dt = time.perf_counter() - t0
+    te = torch.tensor([e_dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e_value = world * 2 * e_pairs * e_steps / float(te.item())
+    if rank == 0:
+        peak, peak_kind = load_peak()
+        kern_ms = total_ms_max / args.steps
+        achieved = n_reads * wl["alg_bytes"] / (kern_ms * 1e-3) / 1e9
+        line = {
+            "metric": "seal_reads_per_s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": kern_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int64", "data": "synthetic",
+            "config": {"workload": wl["desc"], "pairs_per_step_per_gpu": n_pairs, "stored_kmers": stored, "table_entries": entries,
+                       "table_build_s": build_s, "parity_vs_oracle_on_timed_batch": bool(int(okt.item())), "parity_pairs_per_rank": h,
+                       "l2": f"inputs {n_reads * L / 2**20:.0f} MiB per step > 126 MB L2; table {stored * 2 * 16 / 2**20:.0f} MiB"},
+            "e2e": {"value": e_value, "unit": "reads/s", "h2d_bytes_per_step": int(hb.nbytes + (2 * e_pairs + 1) * 4),
+                    "d2h_bytes_per_step": int(e_pairs * (4 + stride) * 4 + 64), "pairs_per_step_per_gpu": e_pairs, "steps": e_steps},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": (13122799000 + 48030976) / 524288 * n_reads,
+                         "traffic_unit": "bytes per launch (ncu dram read+write per read x reads per launch)",
+                         "traffic_source": "profiles/r02w_seal_match_kernel_raw.txt (the kernel before keys and values shared a line)",
+                         "peak_source": peak_kind, "kernel": wl["kernel"], "algorithmic_bytes_per_read": wl["alg_bytes"],
+                         "ms_per_launch": kern_ms},
+        }
+        if world == 1:
+            line["cpu_baseline"] = {"value": 2 * h / cpu_dt, "unit": "reads/s", "cores": 1, "kind": "port",
+                                    "sample": f"{2 * h} reads of the timed batch, Seal oracle (C port), 1 thread"}
+        emit(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -423,6 +600,8 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the BBDuk path has no CPU fallback")
     if args.workload == "cfg5":
         return run_kcount(args, wl)
+    if args.workload == "seal":
+        return run_seal(args, wl)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -860,7 +1039,7 @@ def main():
     ap.add_argument("--cpu-pairs", type=int, default=4 << 20, help="pairs of the cpu_baseline sample (0 = skip)")
     ap.add_argument("--ref-pairs", type=int, default=1 << 19, help="pairs per step of --impl reference")
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS),
-                    help="cfg2 = the headline line (default); cfg3/cfg4 = HBM-resident tables; cfg5 = kmercountexact")
+                    help="cfg2 = the headline line (default); cfg3/cfg4 = HBM-resident tables; cfg5 = kmercountexact; seal = Seal's matching block")
     ap.add_argument("--verify", action="store_true", help="cfg3/cfg4: also build the CPU oracle's table and check a slice")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -22,7 +22,8 @@ from bbtools_b200 import _lib  # noqa: E402
 from bbtools_b200 import seal as PS  # noqa: E402
 
 
-def workload(n_refs, ref_len, n_pairs, seed=1, mode="strains"):
+def workload(n_refs, ref_len, n_pairs, seed=1, mode="strains", read_seed=None):
+    """-> (refs [n_refs, ref_len] uint8, reads [2 * n_pairs, 150] uint8); read_seed: another read sample of the same references"""
     rng = np.random.default_rng(seed)
     acgt = np.frombuffer(b"ACGT", np.uint8)
     refs = np.empty((n_refs, ref_len), np.uint8)
@@ -44,6 +45,8 @@ def workload(n_refs, ref_len, n_pairs, seed=1, mode="strains"):
                 refs[r, q] = acgt[rng.integers(0, 4, len(q))]
             else:
                 refs[r] = acgt[rng.integers(0, 4, ref_len)]
+    if read_seed is not None:
+        rng = np.random.default_rng(read_seed)
     n = 2 * n_pairs
     src = rng.integers(0, n_refs, n_pairs).repeat(2)
     pos = rng.integers(0, ref_len - 150, n)
