@@ -771,6 +771,10 @@ struct seal_handle {
     int32_t n_seqs = 0;
     // matching
     int32_t *d_spill = nullptr;
+    uint8_t *b_bases = nullptr;  // staging of seal_b200_process
+    uint32_t *b_off = nullptr;
+    int32_t *b_res = nullptr;
+    int64_t cap_bases = 0, cap_reads = 0;
     unsigned long long *d_sc = nullptr;  // 4 * (n_seqs+1)
     unsigned long long *d_stats = nullptr;
     int *d_err = nullptr;
@@ -824,6 +828,13 @@ void release_table(seal_handle *h) {
     cudaFree(h->d_ekeys);
     cudaFree(h->d_eids);
     cudaFree(h->d_spill);
+    cudaFree(h->b_bases);
+    cudaFree(h->b_off);
+    cudaFree(h->b_res);
+    h->b_bases = nullptr;
+    h->b_off = nullptr;
+    h->b_res = nullptr;
+    h->cap_bases = h->cap_reads = 0;
     cudaFree(h->d_sc);
     cudaFree(h->d_stats);
     cudaFree(h->d_err);
@@ -1142,10 +1153,12 @@ int seal_b200_process(seal_handle *h, const uint8_t *bases, const int64_t *offse
     SCK(cudaMemset(h->d_stats, 0, 8 * sizeof(unsigned long long)));
     // chunks of whole fragments, < 1 GiB of bases and <= 8 Mi reads each
     const int64_t max_bases = 1ll << 30, max_reads = 1ll << 23;
-    uint8_t *d_bases = nullptr;
-    uint32_t *d_off = nullptr;
-    int32_t *d_res = nullptr;
-    int64_t cap_bases = 0, cap_reads = 0;
+    // device staging of the host entry point: kept with the handle and only ever grown (cudaMalloc / cudaFree per call
+    // cost more than the kernel on small batches)
+    uint8_t *&d_bases = h->b_bases;
+    uint32_t *&d_off = h->b_off;
+    int32_t *&d_res = h->b_res;
+    int64_t &cap_bases = h->cap_bases, &cap_reads = h->cap_reads;
     std::vector<uint32_t> off32;
     int rc = 0;
     int64_t r0 = 0;
@@ -1165,10 +1178,17 @@ int seal_b200_process(seal_handle *h, const uint8_t *bases, const int64_t *offse
             d_bases = nullptr;
             d_off = nullptr;
             d_res = nullptr;
-            cap_bases = nb + 16;
-            cap_reads = nr;
+            cap_bases = std::max(cap_bases, nb + 16);
+            cap_reads = std::max(cap_reads, nr);
             if (cudaMalloc(&d_bases, (size_t)cap_bases) != cudaSuccess || cudaMalloc(&d_off, (size_t)(cap_reads + 1) * 4) != cudaSuccess ||
                 cudaMalloc(&d_res, (size_t)cap_reads * (4 + (size_t)h->p.ids_stride) * 4 + 16) != cudaSuccess) {
+                cudaFree(d_bases);
+                cudaFree(d_off);
+                cudaFree(d_res);
+                d_bases = nullptr;
+                d_off = nullptr;
+                d_res = nullptr;
+                cap_bases = cap_reads = 0;
                 rc = serr(h, "cudaMalloc failed for the batch buffers");
                 break;
             }
@@ -1216,9 +1236,6 @@ int seal_b200_process(seal_handle *h, const uint8_t *bases, const int64_t *offse
         }
         r0 = r1;
     }
-    cudaFree(d_bases);
-    cudaFree(d_off);
-    cudaFree(d_res);
     if (rc) return rc;
     if (check_overflow(h)) return 1;
     if (stats) {
