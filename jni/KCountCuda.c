@@ -1,7 +1,7 @@
 /*
  * KCountCuda.c -- JNI shim between a GPU-backed kmer.KmerTableSet (Java) and the counting entry points of
- * libbbduk_b200.so (include/kcount_b200.h). Pure marshalling, same conventions as jni/BBDukCuda.c and the
- * reference's jni/BBMergeOverlapper.c:389-437. NOT compiled against a real JDK in this repository's image.
+ * libbbduk_b200.so (include/kcount_b200.h). Pure marshalling, same conventions as jni/BBDukCuda.c (arrays copied
+ * with Get / Set*ArrayRegion, no critical section across a CUDA call). NOT compiled against a real JDK in this repository's image.
  *
  * Java side: KmerTableSet.LoadThread (kmer/KmerTableSet.java:489-592) aggregates reads into one byte[] +
  * long[] offsets per >= 1 M reads and calls addReadsNative instead of addKmersToTable (:652-716);
@@ -9,6 +9,7 @@
  */
 #include <jni.h>
 #include <stddef.h>
+#include <stdlib.h>
 
 #include "kcount_b200.h"
 
@@ -18,13 +19,21 @@ JNIEXPORT jlong JNICALL Java_kmer_KmerTableSetGPU_createNative(JNIEnv *env, jcla
     return (jlong)(intptr_t)h;
 }
 
+/* The arrays are COPIED (Get*ArrayRegion): kcount_b200_add_reads synchronises with the device and may grow the table,
+ * far too long to hold a JNI critical section (the garbage collector would be blocked JVM-wide). */
 JNIEXPORT jint JNICALL Java_kmer_KmerTableSetGPU_addReadsNative(JNIEnv *env, jclass cls, jlong handle, jbyteArray jbases,
                                                                 jlongArray joffsets, jlong nReads) {
-    jbyte *b = (jbyte *)(*env)->GetPrimitiveArrayCritical(env, jbases, NULL);
-    jlong *o = (jlong *)(*env)->GetPrimitiveArrayCritical(env, joffsets, NULL);
-    const jint rc = kcount_b200_add_reads((kcount_handle *)(intptr_t)handle, (const uint8_t *)b, (const int64_t *)o, nReads);
-    (*env)->ReleasePrimitiveArrayCritical(env, joffsets, o, JNI_ABORT);
-    (*env)->ReleasePrimitiveArrayCritical(env, jbases, b, JNI_ABORT);
+    const jsize nb = (*env)->GetArrayLength(env, jbases);
+    jbyte *b = (jbyte *)malloc(nb > 0 ? (size_t)nb : 1);
+    jlong *o = (jlong *)malloc((size_t)(nReads + 1) * sizeof(jlong));
+    jint rc = 1;
+    if (b && o && (*env)->GetArrayLength(env, joffsets) >= nReads + 1) {
+        (*env)->GetByteArrayRegion(env, jbases, 0, nb, b);
+        (*env)->GetLongArrayRegion(env, joffsets, 0, (jsize)(nReads + 1), o);
+        rc = kcount_b200_add_reads((kcount_handle *)(intptr_t)handle, (const uint8_t *)b, (const int64_t *)o, nReads);
+    }
+    free(b);
+    free(o);
     return rc;
 }
 
@@ -37,9 +46,13 @@ JNIEXPORT jint JNICALL Java_kmer_KmerTableSetGPU_statsNative(JNIEnv *env, jclass
 }
 
 JNIEXPORT jint JNICALL Java_kmer_KmerTableSetGPU_khistNative(JNIEnv *env, jclass cls, jlong handle, jint histMax, jlongArray jhist) {
-    jlong *hst = (jlong *)(*env)->GetPrimitiveArrayCritical(env, jhist, NULL);
-    const jint rc = kcount_b200_khist((kcount_handle *)(intptr_t)handle, histMax, (int64_t *)hst);
-    (*env)->ReleasePrimitiveArrayCritical(env, jhist, hst, 0);
+    int64_t *hst = (int64_t *)malloc((size_t)(histMax + 1) * sizeof(int64_t));
+    jint rc = 1;
+    if (hst && (*env)->GetArrayLength(env, jhist) >= histMax + 1) {
+        rc = kcount_b200_khist((kcount_handle *)(intptr_t)handle, histMax, hst);
+        if (!rc) (*env)->SetLongArrayRegion(env, jhist, 0, histMax + 1, (const jlong *)hst);
+    }
+    free(hst);
     return rc;
 }
 
