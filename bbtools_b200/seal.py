@@ -183,7 +183,12 @@ _INT_FLAGS = {"k": "k", "hdist": "hdist", "hammingdistance": "hdist", "skip": "r
               "mkh": "min_kmer_hits", "restrictleft": "restrict_left", "restrictright": "restrict_right"}
 _IGNORED = {"forest", "array", "array2", "array1", "arrayh", "hybrid", "arrayhf", "hybridfast", "ways", "ordered", "ord", "showspeed",
             "ss", "prealloc", "preallocate", "initialsize", "nzo", "nonzeroonly", "statscolumns", "columns", "cols", "threads", "t"}
-_FILES = {"in", "in1", "in2", "ref", "literal", "out", "outm", "outu", "pattern", "stats", "refstats", "rpkm"}
+_FILE_ALIASES = {"in": "in1", "in1": "in1", "in2": "in2", "ref": "ref", "literal": "literal",
+                 "out": "outm1", "out1": "outm1", "outm": "outm1", "outm1": "outm1", "outmatched": "outm1", "outmatched1": "outm1",
+                 "out2": "outm2", "outm2": "outm2", "outmatched2": "outm2",
+                 "outu": "outu1", "outu1": "outu1", "outunmatched": "outu1", "outunmatched1": "outu1",
+                 "outu2": "outu2", "outunmatched2": "outu2", "stats": "stats", "scafstats": "stats"}  # jgi/Seal.java:169-188
+_FILES = set(_FILE_ALIASES)
 
 
 def parse_seal_args(args, device=0):
@@ -240,7 +245,7 @@ def parse_seal_args(args, device=0):
             if _parse_bool(b):
                 raise ValueError(f"{a}: not served by the device path (include/seal_b200.h)")
         elif a in _FILES:
-            files[a] = b
+            files[_FILE_ALIASES[a]] = b
         elif a in _IGNORED:
             pass
         else:
@@ -313,3 +318,71 @@ def format_stats(names, stats, counts, in1, in2=None, columns=5, nonzero_only=Tr
         out.append("#Name\tReads\tReadsPct\tBases\tBasesPct\tAmbigReads\n")
         out += ["%s\t%d\t%.5f%%\t%d\t%.5f%%\t%d\n" % (n, r, r * rmult, b, b * bmult, a) for n, r, b, a in rows]
     return "".join(out)
+
+
+class Seal:
+    """seal.sh from files: `Seal(["in=r1.fq", "in2=r2.fq", "ref=a.fa,b.fa", "outm=m.fq", "outu=u.fq", "stats=s.txt", ...])`.
+    FASTQ in / FASTQ out through the native feed (include/fastq_b200.h), streamed in bounded blocks: whole records, the same
+    number from both mate files; a pair goes to outm when it was assigned to at least one reference, else to outu
+    (jgi/Seal.java:2278-2286); Read.numericID runs over the whole input, as ambig=random needs it (:2403).
+    `engine` (tests): anything with SealIndexGPU's add_ref / finalize / process / scaffold_counts."""
+
+    def __init__(self, args, device=0, engine=None):
+        from .fasta import read_fasta
+        self.cfg, self.files = parse_seal_args(args, device)
+        if not self.files.get("in1"):
+            raise ValueError("in= is required")
+        self.engine = engine(self.cfg) if engine is not None else SealIndexGPU(self.cfg)
+        self.names = []
+        for path in (self.files.get("ref") or "").split(","):
+            if path:
+                names, bases, offsets = read_fasta(path)
+                self.names += names
+                self.engine.add_ref(bases, offsets)
+        for i, lit in enumerate((self.files.get("literal") or "").split(",")):
+            if lit:
+                self.names.append(f"literal_{i}")
+                b = np.frombuffer(lit.encode(), np.uint8)
+                self.engine.add_ref(b, np.array([0, len(b)], np.int64))
+        self.stored, self.entries, self.ref_kmers = self.engine.finalize()
+        self.stats = None
+
+    def process(self, block_bytes=None):
+        import os
+
+        from .fastq import FastqBatch, iter_fastq_blocks
+        f = self.files
+        paired = bool(f.get("in2"))
+        per = 2 if paired else 1
+        block = int(block_bytes or os.environ.get("BBDUK_B200_FEED_BLOCK", 256 << 20))
+        routes = [(matched, path, sel) for matched, p1, p2 in ((True, f.get("outm1"), f.get("outm2")), (False, f.get("outu1"), f.get("outu2")))
+                  if p1 for path, sel in (((p1, 1), (p2, 2)) if p2 else ((p1, 0),))]
+        sinks = {path: open(path, "wb") for _, path, _ in routes}
+        total = {n: 0 for n, _ in SealStats._fields_ if n != "reserved"}
+        first_id = 0
+        try:
+            for text1, text2 in iter_fastq_blocks(f["in1"], f.get("in2") or None, block, unit=per):
+                fb = FastqBatch(text1, text2)
+                bases, offsets = fb.arrays()
+                n = len(offsets) - 1
+                res, st = self.engine.process(bases, offsets, paired, first_id)
+                first_id += n // per
+                for k, v in st.as_dict().items():
+                    total[k] += v
+                if paired and not self.cfg.keep_pairs_together:  # assigned = both mates' sites (:2270-2272)
+                    hit = (res.n_assigned[0::2] + res.n_assigned[1::2]) > 0
+                else:
+                    hit = res.n_assigned > 0
+                flags = np.repeat(np.where(hit, 2, 0).astype(np.uint8), per)  # BBDUK_F_REMOVED marks the matched units
+                lens = np.diff(offsets).astype(np.int32)
+                for matched, path, sel in routes:
+                    fb.format(per, np.zeros(n, np.int32), lens, flags, removed=matched, mate_sel=sel, trim_removed=True).tofile(sinks[path])
+        finally:
+            for fh in sinks.values():
+                fh.close()
+        self.stats = total
+        self.counts = self.engine.scaffold_counts()
+        if f.get("stats"):
+            with open(f["stats"], "w") as fh:
+                fh.write(format_stats(self.names, total, self.counts, f["in1"], f.get("in2")))
+        return total

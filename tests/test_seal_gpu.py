@@ -180,3 +180,20 @@ def test_rejects_unsupported_flags():
     g = PS.SealIndexGPU(PS.make_cfg())
     with pytest.raises(RuntimeError, match="before finalize"):
         g.process(*pack(["ACGT"]), False)
+
+
+def test_front_end_files_equal_the_oracle_engine(tmp_path):
+    """seal.sh from files on the GPU engine against the same front end on the oracle engine: byte-identical outputs"""
+    from test_seal_host_cpu import _write_inputs
+    refs, reads = make_case(41, n_refs=8, ref_len=400, n_frag=600, k=31, read_len=140)
+    reads = [r if len(r) > 0 else "A" for r in reads]
+    ref, r1, r2 = _write_inputs(tmp_path, refs, reads)
+    outs = {}
+    for tag, engine in (("gpu", None), ("ora", S.SealOracle)):
+        args = [f"in={r1}", f"in2={r2}", f"ref={ref}", f"outm={tmp_path}/{tag}_m.fq", f"outu={tmp_path}/{tag}_u1.fq",
+                f"outu2={tmp_path}/{tag}_u2.fq", f"stats={tmp_path}/{tag}_stats.txt", "ambig=random", "cz=2"]
+        tool = PS.Seal(args, engine=engine)
+        outs[tag] = (tool.process(block_bytes=20000), (tool.stored, tool.entries, tool.ref_kmers))
+    assert outs["gpu"] == outs["ora"] and outs["gpu"][0]["reads_matched"] > 0
+    for name in ("m.fq", "u1.fq", "u2.fq", "stats.txt"):
+        assert open(f"{tmp_path}/gpu_{name}", "rb").read() == open(f"{tmp_path}/ora_{name}", "rb").read(), name

@@ -110,3 +110,50 @@ def test_stats_file_format():
     txt3 = PS.format_stats(names, st, counts, "r.fq", columns=3, nonzero_only=False)
     assert txt3.splitlines()[:4] == ["#File\tr.fq", "#Total\t40", "#Matched\t18\t45.00000%", "#Name\tReads\tReadsPct"]
     assert txt3.splitlines()[-1] == "gamma\t0\t0.00000%" and len(txt3.splitlines()) == 8
+
+
+def _write_inputs(tmp_path, refs, reads):
+    ref = tmp_path / "ref.fa"
+    ref.write_text("".join(f">ref{i} some description\n{s}\n" for i, s in enumerate(refs)))
+    r1, r2 = tmp_path / "r1.fq", tmp_path / "r2.fq"
+    with open(r1, "w") as a, open(r2, "w") as b:
+        for i in range(0, len(reads), 2):
+            for fh, s, m in ((a, reads[i], 1), (b, reads[i + 1], 2)):
+                fh.write(f"@pair{i // 2}/{m}\n{s}\n+\n{'I' * len(s)}\n")
+    return str(ref), str(r1), str(r2)
+
+
+def _records(path):
+    lines = open(path).read().split("\n")
+    return [tuple(lines[i:i + 4]) for i in range(0, len(lines) - 1, 4)]
+
+
+@pytest.mark.parametrize("flags", [[], ["kpt=f", "ambig=all", "cz=3"], ["ambig=toss", "mkh=5"]])
+def test_seal_front_end_streams_files(tmp_path, flags):
+    """FASTQ in / FASTQ out in several blocks (the oracle standing in for the GPU engine): matched / unmatched partition,
+    running numericID across blocks and the stats= file equal a one-shot run."""
+    from oracle import seal as S
+    refs, reads = make_case(31, n_refs=8, ref_len=400, n_frag=240, k=31, read_len=120)
+    reads = [r if len(r) > 0 else "A" for r in reads]  # 4-line records need a base line; an empty read stays a corner of the array tests
+    ref, r1, r2 = _write_inputs(tmp_path, refs, reads)
+    args = [f"in={r1}", f"in2={r2}", f"ref={ref}", f"outm={tmp_path}/m1.fq", f"outm2={tmp_path}/m2.fq", f"outu={tmp_path}/u.fq",
+            f"stats={tmp_path}/stats.txt"] + flags
+    tool = PS.Seal(args, engine=S.SealOracle)
+    assert tool.names[0] == "ref0 some description" and len(tool.names) == len(refs)
+    total = tool.process(block_bytes=6000)  # a few dozen pairs per block
+    cfg, _ = PS.parse_seal_args(flags)
+    o = S.SealOracle(cfg)
+    o.add_ref(*pack(refs))
+    o.finalize()
+    want, wst = o.process(*pack(reads), True, 0)
+    assert total == wst.as_dict()
+    hit = (want.n_assigned[0::2] + want.n_assigned[1::2]) > 0 if not cfg.keep_pairs_together else want.n_assigned > 0
+    assert 0 < hit.sum() < len(hit)
+    m1, m2, u = _records(f"{tmp_path}/m1.fq"), _records(f"{tmp_path}/m2.fq"), _records(f"{tmp_path}/u.fq")
+    assert [r[0] for r in m1] == [f"@pair{i}/1" for i in np.flatnonzero(hit)]
+    assert [r[0] for r in m2] == [f"@pair{i}/2" for i in np.flatnonzero(hit)]
+    assert [r[0] for r in u] == [f"@pair{i}/{m}" for i in np.flatnonzero(~hit) for m in (1, 2)]  # one file: interleaved
+    assert all(r[1] == reads[2 * i] for r, i in zip(m1, np.flatnonzero(hit)))
+    assert all(len(r[1]) == len(r[3]) for r in m1 + m2 + u)
+    names = [f"ref{i} some description" for i in range(len(refs))]
+    assert open(f"{tmp_path}/stats.txt").read() == PS.format_stats(names, wst.as_dict(), o.scaffold_counts(), r1, r2)
