@@ -191,3 +191,84 @@ def test_default_middle_mask_and_n():
     res, _ = ora.process(*pack([read]), False, 0)
     units, _, _ = cf.process([read], False, 0)
     assert units[0][2] == res.max_hits[0]
+
+
+def _two_refs(seed=5):
+    rng = np.random.default_rng(seed)
+    shared = rand_seq(rng, 40)
+    return shared, shared + "A" + rand_seq(rng, 59), shared + "C" + rand_seq(rng, 59)
+
+
+def _run(kw, refs, reads, paired, nid=0):
+    ora = S.SealOracle(S.make_cfg(mask_middle=0, **kw))
+    ora.add_ref(*pack(refs))
+    ora.finalize()
+    res, st = ora.process(*pack(reads), paired, nid)
+    return res, st.as_dict(), ora.scaffold_counts()
+
+
+def test_hand_computed_pair_rules():
+    """Counts worked out by hand from the Java (k=31, mm=f; a and b share their first 40 bases = 10 k-mers)."""
+    shared, a, b = _two_refs()
+    r1, r2 = a[40:100], a[45:80]  # 30 and 5 windows, reference 1 only
+    # kept together (jgi/Seal.java:2386-2453): one unit, readSum 2, one fragment, bases of both mates
+    res, st, (rd, bs, fr, am) = _run(dict(), [a, b], [r1, r2], True)
+    assert list(res.max_hits) == [35] and list(res.first_id) == [1] and list(res.n_assigned) == [1]
+    assert (rd[1], bs[1], fr[1], am[1]) == (2, 95, 1, 0) and st["reads_matched"] == 2 and st["bases_matched"] == 95
+    # apart (:2462-2606): the fragment goes to the mate with more hits, ties to read 1 (max1>=max2, max2>max1)
+    res, st, (rd, bs, fr, am) = _run(dict(keep_pairs_together=0), [a, b], [r1, r2], True)
+    assert list(res.max_hits) == [30, 5] and (rd[1], bs[1], fr[1]) == (2, 95, 1)
+    res, st, (rd, bs, fr, am) = _run(dict(keep_pairs_together=0), [a, b], [r2, r1], True)
+    assert list(res.max_hits) == [5, 30] and fr[1] == 1
+    res, st, (rd, bs, fr, am) = _run(dict(keep_pairs_together=0), [a, b], [r1, r1], True)
+    assert fr[1] == 1 and rd[1] == 2  # tie: read 1 only
+    # minimum hits: below mkh a kept-together pair is UNMATCHED (:2226-2227), mates taken apart are counted nowhere (:2467, :2535)
+    res, st, _ = _run(dict(min_kmer_hits=6), [a, b], [r2, r2[:34]], True)
+    assert list(res.max_hits) == [9] and st["reads_matched"] == 2
+    res, st, _ = _run(dict(min_kmer_hits=10), [a, b], [r2, r2[:34]], True)
+    assert list(res.n_assigned) == [0] and st["reads_unmatched"] == 2 and st["bases_unmatched"] == 69
+    res, st, _ = _run(dict(min_kmer_hits=5, keep_pairs_together=0), [a, b], [r2, r2[:34]], True)
+    assert list(res.n_assigned) == [1, 0] and (st["reads_matched"], st["reads_unmatched"]) == (1, 0)
+    # mkf: minhits = max(mkh, (int)(mkf * numKmers)) (:2223): 35 reference bases + 20 others = 25 windows, 5 of them hit
+    x = r2 + rand_seq(np.random.default_rng(77), 20)
+    res, st, _ = _run(dict(min_kmer_fraction=0.2), [a, b], [x], False)   # (int)(0.2f * 25) = 5 <= 5
+    assert list(res.max_hits) == [5] and list(res.n_assigned) == [1]
+    res, st, _ = _run(dict(min_kmer_fraction=0.24), [a, b], [x], False)  # (int)(0.24f * 25) = 6 > 5 (0.24f*25 = 6.0000001)
+    assert list(res.max_hits) == [5] and list(res.n_assigned) == [0] and st["reads_unmatched"] == 1
+
+
+def test_hand_computed_scan_rules():
+    shared, a, b = _two_refs()
+    # match=first (:2902): the scan stops at the first hit
+    res, _, _ = _run(dict(match_mode=S.MATCH_FIRST, ambig_mode=S.AMBIG_ALL), [a, b], [a[:70]], False)
+    assert list(res.max_hits) == [1] and list(res.n_sites) == [2]  # the first window lies in the shared part: both ids, once
+    # match=unique: every hit counts until the first k-mer with ONE id (inclusive): 10 shared windows, then a[10:41]
+    res, _, _ = _run(dict(match_mode=S.MATCH_UNIQUE, ambig_mode=S.AMBIG_ALL), [a, b], [a[:70]], False)
+    assert list(res.max_hits) == [11] and list(res.n_sites) == [1] and list(res.first_id) == [1]
+    res, _, _ = _run(dict(ambig_mode=S.AMBIG_ALL), [a, b], [a[:70]], False)
+    assert list(res.max_hits) == [40] and list(res.n_sites) == [1]     # 40 windows for id 1, 10 for id 2
+    # restrictleft=35: windows ending at 30..34 (:2877-2878)
+    res, _, _ = _run(dict(restrict_left=35), [a, b], [a[40:100]], False)
+    assert list(res.max_hits) == [5]
+    # restrictright=35 on 60 bases: the registers start at base 25, len reaches k at base 55: windows ending at 55..59
+    res, _, _ = _run(dict(restrict_right=35), [a, b], [a[40:100]], False)
+    assert list(res.max_hits) == [5]
+    # qskip=3: windows ending at 30, 33, ..., 57 (:2792)
+    res, _, _ = _run(dict(qskip=3), [a, b], [a[40:100]], False)
+    assert list(res.max_hits) == [10]
+    # rskip=3 on a reference without undefined bases: the k-mers ending at run lengths 33, 36, ..., 99 are stored (:1794)
+    ora = S.SealOracle(S.make_cfg(mask_middle=0, rskip=3))
+    ora.add_ref(*pack([a]))
+    assert ora.finalize() == (23, 23, 70)
+    # reverse strand: the reverse complement of a read hits the same k-mers (rcomp=t), and none with rcomp=f
+    comp = str.maketrans("ACGT", "TGCA")
+    rc = a[40:100].translate(comp)[::-1]
+    res, _, _ = _run(dict(), [a, b], [rc], False)
+    assert list(res.max_hits) == [30]
+    res, _, _ = _run(dict(rcomp=0), [a, b], [rc], False)
+    assert list(res.max_hits) == [0]
+    # ambig=first takes the smallest id, toss nothing, random the (numericID % sites)-th in first-seen order
+    for mode, nid, want in ((S.AMBIG_FIRST, 0, [1]), (S.AMBIG_TOSS, 0, []), (S.AMBIG_RANDOM, 5, [2]), (S.AMBIG_ALL, 0, [1, 2])):
+        res, st, _ = _run(dict(ambig_mode=mode), [a, b], [shared], False, nid)
+        assert list(res.ids[:res.n_assigned[0]]) == want and res.n_sites[0] == 2
+        assert st["reads_matched"] == (1 if want else 0)
