@@ -21,7 +21,7 @@ def test_defaults_match_seal():
             assert getattr(c, name) == getattr(d, name), name
     assert (c.k, c.rcomp, c.mask_middle, c.hdist, c.ambig_mode, c.match_mode, c.keep_pairs_together, c.min_kmer_hits) == \
         (31, 1, 1, 0, PS.AMBIG_RANDOM, PS.MATCH_ALL, 1, 1)
-    assert files == {"in": "r.fq", "ref": "a.fa,b.fa", "out": "m.fq"}
+    assert files == {"in1": "r.fq", "ref": "a.fa,b.fa", "outm1": "m.fq"}  # out= is outm= (jgi/Seal.java:177)
 
 
 @pytest.mark.parametrize("args,want", [
