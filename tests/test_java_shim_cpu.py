@@ -100,3 +100,59 @@ def test_patches_only_use_what_the_java_files_offer():
     assert used >= {"addScaffolds", "finalizeTable", "refKmersSeen", "run", "apply", "fetchScaffoldCounts"}
     for member in used:
         assert re.search(r"\b%s\b\s*[(;=,]" % member, gpu), f"patches use .{member} which the Java files do not declare"
+
+
+# ---- Seal (java/jgi/SealGPU.java, jni/SealCuda.c, java/patches/Seal.diff) ------------------------------------------------
+SEAL_JAVA = os.path.join(ROOT, "java", "jgi", "SealGPU.java")
+
+
+def test_seal_native_methods_have_jni_entry_points():
+    src = open(SEAL_JAVA).read()
+    c = open(os.path.join(ROOT, "jni", "SealCuda.c")).read()
+    natives = [(n, p) for _, n, p, nat in java_methods(src, False) if nat]
+    assert sorted(n for n, _ in natives) == ["addRefNative", "createNative", "destroyNative", "finalizeNative", "lastErrorNative",
+                                             "processNative", "scaffoldCountsNative"]
+    for name, params in natives:
+        m = re.search(r"Java_jgi_SealGPU_%s\(JNIEnv \*env, jclass cls([^)]*)\)" % name, c)
+        assert m, f"jni/SealCuda.c lacks Java_jgi_SealGPU_{name}"
+        n_c = len([x for x in m.group(1).split(",") if x.strip()])
+        assert n_c == len(params), f"{name}: Java declares {len(params)} arguments, the shim takes {n_c}"
+    assert len(re.findall(r"JNIEXPORT", c)) == len(natives)  # and the shim exports nothing the class does not declare
+    assert "GetPrimitiveArrayCritical" not in re.sub(r"/\*.*?\*/", "", c, flags=re.S)
+    # createNative's int[] carries the 17 values the shim reads, in the header's order of the integer fields
+    m = re.search(r"final int\[\] cfg=\{(.*?)\};", src, flags=re.S)
+    assert m and len([x for x in m.group(1).split(",") if x.strip()]) == 17
+
+
+def test_seal_patch_applies_to_the_reference(tmp_path):
+    ref_file = os.path.join(REF, "current", "jgi", "Seal.java")
+    if not os.path.exists(ref_file) or not shutil.which("patch"):
+        pytest.skip("reference tree (or patch) not present")
+    d = tmp_path / "current" / "jgi"
+    d.mkdir(parents=True)
+    shutil.copy(ref_file, d / "Seal.java")
+    r = subprocess.run(["patch", "-p1", "--dry-run", "-i", os.path.join(ROOT, "java", "patches", "Seal.diff")],
+                       cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_seal_patch_only_uses_what_sealgpu_offers():
+    gpu = open(SEAL_JAVA).read()
+    txt = open(os.path.join(ROOT, "java", "patches", "Seal.diff")).read()
+    added = "\n".join(ln[1:] for ln in txt.splitlines() if ln.startswith("+") and not ln.startswith("+++"))
+    used = set(re.findall(r"(?:\bgpu|\bgpuHits|\bSealGPU)\.(\w+)", added))
+    assert used >= {"createIfServed", "addRef", "finalizeTable", "refKmers", "match", "addScaffoldCounts", "close", "sites", "assigned",
+                    "removed", "readsMatched", "basesMatched", "readsUnmatched", "basesUnmatched", "Result"}
+    for member in used:
+        assert re.search(r"\b%s\b\s*[(;=,{]" % member, gpu), f"Seal.diff uses .{member} which SealGPU.java does not declare"
+    # the call of createIfServed passes as many arguments as the method declares
+    call = re.search(r"SealGPU\.createIfServed\((.*?)\);", added, flags=re.S).group(1)
+    decl = re.search(r"public static SealGPU createIfServed\((.*?)\)\{", gpu, flags=re.S).group(1)
+    assert len(call.split(",")) == len(decl.split(",")) == 22
+    # every field of Seal the patch reads exists in the reference (when it is present)
+    ref_file = os.path.join(REF, "current", "jgi", "Seal.java")
+    if os.path.exists(ref_file):
+        ref = open(ref_file).read()
+        for name in re.findall(r"[!( ]([a-zA-Z_]\w*)(?:<=0|<0|==null| &&|\))", re.search(r"gpuPreambleIsIdle\(\)\{(.*?)\}", added, flags=re.S).group(1)):
+            if name not in ("return", "null"):
+                assert re.search(r"\b%s\b" % name, ref), name
