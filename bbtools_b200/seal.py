@@ -187,7 +187,7 @@ _FILE_ALIASES = {"in": "in1", "in1": "in1", "in2": "in2", "ref": "ref", "literal
                  "out": "outm1", "out1": "outm1", "outm": "outm1", "outm1": "outm1", "outmatched": "outm1", "outmatched1": "outm1",
                  "out2": "outm2", "outm2": "outm2", "outmatched2": "outm2",
                  "outu": "outu1", "outu1": "outu1", "outunmatched": "outu1", "outunmatched1": "outu1",
-                 "outu2": "outu2", "outunmatched2": "outu2", "stats": "stats", "scafstats": "stats"}  # jgi/Seal.java:169-188
+                 "outu2": "outu2", "outunmatched2": "outu2", "stats": "stats", "scafstats": "stats", "refstats": "refstats"}  # jgi/Seal.java:169-190
 _FILES = set(_FILE_ALIASES)
 
 
@@ -334,15 +334,22 @@ class Seal:
             raise ValueError("in= is required")
         self.engine = engine(self.cfg) if engine is not None else SealIndexGPU(self.cfg)
         self.names = []
+        self.ref_files, self.scaf_per_file, self.scaf_lengths = [], [], []
         for path in (self.files.get("ref") or "").split(","):
             if path:
                 names, bases, offsets = read_fasta(path)
                 self.names += names
+                self.ref_files.append(path)
+                self.scaf_per_file.append(len(names))
+                self.scaf_lengths += [int(x) for x in np.diff(offsets)]
                 self.engine.add_ref(bases, offsets)
         for i, lit in enumerate((self.files.get("literal") or "").split(",")):
             if lit:
                 self.names.append(f"literal_{i}")
                 b = np.frombuffer(lit.encode(), np.uint8)
+                self.ref_files.append("literal")
+                self.scaf_per_file.append(1)
+                self.scaf_lengths.append(len(b))
                 self.engine.add_ref(b, np.array([0, len(b)], np.int64))
         self.stored, self.entries, self.ref_kmers = self.engine.finalize()
         self.stats = None
@@ -385,4 +392,47 @@ class Seal:
         if f.get("stats"):
             with open(f["stats"], "w") as fh:
                 fh.write(format_stats(self.names, total, self.counts, f["in1"], f.get("in2")))
+        if f.get("refstats"):
+            with open(f["refstats"], "w") as fh:
+                fh.write(format_refstats(self.ref_files, self.scaf_per_file, np.array(self.scaf_lengths, np.int64), total, self.counts,
+                                         f["in1"], f.get("in2")))
         return total
+
+
+_EXTENSIONS = ("fa", "fasta", "fna", "ffn", "frn", "fsa", "fas", "seq", "faa", "fq", "fastq", "txt", "gz", "bz2", "zip", "xz", "zst")
+
+
+def strip_to_core(path):
+    """fileIO/ReadWrite.java:1896-1922 stripToCore for the extensions a reference file carries (a subset of FileFormat.EXTENSION_LIST)."""
+    name = path.replace("\\", "/").rsplit("/", 1)[-1]
+    while True:
+        for ext in _EXTENSIONS:
+            if name.endswith("." + ext):
+                name = name[:-len(ext) - 1]
+                break
+        else:
+            return name
+
+
+def format_refstats(ref_files, scaf_per_file, scaf_lengths, stats, counts, in1, in2=None, nonzero_only=True):
+    """The `refstats=` file (jgi/Seal.java:1031-1096 writeRefStats): the per-sequence counters summed per reference FILE,
+    coverage, RPKM and FPKM (single-precision multiplier 1e9f / mapped, double-precision 1 / length).
+    scaf_per_file[i] sequences of ref_files[i] in id order; scaf_lengths[id-1] their lengths."""
+    reads, bases, frags, ambig = counts
+    mapped = int(np.sum(reads))
+    mult = np.float32(1000000000.0) / np.float32(max(1, mapped))
+    out = ["#File\t" + in1 + ("" if in2 is None else "\t" + in2) + "\n", "#Reads\t%d\n" % stats["reads_in"], "#Mapped\t%d\n" % mapped,
+           "#References\t%d\n" % len(ref_files), "#Name\tLength\tScaffolds\tBases\tCoverage\tReads\tRPKM\tFrags\tFPKM\tAmbigReads\n"]
+    sid = 1
+    for path, n in zip(ref_files, scaf_per_file):
+        r = int(np.sum(reads[sid:sid + n]))
+        b = int(np.sum(bases[sid:sid + n]))
+        f = int(np.sum(frags[sid:sid + n]))
+        a = int(np.sum(ambig[sid:sid + n]))
+        ln = int(np.sum(scaf_lengths[sid - 1:sid - 1 + n]))
+        sid += n
+        invlen = 1.0 / max(1, ln)
+        mult2 = float(mult) * invlen
+        if r > 0 or not nonzero_only:
+            out.append("%s\t%d\t%d\t%d\t%.4f\t%d\t%.4f\t%d\t%.4f\t%d\n" % (strip_to_core(path), ln, n, b, b * invlen, r, r * mult2, f, f * mult2, a))
+    return "".join(out)

@@ -157,3 +157,17 @@ def test_seal_front_end_streams_files(tmp_path, flags):
     assert all(len(r[1]) == len(r[3]) for r in m1 + m2 + u)
     names = [f"ref{i} some description" for i in range(len(refs))]
     assert open(f"{tmp_path}/stats.txt").read() == PS.format_stats(names, wst.as_dict(), o.scaffold_counts(), r1, r2)
+
+
+def test_refstats_file_format():
+    # two reference files: a.fa.gz with sequences 1-2 (1000 + 500 bases), dir/b.fasta with sequence 3 (2000 bases)
+    counts = [np.array([0, 6, 2, 4]), np.array([0, 900, 300, 600]), np.array([0, 3, 1, 2]), np.array([0, 0, 1, 0])]
+    st = dict(reads_in=20, bases_in=3000, reads_matched=12, bases_matched=1800, reads_unmatched=8, bases_unmatched=1200)
+    txt = PS.format_refstats(["a.fa.gz", "dir/b.fasta"], [2, 1], np.array([1000, 500, 2000]), st, counts, "r.fq")
+    mult = np.float32(1e9) / np.float32(12)
+    want = ("#File\tr.fq\n#Reads\t20\n#Mapped\t12\n#References\t2\n#Name\tLength\tScaffolds\tBases\tCoverage\tReads\tRPKM\tFrags\tFPKM\tAmbigReads\n"
+            "a\t1500\t2\t1200\t0.8000\t8\t%.4f\t4\t%.4f\t1\n" % (8 * float(mult) / 1500, 4 * float(mult) / 1500)
+            + "b\t2000\t1\t600\t0.3000\t4\t%.4f\t2\t%.4f\t0\n" % (4 * float(mult) / 2000, 2 * float(mult) / 2000))
+    assert txt == want
+    assert "a\t1500\t2\t1200\t0.8000\t8\t444444.4" in txt  # 8 reads / 12 mapped / 1.5 kb = 444,444 RPKM
+    assert PS.strip_to_core("/x/y/genome.v2.fna.gz") == "genome.v2" and PS.strip_to_core("plain") == "plain"
