@@ -87,3 +87,84 @@ def render(bases, offsets, paired, lo, hi, flags, maskbits=None, mask_off=None):
 
 def sha(data):
     return hashlib.sha256(data).hexdigest()
+
+
+# ---- Seal (jgi.Seal, seal.sh): name -> flags; inputs: seal_refs() / seal_reads() below, always paired ---------------------
+SEAL_CASES = {
+    "seal_default": [],
+    "seal_ambig_all_cz3": ["ambig=all", "cz=3"],
+    "seal_ambig_first_k25_mm_f": ["ambig=first", "k=25", "mm=f"],
+    "seal_ambig_toss_mkh5": ["ambig=toss", "mkh=5"],
+    "seal_kpt_f": ["kpt=f", "ambig=all"],
+    "seal_hdist1_k21": ["k=21", "hdist=1"],
+    "seal_match_unique": ["match=unique", "ambig=all"],
+    "seal_match_first_qskip3": ["match=first", "qskip=3"],
+    "seal_czf_mkf": ["czf=0.05", "mkf=0.2", "ambig=all"],
+    "seal_restrict_speed": ["restrictleft=80", "speed=4", "k=27"],
+}
+SEAL_CLASS = "jgi.Seal"  # seal.sh
+
+
+def seal_refs():
+    """8 seeded reference sequences of 600 bases: 1/2 and 5/6 are strains 2 % apart, 3 carries an N and an IUPAC code"""
+    rng = np.random.default_rng(21)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    refs = [acgt[rng.integers(0, 4, 600)].copy() for _ in range(8)]
+    for a, b in ((0, 1), (4, 5)):
+        refs[b] = refs[a].copy()
+        q = rng.integers(0, 600, 12)
+        refs[b][q] = acgt[rng.integers(0, 4, 12)]
+    refs[2][100] = ord("N")
+    refs[2][300] = ord("R")
+    return [(f"seq{i + 1}", bytes(r)) for i, r in enumerate(refs)]
+
+
+def seal_reads(n_pairs=4000):
+    """-> (bases, offsets) of n_pairs seeded 2 x 120 bp pairs: both mates from one reference (either strand), 1 % substitutions,
+    0.2 % N, every tenth pair random"""
+    rng = np.random.default_rng(22)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    refs = [np.frombuffer(s, np.uint8) for _, s in seal_refs()]
+    comp = np.zeros(256, np.uint8)
+    for a, c in zip(b"ACGTNR", b"TGCANY"):
+        comp[a] = c
+    rows = []
+    for p in range(n_pairs):
+        src = refs[int(rng.integers(0, 8))]
+        for _ in range(2):
+            if p % 10 == 9:
+                r = acgt[rng.integers(0, 4, 120)]
+            else:
+                s = int(rng.integers(0, 480))
+                r = src[s:s + 120].copy()
+                e = rng.random(120)
+                r = np.where(e < 0.01, acgt[rng.integers(0, 4, 120)], r)
+                r = np.where(e > 0.998, np.uint8(ord("N")), r)
+                if rng.integers(0, 2):
+                    r = comp[r][::-1]
+            rows.append(r.astype(np.uint8))
+    bases = np.concatenate(rows)
+    return bases, np.arange(2 * n_pairs + 1, dtype=np.int64) * 120
+
+
+def write_seal_inputs(directory):
+    ref = os.path.join(directory, "seal_refs.fa")
+    with open(ref, "wb") as f:
+        for name, s in seal_refs():
+            f.write(b">" + name.encode() + b"\n" + s + b"\n")
+    b, off = seal_reads()
+    paths = [os.path.join(directory, f"seal_{m}.fq") for m in (1, 2)]
+    files = [open(p, "wb") for p in paths]
+    for i in range(len(off) - 1):
+        files[i & 1].write(record(i, True, bytes(b[off[i]:off[i + 1]])))
+    for f in files:
+        f.close()
+    return ref, paths
+
+
+def render_seal(bases, offsets, hit):
+    """outm / outm2 / outu / outu2 as seal.sh writes them with ordered=t: whole pairs, untrimmed (jgi/Seal.java:2278-2286)"""
+    out = [[], [], [], []]
+    for i in range(len(offsets) - 1):
+        out[(0 if hit[i // 2] else 2) + (i & 1)].append(record(i, True, bytes(bases[offsets[i]:offsets[i + 1]])))
+    return [b"".join(x) for x in out]

@@ -85,3 +85,83 @@ def test_gpu_matches_reference_digests(case):
         rendered = pc.render(bases, offsets, paired, out.lo, out.hi, out.flags, out.maskbits if mask else None,
                              out.mask_off if mask else None)
         _check(case, cls, want, rendered, stored)
+
+
+# ---- Seal ----------------------------------------------------------------------------------------------------------------
+def _seal_engine_outputs(engine_cls, flags):
+    """(rendered outm/outm2/outu/outu2, stats lines without the file header, storedKmers) of one pinned Seal command line"""
+    from bbtools_b200 import seal as PS
+    cfg, _ = PS.parse_seal_args(flags)
+    eng = engine_cls(cfg)
+    names = []
+    for name, s in pc.seal_refs():
+        names.append(name)
+        b = np.frombuffer(s, np.uint8)
+        eng.add_ref(b, np.array([0, len(b)], np.int64))
+    stored = eng.finalize()[0]
+    bases, offsets = pc.seal_reads()
+    res, st = eng.process(bases, offsets, True, 0)
+    hit = (res.n_assigned[0::2] + res.n_assigned[1::2]) > 0 if not cfg.keep_pairs_together else res.n_assigned > 0
+    stats = PS.format_stats(names, st.as_dict(), eng.scaffold_counts(), "x")
+    stats = "".join(ln + "\n" for ln in stats.splitlines() if not ln.startswith("#File"))
+    return pc.render_seal(bases, offsets, hit), stats, stored
+
+
+def _check_seal(case, want, got):
+    rendered, stats, stored = got
+    assert want.get("added_kmers") in (None, stored), (case, "Added N kmers")
+    for key, data in zip(("outm", "outm2", "outu", "outu2"), rendered):
+        if want.get(key) is not None:
+            assert pc.sha(data) == want[key], (case, key)
+    if want.get("stats") is not None:
+        assert pc.sha(stats.encode()) == want["stats"], (case, "stats")
+
+
+def _seal_digests():
+    doc = _digests()
+    if "seal_cases" not in doc:
+        pytest.xfail("PARITY UNPINNED: reference_digests.json holds no Seal cases (rerun tools/pin_reference.sh)")
+    return doc["seal_cases"]
+
+
+def test_seal_pin_inputs_are_seeded_and_parse():
+    from bbtools_b200 import seal as PS
+    b1, o1 = pc.seal_reads(200)
+    b2, o2 = pc.seal_reads(200)
+    assert np.array_equal(b1, b2) and np.array_equal(o1, o2) and pc.seal_refs() == pc.seal_refs()
+    for flags in pc.SEAL_CASES.values():
+        PS.parse_seal_args(flags)
+
+
+def test_seal_pin_consumer_works_on_digests_of_the_oracle_itself(tmp_path, monkeypatch):
+    """NOT a pin: the consumer below is run against digests made from the oracle's own output, so that it is known to work
+    the day real digests arrive (a wrong byte in them must fail it: checked too)."""
+    from oracle import seal as S
+    case = "seal_ambig_all_cz3"
+    rendered, stats, stored = _seal_engine_outputs(S.SealOracle, pc.SEAL_CASES[case])
+    assert all(len(x) > 0 for x in rendered)
+    want = {"added_kmers": stored, "stats": pc.sha(stats.encode())}
+    want.update({k: pc.sha(d) for k, d in zip(("outm", "outm2", "outu", "outu2"), rendered)})
+    _check_seal(case, want, (rendered, stats, stored))
+    want["outu"] = pc.sha(rendered[2] + b"x")
+    with pytest.raises(AssertionError):
+        _check_seal(case, want, (rendered, stats, stored))
+
+
+@pytest.mark.parametrize("case", sorted(pc.SEAL_CASES))
+def test_seal_oracle_matches_reference_digests(case):
+    from oracle import seal as S
+    want = _seal_digests()[case]
+    if "error" in want:
+        pytest.skip("the reference failed on this command line: " + want["error"][-200:])
+    _check_seal(case, want, _seal_engine_outputs(S.SealOracle, pc.SEAL_CASES[case]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", sorted(pc.SEAL_CASES))
+def test_seal_gpu_matches_reference_digests(case):
+    from bbtools_b200 import seal as PS
+    want = _seal_digests()[case]
+    if "error" in want:
+        pytest.skip("the reference failed on this command line: " + want["error"][-200:])
+    _check_seal(case, want, _seal_engine_outputs(PS.SealIndexGPU, pc.SEAL_CASES[case]))

@@ -9,7 +9,8 @@ For every command line of tests/pin_common.py:CASES and both main classes (jgi.B
 bbduk.sh) it runs
     java -ea -Xmx2g -cp <reference>/current <class> in=.. [in2=..] out=.. [out2=..] outm=.. [outm2=..] stats=.. ref=adapters.fa
          ordered=t t=<threads> overwrite=t <flags>
-on the seeded FASTQ files and stores, under tests/golden/reference_digests.json, the SHA-256 of every output file, the
+on the seeded FASTQ files (and, for tests/pin_common.py:SEAL_CASES, `java jgi.Seal` = seal.sh on seeded pairs against a seeded
+multi-sequence reference with outm / outu / stats) and stores, under tests/golden/reference_digests.json, the SHA-256 of every output file, the
 `Added N kmers` line (jgi/BBDuk.java:1973), the reads/bases counters the tool prints and the java version. Also runs
 resources/sample1.fq.gz + sample2.fq.gz through the cfg-2 command line (digests only; the tests regenerate nothing from
 those files, they are a check for whoever has the reference tree)."""
@@ -56,6 +57,28 @@ def run_case(java, cp, cls, ins, flags, workdir, threads, ref_fa):
     return res
 
 
+def run_seal_case(java, cp, ins, flags, workdir, threads, ref_fa):
+    """java jgi.Seal (seal.sh) on the seeded pairs: digests of outm / outm2 / outu / outu2, the stats= lines, `Added N kmers`"""
+    outs = {"outm": "m1.fq", "outm2": "m2.fq", "outu": "u1.fq", "outu2": "u2.fq"}
+    cmd = [java, "-ea", "-Xmx2g", "-cp", cp, pc.SEAL_CLASS, f"in={ins[0]}", f"in2={ins[1]}"]
+    for key, name in outs.items():
+        cmd.append(f"{key}={os.path.join(workdir, name)}")
+    stats = os.path.join(workdir, "stats.txt")
+    cmd += [f"stats={stats}", f"ref={ref_fa}", "ordered=t", f"t={threads}", "overwrite=t"] + flags
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        return {"error": r.stderr[-2000:]}
+    res = {"command": " ".join(cmd[4:])}
+    for key, name in outs.items():
+        path = os.path.join(workdir, name)
+        res[key] = pc.sha(open(path, "rb").read()) if os.path.exists(path) else None
+    m = re.search(r"Added (\d+) kmers", r.stderr)
+    res["added_kmers"] = int(m.group(1)) if m else None
+    if os.path.exists(stats):
+        res["stats"] = pc.sha("".join(ln for ln in open(stats) if not ln.startswith("#File")).encode())
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reference", default="/root/reference")
@@ -87,6 +110,13 @@ def main():
                 os.makedirs(wd)
                 doc["samples"][cls] = run_case(a.java, cp, cls, [s1, s2], pc.CASES["cfg2_ktrim_r_k23_mink11_hdist1_tpe"][1], wd,
                                                a.threads, os.path.join(a.reference, "resources", "adapters.fa"))
+        doc["seal_cases"] = {}
+        seal_ref, seal_ins = pc.write_seal_inputs(tmp)
+        for name, flags in pc.SEAL_CASES.items():
+            wd = os.path.join(tmp, name)
+            os.makedirs(wd)
+            doc["seal_cases"][name] = run_seal_case(a.java, cp, seal_ins, flags, wd, a.threads, seal_ref)
+            print(name, doc["seal_cases"][name].get("added_kmers"), file=sys.stderr)
     with open(pc.DIGESTS, "w") as f:
         json.dump(doc, f, indent=1, sort_keys=True)
     print("wrote", pc.DIGESTS)
