@@ -214,7 +214,7 @@ def run_reference_seal(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
         "config": {"workload": wl["desc"], "pairs_per_step": n_pairs,
-                   "note": "CPU restatement (C port, sorted array + binary search as the map) of jgi.Seal's matching block; no JVM in the image"},
+                   "note": "CPU restatement (C port, sorted entries behind a hash index as the map, one thread) of jgi.Seal's matching block; no JVM in the image"},
         "cpu_baseline": {"value": value, "unit": "reads/s", "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))

@@ -23,7 +23,8 @@
  *   jgi/Seal.java:2386-2453   assignTogether; :2462-2606 assignIndependently
  *   stream/Read.java:1665-1683 numValidKmers / numValidPairKmers; jgi/Seal.java:1198-1207 numKmers
  *   dna/AminoAcid.java:269-285 baseToNumber(0) / baseToComplementNumber(0)
- * The hash-table layout is not part of the semantics: the table here is a sorted array of (key, id).
+ * The hash-table layout is not part of the semantics: the table here is a sorted array of (key, id) entries behind an
+ * open-addressed index of the distinct keys.
  */
 #include <math.h>
 #include <stdint.h>
@@ -50,6 +51,8 @@ typedef struct sl_oracle {
     /* table */
     sl_pair *pairs;
     int64_t n_pairs, cap_pairs;
+    int64_t *index;      /* open-addressed hash over the distinct keys: first entry of the key in pairs[], -1 = empty */
+    uint64_t index_mask;
     int64_t stored, ref_kmers;
     /* per-scaffold counters, index = id */
     int64_t *s_reads, *s_bases, *s_frags, *s_ambig;
@@ -86,6 +89,15 @@ static uint64_t sl_rcomp(uint64_t kmer, int k) {
         kmer >>= 2;
     }
     return r;
+}
+
+static uint64_t sl_mix(uint64_t x) {
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdull;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ull;
+    x ^= x >> 33;
+    return x;
 }
 
 static uint64_t sl_to_value(const sl_oracle *o, uint64_t kmer, uint64_t rkmer, uint64_t lengthMask) {
@@ -129,6 +141,7 @@ void sl_ora_destroy(void *h) {
     free(o->ref);
     free(o->seq_off);
     free(o->pairs);
+    free(o->index);
     free(o->s_reads);
     free(o->s_bases);
     free(o->s_frags);
@@ -236,6 +249,19 @@ int sl_ora_finalize(void *h, int64_t *v) {
     }
     o->n_pairs = w;
     o->stored = stored;
+    /* index: the map is a hash table in the reference too (kmer/HashArray.java); layout is not part of the semantics */
+    free(o->index);
+    uint64_t slots = 1024;
+    while (slots < (uint64_t)stored * 2 + 2) slots <<= 1;
+    o->index_mask = slots - 1;
+    o->index = (int64_t *)malloc(slots * sizeof(int64_t));
+    for (uint64_t i = 0; i < slots; i++) o->index[i] = -1;
+    for (int64_t i = 0; i < o->n_pairs; i++) {
+        if (i > 0 && o->pairs[i].key == o->pairs[i - 1].key) continue;
+        uint64_t h = sl_mix(o->pairs[i].key) & o->index_mask;
+        while (o->index[h] >= 0) h = (h + 1) & o->index_mask;
+        o->index[h] = i;
+    }
     const size_t alen = (size_t)o->n_seqs + 1;
     free(o->s_reads);
     free(o->s_bases);
@@ -266,16 +292,19 @@ int64_t sl_ora_table(void *h, uint64_t *keys, int32_t *ids, int64_t cap) {
 
 /* set.getValues(key): index of the first entry with this key and the number of entries, 0 if absent */
 static int64_t sl_lookup(const sl_oracle *o, uint64_t key, int *n) {
-    int64_t lo = 0, hi = o->n_pairs;
-    while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (o->pairs[mid].key < key) lo = mid + 1;
-        else hi = mid;
+    uint64_t h = sl_mix(key) & o->index_mask;
+    *n = 0;
+    for (;;) {
+        const int64_t at = o->index[h];
+        if (at < 0) return 0;
+        if (o->pairs[at].key == key) {
+            int c = 1;
+            while (at + c < o->n_pairs && o->pairs[at + c].key == key) c++;
+            *n = c;
+            return at;
+        }
+        h = (h + 1) & o->index_mask;
     }
-    int c = 0;
-    while (lo + c < o->n_pairs && o->pairs[lo + c].key == key) c++;
-    *n = c;
-    return lo;
 }
 
 typedef struct {
