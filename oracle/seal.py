@@ -29,6 +29,8 @@ def lib():
         L.sl_ora_table.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
         L.sl_ora_process.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.POINTER(SealOut),
                                      C.POINTER(SealStats)]
+        L.sl_ora_process_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.POINTER(SealOut),
+                                        C.POINTER(SealStats), C.c_int32]
         L.sl_ora_scaffold_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
         _LIB = L
     return _LIB
@@ -68,15 +70,19 @@ class SealOracle:
         self.L.sl_ora_table(self.h, keys.ctypes.data, ids.ctypes.data, n)
         return keys, ids
 
-    def process(self, bases, offsets, paired, first_numeric_id=0):
+    def process(self, bases, offsets, paired, first_numeric_id=0, threads=1):
         bases = np.ascontiguousarray(bases, np.uint8)
         offsets = np.ascontiguousarray(offsets, np.int64)
         n = len(offsets) - 1
         res = SealResult(n_units(self.cfg, n, paired), self.cfg.ids_stride)
         st = SealStats()
         o = res.struct()
-        rc = self.L.sl_ora_process(self.h, bases.ctypes.data, offsets.ctypes.data, n, 1 if paired else 0, first_numeric_id,
-                                   C.byref(o), C.byref(st))
+        if threads > 1:
+            rc = self.L.sl_ora_process_mt(self.h, bases.ctypes.data, offsets.ctypes.data, n, 1 if paired else 0, first_numeric_id,
+                                          C.byref(o), C.byref(st), threads)
+        else:
+            rc = self.L.sl_ora_process(self.h, bases.ctypes.data, offsets.ctypes.data, n, 1 if paired else 0, first_numeric_id,
+                                       C.byref(o), C.byref(st))
         if rc:
             raise RuntimeError("seal oracle: process before finalize")
         return res, st

@@ -27,6 +27,7 @@
  * open-addressed index of the distinct keys.
  */
 #include <math.h>
+#include <pthread.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -434,17 +435,17 @@ static void sl_emit(const sl_oracle *o, const seal_out *out, int64_t u, const sl
     }
 }
 
-int sl_ora_process(void *h, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, int32_t paired,
-                   int64_t first_numeric_id, const seal_out *out, seal_stats *st) {
-    sl_oracle *o = (sl_oracle *)h;
-    if (!o->countArray) return 1;
+/* fragments [f0, f1) of the batch: the matching block of ProcessThread.run with the thread's own count array and counters
+ * (scaffoldReadCountsT ..., jgi/Seal.java:1995-2007) */
+static void sl_process_range(sl_oracle *o, const uint8_t *bases, const int64_t *offsets, int32_t paired, int64_t first_numeric_id,
+                             const seal_out *out, int64_t f0, int64_t f1, int32_t *countArray, int64_t *sr, int64_t *sb, int64_t *sf,
+                             int64_t *sa, seal_stats *st) {
     const int k = o->k;
     sl_list idList1 = {0}, idList2 = {0}, countList1 = {0}, countList2 = {0}, finalList1 = {0}, finalList2 = {0};
     seal_stats s;
     memset(&s, 0, sizeof s);
-    const int64_t n_frag = paired ? n_reads / 2 : n_reads;
     const int kpt = o->c.keep_pairs_together != 0;
-    for (int64_t f = 0; f < n_frag; f++) {
+    for (int64_t f = f0; f < f1; f++) {
         const int64_t i1 = paired ? 2 * f : f;
         const uint8_t *b1 = bases + offsets[i1];
         const int64_t L1 = offsets[i1 + 1] - offsets[i1];
@@ -456,9 +457,9 @@ int sl_ora_process(void *h, const uint8_t *bases, const int64_t *offsets, int64_
         s.bases_in += L1 + L2;
         if (kpt) {
             idList1.size = 0;
-            sl_find_best_match(o, b1, L1, 1, o->countArray, &idList1);
-            sl_find_best_match(o, b2, L2, has2, o->countArray, &idList1);
-            const int max = sl_condense(o->countArray, &idList1, &countList1);
+            sl_find_best_match(o, b1, L1, 1, countArray, &idList1);
+            sl_find_best_match(o, b2, L2, has2, countArray, &idList1);
+            const int max = sl_condense(countArray, &idList1, &countList1);
             int cz = o->c.clearzone;
             if (o->c.clearzone_fraction > 0) {
                 const int nv = sl_num_valid_kmers(b1, L1, k) + (has2 ? sl_num_valid_kmers(b2, L2, k) : 0);
@@ -478,10 +479,10 @@ int sl_ora_process(void *h, const uint8_t *bases, const int64_t *offsets, int64_
                 sl_range(o, &finalList1, numericID, &start, &stop);
                 for (int j = start; j < stop; j++) {
                     const int id = finalList1.a[j];
-                    o->s_reads[id] += readSum;
-                    o->s_bases[id] += lenSum;
-                    o->s_frags[id]++;
-                    if (sites > 1) o->s_ambig[id] += readSum;
+                    sr[id] += readSum;
+                    sb[id] += lenSum;
+                    sf[id]++;
+                    if (sites > 1) sa[id] += readSum;
                 }
                 if (start < stop) {
                     s.reads_matched += readSum;
@@ -497,8 +498,8 @@ int sl_ora_process(void *h, const uint8_t *bases, const int64_t *offsets, int64_
             sl_emit(o, out, paired ? f : i1, &finalList1, start, stop, sites, max);
         } else {
             idList1.size = 0;
-            sl_find_best_match(o, b1, L1, 1, o->countArray, &idList1);
-            const int max1 = sl_condense(o->countArray, &idList1, &countList1);
+            sl_find_best_match(o, b1, L1, 1, countArray, &idList1);
+            const int max1 = sl_condense(countArray, &idList1, &countList1);
             {
                 int cz = o->c.clearzone;
                 if (o->c.clearzone_fraction > 0) {
@@ -511,8 +512,8 @@ int sl_ora_process(void *h, const uint8_t *bases, const int64_t *offsets, int64_
             finalList2.size = 0;
             if (has2) {
                 idList2.size = 0;
-                sl_find_best_match(o, b2, L2, 1, o->countArray, &idList2);
-                max2 = sl_condense(o->countArray, &idList2, &countList2);
+                sl_find_best_match(o, b2, L2, 1, countArray, &idList2);
+                max2 = sl_condense(countArray, &idList2, &countList2);
                 int cz = o->c.clearzone;
                 if (o->c.clearzone_fraction > 0) {
                     const int c2 = (int)ceil((double)(float)(o->c.clearzone_fraction * (float)sl_num_valid_kmers(b2, L2, k)));
@@ -534,10 +535,10 @@ int sl_ora_process(void *h, const uint8_t *bases, const int64_t *offsets, int64_
                     const int frag = m ? (max2 > max1) : (max1 >= max2);
                     for (int j = start; j < stop; j++) {
                         const int id = fin->a[j];
-                        o->s_reads[id]++;
-                        o->s_bases[id] += L;
-                        if (frag) o->s_frags[id]++;
-                        if (sites > 1) o->s_ambig[id]++;
+                        sr[id]++;
+                        sb[id] += L;
+                        if (frag) sf[id]++;
+                        if (sites > 1) sa[id]++;
                     }
                     if (start < stop) {
                         s.reads_matched++;
@@ -557,6 +558,91 @@ int sl_ora_process(void *h, const uint8_t *bases, const int64_t *offsets, int64_
     free(countList2.a);
     free(finalList1.a);
     free(finalList2.a);
+    *st = s;
+}
+
+
+int sl_ora_process(void *h, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, int32_t paired,
+                   int64_t first_numeric_id, const seal_out *out, seal_stats *st) {
+    sl_oracle *o = (sl_oracle *)h;
+    if (!o->countArray) return 1;
+    seal_stats s;
+    sl_process_range(o, bases, offsets, paired, first_numeric_id, out, 0, paired ? n_reads / 2 : n_reads, o->countArray, o->s_reads,
+                     o->s_bases, o->s_frags, o->s_ambig, &s);
+    if (st) *st = s;
+    return 0;
+}
+
+/* the same with `threads` ProcessThreads over contiguous slices of the batch; their counters are summed as the reference sums
+ * its threads' (jgi/Seal.java:1640-1672). Results do not depend on the number of threads. */
+typedef struct {
+    sl_oracle *o;
+    const uint8_t *bases;
+    const int64_t *offsets;
+    int32_t paired;
+    int64_t first_numeric_id;
+    const seal_out *out;
+    int64_t f0, f1;
+    int32_t *countArray;
+    int64_t *cnt; /* 4 * alen */
+    seal_stats st;
+} sl_job;
+
+static void *sl_worker(void *arg) {
+    sl_job *j = (sl_job *)arg;
+    const size_t alen = (size_t)j->o->n_seqs + 1;
+    sl_process_range(j->o, j->bases, j->offsets, j->paired, j->first_numeric_id, j->out, j->f0, j->f1, j->countArray, j->cnt,
+                     j->cnt + alen, j->cnt + 2 * alen, j->cnt + 3 * alen, &j->st);
+    return NULL;
+}
+
+int sl_ora_process_mt(void *h, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, int32_t paired,
+                      int64_t first_numeric_id, const seal_out *out, seal_stats *st, int32_t threads) {
+    sl_oracle *o = (sl_oracle *)h;
+    if (!o->countArray) return 1;
+    const int64_t n_frag = paired ? n_reads / 2 : n_reads;
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    if ((int64_t)threads > n_frag) threads = n_frag > 0 ? (int32_t)n_frag : 1;
+    const size_t alen = (size_t)o->n_seqs + 1;
+    sl_job *jobs = (sl_job *)calloc((size_t)threads, sizeof(sl_job));
+    pthread_t *tid = (pthread_t *)calloc((size_t)threads, sizeof(pthread_t));
+    for (int t = 0; t < threads; t++) {
+        sl_job *j = &jobs[t];
+        j->o = o;
+        j->bases = bases;
+        j->offsets = offsets;
+        j->paired = paired;
+        j->first_numeric_id = first_numeric_id;
+        j->out = out;
+        j->f0 = n_frag * t / threads;
+        j->f1 = n_frag * (t + 1) / threads;
+        j->countArray = (int32_t *)calloc(alen, 4);
+        j->cnt = (int64_t *)calloc(4 * alen, 8);
+        pthread_create(&tid[t], NULL, sl_worker, j);
+    }
+    seal_stats s;
+    memset(&s, 0, sizeof s);
+    for (int t = 0; t < threads; t++) {
+        pthread_join(tid[t], NULL);
+        sl_job *j = &jobs[t];
+        s.reads_in += j->st.reads_in;
+        s.bases_in += j->st.bases_in;
+        s.reads_matched += j->st.reads_matched;
+        s.bases_matched += j->st.bases_matched;
+        s.reads_unmatched += j->st.reads_unmatched;
+        s.bases_unmatched += j->st.bases_unmatched;
+        for (size_t i = 0; i < alen; i++) {
+            o->s_reads[i] += j->cnt[i];
+            o->s_bases[i] += j->cnt[alen + i];
+            o->s_frags[i] += j->cnt[2 * alen + i];
+            o->s_ambig[i] += j->cnt[3 * alen + i];
+        }
+        free(j->countArray);
+        free(j->cnt);
+    }
+    free(jobs);
+    free(tid);
     if (st) *st = s;
     return 0;
 }

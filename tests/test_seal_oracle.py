@@ -272,3 +272,21 @@ def test_hand_computed_scan_rules():
         res, st, _ = _run(dict(ambig_mode=mode), [a, b], [shared], False, nid)
         assert list(res.ids[:res.n_assigned[0]]) == want and res.n_sites[0] == 2
         assert st["reads_matched"] == (1 if want else 0)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(keep_pairs_together=0, ambig_mode=S.AMBIG_ALL, clearzone=4), dict(ambig_mode=S.AMBIG_FIRST, k=21, hdist=1)])
+def test_threads_do_not_change_results(kw):
+    """sl_ora_process_mt (the reference arm of bench.py --workload seal): contiguous slices, counters summed"""
+    cfg = S.make_cfg(**kw)
+    refs, reads = make_case(55, n_refs=8, ref_len=400, n_frag=500, k=cfg.k, read_len=120)
+    outs = []
+    for threads in (1, 2, 7):
+        ora = S.SealOracle(cfg)
+        ora.add_ref(*pack(refs))
+        ora.finalize()
+        res, st = ora.process(*pack(reads), True, 99, threads=threads)
+        outs.append(([x.copy() for x in res.fields().values()], st.as_dict(), [c.copy() for c in ora.scaffold_counts()]))
+    for other in outs[1:]:
+        assert all(np.array_equal(a, b) for a, b in zip(outs[0][0], other[0]))
+        assert outs[0][1] == other[1]
+        assert all(np.array_equal(a, b) for a, b in zip(outs[0][2], other[2]))
