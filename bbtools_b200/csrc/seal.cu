@@ -42,9 +42,9 @@ struct SealParams {
     uint64_t mask, middleMask, kmask;
 };
 
-// Hash array of Seal's table: buckets of four slots, keys and values in ONE 64-byte line (a probe of this table is a random
-// DRAM access, and DRAM moves 64-byte bursts: with the BBDuk layout -- keys and values in separate arrays -- every hit
-// cost two bursts). Linear probing over buckets; slots fill in order and nothing is deleted, so an empty last slot ends
+// Hash array of Seal's table: buckets of four slots, keys and values side by side in 64 bytes (a probe of this table is a random
+// DRAM access, and an L2 miss fetches a whole 128-byte line, profiles/r01_e_random_access_microbench.txt: with the BBDuk layout
+// -- keys and values in separate arrays -- every hit cost two lines). Linear probing over buckets; slots fill in order and nothing is deleted, so an empty last slot ends
 // the search (same rule as bb_table_get).
 struct __align__(64) SlBucket {
     uint64_t keys[4];
