@@ -97,7 +97,9 @@ SEAL_API int64_t seal_b200_n_units(const seal_handle *h, int64_t n_reads, int32_
 
 /* Replaces: ProcessThread.run's matching block for a batch (jgi/Seal.java:2186-2276). HOST buffers: ASCII
  * bases + offsets[n_reads+1] (paired: r1,r2 interleaved); first_numeric_id = Read.numericID of the batch's
- * first pair / read (ambig=random picks finalList[numericID % sites], :2403). Results to host arrays. */
+ * first pair / read (ambig=random picks finalList[numericID % sites], :2403). Results to host arrays.
+ * A unit may hit at most 1152 distinct reference ids (128 in shared memory + 1024 in the warp's scratch); beyond that the call
+ * fails with an error instead of truncating the list. One call at a time per handle (the scratch belongs to the handle). */
 SEAL_API int seal_b200_process(seal_handle *h, const uint8_t *bases, const int64_t *offsets, int64_t n_reads,
                                int32_t paired, int64_t first_numeric_id, const seal_out *out, seal_stats *stats);
 
