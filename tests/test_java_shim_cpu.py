@@ -156,3 +156,15 @@ def test_seal_patch_only_uses_what_sealgpu_offers():
         for name in re.findall(r"[!( ]([a-zA-Z_]\w*)(?:<=0|<0|==null| &&|\))", re.search(r"gpuPreambleIsIdle\(\)\{(.*?)\}", added, flags=re.S).group(1)):
             if name not in ("return", "null"):
                 assert re.search(r"\b%s\b" % name, ref), name
+
+
+def test_kcount_native_methods_have_jni_entry_points():
+    src = open(os.path.join(ROOT, "java", "kmer", "KmerTableSetGPU.java")).read()
+    c = open(os.path.join(ROOT, "jni", "KCountCuda.c")).read()
+    natives = [(n, p) for _, n, p, nat in java_methods(src, False) if nat]
+    assert len(natives) == len(re.findall(r"JNIEXPORT", c)) == 6
+    for name, params in natives:
+        m = re.search(r"Java_kmer_KmerTableSetGPU_%s\(JNIEnv \*env, jclass cls([^)]*)\)" % name, c)
+        assert m, f"jni/KCountCuda.c lacks Java_kmer_KmerTableSetGPU_{name}"
+        assert len([x for x in m.group(1).split(",") if x.strip()]) == len(params), name
+    assert "GetPrimitiveArrayCritical" not in re.sub(r"/\*.*?\*/", "", c, flags=re.S)
