@@ -290,3 +290,24 @@ def test_threads_do_not_change_results(kw):
         assert all(np.array_equal(a, b) for a, b in zip(outs[0][0], other[0]))
         assert outs[0][1] == other[1]
         assert all(np.array_equal(a, b) for a, b in zip(outs[0][2], other[2]))
+
+
+def test_random_flag_combinations_oracle_vs_closed_form():
+    """the flag generator of tools/stress_seal_gpu.py (GPU vs oracle) turned on the oracle itself: C restatement vs the closed form"""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from stress_seal_gpu import random_flags
+    rng = np.random.default_rng(2024)
+    for c in range(30):
+        kw = random_flags(rng)
+        cfg = S.make_cfg(**kw)
+        small = cfg.hdist == 2
+        paired = bool(rng.integers(0, 2))
+        refs, reads = make_case(int(rng.integers(1, 1 << 30)), n_refs=3 if small else int(rng.integers(2, 7)), ref_len=120 if small else 250,
+                                n_frag=20, read_len=int(rng.integers(40, 200)), paired=paired, k=cfg.k,
+                                n_rate=float(rng.choice([0.0, 0.01, 0.05])))
+        try:
+            compare(cfg, refs, reads, paired=paired, first_id=int(rng.integers(0, 1 << 40)))
+        except AssertionError as e:
+            raise AssertionError(f"case {c}: flags {kw}, paired {paired}: {e}")
