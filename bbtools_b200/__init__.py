@@ -2,7 +2,8 @@
 
 The package holds only what the path needs: csrc/ (CUDA kernels + the C ABI of
 include/bbduk_b200.h), the ctypes binding, and the host-side mirror of jgi.BBDuk's
-read-in/read-out surface. There is no CPU fallback: importing the binding fails loudly when
+read-in/read-out surface (bbduk.py), of KmerCountExact's counting table (kcount.py) and of Seal's
+loader + matching block (seal.py). There is no CPU fallback: importing the binding fails loudly when
 libbbduk_b200.so has not been built.
 """
 from ._abi import (BBDukCfg, BBDukOut, BBDukStats, BBDukTboCfg, F_DISCARDED, F_KTRIMMED, F_REMOVED, F_SPLIT, F_TBO, F_TPE, GEN_JGI, GEN_S,
